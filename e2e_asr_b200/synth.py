@@ -1,0 +1,178 @@
+"""Deterministic synthetic batches and weights.
+
+The reference ships no data, vocabularies or checkpoints, so every parity and
+benchmark run uses the generator below: numpy PCG64 streams keyed by seed,
+weights drawn with the reference's initialisers (encoder kernels U(+-0.075),
+reference encoder.py:73-74; embedding U(+-1), decoder.py:97-99; every other
+kernel Glorot-uniform, the TF default when no initialiser is in scope; biases 0)
+and keyed by the TF variable names of SURVEY.md Appendix B, which are the
+reference's weight interchange format (beam_search.py:56-98).
+
+Pure numpy: used by the product path (bench, smoke) and by the tests/oracle.
+"""
+import math
+
+import numpy as np
+
+from .base_params import Bunch
+from .data_utils import EOS_ID, GO_ID, PAD_ID  # noqa: F401
+
+DATA_SEED = 1234
+WEIGHT_SEED = 4321
+
+# name -> (B, T, F, H, L, V, U); aux CTC heads as in SURVEY.md section 8d.
+CONFIGS = {
+    # tiny: unit-test size, oracle float64 in milliseconds
+    "tiny": dict(B=3, T=22, F=8, H=8, L=4, V=17, U=6, E=8, A=8, Hd=8, Hl=8,
+                 ctc={"phone_ctc": (3, 5), "state": (2, 9)}),
+    "tiny_b": dict(B=5, T=37, F=12, H=16, L=4, V=23, U=9, E=12, A=8, Hd=16, Hl=8,
+                   ctc={"phone_ctc": (3, 6)}),
+    # cfg-1: base_params defaults, CPU parity
+    "cfg1": dict(B=4, T=200, F=40, H=256, L=4, V=1000, U=25, E=256, A=128,
+                 Hd=256, Hl=256, ctc={"phone_ctc": (3, 48)}),
+    # cfg-2: Switchboard-300h-shaped training batch (the bench workload)
+    "cfg2": dict(B=64, T=700, F=120, H=256, L=4, V=1000, U=120, E=256, A=128,
+                 Hd=256, Hl=256, ctc={"phone_ctc": (3, 48), "state": (2, 1024)}),
+    # cfg-4: long-utterance stress
+    "cfg4": dict(B=32, T=2000, F=120, H=256, L=4, V=1000, U=120, E=256, A=128,
+                 Hd=256, Hl=256, ctc={"phone_ctc": (3, 48), "state": (2, 1024)}),
+    # cfg-5: wide encoder
+    "cfg5": dict(B=256, T=700, F=120, H=512, L=5, V=1000, U=120, E=256, A=128,
+                 Hd=256, Hl=256, ctc={"phone_ctc": (3, 48), "state": (2, 1024)}),
+}
+
+
+def get_config(name, **overrides):
+    cfg = Bunch(CONFIGS[name])
+    cfg.name = name
+    cfg.ctc = dict(cfg.ctc)
+    for k, v in overrides.items():
+        cfg[k] = v
+    return cfg
+
+
+def layer_input_sizes(cfg, skip_step=2, max_scaling_down=8):
+    """Input width of every encoder layer (reference encoder.py:154-178)."""
+    sizes, res = [], 1
+    width = cfg.F
+    for i in range(cfg.L):
+        sizes.append(width)
+        if skip_step > 1 and i != cfg.L - 1 and res < max_scaling_down:
+            width = 2 * cfg.H * skip_step
+            res *= skip_step
+        else:
+            width = 2 * cfg.H
+    return sizes
+
+
+def _glorot(rng, shape, fan_in=None, fan_out=None):
+    if fan_in is None:
+        if len(shape) == 1:
+            fan_in = fan_out = shape[0]
+        else:
+            recept = int(np.prod(shape[:-2])) if len(shape) > 2 else 1
+            fan_in, fan_out = shape[-2] * recept, shape[-1] * recept
+    lim = math.sqrt(6.0 / (fan_in + fan_out))
+    return rng.uniform(-lim, lim, size=shape).astype(np.float32)
+
+
+def make_weights(cfg, seed=WEIGHT_SEED, tasks=("char",), bias_noise=0.0):
+    """Weights keyed by TF variable name.
+
+    `bias_noise` > 0 perturbs the (reference: zero-initialised) biases so parity
+    tests exercise the bias paths with non-trivial values.
+    """
+    rng = np.random.Generator(np.random.PCG64(seed))
+    w = {}
+    H = cfg.H
+
+    def bias(n):
+        if bias_noise > 0:
+            return rng.uniform(-bias_noise, bias_noise, size=(n,)).astype(np.float32)
+        return np.zeros((n,), np.float32)
+
+    for l, I in enumerate(layer_input_sizes(cfg), start=1):
+        for d in ("fw", "bw"):
+            base = "model/encoder/RNNLayer%d/bidirectional_rnn/%s/basic_lstm_cell/" % (l, d)
+            w[base + "kernel"] = rng.uniform(-0.075, 0.075, size=(I + H, 4 * H)).astype(np.float32)
+            w[base + "bias"] = bias(4 * H)
+    D = 2 * H
+    for task in tasks:
+        V = cfg.V if task == "char" else cfg.get("V_" + task, cfg.V)
+        p = "model/rnn_decoder_%s/" % task
+        w[p + "decoder/embedding"] = rng.uniform(-1.0, 1.0, size=(V, cfg.E)).astype(np.float32)
+        w[p + "AttnW"] = _glorot(rng, (1, 1, D, cfg.A))
+        w[p + "AttnV"] = _glorot(rng, (cfg.A,))
+        w[p + "rnn/basic_lstm_cell/kernel"] = _glorot(rng, (cfg.E + cfg.Hl, 4 * cfg.Hl))
+        w[p + "rnn/basic_lstm_cell/bias"] = bias(4 * cfg.Hl)
+        w[p + "rnn/basic_lstm_cell_1/kernel"] = _glorot(rng, (cfg.E + cfg.Hd, 4 * cfg.Hd))
+        w[p + "rnn/basic_lstm_cell_1/bias"] = bias(4 * cfg.Hd)
+        w[p + "rnn/Attention/kernel"] = _glorot(rng, (cfg.Hd, cfg.A))
+        w[p + "rnn/Attention/bias"] = bias(cfg.A)
+        w[p + "rnn/AttnProjection/kernel"] = _glorot(rng, (cfg.Hd + D, cfg.Hd))
+        w[p + "rnn/AttnProjection/bias"] = bias(cfg.Hd)
+        w[p + "rnn/OutputProjection/kernel"] = _glorot(rng, (cfg.Hd, V))
+        w[p + "rnn/OutputProjection/bias"] = bias(V)
+        w[p + "rnn/InputProjection/kernel"] = _glorot(rng, (cfg.Hd + D, cfg.E))
+        w[p + "rnn/InputProjection/bias"] = bias(cfg.E)
+        if cfg.Hl != cfg.Hd:
+            w[p + "rnn/SimpleProjection/kernel"] = _glorot(rng, (cfg.Hl, cfg.Hd))
+            w[p + "rnn/SimpleProjection/bias"] = bias(cfg.Hd)
+    for task, (depth, vocab) in cfg.ctc.items():
+        p = "model/ctc_%s/" % task
+        w[p + "kernel"] = _glorot(rng, (D, vocab + 1))
+        w[p + "bias"] = bias(vocab + 1)
+    return w
+
+
+def pyramid_lens(lens, n):
+    """Sequence lengths after n pyramid reductions (reference encoder.py:117-118)."""
+    lens = np.asarray(lens, np.int64)
+    for _ in range(n):
+        lens = (lens + 1) // 2
+    return lens
+
+
+def depth_reductions(cfg, depth, skip_step=2, max_scaling_down=8):
+    """Number of x2 reductions applied before the output of layer `depth`."""
+    n, res = 0, 1
+    for i in range(depth - 1):
+        if skip_step > 1 and res < max_scaling_down:
+            n += 1
+            res *= skip_step
+    return n
+
+
+def make_batch(cfg, seed=DATA_SEED, tasks=("char",)):
+    """One padded batch with the layout of reference speech_dataset.py:43-45."""
+    rng = np.random.Generator(np.random.PCG64(seed))
+    B, T, F, U = cfg.B, cfg.T, cfg.F, cfg.U
+    lens = rng.integers(max(1, int(math.ceil(0.6 * T))), T + 1, size=B).astype(np.int64)
+    lens[rng.integers(0, B)] = T
+    logmel = rng.standard_normal(size=(B, T, F)).astype(np.float32)
+    for b in range(B):
+        logmel[b, lens[b]:] = 0.0
+    batch = {"logmel": logmel, "logmel_len": lens,
+             "utt_id": np.array(["utt%05d" % i for i in range(B)])}
+    for task in tasks:
+        V = cfg.V if task == "char" else cfg.get("V_" + task, cfg.V)
+        tl = rng.integers(max(1, U // 2), U + 1, size=B).astype(np.int64)
+        tl[rng.integers(0, B)] = U
+        ids = np.full((B, U + 1), PAD_ID, np.int64)
+        for b in range(B):
+            n = int(tl[b])  # number of targets, includes the trailing EOS
+            ids[b, 0] = GO_ID
+            if n > 1:
+                ids[b, 1:n] = rng.integers(3, V, size=n - 1)
+            ids[b, n] = EOS_ID
+        batch[task] = ids
+        batch[task + "_len"] = tl
+    for task, (depth, vocab) in cfg.ctc.items():
+        dl = pyramid_lens(lens, depth_reductions(cfg, depth))
+        ll = np.array([rng.integers(1, max(2, int(dl[b]) // 2 + 1)) for b in range(B)], np.int64)
+        lab = np.zeros((B, int(ll.max())), np.int64)
+        for b in range(B):
+            lab[b, :ll[b]] = rng.integers(0, vocab, size=int(ll[b]))
+        batch[task] = lab
+        batch[task + "_len"] = ll
+    return batch
