@@ -1,0 +1,108 @@
+"""ctypes binding of libe2e_asr_b200.so (C ABI in include/e2e_asr_b200.h).
+
+There is no CPU fallback: if the shared library is missing (not built) or no
+CUDA device is present, every op raises.
+"""
+import ctypes
+import os
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libe2e_asr_b200.so")
+
+# signature codes: p = device/host pointer, i = int, l = long long, z = size_t, f = float
+_SIGS = {
+    "e2e_gemm": "piiiiiipipipippii",
+    "e2e_colsum": "piipipi",
+    "e2e_lstm_pack_weights": "piipppiipp",
+    "e2e_lstm_unpack_grads": "piipppiippi",
+    "e2e_lstm_rec_fwd": "piiiiillppppppzp",
+    "e2e_lstm_rec_bwd": "piiiiillppppppzp",
+    "e2e_prepare_input": "piiiiiipp",
+    "e2e_embed_gather": "piippp",
+    "e2e_embed_scatter_add": "piipppi",
+    "e2e_decoder_loop_fwd": "pp",
+    "e2e_decoder_loop_bwd": "pp",
+    "e2e_attn_fwd": "piiiiipppppppi",
+    "e2e_dec_pointwise_fwd": "piiipppipppippip",
+    "e2e_mask_rows": "piiipp",
+    "e2e_argmax_rows": "piipip",
+    "e2e_ce_fwd": "piiipppppp",
+    "e2e_ce_bwd": "piiipppppp",
+    "e2e_row_lse": "piipip",
+    "e2e_ctc_fwd_grad": "piiillppppipipppf",
+    "e2e_sumsq": "pzpppfi",
+    "e2e_clip_by_norm": "pzppfp",
+    "e2e_scale": "pzppf",
+    "e2e_mean": "pipp",
+    "e2e_axpy": "pzfpp",
+}
+_CT = {"p": ctypes.c_void_p, "i": ctypes.c_int, "l": ctypes.c_longlong, "z": ctypes.c_size_t, "f": ctypes.c_float}
+
+
+class DecLoopFwdArgs(ctypes.Structure):
+    _fields_ = ([(n, ctypes.c_int) for n in ("B", "U", "E", "Hd", "A", "D", "Tn", "Tp", "gemm_mode")] +
+                [(n, ctypes.c_void_p) for n in ("in_k", "dec_k", "dec_b", "q_k", "q_b", "attn_v", "pre", "HF",
+                                                "enc", "enc_len", "lens", "xh", "cprev", "acts", "cat", "y",
+                                                "alpha", "gates_tmp")])
+
+
+class DecLoopBwdArgs(ctypes.Structure):
+    _fields_ = [("f", DecLoopFwdArgs)] + [(n, ctypes.c_void_p) for n in (
+        "dcat", "dgates", "dxh", "dy", "dv_part", "dHF", "denc", "dc_carry")]
+
+
+_lib = None
+
+
+def lib():
+    """Loads the shared library (once).  Raises if it was not built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                "e2e_asr_b200: %s not found -- run `python -c 'import __graft_entry__ as g; g.build()'` "
+                "(there is no CPU fallback)" % LIB_PATH)
+        l = ctypes.CDLL(LIB_PATH)
+        for name, sig in _SIGS.items():
+            fn = getattr(l, name)
+            fn.argtypes = [_CT[c] for c in sig]
+            fn.restype = ctypes.c_int
+        l.e2e_last_error.restype = ctypes.c_char_p
+        l.e2e_version.restype = ctypes.c_int
+        l.e2e_sm_count.restype = ctypes.c_int
+        _lib = l
+    return _lib
+
+
+def exported_symbols():
+    return sorted(list(_SIGS.keys()) + ["e2e_last_error", "e2e_version", "e2e_sm_count"])
+
+
+def _ptr(x):
+    if x is None:
+        return None
+    if isinstance(x, torch.Tensor):
+        return x.data_ptr()
+    return x
+
+
+def stream_ptr():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def call(name, *args):
+    """Invoke `name(stream, *args)`; tensors are passed as raw device pointers."""
+    l = lib()
+    if not torch.cuda.is_available():
+        raise RuntimeError("e2e_asr_b200: no CUDA device (there is no CPU fallback)")
+    conv = []
+    for a in args:
+        if isinstance(a, ctypes.Structure):
+            conv.append(ctypes.addressof(a))
+        else:
+            conv.append(_ptr(a))
+    rc = getattr(l, name)(stream_ptr(), *conv)
+    if rc != 0:
+        raise RuntimeError("%s failed (%d): %s" % (name, rc, l.e2e_last_error().decode()))

@@ -1,0 +1,89 @@
+"""Attention decoder with the reference's signature (attn_decoder.py:18-186):
+`AttnDecoder(isTraining, params, scope)(decoder_inp, seq_len,
+encoder_hidden_states, seq_len_inp)` -> logits [(U*B), V], time-major rows."""
+import numpy as np
+import torch
+
+from . import ops
+from .decoder import Decoder
+
+
+class AttnDecoder(Decoder):
+    """Implements the attention decoder of encoder-decoder framework."""
+
+    @classmethod
+    def class_params(cls):
+        params = super(AttnDecoder, cls).class_params()
+        params['attention_vec_size'] = 128
+        params['lm_hidden_size'] = 256
+        params['ind_softmax'] = False
+        return params
+
+    def __init__(self, isTraining, params=None, scope=None, variables=None):
+        super(AttnDecoder, self).__init__(isTraining=isTraining, params=params, variables=variables)
+        self.scope = scope
+        self.stash = {}
+
+    def scope_name(self):
+        return "model/rnn_decoder" + ("" if self.scope is None else "_" + self.scope)
+
+    def get_variables(self, attn_size):
+        """All variables of the decoder scope, created with the reference's names,
+        shapes and initialisers."""
+        p, vs, s = self.params, self._store(), self.scope_name() + "/"
+        E, Hd, Hl, A, V = p.emb_size, p.hidden_size_dec, p.lm_hidden_size, p.attention_vec_size, p.vocab_size
+        D = attn_size
+        out_name = "OutputProjection2" if p.ind_softmax else "OutputProjection"   # attn_decoder.py:119-125
+        v = dict(
+            emb=vs.get(s + "decoder/embedding", (V, E), ("uniform", 1.0)),          # decoder.py:97-99
+            attn_w=vs.get(s + "AttnW", (1, 1, D, A)),
+            attn_v=vs.get(s + "AttnV", (A,)),
+            lm_k=vs.get(s + "rnn/basic_lstm_cell/kernel", (E + Hl, 4 * Hl)),
+            lm_b=vs.get(s + "rnn/basic_lstm_cell/bias", (4 * Hl,), ("zeros",)),
+            dec_k=vs.get(s + "rnn/basic_lstm_cell_1/kernel", (E + Hd, 4 * Hd)),
+            dec_b=vs.get(s + "rnn/basic_lstm_cell_1/bias", (4 * Hd,), ("zeros",)),
+            q_k=vs.get(s + "rnn/Attention/kernel", (Hd, A)),
+            q_b=vs.get(s + "rnn/Attention/bias", (A,), ("zeros",)),
+            ap_k=vs.get(s + "rnn/AttnProjection/kernel", (Hd + D, Hd)),
+            ap_b=vs.get(s + "rnn/AttnProjection/bias", (Hd,), ("zeros",)),
+            out_k=vs.get(s + "rnn/%s/kernel" % out_name, (Hd, V)),
+            out_b=vs.get(s + "rnn/%s/bias" % out_name, (V,), ("zeros",)),
+            in_k=vs.get(s + "rnn/InputProjection/kernel", (Hd + D, E)),
+            in_b=vs.get(s + "rnn/InputProjection/bias", (E,), ("zeros",)),
+            sp_k=None, sp_b=None)
+        if Hl != Hd:                                                                 # attn_decoder.py:149-151
+            v["sp_k"] = vs.get(s + "rnn/SimpleProjection/kernel", (Hl, Hd))
+            v["sp_b"] = vs.get(s + "rnn/SimpleProjection/bias", (Hd,), ("zeros",))
+        return v
+
+    def __call__(self, decoder_inp, seq_len, encoder_hidden_states, seq_len_inp):
+        """decoder_inp: [U+1, B] int64 ids (row 0 = GO); seq_len: [B] number of
+        targets; encoder_hidden_states: [B, T_enc, D]; seq_len_inp: [B]."""
+        self._check_supported()
+        enc = encoder_hidden_states
+        dev = enc.device
+        v = self.get_variables(enc.shape[2])
+        lens_host = np.asarray(ops.host_array(seq_len))
+        U = int(lens_host.max()) if len(lens_host) else 0        # raw_rnn stops when all rows are finished
+        lens = ops.to_i32(seq_len, dev)
+        enc_len = ops.to_i32(seq_len_inp, dev)
+        if self.input_rule() == "teacher":
+            return ops.AttnDecoderFn.apply(
+                enc, v["emb"], v["attn_w"], v["attn_v"], v["lm_k"], v["lm_b"], v["dec_k"], v["dec_b"], v["q_k"],
+                v["q_b"], v["ap_k"], v["ap_b"], v["out_k"], v["out_b"], v["in_k"], v["in_b"], v["sp_k"], v["sp_b"],
+                decoder_inp, lens, enc_len, U, self.stash)
+        from .inference import greedy_decode_logits
+        with torch.no_grad():
+            return greedy_decode_logits(v, decoder_inp, lens, U, enc, enc_len)
+
+    @classmethod
+    def add_parse_options(cls, parser):
+        # flag names and defaults of attn_decoder.py:174-186
+        super(AttnDecoder, cls).add_parse_options(parser)
+        parser.add_argument("-samp_prob", "--samp_prob", default=0.1, type=float,
+                            help="Scheduled sampling probability")
+        parser.add_argument("-attn_vec_size", "--attention_vec_size", default=128, type=int,
+                            help="Attention vector size")
+        parser.add_argument("-lm_hsize", "--lm_hidden_size", default=256, type=int, help="Hidden Size of LM layer")
+        parser.add_argument('-ind_softmax', "--ind_softmax", default=False, action="store_true",
+                            help="Independent (from LM) softmax params")

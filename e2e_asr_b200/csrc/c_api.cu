@@ -1,0 +1,251 @@
+// extern "C" surface of libe2e_asr_b200.so (declared in include/e2e_asr_b200.h)
+// and the host-side sequencing of the decoder loop.
+#include <stdarg.h>
+#include <string.h>
+
+#include "../../include/e2e_asr_b200.h"
+#include "common.cuh"
+
+namespace e2e {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+int sm_count() {
+    static int n = 0;
+    if (n == 0) {
+        int dev = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess) return 148;
+        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+    }
+    return n;
+}
+
+// implemented in the other translation units
+int gemm_simt(cudaStream_t, int, int, int, int, int, const float*, int, const float*, int, float*, int,
+              const float*, const float*, int, int);
+int gemm_tc(cudaStream_t, int mode, int, int, int, int, int, const float*, int, const float*, int, float*, int,
+            const float*, const float*, int, int, bool* handled);
+int colsum(cudaStream_t, int, int, const float*, int, float*, int);
+int lstm_rec(cudaStream_t, bool, int, int, int, int, int, long long, long long, float*, float*, float*,
+             const float*, const float*, const int*, void*, size_t, int*);
+int lstm_pack_weights(cudaStream_t, int, int, const float*, const float*, float*, int, int, float*, float*);
+int lstm_unpack_grads(cudaStream_t, int, int, float*, float*, const float*, int, int, const float*, const float*, int);
+int prepare_input(cudaStream_t, int, int, int, int, int, int, const float*, float*);
+int embed_gather(cudaStream_t, int, int, const float*, const long long*, float*);
+int embed_scatter_add(cudaStream_t, int, int, float*, const long long*, const float*, int);
+int dec_pointwise_fwd(cudaStream_t, int, int, int, const float*, const float*, const float*, int, const int*,
+                      float*, float*, int, float*, float*, int, float*);
+int dec_pointwise_bwd(cudaStream_t, int, int, int, const float*, const float*, int, const float*, const float*,
+                      int, float*, const float*, int, const int*, float*);
+int attn_fwd(cudaStream_t, int, int, int, int, int, const float*, const float*, const int*, const float*,
+             const float*, float*, float*, int);
+int attn_bwd(cudaStream_t, int, int, int, int, int, const float*, const float*, const int*, const float*,
+             const float*, const float*, const float*, int, float*, float*, float*, float*);
+int mask_rows(cudaStream_t, int, int, int, float*, const int*);
+int argmax_rows(cudaStream_t, int, int, const float*, int, long long*);
+int row_lse(cudaStream_t, int, int, const float*, int, float*);
+int ce_fwd(cudaStream_t, int, int, int, const float*, const long long*, const int*, float*, float*, float*);
+int ce_bwd(cudaStream_t, int, int, int, const float*, const long long*, const int*, const float*, const float*,
+           float*);
+int ctc_fwd_grad(cudaStream_t, int, int, int, long long, long long, const float*, const float*, const int*,
+                 const long long*, int, const int*, int, float*, float*, float*, float);
+int sumsq(cudaStream_t, size_t, const float*, float*, float*, float, int);
+int clip_by_norm(cudaStream_t, size_t, float*, const float*, float, float*);
+int scale_inplace(cudaStream_t, size_t, float*, const float*, float);
+int mean_vec(cudaStream_t, int, const float*, float*);
+int axpy(cudaStream_t, size_t, float, const float*, float*);
+
+static int gemm_any(cudaStream_t st, int mode, int tA, int tB, int M, int N, int K, const float* A, int lda,
+                    const float* B, int ldb, float* C, int ldc, const float* bias, const float* Z, int ldz,
+                    int accumulate) {
+    if (mode != 0) {
+        bool handled = false;
+        int rc = gemm_tc(st, mode, tA, tB, M, N, K, A, lda, B, ldb, C, ldc, bias, Z, ldz, accumulate, &handled);
+        if (rc) return rc;
+        if (handled) return 0;
+    }
+    return gemm_simt(st, tA, tB, M, N, K, A, lda, B, ldb, C, ldc, bias, Z, ldz, accumulate);
+}
+
+}  // namespace e2e
+
+using namespace e2e;
+#define ST(s) ((cudaStream_t)(s))
+
+extern "C" {
+
+int e2e_version(void) { return 1; }
+const char* e2e_last_error(void) { return e2e::g_err; }
+int e2e_sm_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0) {
+        set_error("no CUDA device: e2e_asr_b200 has no CPU fallback");
+        return -1;
+    }
+    return sm_count();
+}
+
+int e2e_gemm(void* stream, int mode, int transA, int transB, int M, int N, int K, const float* A, int lda,
+             const float* B, int ldb, float* C, int ldc, const float* bias, const float* Z, int ldz,
+             int accumulate) {
+    return gemm_any(ST(stream), mode, transA, transB, M, N, K, A, lda, B, ldb, C, ldc, bias, Z, ldz, accumulate);
+}
+int e2e_colsum(void* stream, int M, int N, const float* X, int ldx, float* out, int accumulate) {
+    return colsum(ST(stream), M, N, X, ldx, out, accumulate);
+}
+int e2e_lstm_pack_weights(void* stream, int I, int H, const float* kernel, const float* bias, float* Wx, int ldwx,
+                          int col0, float* Wh, float* bias_packed) {
+    return lstm_pack_weights(ST(stream), I, H, kernel, bias, Wx, ldwx, col0, Wh, bias_packed);
+}
+int e2e_lstm_unpack_grads(void* stream, int I, int H, float* dkernel, float* dbias, const float* dWx, int ldwx,
+                          int col0, const float* dWh, const float* dbias_packed, int accumulate) {
+    return lstm_unpack_grads(ST(stream), I, H, dkernel, dbias, dWx, ldwx, col0, dWh, dbias_packed, accumulate);
+}
+int e2e_lstm_rec_fwd(void* stream, int B, int T, int Tp, int H, int ndir, long long sb, long long st, float* G,
+                     float* Hout, float* Cst, const float* Wh, const int* lens, void* ctr_ws, size_t ctr_ws_bytes,
+                     int* err_flag) {
+    return lstm_rec(ST(stream), false, B, T, Tp, H, ndir, sb, st, G, Hout, Cst, Wh, nullptr, lens, ctr_ws,
+                    ctr_ws_bytes, err_flag);
+}
+int e2e_lstm_rec_bwd(void* stream, int B, int T, int Tp, int H, int ndir, long long sb, long long st, float* G,
+                     const float* Cst, const float* Wh, const float* dOut, const int* lens, void* ctr_ws,
+                     size_t ctr_ws_bytes, int* err_flag) {
+    return lstm_rec(ST(stream), true, B, T, Tp, H, ndir, sb, st, G, nullptr, const_cast<float*>(Cst), Wh, dOut,
+                    lens, ctr_ws, ctr_ws_bytes, err_flag);
+}
+int e2e_prepare_input(void* stream, int B, int T, int F, int Tp, int stack, int stride, const float* in,
+                      float* out) {
+    return prepare_input(ST(stream), B, T, F, Tp, stack, stride, in, out);
+}
+int e2e_embed_gather(void* stream, int n, int E, const float* emb, const long long* ids, float* out) {
+    return embed_gather(ST(stream), n, E, emb, ids, out);
+}
+int e2e_embed_scatter_add(void* stream, int n, int E, float* demb, const long long* ids, const float* dout,
+                          int ldd) {
+    return embed_scatter_add(ST(stream), n, E, demb, ids, dout, ldd);
+}
+
+int e2e_decoder_loop_fwd(void* stream, const e2e_dec_loop_fwd_args* a) {
+    cudaStream_t st = ST(stream);
+    const int B = a->B, U = a->U, E = a->E, Hd = a->Hd, A = a->A, D = a->D;
+    const int XH = E + Hd, CAT = Hd + D, mode = a->gemm_mode;
+    for (int t = 0; t < U; ++t) {
+        float* xh_t = a->xh + (size_t)t * B * XH;
+        float* cat_t = a->cat + (size_t)t * B * CAT;
+        const float* cat_p = a->cat + (size_t)(t - 1) * B * CAT;
+        // xin_t = pre_t + ctx_{t-1} . in_k[Hd:]              (attn_decoder.py:157-158)
+        int rc = gemm_any(st, mode, 0, 0, B, E, t == 0 ? 0 : D, t == 0 ? a->enc : cat_p + Hd, CAT,
+                          a->in_k + (size_t)Hd * E, E, xh_t, XH, nullptr, a->pre + (size_t)t * B * E, E, 0);
+        if (rc) return rc;
+        // gates = [xin, h] . dec_k + dec_b                   (raw_rnn body -> BasicLSTMCell)
+        rc = gemm_any(st, mode, 0, 0, B, 4 * Hd, XH, xh_t, XH, a->dec_k, 4 * Hd, a->gates_tmp, 4 * Hd, a->dec_b,
+                      nullptr, 0, 0);
+        if (rc) return rc;
+        bool last = t + 1 == U;
+        rc = dec_pointwise_fwd(st, B, Hd, t, a->gates_tmp, a->cprev + (size_t)t * B * Hd, xh_t + E, XH, a->lens,
+                               a->acts + (size_t)t * B * 4 * Hd, cat_t, CAT,
+                               last ? nullptr : a->cprev + (size_t)(t + 1) * B * Hd,
+                               last ? nullptr : a->xh + (size_t)(t + 1) * B * XH + E, XH, nullptr);
+        if (rc) return rc;
+        // y = c_new . q_k + q_b (query is the cell state, attn_decoder.py:114)
+        float* y_t = a->y + (size_t)t * B * A;
+        rc = gemm_any(st, mode, 0, 0, B, A, Hd, cat_t, CAT, a->q_k, A, y_t, A, a->q_b, nullptr, 0, 0);
+        if (rc) return rc;
+        rc = attn_fwd(st, B, a->Tn, a->Tp, A, D, a->HF, a->enc, a->enc_len, y_t, a->attn_v,
+                      a->alpha + (size_t)t * B * a->Tn, cat_t + Hd, CAT);
+        if (rc) return rc;
+    }
+    return 0;
+}
+
+int e2e_decoder_loop_bwd(void* stream, const e2e_dec_loop_bwd_args* g) {
+    cudaStream_t st = ST(stream);
+    const e2e_dec_loop_fwd_args* a = &g->f;
+    const int B = a->B, U = a->U, E = a->E, Hd = a->Hd, A = a->A, D = a->D;
+    const int XH = E + Hd, CAT = Hd + D, mode = a->gemm_mode;
+    for (int t = U - 1; t >= 0; --t) {
+        float* dcat_t = g->dcat + (size_t)t * B * CAT;
+        const float* cat_t = a->cat + (size_t)t * B * CAT;
+        float* dy_t = g->dy + (size_t)t * B * A;
+        int rc = attn_bwd(st, B, a->Tn, a->Tp, A, D, a->HF, a->enc, a->enc_len, a->y + (size_t)t * B * A,
+                          a->attn_v, a->alpha + (size_t)t * B * a->Tn, dcat_t + Hd, CAT, g->dHF, g->denc, dy_t,
+                          g->dv_part);
+        if (rc) return rc;
+        // d c_new += dy . q_k^T
+        rc = gemm_any(st, mode, 0, 1, B, Hd, A, dy_t, A, a->q_k, A, dcat_t, CAT, nullptr, nullptr, 0, 1);
+        if (rc) return rc;
+        float* dz_t = g->dgates + (size_t)t * B * 4 * Hd;
+        bool last = t + 1 == U;
+        rc = dec_pointwise_bwd(st, B, Hd, t, a->acts + (size_t)t * B * 4 * Hd, cat_t, CAT,
+                               a->cprev + (size_t)t * B * Hd, dcat_t, CAT, g->dc_carry,
+                               last ? nullptr : g->dxh + (size_t)(t + 1) * B * XH + E, XH, a->lens, dz_t);
+        if (rc) return rc;
+        // (dxin | dh_prev) = dz . dec_k^T
+        float* dxh_t = g->dxh + (size_t)t * B * XH;
+        rc = gemm_any(st, mode, 0, 1, B, XH, 4 * Hd, dz_t, 4 * Hd, a->dec_k, 4 * Hd, dxh_t, XH, nullptr, nullptr, 0,
+                      0);
+        if (rc) return rc;
+        // d ctx_{t-1} += dxin . in_k[Hd:]^T
+        if (t > 0) {
+            rc = gemm_any(st, mode, 0, 1, B, D, E, dxh_t, XH, a->in_k + (size_t)Hd * E, E,
+                          g->dcat + (size_t)(t - 1) * B * CAT + Hd, CAT, nullptr, nullptr, 0, 1);
+            if (rc) return rc;
+        }
+    }
+    return 0;
+}
+
+int e2e_attn_fwd(void* stream, int B, int Tn, int Tp, int A, int D, const float* HF, const float* enc,
+                 const int* enc_len, const float* y, const float* v, float* alpha, float* ctx, int ldctx) {
+    return attn_fwd(ST(stream), B, Tn, Tp, A, D, HF, enc, enc_len, y, v, alpha, ctx, ldctx);
+}
+int e2e_dec_pointwise_fwd(void* stream, int B, int H, int t, const float* gates_pre, const float* cprev,
+                          const float* hprev, int ldh, const int* lens, float* acts, float* cnew_out, int ldc,
+                          float* c_next, float* h_next, int ldhn, float* h_new_out) {
+    return dec_pointwise_fwd(ST(stream), B, H, t, gates_pre, cprev, hprev, ldh, lens, acts, cnew_out, ldc, c_next,
+                             h_next, ldhn, h_new_out);
+}
+int e2e_mask_rows(void* stream, int U, int B, int V, float* logits, const int* lens) {
+    return mask_rows(ST(stream), U, B, V, logits, lens);
+}
+int e2e_argmax_rows(void* stream, int rows, int V, const float* x, int ldx, long long* out) {
+    return argmax_rows(ST(stream), rows, V, x, ldx, out);
+}
+int e2e_ce_fwd(void* stream, int U, int B, int V, const float* logits, const long long* targets, const int* lens,
+               float* lse, float* cost, float* loss) {
+    return ce_fwd(ST(stream), U, B, V, logits, targets, lens, lse, cost, loss);
+}
+int e2e_ce_bwd(void* stream, int U, int B, int V, const float* logits, const long long* targets, const int* lens,
+               const float* lse, const float* gscale, float* dlogits) {
+    return ce_bwd(ST(stream), U, B, V, logits, targets, lens, lse, gscale, dlogits);
+}
+int e2e_row_lse(void* stream, int rows, int V, const float* x, int ldx, float* lse) {
+    return row_lse(ST(stream), rows, V, x, ldx, lse);
+}
+int e2e_ctc_fwd_grad(void* stream, int T, int B, int C, long long sb, long long stt, const float* logits,
+                     const float* lse_rows, const int* in_lens, const long long* labels, int ldl,
+                     const int* label_lens, int max_label_len, float* alpha_ws, float* loss_b, float* grad,
+                     float out_scale) {
+    return ctc_fwd_grad(ST(stream), T, B, C, sb, stt, logits, lse_rows, in_lens, labels, ldl, label_lens,
+                        max_label_len, alpha_ws, loss_b, grad, out_scale);
+}
+int e2e_sumsq(void* stream, size_t n, const float* x, float* partials296, float* out, float sign, int accumulate) {
+    return sumsq(ST(stream), n, x, partials296, out, sign, accumulate);
+}
+int e2e_clip_by_norm(void* stream, size_t n, float* x, const float* sq, float clip, float* norm_out) {
+    return clip_by_norm(ST(stream), n, x, sq, clip, norm_out);
+}
+int e2e_scale(void* stream, size_t n, float* x, const float* dev_scalar, float a) {
+    return scale_inplace(ST(stream), n, x, dev_scalar, a);
+}
+int e2e_mean(void* stream, int n, const float* x, float* out) { return mean_vec(ST(stream), n, x, out); }
+int e2e_axpy(void* stream, size_t n, float a, const float* x, float* y) { return axpy(ST(stream), n, a, x, y); }
+
+}  // extern "C"

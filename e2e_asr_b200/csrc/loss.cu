@@ -1,0 +1,298 @@
+// Losses: the reference's masked, length-normalised sequence cross-entropy
+// (losses.py:6-35) and the builder-defined auxiliary CTC (TF-1.x
+// tf.nn.ctc_loss semantics, blank = C-1; no reference code exists for it).
+#include "common.cuh"
+
+namespace e2e {
+
+// ---- row log-sum-exp -------------------------------------------------------
+// one warp per row; lse[row] = log sum_v exp(x[row, v])
+__global__ void row_lse_kernel(int rows, int V, const float* __restrict__ x, int ldx, float* __restrict__ lse) {
+    int row = blockIdx.x * (blockDim.x / 32) + threadIdx.x / 32;
+    int lane = threadIdx.x % 32;
+    if (row >= rows) return;
+    const float* r = x + (size_t)row * ldx;
+    float mx = -INFINITY;
+    for (int v = lane; v < V; v += 32) mx = fmaxf(mx, r[v]);
+    mx = warp_max(mx);
+    float s = 0.f;
+    for (int v = lane; v < V; v += 32) s += expf(r[v] - mx);
+    s = warp_sum(s);
+    if (lane == 0) lse[row] = mx + logf(s);
+}
+
+int row_lse(cudaStream_t st, int rows, int V, const float* x, int ldx, float* lse) {
+    if (rows <= 0) return 0;
+    row_lse_kernel<<<cdiv(rows, 8), 256, 0, st>>>(rows, V, x, ldx, lse);
+    E2E_LAUNCH_CHECK();
+    return 0;
+}
+
+// ---- sequence cross-entropy (losses.py:18-35) ------------------------------
+// logits [(U*B), V] time-major rows (t*B+b); targets [U][B] (row stride ldt in
+// elements, so a [U+1,B] decoder-input tensor shifted by one row can be passed);
+// cost_row = (lse - logit[target]) * [t < len_b] / (len_b * B).
+__global__ void ce_rowcost_kernel(int U, int B, int V, const float* __restrict__ logits,
+                                  const long long* __restrict__ targets, const int* __restrict__ lens,
+                                  float* __restrict__ lse, float* __restrict__ cost) {
+    int row = blockIdx.x * (blockDim.x / 32) + threadIdx.x / 32;
+    int lane = threadIdx.x % 32;
+    if (row >= U * B) return;
+    int t = row / B, b = row % B;
+    const float* r = logits + (size_t)row * V;
+    float mx = -INFINITY;
+    for (int v = lane; v < V; v += 32) mx = fmaxf(mx, r[v]);
+    mx = warp_max(mx);
+    float s = 0.f;
+    for (int v = lane; v < V; v += 32) s += expf(r[v] - mx);
+    s = warp_sum(s);
+    if (lane == 0) {
+        float l = mx + logf(s);
+        lse[row] = l;
+        int len = lens[b];
+        cost[row] = (t < len) ? (l - r[targets[row]]) / ((float)len * (float)B) : 0.f;
+    }
+}
+
+// deterministic single-block sum: out[0] = sum x[0..n)
+__global__ void sum_kernel(int n, const float* __restrict__ x, float* __restrict__ out, float scale) {
+    __shared__ float red[32];
+    float s = 0.f;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) s += x[i];
+    s = warp_sum(s);
+    if (threadIdx.x % 32 == 0) red[threadIdx.x / 32] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float tot = 0.f;
+        for (int w = 0; w < (int)blockDim.x / 32; ++w) tot += red[w];
+        out[0] = tot * scale;
+    }
+}
+
+int ce_fwd(cudaStream_t st, int U, int B, int V, const float* logits, const long long* targets, const int* lens,
+           float* lse, float* cost, float* loss) {
+    if (U * B <= 0) return 0;
+    ce_rowcost_kernel<<<cdiv(U * B, 8), 256, 0, st>>>(U, B, V, logits, targets, lens, lse, cost);
+    E2E_LAUNCH_CHECK();
+    sum_kernel<<<1, 1024, 0, st>>>(U * B, cost, loss, 1.0f);
+    E2E_LAUNCH_CHECK();
+    return 0;
+}
+
+// dlogits = g * [t<len]/(len*B) * (softmax - onehot), g read from device memory
+__global__ void ce_bwd_kernel(int U, int B, int V, const float* __restrict__ logits,
+                              const long long* __restrict__ targets, const int* __restrict__ lens,
+                              const float* __restrict__ lse, const float* __restrict__ gscale,
+                              float* __restrict__ dlogits) {
+    int row = blockIdx.x;
+    int t = row / B, b = row % B;
+    int len = lens[b];
+    float* d = dlogits + (size_t)row * V;
+    if (t >= len) {
+        for (int v = threadIdx.x; v < V; v += blockDim.x) d[v] = 0.f;
+        return;
+    }
+    float w = gscale[0] / ((float)len * (float)B);
+    const float* r = logits + (size_t)row * V;
+    float l = lse[row];
+    int tg = (int)targets[row];
+    for (int v = threadIdx.x; v < V; v += blockDim.x) d[v] = w * (expf(r[v] - l) - (v == tg ? 1.f : 0.f));
+}
+
+int ce_bwd(cudaStream_t st, int U, int B, int V, const float* logits, const long long* targets, const int* lens,
+           const float* lse, const float* gscale, float* dlogits) {
+    if (U * B <= 0) return 0;
+    ce_bwd_kernel<<<U * B, 256, 0, st>>>(U, B, V, logits, targets, lens, lse, gscale, dlogits);
+    E2E_LAUNCH_CHECK();
+    return 0;
+}
+
+// ---- CTC: one warp per utterance, log space, fused gradient -----------------
+// logits rows are addressed as (b*sb + t*st)*C (so batch-major encoder states
+// projected by a GEMM need no transpose); lse_rows holds the per-row softmax
+// normaliser.  Lane l owns the SPL consecutive extended-label states
+// [l*SPL, (l+1)*SPL); neighbours are exchanged with shuffles, alpha_t is kept in
+// registers and spilled to `alpha_ws` [B][T][S_max] for the beta/gradient sweep.
+// grad = softmax - (1/p) sum_{s in lab(k)} alpha_t(s) beta_t(s) / y_t(k), zero for t >= len,
+// scaled by out_scale.  Infeasible labels give loss = +inf like TF's error path
+// would abort; callers must supply feasible labels.
+__device__ __forceinline__ float log_add(float a, float b) {
+    if (a == -INFINITY) return b;
+    if (b == -INFINITY) return a;
+    float m = fmaxf(a, b);
+    return m + log1pf(expf(-fabsf(a - b)));
+}
+
+template <int SPL>
+__global__ void __launch_bounds__(32)
+ctc_kernel(int T, int B, int C, long long sb, long long stt, const float* __restrict__ logits,
+           const float* __restrict__ lse_rows, const int* __restrict__ in_lens,
+           const long long* __restrict__ labels, int ldl, const int* __restrict__ label_lens,
+           float* __restrict__ alpha_ws, int S_max, float* __restrict__ loss_b, float* __restrict__ grad,
+           float out_scale) {
+    extern __shared__ float occ[];     // [C]
+    const int b = blockIdx.x, lane = threadIdx.x;
+    const int Tb = min(in_lens[b], T), L = label_lens[b];
+    const int S = 2 * L + 1, blank = C - 1;
+    const float NEG = -INFINITY;
+    int ext[SPL];
+    bool skip[SPL];
+#pragma unroll
+    for (int i = 0; i < SPL; ++i) {
+        int s = lane * SPL + i;
+        int e = blank;
+        bool sk = false;
+        if (s < S && (s & 1)) {
+            e = (int)labels[(size_t)b * ldl + s / 2];
+            if (s >= 3) sk = e != (int)labels[(size_t)b * ldl + s / 2 - 1];
+        }
+        ext[i] = e;
+        skip[i] = sk;
+    }
+    float* aw = alpha_ws + (size_t)b * T * S_max;
+    float a[SPL];
+#pragma unroll
+    for (int i = 0; i < SPL; ++i) a[i] = NEG;
+    // ---- alpha sweep
+    for (int t = 0; t < Tb; ++t) {
+        const float* row = logits + ((size_t)b * sb + (size_t)t * stt) * C;
+        const float nz = lse_rows[(size_t)b * sb + (size_t)t * stt];
+        float prev1 = __shfl_up_sync(0xffffffffu, a[SPL - 1], 1);
+        float prev2 = __shfl_up_sync(0xffffffffu, SPL >= 2 ? a[SPL >= 2 ? SPL - 2 : 0] : 0.f, 1);
+        if (SPL == 1) prev2 = __shfl_up_sync(0xffffffffu, a[0], 2);
+        if (lane == 0) { prev1 = NEG; prev2 = NEG; }
+        if (SPL == 1 && lane == 1) prev2 = NEG;
+        float na[SPL];
+#pragma unroll
+        for (int i = 0; i < SPL; ++i) {
+            int s = lane * SPL + i;
+            float lp = (s < S) ? row[ext[i]] - nz : NEG;
+            float v;
+            if (t == 0) {
+                v = (s <= 1 && s < S) ? lp : NEG;
+            } else {
+                float p0 = a[i];
+                float p1 = i >= 1 ? a[i >= 1 ? i - 1 : 0] : prev1;
+                float p2 = i >= 2 ? a[i >= 2 ? i - 2 : 0] : (i == 1 ? prev1 : prev2);
+                if (SPL == 1) { p1 = prev1; p2 = prev2; }
+                v = log_add(p0, p1);
+                if (skip[i]) v = log_add(v, p2);
+                v = (s < S) ? v + lp : NEG;
+            }
+            na[i] = v;
+        }
+#pragma unroll
+        for (int i = 0; i < SPL; ++i) {
+            a[i] = na[i];
+            int s = lane * SPL + i;
+            if (s < S) aw[(size_t)t * S_max + s] = na[i];
+        }
+    }
+    // log-likelihood = logaddexp(alpha_{T-1}(S-1), alpha_{T-1}(S-2))
+    float ll = NEG;
+    {
+        float mine = NEG;
+#pragma unroll
+        for (int i = 0; i < SPL; ++i) {
+            int s = lane * SPL + i;
+            if (Tb > 0 && (s == S - 1 || (s == S - 2 && S >= 2))) mine = log_add(mine, a[i]);
+        }
+        for (int o = 16; o > 0; o >>= 1) mine = log_add(mine, __shfl_xor_sync(0xffffffffu, mine, o));
+        ll = mine;
+    }
+    if (lane == 0) loss_b[b] = -ll;
+    const float gs = out_scale;
+    // ---- beta sweep + gradient
+    float bt[SPL];
+#pragma unroll
+    for (int i = 0; i < SPL; ++i) bt[i] = NEG;
+    for (int t = T - 1; t >= 0; --t) {
+        float* grow = grad + ((size_t)b * sb + (size_t)t * stt) * C;
+        if (t >= Tb) {
+            for (int k = lane; k < C; k += 32) grow[k] = 0.f;
+            continue;
+        }
+        const float* row = logits + ((size_t)b * sb + (size_t)t * stt) * C;
+        const float nz = lse_rows[(size_t)b * sb + (size_t)t * stt];
+        float nxt1 = __shfl_down_sync(0xffffffffu, bt[0], 1);
+        float nxt2 = __shfl_down_sync(0xffffffffu, SPL >= 2 ? bt[SPL >= 2 ? 1 : 0] : 0.f, 1);
+        if (SPL == 1) nxt2 = __shfl_down_sync(0xffffffffu, bt[0], 2);
+        // skip flag of state s+2 (needed by the transition s -> s+2)
+        bool nskip1 = __shfl_down_sync(0xffffffffu, (int)skip[0], 1);
+        bool nskip2 = __shfl_down_sync(0xffffffffu, (int)(SPL >= 2 ? skip[SPL >= 2 ? 1 : 0] : false), 1);
+        if (SPL == 1) nskip2 = __shfl_down_sync(0xffffffffu, (int)skip[0], 2);
+        if (lane == 31) { nxt1 = NEG; nxt2 = NEG; nskip1 = false; nskip2 = false; }
+        if (SPL == 1 && lane == 30) { nxt2 = NEG; nskip2 = false; }
+        float nb[SPL];
+#pragma unroll
+        for (int i = 0; i < SPL; ++i) {
+            int s = lane * SPL + i;
+            float lp = (s < S) ? row[ext[i]] - nz : NEG;
+            float v;
+            if (t == Tb - 1) {
+                v = (s < S && (s == S - 1 || s == S - 2)) ? lp : NEG;
+            } else {
+                float n0 = bt[i];
+                float n1 = (i + 1 < SPL) ? bt[(i + 1 < SPL) ? i + 1 : 0] : nxt1;
+                float n2;
+                bool sk2;
+                if (SPL == 1) { n1 = nxt1; n2 = nxt2; sk2 = nskip2; }
+                else if (i + 2 < SPL) { n2 = bt[(i + 2 < SPL) ? i + 2 : 0]; sk2 = skip[(i + 2 < SPL) ? i + 2 : 0]; }
+                else if (i + 2 == SPL) { n2 = nxt1; sk2 = nskip1; }
+                else { n2 = nxt2; sk2 = nskip2; }
+                v = log_add(n0, n1);
+                if (sk2) v = log_add(v, n2);
+                v = (s < S) ? v + lp : NEG;
+            }
+            nb[i] = v;
+        }
+#pragma unroll
+        for (int i = 0; i < SPL; ++i) bt[i] = nb[i];
+        // occupancy per class: sum_s exp(alpha+beta - ll - logp_t(k))   (alpha,beta both hold the emission)
+        for (int k = lane; k < C; k += 32) occ[k] = 0.f;
+        __syncwarp();
+#pragma unroll
+        for (int i = 0; i < SPL; ++i) {
+            int s = lane * SPL + i;
+            if (s < S) {
+                float al = aw[(size_t)t * S_max + s];
+                float lp = row[ext[i]] - nz;
+                float e = al + bt[i] - ll - lp;
+                if (al != NEG && bt[i] != NEG) atomicAdd(&occ[ext[i]], expf(e));
+            }
+        }
+        __syncwarp();
+        for (int k = lane; k < C; k += 32) grow[k] = gs * (expf(row[k] - nz) - occ[k]);
+        __syncwarp();
+    }
+}
+
+int ctc_fwd_grad(cudaStream_t st, int T, int B, int C, long long sb, long long stt, const float* logits,
+                 const float* lse_rows, const int* in_lens, const long long* labels, int ldl,
+                 const int* label_lens, int max_label_len, float* alpha_ws, float* loss_b, float* grad,
+                 float out_scale) {
+    if (B <= 0 || T <= 0) return 0;
+    int S_max = 2 * max_label_len + 1;
+    size_t smem = sizeof(float) * C;
+    E2E_REQUIRE(S_max <= 32 * 32, "ctc: label length %d too long (max 511)", max_label_len);
+    E2E_REQUIRE(smem <= 200 * 1024, "ctc: %d classes do not fit shared memory", C);
+#define CTC_CASE(SPL_)                                                                                          \
+    {                                                                                                           \
+        if (smem > 48 * 1024)                                                                                   \
+            E2E_CHECK_CUDA(cudaFuncSetAttribute(ctc_kernel<SPL_>, cudaFuncAttributeMaxDynamicSharedMemorySize,  \
+                                                (int)smem));                                                    \
+        ctc_kernel<SPL_><<<B, 32, smem, st>>>(T, B, C, sb, stt, logits, lse_rows, in_lens, labels, ldl,        \
+                                              label_lens, alpha_ws, S_max, loss_b, grad, out_scale);    \
+    }
+    if (S_max <= 32) CTC_CASE(1)
+    else if (S_max <= 64) CTC_CASE(2)
+    else if (S_max <= 128) CTC_CASE(4)
+    else if (S_max <= 256) CTC_CASE(8)
+    else if (S_max <= 512) CTC_CASE(16)
+    else CTC_CASE(32)
+#undef CTC_CASE
+    E2E_LAUNCH_CHECK();
+    return 0;
+}
+
+}  // namespace e2e

@@ -1,0 +1,68 @@
+"""Decoder base class (reference decoder.py:17-193): hyper-parameters, variable
+creation and the choice of next-input rule.  The actual stepping lives in
+attn_decoder.py / the CUDA decoder loop."""
+from .base_params import BaseParams, Bunch
+from .variables import default_store
+
+
+class Decoder(BaseParams):
+    """Base class for decoder in encoder-decoder framework."""
+
+    @classmethod
+    def class_params(cls):
+        """Decoder class parameters (decoder.py:22-34)."""
+        params = Bunch()
+        params['out_prob_dec'] = 0.9
+        params['hidden_size_dec'] = 256
+        params['num_layers_dec'] = 1
+        params['emb_size'] = 256
+        params['vocab_size'] = 1000
+        params['samp_prob'] = 0.1
+        params['max_output'] = 400
+        params['use_lstm'] = True
+        return params
+
+    def __init__(self, isTraining=True, params=None, variables=None):
+        self.params = self.class_params() if params is None else params
+        self.isTraining = isTraining
+        self.variables = variables
+
+    def _store(self):
+        return self.variables if self.variables is not None else default_store()
+
+    def _check_supported(self):
+        p = self.params
+        if not p.use_lstm:
+            raise NotImplementedError("Decoder: use_lstm=False (GRUCell, decoder.py:58) is not built yet")
+        if p.num_layers_dec != 1:
+            raise NotImplementedError("Decoder: num_layers_dec > 1 (MultiRNNCell, decoder.py:64-68) is not built yet")
+        if self.isTraining and p.out_prob_dec != 1.0:
+            raise NotImplementedError("Decoder: dropout (out_prob_dec=%g) is not built yet; parity and benchmark "
+                                      "runs use 1.0 (SURVEY.md section 7)" % p.out_prob_dec)
+        if self.isTraining and p.samp_prob > 0:
+            raise NotImplementedError("Decoder: scheduled sampling (samp_prob=%g, decoder.py:155-180) is not built "
+                                      "yet; parity and benchmark runs use samp_prob=0" % p.samp_prob)
+
+    def get_state(self, state):
+        """The attention query / projection input is the LSTM CELL state c of the
+        last layer (decoder.py:74-82). `state` is a (c, h) pair."""
+        if self.params.num_layers_dec > 1:
+            state = state[-1]
+        return state[0] if self.params.use_lstm else state
+
+    def input_rule(self):
+        """Which token feeds step t+1 (decoder.py:103-115): 'teacher' in training
+        with samp_prob == 0, 'sample' with scheduled sampling, 'greedy' at eval."""
+        if self.isTraining:
+            return "sample" if self.params.samp_prob > 0 else "teacher"
+        return "greedy"
+
+    @classmethod
+    def add_parse_options(cls, parser):
+        # flag names and defaults of decoder.py:182-193
+        parser.add_argument("-hsize_dec", "--hidden_size_dec", default=256, type=int,
+                            help="Hidden size of decoder RNN")
+        parser.add_argument("-emb_size", "--emb_size", default=256, type=int, help="Embedding size")
+        parser.add_argument("-num_layers_dec", "--num_layers_dec", default=1, type=int,
+                            help="Number of RNN layers")
+        parser.add_argument("-out_prob_dec", "--out_prob_dec", default=0.9, type=float, help="1 - dropout_prob")

@@ -1,0 +1,153 @@
+"""Encoder: pyramidal multi-layer BiLSTM over log-mel frames.
+
+Same constructor / __call__ signature, hyper-parameters and return values as the
+reference `Encoder` (encoder.py:15-200); the TF graph ops are replaced by the
+persistent-recurrence and GEMM kernels of libe2e_asr_b200.so.
+
+Layout: every layer works on a zero-padded batch-major buffer [B, Tp_l, C] with
+Tp_1 a multiple of 2^(#pyramid steps) and Tp_l >= max(len_l) + 1.  The pyramid
+reshape (encoder.py:94-119) is then a free view, and the public states are
+time-narrowed views with exactly the reference's shapes [B, T_l, 2H].
+"""
+import math
+
+import numpy as np
+import torch
+
+from . import ops
+from .base_params import BaseParams, Bunch
+from .variables import default_store
+
+
+class Encoder(BaseParams):
+    """Encoder class that encodes input sequence."""
+
+    @classmethod
+    def class_params(cls):
+        """Encoder class parameters (encoder.py:19-31)."""
+        params = Bunch()
+        params['bi_dir'] = True
+        params['hidden_size'] = 256
+        params['out_prob'] = 0.9
+        params['skip_step'] = 2  # Pyramidal architecture
+        params['initial_res_fac'] = 1
+        params['use_lstm'] = False
+        params['stack_cons'] = 1
+        params['max_scaling_down'] = 8
+        return params
+
+    def __init__(self, params=None, isTraining=True, variables=None):
+        self.params = params if params is not None else self.class_params()
+        self.isTraining = isTraining
+        self.variables = variables
+
+    def _check_supported(self):
+        p = self.params
+        if not p.use_lstm:
+            raise NotImplementedError("Encoder: use_lstm=False (GRUCell, encoder.py:48) is not built yet; "
+                                      "pass use_lstm=True (the reference CLI default, encoder.py:187)")
+        if not p.bi_dir:
+            raise NotImplementedError("Encoder: bi_dir=False is not built yet")
+        if self.isTraining and p.out_prob != 1.0:
+            raise NotImplementedError("Encoder: output dropout (out_prob=%g) is not built yet; parity and "
+                                      "benchmark runs use out_prob=1.0 (SURVEY.md section 7)" % p.out_prob)
+        if p.skip_step not in (1, 2):
+            raise NotImplementedError("Encoder: skip_step must be 1 or 2")
+
+    def _layer_vars(self, layer_depth, in_size):
+        """Variables of RNNLayer<d> (encoder.py:72-81): U(-0.075, 0.075) kernels, zero biases."""
+        vs = self.variables if self.variables is not None else default_store()
+        H = self.params.hidden_size
+        out = []
+        for d in ("fw", "bw"):
+            base = "model/encoder/RNNLayer%d/bidirectional_rnn/%s/basic_lstm_cell/" % (layer_depth, d)
+            out.append(vs.get(base + "kernel", (in_size + H, 4 * H), ("uniform", 0.075)))
+            out.append(vs.get(base + "bias", (4 * H,), ("zeros",)))
+        return out
+
+    def _layer_encoder_input(self, x_padded, lens_i32, max_len, layer_depth=1):
+        """Run one BiLSTM layer on a padded batch-major buffer (encoder.py:55-91)."""
+        k_fw, b_fw, k_bw, b_bw = self._layer_vars(layer_depth, x_padded.shape[2])
+        return ops.BiLSTMLayerFn.apply(x_padded, k_fw, b_fw, k_bw, b_bw, lens_i32, max_len)
+
+    def __call__(self, encoder_input, seq_len, num_layers):
+        """Run the encoder (encoder.py:122-180).
+
+        Args:
+            encoder_input: [B, T, F] float32 (batch major, zero padded past seq_len).
+            seq_len: [B] valid frames per utterance.
+            num_layers: dict task -> encoder depth; a task named "state" (or ending
+                in "_ctc") gets the time-major view (encoder.py:143-144).
+        Returns:
+            attention_states {depth: [B,T_d,2H]}, time_major_states {depth: [T_d,B,2H]},
+            seq_len_inps {depth: [B] int64}.
+        """
+        self._check_supported()
+        params = self.params
+        attention_states, time_major_states, seq_len_inps = {}, {}, {}
+        max_depth = 0
+        for task, num_layer in num_layers.items():
+            if task == "state" or task.endswith("_ctc"):
+                time_major_states[num_layer] = None
+            else:
+                attention_states[num_layer] = None
+            max_depth = max(max_depth, num_layer)
+
+        dev = encoder_input.device
+        lens_host = np.asarray(ops.host_array(seq_len), np.int64)
+        B, T, F = encoder_input.shape
+        res = params.initial_res_fac
+        if res > 1:
+            lens_host = -(-lens_host // res)
+            T = -(-T // res)
+        # number of pyramid reductions that will be applied (encoder.py:172)
+        n_red, r = 0, res
+        for i in range(max_depth):
+            if params.skip_step > 1 and i != max_depth - 1 and r < params.max_scaling_down:
+                n_red += 1
+                r *= params.skip_step
+        q = 2 ** n_red
+        Tp = q * (-(-T // q) + 1)
+        x = ops.prepare_input(encoder_input, Tp, params.stack_cons, max(res, 1))
+        if self.isTraining is False:
+            x = x.detach()
+
+        T_l = T
+        for i in range(max_depth):
+            layer_depth = i + 1
+            lens_dev = torch.from_numpy(lens_host.astype(np.int32)).to(dev, non_blocking=True)
+            max_len = int(lens_host.max()) if B else 0
+            out = self._layer_encoder_input(x, lens_dev, max_len, layer_depth)       # [B, Tp, 2H]
+            view = out[:, :T_l]
+            if layer_depth in time_major_states:
+                time_major_states[layer_depth] = view.transpose(0, 1)
+            if layer_depth in attention_states:
+                attention_states[layer_depth] = view
+            sl = torch.from_numpy(lens_host.copy()).to(dev, non_blocking=True)
+            sl._host = lens_host.copy()
+            sl._i32 = lens_dev
+            seq_len_inps[layer_depth] = sl
+            if params.skip_step > 1 and i != (max_depth - 1) and res < params.max_scaling_down:
+                # _get_pyramid_input: frame 2k || frame 2k+1, len = ceil(len/2)
+                x = out.view(B, Tp // 2, out.shape[2] * 2)
+                Tp //= 2
+                T_l = -(-T_l // 2)
+                lens_host = -(-lens_host // 2)
+                res *= params.skip_step
+            else:
+                x = out
+        return attention_states, time_major_states, seq_len_inps
+
+    @classmethod
+    def add_parse_options(cls, parser):
+        # flag names and defaults of encoder.py:183-200
+        parser.add_argument("-out_prob", "--out_prob", default=0.9, type=float,
+                            help="Output keep probability for dropout")
+        parser.add_argument("-use_lstm", "--use_lstm", default=True, action="store_true", help="LSTM cells")
+        parser.add_argument("-hsize", "--hidden_size", default=256, type=int, help="Hidden layer size")
+        parser.add_argument("-skip_step", "--skip_step", default=2, type=int,
+                            help="Frame skipping factor as we go up the stacked layers")
+        parser.add_argument("-init_res_fac", "--initial_res_fac", default=1, type=int,
+                            help="Initial resolution factor")
+        parser.add_argument("-stack_cons", default=1, type=int, help="Stacking consecutive frames in input")
+        parser.add_argument("-max_scaling_down", default=8, type=int, help="Maximum reduction in resolution")

@@ -1,0 +1,426 @@
+"""torch.autograd.Function wrappers around the sm_100a kernels (C ABI, _lib.py).
+
+PyTorch is used for device-memory allocation, stream plumbing and the autograd
+graph between modules only; every FLOP of the hot path runs in
+libe2e_asr_b200.so.  There is no eager/CPU fallback.
+"""
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import call
+
+# 0 = fp32 FFMA, 1 = 3xTF32 tcgen05 (fp32-accurate), 2 = bf16 tcgen05
+_GEMM_MODE = 0
+
+
+def set_gemm_mode(mode):
+    global _GEMM_MODE
+    _GEMM_MODE = {"fp32": 0, "tf32x3": 1, "bf16": 2}.get(mode, mode)
+
+
+def get_gemm_mode():
+    return _GEMM_MODE
+
+
+_state = {}
+
+
+def _dev_state(device):
+    """Per-device scratch: recurrence step counters, barrier error flag, reduction partials."""
+    key = str(device)
+    if key not in _state:
+        _state[key] = dict(ctr=torch.zeros(4096, dtype=torch.int32, device=device),
+                           err=torch.zeros(1, dtype=torch.int32, device=device),
+                           partials=torch.zeros(512, dtype=torch.float32, device=device),
+                           one=torch.ones(1, dtype=torch.float32, device=device))
+    return _state[key]
+
+
+def check_device_errors(device):
+    """Raises if a persistent-kernel step barrier ever timed out (host sync)."""
+    st = _dev_state(device)
+    if int(st["err"].item()) != 0:
+        raise RuntimeError("e2e_asr_b200: a recurrence step barrier timed out on the device")
+
+
+def host_array(t):
+    """Host copy of a small integer tensor (lengths).  Tensors produced by
+    Seq2SeqModel.get_batch carry `_host` so no device sync is needed."""
+    h = getattr(t, "_host", None)
+    if h is not None:
+        return h
+    return t.detach().cpu().numpy()
+
+
+def to_i32(t, device):
+    c = getattr(t, "_i32", None)
+    if c is not None and c.device == torch.device(device):
+        return c
+    r = t.detach().to(device=device, dtype=torch.int32).contiguous()
+    try:
+        t._i32 = r
+    except Exception:
+        pass
+    return r
+
+
+def gemm(a, b, out=None, ta=False, tb=False, bias=None, z=None, accumulate=False, mode=None):
+    """out = op(a) @ op(b) (+bias) (+z) (+out).  2-D tensors with unit inner stride;
+    the leading dimension is the row stride, so column-sliced views work."""
+    assert a.dim() == 2 and b.dim() == 2 and a.stride(1) == 1 and b.stride(1) == 1
+    M, K = (a.shape[1], a.shape[0]) if ta else (a.shape[0], a.shape[1])
+    Kb, N = (b.shape[1], b.shape[0]) if tb else (b.shape[0], b.shape[1])
+    assert K == Kb, (a.shape, b.shape, ta, tb)
+    if out is None:
+        assert not accumulate
+        out = torch.empty((M, N), dtype=torch.float32, device=a.device)
+    assert out.shape[0] == M and out.shape[1] == N and out.stride(1) == 1
+    lda = a.stride(0) if a.shape[0] > 1 else max(a.shape[1], 1)
+    ldb = b.stride(0) if b.shape[0] > 1 else max(b.shape[1], 1)
+    ldc = out.stride(0) if out.shape[0] > 1 else max(out.shape[1], 1)
+    ldz = 0
+    if z is not None:
+        assert z.stride(1) == 1
+        ldz = z.stride(0) if z.shape[0] > 1 else z.shape[1]
+    call("e2e_gemm", _GEMM_MODE if mode is None else mode, int(ta), int(tb), M, N, K, a, lda, b, ldb, out, ldc,
+         bias, z, ldz, int(accumulate))
+    return out
+
+
+def colsum(x, out=None, accumulate=False):
+    assert x.dim() == 2 and x.stride(1) == 1
+    if out is None:
+        out = torch.empty((x.shape[1],), dtype=torch.float32, device=x.device)
+    call("e2e_colsum", x.shape[0], x.shape[1], x, x.stride(0) if x.shape[0] > 1 else x.shape[1], out,
+         int(accumulate))
+    return out
+
+
+def flat_rows(x):
+    """For a 3-D activations tensor (any of: contiguous, a time-narrowed view of a
+    padded [B,Tp,D] buffer, or the transpose of one) return (flat2d, r0, r1):
+    flat2d is a [rows, D] view of the underlying memory and element (i, j, :) of
+    x is row i*r0 + j*r1 of it.  Lets GEMMs run over the padded buffer with no
+    copy while the public tensors keep the reference's shapes."""
+    assert x.dim() == 3 and x.stride(2) == 1
+    D = x.shape[2]
+    s0, s1 = x.stride(0), x.stride(1)
+    if x.shape[0] == 1:
+        s0 = x.shape[1] * s1 if s1 % D == 0 else D
+    if x.shape[1] == 1:
+        s1 = D
+    if s0 % D or s1 % D:
+        x = x.contiguous()
+        s0, s1 = x.stride(0), x.stride(1)
+    r0, r1 = s0 // D, s1 // D
+    avail = (x.untyped_storage().nbytes() // 4 - x.storage_offset()) // D
+    if r0 >= r1:
+        rows = min(avail, x.shape[0] * r0)
+    else:
+        rows = min(avail, x.shape[1] * r1)
+    need = (x.shape[0] - 1) * r0 + (x.shape[1] - 1) * r1 + 1
+    assert rows >= need
+    flat = torch.as_strided(x, (rows, D), (D, 1), x.storage_offset())
+    return flat, r0, r1
+
+
+# ---------------------------------------------------------------------------
+# Encoder layer
+# ---------------------------------------------------------------------------
+
+def _pack_lstm(kernels, biases, I, H, device):
+    """TF (gate-blocked) kernels of each direction -> packed Wx [I, nd*4H], Wh [nd,H,4H], bias [nd*4H]."""
+    nd = len(kernels)
+    Wx = torch.empty((I, nd * 4 * H), dtype=torch.float32, device=device)
+    Wh = torch.empty((nd, H, 4 * H), dtype=torch.float32, device=device)
+    bp = torch.empty((nd * 4 * H,), dtype=torch.float32, device=device)
+    for d in range(nd):
+        call("e2e_lstm_pack_weights", I, H, kernels[d], biases[d], Wx, nd * 4 * H, d * 4 * H, Wh[d], bp)
+    return Wx, Wh, bp
+
+
+def _unpack_lstm(dWx, dWh, dbp, I, H, nd, device):
+    outs = []
+    for d in range(nd):
+        dk = torch.empty((I + H, 4 * H), dtype=torch.float32, device=device)
+        db = torch.empty((4 * H,), dtype=torch.float32, device=device)
+        call("e2e_lstm_unpack_grads", I, H, dk, db, dWx, nd * 4 * H, d * 4 * H, dWh[d], dbp, 0)
+        outs += [dk, db]
+    return outs
+
+
+class BiLSTMLayerFn(torch.autograd.Function):
+    """One bidirectional LSTM encoder layer over a zero-padded batch-major buffer
+    (reference Encoder._layer_encoder_input, encoder.py:55-91).
+
+    x: [B, Tp, I] contiguous with Tp >= max(len)+1; returns [B, Tp, 2H] (fw | bw),
+    zero for t >= len.  The pyramid (encoder.py:94-119) is then a free reshape.
+    """
+
+    @staticmethod
+    def forward(ctx, x, k_fw, b_fw, k_bw, b_bw, lens_i32, T):
+        B, Tp, I = x.shape
+        H = k_fw.shape[1] // 4
+        dev = x.device
+        assert x.is_contiguous() and Tp >= T + 1
+        st = _dev_state(dev)
+        Wx, Wh, bp = _pack_lstm([k_fw, k_bw], [b_fw, b_bw], I, H, dev)
+        x2 = x.view(B * Tp, I)
+        G = gemm(x2, Wx, bias=bp)                                   # [B*Tp, 8H]
+        out = torch.zeros((B, Tp, 2 * H), dtype=torch.float32, device=dev)
+        Cst = torch.empty((B, Tp, 2, H), dtype=torch.float32, device=dev)
+        call("e2e_lstm_rec_fwd", B, T, Tp, H, 2, Tp, 1, G, out, Cst, Wh, lens_i32, st["ctr"],
+             st["ctr"].numel() * 4, st["err"])
+        ctx.save_for_backward(x, Wx, Wh, G, Cst, out, lens_i32)
+        ctx.dims = (B, Tp, I, H, T)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        x, Wx, Wh, G, Cst, out, lens_i32 = ctx.saved_tensors
+        B, Tp, I, H, T = ctx.dims
+        dev = x.device
+        st = _dev_state(dev)
+        dout = dout.contiguous()
+        call("e2e_lstm_rec_bwd", B, T, Tp, H, 2, Tp, 1, G, Cst, Wh, dout, lens_i32, st["ctr"],
+             st["ctr"].numel() * 4, st["err"])                     # G now holds d(pre-activations)
+        N = B * Tp
+        x2, o2 = x.view(N, I), out.view(N, 2 * H)
+        dX = gemm(G, Wx, tb=True).view(B, Tp, I) if ctx.needs_input_grad[0] else None
+        dWx = gemm(x2, G, ta=True)                                  # [I, 8H]
+        dWh = torch.empty((2, H, 4 * H), dtype=torch.float32, device=dev)
+        # h_{t-1}^T dz_t: fw pairs out[t-1] with dz[t], bw pairs out[t+1] with dz[t]; the flat
+        # one-row shift never crosses an utterance because out[b, Tp-1] == 0 and dz[b, Tp-1] == 0.
+        gemm(o2[:N - 1, 0:H], G[1:, 0:4 * H], ta=True, out=dWh[0])
+        gemm(o2[1:, H:2 * H], G[:N - 1, 4 * H:8 * H], ta=True, out=dWh[1])
+        dbp = colsum(G)
+        dk_fw, db_fw, dk_bw, db_bw = _unpack_lstm(dWx, dWh, dbp, I, H, 2, dev)
+        return dX, dk_fw, db_fw, dk_bw, db_bw, None, None
+
+
+# ---------------------------------------------------------------------------
+# Attention decoder (teacher forced)
+# ---------------------------------------------------------------------------
+
+class AttnDecoderFn(torch.autograd.Function):
+    """AttnDecoder.__call__ under teacher forcing (attn_decoder.py:37-172; step
+    order SURVEY.md A.4).  Everything that does not depend on the decoder state is
+    batched over all U steps (embedding, LM-LSTM, lm half of InputProjection,
+    hidden_features, AttnProjection, OutputProjection); only
+    xin -> dec-LSTM -> attention runs step by step (e2e_decoder_loop_*)."""
+
+    @staticmethod
+    def forward(ctx, enc, emb, attn_w, attn_v, lm_k, lm_b, dec_k, dec_b, q_k, q_b, ap_k, ap_b, out_k, out_b,
+                in_k, in_b, sp_k, sp_b, ids, lens_i32, enc_len_i32, U, stash):
+        dev = enc.device
+        st = _dev_state(dev)
+        B, Tn, D = enc.shape
+        V, E = emb.shape
+        Hl, Hd, A = lm_k.shape[1] // 4, dec_k.shape[1] // 4, q_k.shape[1]
+        f32 = dict(dtype=torch.float32, device=dev)
+        enc_flat, r0, r1 = flat_rows(enc)
+        assert r1 == 1, "encoder states must be batch-major"
+        Tp = r0
+        ids = ids[:U].contiguous()
+        # --- state-independent, batched over all steps
+        u = torch.empty((U * B, E), **f32)
+        call("e2e_embed_gather", U * B, E, emb, ids, u)
+        Wx_lm, Wh_lm, bp_lm = _pack_lstm([lm_k], [lm_b], E, Hl, dev)
+        G_lm = gemm(u, Wx_lm, bias=bp_lm)                            # [U*B, 4Hl]
+        hl = torch.zeros((U * B, Hl), **f32)
+        C_lm = torch.empty((U * B, Hl), **f32)
+        call("e2e_lstm_rec_fwd", B, U, U, Hl, 1, 1, B, G_lm, hl, C_lm, Wh_lm, lens_i32, st["ctr"],
+             st["ctr"].numel() * 4, st["err"])
+        m = gemm(hl, sp_k, bias=sp_b) if sp_k is not None else hl    # SimpleProjection (:149-151)
+        pre = gemm(m, in_k[:Hd], bias=in_b)                          # lm half of InputProjection (:157-158)
+        HF = gemm(enc_flat, attn_w.view(D, A))                       # hidden_features (:70-73), padded rows too
+        # --- sequential loop
+        a = _lib.DecLoopFwdArgs()
+        a.B, a.U, a.E, a.Hd, a.A, a.D, a.Tn, a.Tp, a.gemm_mode = B, U, E, Hd, A, D, Tn, Tp, _GEMM_MODE
+        bufs = dict(xh=torch.zeros((U * B, E + Hd), **f32), cprev=torch.zeros((U * B, Hd), **f32),
+                    acts=torch.empty((U * B, 4 * Hd), **f32), cat=torch.empty((U * B, Hd + D), **f32),
+                    y=torch.empty((U * B, A), **f32), alpha=torch.empty((U * B, Tn), **f32),
+                    gates_tmp=torch.empty((B, 4 * Hd), **f32))
+        ptrs = dict(in_k=in_k, dec_k=dec_k, dec_b=dec_b, q_k=q_k, q_b=q_b, attn_v=attn_v, pre=pre, HF=HF,
+                    enc=enc_flat, enc_len=enc_len_i32, lens=lens_i32, **bufs)
+        for k, v in ptrs.items():
+            setattr(a, k, v.data_ptr())
+        call("e2e_decoder_loop_fwd", a)
+        proj = gemm(bufs["cat"], ap_k, bias=ap_b)                     # AttnProjection (:116-118)
+        logits = gemm(proj, out_k, bias=out_b)                        # OutputProjection (:124-125)
+        call("e2e_mask_rows", U, B, V, logits, lens_i32)              # raw_rnn zeroes finished rows
+        ctx.save_for_backward(enc, emb, attn_w, attn_v, lm_k, dec_k, dec_b, q_k, q_b, ap_k, out_k, in_k, sp_k,
+                              ids, lens_i32, enc_len_i32, u, Wx_lm, Wh_lm, G_lm, hl, C_lm, m, pre, HF, proj,
+                              bufs["xh"], bufs["cprev"], bufs["acts"], bufs["cat"], bufs["y"], bufs["alpha"],
+                              bufs["gates_tmp"])
+        ctx.dims = (B, Tn, D, V, E, Hl, Hd, A, U, Tp)
+        ctx.stash = stash
+        return logits
+
+    @staticmethod
+    def backward(ctx, dlogits):
+        (enc, emb, attn_w, attn_v, lm_k, dec_k, dec_b, q_k, q_b, ap_k, out_k, in_k, sp_k, ids, lens_i32,
+         enc_len_i32, u, Wx_lm, Wh_lm, G_lm, hl, C_lm, m, pre, HF, proj, xh, cprev, acts, cat, y, alpha,
+         gates_tmp) = ctx.saved_tensors
+        B, Tn, D, V, E, Hl, Hd, A, U, Tp = ctx.dims
+        dev = enc.device
+        st = _dev_state(dev)
+        f32 = dict(dtype=torch.float32, device=dev)
+        dlogits = dlogits.contiguous()
+        enc_flat, _, _ = flat_rows(enc)
+        # batched projections
+        dout_k = gemm(proj, dlogits, ta=True)
+        dout_b = colsum(dlogits)
+        dproj = gemm(dlogits, out_k, tb=True)
+        dap_k = gemm(cat, dproj, ta=True)
+        dap_b = colsum(dproj)
+        dcat = gemm(dproj, ap_k, tb=True)                             # [U*B, Hd+D]
+        # sequential loop
+        g = _lib.DecLoopBwdArgs()
+        a = g.f
+        a.B, a.U, a.E, a.Hd, a.A, a.D, a.Tn, a.Tp, a.gemm_mode = B, U, E, Hd, A, D, Tn, Tp, _GEMM_MODE
+        for k, v in dict(in_k=in_k, dec_k=dec_k, dec_b=dec_b, q_k=q_k, q_b=q_b, attn_v=attn_v, pre=pre, HF=HF,
+                         enc=enc_flat, enc_len=enc_len_i32, lens=lens_i32, xh=xh, cprev=cprev, acts=acts,
+                         cat=cat, y=y, alpha=alpha, gates_tmp=gates_tmp).items():
+            setattr(a, k, v.data_ptr())
+        nrows = enc_flat.shape[0]
+        out = dict(dcat=dcat, dgates=torch.empty((U * B, 4 * Hd), **f32), dxh=torch.empty((U * B, E + Hd), **f32),
+                   dy=torch.empty((U * B, A), **f32), dv_part=torch.zeros((B, A), **f32),
+                   dHF=torch.zeros((nrows, A), **f32), denc=torch.zeros((nrows, D), **f32),
+                   dc_carry=torch.zeros((B, Hd), **f32))
+        for k, v in out.items():
+            setattr(g, k, v.data_ptr())
+        call("e2e_decoder_loop_bwd", g)
+        dgates, dxh, dy, dHF, denc = out["dgates"], out["dxh"], out["dy"], out["dHF"], out["denc"]
+        dq_k = gemm(cat[:, :Hd], dy, ta=True)
+        dq_b = colsum(dy)
+        dattn_v = colsum(out["dv_part"])
+        ddec_k = gemm(xh, dgates, ta=True)
+        ddec_b = colsum(dgates)
+        dxin = dxh[:, :E]
+        din_k = torch.zeros((Hd + D, E), **f32)
+        gemm(m, dxin, ta=True, out=din_k[:Hd])
+        if U > 1:   # ctx_{t-1} pairs with dxin_t: time-major rows shift by B
+            gemm(cat[:(U - 1) * B, Hd:], dxin[B:], ta=True, out=din_k[Hd:])
+        din_b = colsum(dxin)
+        dm = gemm(dxin, in_k[:Hd], tb=True)                           # [U*B, Hd]
+        dsp_k = dsp_b = None
+        if sp_k is not None:
+            dsp_k = gemm(hl, dm, ta=True)
+            dsp_b = colsum(dm)
+            dm = gemm(dm, sp_k, tb=True)
+        # LM-LSTM backward (time-major rows: b stride 1, t stride B)
+        call("e2e_lstm_rec_bwd", B, U, U, Hl, 1, 1, B, G_lm, C_lm, Wh_lm, dm, lens_i32, st["ctr"],
+             st["ctr"].numel() * 4, st["err"])
+        dWx_lm = gemm(u, G_lm, ta=True)
+        dWh_lm = torch.zeros((1, Hl, 4 * Hl), **f32)
+        if U > 1:
+            gemm(hl[:(U - 1) * B], G_lm[B:], ta=True, out=dWh_lm[0])
+        dbp_lm = colsum(G_lm)
+        dlm_k, dlm_b = _unpack_lstm(dWx_lm, dWh_lm, dbp_lm, E, Hl, 1, dev)
+        du = gemm(G_lm, Wx_lm, tb=True)                               # [U*B, E] = IndexedSlices values
+        demb = torch.zeros((V, E), **f32)
+        call("e2e_embed_scatter_add", U * B, E, demb, ids, du, E)
+        if ctx.stash is not None:
+            # tf.global_norm takes the embedding gradient's IndexedSlices values
+            ctx.stash["emb_values"] = du
+        # hidden_features = enc (*) AttnW
+        dattn_w = gemm(enc_flat, dHF, ta=True).view(attn_w.shape)
+        gemm(dHF, attn_w.view(D, A), tb=True, out=denc, accumulate=True)
+        denc_view = torch.as_strided(denc, (B, Tn, D), (Tp * D, D, 1)) if ctx.needs_input_grad[0] else None
+        return (denc_view, demb, dattn_w, dattn_v, dlm_k, dlm_b, ddec_k, ddec_b, dq_k, dq_b, dap_k, dap_b, dout_k,
+                dout_b, din_k, din_b, dsp_k, dsp_b, None, None, None, None, None)
+
+
+# ---------------------------------------------------------------------------
+# Losses
+# ---------------------------------------------------------------------------
+
+class CrossEntropyFn(torch.autograd.Function):
+    """LossUtils.cross_entropy_loss (losses.py:6-35)."""
+
+    @staticmethod
+    def forward(ctx, logits, targets, lens_i32):
+        U, B = targets.shape
+        V = logits.shape[1]
+        dev = logits.device
+        logits = logits.contiguous()
+        targets = targets.contiguous()
+        lse = torch.empty((U * B,), dtype=torch.float32, device=dev)
+        cost = torch.empty((U * B,), dtype=torch.float32, device=dev)
+        loss = torch.empty((1,), dtype=torch.float32, device=dev)
+        call("e2e_ce_fwd", U, B, V, logits, targets, lens_i32, lse, cost, loss)
+        ctx.save_for_backward(logits, targets, lens_i32, lse)
+        return loss.view(())
+
+    @staticmethod
+    def backward(ctx, g):
+        logits, targets, lens_i32, lse = ctx.saved_tensors
+        U, B = targets.shape
+        V = logits.shape[1]
+        d = torch.empty_like(logits)
+        g = g.contiguous().view(1).to(torch.float32)
+        call("e2e_ce_bwd", U, B, V, logits, targets, lens_i32, lse, g, d)
+        return d, None, None
+
+
+class CTCHeadFn(torch.autograd.Function):
+    """Auxiliary CTC head on an encoder layer: logits = states.W + b, then
+    tf.nn.ctc_loss semantics (blank = C-1), mean over the batch.
+    states: [B,T,D] (or its [T,B,D] transpose view) over a padded buffer."""
+
+    @staticmethod
+    def forward(ctx, states, kernel, bias, in_lens_i32, labels, label_lens_i32, max_label_len, stash):
+        dev = states.device
+        f32 = dict(dtype=torch.float32, device=dev)
+        flat, r0, r1 = flat_rows(states)
+        if r0 >= r1:     # batch-major [B,T,D]
+            B, T = states.shape[0], states.shape[1]
+            sb, stt = r0, r1
+        else:            # time-major view [T,B,D]
+            T, B = states.shape[0], states.shape[1]
+            sb, stt = r1, r0
+        C = kernel.shape[1]
+        rows = flat.shape[0]
+        logits = gemm(flat, kernel, bias=bias)                         # [rows, C]
+        lse = torch.empty((rows,), **f32)
+        call("e2e_row_lse", rows, C, logits, C, lse)
+        labels = labels.contiguous()
+        S = 2 * max_label_len + 1
+        alpha_ws = torch.empty((B * T * S,), **f32)
+        loss_b = torch.empty((B,), **f32)
+        grad = torch.zeros((rows, C), **f32)
+        call("e2e_ctc_fwd_grad", T, B, C, sb, stt, logits, lse, in_lens_i32, labels, labels.stride(0),
+             label_lens_i32, max_label_len, alpha_ws, loss_b, grad, 1.0 / B)
+        loss = torch.empty((1,), **f32)
+        call("e2e_mean", B, loss_b, loss)
+        ctx.save_for_backward(states, kernel, grad)
+        if stash is not None:
+            stash["logits"] = logits
+            stash["loss_b"] = loss_b
+            stash["layout"] = (B, T, sb, stt)
+        return loss.view(())
+
+    @staticmethod
+    def backward(ctx, g):
+        states, kernel, grad = ctx.saved_tensors
+        flat, r0, r1 = flat_rows(states)
+        g = g.contiguous().view(1).to(torch.float32)
+        call("e2e_scale", grad.numel(), grad, g, 1.0)                  # grad *= upstream (in place)
+        dk = gemm(flat, grad, ta=True)
+        db = colsum(grad)
+        dst = None
+        if ctx.needs_input_grad[0]:
+            dflat = gemm(grad, kernel, tb=True)
+            D = states.shape[2]
+            dst = torch.as_strided(dflat, states.shape, (r0 * D, r1 * D, 1))
+        return dst, dk, db, None, None, None, None, None
+
+
+def prepare_input(x, Tp, stack=1, stride=1):
+    """get_batch frame stacking + initial striding + zero padding (one kernel)."""
+    B, T, F = x.shape
+    out = torch.empty((B, Tp, F * stack), dtype=torch.float32, device=x.device)
+    call("e2e_prepare_input", B, T, F, Tp, stack, stride, x.contiguous(), out)
+    return out

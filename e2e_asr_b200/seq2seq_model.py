@@ -1,0 +1,241 @@
+"""Seq2SeqModel: the multitask attention encoder-decoder training step.
+
+Keeps the reference's constructor, hyper-parameters and public attributes
+(seq2seq_model.py:26-216): `Seq2SeqModel(data_iter, isTraining, params)` builds the
+model and runs `create_computational_graph()` on the next batch of `data_iter`
+(TF built a graph once and re-ran it; here every call to
+`create_computational_graph()` / `run_step()` executes one step eagerly on the
+GPU), leaving `encoder_inputs, decoder_inputs, seq_len, seq_len_target, targets,
+encoder_hidden_states, time_major_states, seq_len_encs, outputs, losses,
+total_loss, updates` behind.
+
+Additions the north-star asks for (absent from the reference):
+auxiliary CTC heads on lower encoder layers (`params.ctc_tasks`), and data-parallel
+gradient averaging over NCCL (`dist.GradAllReducer`).  The Adam update
+(seq2seq_model.py:137,153-155) is not built yet: `updates` holds the clipped
+gradients.
+"""
+import numpy as np
+import torch
+
+from . import ops
+from ._lib import call
+from .attn_decoder import AttnDecoder
+from .base_params import BaseParams, Bunch
+from .encoder import Encoder
+from .losses import LossUtils
+from .tf_utils import create_shifted_targets
+from .variables import VariableStore
+
+
+class Seq2SeqModel(BaseParams):
+    """Implements the Attention-Enabled Encoder-Decoder model."""
+
+    @classmethod
+    def class_params(cls):
+        params = Bunch()
+        # Task specification (seq2seq_model.py:31-35)
+        params['tasks'] = ['char']
+        params['num_layers'] = {'char': 4}
+        params['max_output'] = {'char': 120}
+        # Optimization params
+        params['learning_rate'] = 1e-3
+        params['learning_rate_decay_factor'] = 0.5
+        params['max_gradient_norm'] = 5.0
+        # Loss params
+        params['avg'] = True
+        params['encoder_params'] = Encoder.class_params()
+        params['decoder_params'] = {'char': AttnDecoder.class_params()}
+        # --- additions (not in the reference) ---
+        # auxiliary CTC heads: task -> vocabulary size (blank is added as the last class);
+        # the encoder depth comes from num_layers[task]; labels from batch[task], batch[task+"_len"]
+        params['ctc_tasks'] = {}
+        # tf.clip_by_global_norm sees the embedding gradient as IndexedSlices
+        params['tf_indexed_slices_norm'] = True
+        return params
+
+    def __init__(self, data_iter, isTraining=True, params=None, variables=None, device="cuda", reducer=None):
+        self.params = self.class_params() if params is None else params
+        params = self.params
+        self.device = torch.device(device)
+        self.variables = variables if variables is not None else VariableStore(self.device)
+        self.encoder = Encoder(isTraining=isTraining, params=params.encoder_params, variables=self.variables)
+        self.decoder = {}
+        for task in params.tasks:
+            self.decoder[task] = AttnDecoder(isTraining=isTraining, params=params.decoder_params[task],
+                                             scope=task, variables=self.variables)
+        self.data_iter = data_iter
+        self.isTraining = isTraining
+        self.reducer = reducer
+        self.learning_rate = float(params.learning_rate)
+        self.global_step = 0
+        self.epoch = 0
+        self._pinned = {}
+        self._sq = torch.zeros(1, dtype=torch.float32, device=self.device)
+        self._sq_emb = torch.zeros(1, dtype=torch.float32, device=self.device)
+        self.grad_norm = torch.zeros(1, dtype=torch.float32, device=self.device)
+        self.ctc_stash = {}
+        if data_iter is not None:
+            self.create_computational_graph()
+
+    # learning-rate / epoch bookkeeping ops of seq2seq_model.py:74-83
+    def learning_rate_decay_op(self):
+        self.learning_rate *= self.params.learning_rate_decay_factor
+        return self.learning_rate
+
+    def epoch_incr(self):
+        self.epoch += 1
+        return self.epoch
+
+    # ------------------------------------------------------------------
+    def _to_device(self, key, arr, dtype):
+        """Host array -> device through a reusable pinned staging buffer."""
+        if isinstance(arr, torch.Tensor):
+            if arr.device == self.device:
+                return arr.to(dtype)
+            arr = arr.numpy()
+        arr = np.ascontiguousarray(arr)
+        t = torch.from_numpy(arr)
+        if t.dtype != dtype:
+            t = t.to(dtype)
+        buf = self._pinned.get(key)
+        if buf is None or buf.shape != t.shape or buf.dtype != dtype:
+            buf = torch.empty(t.shape, dtype=dtype).pin_memory()
+            self._pinned[key] = buf
+        buf.copy_(t)
+        return buf.to(self.device, non_blocking=True)
+
+    def _len_tensor(self, key, arr):
+        host = np.asarray(arr.cpu().numpy() if isinstance(arr, torch.Tensor) else arr, np.int64)
+        t = self._to_device(key, host, torch.int64)
+        t._host = host
+        t._i32 = self._to_device(key + "/i32", host.astype(np.int32), torch.int32)
+        return t
+
+    def get_batch(self, batch):
+        """Get a batch from the iterator (seq2seq_model.py:159-197).  Frame stacking
+        (:164-183) is fused into the encoder's input staging kernel."""
+        encoder_inputs = self._to_device("logmel", batch["logmel"], torch.float32)
+        encoder_len = self._len_tensor("logmel_len", batch["logmel_len"])
+        decoder_inputs, decoder_len = {}, {}
+        for task in self.params.tasks:
+            ids = batch[task]
+            ids = ids.cpu().numpy() if isinstance(ids, torch.Tensor) else np.asarray(ids)
+            decoder_inputs[task] = self._to_device(task, np.ascontiguousarray(ids.T), torch.int64)   # time major (:189)
+            ln = batch[task + "_len"]
+            if not self.isTraining:                                                                  # (:191-193)
+                ln = np.ones_like(np.asarray(ln)) * self.params.max_output[task]
+            decoder_len[task] = self._len_tensor(task + "_len", ln)
+        for task in self.params.ctc_tasks:
+            decoder_inputs[task] = self._to_device(task, batch[task], torch.int64)                   # [B, Lmax] labels
+            decoder_len[task] = self._len_tensor(task + "_len", batch[task + "_len"])
+        if not self.isTraining and "utt_id" in batch:
+            decoder_inputs["utt_id"] = batch["utt_id"]
+        return [encoder_inputs, decoder_inputs, encoder_len, decoder_len]
+
+    # ------------------------------------------------------------------
+    def create_computational_graph(self, batch=None):
+        """One step (seq2seq_model.py:88-157)."""
+        params = self.params
+        if batch is None:
+            batch = self.data_iter.get_next()
+        self.encoder_inputs, self.decoder_inputs, self.seq_len, self.seq_len_target = self.get_batch(batch)
+
+        self.targets, self.target_weights = {}, {}
+        for task in params.tasks:
+            self.targets[task], self.target_weights[task] = create_shifted_targets(
+                self.decoder_inputs[task], self.seq_len_target[task]) if self.isTraining else (None, None)
+
+        if self.isTraining:
+            self.variables.zero_grad()
+        depth_of = dict((t, params.num_layers[t]) for t in list(params.tasks) + list(params.ctc_tasks))
+        ctx = torch.enable_grad() if self.isTraining else torch.no_grad()
+        with ctx:
+            self.encoder_hidden_states, self.time_major_states, self.seq_len_encs = \
+                self.encoder(self.encoder_inputs, self.seq_len, depth_of)
+
+            self.outputs = {}
+            for task in params.tasks:
+                d = params.num_layers[task]
+                self.outputs[task] = self.decoder[task](
+                    self.decoder_inputs[task], self.seq_len_target[task],
+                    self.encoder_hidden_states[d], self.seq_len_encs[d])
+
+            if not self.isTraining:
+                return
+            self.losses = {}
+            for task in params.tasks:
+                self.losses[task] = LossUtils.cross_entropy_loss(
+                    self.outputs[task], self.targets[task], self.seq_len_target[task])
+            for task, vocab in params.ctc_tasks.items():
+                d = params.num_layers[task]
+                D = self.time_major_states[d].shape[2]
+                k = self.variables.get("model/ctc_%s/kernel" % task, (D, vocab + 1))
+                b = self.variables.get("model/ctc_%s/bias" % task, (vocab + 1,), ("zeros",))
+                self.ctc_stash[task] = {}
+                self.losses[task] = LossUtils.ctc_head_loss(
+                    self.time_major_states[d], k, b, self.seq_len_encs[d], self.decoder_inputs[task],
+                    self.seq_len_target[task], self.ctc_stash[task])
+
+            # Add losses across the tasks (:140-144)
+            self.total_loss = 0.0
+            for task in self.losses:
+                self.total_loss = self.total_loss + self.losses[task]
+            if params.avg:
+                self.total_loss = self.total_loss / float(len(self.losses))
+
+        # Gradients, clipping (:148-151).  Adam (:137,153-155) is the "next" row.
+        self.total_loss.backward()
+        if self.reducer is not None:
+            self.reducer.allreduce_mean(self.variables.flat_grads())
+        self.clip_gradients()
+        self.updates = self.variables
+        self.global_step += 1
+
+    run_step = create_computational_graph
+
+    def clip_gradients(self):
+        """tf.clip_by_global_norm(gradients, max_gradient_norm) over the flat buffer.
+        With `tf_indexed_slices_norm` the embedding gradient enters the norm as TF's
+        IndexedSlices values (one row per looked-up token, duplicates not summed)."""
+        vs = self.variables
+        st = ops._dev_state(self.device)
+        g = vs.flat_grads()
+        call("e2e_sumsq", g.numel(), g, st["partials"], self._sq, 1.0, 0)
+        if self.params.tf_indexed_slices_norm:
+            first = True
+            for task in self.params.tasks:
+                du = self.decoder[task].stash.get("emb_values")
+                if du is None:
+                    continue
+                ge = vs.grad(self.decoder[task].scope_name() + "/decoder/embedding")
+                call("e2e_sumsq", ge.numel(), ge, st["partials"], self._sq, -1.0, 1)
+                call("e2e_sumsq", du.numel(), du, st["partials"], self._sq_emb, 1.0, 0 if first else 1)
+                first = False
+            if not first:
+                n = 1
+                if self.reducer is not None:       # values of all ranks, each scaled by 1/n
+                    self.reducer.allreduce_sum(self._sq_emb)
+                    n = self.reducer.world_size
+                call("e2e_axpy", 1, 1.0 / (n * n), self._sq_emb, self._sq)
+        call("e2e_clip_by_norm", g.numel(), g, self._sq, float(self.params.max_gradient_norm), self.grad_norm)
+
+    def gradients(self):
+        """Clipped gradients keyed by TF variable name (host copies)."""
+        return {n: self.variables.grad(n).detach().cpu().numpy().copy() for n in self.variables.names()}
+
+    @classmethod
+    def add_parse_options(cls, parser):
+        # flag names and defaults of seq2seq_model.py:199-216
+        parser.add_argument("-tasks", "--tasks", default="", type=str, help="Auxiliary task choices")
+        parser.add_argument("-nlc", "--num_layers_char", default=4, type=int,
+                            help="Output layer of encoder which is used for char.")
+        parser.add_argument("-nlp", "--num_layers_phone", default=3, type=int,
+                            help="Output layer of encoder which is used for phone.")
+        parser.add_argument("-max_out_char", "--max_output_char", default=120, type=int,
+                            help="Maximum length of char/word-piece sequence")
+        parser.add_argument("-max_out_phone", "--max_output_phone", default=250, type=int,
+                            help="Maximum length of phone sequence")
+        parser.add_argument("-lr_decay", "--learning_rate_decay_factor", default=0.5, type=float,
+                            help="Learning rate decay factor")
+        parser.add_argument("-avg", "--avg", default=False, action="store_true", help="Average the loss")

@@ -1,0 +1,75 @@
+"""Helpers shared by tests, smoke() and bench.py: build a Seq2SeqModel for a
+synthetic config and compare one step against an oracle result dict.  (The
+oracle itself is NOT imported here; callers pass its output in.)"""
+import copy
+
+import numpy as np
+import torch
+
+from . import synth
+from .seq2seq_model import Seq2SeqModel
+from .variables import VariableStore
+
+
+def model_params(cfg, tasks=("char",), ctc=True, avg=True):
+    p = Seq2SeqModel.class_params()
+    p.tasks = list(tasks)
+    p.num_layers = {t: cfg.L for t in tasks}
+    p.max_output = {t: cfg.U for t in tasks}
+    p.avg = avg
+    ep = p.encoder_params
+    ep.hidden_size, ep.use_lstm, ep.out_prob = cfg.H, True, 1.0
+    dp = {}
+    for t in tasks:
+        d = copy.deepcopy(p.decoder_params["char"])
+        d.out_prob_dec, d.samp_prob = 1.0, 0.0
+        d.hidden_size_dec, d.emb_size, d.vocab_size = cfg.Hd, cfg.E, cfg.V
+        d.attention_vec_size, d.lm_hidden_size, d.max_output = cfg.A, cfg.Hl, cfg.U
+        dp[t] = d
+    p.decoder_params = dp
+    p.ctc_tasks = {}
+    if ctc:
+        for t, (depth, vocab) in cfg.ctc.items():
+            p.ctc_tasks[t] = vocab
+            p.num_layers[t] = depth
+    return p
+
+
+def build_model(cfg, weights=None, device="cuda", isTraining=True, ctc=True, reducer=None, capacity=None):
+    if capacity is None:
+        n = sum(int(np.prod(v.shape)) + 4 for v in (weights or synth.make_weights(cfg)).values())
+        capacity = n + 1024
+    vs = VariableStore(device, capacity=capacity)
+    if weights is not None:
+        vs.load(weights)
+    return Seq2SeqModel(None, isTraining=isTraining, params=model_params(cfg, ctc=ctc), variables=vs,
+                        device=device, reducer=reducer)
+
+
+def rel_err(a, b):
+    a = np.asarray(a, np.float64)
+    b = np.asarray(b, np.float64)
+    return float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-30))
+
+
+def compare_step(model, ref, rtol=1e-4, check_logits=True):
+    """Asserts losses / logits / clipped grads of `model` (after run_step) match the
+    oracle dict `ref` within `rtol` (max-abs error relative to the tensor's max-abs,
+    the north-star's "1e-4 relative").  Returns the worst gradient error."""
+    for t, l in ref["losses"].items():
+        got = float(model.losses[t])
+        assert abs(got - l) <= rtol * max(1.0, abs(l)), ("loss", t, got, l)
+    assert abs(float(model.total_loss) - ref["total_loss"]) <= rtol * max(1.0, abs(ref["total_loss"]))
+    if check_logits:
+        for t in model.params.tasks:
+            e = rel_err(model.outputs[t].detach().cpu().numpy(), ref["logits"][t])
+            assert e <= rtol, ("logits", t, e)
+    norm = float(model.grad_norm)
+    assert abs(norm - ref["norm"]) <= rtol * max(1.0, ref["norm"]), ("norm", norm, ref["norm"])
+    worst = 0.0
+    grads = model.gradients()
+    for k, g in ref["clipped"].items():
+        e = rel_err(grads[k], g)
+        worst = max(worst, e)
+        assert e <= rtol, ("grad", k, e)
+    return worst

@@ -1,0 +1,160 @@
+/* e2e_asr_b200 -- C ABI of the B200-native kernels behind the reference's Python
+ * model API (shtoshni/e2e_asr).
+ *
+ * The reference has no FFI / plugin registry: its device
+ * maths are TensorFlow-1.x library ops called from Python.  Each entry point
+ * below therefore names the reference call site (file:line under
+ * /root/reference) whose TF op(s) it replaces.  INTEGRATION.md shows the ctypes
+ * binding a maintainer of the reference would add.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer borrowed from the caller (torch
+ *     allocations), fp32 unless stated; `ids`/`targets`/`labels` are int64 as in
+ *     the reference's batches (speech_dataset.py:17-24); `lens` arrays are int32.
+ *   - `stream` is a cudaStream_t; all work is enqueued on it; no host sync, no
+ *     allocation inside (scratch comes in through explicit workspace arguments).
+ *   - return value 0 = ok; non-zero = error, message from e2e_last_error().
+ *   - there is no CPU fallback: without a CUDA device every call fails.
+ */
+#ifndef E2E_ASR_B200_H
+#define E2E_ASR_B200_H
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+int e2e_version(void);
+const char* e2e_last_error(void);
+int e2e_sm_count(void);
+
+/* Dense contraction  C[M,N] = op(A) op(B) (+bias[N]) (+Z[M,N]) (+C)   row-major.
+ * Replaces every `_linear` / matmul / 1x1 conv2d on the path: attn_decoder.py:73
+ * (hidden_features), :80 (Attention), :117 (AttnProjection), :122-125
+ * (OutputProjection), :151 (SimpleProjection), :158 (InputProjection); the
+ * x-part of BasicLSTMCell's [x,h].K (encoder.py:77-81); and their gradients
+ * (tf.gradients, seq2seq_model.py:148).
+ * mode: 0 = fp32 FFMA (exact fp32), 1 = 3xTF32 tcgen05 (fp32-accurate tensor
+ * core), 2 = bf16 tcgen05.  Shapes a tensor-core mode cannot take fall back to
+ * mode 0 (still on the GPU). */
+int e2e_gemm(void* stream, int mode, int transA, int transB, int M, int N, int K,
+             const float* A, int lda, const float* B, int ldb, float* C, int ldc,
+             const float* bias, const float* Z, int ldz, int accumulate);
+
+/* out[N] (+)= column sums of X[M,N]  (bias gradients) */
+int e2e_colsum(void* stream, int M, int N, const float* X, int ldx, float* out, int accumulate);
+
+/* TF BasicLSTMCell variable layout <-> kernel layout.  `kernel` is the TF variable
+ * [(I+H),4H] with gate-blocked columns i|j|f|o (basic_lstm.py:17; Appendix B of
+ * SURVEY.md); packed: Wx[I][ldwx] at column col0 (gate-interleaved [unit][4]),
+ * Wh[H][H][4], bias_packed[col0 ...]. */
+int e2e_lstm_pack_weights(void* stream, int I, int H, const float* kernel, const float* bias,
+                          float* Wx, int ldwx, int col0, float* Wh, float* bias_packed);
+int e2e_lstm_unpack_grads(void* stream, int I, int H, float* dkernel, float* dbias,
+                          const float* dWx, int ldwx, int col0, const float* dWh,
+                          const float* dbias_packed, int accumulate);
+
+/* Persistent LSTM recurrence over all timesteps of one (bi)directional layer.
+ * Replaces tf.nn.bidirectional_dynamic_rnn / dynamic_rnn with sequence_length
+ * (encoder.py:77-89) and the decoder's lm_cell loop (attn_decoder.py:148).
+ * Row (b,t) of every [.,.,x] buffer is b*sb + t*st.  G [rows][ndir][H][4]: in =
+ * x-projection+bias, out = gate activations (fwd) / d pre-activations (bwd).
+ * Hout [rows][ndir*H] must be zero-initialised (rows with t >= len stay 0).
+ * ctr_ws: >= 4*ndir*ceil(B/4) bytes of scratch; err_flag: device int set to 1 if a
+ * step barrier ever times out. */
+int e2e_lstm_rec_fwd(void* stream, int B, int T, int Tp, int H, int ndir, long long sb, long long st,
+                     float* G, float* Hout, float* Cst, const float* Wh, const int* lens,
+                     void* ctr_ws, size_t ctr_ws_bytes, int* err_flag);
+int e2e_lstm_rec_bwd(void* stream, int B, int T, int Tp, int H, int ndir, long long sb, long long st,
+                     float* G, const float* Cst, const float* Wh, const float* dOut, const int* lens,
+                     void* ctr_ws, size_t ctr_ws_bytes, int* err_flag);
+
+/* Seq2SeqModel.get_batch frame stacking (seq2seq_model.py:164-183) + initial
+ * striding (encoder.py:149-153) + zero padding to Tp rows per utterance. */
+int e2e_prepare_input(void* stream, int B, int T, int F, int Tp, int stack, int stride,
+                      const float* in, float* out);
+
+/* embedding_lookup (decoder.py:101) and its IndexedSlices gradient */
+int e2e_embed_gather(void* stream, int n, int E, const float* emb, const long long* ids, float* out);
+int e2e_embed_scatter_add(void* stream, int n, int E, float* demb, const long long* ids,
+                          const float* dout, int ldd);
+
+/* The sequential part of AttnDecoder.__call__ (attn_decoder.py:76-166, raw_rnn
+ * loop; step order of SURVEY.md A.4) under teacher forcing, after the
+ * state-independent parts (embedding, LM-LSTM, the lm_output half of
+ * InputProjection) have been batched over all steps by the caller. */
+typedef struct {
+    int B, U, E, Hd, A, D, Tn, Tp;     /* Tn: attention length, Tp: rows per utterance in HF/enc */
+    int gemm_mode;
+    const float* in_k;     /* InputProjection/kernel  [Hd+D, E] */
+    const float* dec_k;    /* basic_lstm_cell_1/kernel [E+Hd, 4Hd] */
+    const float* dec_b;    /* [4Hd] */
+    const float* q_k;      /* Attention/kernel [Hd, A] */
+    const float* q_b;      /* [A] */
+    const float* attn_v;   /* AttnV [A] */
+    const float* pre;      /* [U,B,E]  lm_output . in_k[:Hd] + in_b */
+    const float* HF;       /* [B,Tp,A] hidden_features */
+    const float* enc;      /* [B,Tp,D] encoder states */
+    const int* enc_len;    /* [B] */
+    const int* lens;       /* [B] target lengths */
+    float* xh;             /* [U,B,E+Hd]  (xin_t | committed h_{t-1}); zero-initialised */
+    float* cprev;          /* [U,B,Hd]    committed c_{t-1};           zero-initialised */
+    float* acts;           /* [U,B,4Hd] */
+    float* cat;            /* [U,B,Hd+D]  (c_new_t | ctx_t) */
+    float* y;              /* [U,B,A] */
+    float* alpha;          /* [U,B,Tn] */
+    float* gates_tmp;      /* [B,4Hd] */
+} e2e_dec_loop_fwd_args;
+int e2e_decoder_loop_fwd(void* stream, const e2e_dec_loop_fwd_args* a);
+
+typedef struct {
+    e2e_dec_loop_fwd_args f;   /* same weights / saved tensors as the forward */
+    float* dcat;           /* [U,B,Hd+D] in: d(c_new|ctx) from AttnProjection; updated in place */
+    float* dgates;         /* [U,B,4Hd] out */
+    float* dxh;            /* [U,B,E+Hd] out: (dxin_t | dh_{t-1}) */
+    float* dy;             /* [U,B,A] out */
+    float* dv_part;        /* [B,A]    zero-initialised, accumulated */
+    float* dHF;            /* [B,Tp,A] zero-initialised, accumulated */
+    float* denc;           /* [B,Tp,D] accumulated into */
+    float* dc_carry;       /* [B,Hd]   zero-initialised scratch */
+} e2e_dec_loop_bwd_args;
+int e2e_decoder_loop_bwd(void* stream, const e2e_dec_loop_bwd_args* a);
+
+/* single kernels of the loop, exposed for inference (greedy / beam) and tests */
+int e2e_attn_fwd(void* stream, int B, int Tn, int Tp, int A, int D, const float* HF, const float* enc,
+                 const int* enc_len, const float* y, const float* v, float* alpha, float* ctx, int ldctx);
+int e2e_dec_pointwise_fwd(void* stream, int B, int H, int t, const float* gates_pre, const float* cprev,
+                          const float* hprev, int ldh, const int* lens, float* acts, float* cnew_out,
+                          int ldc, float* c_next, float* h_next, int ldhn, float* h_new_out);
+int e2e_mask_rows(void* stream, int U, int B, int V, float* logits, const int* lens);
+int e2e_argmax_rows(void* stream, int rows, int V, const float* x, int ldx, long long* out);
+
+/* LossUtils.cross_entropy_loss (losses.py:6-35): fwd writes lse[U*B], cost[U*B]
+ * and loss[0]; bwd writes dlogits = gscale[0] * dloss/dlogits. */
+int e2e_ce_fwd(void* stream, int U, int B, int V, const float* logits, const long long* targets,
+               const int* lens, float* lse, float* cost, float* loss);
+int e2e_ce_bwd(void* stream, int U, int B, int V, const float* logits, const long long* targets,
+               const int* lens, const float* lse, const float* gscale, float* dlogits);
+
+/* Auxiliary CTC on a lower encoder layer (north-star requirement; the reference
+ * only keeps the hook, encoder.py:143-144,160-161 / seq2seq_model.py:104).
+ * TF-1.x tf.nn.ctc_loss semantics, blank = C-1.  logits row (b,t) = b*sb + t*st.
+ * Writes loss_b[B] (= -log p) and grad = out_scale * d(loss_b)/dlogits. */
+int e2e_row_lse(void* stream, int rows, int V, const float* x, int ldx, float* lse);
+int e2e_ctc_fwd_grad(void* stream, int T, int B, int C, long long sb, long long st, const float* logits,
+                     const float* lse_rows, const int* in_lens, const long long* labels, int ldl,
+                     const int* label_lens, int max_label_len, float* alpha_ws, float* loss_b,
+                     float* grad, float out_scale);
+
+/* tf.clip_by_global_norm (seq2seq_model.py:150-151) on the flat gradient buffer */
+int e2e_sumsq(void* stream, size_t n, const float* x, float* partials296, float* out, float sign, int accumulate);
+int e2e_clip_by_norm(void* stream, size_t n, float* x, const float* sumsq, float clip, float* norm_out);
+int e2e_scale(void* stream, size_t n, float* x, const float* dev_scalar, float a);
+int e2e_mean(void* stream, int n, const float* x, float* out);
+int e2e_axpy(void* stream, size_t n, float a, const float* x, float* y);   /* y += a*x */
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* E2E_ASR_B200_H */

@@ -1,0 +1,171 @@
+"""Kernel-level parity on the GPU (through the C ABI) against the CPU oracle."""
+import numpy as np
+import pytest
+import torch
+
+from e2e_asr_b200 import ops, synth
+from oracle import model as om
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def T(a, dtype=torch.float32):
+    return torch.tensor(np.asarray(a), dtype=dtype, device=DEV)
+
+
+def relerr(a, b):
+    a = a.detach().cpu().numpy().astype(np.float64) if isinstance(a, torch.Tensor) else np.asarray(a, np.float64)
+    b = np.asarray(b, np.float64)
+    return float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-30))
+
+
+@pytest.mark.parametrize("M,N,K", [(1, 1, 1), (3, 5, 7), (64, 1024, 512), (130, 257, 33), (7680, 1000, 256),
+                                   (64, 256, 512), (300, 200, 4100), (5, 8, 0)])
+@pytest.mark.parametrize("ta,tb", [(False, False), (True, False), (False, True), (True, True)])
+def test_gemm(M, N, K, ta, tb):
+    rng = np.random.default_rng(M * 1000 + N + K)
+    a = rng.standard_normal((K, M) if ta else (M, K)).astype(np.float32)
+    b = rng.standard_normal((N, K) if tb else (K, N)).astype(np.float32)
+    bias = rng.standard_normal(N).astype(np.float32)
+    z = rng.standard_normal((M, N)).astype(np.float32)
+    c0 = rng.standard_normal((M, N)).astype(np.float32)
+    ref = (a.T if ta else a).astype(np.float64) @ (b.T if tb else b).astype(np.float64)
+    out = ops.gemm(T(a), T(b), ta=ta, tb=tb)
+    assert relerr(out, ref) < 2e-5 if K else float(out.abs().max()) == 0.0
+    out = ops.gemm(T(a), T(b), ta=ta, tb=tb, bias=T(bias), z=T(z))
+    assert relerr(out, ref + bias + z) < 2e-5
+    c = T(c0)
+    ops.gemm(T(a), T(b), ta=ta, tb=tb, out=c, accumulate=True)
+    assert relerr(c, ref + c0) < 2e-5
+
+
+def test_gemm_strided_views():
+    rng = np.random.default_rng(5)
+    big = T(rng.standard_normal((50, 40)))
+    w = T(rng.standard_normal((16, 24)))
+    out = torch.zeros((50, 30), device=DEV)
+    ops.gemm(big[:, 8:24], w, out=out[:, 3:27])
+    ref = big[:, 8:24].cpu().numpy() @ w.cpu().numpy()
+    assert relerr(out[:, 3:27], ref) < 2e-5
+    assert float(out[:, :3].abs().max()) == 0 and float(out[:, 27:].abs().max()) == 0
+    cs = ops.colsum(big[:, 8:24])
+    assert relerr(cs, big[:, 8:24].cpu().numpy().sum(0)) < 2e-5
+
+
+@pytest.mark.parametrize("B,T_,I,H", [(3, 11, 6, 8), (5, 20, 12, 16), (17, 9, 40, 24), (4, 30, 40, 256),
+                                      (70, 6, 16, 32)])
+def test_bilstm_layer_fwd_bwd(B, T_, I, H):
+    rng = np.random.default_rng(B + T_ + I + H)
+    lens = rng.integers(1, T_ + 1, size=B)
+    lens[0] = T_
+    x = rng.standard_normal((B, T_, I)).astype(np.float32)
+    for b in range(B):
+        x[b, lens[b]:] = 0
+    ks = [rng.uniform(-0.3, 0.3, (I + H, 4 * H)).astype(np.float32) for _ in range(2)]
+    bs = [rng.uniform(-0.3, 0.3, (4 * H,)).astype(np.float32) for _ in range(2)]
+    ref_out, cache = om.birnn_layer_fwd(x.astype(np.float64), lens, ks[0].astype(np.float64), bs[0].astype(np.float64),
+                                        ks[1].astype(np.float64), bs[1].astype(np.float64))
+    dout = rng.standard_normal(ref_out.shape)
+    ref_dx, ref_g = om.birnn_layer_bwd(dout, cache)
+    Tp = T_ + 2 - (T_ % 2)
+    xp = torch.zeros((B, Tp, I), device=DEV)
+    xp[:, :T_] = T(x)
+    xp.requires_grad_(True)
+    params = [T(ks[0]).requires_grad_(), T(bs[0]).requires_grad_(), T(ks[1]).requires_grad_(), T(bs[1]).requires_grad_()]
+    out = ops.BiLSTMLayerFn.apply(xp, *params, T(lens, torch.int32), int(lens.max()))
+    assert relerr(out[:, :T_], ref_out) < 1e-5
+    assert float(out[:, T_:].abs().max()) == 0.0
+    dp = torch.zeros_like(out)
+    dp[:, :T_] = T(dout)
+    out.backward(dp)
+    ops.check_device_errors(DEV)
+    assert relerr(xp.grad[:, :T_], ref_dx) < 2e-5
+    for d in range(2):
+        assert relerr(params[2 * d].grad, ref_g[d][0]) < 2e-5
+        assert relerr(params[2 * d + 1].grad, ref_g[d][1]) < 2e-5
+
+
+@pytest.mark.parametrize("cname", ["tiny", "tiny_b"])
+def test_attn_decoder_fwd_bwd(cname):
+    from e2e_asr_b200.attn_decoder import AttnDecoder
+    from e2e_asr_b200.testing import model_params
+    from e2e_asr_b200.variables import VariableStore
+    cfg = synth.get_config(cname)
+    w = synth.make_weights(cfg, bias_noise=0.1)
+    batch = synth.make_batch(cfg)
+    rng = np.random.default_rng(3)
+    B, Tn, D = cfg.B, 7, 2 * cfg.H
+    enc = np.tanh(rng.standard_normal((B, Tn, D)))
+    enc_len = rng.integers(2, Tn + 1, size=B)
+    enc_len[0] = Tn
+    for b in range(B):
+        enc[b, enc_len[b]:] = 0
+    dec_inp = batch["char"].T
+    seq_len = batch["char_len"]
+    W64 = {k: v.astype(np.float64) for k, v in w.items()}
+    ref_logits, cache = om.attn_decoder_fwd(W64, "char", dec_inp, seq_len, enc, enc_len)
+    targets = dec_inp[1:int(seq_len.max()) + 1]
+    ref_loss, dlog = om.cross_entropy_loss(ref_logits, targets, seq_len)
+    ref_g, ref_denc = om.attn_decoder_bwd(dlog, cache)
+    vs = VariableStore(DEV, capacity=1 << 20)
+    vs.load(w)
+    dec = AttnDecoder(True, model_params(cfg).decoder_params["char"], scope="char", variables=vs)
+    enc_t = T(enc).requires_grad_()
+    sl = T(seq_len, torch.int64)
+    logits = dec(T(dec_inp, torch.int64), sl, enc_t, T(enc_len, torch.int64))
+    assert relerr(logits, ref_logits) < 2e-5
+    from e2e_asr_b200.losses import LossUtils
+    loss = LossUtils.cross_entropy_loss(logits, T(targets, torch.int64), sl)
+    assert abs(float(loss) - ref_loss) < 1e-5 * max(1, abs(ref_loss))
+    loss.backward()
+    assert relerr(enc_t.grad, ref_denc) < 5e-5
+    for k, g in ref_g.items():
+        assert relerr(vs.grad(k), g) < 5e-5, k
+
+
+def test_ctc_head():
+    from e2e_asr_b200.losses import LossUtils
+    rng = np.random.default_rng(8)
+    for (T_, B, D, C, Lmax) in [(12, 4, 6, 5, 4), (40, 3, 8, 11, 19), (150, 2, 8, 30, 70), (9, 5, 4, 3, 1)]:
+        st = rng.standard_normal((B, T_, D))
+        in_lens = rng.integers(max(2 * Lmax + 1, 2), T_ + 1, size=B)
+        lab_lens = rng.integers(1, Lmax + 1, size=B)
+        lab_lens[0] = Lmax
+        labels = rng.integers(0, C - 1, size=(B, Lmax))
+        labels[0, :2] = labels[0, 0]            # a repeat
+        k = rng.standard_normal((D, C)) * 0.7
+        bias = rng.standard_normal(C) * 0.3
+        lg = (st @ k + bias).transpose(1, 0, 2)
+        ref_lb, ref_dlg = om.ctc_loss(np.ascontiguousarray(lg), in_lens, labels, lab_lens)
+        ref_dlg = ref_dlg / B
+        ref_dk = np.einsum("btd,tbc->dc", st, ref_dlg)
+        ref_dst = np.einsum("tbc,dc->btd", ref_dlg, k)
+        Tp = T_ + 3
+        buf = torch.zeros((B, Tp, D), device=DEV)
+        buf[:, :T_] = T(st)
+        buf.requires_grad_()
+        kt, bt = T(k).requires_grad_(), T(bias).requires_grad_()
+        for view in (buf[:, :T_], buf[:, :T_].transpose(0, 1)):
+            for p in (buf, kt, bt):
+                p.grad = None
+            stash = {}
+            loss = LossUtils.ctc_head_loss(view, kt, bt, T(in_lens, torch.int64), T(labels, torch.int64),
+                                           T(lab_lens, torch.int64), stash)
+            assert relerr(stash["loss_b"], ref_lb) < 2e-5
+            assert abs(float(loss) - ref_lb.mean()) < 2e-5 * abs(ref_lb.mean())
+            (loss * 2.0).backward()
+            assert relerr(kt.grad, 2 * ref_dk) < 1e-4
+            assert relerr(bt.grad, 2 * ref_dlg.sum((0, 1))) < 1e-4
+            assert relerr(buf.grad[:, :T_], 2 * ref_dst) < 1e-4
+            assert float(buf.grad[:, T_:].abs().max()) == 0
+
+
+def test_prepare_input_stack_stride():
+    rng = np.random.default_rng(4)
+    x = rng.standard_normal((3, 11, 5)).astype(np.float32)
+    for stack, stride in [(1, 1), (3, 1), (2, 2), (1, 3)]:
+        ref = om.stack_frames(x, stack)[:, ::stride]
+        out = ops.prepare_input(T(x), 16, stack, stride).cpu().numpy()
+        np.testing.assert_array_equal(out[:, :ref.shape[1]], ref)
+        assert np.all(out[:, ref.shape[1]:] == 0)

@@ -1,0 +1,41 @@
+"""CPU-side checks of the C-ABI library: it loads, exports every symbol the header
+declares, and refuses to compute without a GPU (no CPU fallback)."""
+import ctypes
+import os
+import re
+
+import pytest
+import torch
+
+import __graft_entry__ as entry
+from e2e_asr_b200 import _lib
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def libpath():
+    return entry.build()
+
+
+def test_exports_every_declared_symbol(libpath):
+    header = open(os.path.join(ROOT, "include", "e2e_asr_b200.h")).read()
+    declared = set(re.findall(r"\b(e2e_[a-z0-9_]+)\s*\(", header))
+    assert len(declared) >= 25
+    handle = ctypes.CDLL(libpath)
+    for sym in sorted(declared):
+        assert hasattr(handle, sym), sym
+    assert declared == set(_lib.exported_symbols())
+
+
+def test_struct_layout_matches_header():
+    # 9 ints (padded to 40 bytes) + 18 pointers; bwd adds 8 pointers
+    assert ctypes.sizeof(_lib.DecLoopFwdArgs) == 40 + 18 * 8
+    assert ctypes.sizeof(_lib.DecLoopBwdArgs) == 40 + 26 * 8
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU behaviour")
+def test_no_cpu_fallback(libpath):
+    with pytest.raises(RuntimeError, match="no CUDA device"):
+        _lib.call("e2e_mean", 1, None, None)
+    assert _lib.lib().e2e_sm_count() == -1
