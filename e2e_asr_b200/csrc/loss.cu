@@ -107,20 +107,26 @@ int ce_bwd(cudaStream_t st, int U, int B, int V, const float* logits, const long
     return 0;
 }
 
-// ---- CTC: one warp per utterance, log space, fused gradient -----------------
+// ---- CTC: one warp per utterance, scaled forward-backward, fused gradient -----
 // logits rows are addressed as (b*sb + t*st)*C (so batch-major encoder states
 // projected by a GEMM need no transpose); lse_rows holds the per-row softmax
 // normaliser.  Lane l owns the SPL consecutive extended-label states
-// [l*SPL, (l+1)*SPL); neighbours are exchanged with shuffles, alpha_t is kept in
-// registers and spilled to `alpha_ws` [B][T][S_max] for the beta/gradient sweep.
-// grad = softmax - (1/p) sum_{s in lab(k)} alpha_t(s) beta_t(s) / y_t(k), zero for t >= len,
-// scaled by out_scale.  Infeasible labels give loss = +inf like TF's error path
-// would abort; callers must supply feasible labels.
-__device__ __forceinline__ float log_add(float a, float b) {
-    if (a == -INFINITY) return b;
-    if (b == -INFINITY) return a;
-    float m = fmaxf(a, b);
-    return m + log1pf(expf(-fabsf(a - b)));
+// [l*SPL, (l+1)*SPL); neighbours are exchanged with shuffles.
+//
+// Numerics: alpha_t and beta_t are kept in the LINEAR domain, renormalised to sum
+// 1 at every frame (Rabiner scaling): no log/exp in the recursions, fp32 relative
+// error stays ~1e-7 per frame instead of the ~1e-5 absolute error a float log-space
+// recursion accumulates.  log p = sum_t log c_t (double accumulator).  The state
+// occupancy gamma_t(s) = alpha_t(s) beta_t(s) / (p y_t(s)) sums to 1 over s for
+// every t, so it is obtained by normalising alpha^ beta^ / y per frame (products in
+// double to survive underflow):
+//   grad_t(k) = softmax_t(k) - sum_{s in lab(k)} gamma_t(s),  zero for t >= len.
+// alpha^ is spilled to `alpha_ws` [B][T][S_max] for the beta/gradient sweep.
+// Infeasible labels give loss = +inf (TF raises); callers supply feasible labels.
+__device__ __forceinline__ double warp_sum_d(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
 }
 
 template <int SPL>
@@ -134,7 +140,6 @@ ctc_kernel(int T, int B, int C, long long sb, long long stt, const float* __rest
     const int b = blockIdx.x, lane = threadIdx.x;
     const int Tb = min(in_lens[b], T), L = label_lens[b];
     const int S = 2 * L + 1, blank = C - 1;
-    const float NEG = -INFINITY;
     int ext[SPL];
     bool skip[SPL];
 #pragma unroll
@@ -152,60 +157,62 @@ ctc_kernel(int T, int B, int C, long long sb, long long stt, const float* __rest
     float* aw = alpha_ws + (size_t)b * T * S_max;
     float a[SPL];
 #pragma unroll
-    for (int i = 0; i < SPL; ++i) a[i] = NEG;
+    for (int i = 0; i < SPL; ++i) a[i] = 0.f;
+    double logp = 0.0;
     // ---- alpha sweep
     for (int t = 0; t < Tb; ++t) {
         const float* row = logits + ((size_t)b * sb + (size_t)t * stt) * C;
         const float nz = lse_rows[(size_t)b * sb + (size_t)t * stt];
         float prev1 = __shfl_up_sync(0xffffffffu, a[SPL - 1], 1);
-        float prev2 = __shfl_up_sync(0xffffffffu, SPL >= 2 ? a[SPL >= 2 ? SPL - 2 : 0] : 0.f, 1);
+        float prev2 = __shfl_up_sync(0xffffffffu, a[SPL >= 2 ? SPL - 2 : 0], 1);
         if (SPL == 1) prev2 = __shfl_up_sync(0xffffffffu, a[0], 2);
-        if (lane == 0) { prev1 = NEG; prev2 = NEG; }
-        if (SPL == 1 && lane == 1) prev2 = NEG;
+        if (lane == 0) { prev1 = 0.f; prev2 = 0.f; }
+        if (SPL == 1 && lane == 1) prev2 = 0.f;
         float na[SPL];
+        float lsum = 0.f;
 #pragma unroll
         for (int i = 0; i < SPL; ++i) {
             int s = lane * SPL + i;
-            float lp = (s < S) ? row[ext[i]] - nz : NEG;
+            float y = (s < S) ? expf(row[ext[i]] - nz) : 0.f;
             float v;
             if (t == 0) {
-                v = (s <= 1 && s < S) ? lp : NEG;
+                v = (s <= 1) ? y : 0.f;
             } else {
-                float p0 = a[i];
                 float p1 = i >= 1 ? a[i >= 1 ? i - 1 : 0] : prev1;
                 float p2 = i >= 2 ? a[i >= 2 ? i - 2 : 0] : (i == 1 ? prev1 : prev2);
                 if (SPL == 1) { p1 = prev1; p2 = prev2; }
-                v = log_add(p0, p1);
-                if (skip[i]) v = log_add(v, p2);
-                v = (s < S) ? v + lp : NEG;
+                v = (a[i] + p1 + (skip[i] ? p2 : 0.f)) * y;
             }
             na[i] = v;
+            lsum += v;
         }
+        float c = warp_sum(lsum);
+        float inv = c > 0.f ? 1.0f / c : 0.f;
+        logp += log((double)c);
 #pragma unroll
         for (int i = 0; i < SPL; ++i) {
-            a[i] = na[i];
+            a[i] = na[i] * inv;
             int s = lane * SPL + i;
-            if (s < S) aw[(size_t)t * S_max + s] = na[i];
+            if (s < S) aw[(size_t)t * S_max + s] = a[i];
         }
     }
-    // log-likelihood = logaddexp(alpha_{T-1}(S-1), alpha_{T-1}(S-2))
-    float ll = NEG;
+    // p = (alpha_{T-1}(S-1) + alpha_{T-1}(S-2)) * prod c_t
     {
-        float mine = NEG;
+        float mine = 0.f;
 #pragma unroll
         for (int i = 0; i < SPL; ++i) {
             int s = lane * SPL + i;
-            if (Tb > 0 && (s == S - 1 || (s == S - 2 && S >= 2))) mine = log_add(mine, a[i]);
+            if (Tb > 0 && (s == S - 1 || (s == S - 2 && S >= 2))) mine += a[i];
         }
-        for (int o = 16; o > 0; o >>= 1) mine = log_add(mine, __shfl_xor_sync(0xffffffffu, mine, o));
-        ll = mine;
+        mine = warp_sum(mine);
+        logp += log((double)mine);
     }
-    if (lane == 0) loss_b[b] = -ll;
+    if (lane == 0) loss_b[b] = (float)(-logp);
     const float gs = out_scale;
     // ---- beta sweep + gradient
     float bt[SPL];
 #pragma unroll
-    for (int i = 0; i < SPL; ++i) bt[i] = NEG;
+    for (int i = 0; i < SPL; ++i) bt[i] = 0.f;
     for (int t = T - 1; t >= 0; --t) {
         float* grow = grad + ((size_t)b * sb + (size_t)t * stt) * C;
         if (t >= Tb) {
@@ -215,24 +222,25 @@ ctc_kernel(int T, int B, int C, long long sb, long long stt, const float* __rest
         const float* row = logits + ((size_t)b * sb + (size_t)t * stt) * C;
         const float nz = lse_rows[(size_t)b * sb + (size_t)t * stt];
         float nxt1 = __shfl_down_sync(0xffffffffu, bt[0], 1);
-        float nxt2 = __shfl_down_sync(0xffffffffu, SPL >= 2 ? bt[SPL >= 2 ? 1 : 0] : 0.f, 1);
+        float nxt2 = __shfl_down_sync(0xffffffffu, bt[SPL >= 2 ? 1 : 0], 1);
         if (SPL == 1) nxt2 = __shfl_down_sync(0xffffffffu, bt[0], 2);
         // skip flag of state s+2 (needed by the transition s -> s+2)
         bool nskip1 = __shfl_down_sync(0xffffffffu, (int)skip[0], 1);
-        bool nskip2 = __shfl_down_sync(0xffffffffu, (int)(SPL >= 2 ? skip[SPL >= 2 ? 1 : 0] : false), 1);
+        bool nskip2 = __shfl_down_sync(0xffffffffu, (int)skip[SPL >= 2 ? 1 : 0], 1);
         if (SPL == 1) nskip2 = __shfl_down_sync(0xffffffffu, (int)skip[0], 2);
-        if (lane == 31) { nxt1 = NEG; nxt2 = NEG; nskip1 = false; nskip2 = false; }
-        if (SPL == 1 && lane == 30) { nxt2 = NEG; nskip2 = false; }
-        float nb[SPL];
+        if (lane == 31) { nxt1 = 0.f; nxt2 = 0.f; nskip1 = false; nskip2 = false; }
+        if (SPL == 1 && lane == 30) { nxt2 = 0.f; nskip2 = false; }
+        float nb[SPL], yv[SPL];
+        float lsum = 0.f;
 #pragma unroll
         for (int i = 0; i < SPL; ++i) {
             int s = lane * SPL + i;
-            float lp = (s < S) ? row[ext[i]] - nz : NEG;
+            float y = (s < S) ? expf(row[ext[i]] - nz) : 0.f;
+            yv[i] = y;
             float v;
             if (t == Tb - 1) {
-                v = (s < S && (s == S - 1 || s == S - 2)) ? lp : NEG;
+                v = (s == S - 1 || s == S - 2) ? y : 0.f;
             } else {
-                float n0 = bt[i];
                 float n1 = (i + 1 < SPL) ? bt[(i + 1 < SPL) ? i + 1 : 0] : nxt1;
                 float n2;
                 bool sk2;
@@ -240,27 +248,31 @@ ctc_kernel(int T, int B, int C, long long sb, long long stt, const float* __rest
                 else if (i + 2 < SPL) { n2 = bt[(i + 2 < SPL) ? i + 2 : 0]; sk2 = skip[(i + 2 < SPL) ? i + 2 : 0]; }
                 else if (i + 2 == SPL) { n2 = nxt1; sk2 = nskip1; }
                 else { n2 = nxt2; sk2 = nskip2; }
-                v = log_add(n0, n1);
-                if (sk2) v = log_add(v, n2);
-                v = (s < S) ? v + lp : NEG;
+                v = (bt[i] + n1 + (sk2 ? n2 : 0.f)) * y;
             }
             nb[i] = v;
+            lsum += v;
         }
+        float d = warp_sum(lsum);
+        float invd = d > 0.f ? 1.0f / d : 0.f;
+        double gm[SPL];
+        double zs = 0.0;
 #pragma unroll
-        for (int i = 0; i < SPL; ++i) bt[i] = nb[i];
-        // occupancy per class: sum_s exp(alpha+beta - ll - logp_t(k))   (alpha,beta both hold the emission)
+        for (int i = 0; i < SPL; ++i) {
+            bt[i] = nb[i] * invd;
+            int s = lane * SPL + i;
+            double g = 0.0;
+            if (s < S && yv[i] > 0.f) g = (double)aw[(size_t)t * S_max + s] * (double)bt[i] / (double)yv[i];
+            gm[i] = g;
+            zs += g;
+        }
+        zs = warp_sum_d(zs);
+        const double invz = zs > 0.0 ? 1.0 / zs : 0.0;
         for (int k = lane; k < C; k += 32) occ[k] = 0.f;
         __syncwarp();
 #pragma unroll
-        for (int i = 0; i < SPL; ++i) {
-            int s = lane * SPL + i;
-            if (s < S) {
-                float al = aw[(size_t)t * S_max + s];
-                float lp = row[ext[i]] - nz;
-                float e = al + bt[i] - ll - lp;
-                if (al != NEG && bt[i] != NEG) atomicAdd(&occ[ext[i]], expf(e));
-            }
-        }
+        for (int i = 0; i < SPL; ++i)
+            if (gm[i] > 0.0) atomicAdd(&occ[ext[i]], (float)(gm[i] * invz));
         __syncwarp();
         for (int k = lane; k < C; k += 32) grow[k] = gs * (expf(row[k] - nz) - occ[k]);
         __syncwarp();

@@ -388,8 +388,8 @@ int lstm_rec(cudaStream_t st, bool bwd, int B, int T, int Tp, int H, int ndir, l
     const int max_slices_per_launch = nsm / (ndir * nslices);
     const int nb_total = cdiv(B, R);
     size_t smem = rec_smem(bwd, RT, UPC, H);
-    for (int sb = 0; sb < nb_total; sb += max_slices_per_launch) {
-        int nb = min(max_slices_per_launch, nb_total - sb);
+    for (int slice0 = 0; slice0 < nb_total; slice0 += max_slices_per_launch) {
+        int nb = min(max_slices_per_launch, nb_total - slice0);
         int ngroups = nb * ndir;
         E2E_REQUIRE((size_t)ngroups * sizeof(unsigned) <= ctr_ws_bytes, "lstm_rec: counter workspace too small");
         E2E_CHECK_CUDA(cudaMemsetAsync(ctr_ws, 0, (size_t)ngroups * sizeof(unsigned), st));
@@ -397,7 +397,7 @@ int lstm_rec(cudaStream_t st, bool bwd, int B, int T, int Tp, int H, int ndir, l
         p.G = G; p.Hout = Hout; p.Cst = Cst; p.Wh = Wh; p.dOut = dOut; p.lens = lens;
         p.ctr = (unsigned*)ctr_ws; p.err = err_flag;
         p.B = B; p.T = T; p.Tp = Tp; p.H = H; p.ndir = ndir; p.sb = sb; p.st = stt;
-        p.b_begin = sb * R; p.nb_slices = nb;
+        p.b_begin = slice0 * R; p.nb_slices = nb;
         int rc;
 #define CASE(RT_, UPC_) if (RT == RT_ && UPC == UPC_) { rc = launch_rec<RT_, UPC_>(st, bwd, p, ngroups, smem); if (rc) return rc; continue; }
         CASE(1, 8) CASE(2, 8) CASE(4, 8) CASE(8, 8)

@@ -68,8 +68,14 @@ def compare_step(model, ref, rtol=1e-4, check_logits=True):
     assert abs(norm - ref["norm"]) <= rtol * max(1.0, ref["norm"]), ("norm", norm, ref["norm"])
     worst = 0.0
     grads = model.gradients()
+    gmax = max(float(np.abs(g).max()) for g in ref["clipped"].values())
     for k, g in ref["clipped"].items():
-        e = rel_err(grads[k], g)
+        # per-variable max-abs error relative to that variable's max-abs value; variables
+        # whose whole gradient is below 1e-4 of the largest gradient entry of the model
+        # (pure cancellation residue -- the float32 oracle itself is only ~2e-4 accurate
+        # on them) are measured against that floor instead.
+        err = float(np.abs(np.asarray(grads[k], np.float64) - g).max())
+        e = err / max(float(np.abs(g).max()), 1e-4 * gmax)
         worst = max(worst, e)
         assert e <= rtol, ("grad", k, e)
     return worst

@@ -73,8 +73,11 @@ class VariableStore(object):
         self.order.append(name)
         val = torch.from_numpy(np.ascontiguousarray(self._init_value(name, shape, init)).reshape(-1))
         self.flat[off:off + size].copy_(val)
-        v = self.flat[off:off + size].view(shape).detach().requires_grad_(True)
-        v.grad = self.gflat[off:off + size].view(shape)
+        # `.data` gives the view its own autograd version counter: creating a later
+        # variable (an in-place write into `flat`) must not invalidate tensors that
+        # an earlier op already saved for backward.
+        v = self.flat.data[off:off + size].view(shape).requires_grad_(True)
+        v.grad = self.gflat.data[off:off + size].view(shape)
         self.vars[name] = v
         return v
 
@@ -99,7 +102,7 @@ class VariableStore(object):
         self.gflat[:self.used].zero_()
         for n, v in self.vars.items():     # re-attach (autograd may have replaced .grad)
             o, shp = self.specs[n]
-            v.grad = self.gflat[o:o + int(np.prod(shp))].view(shp)
+            v.grad = self.gflat.data[o:o + int(np.prod(shp))].view(shp)
 
     def state_dict(self):
         return {n: self.vars[n].detach().cpu().numpy().copy() for n in self.order}
