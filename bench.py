@@ -1,0 +1,304 @@
+#!/usr/bin/env python
+"""Benchmark of the hot path: teacher-forced fwd+bwd training step.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--config cfg2]
+
+Prints ONE JSON line (rank 0).  metric = train frames/sec (valid log-mel frames,
+sum of logmel_len) for fwd + bwd + gradient clipping on BASELINE.json configs[1]
+("cfg2": B=64/GPU, T=700, F=120, 4-layer pyramidal BiLSTM 256/dir, char attention
+decoder, phone+state aux CTC), weak scaling (per-GPU batch fixed).
+
+  value : inputs already resident in HBM when the timed region starts
+  e2e   : the same step through the public API from pinned HOST buffers (H2D of
+          the batch + D2H of the loss inside the timed region)
+  --impl reference : the reference's CPU path.  TensorFlow-1.x / Python 2 cannot run
+          in this image, so this is the line-by-line NumPy restatement in oracle/
+          ("port"), float32, all host cores, on a bounded sample of the workload.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "train_frames_per_sec_fwd_bwd"
+UNIT = "frames/s"
+
+
+def load_peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            p = json.load(f)
+        return dict(hbm=p["hbm_gbs"], tc_burst=p["bf16_tflops"], tc_sustained=p["bf16_tflops_sustained"],
+                    source="measured (MEASURED_PEAKS.json)")
+    except Exception:
+        return dict(hbm=6650.0, tc_burst=1590.0, tc_sustained=1400.0, source="fallback (B200_PROFILING.md)")
+
+
+class ClockSampler(object):
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index=0):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(gpu_index), "--query-gpu=" + self.Q,
+                                       "--format=csv,noheader,nounits", "-lms", "100"],
+                                      stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        if self.p is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.flush()
+        self.f.seek(0)
+        sm, mx, pw, reasons = [], [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in self.f.read().splitlines():
+            parts = [x.strip() for x in line.split(",")]
+            if len(parts) < 7:
+                continue
+            try:
+                sm.append(float(parts[0])); mx.append(float(parts[1])); pw.append(float(parts[2]))
+            except ValueError:
+                continue
+            for n, v in zip(names, parts[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        self.f.close()
+        os.unlink(self.f.name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "power_w_max": float(max(pw)),
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def cpu_reference_step(cfg_name, sample_B, steps, warmup, threads=None):
+    """Times the CPU restatement (oracle/) on a bounded sample: the first sample_B
+    utterances' worth of the workload (same T/F/H/U, batch reduced)."""
+    from e2e_asr_b200 import synth
+    from oracle import model as om
+    cfg = synth.get_config(cfg_name, B=sample_B)
+    w = synth.make_weights(cfg)
+    batch = synth.make_batch(cfg)
+    frames = int(batch["logmel_len"].sum())
+    kw = dict(num_layers={"char": cfg.L}, ctc_tasks=cfg.ctc, dtype=np.float32)
+    times = []
+    for i in range(warmup + steps):
+        t0 = time.perf_counter()
+        om.train_step(w, batch, **kw)
+        dt = time.perf_counter() - t0
+        if i >= warmup:
+            times.append(dt)
+    sec = float(np.mean(times))
+    return frames / sec, sec, frames, cfg
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    sample_B = 8
+    steps, warmup = max(1, min(args.steps, 3)), min(args.warmup, 1)
+    fps, sec, frames, cfg = cpu_reference_step(args.config, sample_B, steps, warmup)
+    sample = ("%s shapes with batch %d of %d utterances (%d valid frames/step), float32 NumPy restatement "
+              "of the reference graph (oracle/model.py), %d step(s) after %d warm-up"
+              % (args.config, sample_B, cfg_B(args.config), frames, steps, warmup))
+    line = {
+        "impl": "reference", "metric": METRIC, "value": fps, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
+        "warmup": warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args.config, 1, note="CPU arm runs a bounded sample"),
+        "cpu_baseline": {"value": fps, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": fps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+def cfg_B(name):
+    from e2e_asr_b200 import synth
+    return synth.CONFIGS[name]["B"]
+
+
+def workload_config(name, n_gpus, note=None):
+    from e2e_asr_b200 import synth
+    c = synth.CONFIGS[name]
+    d = {"workload": "BASELINE.json configs[1] (%s): Switchboard-300h-shaped teacher-forced fwd+bwd+clip" % name,
+         "batch_per_gpu": c["B"], "global_batch": c["B"] * n_gpus, "frames_T": c["T"], "feat_F": c["F"],
+         "hidden_per_dir": c["H"], "enc_layers": c["L"], "vocab": c["V"], "target_len_U": c["U"],
+         "aux_ctc": {k: {"depth": v[0], "vocab": v[1]} for k, v in c["ctc"].items()},
+         "parallelism": "dp%d" % n_gpus, "dropout": "off (out_prob=1)", "samp_prob": 0.0,
+         "l2": "activations per step (~2 GB) exceed the 126 MB L2; no explicit flush"}
+    if note:
+        d["note"] = note
+    return d
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200")
+    ap.add_argument("--config", default="cfg2")
+    ap.add_argument("--gemm", default=None, help="fp32 | tf32x3 | bf16 (default: library default)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    import torch.distributed as dist
+    from e2e_asr_b200 import _lib, ops, synth
+    from e2e_asr_b200 import dist as edist
+    from e2e_asr_b200.testing import build_model
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (the product path has no CPU fallback)")
+    rank, world, local = edist.init_from_env()
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if args.gemm:
+        ops.set_gemm_mode(args.gemm)
+    W = max(args.warmup, 3)
+    K = args.steps
+    peaks = load_peaks()
+
+    cfg = synth.get_config(args.config)
+    weights = synth.make_weights(cfg)
+    batch = synth.make_batch(cfg, seed=synth.DATA_SEED + rank)      # weak scaling: every rank its own batch
+    frames = int(batch["logmel_len"].sum())
+    reducer = edist.GradAllReducer() if world > 1 else None
+    model = build_model(cfg, weights, device=dev, reducer=reducer)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(ms):
+        if world == 1:
+            return ms
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def sum_over_ranks(v):
+        if world == 1:
+            return v
+        t = torch.tensor([v], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t.item())
+
+    # ---------------- device-resident inputs ("value")
+    prepared = model.get_batch(batch)
+    for _ in range(W):
+        model.run_step(prepared=prepared)
+    barrier()
+    ops.check_device_errors(dev)
+    prof = _lib.Profiler()
+    _lib.PROFILER = prof
+    _lib.launch_count(reset=True)
+    sampler = ClockSampler(local) if rank == 0 else None
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(K):
+        model.run_step(prepared=prepared)
+    e1.record()
+    barrier()
+    ms = max_over_ranks(e0.elapsed_time(e1))
+    clocks = sampler.stop() if sampler else None
+    launches = _lib.launch_count()
+    _lib.PROFILER = None
+    loss_val = float(model.total_loss)
+    total_frames = sum_over_ranks(frames)
+    value = total_frames * K / (ms * 1e-3)
+
+    # ---------------- end to end from host buffers ("e2e")
+    for _ in range(2):
+        model.run_step(batch)
+        float(model.total_loss)
+    barrier()
+    e0.record()
+    for _ in range(K):
+        model.run_step(batch)                   # H2D of the batch from pinned staging inside
+        _ = float(model.total_loss)             # D2H of the step's result
+    e1.record()
+    barrier()
+    ms_e2e = max_over_ranks(e0.elapsed_time(e1))
+    h2d = int(batch["logmel"].nbytes + sum(batch[k].nbytes for k in batch if k != "logmel" and k != "utt_id"
+                                            and hasattr(batch[k], "nbytes")))
+    e2e = {"value": total_frames * K / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d,
+           "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / K}
+    ops.check_device_errors(dev)
+
+    if rank != 0:
+        return
+    # ---------------- per-kernel-class breakdown and roofline (CUDA events of the timed region)
+    summ = prof.summary()
+    tot = sum(v["ms"] for v in summ.values())
+    breakdown = {k: {"ms_per_step": v["ms"] / K, "calls_per_step": v["calls"] / K,
+                     "share": v["ms"] / tot if tot else 0.0} for k, v in sorted(summ.items(), key=lambda kv: -kv[1]["ms"])}
+    top = max(summ.items(), key=lambda kv: kv[1]["ms"])
+    name, tv = top
+    if name == "e2e_gemm":
+        ach = tv["work"] / (tv["ms"] * 1e-3) / 1e12
+        peak = peaks["tc_sustained"]
+        roof = {"kernel": "e2e_gemm (all dense projections, mode=%d)" % ops.get_gemm_mode(), "bound": "tensor",
+                "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak, "traffic": None,
+                "peak_source": peaks["source"] + ", sustained bf16", "algorithmic_gflop_per_step": tv["work"] / K / 1e9,
+                "avg_launch_ms": tv["ms"] / tv["calls"]}
+    else:
+        # recurrence / decoder loop: latency bound; algorithmic HBM bytes are small, report per-timestep latency
+        steps_total = tv["work"]
+        roof = {"kernel": name, "bound": "hbm", "achieved": None, "peak": peaks["hbm"], "unit": "GB/s",
+                "frac": None, "traffic": None, "peak_source": peaks["source"],
+                "us_per_timestep": tv["ms"] * 1e3 / max(steps_total, 1.0), "note": "latency-bound sequential kernel"}
+    rec = {k: summ[k] for k in summ if "rec" in k}
+    extra = {k: {"us_per_timestep": v["ms"] * 1e3 / max(v["work"], 1.0)} for k, v in rec.items()}
+    for k in ("e2e_decoder_loop_fwd", "e2e_decoder_loop_bwd"):
+        if k in summ:
+            extra[k] = {"us_per_timestep": summ[k]["ms"] * 1e3 / max(summ[k]["work"], 1.0)}
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+        "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": {0: "f32", 1: "tf32x3", 2: "bf16"}[ops.get_gemm_mode()], "data": "synthetic",
+        "config": workload_config(args.config, world), "frames_per_step_per_gpu": frames,
+        "padded_frames_per_step_per_gpu": cfg.B * cfg.T, "loss": loss_val,
+        "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "launches_per_step": launches / K,
+        "roofline": roof, "breakdown": breakdown, "sequential_kernels": extra,
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        cores = os.cpu_count() or 1
+        sample_B = 8
+        fps, sec, fr, _ = cpu_reference_step(args.config, sample_B, 2, 1)
+        line["cpu_baseline"] = {
+            "value": fps, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": "%s shapes, batch %d of %d utterances (%d valid frames), float32 NumPy restatement "
+                      "(oracle/model.py), mean of 2 steps after 1 warm-up, %.1f s/step"
+                      % (args.config, sample_B, cfg.B, fr, sec)}
+    print(json.dumps(line))
+
+
+if __name__ == "__main__":
+    main()

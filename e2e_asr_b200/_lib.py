@@ -72,12 +72,19 @@ def lib():
         l.e2e_last_error.restype = ctypes.c_char_p
         l.e2e_version.restype = ctypes.c_int
         l.e2e_sm_count.restype = ctypes.c_int
+        l.e2e_launch_count.restype = ctypes.c_ulonglong
+        l.e2e_launch_count.argtypes = [ctypes.c_int]
+        l.e2e_set_workspace.restype = ctypes.c_int
+        l.e2e_set_workspace.argtypes = [ctypes.c_void_p, ctypes.c_size_t]
+        l.e2e_set_tc_debug.restype = ctypes.c_int
+        l.e2e_set_tc_debug.argtypes = [ctypes.c_void_p, ctypes.c_longlong]
         _lib = l
     return _lib
 
 
 def exported_symbols():
-    return sorted(list(_SIGS.keys()) + ["e2e_last_error", "e2e_version", "e2e_sm_count"])
+    return sorted(list(_SIGS.keys()) + ["e2e_last_error", "e2e_version", "e2e_sm_count", "e2e_launch_count",
+                   "e2e_set_workspace", "e2e_set_tc_debug"])
 
 
 def _ptr(x):
@@ -92,7 +99,32 @@ def stream_ptr():
     return torch.cuda.current_stream().cuda_stream
 
 
-def call(name, *args):
+class Profiler(object):
+    """Optional per-entry-point device timing: CUDA events recorded on the launching
+    stream around every C call (bench.py turns this on for the timed region)."""
+
+    def __init__(self):
+        self.records = []      # (name, start_event, end_event, work)
+
+    def summary(self):
+        torch.cuda.synchronize()
+        out = {}
+        for name, e0, e1, work in self.records:
+            d = out.setdefault(name, dict(ms=0.0, calls=0, work=0.0))
+            d["ms"] += e0.elapsed_time(e1)
+            d["calls"] += 1
+            d["work"] += work
+        return out
+
+
+PROFILER = None
+
+
+def launch_count(reset=False):
+    return int(lib().e2e_launch_count(1 if reset else 0))
+
+
+def call(name, *args, work=0.0, tag=None):
     """Invoke `name(stream, *args)`; tensors are passed as raw device pointers."""
     l = lib()
     if not torch.cuda.is_available():
@@ -103,6 +135,14 @@ def call(name, *args):
             conv.append(ctypes.addressof(a))
         else:
             conv.append(_ptr(a))
+    prof = PROFILER
+    if prof is not None:
+        e0 = torch.cuda.Event(enable_timing=True)
+        e1 = torch.cuda.Event(enable_timing=True)
+        e0.record()
     rc = getattr(l, name)(stream_ptr(), *conv)
+    if prof is not None:
+        e1.record()
+        prof.records.append((tag or name, e0, e1, work))
     if rc != 0:
         raise RuntimeError("%s failed (%d): %s" % (name, rc, l.e2e_last_error().decode()))

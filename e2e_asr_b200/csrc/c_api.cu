@@ -9,6 +9,7 @@
 namespace e2e {
 
 static thread_local char g_err[512] = "";
+unsigned long long g_launches = 0;
 
 void set_error(const char* fmt, ...) {
     va_list ap;
@@ -32,6 +33,8 @@ int gemm_simt(cudaStream_t, int, int, int, int, int, const float*, int, const fl
               const float*, const float*, int, int);
 int gemm_tc(cudaStream_t, int mode, int, int, int, int, int, const float*, int, const float*, int, float*, int,
             const float*, const float*, int, int, bool* handled);
+void set_workspace(void*, size_t);
+void set_tc_debug(float*, long long);
 int colsum(cudaStream_t, int, int, const float*, int, float*, int);
 int lstm_rec(cudaStream_t, bool, int, int, int, int, int, long long, long long, float*, float*, float*,
              const float*, const float*, const int*, void*, size_t, int*);
@@ -82,6 +85,11 @@ using namespace e2e;
 extern "C" {
 
 int e2e_version(void) { return 1; }
+unsigned long long e2e_launch_count(int reset) {
+    unsigned long long n = e2e::g_launches;
+    if (reset) e2e::g_launches = 0;
+    return n;
+}
 const char* e2e_last_error(void) { return e2e::g_err; }
 int e2e_sm_count(void) {
     int n = 0;
@@ -96,6 +104,14 @@ int e2e_gemm(void* stream, int mode, int transA, int transB, int M, int N, int K
              const float* B, int ldb, float* C, int ldc, const float* bias, const float* Z, int ldz,
              int accumulate) {
     return gemm_any(ST(stream), mode, transA, transB, M, N, K, A, lda, B, ldb, C, ldc, bias, Z, ldz, accumulate);
+}
+int e2e_set_tc_debug(float* dbg, long long min_work) {
+    set_tc_debug(dbg, min_work);
+    return 0;
+}
+int e2e_set_workspace(void* ptr, size_t bytes) {
+    set_workspace(ptr, bytes);
+    return 0;
 }
 int e2e_colsum(void* stream, int M, int N, const float* X, int ldx, float* out, int accumulate) {
     return colsum(ST(stream), M, N, X, ldx, out, accumulate);

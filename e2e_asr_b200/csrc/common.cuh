@@ -26,7 +26,13 @@ void set_error(const char* fmt, ...);
         }                                                                               \
     } while (0)
 
-#define E2E_LAUNCH_CHECK() E2E_CHECK_CUDA(cudaGetLastError())
+// every kernel launch of this library goes through here: error check + launch counter
+extern unsigned long long g_launches;
+#define E2E_LAUNCH_CHECK()                 \
+    do {                                   \
+        ++e2e::g_launches;                 \
+        E2E_CHECK_CUDA(cudaGetLastError()); \
+    } while (0)
 
 static inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
 

@@ -1,13 +1,480 @@
-// Tensor-core GEMM paths (tcgen05 + TMA).  Placeholder translation unit: until
-// the tcgen05 kernels land, every request reports "not handled" and e2e_gemm
-// runs the fp32 FFMA kernel (still on the GPU; there is no CPU path).
+// Tensor-core GEMM for sm_100a: TMA (cp.async.bulk.tensor) -> 128B-swizzled shared
+// memory -> tcgen05.mma with the accumulator in TMEM -> tcgen05.ld epilogue.
+//
+//   C[M,N] = op(A)[M,K] * op(B)[K,N] (+ bias[N]) (+ Z[M,N]) (+ C)
+//
+// Serves the dense contractions of the path (SURVEY.md 2.3 K1/K4/K7 and their
+// dX/dW twins).  Two numeric modes:
+//   mode 1 "tf32x3": fp32-accurate.  Each fp32 operand is split by a pre-pass into
+//          big = x with the low 13 mantissa bits cleared (exactly a TF32 number) and
+//          small = x - big (exact); the kernel accumulates
+//          big*big + big*small + small*big in the fp32 TMEM accumulator
+//          (kind::tf32), error ~2^-21 relative -- the north-star's 1e-4 budget.
+//   mode 2 "bf16":   operands rounded to bf16 by the pre-pass, one kind::f16 MMA.
+// All four transpose combinations are native: a row-major operand whose
+// contiguous dimension is K is a K-major UMMA operand, otherwise an MN-major one
+// (instruction-descriptor bits 15/16); TMA boxes always follow the contiguous
+// dimension, so nothing is ever transposed in memory.
+//
+// CTA = one 128x128 output tile (x one K split): warp 0 = TMA producer, warp 1 =
+// TMEM allocator + single-thread MMA issuer, warps 2..5 = epilogue (each owns the
+// 32 TMEM lanes its warp-id%4 may access).  3-stage mbarrier ring, 64 KB/stage.
+#include <cuda.h>
+#include <cuda_bf16.h>
+
 #include "common.cuh"
 
 namespace e2e {
 
-int gemm_tc(cudaStream_t, int, int, int, int, int, int, const float*, int, const float*, int, float*, int,
-            const float*, const float*, int, int, bool* handled) {
+namespace {
+
+constexpr int TBM = 128, TBN = 128;
+constexpr int STAGES = 3;
+constexpr int OPER_BYTES = 16384;                  // one 128 x (128 B) operand tile
+constexpr int STAGE_BYTES = 4 * OPER_BYTES;        // A_big, A_small, B_big, B_small (bf16: A, -, B, -)
+constexpr int TC_THREADS = 192;
+constexpr int TMEM_COLS = 128;
+
+// ------------------------------------------------------------------ PTX helpers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n.reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n}\n"
+        : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    return ok != 0;
+}
+// Bounded wait: a pipeline bug must fault (trap) instead of hanging the GPU.
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    if (mbar_try_wait(bar, parity)) return;
+    const long long t0 = clock64();
+    while (!mbar_try_wait(bar, parity)) {
+        if (clock64() - t0 > (1ll << 33)) __trap();
+    }
+}
+__device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t cols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t addr, uint32_t cols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(addr), "r"(cols) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+template <bool BF16>
+__device__ __forceinline__ void umma(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+    if (BF16) {
+        asm volatile(
+            "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
+            "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}\n"
+            ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum) : "memory");
+    } else {
+        asm volatile(
+            "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
+            "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n}\n"
+            ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum) : "memory");
+    }
+}
+// tcgen05.commit: the mbarrier gets one arrival when all previously issued MMAs retire
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+          "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+          "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr) : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// Shared-memory matrix descriptor (Blackwell version field = 1).  layout_type: 2 =
+// SWIZZLE_128B (16-byte chunks), 1 = SWIZZLE_128B_BASE32B (32-byte chunks) -- the only
+// layout the hardware accepts for MN-major 32-bit (tf32) operands.
+__device__ __forceinline__ uint64_t make_sdesc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes,
+                                               uint32_t layout_type) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+    d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+    d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+    d |= (uint64_t)1 << 46;       // descriptor version
+    d |= (uint64_t)layout_type << 61;
+    return d;
+}
+
+struct TcParams {
+    int M, N, K;
+    float* C;
+    int ldc;
+    const float* bias;
+    const float* Z;
+    int ldz;
+    int accumulate;
+    int kblocks_per_split;     // K blocks (of BKE elements) handled by one blockIdx.z
+    int a_mn_major, b_mn_major;
+    float* dbg;                // debug: if set, stage-0 smem (64 KB) and the raw TMEM tile are dumped here
+};
+
+// BF16: element = 2 bytes, 64 elements per 128 B, UMMA_K = 16;  TF32: 4 bytes, 32 per 128 B, UMMA_K = 8.
+template <bool BF16>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA1,
+               const __grid_constant__ CUtensorMap mapB0, const __grid_constant__ CUtensorMap mapB1, TcParams p) {
+    constexpr int BKE = BF16 ? 64 : 32;            // K elements per stage (one 128-byte swizzle span)
+    constexpr int ELT = BF16 ? 2 : 4;
+    constexpr int NPROD = BF16 ? 1 : 3;            // MMAs per k-step
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    __shared__ __align__(8) uint64_t full_bar[STAGES], empty_bar[STAGES], tmem_full_bar;
+    __shared__ uint32_t tmem_base_smem;
+
+    const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+    const int m0 = blockIdx.y * TBM, n0 = blockIdx.x * TBN;
+    const int kb_total = (p.K + BKE - 1) / BKE;
+    const int kb_begin = blockIdx.z * p.kblocks_per_split;
+    const int kb_end = min(kb_total, kb_begin + p.kblocks_per_split);
+    const int nkb = kb_end - kb_begin;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+        mbar_init(&tmem_full_bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) tmem_alloc(&tmem_base_smem, TMEM_COLS);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_d = tmem_base_smem;
+
+    if (warp == 0) {
+        // ================= TMA producer (one elected lane) =================
+        if (lane == 0) {
+            for (int i = 0; i < nkb; ++i) {
+                const int s = i % STAGES;
+                const uint32_t ph = (i / STAGES) & 1;
+                mbar_wait(&empty_bar[s], ph ^ 1);
+                uint8_t* st = smem + (size_t)s * STAGE_BYTES;
+                const int k0 = (kb_begin + i) * BKE;
+                mbar_expect_tx(&full_bar[s], (BF16 ? 2 : 4) * OPER_BYTES);
+#pragma unroll
+                for (int part = 0; part < (BF16 ? 1 : 2); ++part) {
+                    const CUtensorMap* ma = part ? &mapA1 : &mapA0;
+                    const CUtensorMap* mb = part ? &mapB1 : &mapB0;
+                    uint8_t* sa = st + part * OPER_BYTES;
+                    uint8_t* sb = st + (2 + part) * OPER_BYTES;
+                    if (!p.a_mn_major) {
+                        tma_load_2d(ma, &full_bar[s], sa, k0, m0);                 // box {BKE (K), 128 rows of M}
+                    } else {
+                        // stored [K][M]: boxes {128B of M, BKE rows of K}, one per 128-byte M chunk
+                        constexpr int CH = 128 / ELT;                               // M elements per chunk
+                        for (int c = 0; c < TBM / CH; ++c)
+                            tma_load_2d(ma, &full_bar[s], sa + c * (BKE * 128), m0 + c * CH, k0);
+                    }
+                    if (p.b_mn_major) {
+                        constexpr int CH = 128 / ELT;
+                        for (int c = 0; c < TBN / CH; ++c)
+                            tma_load_2d(mb, &full_bar[s], sb + c * (BKE * 128), n0 + c * CH, k0);
+                    } else {
+                        tma_load_2d(mb, &full_bar[s], sb, k0, n0);                 // stored [N][K]
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ================= MMA issuer (single thread) =================
+        if (lane == 0) {
+            // instruction descriptor: D=f32, A/B format, majors, N>>3, M>>4
+            uint32_t idesc = (1u << 4) | ((BF16 ? 1u : 2u) << 7) | ((BF16 ? 1u : 2u) << 10) |
+                             ((uint32_t)(p.a_mn_major ? 1 : 0) << 15) | ((uint32_t)(p.b_mn_major ? 1 : 0) << 16) |
+                             ((uint32_t)(TBN >> 3) << 17) | ((uint32_t)(TBM >> 4) << 24);
+            constexpr int UK = BF16 ? 16 : 8;                  // K elements per instruction
+            constexpr int KSTEPS = BKE / UK;                   // 4
+            // K-major: rows of 128 B, 8-row groups 1024 B apart; advance 32 B per k-step.
+            // MN-major: atoms of (128 B of MN) x (8 k rows) = 1024 B; MN chunks BKE*128 B apart (LBO);
+            //           8-row k groups 1024 B apart (SBO); advance UK rows = UK*128 B per k-step.
+            //           tf32 MN-major uses the 32-byte-atom swizzle whose k groups are 4 rows = 512 B.
+            const uint32_t a_lbo = p.a_mn_major ? BKE * 128 : 16, a_sbo = (!BF16 && p.a_mn_major) ? 512 : 1024;
+            const uint32_t b_lbo = p.b_mn_major ? BKE * 128 : 16, b_sbo = (!BF16 && p.b_mn_major) ? 512 : 1024;
+            const uint32_t a_lt = (!BF16 && p.a_mn_major) ? 1 : 2, b_lt = (!BF16 && p.b_mn_major) ? 1 : 2;
+            const uint32_t a_step = p.a_mn_major ? UK * 128 : 32;
+            const uint32_t b_step = p.b_mn_major ? UK * 128 : 32;
+            for (int i = 0; i < nkb; ++i) {
+                const int s = i % STAGES;
+                const uint32_t ph = (i / STAGES) & 1;
+                mbar_wait(&full_bar[s], ph);
+                tc_fence_after();
+                const uint32_t st = smem_u32(smem + (size_t)s * STAGE_BYTES);
+#pragma unroll
+                for (int k = 0; k < KSTEPS; ++k) {
+                    const uint64_t a0 = make_sdesc(st + k * a_step, a_lbo, a_sbo, a_lt);
+                    const uint64_t b0 = make_sdesc(st + 2 * OPER_BYTES + k * b_step, b_lbo, b_sbo, b_lt);
+                    if (BF16) {
+                        umma<true>(tmem_d, a0, b0, idesc, (i | k) != 0);
+                    } else {
+                        const uint64_t a1 = make_sdesc(st + OPER_BYTES + k * a_step, a_lbo, a_sbo, a_lt);
+                        const uint64_t b1 = make_sdesc(st + 3 * OPER_BYTES + k * b_step, b_lbo, b_sbo, b_lt);
+                        umma<false>(tmem_d, a1, b0, idesc, (i | k) != 0);     // small * big
+                        umma<false>(tmem_d, a0, b1, idesc, 1);                // big * small
+                        umma<false>(tmem_d, a0, b0, idesc, 1);                // big * big
+                    }
+                }
+                umma_commit(&empty_bar[s]);            // frees the smem stage when these MMAs retire
+            }
+            umma_commit(&tmem_full_bar);               // accumulator complete
+        }
+    } else {
+        // ================= epilogue: TMEM -> registers -> global =================
+        mbar_wait(&tmem_full_bar, 0);
+        tc_fence_after();
+        const int q = warp % 4;                        // TMEM lane quarter this warp may access
+        const int m = m0 + q * 32 + lane;
+        if (p.dbg != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) {
+            const float* s0 = reinterpret_cast<const float*>(smem);
+            for (int i = (warp - 2) * 32 + lane; i < STAGE_BYTES / 4; i += 128) p.dbg[i] = s0[i];
+            for (int c0 = 0; c0 < TBN; c0 += 32) {
+                uint32_t r[32];
+                tmem_ld32(tmem_d + ((uint32_t)(q * 32) << 16) + c0, r);
+                for (int j = 0; j < 32; ++j)
+                    p.dbg[STAGE_BYTES / 4 + (q * 32 + lane) * TBN + c0 + j] = __uint_as_float(r[j]);
+            }
+        }
+        const bool split = gridDim.z > 1;
+        const bool lead = blockIdx.z == 0;
+#pragma unroll 1
+        for (int c0 = 0; c0 < TBN; c0 += 32) {
+            uint32_t r[32];
+            if (nkb > 0) {
+                tmem_ld32(tmem_d + ((uint32_t)(q * 32) << 16) + c0, r);
+            } else {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) r[j] = 0u;
+            }
+            const bool vec = !split && (p.ldc % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.C) & 15) == 0) &&
+                             (n0 + c0 + 32 <= p.N);
+            if (m < p.M && vec) {
+                float* crow = p.C + (size_t)m * p.ldc + n0 + c0;
+#pragma unroll
+                for (int j = 0; j < 32; j += 4) {
+                    float v[4];
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        v[e] = __uint_as_float(r[j + e]);
+                        if (p.bias) v[e] += __ldg(p.bias + n0 + c0 + j + e);
+                        if (p.Z) v[e] += __ldg(p.Z + (size_t)m * p.ldz + n0 + c0 + j + e);
+                    }
+                    float4* dst = reinterpret_cast<float4*>(crow + j);
+                    if (p.accumulate) {
+                        float4 o = *dst;
+                        v[0] += o.x; v[1] += o.y; v[2] += o.z; v[3] += o.w;
+                    }
+                    *dst = make_float4(v[0], v[1], v[2], v[3]);
+                }
+            } else if (m < p.M) {
+                float* crow = p.C + (size_t)m * p.ldc;
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    int n = n0 + c0 + j;
+                    if (n < p.N) {
+                        float v = __uint_as_float(r[j]);
+                        if (!split || lead) {
+                            if (p.bias) v += __ldg(p.bias + n);
+                            if (p.Z) v += __ldg(p.Z + (size_t)m * p.ldz + n);
+                        }
+                        if (split) atomicAdd(crow + n, v);
+                        else crow[n] = p.accumulate ? crow[n] + v : v;
+                    }
+                }
+            }
+        }
+        tc_fence_before();
+    }
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc(tmem_d, TMEM_COLS);
+    }
+}
+
+// ------------------------------------------------------------------ pre-pass
+// big = x with the low 13 mantissa bits cleared (a TF32 value), small = x - big.
+__global__ void split_tf32_kernel(size_t rows, int cols, const float* __restrict__ x, int ldx,
+                                  float* __restrict__ big, float* __restrict__ small, int ldo) {
+    size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    size_t total = rows * (size_t)(ldo / 4);
+    if (i >= total) return;
+    size_t r = i / (ldo / 4);
+    int c = (int)(i % (ldo / 4)) * 4;
+    float v[4], b[4], s[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        v[j] = (c + j < cols) ? x[r * ldx + c + j] : 0.f;
+        b[j] = __uint_as_float(__float_as_uint(v[j]) & 0xFFFFE000u);
+        s[j] = v[j] - b[j];
+    }
+    *reinterpret_cast<float4*>(big + r * ldo + c) = make_float4(b[0], b[1], b[2], b[3]);
+    *reinterpret_cast<float4*>(small + r * ldo + c) = make_float4(s[0], s[1], s[2], s[3]);
+}
+__global__ void cvt_bf16_kernel(size_t rows, int cols, const float* __restrict__ x, int ldx,
+                                __nv_bfloat16* __restrict__ out, int ldo) {
+    size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    size_t total = rows * (size_t)(ldo / 8);
+    if (i >= total) return;
+    size_t r = i / (ldo / 8);
+    int c = (int)(i % (ldo / 8)) * 8;
+    __align__(16) __nv_bfloat16 o[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) o[j] = __float2bfloat16((c + j < cols) ? x[r * ldx + c + j] : 0.f);
+    *reinterpret_cast<uint4*>(out + r * ldo + c) = *reinterpret_cast<const uint4*>(o);
+}
+
+// ------------------------------------------------------------------ host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode() {
+    static EncodeTiledFn fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void* sym = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = (EncodeTiledFn)sym;
+    }
+    return fn;
+}
+
+// 2-D row-major tensor [rows][cols] (cols contiguous, row stride ld elements); box = {box_c, box_r}
+bool make_map(CUtensorMap* map, bool bf16, const void* ptr, size_t rows, size_t cols, size_t ld, int box_c,
+              int box_r, bool atom32) {
+    EncodeTiledFn enc = get_encode();
+    if (!enc) return false;
+    cuuint64_t dims[2] = {cols, rows};
+    cuuint64_t strides[1] = {ld * (bf16 ? 2 : 4)};
+    cuuint32_t box[2] = {(cuuint32_t)box_c, (cuuint32_t)box_r};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(map, bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2,
+                     const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     atom32 ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
+                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS;
+}
+
+void* g_ws = nullptr;
+size_t g_ws_bytes = 0;
+float* g_dbg = nullptr;
+long long g_min_work = 1ll << 27;
+
+}  // namespace
+
+void set_workspace(void* ptr, size_t bytes) {
+    g_ws = ptr;
+    g_ws_bytes = bytes;
+}
+void set_tc_debug(float* dbg, long long min_work) {
+    g_dbg = dbg;
+    g_min_work = min_work;
+}
+
+// Returns with *handled = false when the shape/alignment is not eligible (caller falls back to FFMA).
+int gemm_tc(cudaStream_t st, int mode, int transA, int transB, int M, int N, int K, const float* A, int lda,
+            const float* B, int ldb, float* C, int ldc, const float* bias, const float* Z, int ldz, int accumulate,
+            bool* handled) {
     *handled = false;
+    if (mode != 1 && mode != 2) return 0;
+    const bool bf16 = mode == 2;
+    // big enough to pay for the pre-pass and to fill tiles; K >= one stage
+    if (M < 96 || N < 64 || K < 32 || (long long)M * N * K < g_min_work) return 0;
+    if (!get_encode() || g_ws == nullptr) return 0;
+    // stored shapes
+    const size_t a_rows = transA ? K : M, a_cols = transA ? M : K;
+    const size_t b_rows = transB ? N : K, b_cols = transB ? K : N;
+    const int eper = bf16 ? 8 : 4;                                  // elements per 16 bytes
+    const size_t a_ld = (a_cols + eper - 1) / eper * eper, b_ld = (b_cols + eper - 1) / eper * eper;
+    const size_t esz = bf16 ? 2 : 4, nparts = bf16 ? 1 : 2;
+    size_t a_bytes = (a_rows * a_ld * esz + 1023) / 1024 * 1024, b_bytes = (b_rows * b_ld * esz + 1023) / 1024 * 1024;
+    if (nparts * (a_bytes + b_bytes) > g_ws_bytes) return 0;
+    uint8_t* ws = (uint8_t*)g_ws;
+    void* A0 = ws;
+    void* A1 = ws + a_bytes;
+    void* B0 = ws + nparts * a_bytes;
+    void* B1 = ws + nparts * a_bytes + b_bytes;
+    if (bf16) {
+        cvt_bf16_kernel<<<cdiv(a_rows * (a_ld / 8), 256), 256, 0, st>>>(a_rows, (int)a_cols, A, lda, (__nv_bfloat16*)A0, (int)a_ld);
+        E2E_LAUNCH_CHECK();
+        cvt_bf16_kernel<<<cdiv(b_rows * (b_ld / 8), 256), 256, 0, st>>>(b_rows, (int)b_cols, B, ldb, (__nv_bfloat16*)B0, (int)b_ld);
+        E2E_LAUNCH_CHECK();
+    } else {
+        split_tf32_kernel<<<cdiv(a_rows * (a_ld / 4), 256), 256, 0, st>>>(a_rows, (int)a_cols, A, lda, (float*)A0, (float*)A1, (int)a_ld);
+        E2E_LAUNCH_CHECK();
+        split_tf32_kernel<<<cdiv(b_rows * (b_ld / 4), 256), 256, 0, st>>>(b_rows, (int)b_cols, B, ldb, (float*)B0, (float*)B1, (int)b_ld);
+        E2E_LAUNCH_CHECK();
+    }
+    const int bke = bf16 ? 64 : 32;           // elements per 128-byte span
+    // A: K-major when the stored matrix is [M][K] (not transposed); B: K-major when stored [N][K] (transposed)
+    const int a_mn = transA ? 1 : 0, b_mn = transB ? 0 : 1;
+    CUtensorMap mA0, mA1, mB0, mB1;
+    bool ok = true;
+    const bool a32 = !bf16 && a_mn, b32 = !bf16 && b_mn;      // tf32 MN-major: 32-byte-atom swizzle
+    ok &= make_map(&mA0, bf16, A0, a_rows, a_cols, a_ld, bke, a_mn ? bke : TBM, a32);
+    ok &= make_map(&mB0, bf16, B0, b_rows, b_cols, b_ld, bke, b_mn ? bke : TBN, b32);
+    if (!bf16) {
+        ok &= make_map(&mA1, bf16, A1, a_rows, a_cols, a_ld, bke, a_mn ? bke : TBM, a32);
+        ok &= make_map(&mB1, bf16, B1, b_rows, b_cols, b_ld, bke, b_mn ? bke : TBN, b32);
+    } else {
+        mA1 = mA0;
+        mB1 = mB0;
+    }
+    if (!ok) return 0;
+
+    TcParams p;
+    p.M = M; p.N = N; p.K = K; p.C = C; p.ldc = ldc; p.bias = bias; p.Z = Z; p.ldz = ldz;
+    p.accumulate = accumulate; p.a_mn_major = a_mn; p.b_mn_major = b_mn; p.dbg = g_dbg;
+    const int gm = cdiv(M, TBM), gn = cdiv(N, TBN), tiles = gm * gn;
+    const int kb_total = cdiv(K, bke);
+    int splits = 1;
+    const int nsm = sm_count();
+    if (tiles * 2 <= nsm && kb_total >= 16) splits = min(nsm / tiles, kb_total / 8);
+    if (splits < 1) splits = 1;
+    p.kblocks_per_split = cdiv(kb_total, splits);
+    splits = cdiv(kb_total, p.kblocks_per_split);
+    if (splits > 1 && !accumulate) {
+        if (ldc == N) E2E_CHECK_CUDA(cudaMemsetAsync(C, 0, sizeof(float) * (size_t)M * N, st));
+        else E2E_CHECK_CUDA(cudaMemset2DAsync(C, sizeof(float) * ldc, 0, sizeof(float) * N, M, st));
+    }
+    const size_t smem = (size_t)STAGES * STAGE_BYTES + 1024;
+    dim3 grid(gn, gm, splits);
+    if (bf16) {
+        E2E_CHECK_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        gemm_tc_kernel<true><<<grid, TC_THREADS, smem, st>>>(mA0, mA1, mB0, mB1, p);
+    } else {
+        E2E_CHECK_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        gemm_tc_kernel<false><<<grid, TC_THREADS, smem, st>>>(mA0, mA1, mB0, mB1, p);
+    }
+    E2E_LAUNCH_CHECK();
+    *handled = true;
     return 0;
 }
 

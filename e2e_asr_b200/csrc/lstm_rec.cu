@@ -351,6 +351,7 @@ static int launch_rec(cudaStream_t st, bool bwd, RecParams p, int ngroups, size_
     void* args[] = {&p};
     // cooperative launch: guarantees all CTAs of every group are co-resident
     E2E_CHECK_CUDA(cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(16 * UPC), args, smem, st));
+    ++g_launches;
     return 0;
 }
 

@@ -19,6 +19,17 @@ def set_gemm_mode(mode):
     _GEMM_MODE = {"fp32": 0, "tf32x3": 1, "bf16": 2}.get(mode, mode)
 
 
+_workspace = {}
+
+
+def ensure_workspace(device, nbytes=2 << 30):
+    """Registers the operand pre-pass scratch of the tensor-core GEMM modes."""
+    key = str(device)
+    if key not in _workspace or _workspace[key].numel() < nbytes:
+        _workspace[key] = torch.empty((nbytes,), dtype=torch.uint8, device=device)
+    _lib.lib().e2e_set_workspace(_workspace[key].data_ptr(), _workspace[key].numel())
+
+
 def get_gemm_mode():
     return _GEMM_MODE
 
@@ -83,8 +94,11 @@ def gemm(a, b, out=None, ta=False, tb=False, bias=None, z=None, accumulate=False
     if z is not None:
         assert z.stride(1) == 1
         ldz = z.stride(0) if z.shape[0] > 1 else z.shape[1]
-    call("e2e_gemm", _GEMM_MODE if mode is None else mode, int(ta), int(tb), M, N, K, a, lda, b, ldb, out, ldc,
-         bias, z, ldz, int(accumulate))
+    mode = _GEMM_MODE if mode is None else mode
+    if mode != 0 and str(a.device) not in _workspace:
+        ensure_workspace(a.device)
+    call("e2e_gemm", mode, int(ta), int(tb), M, N, K, a, lda, b, ldb, out, ldc,
+         bias, z, ldz, int(accumulate), work=2.0 * M * N * K)
     return out
 
 
@@ -171,7 +185,7 @@ class BiLSTMLayerFn(torch.autograd.Function):
         out = torch.zeros((B, Tp, 2 * H), dtype=torch.float32, device=dev)
         Cst = torch.empty((B, Tp, 2, H), dtype=torch.float32, device=dev)
         call("e2e_lstm_rec_fwd", B, T, Tp, H, 2, Tp, 1, G, out, Cst, Wh, lens_i32, st["ctr"],
-             st["ctr"].numel() * 4, st["err"])
+             st["ctr"].numel() * 4, st["err"], work=float(T), tag="enc_rec_fwd")
         ctx.save_for_backward(x, Wx, Wh, G, Cst, out, lens_i32)
         ctx.dims = (B, Tp, I, H, T)
         return out
@@ -184,7 +198,7 @@ class BiLSTMLayerFn(torch.autograd.Function):
         st = _dev_state(dev)
         dout = dout.contiguous()
         call("e2e_lstm_rec_bwd", B, T, Tp, H, 2, Tp, 1, G, Cst, Wh, dout, lens_i32, st["ctr"],
-             st["ctr"].numel() * 4, st["err"])                     # G now holds d(pre-activations)
+             st["ctr"].numel() * 4, st["err"], work=float(T), tag="enc_rec_bwd")   # G now holds d(pre-activations)
         N = B * Tp
         x2, o2 = x.view(N, I), out.view(N, 2 * H)
         dX = gemm(G, Wx, tb=True).view(B, Tp, I) if ctx.needs_input_grad[0] else None
@@ -231,7 +245,7 @@ class AttnDecoderFn(torch.autograd.Function):
         hl = torch.zeros((U * B, Hl), **f32)
         C_lm = torch.empty((U * B, Hl), **f32)
         call("e2e_lstm_rec_fwd", B, U, U, Hl, 1, 1, B, G_lm, hl, C_lm, Wh_lm, lens_i32, st["ctr"],
-             st["ctr"].numel() * 4, st["err"])
+             st["ctr"].numel() * 4, st["err"], work=float(U), tag="lm_rec_fwd")
         m = gemm(hl, sp_k, bias=sp_b) if sp_k is not None else hl    # SimpleProjection (:149-151)
         pre = gemm(m, in_k[:Hd], bias=in_b)                          # lm half of InputProjection (:157-158)
         HF = gemm(enc_flat, attn_w.view(D, A))                       # hidden_features (:70-73), padded rows too
@@ -246,7 +260,7 @@ class AttnDecoderFn(torch.autograd.Function):
                     enc=enc_flat, enc_len=enc_len_i32, lens=lens_i32, **bufs)
         for k, v in ptrs.items():
             setattr(a, k, v.data_ptr())
-        call("e2e_decoder_loop_fwd", a)
+        call("e2e_decoder_loop_fwd", a, work=float(U))
         proj = gemm(bufs["cat"], ap_k, bias=ap_b)                     # AttnProjection (:116-118)
         logits = gemm(proj, out_k, bias=out_b)                        # OutputProjection (:124-125)
         call("e2e_mask_rows", U, B, V, logits, lens_i32)              # raw_rnn zeroes finished rows
@@ -291,7 +305,7 @@ class AttnDecoderFn(torch.autograd.Function):
                    dc_carry=torch.zeros((B, Hd), **f32))
         for k, v in out.items():
             setattr(g, k, v.data_ptr())
-        call("e2e_decoder_loop_bwd", g)
+        call("e2e_decoder_loop_bwd", g, work=float(U))
         dgates, dxh, dy, dHF, denc = out["dgates"], out["dxh"], out["dy"], out["dHF"], out["denc"]
         dq_k = gemm(cat[:, :Hd], dy, ta=True)
         dq_b = colsum(dy)
@@ -312,7 +326,7 @@ class AttnDecoderFn(torch.autograd.Function):
             dm = gemm(dm, sp_k, tb=True)
         # LM-LSTM backward (time-major rows: b stride 1, t stride B)
         call("e2e_lstm_rec_bwd", B, U, U, Hl, 1, 1, B, G_lm, C_lm, Wh_lm, dm, lens_i32, st["ctr"],
-             st["ctr"].numel() * 4, st["err"])
+             st["ctr"].numel() * 4, st["err"], work=float(U), tag="lm_rec_bwd")
         dWx_lm = gemm(u, G_lm, ta=True)
         dWh_lm = torch.zeros((1, Hl, 4 * Hl), **f32)
         if U > 1:

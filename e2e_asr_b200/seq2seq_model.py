@@ -134,12 +134,16 @@ class Seq2SeqModel(BaseParams):
         return [encoder_inputs, decoder_inputs, encoder_len, decoder_len]
 
     # ------------------------------------------------------------------
-    def create_computational_graph(self, batch=None):
-        """One step (seq2seq_model.py:88-157)."""
+    def create_computational_graph(self, batch=None, prepared=None):
+        """One step (seq2seq_model.py:88-157).  `prepared` = a previous get_batch()
+        result (device-resident inputs), otherwise `batch` (or the next batch of
+        data_iter) is staged host -> device first."""
         params = self.params
-        if batch is None:
-            batch = self.data_iter.get_next()
-        self.encoder_inputs, self.decoder_inputs, self.seq_len, self.seq_len_target = self.get_batch(batch)
+        if prepared is None:
+            if batch is None:
+                batch = self.data_iter.get_next()
+            prepared = self.get_batch(batch)
+        self.encoder_inputs, self.decoder_inputs, self.seq_len, self.seq_len_target = prepared
 
         self.targets, self.target_weights = {}, {}
         for task in params.tasks:

@@ -28,6 +28,8 @@ extern "C" {
 int e2e_version(void);
 const char* e2e_last_error(void);
 int e2e_sm_count(void);
+/* number of kernels this library has launched (host counter); reset != 0 clears it */
+unsigned long long e2e_launch_count(int reset);
 
 /* Dense contraction  C[M,N] = op(A) op(B) (+bias[N]) (+Z[M,N]) (+C)   row-major.
  * Replaces every `_linear` / matmul / 1x1 conv2d on the path: attn_decoder.py:73
@@ -41,6 +43,13 @@ int e2e_sm_count(void);
 int e2e_gemm(void* stream, int mode, int transA, int transB, int M, int N, int K,
              const float* A, int lda, const float* B, int ldb, float* C, int ldc,
              const float* bias, const float* Z, int ldz, int accumulate);
+
+/* Scratch for the tensor-core modes' operand pre-pass (TF32 big/small split or
+ * bf16 copies): a caller-owned device buffer; GEMMs whose operands do not fit run
+ * the FFMA kernel.  NOT a stream argument: plain (ptr, bytes). */
+int e2e_set_workspace(void* ptr, size_t bytes);
+/* test hook: dump buffer for the tensor-core kernel (or NULL) and the minimum M*N*K it takes */
+int e2e_set_tc_debug(float* dbg, long long min_work);
 
 /* out[N] (+)= column sums of X[M,N]  (bias gradients) */
 int e2e_colsum(void* stream, int M, int N, const float* X, int ldx, float* out, int accumulate);

@@ -169,3 +169,25 @@ def test_prepare_input_stack_stride():
         out = ops.prepare_input(T(x), 16, stack, stride).cpu().numpy()
         np.testing.assert_array_equal(out[:, :ref.shape[1]], ref)
         assert np.all(out[:, ref.shape[1]:] == 0)
+
+
+@pytest.mark.parametrize("mode,tol", [(1, 2e-5), (2, 2e-2)])
+@pytest.mark.parametrize("M,N,K", [(128, 128, 32), (256, 384, 96), (1000, 520, 264), (4480, 2048, 120),
+                                   (256, 1024, 5000), (777, 333, 1111)])
+@pytest.mark.parametrize("ta,tb", [(False, False), (True, False), (False, True), (True, True)])
+def test_gemm_tensor_core(mode, tol, M, N, K, ta, tb):
+    """tcgen05 paths: mode 1 = 3xTF32 (fp32-accurate), mode 2 = bf16 (looser, stated tolerance)."""
+    rng = np.random.default_rng(M + N + K + mode)
+    a = rng.standard_normal((K, M) if ta else (M, K)).astype(np.float32)
+    b = rng.standard_normal((N, K) if tb else (K, N)).astype(np.float32)
+    bias = rng.standard_normal(N).astype(np.float32)
+    z = rng.standard_normal((M, N)).astype(np.float32)
+    ref = (a.T if ta else a).astype(np.float64) @ (b.T if tb else b).astype(np.float64)
+    out = ops.gemm(T(a), T(b), ta=ta, tb=tb, mode=mode)
+    assert relerr(out, ref) < tol
+    out = ops.gemm(T(a), T(b), ta=ta, tb=tb, bias=T(bias), z=T(z), mode=mode)
+    assert relerr(out, ref + bias + z) < tol
+    c0 = rng.standard_normal((M, N)).astype(np.float32)
+    c = T(c0)
+    ops.gemm(T(a), T(b), ta=ta, tb=tb, out=c, accumulate=True, mode=mode)
+    assert relerr(c, ref + c0) < tol

@@ -47,3 +47,32 @@ def test_clipping_active_and_dense_norm_option():
     model.params.tf_indexed_slices_norm = False
     model.run_step(batch)
     assert abs(float(model.grad_norm) - ref["dense_norm"]) < 1e-4 * ref["dense_norm"]
+
+
+@pytest.mark.parametrize("mode,rtol", [("tf32x3", 1e-4), ("bf16", 5e-2)])
+def test_train_step_tensor_core_modes(mode, rtol):
+    """cfg1 through the tcgen05 GEMMs.  tf32x3 is the fp32-accurate mode and must meet
+    the same 1e-4 bar as FFMA; bf16 is the reduced-precision mode: stated tolerance
+    5e-2 on gradients/logits (relative to each tensor's max), 1e-2 on the loss."""
+    cfg = synth.get_config("cfg1")
+    w = synth.make_weights(cfg, bias_noise=0.1)
+    batch = synth.make_batch(cfg)
+    ref = om.train_step(w, batch, num_layers={"char": cfg.L}, ctc_tasks=cfg.ctc)
+    ops.set_gemm_mode(mode)
+    try:
+        model = build_model(cfg, w, device="cuda:0")
+        model.run_step(batch)
+        ops.check_device_errors("cuda:0")
+        if mode == "bf16":
+            for t, l in ref["losses"].items():
+                assert abs(float(model.losses[t]) - l) <= 1e-2 * max(1.0, abs(l))
+            grads = model.gradients()
+            gmax = max(float(np.abs(g).max()) for g in ref["clipped"].values())
+            for k, g in ref["clipped"].items():
+                err = float(np.abs(grads[k].astype(np.float64) - g).max())
+                assert err <= rtol * max(float(np.abs(g).max()), 1e-2 * gmax), (k, err)
+        else:
+            worst = compare_step(model, ref, rtol=rtol)
+            print(mode, "worst grad rel err", worst)
+    finally:
+        ops.set_gemm_mode("fp32")
