@@ -34,6 +34,8 @@ int gemm_simt(cudaStream_t, int, int, int, int, int, const float*, int, const fl
 int gemm_tc(cudaStream_t, int mode, int, int, int, int, int, const float*, int, const float*, int, float*, int,
             const float*, const float*, int, int, bool* handled);
 void set_workspace(void*, size_t);
+extern int g_rec_mode;
+extern long long* g_rec_dbg;
 void set_tc_debug(float*, long long);
 int colsum(cudaStream_t, int, int, const float*, int, float*, int);
 int lstm_rec(cudaStream_t, bool, int, int, int, int, int, long long, long long, float*, float*, float*,
@@ -107,6 +109,14 @@ int e2e_gemm(void* stream, int mode, int transA, int transB, int M, int N, int K
 }
 int e2e_set_tc_debug(float* dbg, long long min_work) {
     set_tc_debug(dbg, min_work);
+    return 0;
+}
+int e2e_set_rec_mode(int mode) {
+    g_rec_mode = mode;
+    return 0;
+}
+int e2e_set_rec_debug(long long* dbg) {
+    g_rec_dbg = dbg;
     return 0;
 }
 int e2e_set_workspace(void* ptr, size_t bytes) {

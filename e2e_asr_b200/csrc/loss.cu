@@ -129,14 +129,15 @@ __device__ __forceinline__ double warp_sum_d(double v) {
     return v;
 }
 
+// Kernel A: the two sequential sweeps.  Only the S gathered emissions per frame
+// are touched here (the next frame's are prefetched while the current one is
+// processed); gamma_t(s) overwrites alpha^_t(s) in `ws` [B][T][S_max].
 template <int SPL>
 __global__ void __launch_bounds__(32)
-ctc_kernel(int T, int B, int C, long long sb, long long stt, const float* __restrict__ logits,
-           const float* __restrict__ lse_rows, const int* __restrict__ in_lens,
-           const long long* __restrict__ labels, int ldl, const int* __restrict__ label_lens,
-           float* __restrict__ alpha_ws, int S_max, float* __restrict__ loss_b, float* __restrict__ grad,
-           float out_scale) {
-    extern __shared__ float occ[];     // [C]
+ctc_sweep_kernel(int T, int B, int C, long long sb, long long stt, const float* __restrict__ logits,
+                 const float* __restrict__ lse_rows, const int* __restrict__ in_lens,
+                 const long long* __restrict__ labels, int ldl, const int* __restrict__ label_lens,
+                 float* __restrict__ ws, int S_max, float* __restrict__ loss_b) {
     const int b = blockIdx.x, lane = threadIdx.x;
     const int Tb = min(in_lens[b], T), L = label_lens[b];
     const int S = 2 * L + 1, blank = C - 1;
@@ -154,15 +155,23 @@ ctc_kernel(int T, int B, int C, long long sb, long long stt, const float* __rest
         ext[i] = e;
         skip[i] = sk;
     }
-    float* aw = alpha_ws + (size_t)b * T * S_max;
-    float a[SPL];
-#pragma unroll
-    for (int i = 0; i < SPL; ++i) a[i] = 0.f;
-    double logp = 0.0;
-    // ---- alpha sweep
-    for (int t = 0; t < Tb; ++t) {
+    float* aw = ws + (size_t)b * T * S_max;
+    auto emissions = [&](int t, float (&y)[SPL]) {
         const float* row = logits + ((size_t)b * sb + (size_t)t * stt) * C;
         const float nz = lse_rows[(size_t)b * sb + (size_t)t * stt];
+#pragma unroll
+        for (int i = 0; i < SPL; ++i) y[i] = (lane * SPL + i < S) ? expf(row[ext[i]] - nz) : 0.f;
+    };
+    float a[SPL], y[SPL], yn[SPL];
+#pragma unroll
+    for (int i = 0; i < SPL; ++i) { a[i] = 0.f; yn[i] = 0.f; }
+    double logp = 0.0;
+    if (Tb > 0) emissions(0, yn);
+    // ---- alpha sweep
+    for (int t = 0; t < Tb; ++t) {
+#pragma unroll
+        for (int i = 0; i < SPL; ++i) y[i] = yn[i];
+        if (t + 1 < Tb) emissions(t + 1, yn);
         float prev1 = __shfl_up_sync(0xffffffffu, a[SPL - 1], 1);
         float prev2 = __shfl_up_sync(0xffffffffu, a[SPL >= 2 ? SPL - 2 : 0], 1);
         if (SPL == 1) prev2 = __shfl_up_sync(0xffffffffu, a[0], 2);
@@ -173,22 +182,21 @@ ctc_kernel(int T, int B, int C, long long sb, long long stt, const float* __rest
 #pragma unroll
         for (int i = 0; i < SPL; ++i) {
             int s = lane * SPL + i;
-            float y = (s < S) ? expf(row[ext[i]] - nz) : 0.f;
             float v;
             if (t == 0) {
-                v = (s <= 1) ? y : 0.f;
+                v = (s <= 1) ? y[i] : 0.f;
             } else {
                 float p1 = i >= 1 ? a[i >= 1 ? i - 1 : 0] : prev1;
                 float p2 = i >= 2 ? a[i >= 2 ? i - 2 : 0] : (i == 1 ? prev1 : prev2);
                 if (SPL == 1) { p1 = prev1; p2 = prev2; }
-                v = (a[i] + p1 + (skip[i] ? p2 : 0.f)) * y;
+                v = (a[i] + p1 + (skip[i] ? p2 : 0.f)) * y[i];
             }
             na[i] = v;
             lsum += v;
         }
         float c = warp_sum(lsum);
         float inv = c > 0.f ? 1.0f / c : 0.f;
-        logp += log((double)c);
+        logp += (double)logf(c);
 #pragma unroll
         for (int i = 0; i < SPL; ++i) {
             a[i] = na[i] * inv;
@@ -196,8 +204,7 @@ ctc_kernel(int T, int B, int C, long long sb, long long stt, const float* __rest
             if (s < S) aw[(size_t)t * S_max + s] = a[i];
         }
     }
-    // p = (alpha_{T-1}(S-1) + alpha_{T-1}(S-2)) * prod c_t
-    {
+    {   // p = (alpha_{T-1}(S-1) + alpha_{T-1}(S-2)) * prod c_t
         float mine = 0.f;
 #pragma unroll
         for (int i = 0; i < SPL; ++i) {
@@ -205,41 +212,40 @@ ctc_kernel(int T, int B, int C, long long sb, long long stt, const float* __rest
             if (Tb > 0 && (s == S - 1 || (s == S - 2 && S >= 2))) mine += a[i];
         }
         mine = warp_sum(mine);
-        logp += log((double)mine);
+        logp += (double)logf(mine);
     }
     if (lane == 0) loss_b[b] = (float)(-logp);
-    const float gs = out_scale;
-    // ---- beta sweep + gradient
+    // ---- beta sweep; gamma replaces alpha^ in ws
     float bt[SPL];
 #pragma unroll
     for (int i = 0; i < SPL; ++i) bt[i] = 0.f;
-    for (int t = T - 1; t >= 0; --t) {
-        float* grow = grad + ((size_t)b * sb + (size_t)t * stt) * C;
-        if (t >= Tb) {
-            for (int k = lane; k < C; k += 32) grow[k] = 0.f;
-            continue;
+    if (Tb > 0) emissions(Tb - 1, yn);
+    for (int t = Tb - 1; t >= 0; --t) {
+#pragma unroll
+        for (int i = 0; i < SPL; ++i) y[i] = yn[i];
+        float al[SPL];
+#pragma unroll
+        for (int i = 0; i < SPL; ++i) {
+            int s = lane * SPL + i;
+            al[i] = (s < S) ? aw[(size_t)t * S_max + s] : 0.f;
         }
-        const float* row = logits + ((size_t)b * sb + (size_t)t * stt) * C;
-        const float nz = lse_rows[(size_t)b * sb + (size_t)t * stt];
+        if (t > 0) emissions(t - 1, yn);
         float nxt1 = __shfl_down_sync(0xffffffffu, bt[0], 1);
         float nxt2 = __shfl_down_sync(0xffffffffu, bt[SPL >= 2 ? 1 : 0], 1);
         if (SPL == 1) nxt2 = __shfl_down_sync(0xffffffffu, bt[0], 2);
-        // skip flag of state s+2 (needed by the transition s -> s+2)
         bool nskip1 = __shfl_down_sync(0xffffffffu, (int)skip[0], 1);
         bool nskip2 = __shfl_down_sync(0xffffffffu, (int)skip[SPL >= 2 ? 1 : 0], 1);
         if (SPL == 1) nskip2 = __shfl_down_sync(0xffffffffu, (int)skip[0], 2);
         if (lane == 31) { nxt1 = 0.f; nxt2 = 0.f; nskip1 = false; nskip2 = false; }
         if (SPL == 1 && lane == 30) { nxt2 = 0.f; nskip2 = false; }
-        float nb[SPL], yv[SPL];
+        float nb[SPL];
         float lsum = 0.f;
 #pragma unroll
         for (int i = 0; i < SPL; ++i) {
             int s = lane * SPL + i;
-            float y = (s < S) ? expf(row[ext[i]] - nz) : 0.f;
-            yv[i] = y;
             float v;
             if (t == Tb - 1) {
-                v = (s == S - 1 || s == S - 2) ? y : 0.f;
+                v = (s == S - 1 || s == S - 2) ? y[i] : 0.f;
             } else {
                 float n1 = (i + 1 < SPL) ? bt[(i + 1 < SPL) ? i + 1 : 0] : nxt1;
                 float n2;
@@ -248,7 +254,7 @@ ctc_kernel(int T, int B, int C, long long sb, long long stt, const float* __rest
                 else if (i + 2 < SPL) { n2 = bt[(i + 2 < SPL) ? i + 2 : 0]; sk2 = skip[(i + 2 < SPL) ? i + 2 : 0]; }
                 else if (i + 2 == SPL) { n2 = nxt1; sk2 = nskip1; }
                 else { n2 = nxt2; sk2 = nskip2; }
-                v = (bt[i] + n1 + (sk2 ? n2 : 0.f)) * y;
+                v = (bt[i] + n1 + (sk2 ? n2 : 0.f)) * y[i];
             }
             nb[i] = v;
             lsum += v;
@@ -260,23 +266,54 @@ ctc_kernel(int T, int B, int C, long long sb, long long stt, const float* __rest
 #pragma unroll
         for (int i = 0; i < SPL; ++i) {
             bt[i] = nb[i] * invd;
-            int s = lane * SPL + i;
             double g = 0.0;
-            if (s < S && yv[i] > 0.f) g = (double)aw[(size_t)t * S_max + s] * (double)bt[i] / (double)yv[i];
+            if (y[i] > 0.f) g = (double)al[i] * (double)bt[i] * (double)(1.0f / y[i]);
             gm[i] = g;
             zs += g;
         }
         zs = warp_sum_d(zs);
+        // zs is O(1e-38 .. 1): scale by its float reciprocal of the renormalised value
         const double invz = zs > 0.0 ? 1.0 / zs : 0.0;
-        for (int k = lane; k < C; k += 32) occ[k] = 0.f;
-        __syncwarp();
 #pragma unroll
-        for (int i = 0; i < SPL; ++i)
-            if (gm[i] > 0.0) atomicAdd(&occ[ext[i]], (float)(gm[i] * invz));
-        __syncwarp();
-        for (int k = lane; k < C; k += 32) grow[k] = gs * (expf(row[k] - nz) - occ[k]);
-        __syncwarp();
+        for (int i = 0; i < SPL; ++i) {
+            int s = lane * SPL + i;
+            if (s < S) aw[(size_t)t * S_max + s] = (float)(gm[i] * invz);
+        }
     }
+}
+
+// Kernel B: one warp per (utterance, frame) row, fully parallel:
+//   grad[k] = out_scale * (softmax(k) - sum_{s: ext(s)=k} gamma(s)),   0 for t >= len.
+constexpr int CTC_ROWS_PER_CTA = 8;
+__global__ void __launch_bounds__(32 * CTC_ROWS_PER_CTA)
+ctc_grad_kernel(int T, int B, int C, long long sb, long long stt, const float* __restrict__ logits,
+                const float* __restrict__ lse_rows, const int* __restrict__ in_lens,
+                const long long* __restrict__ labels, int ldl, const int* __restrict__ label_lens,
+                const float* __restrict__ ws, int S_max, float* __restrict__ grad, float out_scale) {
+    extern __shared__ float occ_all[];
+    const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+    const long long r = (long long)blockIdx.x * CTC_ROWS_PER_CTA + warp;
+    if (r >= (long long)B * T) return;
+    const int b = (int)(r / T), t = (int)(r % T);
+    float* occ = occ_all + (size_t)warp * C;
+    float* grow = grad + ((size_t)b * sb + (size_t)t * stt) * C;
+    if (t >= min(in_lens[b], T)) {
+        for (int k = lane; k < C; k += 32) grow[k] = 0.f;
+        return;
+    }
+    const int S = 2 * label_lens[b] + 1, blank = C - 1;
+    for (int k = lane; k < C; k += 32) occ[k] = 0.f;
+    __syncwarp();
+    const float* g = ws + ((size_t)b * T + t) * S_max;
+    for (int s = lane; s < S; s += 32) {
+        float v = g[s];
+        int e = (s & 1) ? (int)labels[(size_t)b * ldl + s / 2] : blank;
+        if (v != 0.f) atomicAdd(&occ[e], v);
+    }
+    __syncwarp();
+    const float* row = logits + ((size_t)b * sb + (size_t)t * stt) * C;
+    const float nz = lse_rows[(size_t)b * sb + (size_t)t * stt];
+    for (int k = lane; k < C; k += 32) grow[k] = out_scale * (expf(row[k] - nz) - occ[k]);
 }
 
 int ctc_fwd_grad(cudaStream_t st, int T, int B, int C, long long sb, long long stt, const float* logits,
@@ -285,17 +322,12 @@ int ctc_fwd_grad(cudaStream_t st, int T, int B, int C, long long sb, long long s
                  float out_scale) {
     if (B <= 0 || T <= 0) return 0;
     int S_max = 2 * max_label_len + 1;
-    size_t smem = sizeof(float) * C;
+    size_t smem = sizeof(float) * C * CTC_ROWS_PER_CTA;
     E2E_REQUIRE(S_max <= 32 * 32, "ctc: label length %d too long (max 511)", max_label_len);
     E2E_REQUIRE(smem <= 200 * 1024, "ctc: %d classes do not fit shared memory", C);
-#define CTC_CASE(SPL_)                                                                                          \
-    {                                                                                                           \
-        if (smem > 48 * 1024)                                                                                   \
-            E2E_CHECK_CUDA(cudaFuncSetAttribute(ctc_kernel<SPL_>, cudaFuncAttributeMaxDynamicSharedMemorySize,  \
-                                                (int)smem));                                                    \
-        ctc_kernel<SPL_><<<B, 32, smem, st>>>(T, B, C, sb, stt, logits, lse_rows, in_lens, labels, ldl,        \
-                                              label_lens, alpha_ws, S_max, loss_b, grad, out_scale);    \
-    }
+#define CTC_CASE(SPL_)                                                                                   \
+    ctc_sweep_kernel<SPL_><<<B, 32, 0, st>>>(T, B, C, sb, stt, logits, lse_rows, in_lens, labels, ldl, \
+                                             label_lens, alpha_ws, S_max, loss_b);
     if (S_max <= 32) CTC_CASE(1)
     else if (S_max <= 64) CTC_CASE(2)
     else if (S_max <= 128) CTC_CASE(4)
@@ -303,6 +335,11 @@ int ctc_fwd_grad(cudaStream_t st, int T, int B, int C, long long sb, long long s
     else if (S_max <= 512) CTC_CASE(16)
     else CTC_CASE(32)
 #undef CTC_CASE
+    E2E_LAUNCH_CHECK();
+    if (smem > 48 * 1024)
+        E2E_CHECK_CUDA(cudaFuncSetAttribute(ctc_grad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    ctc_grad_kernel<<<cdiv((long long)B * T, CTC_ROWS_PER_CTA), 32 * CTC_ROWS_PER_CTA, smem, st>>>(
+        T, B, C, sb, stt, logits, lse_rows, in_lens, labels, ldl, label_lens, alpha_ws, S_max, grad, out_scale);
     E2E_LAUNCH_CHECK();
     return 0;
 }

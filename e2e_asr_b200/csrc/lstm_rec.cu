@@ -361,6 +361,10 @@ static size_t rec_smem(bool bwd, int RT, int UPC, int H) {
     return sizeof(float) * ((size_t)(UPC + R) * (4 * H + 4));
 }
 
+int lstm_rec_cluster(cudaStream_t, bool, int, int, int, int, int, long long, long long, float*, float*, float*,
+                     const float*, const float*, const int*);
+int g_rec_mode = 0;     // 0 = cluster/DSMEM kernel when eligible, 1 = always the L2 / global-barrier kernel
+
 // workspace: ctr_ws must hold >= 4*ceil(B/4) unsigned + 1 int, zeroed by this function.
 int lstm_rec(cudaStream_t st, bool bwd, int B, int T, int Tp, int H, int ndir, long long sb, long long stt,
              float* G, float* Hout, float* Cst, const float* Wh, const float* dOut, const int* lens,
@@ -369,6 +373,10 @@ int lstm_rec(cudaStream_t st, bool bwd, int B, int T, int Tp, int H, int ndir, l
     E2E_REQUIRE(ndir == 1 || ndir == 2, "lstm_rec: ndir must be 1 or 2");
     E2E_REQUIRE(Tp >= T, "lstm_rec: Tp (%d) must be >= T (%d)", Tp, T);
     if (B <= 0 || T <= 0) return 0;
+    if (g_rec_mode == 0) {
+        int rc = lstm_rec_cluster(st, bwd, B, T, Tp, H, ndir, sb, stt, G, Hout, Cst, Wh, dOut, lens);
+        if (rc >= 0) return rc;     // launched (0) or failed (>0); -1 = not eligible -> fall through
+    }
     const int UPC = (H % 16 == 0) ? 16 : 8;
     const int nslices = H / UPC;
     const int nsm = sm_count();

@@ -72,6 +72,11 @@ int e2e_lstm_unpack_grads(void* stream, int I, int H, float* dkernel, float* dbi
  * Hout [rows][ndir*H] must be zero-initialised (rows with t >= len stay 0).
  * ctr_ws: >= 4*ndir*ceil(B/4) bytes of scratch; err_flag: device int set to 1 if a
  * step barrier ever times out. */
+/* 0 (default): thread-block-cluster / DSMEM recurrence when H/16 is 1,2,4,8 or 16;
+ * 1: always the L2-exchange kernel with per-group global counters. */
+int e2e_set_rec_mode(int mode);
+/* test hook: device buffer (>= 5*T int64) receiving per-step clock64 stamps of the forward cluster kernel, or NULL */
+int e2e_set_rec_debug(long long* dbg);
 int e2e_lstm_rec_fwd(void* stream, int B, int T, int Tp, int H, int ndir, long long sb, long long st,
                      float* G, float* Hout, float* Cst, const float* Wh, const int* lens,
                      void* ctr_ws, size_t ctr_ws_bytes, int* err_flag);

@@ -53,16 +53,30 @@ def test_gemm_strided_views():
     assert relerr(cs, big[:, 8:24].cpu().numpy().sum(0)) < 2e-5
 
 
+@pytest.mark.parametrize("rec_mode", [0, 1])
 @pytest.mark.parametrize("B,T_,I,H", [(3, 11, 6, 8), (5, 20, 12, 16), (17, 9, 40, 24), (4, 30, 40, 256),
-                                      (70, 6, 16, 32)])
-def test_bilstm_layer_fwd_bwd(B, T_, I, H):
+                                      (70, 6, 16, 32), (33, 25, 24, 128), (64, 40, 16, 256)])
+def test_bilstm_layer_fwd_bwd(B, T_, I, H, rec_mode):
+    """rec_mode 0 = cluster/DSMEM recurrence where eligible, 1 = L2-exchange kernel."""
+    from e2e_asr_b200 import _lib
+    _lib.lib().e2e_set_rec_mode(rec_mode)
+    try:
+        _bilstm_case(B, T_, I, H)
+    finally:
+        _lib.lib().e2e_set_rec_mode(0)
+
+
+def _bilstm_case(B, T_, I, H):
     rng = np.random.default_rng(B + T_ + I + H)
     lens = rng.integers(1, T_ + 1, size=B)
     lens[0] = T_
     x = rng.standard_normal((B, T_, I)).astype(np.float32)
     for b in range(B):
         x[b, lens[b]:] = 0
-    ks = [rng.uniform(-0.3, 0.3, (I + H, 4 * H)).astype(np.float32) for _ in range(2)]
+    # weight scale keeps the recurrence non-chaotic (gain ~1.2, the reference's U(+-0.075) at
+    # H=256): in a chaotic regime any rounding difference is amplified exponentially with t
+    ws = min(0.3, 1.2 / np.sqrt(H))
+    ks = [rng.uniform(-ws, ws, (I + H, 4 * H)).astype(np.float32) for _ in range(2)]
     bs = [rng.uniform(-0.3, 0.3, (4 * H,)).astype(np.float32) for _ in range(2)]
     ref_out, cache = om.birnn_layer_fwd(x.astype(np.float64), lens, ks[0].astype(np.float64), bs[0].astype(np.float64),
                                         ks[1].astype(np.float64), bs[1].astype(np.float64))
