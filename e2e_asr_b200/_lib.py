@@ -37,8 +37,14 @@ _SIGS = {
     "e2e_scale": "pzppf",
     "e2e_mean": "pipp",
     "e2e_axpy": "pzfpp",
+    "e2e_gemm_f64": "piiipipipip",
+    "e2e_lstm_step_f64": "piippppi",
+    "e2e_attn_beam_f64": "piiiipppppppi",
+    "e2e_logsoftmax_topk_f64": "piippdpippp",
+    "e2e_embed_gather_f64": "piipppi",
 }
-_CT = {"p": ctypes.c_void_p, "i": ctypes.c_int, "l": ctypes.c_longlong, "z": ctypes.c_size_t, "f": ctypes.c_float}
+_CT = {"p": ctypes.c_void_p, "i": ctypes.c_int, "l": ctypes.c_longlong, "z": ctypes.c_size_t, "f": ctypes.c_float,
+       "d": ctypes.c_double}
 
 
 class DecLoopFwdArgs(ctypes.Structure):

@@ -1,0 +1,237 @@
+// Float64 decoder-step kernels for beam search (reference beam_search.py:137-221).
+//
+// The reference scores hypotheses in float64 (its zero states are np.zeros, so every
+// GEMV after the embedding is promoted) while weights, embeddings,
+// encoder states and enc.AttnW stay float32.  These kernels keep exactly that dtype
+// flow on the device -- fp32 operands are widened at load, all arithmetic is fp64 --
+// and are batched over every live hypothesis of every utterance.
+#include "common.cuh"
+
+namespace e2e {
+
+// C[M,N] (f64) = A[M,K] (f64) . B[K,N] (f32 weights) + bias[N] (f32)       32x32 tile, 4x1 per thread... simple
+constexpr int DT = 32, DK = 16;
+__global__ void __launch_bounds__(256)
+gemm_f64_kernel(int M, int N, int K, const double* __restrict__ A, int lda, const float* __restrict__ B, int ldb,
+                double* __restrict__ C, int ldc, const float* __restrict__ bias) {
+    __shared__ double As[DK][DT + 1];
+    __shared__ double Bs[DK][DT + 1];
+    const int tx = threadIdx.x % 32, ty = threadIdx.x / 32;      // 32 x 8 threads, 4 rows each
+    const int m0 = blockIdx.y * DT, n0 = blockIdx.x * DT;
+    double acc[4] = {0.0, 0.0, 0.0, 0.0};
+    for (int k0 = 0; k0 < K; k0 += DK) {
+        for (int i = threadIdx.x; i < DT * DK; i += 256) {
+            int r = i / DK, k = i % DK;
+            As[k][r] = (m0 + r < M && k0 + k < K) ? A[(size_t)(m0 + r) * lda + k0 + k] : 0.0;
+        }
+        for (int i = threadIdx.x; i < DT * DK; i += 256) {
+            int k = i / DT, c = i % DT;
+            Bs[k][c] = (k0 + k < K && n0 + c < N) ? (double)B[(size_t)(k0 + k) * ldb + n0 + c] : 0.0;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < DK; ++k) {
+            double b = Bs[k][tx];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) acc[j] = fma(As[k][ty * 4 + j], b, acc[j]);
+        }
+        __syncthreads();
+    }
+    const int n = n0 + tx;
+    if (n < N) {
+        double bv = bias ? (double)bias[n] : 0.0;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            int m = m0 + ty * 4 + j;
+            if (m < M) C[(size_t)m * ldc + n] = acc[j] + bv;
+        }
+    }
+}
+
+int gemm_f64(cudaStream_t st, int M, int N, int K, const double* A, int lda, const float* B, int ldb, double* C,
+             int ldc, const float* bias) {
+    if (M <= 0 || N <= 0) return 0;
+    gemm_f64_kernel<<<dim3(cdiv(N, DT), cdiv(M, DT)), 256, 0, st>>>(M, N, K, A, lda, B, ldb, C, ldc, bias);
+    E2E_LAUNCH_CHECK();
+    return 0;
+}
+
+// BasicLSTM.__call__ (basic_lstm.py:14-23) on pre-activations z [n,4H] (i|j|f|o); returns (new_c, new_h)
+__global__ void lstm_step_f64_kernel(int n, int H, const double* __restrict__ z, const double* __restrict__ c_prev,
+                                     double* __restrict__ c_out, double* __restrict__ h_out, int ldh) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n * H) return;
+    int r = i / H, u = i % H;
+    const double* g = z + (size_t)r * 4 * H;
+    double si = 1.0 / (1.0 + exp(-g[u]));
+    double tj = tanh(g[H + u]);
+    double sf = 1.0 / (1.0 + exp(-(g[2 * H + u] + 1.0)));
+    double so = 1.0 / (1.0 + exp(-g[3 * H + u]));
+    double cn = c_prev[(size_t)r * H + u] * sf + si * tj;
+    c_out[(size_t)r * H + u] = cn;
+    h_out[(size_t)r * ldh + u] = so * tanh(cn);
+}
+int lstm_step_f64(cudaStream_t st, int n, int H, const double* z, const double* c_prev, double* c_out, double* h_out,
+                  int ldh) {
+    if (n <= 0) return 0;
+    lstm_step_f64_kernel<<<cdiv(n * H, 256), 256, 0, st>>>(n, H, z, c_prev, c_out, h_out, ldh);
+    E2E_LAUNCH_CHECK();
+    return 0;
+}
+
+// calc_attention (beam_search.py:150-159): one CTA per hypothesis; the utterance's encoder rows are
+// [row_off, row_off + T) of enc / HF (already length-sliced: NO mask, beam_search.py:155).
+__global__ void __launch_bounds__(256)
+attn_beam_f64_kernel(int A, int D, const float* __restrict__ HF, const float* __restrict__ enc,
+                     const int* __restrict__ row_off, const int* __restrict__ Tlen, const double* __restrict__ y,
+                     const float* __restrict__ v, double* __restrict__ ctx, int ldctx) {
+    extern __shared__ double sm[];
+    double* y_s = sm;          // [A]
+    double* s_s = sm + A;      // [T]
+    __shared__ double red[32];
+    const int r = blockIdx.x, tid = threadIdx.x, lane = tid % 32, warp = tid / 32, nw = 8;
+    const int off = row_off[r], T = Tlen[r];
+    for (int a = tid; a < A; a += 256) y_s[a] = y[(size_t)r * A + a];
+    __syncthreads();
+    for (int tau = warp; tau < T; tau += nw) {
+        double p = 0.0;
+        for (int a = lane; a < A; a += 32)
+            p += tanh((double)HF[(size_t)(off + tau) * A + a] + y_s[a]) * (double)v[a];
+        for (int o = 16; o > 0; o >>= 1) p += __shfl_xor_sync(0xffffffffu, p, o);
+        if (lane == 0) s_s[tau] = p;
+    }
+    __syncthreads();
+    double mx = -INFINITY;
+    for (int tau = tid; tau < T; tau += 256) mx = fmax(mx, s_s[tau]);
+    for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    if (lane == 0) red[warp] = mx;
+    __syncthreads();
+    mx = red[0];
+    for (int w = 1; w < nw; ++w) mx = fmax(mx, red[w]);
+    __syncthreads();
+    double sum = 0.0;
+    for (int tau = tid; tau < T; tau += 256) {
+        double e = exp(s_s[tau] - mx);
+        s_s[tau] = e;
+        sum += e;
+    }
+    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    if (lane == 0) red[warp] = sum;
+    __syncthreads();
+    sum = 0.0;
+    for (int w = 0; w < nw; ++w) sum += red[w];
+    for (int d = tid; d < D; d += 256) {
+        double c = 0.0;
+        for (int tau = 0; tau < T; ++tau) c = fma(s_s[tau] / sum, (double)enc[(size_t)(off + tau) * D + d], c);
+        ctx[(size_t)r * ldctx + d] = c;
+    }
+}
+int attn_beam_f64(cudaStream_t st, int n, int A, int D, int Tmax, const float* HF, const float* enc,
+                  const int* row_off, const int* Tlen, const double* y, const float* v, double* ctx, int ldctx) {
+    if (n <= 0) return 0;
+    size_t smem = sizeof(double) * (A + Tmax);
+    if (smem > 48 * 1024)
+        E2E_CHECK_CUDA(cudaFuncSetAttribute(attn_beam_f64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attn_beam_f64_kernel<<<n, 256, smem, st>>>(A, D, HF, enc, row_off, Tlen, y, v, ctx, ldctx);
+    E2E_LAUNCH_CHECK();
+    return 0;
+}
+
+// get_top_k tail (beam_search.py:196-214): combined = log(softmax(dec)) + lm_weight*log(softmax(lm));
+// the k largest entries per row (as a set, like np.argpartition), written in descending score order.
+__global__ void __launch_bounds__(256)
+logsoftmax_topk_f64_kernel(int V, const double* __restrict__ logits, const double* __restrict__ lm_logits,
+                           double lm_weight, const int* __restrict__ krow, int kmax, int* __restrict__ out_idx,
+                           double* __restrict__ out_val, double* __restrict__ scratch) {
+    __shared__ double red[32];
+    __shared__ int redi[32];
+    const int r = blockIdx.x, tid = threadIdx.x, lane = tid % 32, warp = tid / 32, nw = 8;
+    const double* x = logits + (size_t)r * V;
+    double* comb = scratch + (size_t)r * V;
+    auto block_max = [&](double v) {
+        for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+        if (lane == 0) red[warp] = v;
+        __syncthreads();
+        double m = red[0];
+        for (int w = 1; w < nw; ++w) m = fmax(m, red[w]);
+        __syncthreads();
+        return m;
+    };
+    auto block_sum = [&](double v) {
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if (lane == 0) red[warp] = v;
+        __syncthreads();
+        double s = 0.0;
+        for (int w = 0; w < nw; ++w) s += red[w];
+        __syncthreads();
+        return s;
+    };
+    double mx = -INFINITY;
+    for (int v = tid; v < V; v += 256) mx = fmax(mx, x[v]);
+    mx = block_max(mx);
+    double s = 0.0;
+    for (int v = tid; v < V; v += 256) s += exp(x[v] - mx);
+    s = block_sum(s);
+    for (int v = tid; v < V; v += 256) comb[v] = log(exp(x[v] - mx) / s);
+    if (lm_logits != nullptr) {
+        const double* xl = lm_logits + (size_t)r * V;
+        double ml = -INFINITY;
+        for (int v = tid; v < V; v += 256) ml = fmax(ml, xl[v]);
+        ml = block_max(ml);
+        double sl = 0.0;
+        for (int v = tid; v < V; v += 256) sl += exp(xl[v] - ml);
+        sl = block_sum(sl);
+        for (int v = tid; v < V; v += 256) comb[v] += lm_weight * log(exp(xl[v] - ml) / sl);
+    }
+    __syncthreads();
+    const int k = krow[r];
+    for (int j = 0; j < kmax; ++j) {
+        if (j >= k) {
+            if (tid == 0) { out_idx[(size_t)r * kmax + j] = -1; out_val[(size_t)r * kmax + j] = -INFINITY; }
+            continue;
+        }
+        double best = -INFINITY;
+        int bi = 0x7fffffff;
+        for (int v = tid; v < V; v += 256) {
+            double c = comb[v];
+            if (c > best || (c == best && v < bi)) { best = c; bi = v; }
+        }
+        for (int o = 16; o > 0; o >>= 1) {
+            double ob = __shfl_xor_sync(0xffffffffu, best, o);
+            int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+            if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; }
+        }
+        if (lane == 0) { red[warp] = best; redi[warp] = bi; }
+        __syncthreads();
+        if (tid == 0) {
+            for (int w = 1; w < nw; ++w)
+                if (red[w] > best || (red[w] == best && redi[w] < bi)) { best = red[w]; bi = redi[w]; }
+            out_idx[(size_t)r * kmax + j] = bi;
+            out_val[(size_t)r * kmax + j] = best;
+            comb[bi] = -INFINITY;
+        }
+        __syncthreads();
+    }
+}
+int logsoftmax_topk_f64(cudaStream_t st, int n, int V, const double* logits, const double* lm_logits,
+                        double lm_weight, const int* krow, int kmax, int* out_idx, double* out_val, double* scratch) {
+    if (n <= 0) return 0;
+    logsoftmax_topk_f64_kernel<<<n, 256, 0, st>>>(V, logits, lm_logits, lm_weight, krow, kmax, out_idx, out_val, scratch);
+    E2E_LAUNCH_CHECK();
+    return 0;
+}
+
+// rows of a float32 table widened to float64: out[r, :E] = (double) emb[ids[r], :]
+__global__ void embed_gather_f64_kernel(int n, int E, const float* __restrict__ emb, const long long* __restrict__ ids,
+                                        double* __restrict__ out, int ldo) {
+    int r = blockIdx.x;
+    for (int e = threadIdx.x; e < E; e += blockDim.x) out[(size_t)r * ldo + e] = (double)emb[(size_t)ids[r] * E + e];
+}
+int embed_gather_f64(cudaStream_t st, int n, int E, const float* emb, const long long* ids, double* out, int ldo) {
+    if (n <= 0) return 0;
+    embed_gather_f64_kernel<<<n, 128, 0, st>>>(n, E, emb, ids, out, ldo);
+    E2E_LAUNCH_CHECK();
+    return 0;
+}
+
+}  // namespace e2e

@@ -66,6 +66,13 @@ int clip_by_norm(cudaStream_t, size_t, float*, const float*, float, float*);
 int scale_inplace(cudaStream_t, size_t, float*, const float*, float);
 int mean_vec(cudaStream_t, int, const float*, float*);
 int axpy(cudaStream_t, size_t, float, const float*, float*);
+int gemm_f64(cudaStream_t, int, int, int, const double*, int, const float*, int, double*, int, const float*);
+int lstm_step_f64(cudaStream_t, int, int, const double*, const double*, double*, double*, int);
+int attn_beam_f64(cudaStream_t, int, int, int, int, const float*, const float*, const int*, const int*, const double*,
+                  const float*, double*, int);
+int logsoftmax_topk_f64(cudaStream_t, int, int, const double*, const double*, double, const int*, int, int*, double*,
+                        double*);
+int embed_gather_f64(cudaStream_t, int, int, const float*, const long long*, double*, int);
 
 static int gemm_any(cudaStream_t st, int mode, int tA, int tB, int M, int N, int K, const float* A, int lda,
                     const float* B, int ldb, float* C, int ldc, const float* bias, const float* Z, int ldz,
@@ -273,5 +280,26 @@ int e2e_scale(void* stream, size_t n, float* x, const float* dev_scalar, float a
 }
 int e2e_mean(void* stream, int n, const float* x, float* out) { return mean_vec(ST(stream), n, x, out); }
 int e2e_axpy(void* stream, size_t n, float a, const float* x, float* y) { return axpy(ST(stream), n, a, x, y); }
+
+int e2e_gemm_f64(void* stream, int M, int N, int K, const double* A, int lda, const float* B, int ldb, double* C,
+                 int ldc, const float* bias) {
+    return gemm_f64(ST(stream), M, N, K, A, lda, B, ldb, C, ldc, bias);
+}
+int e2e_lstm_step_f64(void* stream, int n, int H, const double* z, const double* c_prev, double* c_out, double* h_out,
+                      int ldh) {
+    return lstm_step_f64(ST(stream), n, H, z, c_prev, c_out, h_out, ldh);
+}
+int e2e_attn_beam_f64(void* stream, int n, int A, int D, int Tmax, const float* HF, const float* enc,
+                      const int* row_off, const int* Tlen, const double* y, const float* v, double* ctx, int ldctx) {
+    return attn_beam_f64(ST(stream), n, A, D, Tmax, HF, enc, row_off, Tlen, y, v, ctx, ldctx);
+}
+int e2e_logsoftmax_topk_f64(void* stream, int n, int V, const double* logits, const double* lm_logits,
+                            double lm_weight, const int* krow, int kmax, int* out_idx, double* out_val,
+                            double* scratch) {
+    return logsoftmax_topk_f64(ST(stream), n, V, logits, lm_logits, lm_weight, krow, kmax, out_idx, out_val, scratch);
+}
+int e2e_embed_gather_f64(void* stream, int n, int E, const float* emb, const long long* ids, double* out, int ldo) {
+    return embed_gather_f64(ST(stream), n, E, emb, ids, out, ldo);
+}
 
 }  // extern "C"

@@ -161,6 +161,23 @@ int e2e_ctc_fwd_grad(void* stream, int T, int B, int C, long long sb, long long 
                      const int* label_lens, int max_label_len, float* alpha_ws, float* loss_b,
                      float* grad, float out_scale);
 
+/* Beam search decoder step in float64 (beam_search.py:137-221; dtype flow of SURVEY.md
+ * A.6: fp32 weights / embeddings / encoder states widened at load, fp64 arithmetic),
+ * batched over every live hypothesis.  BasicLSTM.__call__ (basic_lstm.py:14-23),
+ * calc_attention (beam_search.py:150-159, no length mask), get_top_k's
+ * log-softmax + lm_weight term + top-k (beam_search.py:196-214). */
+int e2e_gemm_f64(void* stream, int M, int N, int K, const double* A, int lda, const float* B, int ldb,
+                 double* C, int ldc, const float* bias);
+int e2e_lstm_step_f64(void* stream, int n, int H, const double* z, const double* c_prev, double* c_out,
+                      double* h_out, int ldh);
+int e2e_attn_beam_f64(void* stream, int n, int A, int D, int Tmax, const float* HF, const float* enc,
+                      const int* row_off, const int* Tlen, const double* y, const float* v, double* ctx,
+                      int ldctx);
+int e2e_logsoftmax_topk_f64(void* stream, int n, int V, const double* logits, const double* lm_logits,
+                            double lm_weight, const int* krow, int kmax, int* out_idx, double* out_val,
+                            double* scratch);
+int e2e_embed_gather_f64(void* stream, int n, int E, const float* emb, const long long* ids, double* out, int ldo);
+
 /* tf.clip_by_global_norm (seq2seq_model.py:150-151) on the flat gradient buffer */
 int e2e_sumsq(void* stream, size_t n, const float* x, float* partials296, float* out, float sign, int accumulate);
 int e2e_clip_by_norm(void* stream, size_t n, float* x, const float* sumsq, float clip, float* norm_out);

@@ -76,3 +76,29 @@ def test_train_step_tensor_core_modes(mode, rtol):
             print(mode, "worst grad rel err", worst)
     finally:
         ops.set_gemm_mode("fp32")
+
+
+@pytest.mark.parametrize("cname", ["tiny", "tiny_b", "cfg1"])
+def test_greedy_decode_ids_bit_exact(cname):
+    """Eval-mode graph: always max_output steps, argmax feedback.  Token ids
+    extracted as eval_model.py:84-87 must equal the oracle's greedy ids exactly."""
+    from oracle import beam as ob
+    cfg = synth.get_config(cname)
+    w = synth.make_weights(cfg, bias_noise=0.1)
+    w["model/rnn_decoder_char/rnn/OutputProjection/kernel"] = w["model/rnn_decoder_char/rnn/OutputProjection/kernel"] * 6.0
+    batch = synth.make_batch(cfg)
+    model = build_model(cfg, w, device="cuda:0", isTraining=False, ctc=False)
+    model.run_step(batch)
+    logits = model.outputs["char"].detach().cpu().numpy()
+    U = cfg.U
+    assert logits.shape == (U * cfg.B, cfg.V)
+    ids = ob.greedy_ids_from_logits(logits, cfg.B)
+    # oracle: same encoder states (float64), greedy decoder with len := max_output
+    W64 = {k: v.astype(np.float64) for k, v in w.items()}
+    states, lens_d, _ = om.encoder_fwd(W64, batch["logmel"].astype(np.float64), batch["logmel_len"], {"char": cfg.L})
+    ref_logits, _ = om.attn_decoder_fwd(W64, "char", batch["char"].T, np.full(cfg.B, U), states[cfg.L],
+                                        lens_d[cfg.L], mode="greedy", max_steps=U)
+    ref_ids = ob.greedy_ids_from_logits(ref_logits, cfg.B)
+    np.testing.assert_array_equal(ids, ref_ids)
+    e = np.abs(logits - ref_logits).max() / np.abs(ref_logits).max()
+    assert e < 1e-4
