@@ -24,6 +24,8 @@ _SIGS = {
     "e2e_embed_scatter_add": "piipppi",
     "e2e_decoder_loop_fwd": "pp",
     "e2e_decoder_loop_bwd": "pp",
+    "e2e_decoder_persist_fwd": "pp",
+    "e2e_decoder_persist_bwd": "ppppp",
     "e2e_attn_fwd": "piiiiipppppppi",
     "e2e_dec_pointwise_fwd": "piiipppipppippip",
     "e2e_mask_rows": "piiipp",
@@ -57,6 +59,13 @@ class DecLoopFwdArgs(ctypes.Structure):
 class DecLoopBwdArgs(ctypes.Structure):
     _fields_ = [("f", DecLoopFwdArgs)] + [(n, ctypes.c_void_p) for n in (
         "dcat", "dgates", "dxh", "dy", "dv_part", "dHF", "denc", "dc_carry")]
+
+
+class DecPersistArgs(ctypes.Structure):
+    _fields_ = ([(n, ctypes.c_int) for n in ("B", "U", "Hd", "A", "D", "Tn", "Tp")] +
+                [(n, ctypes.c_void_p) for n in ("W_ch", "pre_g", "q_k", "q_b", "attn_v", "HF", "enc", "enc_len",
+                                                "lens", "cat", "hprev", "cprev", "acts", "y", "alpha", "dcat", "dz",
+                                                "dch", "dy", "ds", "dc_carry", "ctr", "err")])
 
 
 _lib = None

@@ -68,7 +68,7 @@ class AttnDecoder(Decoder):
         lens = ops.to_i32(seq_len, dev)
         enc_len = ops.to_i32(seq_len_inp, dev)
         if self.input_rule() == "teacher":
-            return ops.AttnDecoderFn.apply(
+            return ops.attn_decoder_apply(
                 enc, v["emb"], v["attn_w"], v["attn_v"], v["lm_k"], v["lm_b"], v["dec_k"], v["dec_b"], v["q_k"],
                 v["q_b"], v["ap_k"], v["ap_b"], v["out_k"], v["out_b"], v["in_k"], v["in_b"], v["sp_k"], v["sp_b"],
                 decoder_inp, lens, enc_len, U, self.stash)

@@ -66,6 +66,7 @@ int clip_by_norm(cudaStream_t, size_t, float*, const float*, float, float*);
 int scale_inplace(cudaStream_t, size_t, float*, const float*, float);
 int mean_vec(cudaStream_t, int, const float*, float*);
 int axpy(cudaStream_t, size_t, float, const float*, float*);
+int dec_persist(cudaStream_t, bool, const e2e_dec_persist_args*, float*, float*, float*);
 int gemm_f64(cudaStream_t, int, int, int, const double*, int, const float*, int, double*, int, const float*);
 int lstm_step_f64(cudaStream_t, int, int, const double*, const double*, double*, double*, int);
 int attn_beam_f64(cudaStream_t, int, int, int, int, const float*, const float*, const int*, const int*, const double*,
@@ -235,6 +236,12 @@ int e2e_decoder_loop_bwd(void* stream, const e2e_dec_loop_bwd_args* g) {
     return 0;
 }
 
+int e2e_decoder_persist_fwd(void* stream, const e2e_dec_persist_args* a) {
+    return dec_persist(ST(stream), false, a, nullptr, nullptr, nullptr);
+}
+int e2e_decoder_persist_bwd(void* stream, const e2e_dec_persist_args* a, float* denc, float* dHF, float* dv_part) {
+    return dec_persist(ST(stream), true, a, denc, dHF, dv_part);
+}
 int e2e_attn_fwd(void* stream, int B, int Tn, int Tp, int A, int D, const float* HF, const float* enc,
                  const int* enc_len, const float* y, const float* v, float* alpha, float* ctx, int ldctx) {
     return attn_fwd(ST(stream), B, Tn, Tp, A, D, HF, enc, enc_len, y, v, alpha, ctx, ldctx);

@@ -1,0 +1,535 @@
+// Persistent attention-decoder loop: ALL U teacher-forced steps of
+// AttnDecoder.__call__'s raw_rnn body (attn_decoder.py:76-166) in one
+// cooperative launch per direction (forward / backward), replacing ~5 launches per
+// step.  State-independent work is batched outside (ops.AttnDecoderFnV2); per step
+// the kernel runs three grid-synchronous phases over all CTAs:
+//
+//   forward   G: gates = pre_g[t] + [ctx_{t-1} | h_{t-1}] . W_ch  (+ LSTM pointwise)
+//                W_ch = [W_in_c.W_x ; W_h] folds InputProjection's ctx half into the
+//                decoder-LSTM kernel, so xin is never materialised.  Tile = 16 rows x
+//                8 units; the CTA's 32 gate columns of W_ch stay in shared memory.
+//             Y: y = c_new . q_k + q_b            (query is the CELL state)
+//             A: masked-softmax attention read-out, CTA per (row, half of D)
+//   backward  A': attention backward per row -> ds, dy
+//             P : dc_new += dy . q_k^T, LSTM pointwise backward -> dz_t
+//             X : [dctx_{t-1} | dh_{t-1}] = dz_t . W_ch^T
+// dHF / dEnc (sums over all steps) are produced after the loop by two parallel
+// kernels from the stored ds_t, alpha_t, y_t, dctx_t -- no read-modify-write per step.
+// The dense products use mma.sync m16n8k8 with error-compensated TF32 (3xTF32).
+#include "../../include/e2e_asr_b200.h"
+#include "common.cuh"
+
+namespace e2e {
+
+namespace {
+
+constexpr int NTH = 256;
+
+__device__ __forceinline__ void split_tf32(float x, uint32_t& hi, uint32_t& lo) {
+    hi = __float_as_uint(x) & 0xFFFFE000u;
+    lo = __float_as_uint(x - __uint_as_float(hi));
+}
+__device__ __forceinline__ void mma_tf32(float (&d)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
+    asm volatile(
+        "mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+        : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+        : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+}
+// D[16 x 8] += A[16 x K] (rows a_s, stride lda, K range [k_begin,k_end)) . B, B[k][n] = bt[n*ldb + k]
+__device__ __forceinline__ void mma_block(float (&d)[4], const float* a_s, int lda, const float* bt, int ldb,
+                                          int k_begin, int k_end, int g, int tq) {
+    const float* a0 = a_s + g * lda;
+    const float* a1 = a_s + (g + 8) * lda;
+    const float* b0 = bt + g * ldb;
+    for (int k = k_begin + tq; k < k_end; k += 8) {
+        uint32_t ah[4], al[4], bh[2], bl[2];
+        split_tf32(a0[k], ah[0], al[0]);
+        split_tf32(a1[k], ah[1], al[1]);
+        split_tf32(a0[k + 4], ah[2], al[2]);
+        split_tf32(a1[k + 4], ah[3], al[3]);
+        split_tf32(b0[k], bh[0], bl[0]);
+        split_tf32(b0[k + 4], bh[1], bl[1]);
+        mma_tf32(d, al, bh);
+        mma_tf32(d, ah, bl);
+        mma_tf32(d, ah, bh);
+    }
+}
+
+// grid-wide barrier on a monotonically increasing counter (cooperative launch => co-resident)
+__device__ __forceinline__ void grid_barrier(unsigned* ctr, unsigned& epoch, int* err) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        red_release_gpu_add(ctr, 1u);
+        ++epoch;
+        spin_wait_ge(ctr, epoch * gridDim.x, err);
+    }
+    __syncthreads();
+}
+
+__device__ __forceinline__ float ldcg(const float* p) { return __ldcg(p); }
+
+}  // namespace
+
+// ======================================================================= forward
+__global__ void __launch_bounds__(NTH, 1) dec_fwd_persist_kernel(e2e_dec_persist_args p) {
+    extern __shared__ __align__(16) float smem[];
+    const int B = p.B, U = p.U, Hd = p.Hd, A = p.A, D = p.D, Tn = p.Tn, Tp = p.Tp;
+    const int K = D + Hd, G4 = 4 * Hd, CAT = Hd + D;
+    const int KS = K + 8;                      // Wt row stride
+    const int AS = K + 4;                      // A tile row stride
+    float* Wt = smem;                          // [32][KS]   W_ch^T slice of this CTA's column block
+    float* a_s = Wt + 32 * KS;                 // [16][AS]   A tile / scratch of the other phases
+    float* red = a_s + 16 * AS;                // [4][32][4] cross-warp partials (also 8 warps x 128 in phase Y)
+    const int tid = threadIdx.x, w = tid / 32, lane = tid % 32, g = lane / 4, tq = lane % 4;
+    const int NCB = Hd / 8, nrb = (B + 15) / 16, gtiles = nrb * NCB;
+    const bool resident = gtiles <= (int)gridDim.x;
+    unsigned epoch = 0;
+
+    auto load_wt = [&](int cb) {
+        // Wt[n][k] = W_ch[k][32*cb + n]
+        for (int i = tid; i < 32 * K; i += NTH) {
+            int k = i / 32, n = i % 32;
+            Wt[n * KS + k] = p.W_ch[(size_t)k * G4 + 32 * cb + n];
+        }
+    };
+    if (resident && (int)blockIdx.x < gtiles) load_wt(blockIdx.x % NCB);
+    __syncthreads();
+
+    for (int t = 0; t < U; ++t) {
+        // ------------------------------------------------------------ phase G
+        for (int tile = blockIdx.x; tile < gtiles; tile += gridDim.x) {
+            const int rb = tile / NCB, cb = tile % NCB;
+            if (!resident) { __syncthreads(); load_wt(cb); }
+            // A tile: [ctx_{t-1} (D) | h_{t-1} (Hd)] for rows rb*16 .. +16
+            for (int i = tid; i < 16 * (K / 4); i += NTH) {
+                int r = i / (K / 4), k = (i % (K / 4)) * 4;
+                int b = rb * 16 + r;
+                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (b < B) {
+                    if (k < D) {
+                        if (t > 0) v = __ldcg(reinterpret_cast<const float4*>(p.cat + ((size_t)(t - 1) * B + b) * CAT + Hd + k));
+                    } else {
+                        v = __ldcg(reinterpret_cast<const float4*>(p.hprev + ((size_t)t * B + b) * Hd + (k - D)));
+                    }
+                }
+                *reinterpret_cast<float4*>(a_s + r * AS + k) = v;
+            }
+            __syncthreads();
+            const int nt = w % 4, kh = w / 4;
+            float d[4] = {0.f, 0.f, 0.f, 0.f};
+            {
+                int kmid = (K / 16) * 8;       // split K (multiple of 8) between the two warps of an n-tile
+                mma_block(d, a_s, AS, Wt + (8 * nt) * KS, KS, kh ? kmid : 0, kh ? K : kmid, g, tq);
+            }
+            if (kh == 1) *reinterpret_cast<float4*>(red + (nt * 32 + lane) * 4) = make_float4(d[0], d[1], d[2], d[3]);
+            __syncthreads();
+            if (kh == 0) {
+                float4 o = *reinterpret_cast<const float4*>(red + (nt * 32 + lane) * 4);
+                d[0] += o.x; d[1] += o.y; d[2] += o.z; d[3] += o.w;
+                const bool even = (tq & 1) == 0;
+                const float s0 = even ? d[2] : d[0], s1 = even ? d[3] : d[1];
+                const float r0 = __shfl_xor_sync(0xffffffffu, s0, 1), r1 = __shfl_xor_sync(0xffffffffu, s1, 1);
+                float z0 = even ? d[0] : r0, z1 = even ? d[1] : r1, z2 = even ? r0 : d[2], z3 = even ? r1 : d[3];
+                const int prow = g + 8 * (tq & 1);
+                const int unit = cb * 8 + 2 * nt + (tq >> 1);
+                const int b = rb * 16 + prow;
+                if (b < B) {
+                    const size_t row = (size_t)t * B + b;
+                    float4 pg = __ldg(reinterpret_cast<const float4*>(p.pre_g + row * G4 + unit * 4));
+                    float si = sigmoidf_acc(z0 + pg.x);
+                    float tj = tanhf(z1 + pg.y);
+                    float sf = sigmoidf_acc(z2 + pg.z + 1.0f);
+                    float so = sigmoidf_acc(z3 + pg.w);
+                    float cp = __ldcg(p.cprev + row * Hd + unit);
+                    float cn = cp * sf + si * tj;
+                    float hn = tanhf(cn) * so;
+                    *reinterpret_cast<float4*>(p.acts + row * G4 + unit * 4) = make_float4(si, tj, sf, so);
+                    p.cat[row * CAT + unit] = cn;
+                    if (t + 1 < U) {      // committed state: finished rows keep (c, h)  (raw_rnn)
+                        const bool live = t < p.lens[b];
+                        float hp = a_s[prow * AS + D + unit];
+                        p.cprev[(row + B) * Hd + unit] = live ? cn : cp;
+                        p.hprev[(row + B) * Hd + unit] = live ? hn : hp;
+                    }
+                }
+            }
+            __syncthreads();
+        }
+        grid_barrier(p.ctr, epoch, p.err);
+        // ------------------------------------------------------------ phase Y: y = c_new . q_k + q_b
+        {
+            const int ytiles = nrb * (A / 8);
+            float* c_s = a_s;                       // [16][Hd+4]
+            float* q_s = a_s + 16 * (Hd + 4);       // [8][Hd+8]   q_s[n][k] = q_k[k][8*nt + n]
+            const int CS_ = Hd + 4, QS_ = Hd + 8;
+            for (int tile = blockIdx.x; tile < ytiles; tile += gridDim.x) {
+                const int rb = tile / (A / 8), nt = tile % (A / 8);
+                __syncthreads();
+                for (int i = tid; i < 16 * (Hd / 4); i += NTH) {
+                    int r = i / (Hd / 4), k = (i % (Hd / 4)) * 4;
+                    int b = rb * 16 + r;
+                    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (b < B) v = __ldcg(reinterpret_cast<const float4*>(p.cat + ((size_t)t * B + b) * CAT + k));
+                    *reinterpret_cast<float4*>(c_s + r * CS_ + k) = v;
+                }
+                for (int i = tid; i < 8 * Hd; i += NTH) {
+                    int k = i / 8, n = i % 8;
+                    q_s[n * QS_ + k] = p.q_k[(size_t)k * A + 8 * nt + n];
+                }
+                __syncthreads();
+                // 8 warps split K
+                const int ksteps = Hd / 8, per = (ksteps + 7) / 8;
+                const int k0 = min(ksteps, w * per) * 8, k1 = min(ksteps, (w + 1) * per) * 8;
+                float d[4] = {0.f, 0.f, 0.f, 0.f};
+                mma_block(d, c_s, CS_, q_s, QS_, k0, k1, g, tq);
+                __syncthreads();
+                float* part = red;                  // [8 warps][32 lanes][4]
+                *reinterpret_cast<float4*>(part + (w * 32 + lane) * 4) = make_float4(d[0], d[1], d[2], d[3]);
+                __syncthreads();
+                if (w == 0) {
+                    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+                    for (int ww = 0; ww < 8; ++ww) {
+                        float4 o = *reinterpret_cast<const float4*>(part + (ww * 32 + lane) * 4);
+                        acc.x += o.x; acc.y += o.y; acc.z += o.z; acc.w += o.w;
+                    }
+                    const int col = 8 * nt + 2 * tq;
+                    const float qb0 = p.q_b[col], qb1 = p.q_b[col + 1];
+                    int b0 = rb * 16 + g, b1 = rb * 16 + g + 8;
+                    if (b0 < B) *reinterpret_cast<float2*>(p.y + ((size_t)t * B + b0) * A + col) = make_float2(acc.x + qb0, acc.y + qb1);
+                    if (b1 < B) *reinterpret_cast<float2*>(p.y + ((size_t)t * B + b1) * A + col) = make_float2(acc.z + qb0, acc.w + qb1);
+                }
+            }
+        }
+        grid_barrier(p.ctr, epoch, p.err);
+        // ------------------------------------------------------------ phase A: attention read-out
+        {
+            float* y_s = a_s;                       // [A]
+            float* v_s = a_s + A;                   // [A]
+            float* s_s = a_s + 2 * A;               // [Tn]
+            float* redw = s_s + Tn;                 // [8]
+            for (int item = blockIdx.x; item < 2 * B; item += gridDim.x) {
+                const int b = item / 2, half = item % 2;
+                const int len = min(p.enc_len[b], Tn);
+                __syncthreads();
+                for (int a = tid; a < A; a += NTH) { y_s[a] = __ldcg(p.y + ((size_t)t * B + b) * A + a); v_s[a] = p.attn_v[a]; }
+                __syncthreads();
+                const float* HFb = p.HF + (size_t)b * Tp * A;
+                for (int tau = w; tau < len; tau += 8) {
+                    float acc = 0.f;
+                    for (int a = lane; a < A; a += 32) acc += v_s[a] * tanhf(HFb[(size_t)tau * A + a] + y_s[a]);
+                    acc = warp_sum(acc);
+                    if (lane == 0) s_s[tau] = acc;
+                }
+                __syncthreads();
+                float mx = -INFINITY;
+                for (int tau = tid; tau < len; tau += NTH) mx = fmaxf(mx, s_s[tau]);
+                mx = warp_max(mx);
+                if (lane == 0) redw[w] = mx;
+                __syncthreads();
+                mx = redw[0];
+                for (int ww = 1; ww < 8; ++ww) mx = fmaxf(mx, redw[ww]);
+                __syncthreads();
+                float sum = 0.f;
+                for (int tau = tid; tau < len; tau += NTH) {
+                    float e = expf(s_s[tau] - mx);
+                    s_s[tau] = e;
+                    sum += e;
+                }
+                sum = warp_sum(sum);
+                if (lane == 0) redw[w] = sum;
+                __syncthreads();
+                sum = 0.f;
+                for (int ww = 0; ww < 8; ++ww) sum += redw[ww];
+                const float inv = 1.0f / sum;
+                __syncthreads();
+                for (int tau = tid; tau < Tn; tau += NTH) {
+                    float al = tau < len ? s_s[tau] * inv : 0.f;
+                    if (tau < len) s_s[tau] = al;
+                    if (half == 0) p.alpha[((size_t)t * B + b) * Tn + tau] = al;
+                }
+                __syncthreads();
+                const float* encb = p.enc + (size_t)b * Tp * D;
+                const int dh = D / 2;
+                for (int dd = tid; dd < dh; dd += NTH) {
+                    const int dcol = half * dh + dd;
+                    float c = 0.f;
+                    for (int tau = 0; tau < len; ++tau) c = fmaf(s_s[tau], encb[(size_t)tau * D + dcol], c);
+                    p.cat[((size_t)t * B + b) * CAT + Hd + dcol] = c;
+                }
+            }
+        }
+        grid_barrier(p.ctr, epoch, p.err);
+    }
+}
+
+// ======================================================================= backward
+__global__ void __launch_bounds__(NTH, 1) dec_bwd_persist_kernel(e2e_dec_persist_args p) {
+    extern __shared__ __align__(16) float smem[];
+    const int B = p.B, U = p.U, Hd = p.Hd, A = p.A, D = p.D, Tn = p.Tn, Tp = p.Tp;
+    const int K = D + Hd, G4 = 4 * Hd, CAT = Hd + D;
+    const int NX = 24;                          // output columns of [dctx|dh] per CTA tile (3 n-tiles)
+    const int WS = G4 + 8;                      // Wt2 row stride
+    const int ZS = G4 + 4;                      // dz tile row stride
+    float* Wt2 = smem;                          // [NX][WS]  rows of W_ch owned by this CTA (phase X)
+    float* z_s = Wt2 + NX * WS;                 // [16][ZS]  dz tile / scratch of the other phases
+    float* red = z_s + 16 * ZS;                 // [8][32][4]
+    const int tid = threadIdx.x, w = tid / 32, lane = tid % 32, g = lane / 4, tq = lane % 4;
+    const int nrb = (B + 15) / 16;
+    const int NXB = (K + NX - 1) / NX, xtiles = nrb * NXB;
+    const bool resident = xtiles <= (int)gridDim.x;
+    unsigned epoch = 0;
+
+    auto load_wt2 = [&](int xb) {
+        for (int i = tid; i < NX * (G4 / 4); i += NTH) {
+            int n = i / (G4 / 4), c4 = (i % (G4 / 4)) * 4;
+            int kr = xb * NX + n;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (kr < K) v = *reinterpret_cast<const float4*>(p.W_ch + (size_t)kr * G4 + c4);
+            *reinterpret_cast<float4*>(Wt2 + n * WS + c4) = v;
+        }
+    };
+    if (resident && (int)blockIdx.x < xtiles) load_wt2(blockIdx.x % NXB);
+    __syncthreads();
+
+    for (int t = U - 1; t >= 0; --t) {
+        // ------------------------------------------------------------ phase A': attention backward (CTA per row)
+        {
+            float* y_s = z_s;                   // [A]
+            float* v_s = y_s + A;               // [A]
+            float* dctx_s = v_s + A;            // [D]
+            float* ds_s = dctx_s + D;           // [Tn]
+            float* acc_s = ds_s + Tn;           // [8][A]
+            float* redw = acc_s + 8 * A;        // [8]
+            for (int b = blockIdx.x; b < B; b += gridDim.x) {
+                const int len = min(p.enc_len[b], Tn);
+                const size_t row = (size_t)t * B + b;
+                __syncthreads();
+                for (int a = tid; a < A; a += NTH) { y_s[a] = p.y[row * A + a]; v_s[a] = p.attn_v[a]; }
+                for (int dd = tid; dd < D; dd += NTH) dctx_s[dd] = __ldcg(p.dcat + row * CAT + Hd + dd);
+                __syncthreads();
+                const float* al = p.alpha + row * Tn;
+                const float* encb = p.enc + (size_t)b * Tp * D;
+                float part = 0.f;
+                for (int tau = w; tau < len; tau += 8) {
+                    float acc = 0.f;
+                    for (int dd = lane; dd < D; dd += 32) acc = fmaf(dctx_s[dd], encb[(size_t)tau * D + dd], acc);
+                    acc = warp_sum(acc);
+                    if (lane == 0) { ds_s[tau] = acc; part += al[tau] * acc; }
+                }
+                if (lane == 0) redw[w] = part;
+                __syncthreads();
+                float dot = 0.f;
+                for (int ww = 0; ww < 8; ++ww) dot += redw[ww];
+                for (int tau = tid; tau < Tn; tau += NTH) {
+                    float dsv = tau < len ? al[tau] * (ds_s[tau] - dot) : 0.f;
+                    if (tau < len) ds_s[tau] = dsv;
+                    p.ds[row * Tn + tau] = dsv;
+                }
+                __syncthreads();
+                const float* HFb = p.HF + (size_t)b * Tp * A;
+                for (int a0 = 0; a0 < A; a0 += 32) {
+                    const int a = a0 + lane;
+                    float dya = 0.f;
+                    if (a < A)
+                        for (int tau = w; tau < len; tau += 8) {
+                            float th = tanhf(HFb[(size_t)tau * A + a] + y_s[a]);
+                            dya += ds_s[tau] * v_s[a] * (1.f - th * th);
+                        }
+                    if (a < A) acc_s[w * A + a] = dya;
+                }
+                __syncthreads();
+                for (int a = tid; a < A; a += NTH) {
+                    float dya = 0.f;
+                    for (int ww = 0; ww < 8; ++ww) dya += acc_s[ww * A + a];
+                    p.dy[row * A + a] = dya;
+                }
+            }
+        }
+        grid_barrier(p.ctr, epoch, p.err);
+        // ------------------------------------------------------------ phase P: dc_new += dy . q_k^T ; pointwise backward
+        {
+            const int NCB = Hd / 8, ptiles = nrb * NCB;
+            float* dy_s = z_s;                       // [16][A+4]
+            float* q_s = z_s + 16 * (A + 4);         // [8][A+8]   q_s[n][k] = q_k[8*cb + n][k]
+            const int DS_ = A + 4, QS_ = A + 8;
+            for (int tile = blockIdx.x; tile < ptiles; tile += gridDim.x) {
+                const int rb = tile / NCB, cb = tile % NCB;
+                __syncthreads();
+                for (int i = tid; i < 16 * (A / 4); i += NTH) {
+                    int r = i / (A / 4), k = (i % (A / 4)) * 4;
+                    int b = rb * 16 + r;
+                    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (b < B) v = __ldcg(reinterpret_cast<const float4*>(p.dy + ((size_t)t * B + b) * A + k));
+                    *reinterpret_cast<float4*>(dy_s + r * DS_ + k) = v;
+                }
+                for (int i = tid; i < 8 * A; i += NTH) {
+                    int n = i / A, k = i % A;
+                    q_s[n * QS_ + k] = p.q_k[(size_t)(8 * cb + n) * A + k];
+                }
+                __syncthreads();
+                const int ksteps = A / 8, per = (ksteps + 7) / 8;
+                const int k0 = min(ksteps, w * per) * 8, k1 = min(ksteps, (w + 1) * per) * 8;
+                float d[4] = {0.f, 0.f, 0.f, 0.f};
+                mma_block(d, dy_s, DS_, q_s, QS_, k0, k1, g, tq);
+                *reinterpret_cast<float4*>(red + (w * 32 + lane) * 4) = make_float4(d[0], d[1], d[2], d[3]);
+                __syncthreads();
+                // 16 rows x 8 units = 128 (row, unit) elements: thread tid < 128
+                if (tid < 128) {
+                    const int prow = tid / 8, ul = tid % 8;
+                    // fragment element (prow, ul): lane = (prow % 8) * 4 + ul / 2, reg = (prow / 8) * 2 + ul % 2
+                    const int fl = (prow % 8) * 4 + ul / 2, fr = (prow / 8) * 2 + (ul % 2);
+                    float dcq = 0.f;
+                    for (int ww = 0; ww < 8; ++ww) dcq += red[(ww * 32 + fl) * 4 + fr];
+                    const int b = rb * 16 + prow, unit = cb * 8 + ul;
+                    if (b < B) {
+                        const size_t row = (size_t)t * B + b;
+                        float4 dz = make_float4(0.f, 0.f, 0.f, 0.f);
+                        float dcc = 0.f;
+                        if (t < p.lens[b]) {
+                            float4 act = *reinterpret_cast<const float4*>(p.acts + row * G4 + unit * 4);
+                            float si = act.x, tj = act.y, sf = act.z, so = act.w;
+                            float tc = tanhf(p.cat[row * CAT + unit]);
+                            float dh = (t + 1 < U) ? __ldcg(p.dch + (row + B) * K + D + unit) : 0.f;
+                            float dc = __ldcg(p.dcat + row * CAT + unit) + dcq + p.dc_carry[(size_t)b * Hd + unit] +
+                                       dh * so * (1.f - tc * tc);
+                            dz.x = dc * tj * si * (1.f - si);
+                            dz.y = dc * si * (1.f - tj * tj);
+                            dz.z = dc * p.cprev[row * Hd + unit] * sf * (1.f - sf);
+                            dz.w = dh * tc * so * (1.f - so);
+                            dcc = dc * sf;
+                        }
+                        p.dc_carry[(size_t)b * Hd + unit] = dcc;
+                        *reinterpret_cast<float4*>(p.dz + row * G4 + unit * 4) = dz;
+                    }
+                }
+            }
+        }
+        grid_barrier(p.ctr, epoch, p.err);
+        // ------------------------------------------------------------ phase X: [dctx_{t-1} | dh_{t-1}] = dz_t . W_ch^T
+        for (int tile = blockIdx.x; tile < xtiles; tile += gridDim.x) {
+            const int rb = tile / NXB, xb = tile % NXB;
+            __syncthreads();
+            if (!resident) load_wt2(xb);
+            for (int i = tid; i < 16 * (G4 / 4); i += NTH) {
+                int r = i / (G4 / 4), k = (i % (G4 / 4)) * 4;
+                int b = rb * 16 + r;
+                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (b < B) v = __ldcg(reinterpret_cast<const float4*>(p.dz + ((size_t)t * B + b) * G4 + k));
+                *reinterpret_cast<float4*>(z_s + r * ZS + k) = v;
+            }
+            __syncthreads();
+            // 3 n-tiles x K split over warps: warp w -> n-tile w % 3 (warps 0..5), k-half w / 3; warps 6,7 idle
+            float d[4] = {0.f, 0.f, 0.f, 0.f};
+            const int nt = w % 3, kh = w / 3;
+            if (w < 6) {
+                int kmid = (G4 / 16) * 8;
+                mma_block(d, z_s, ZS, Wt2 + (8 * nt) * WS, WS, kh ? kmid : 0, kh ? G4 : kmid, g, tq);
+                if (kh == 1) *reinterpret_cast<float4*>(red + (nt * 32 + lane) * 4) = make_float4(d[0], d[1], d[2], d[3]);
+            }
+            __syncthreads();
+            if (w < 3) {
+                float4 o = *reinterpret_cast<const float4*>(red + (nt * 32 + lane) * 4);
+                d[0] += o.x; d[1] += o.y; d[2] += o.z; d[3] += o.w;
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const int r = g + 8 * (e / 2), col = xb * NX + 8 * nt + 2 * tq + (e % 2);
+                    const int b = rb * 16 + r;
+                    if (b < B && col < K) {
+                        const size_t row = (size_t)t * B + b;
+                        p.dch[row * K + col] = d[e];
+                        // dctx_{t-1} joins the AttnProjection part already in dcat[t-1]
+                        if (col < D && t > 0) p.dcat[(row - B) * CAT + Hd + col] += d[e];
+                    }
+                }
+            }
+        }
+        grid_barrier(p.ctr, epoch, p.err);
+    }
+}
+
+// ======================================================================= deferred sums over t
+// denc[b,tau,:] += sum_t alpha_t[b,tau] * dctx_t[b,:]      (one CTA per (b, tau))
+__global__ void __launch_bounds__(256) dec_denc_kernel(e2e_dec_persist_args p, float* __restrict__ denc) {
+    const int b = blockIdx.x / p.Tn, tau = blockIdx.x % p.Tn;
+    if (tau >= min(p.enc_len[b], p.Tn)) return;
+    const int CAT = p.Hd + p.D;
+    extern __shared__ float al_s[];          // [U]
+    for (int t = threadIdx.x; t < p.U; t += blockDim.x) al_s[t] = p.alpha[((size_t)t * p.B + b) * p.Tn + tau];
+    __syncthreads();
+    for (int d = threadIdx.x; d < p.D; d += blockDim.x) {
+        float acc = 0.f;
+        for (int t = 0; t < p.U; ++t) acc = fmaf(al_s[t], p.dcat[((size_t)t * p.B + b) * CAT + p.Hd + d], acc);
+        denc[((size_t)b * p.Tp + tau) * p.D + d] += acc;
+    }
+}
+// dHF[b,tau,a] = sum_t ds_t[b,tau] v_a (1 - th^2), th = tanh(HF[b,tau,a] + y_t[b,a]); dv_part[b*Tn+tau, a] = sum_t ds th
+__global__ void __launch_bounds__(128) dec_dhf_kernel(e2e_dec_persist_args p, float* __restrict__ dHF,
+                                                      float* __restrict__ dv_part) {
+    const int b = blockIdx.x / p.Tn, tau = blockIdx.x % p.Tn;
+    const bool valid = tau < min(p.enc_len[b], p.Tn);
+    extern __shared__ float ds_sm[];         // [U]
+    for (int t = threadIdx.x; t < p.U; t += blockDim.x) ds_sm[t] = valid ? p.ds[((size_t)t * p.B + b) * p.Tn + tau] : 0.f;
+    __syncthreads();
+    for (int a = threadIdx.x; a < p.A; a += blockDim.x) {
+        float acc = 0.f, accv = 0.f;
+        if (valid) {
+            const float hf = p.HF[((size_t)b * p.Tp + tau) * p.A + a], va = p.attn_v[a];
+            for (int t = 0; t < p.U; ++t) {
+                float dsv = ds_sm[t];
+                if (dsv != 0.f) {
+                    float th = tanhf(hf + p.y[((size_t)t * p.B + b) * p.A + a]);
+                    acc += dsv * va * (1.f - th * th);
+                    accv = fmaf(dsv, th, accv);
+                }
+            }
+            dHF[((size_t)b * p.Tp + tau) * p.A + a] = acc;
+        }
+        dv_part[(size_t)blockIdx.x * p.A + a] = accv;
+    }
+}
+
+static size_t fwd_smem_bytes(const e2e_dec_persist_args& p) {
+    int K = p.D + p.Hd;
+    size_t g = (size_t)32 * (K + 8) + 16 * (K + 4) + 8 * 32 * 4;
+    size_t yph = (size_t)32 * (K + 8) + 16 * (p.Hd + 4) + 8 * (p.Hd + 8) + 8 * 32 * 4;
+    size_t aph = (size_t)32 * (K + 8) + 2 * p.A + p.Tn + 16;
+    return sizeof(float) * (max(g, max(yph, aph)) + 64);
+}
+static size_t bwd_smem_bytes(const e2e_dec_persist_args& p) {
+    int G4 = 4 * p.Hd;
+    size_t x = (size_t)24 * (G4 + 8) + 16 * (G4 + 4) + 8 * 32 * 4;
+    size_t a = (size_t)24 * (G4 + 8) + 2 * p.A + p.D + p.Tn + 8 * p.A + 16;
+    size_t pp = (size_t)24 * (G4 + 8) + 16 * (p.A + 4) + 8 * (p.A + 8) + 16 * (G4 + 4) + 8 * 32 * 4;
+    return sizeof(float) * (max(x, max(a, pp)) + 64);
+}
+
+int dec_persist(cudaStream_t st, bool bwd, const e2e_dec_persist_args* a, float* denc, float* dHF, float* dv_part) {
+    e2e_dec_persist_args p = *a;
+    E2E_REQUIRE(p.Hd % 8 == 0 && p.A % 8 == 0 && p.D % 8 == 0, "decoder_persist: Hd, A, D must be multiples of 8");
+    E2E_REQUIRE(2 * p.A + p.Tn + 16 <= 16 * (p.D + p.Hd + 4) && 10 * p.A + p.D + p.Tn + 16 <= 16 * (4 * p.Hd + 4),
+                "decoder_persist: attention length %d too long for the shared-memory scratch", p.Tn);
+    if (p.B <= 0 || p.U <= 0) return 0;
+    const void* fn = bwd ? (const void*)dec_bwd_persist_kernel : (const void*)dec_fwd_persist_kernel;
+    size_t smem = bwd ? bwd_smem_bytes(p) : fwd_smem_bytes(p);
+    E2E_REQUIRE(smem <= 227 * 1024, "decoder_persist: shapes need %zu B of shared memory", smem);
+    E2E_CHECK_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int nsm = sm_count();
+    int nrb = (p.B + 15) / 16;
+    int want = bwd ? max(max(p.B, nrb * (p.Hd / 8)), nrb * ((p.D + p.Hd + 23) / 24))
+                   : max(max(2 * p.B, nrb * (p.Hd / 8)), nrb * (p.A / 8));
+    int grid = min(nsm, want);
+    E2E_CHECK_CUDA(cudaMemsetAsync(p.ctr, 0, sizeof(unsigned), st));
+    void* args[] = {&p};
+    E2E_CHECK_CUDA(cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(NTH), args, smem, st));
+    ++g_launches;
+    if (bwd) {
+        dec_denc_kernel<<<p.B * p.Tn, 256, sizeof(float) * p.U, st>>>(p, denc);
+        E2E_LAUNCH_CHECK();
+        dec_dhf_kernel<<<p.B * p.Tn, 128, sizeof(float) * p.U, st>>>(p, dHF, dv_part);
+        E2E_LAUNCH_CHECK();
+    }
+    return 0;
+}
+
+}  // namespace e2e

@@ -347,6 +347,154 @@ class AttnDecoderFn(torch.autograd.Function):
                 dout_b, din_k, din_b, dsp_k, dsp_b, None, None, None, None, None)
 
 
+_DECODER_IMPL = "persist"      # "persist": one cooperative launch per direction; "loop": per-step kernels
+
+
+def set_decoder_impl(name):
+    global _DECODER_IMPL
+    assert name in ("persist", "loop")
+    _DECODER_IMPL = name
+
+
+def attn_decoder_apply(*args):
+    fn = AttnDecoderFnV2 if _DECODER_IMPL == "persist" else AttnDecoderFn
+    return fn.apply(*args)
+
+
+class AttnDecoderFnV2(torch.autograd.Function):
+    """Same contract as AttnDecoderFn, built on the persistent decoder kernels
+    (csrc/decoder_persist.cu).  InputProjection's ctx half is folded into the
+    decoder-LSTM kernel:  gates_t = pre_g[t] + [ctx_{t-1} | h_{t-1}] . W_ch with
+    W_ch = [in_k[Hd:] . Wx ; Wh] and pre_g = (m . in_k[:Hd] + in_b) . Wx + b, so the
+    sequential loop is gates -> attention only; the chain rule through the product
+    W_cx = in_k[Hd:] . Wx is applied after the loop."""
+
+    @staticmethod
+    def forward(ctx, enc, emb, attn_w, attn_v, lm_k, lm_b, dec_k, dec_b, q_k, q_b, ap_k, ap_b, out_k, out_b,
+                in_k, in_b, sp_k, sp_b, ids, lens_i32, enc_len_i32, U, stash):
+        dev = enc.device
+        st = _dev_state(dev)
+        B, Tn, D = enc.shape
+        V, E = emb.shape
+        Hl, Hd, A = lm_k.shape[1] // 4, dec_k.shape[1] // 4, q_k.shape[1]
+        f32 = dict(dtype=torch.float32, device=dev)
+        enc_flat, r0, r1 = flat_rows(enc)
+        assert r1 == 1, "encoder states must be batch-major"
+        Tp = r0
+        ids = ids[:U].contiguous()
+        u = torch.empty((U * B, E), **f32)
+        call("e2e_embed_gather", U * B, E, emb, ids, u)
+        Wx_lm, Wh_lm, bp_lm = _pack_lstm([lm_k], [lm_b], E, Hl, dev)
+        G_lm = gemm(u, Wx_lm, bias=bp_lm)
+        hl = torch.zeros((U * B, Hl), **f32)
+        C_lm = torch.empty((U * B, Hl), **f32)
+        call("e2e_lstm_rec_fwd", B, U, U, Hl, 1, 1, B, G_lm, hl, C_lm, Wh_lm, lens_i32, st["ctr"],
+             st["ctr"].numel() * 4, st["err"], work=float(U), tag="lm_rec_fwd")
+        m = gemm(hl, sp_k, bias=sp_b) if sp_k is not None else hl
+        pre = gemm(m, in_k[:Hd], bias=in_b)                          # [U*B, E]
+        # decoder-LSTM kernel in gate-interleaved layout, with the ctx half of InputProjection folded in
+        W_ch = torch.empty((D + Hd, 4 * Hd), **f32)
+        Wx_dec = torch.empty((E, 4 * Hd), **f32)
+        bp_dec = torch.empty((4 * Hd,), **f32)
+        call("e2e_lstm_pack_weights", E, Hd, dec_k, dec_b, Wx_dec, 4 * Hd, 0, W_ch[D:], bp_dec)
+        gemm(in_k[Hd:], Wx_dec, out=W_ch[:D])                        # W_cx = W_in_c . Wx
+        pre_g = gemm(pre, Wx_dec, bias=bp_dec)                       # [U*B, 4Hd]
+        HF = gemm(enc_flat, attn_w.view(D, A))
+        bufs = dict(cat=torch.empty((U * B, Hd + D), **f32), hprev=torch.zeros((U * B, Hd), **f32),
+                    cprev=torch.zeros((U * B, Hd), **f32), acts=torch.empty((U * B, 4 * Hd), **f32),
+                    y=torch.empty((U * B, A), **f32), alpha=torch.empty((U * B, Tn), **f32))
+        a = _lib.DecPersistArgs()
+        a.B, a.U, a.Hd, a.A, a.D, a.Tn, a.Tp = B, U, Hd, A, D, Tn, Tp
+        for k, v in dict(W_ch=W_ch, pre_g=pre_g, q_k=q_k, q_b=q_b, attn_v=attn_v, HF=HF, enc=enc_flat,
+                         enc_len=enc_len_i32, lens=lens_i32, ctr=st["ctr"], err=st["err"], **bufs).items():
+            setattr(a, k, v.data_ptr())
+        call("e2e_decoder_persist_fwd", a, work=float(U))
+        proj = gemm(bufs["cat"], ap_k, bias=ap_b)
+        logits = gemm(proj, out_k, bias=out_b)
+        call("e2e_mask_rows", U, B, V, logits, lens_i32)
+        ctx.save_for_backward(enc, emb, attn_w, attn_v, lm_k, dec_k, q_k, q_b, ap_k, out_k, in_k, sp_k, ids,
+                              lens_i32, enc_len_i32, u, Wx_lm, Wh_lm, G_lm, hl, C_lm, m, pre, pre_g, W_ch, Wx_dec,
+                              HF, proj, bufs["cat"], bufs["hprev"], bufs["cprev"], bufs["acts"], bufs["y"],
+                              bufs["alpha"])
+        ctx.dims = (B, Tn, D, V, E, Hl, Hd, A, U, Tp)
+        ctx.stash = stash
+        return logits
+
+    @staticmethod
+    def backward(ctx, dlogits):
+        (enc, emb, attn_w, attn_v, lm_k, dec_k, q_k, q_b, ap_k, out_k, in_k, sp_k, ids, lens_i32, enc_len_i32, u,
+         Wx_lm, Wh_lm, G_lm, hl, C_lm, m, pre, pre_g, W_ch, Wx_dec, HF, proj, cat, hprev, cprev, acts, y,
+         alpha) = ctx.saved_tensors
+        B, Tn, D, V, E, Hl, Hd, A, U, Tp = ctx.dims
+        dev = enc.device
+        st = _dev_state(dev)
+        f32 = dict(dtype=torch.float32, device=dev)
+        dlogits = dlogits.contiguous()
+        enc_flat, _, _ = flat_rows(enc)
+        nrows = enc_flat.shape[0]
+        dout_k = gemm(proj, dlogits, ta=True)
+        dout_b = colsum(dlogits)
+        dproj = gemm(dlogits, out_k, tb=True)
+        dap_k = gemm(cat, dproj, ta=True)
+        dap_b = colsum(dproj)
+        dcat = gemm(dproj, ap_k, tb=True)                             # [U*B, Hd+D]
+        out = dict(dcat=dcat, dz=torch.empty((U * B, 4 * Hd), **f32), dch=torch.empty((U * B, D + Hd), **f32),
+                   dy=torch.empty((U * B, A), **f32), ds=torch.empty((U * B, Tn), **f32),
+                   dc_carry=torch.zeros((B, Hd), **f32))
+        denc = torch.zeros((nrows, D), **f32)
+        dHF = torch.zeros((nrows, A), **f32)
+        dv_part = torch.empty((B * Tn, A), **f32)
+        a = _lib.DecPersistArgs()
+        a.B, a.U, a.Hd, a.A, a.D, a.Tn, a.Tp = B, U, Hd, A, D, Tn, Tp
+        for k, v in dict(W_ch=W_ch, pre_g=pre_g, q_k=q_k, q_b=q_b, attn_v=attn_v, HF=HF, enc=enc_flat,
+                         enc_len=enc_len_i32, lens=lens_i32, cat=cat, hprev=hprev, cprev=cprev, acts=acts, y=y,
+                         alpha=alpha, ctr=st["ctr"], err=st["err"], **out).items():
+            setattr(a, k, v.data_ptr())
+        call("e2e_decoder_persist_bwd", a, denc, dHF, dv_part, work=float(U))
+        dz, dy = out["dz"], out["dy"]
+        dq_k = gemm(cat[:, :Hd], dy, ta=True)
+        dq_b = colsum(dy)
+        dattn_v = colsum(dv_part)
+        # gates = pre.Wx + ctx_prev.(W_in_c.Wx) + h_prev.Wh + b   (columns gate-interleaved)
+        dW_cx = torch.zeros((D, 4 * Hd), **f32)
+        if U > 1:
+            gemm(cat[:(U - 1) * B, Hd:], dz[B:], ta=True, out=dW_cx)   # ctx_{t-1} pairs with dz_t
+        dWh_dec = gemm(hprev, dz, ta=True).view(1, Hd, 4 * Hd)
+        dWx_dec = gemm(pre, dz, ta=True)
+        gemm(in_k[Hd:], dW_cx, ta=True, out=dWx_dec, accumulate=True)  # + W_in_c^T . dW_cx
+        dbp_dec = colsum(dz)
+        ddec_k, ddec_b = _unpack_lstm(dWx_dec, dWh_dec, dbp_dec, E, Hd, 1, dev)
+        dpre = gemm(dz, Wx_dec, tb=True)                              # [U*B, E]
+        din_k = torch.empty((Hd + D, E), **f32)
+        gemm(m, dpre, ta=True, out=din_k[:Hd])
+        gemm(dW_cx, Wx_dec, tb=True, out=din_k[Hd:])                  # dW_in_c = dW_cx . Wx^T
+        din_b = colsum(dpre)
+        dm = gemm(dpre, in_k[:Hd], tb=True)
+        dsp_k = dsp_b = None
+        if sp_k is not None:
+            dsp_k = gemm(hl, dm, ta=True)
+            dsp_b = colsum(dm)
+            dm = gemm(dm, sp_k, tb=True)
+        call("e2e_lstm_rec_bwd", B, U, U, Hl, 1, 1, B, G_lm, C_lm, Wh_lm, dm, lens_i32, st["ctr"],
+             st["ctr"].numel() * 4, st["err"], work=float(U), tag="lm_rec_bwd")
+        dWx_lm = gemm(u, G_lm, ta=True)
+        dWh_lm = torch.zeros((1, Hl, 4 * Hl), **f32)
+        if U > 1:
+            gemm(hl[:(U - 1) * B], G_lm[B:], ta=True, out=dWh_lm[0])
+        dbp_lm = colsum(G_lm)
+        dlm_k, dlm_b = _unpack_lstm(dWx_lm, dWh_lm, dbp_lm, E, Hl, 1, dev)
+        du = gemm(G_lm, Wx_lm, tb=True)
+        demb = torch.zeros((V, E), **f32)
+        call("e2e_embed_scatter_add", U * B, E, demb, ids, du, E)
+        if ctx.stash is not None:
+            ctx.stash["emb_values"] = du
+        dattn_w = gemm(enc_flat, dHF, ta=True).view(attn_w.shape)
+        gemm(dHF, attn_w.view(D, A), tb=True, out=denc, accumulate=True)
+        denc_view = torch.as_strided(denc, (B, Tn, D), (Tp * D, D, 1)) if ctx.needs_input_grad[0] else None
+        return (denc_view, demb, dattn_w, dattn_v, dlm_k, dlm_b, ddec_k, ddec_b, dq_k, dq_b, dap_k, dap_b, dout_k,
+                dout_b, din_k, din_b, dsp_k, dsp_b, None, None, None, None, None)
+
+
 # ---------------------------------------------------------------------------
 # Losses
 # ---------------------------------------------------------------------------

@@ -135,6 +135,42 @@ typedef struct {
 } e2e_dec_loop_bwd_args;
 int e2e_decoder_loop_bwd(void* stream, const e2e_dec_loop_bwd_args* a);
 
+/* Persistent version of the same loop: all U steps in ONE cooperative launch per
+ * direction (three grid-synchronous phases per step), with InputProjection's ctx
+ * half folded into the decoder-LSTM kernel: W_ch = [in_k[Hd:] . Wx ; Wh] with
+ * gate-interleaved columns, pre_g = (lm_out . in_k[:Hd] + in_b) . Wx + b.
+ * Buffers marked (z) must be zero-initialised by the caller. */
+typedef struct {
+    int B, U, Hd, A, D, Tn, Tp;
+    const float* W_ch;     /* [D+Hd, 4Hd] */
+    const float* pre_g;    /* [U,B,4Hd] */
+    const float* q_k;      /* [Hd, A] */
+    const float* q_b;      /* [A] */
+    const float* attn_v;   /* [A] */
+    const float* HF;       /* [B,Tp,A] */
+    const float* enc;      /* [B,Tp,D] */
+    const int* enc_len;
+    const int* lens;
+    float* cat;            /* [U,B,Hd+D]  (c_new | ctx) */
+    float* hprev;          /* [U,B,Hd] committed h_{t-1} (z) */
+    float* cprev;          /* [U,B,Hd] committed c_{t-1} (z) */
+    float* acts;           /* [U,B,4Hd] gate activations, interleaved */
+    float* y;              /* [U,B,A] */
+    float* alpha;          /* [U,B,Tn] */
+    /* backward only */
+    float* dcat;           /* [U,B,Hd+D] in: AttnProjection gradient; ctx half accumulates d ctx */
+    float* dz;             /* [U,B,4Hd] out: d gate pre-activations, interleaved */
+    float* dch;            /* [U,B,D+Hd] out: (d ctx_{t-1} | d h_{t-1}) produced at step t */
+    float* dy;             /* [U,B,A] out */
+    float* ds;             /* [U,B,Tn] out: d attention scores */
+    float* dc_carry;       /* [B,Hd] (z) */
+    unsigned* ctr;         /* 1 counter of scratch */
+    int* err;              /* barrier-timeout flag */
+} e2e_dec_persist_args;
+int e2e_decoder_persist_fwd(void* stream, const e2e_dec_persist_args* a);
+/* also accumulates denc [B,Tp,D] += sum_t alpha_t dctx_t, writes dHF [B,Tp,A] (z) and dv_part [B*Tn, A] */
+int e2e_decoder_persist_bwd(void* stream, const e2e_dec_persist_args* a, float* denc, float* dHF, float* dv_part);
+
 /* single kernels of the loop, exposed for inference (greedy / beam) and tests */
 int e2e_attn_fwd(void* stream, int B, int Tn, int Tp, int A, int D, const float* HF, const float* enc,
                  const int* enc_len, const float* y, const float* v, float* alpha, float* ctx, int ldctx);

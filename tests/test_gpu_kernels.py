@@ -100,8 +100,17 @@ def _bilstm_case(B, T_, I, H):
         assert relerr(params[2 * d + 1].grad, ref_g[d][1]) < 2e-5
 
 
+@pytest.mark.parametrize("impl", ["persist", "loop"])
 @pytest.mark.parametrize("cname", ["tiny", "tiny_b"])
-def test_attn_decoder_fwd_bwd(cname):
+def test_attn_decoder_fwd_bwd(cname, impl):
+    ops.set_decoder_impl(impl)
+    try:
+        _attn_decoder_case(cname)
+    finally:
+        ops.set_decoder_impl("persist")
+
+
+def _attn_decoder_case(cname):
     from e2e_asr_b200.attn_decoder import AttnDecoder
     from e2e_asr_b200.testing import model_params
     from e2e_asr_b200.variables import VariableStore
