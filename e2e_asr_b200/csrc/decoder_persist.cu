@@ -41,7 +41,16 @@ __device__ __forceinline__ void mma_block(float (&d)[4], const float* a_s, int l
     const float* a0 = a_s + g * lda;
     const float* a1 = a_s + (g + 8) * lda;
     const float* b0 = bt + g * ldb;
-    for (int k = k_begin + tq; k < k_end; k += 8) {
+    // 4 independent accumulator chains: {even, odd k-step} x {hi*hi, cross terms}; a single chain
+    // would serialise on the mma.sync result latency
+    float dm[2][4], dx[2][4];
+#pragma unroll
+    for (int i = 0; i < 2; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { dm[i][j] = 0.f; dx[i][j] = 0.f; }
+    int ph = 0;
+#pragma unroll 4
+    for (int k = k_begin + tq; k < k_end; k += 8, ph ^= 1) {
         uint32_t ah[4], al[4], bh[2], bl[2];
         split_tf32(a0[k], ah[0], al[0]);
         split_tf32(a1[k], ah[1], al[1]);
@@ -49,10 +58,18 @@ __device__ __forceinline__ void mma_block(float (&d)[4], const float* a_s, int l
         split_tf32(a1[k + 4], ah[3], al[3]);
         split_tf32(b0[k], bh[0], bl[0]);
         split_tf32(b0[k + 4], bh[1], bl[1]);
-        mma_tf32(d, al, bh);
-        mma_tf32(d, ah, bl);
-        mma_tf32(d, ah, bh);
+        if (ph == 0) {
+            mma_tf32(dx[0], al, bh);
+            mma_tf32(dm[0], ah, bh);
+            mma_tf32(dx[0], ah, bl);
+        } else {
+            mma_tf32(dx[1], al, bh);
+            mma_tf32(dm[1], ah, bh);
+            mma_tf32(dx[1], ah, bl);
+        }
     }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) d[j] += (dx[0][j] + dx[1][j]) + (dm[0][j] + dm[1][j]);
 }
 
 // grid-wide barrier on a monotonically increasing counter (cooperative launch => co-resident)
@@ -105,16 +122,19 @@ __global__ void __launch_bounds__(NTH, 1) dec_fwd_persist_kernel(e2e_dec_persist
             for (int i = tid; i < 16 * (K / 4); i += NTH) {
                 int r = i / (K / 4), k = (i % (K / 4)) * 4;
                 int b = rb * 16 + r;
-                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                const float* src = nullptr;
                 if (b < B) {
                     if (k < D) {
-                        if (t > 0) v = __ldcg(reinterpret_cast<const float4*>(p.cat + ((size_t)(t - 1) * B + b) * CAT + Hd + k));
+                        if (t > 0) src = p.cat + ((size_t)(t - 1) * B + b) * CAT + Hd + k;
                     } else {
-                        v = __ldcg(reinterpret_cast<const float4*>(p.hprev + ((size_t)t * B + b) * Hd + (k - D)));
+                        src = p.hprev + ((size_t)t * B + b) * Hd + (k - D);
                     }
                 }
-                *reinterpret_cast<float4*>(a_s + r * AS + k) = v;
+                if (src) cp_async16(a_s + r * AS + k, src);       // L2 -> smem, all requests in flight
+                else *reinterpret_cast<float4*>(a_s + r * AS + k) = make_float4(0.f, 0.f, 0.f, 0.f);
             }
+            cp_async_commit();
+            cp_async_wait_all();
             __syncthreads();
             const int nt = w % 4, kh = w / 4;
             float d[4] = {0.f, 0.f, 0.f, 0.f};
@@ -215,9 +235,14 @@ __global__ void __launch_bounds__(NTH, 1) dec_fwd_persist_kernel(e2e_dec_persist
                 for (int a = tid; a < A; a += NTH) { y_s[a] = __ldcg(p.y + ((size_t)t * B + b) * A + a); v_s[a] = p.attn_v[a]; }
                 __syncthreads();
                 const float* HFb = p.HF + (size_t)b * Tp * A;
+#pragma unroll 2
                 for (int tau = w; tau < len; tau += 8) {
                     float acc = 0.f;
-                    for (int a = lane; a < A; a += 32) acc += v_s[a] * tanhf(HFb[(size_t)tau * A + a] + y_s[a]);
+                    for (int a = lane * 4; a < A; a += 128) {
+                        float4 hf = __ldg(reinterpret_cast<const float4*>(HFb + (size_t)tau * A + a));
+                        acc += v_s[a] * tanhf(hf.x + y_s[a]) + v_s[a + 1] * tanhf(hf.y + y_s[a + 1]) +
+                               v_s[a + 2] * tanhf(hf.z + y_s[a + 2]) + v_s[a + 3] * tanhf(hf.w + y_s[a + 3]);
+                    }
                     acc = warp_sum(acc);
                     if (lane == 0) s_s[tau] = acc;
                 }
@@ -251,11 +276,46 @@ __global__ void __launch_bounds__(NTH, 1) dec_fwd_persist_kernel(e2e_dec_persist
                 __syncthreads();
                 const float* encb = p.enc + (size_t)b * Tp * D;
                 const int dh = D / 2;
-                for (int dd = tid; dd < dh; dd += NTH) {
-                    const int dcol = half * dh + dd;
-                    float c = 0.f;
-                    for (int tau = 0; tau < len; ++tau) c = fmaf(s_s[tau], encb[(size_t)tau * D + dcol], c);
-                    p.cat[((size_t)t * B + b) * CAT + Hd + dcol] = c;
+                if (dh % 4 == 0 && dh <= 512) {
+                    // warp w sums its taus (w, w+8, ...); lane owns float4 columns lane, lane+32, ...
+                    float* part = a_s + ((2 * A + Tn + 16 + 3) & ~3);   // [8][dh], 16-byte aligned
+                    const int nv = dh / 4;
+                    float4 acc[4];
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) acc[c] = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 4
+                    for (int tau = w; tau < len; tau += 8) {
+                        const float al = s_s[tau];
+                        const float4* er = reinterpret_cast<const float4*>(encb + (size_t)tau * D + half * dh);
+#pragma unroll
+                        for (int c = 0; c < 4; ++c) {
+                            const int ci = lane + 32 * c;
+                            if (ci < nv) {
+                                float4 e = __ldg(er + ci);
+                                acc[c].x = fmaf(al, e.x, acc[c].x); acc[c].y = fmaf(al, e.y, acc[c].y);
+                                acc[c].z = fmaf(al, e.z, acc[c].z); acc[c].w = fmaf(al, e.w, acc[c].w);
+                            }
+                        }
+                    }
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) {
+                        const int ci = lane + 32 * c;
+                        if (ci < nv) *reinterpret_cast<float4*>(part + w * dh + ci * 4) = acc[c];
+                    }
+                    __syncthreads();
+                    for (int dd = tid; dd < dh; dd += NTH) {
+                        float c = 0.f;
+#pragma unroll
+                        for (int ww = 0; ww < 8; ++ww) c += part[ww * dh + dd];
+                        p.cat[((size_t)t * B + b) * CAT + Hd + half * dh + dd] = c;
+                    }
+                } else {
+                    for (int dd = tid; dd < dh; dd += NTH) {
+                        const int dcol = half * dh + dd;
+                        float c = 0.f;
+                        for (int tau = 0; tau < len; ++tau) c = fmaf(s_s[tau], encb[(size_t)tau * D + dcol], c);
+                        p.cat[((size_t)t * B + b) * CAT + Hd + dcol] = c;
+                    }
                 }
             }
         }
@@ -311,9 +371,14 @@ __global__ void __launch_bounds__(NTH, 1) dec_bwd_persist_kernel(e2e_dec_persist
                 const float* al = p.alpha + row * Tn;
                 const float* encb = p.enc + (size_t)b * Tp * D;
                 float part = 0.f;
+#pragma unroll 2
                 for (int tau = w; tau < len; tau += 8) {
                     float acc = 0.f;
-                    for (int dd = lane; dd < D; dd += 32) acc = fmaf(dctx_s[dd], encb[(size_t)tau * D + dd], acc);
+                    for (int dd = lane * 4; dd < D; dd += 128) {
+                        float4 e = __ldg(reinterpret_cast<const float4*>(encb + (size_t)tau * D + dd));
+                        acc = fmaf(dctx_s[dd], e.x, acc); acc = fmaf(dctx_s[dd + 1], e.y, acc);
+                        acc = fmaf(dctx_s[dd + 2], e.z, acc); acc = fmaf(dctx_s[dd + 3], e.w, acc);
+                    }
                     acc = warp_sum(acc);
                     if (lane == 0) { ds_s[tau] = acc; part += al[tau] * acc; }
                 }
@@ -332,8 +397,9 @@ __global__ void __launch_bounds__(NTH, 1) dec_bwd_persist_kernel(e2e_dec_persist
                     const int a = a0 + lane;
                     float dya = 0.f;
                     if (a < A)
+#pragma unroll 4
                         for (int tau = w; tau < len; tau += 8) {
-                            float th = tanhf(HFb[(size_t)tau * A + a] + y_s[a]);
+                            float th = tanhf(__ldg(HFb + (size_t)tau * A + a) + y_s[a]);
                             dya += ds_s[tau] * v_s[a] * (1.f - th * th);
                         }
                     if (a < A) acc_s[w * A + a] = dya;
@@ -507,7 +573,8 @@ static size_t bwd_smem_bytes(const e2e_dec_persist_args& p) {
 int dec_persist(cudaStream_t st, bool bwd, const e2e_dec_persist_args* a, float* denc, float* dHF, float* dv_part) {
     e2e_dec_persist_args p = *a;
     E2E_REQUIRE(p.Hd % 8 == 0 && p.A % 8 == 0 && p.D % 8 == 0, "decoder_persist: Hd, A, D must be multiples of 8");
-    E2E_REQUIRE(2 * p.A + p.Tn + 16 <= 16 * (p.D + p.Hd + 4) && 10 * p.A + p.D + p.Tn + 16 <= 16 * (4 * p.Hd + 4),
+    E2E_REQUIRE(2 * p.A + p.Tn + 32 + 4 * p.D <= 16 * (p.D + p.Hd + 4) &&
+                    10 * p.A + p.D + p.Tn + 16 <= 16 * (4 * p.Hd + 4),
                 "decoder_persist: attention length %d too long for the shared-memory scratch", p.Tn);
     if (p.B <= 0 || p.U <= 0) return 0;
     const void* fn = bwd ? (const void*)dec_bwd_persist_kernel : (const void*)dec_fwd_persist_kernel;

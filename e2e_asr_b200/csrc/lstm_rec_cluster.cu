@@ -169,20 +169,34 @@ __global__ void __launch_bounds__(NTH, 1) rec_fwd_cluster_kernel(CParams p) {
             if (rec) p.dbg[s * 5 + 1] = clock64();
             const float* hb = h_s + (size_t)buf * CS * TILE_FLOATS;
             const float* wrow = Wt + (size_t)(8 * w + g) * WKS;
-#pragma unroll 8
-            for (int kk = 0; kk < H / 8; ++kk) {
-                const int k = 8 * kk + tq;
-                const int src = k / UPC, off = k % UPC;
-                const float* ha = hb + (size_t)(src * R + g) * HSTR + off;
-                uint32_t ah[4], al[4], bh[2], bl[2];
-                split_tf32(ha[0], ah[0], al[0]);
-                split_tf32(ha[8 * HSTR], ah[1], al[1]);
-                split_tf32(ha[4], ah[2], al[2]);
-                split_tf32(ha[8 * HSTR + 4], ah[3], al[3]);
-                split_tf32(wrow[k], bh[0], bl[0]);
-                split_tf32(wrow[k + 4], bh[1], bl[1]);
-                mma_3xtf32(d, ah, al, bh, bl);
+            // independent accumulator chains (the mma.sync result latency would otherwise serialise
+            // the 96 MMAs): 2 k-phases x {hi*hi, cross terms}
+            float dm[2][4], dx[2][4];
+#pragma unroll
+            for (int i = 0; i < 2; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) { dm[i][j] = 0.f; dx[i][j] = 0.f; }
+#pragma unroll 4
+            for (int kk = 0; kk < H / 8; kk += 2) {
+#pragma unroll
+                for (int i = 0; i < 2; ++i) {
+                    const int k = 8 * (kk + i) + tq;
+                    const int src = k / UPC, off = k % UPC;
+                    const float* ha = hb + (size_t)(src * R + g) * HSTR + off;
+                    uint32_t ah[4], al[4], bh[2], bl[2];
+                    split_tf32(ha[0], ah[0], al[0]);
+                    split_tf32(ha[8 * HSTR], ah[1], al[1]);
+                    split_tf32(ha[4], ah[2], al[2]);
+                    split_tf32(ha[8 * HSTR + 4], ah[3], al[3]);
+                    split_tf32(wrow[k], bh[0], bl[0]);
+                    split_tf32(wrow[k + 4], bh[1], bl[1]);
+                    mma_tf32(dx[i], al, bh);
+                    mma_tf32(dm[i], ah, bh);
+                    mma_tf32(dx[i], ah, bl);
+                }
             }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) d[j] = (dx[0][j] + dx[1][j]) + (dm[0][j] + dm[1][j]);
         }
         if (rec) p.dbg[s * 5 + 2] = clock64();
         // fragment exchange: even tq keeps row g (gets f,o from its neighbour), odd tq keeps row g+8
@@ -293,11 +307,11 @@ __global__ void __launch_bounds__(NTH, 1) rec_bwd_cluster_kernel(CParams p) {
         float dh = 0.f;
         if (s > 0) {
             float* ps = pst + (size_t)buf * CS * TILE_FLOATS;
-            float d[MAXT][4];
+            float d[MAXT][4], dxx[MAXT][4];
 #pragma unroll
             for (int i = 0; i < MAXT; ++i)
 #pragma unroll
-                for (int j = 0; j < 4; ++j) d[i][j] = 0.f;
+                for (int j = 0; j < 4; ++j) { d[i][j] = 0.f; dxx[i][j] = 0.f; }
 #pragma unroll
             for (int kk = 0; kk < NC / 8; ++kk) {
                 const int kc = 8 * kk + tq;
@@ -313,7 +327,9 @@ __global__ void __launch_bounds__(NTH, 1) rec_bwd_cluster_kernel(CParams p) {
                         uint32_t bh[2], bl[2];
                         split_tf32(Wt[(size_t)kc * WKS + 8 * nt + g], bh[0], bl[0]);
                         split_tf32(Wt[(size_t)(kc + 4) * WKS + 8 * nt + g], bh[1], bl[1]);
-                        mma_3xtf32(d[i], ah, al, bh, bl);
+                        mma_tf32(dxx[i], al, bh);
+                        mma_tf32(d[i], ah, bh);
+                        mma_tf32(dxx[i], ah, bl);
                     }
                 }
             }
@@ -321,6 +337,8 @@ __global__ void __launch_bounds__(NTH, 1) rec_bwd_cluster_kernel(CParams p) {
             for (int i = 0; i < MAXT; ++i) {
                 const int nt = w + 8 * i;
                 if (nt < NTILES) {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) d[i][j] += dxx[i][j];
                     const int dest = nt / 2, du = (nt % 2) * 8 + 2 * tq;
                     *reinterpret_cast<float2*>(ps + (size_t)(dest * R + g) * HSTR + du) = make_float2(d[i][0], d[i][1]);
                     *reinterpret_cast<float2*>(ps + (size_t)(dest * R + g + 8) * HSTR + du) = make_float2(d[i][2], d[i][3]);
