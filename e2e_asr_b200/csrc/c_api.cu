@@ -34,6 +34,7 @@ int gemm_simt(cudaStream_t, int, int, int, int, int, const float*, int, const fl
 int gemm_tc(cudaStream_t, int mode, int, int, int, int, int, const float*, int, const float*, int, float*, int,
             const float*, const float*, int, int, bool* handled);
 void set_workspace(void*, size_t);
+void set_stream_workspace(cudaStream_t, void*, size_t);
 extern int g_rec_mode;
 extern long long* g_rec_dbg;
 void set_tc_debug(float*, long long);
@@ -125,6 +126,10 @@ int e2e_set_rec_mode(int mode) {
 }
 int e2e_set_rec_debug(long long* dbg) {
     g_rec_dbg = dbg;
+    return 0;
+}
+int e2e_set_stream_workspace(void* stream, void* ptr, size_t bytes) {
+    set_stream_workspace(ST(stream), ptr, bytes);
     return 0;
 }
 int e2e_set_workspace(void* ptr, size_t bytes) {

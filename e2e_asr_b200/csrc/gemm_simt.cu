@@ -196,27 +196,58 @@ int gemm_simt(cudaStream_t st, int transA, int transB, int M, int N, int K, cons
     return 0;
 }
 
-// out[n] (+)= sum_m X[m, n]   (bias gradients)
+// out[n] (+)= sum_m X[m, n]   (bias gradients).  Thread = 4 adjacent columns (float4 loads),
+// rows strided over a 2-D grid with 4 loads in flight per thread; partial sums by atomicAdd.
 __global__ void colsum_kernel(int M, int N, const float* __restrict__ X, int ldx, float* __restrict__ out,
-                              int accumulate, int rows_per_block) {
-    int n = blockIdx.x * blockDim.x + threadIdx.x;
-    if (n >= N) return;
-    int m0 = blockIdx.y * rows_per_block, m1 = min(M, m0 + rows_per_block);
-    float s = 0.f;
-    for (int m = m0; m < m1; ++m) s += X[(size_t)m * ldx + n];
-    if (gridDim.y > 1) atomicAdd(out + n, s);
-    else out[n] = accumulate ? out[n] + s : s;
+                              int accumulate, int rows_per_block, int vec) {
+    const int m0 = blockIdx.y * rows_per_block, m1 = min(M, m0 + rows_per_block);
+    if (vec) {
+        int n = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+        if (n >= N) return;
+        float4 s0 = make_float4(0.f, 0.f, 0.f, 0.f), s1 = s0, s2 = s0, s3 = s0;
+        int m = m0;
+        for (; m + 3 < m1; m += 4) {
+            float4 a = __ldg(reinterpret_cast<const float4*>(X + (size_t)m * ldx + n));
+            float4 b = __ldg(reinterpret_cast<const float4*>(X + (size_t)(m + 1) * ldx + n));
+            float4 c = __ldg(reinterpret_cast<const float4*>(X + (size_t)(m + 2) * ldx + n));
+            float4 d = __ldg(reinterpret_cast<const float4*>(X + (size_t)(m + 3) * ldx + n));
+            s0.x += a.x; s0.y += a.y; s0.z += a.z; s0.w += a.w;
+            s1.x += b.x; s1.y += b.y; s1.z += b.z; s1.w += b.w;
+            s2.x += c.x; s2.y += c.y; s2.z += c.z; s2.w += c.w;
+            s3.x += d.x; s3.y += d.y; s3.z += d.z; s3.w += d.w;
+        }
+        for (; m < m1; ++m) {
+            float4 a = __ldg(reinterpret_cast<const float4*>(X + (size_t)m * ldx + n));
+            s0.x += a.x; s0.y += a.y; s0.z += a.z; s0.w += a.w;
+        }
+        float r[4] = {(s0.x + s1.x) + (s2.x + s3.x), (s0.y + s1.y) + (s2.y + s3.y), (s0.z + s1.z) + (s2.z + s3.z),
+                      (s0.w + s1.w) + (s2.w + s3.w)};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            if (gridDim.y > 1) atomicAdd(out + n + j, r[j]);
+            else out[n + j] = accumulate ? out[n + j] + r[j] : r[j];
+        }
+    } else {
+        int n = blockIdx.x * blockDim.x + threadIdx.x;
+        if (n >= N) return;
+        float s = 0.f;
+        for (int m = m0; m < m1; ++m) s += X[(size_t)m * ldx + n];
+        if (gridDim.y > 1) atomicAdd(out + n, s);
+        else out[n] = accumulate ? out[n] + s : s;
+    }
 }
 
 int colsum(cudaStream_t st, int M, int N, const float* X, int ldx, float* out, int accumulate) {
     if (N <= 0) return 0;
-    int gx = cdiv(N, 128);
+    const int vec = (N % 4 == 0) && (ldx % 4 == 0) && ((reinterpret_cast<uintptr_t>(X) & 15) == 0);
+    const int cols_per_block = vec ? 128 * 4 : 128;
+    int gx = cdiv(N, cols_per_block);
     int gy = 1;
-    if (M > 512) gy = min(cdiv(M, 256), max(1, 4 * sm_count() / gx));
+    if (M > 256) gy = min(cdiv(M, 64), max(1, 8 * sm_count() / gx));
     int rpb = M > 0 ? cdiv(M, gy) : 1;
     gy = M > 0 ? cdiv(M, rpb) : 1;
     if (gy > 1 && !accumulate) E2E_CHECK_CUDA(cudaMemsetAsync(out, 0, sizeof(float) * N, st));
-    colsum_kernel<<<dim3(gx, gy), 128, 0, st>>>(M, N, X, ldx, out, accumulate, rpb);
+    colsum_kernel<<<dim3(gx, gy), 128, 0, st>>>(M, N, X, ldx, out, accumulate, rpb, vec);
     E2E_LAUNCH_CHECK();
     return 0;
 }

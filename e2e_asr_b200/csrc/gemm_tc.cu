@@ -384,6 +384,10 @@ bool make_map(CUtensorMap* map, bool bf16, const void* ptr, size_t rows, size_t 
 
 void* g_ws = nullptr;
 size_t g_ws_bytes = 0;
+// per-stream scratch (concurrent streams must not share the operand pre-pass buffers)
+struct StreamWs { cudaStream_t st; void* ptr; size_t bytes; };
+StreamWs g_stream_ws[8];
+int g_n_stream_ws = 0;
 float* g_dbg = nullptr;
 long long g_min_work = 1ll << 27;
 
@@ -392,6 +396,11 @@ long long g_min_work = 1ll << 27;
 void set_workspace(void* ptr, size_t bytes) {
     g_ws = ptr;
     g_ws_bytes = bytes;
+}
+void set_stream_workspace(cudaStream_t st, void* ptr, size_t bytes) {
+    for (int i = 0; i < g_n_stream_ws; ++i)
+        if (g_stream_ws[i].st == st) { g_stream_ws[i].ptr = ptr; g_stream_ws[i].bytes = bytes; return; }
+    if (g_n_stream_ws < 8) g_stream_ws[g_n_stream_ws++] = StreamWs{st, ptr, bytes};
 }
 void set_tc_debug(float* dbg, long long min_work) {
     g_dbg = dbg;
@@ -407,7 +416,11 @@ int gemm_tc(cudaStream_t st, int mode, int transA, int transB, int M, int N, int
     const bool bf16 = mode == 2;
     // big enough to pay for the pre-pass and to fill tiles; K >= one stage
     if (M < 96 || N < 64 || K < 32 || (long long)M * N * K < g_min_work) return 0;
-    if (!get_encode() || g_ws == nullptr) return 0;
+    void* ws_ptr = g_ws;
+    size_t ws_bytes = g_ws_bytes;
+    for (int i = 0; i < g_n_stream_ws; ++i)
+        if (g_stream_ws[i].st == st) { ws_ptr = g_stream_ws[i].ptr; ws_bytes = g_stream_ws[i].bytes; }
+    if (!get_encode() || ws_ptr == nullptr) return 0;
     // stored shapes
     const size_t a_rows = transA ? K : M, a_cols = transA ? M : K;
     const size_t b_rows = transB ? N : K, b_cols = transB ? K : N;
@@ -415,8 +428,8 @@ int gemm_tc(cudaStream_t st, int mode, int transA, int transB, int M, int N, int
     const size_t a_ld = (a_cols + eper - 1) / eper * eper, b_ld = (b_cols + eper - 1) / eper * eper;
     const size_t esz = bf16 ? 2 : 4, nparts = bf16 ? 1 : 2;
     size_t a_bytes = (a_rows * a_ld * esz + 1023) / 1024 * 1024, b_bytes = (b_rows * b_ld * esz + 1023) / 1024 * 1024;
-    if (nparts * (a_bytes + b_bytes) > g_ws_bytes) return 0;
-    uint8_t* ws = (uint8_t*)g_ws;
+    if (nparts * (a_bytes + b_bytes) > ws_bytes) return 0;
+    uint8_t* ws = (uint8_t*)ws_ptr;
     void* A0 = ws;
     void* A1 = ws + a_bytes;
     void* B0 = ws + nparts * a_bytes;

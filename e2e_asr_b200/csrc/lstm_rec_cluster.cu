@@ -223,11 +223,14 @@ __global__ void __launch_bounds__(NTH, 1) rec_fwd_cluster_kernel(CParams p) {
         fence_proxy_async();
         __syncthreads();
         if (rec) p.dbg[s * 5 + 4] = clock64();
-        if (s + 1 < T && tid < CS) {
+        // every warp issues its share of the CS peer copies (lane i of warp w -> rank w + 8 i), so the
+        // copy-engine requests go out in parallel instead of serialising inside one warp
+        if (s + 1 < T) {
             if (tid == 0) mbar_expect_tx(&full[buf ^ 1], CS * TILE_BYTES);
-            __syncwarp((1u << CS) - 1u);
-            dsmem_bulk_copy(s_u32(h_s + ((size_t)(buf ^ 1) * CS + rank) * TILE_FLOATS), s_u32(&full[buf ^ 1]), tid,
-                            stage + (size_t)buf * TILE_FLOATS, TILE_BYTES);
+            const int dst_rank = w + 8 * lane;
+            if (lane < (CS + 7) / 8 && dst_rank < CS)
+                dsmem_bulk_copy(s_u32(h_s + ((size_t)(buf ^ 1) * CS + rank) * TILE_FLOATS), s_u32(&full[buf ^ 1]),
+                                dst_rank, stage + (size_t)buf * TILE_FLOATS, TILE_BYTES);
         }
         if (active) {
             reinterpret_cast<float4*>(p.G)[(row * ndir + dir) * H + unit] = act;
@@ -346,11 +349,12 @@ __global__ void __launch_bounds__(NTH, 1) rec_bwd_cluster_kernel(CParams p) {
             }
             fence_proxy_async();
             __syncthreads();
-            if (tid < CS) {
+            {
                 if (tid == 0) mbar_expect_tx(&full[buf], CS * TILE_BYTES);
-                __syncwarp((1u << CS) - 1u);
-                dsmem_bulk_copy(s_u32(red_s + ((size_t)buf * CS + rank) * TILE_FLOATS), s_u32(&full[buf]), tid,
-                                ps + (size_t)tid * TILE_FLOATS, TILE_BYTES);
+                const int dst_rank = w + 8 * lane;
+                if (lane < (CS + 7) / 8 && dst_rank < CS)
+                    dsmem_bulk_copy(s_u32(red_s + ((size_t)buf * CS + rank) * TILE_FLOATS), s_u32(&full[buf]),
+                                    dst_rank, ps + (size_t)dst_rank * TILE_FLOATS, TILE_BYTES);
             }
             mbar_wait(&full[buf], ph[buf]);
             ph[buf] ^= 1u;

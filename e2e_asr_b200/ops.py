@@ -22,12 +22,16 @@ def set_gemm_mode(mode):
 _workspace = {}
 
 
-def ensure_workspace(device, nbytes=2 << 30):
-    """Registers the operand pre-pass scratch of the tensor-core GEMM modes."""
-    key = str(device)
+def ensure_workspace(device, nbytes=2 << 30, stream=None):
+    """Registers the operand pre-pass scratch of the tensor-core GEMM modes (the default one,
+    or a private one for GEMMs enqueued on a side `stream`)."""
+    key = str(device) if stream is None else "%s/%d" % (device, stream.cuda_stream)
     if key not in _workspace or _workspace[key].numel() < nbytes:
         _workspace[key] = torch.empty((nbytes,), dtype=torch.uint8, device=device)
-    _lib.lib().e2e_set_workspace(_workspace[key].data_ptr(), _workspace[key].numel())
+    if stream is None:
+        _lib.lib().e2e_set_workspace(_workspace[key].data_ptr(), _workspace[key].numel())
+    else:
+        _lib.lib().e2e_set_stream_workspace(stream.cuda_stream, _workspace[key].data_ptr(), _workspace[key].numel())
 
 
 def get_gemm_mode():
@@ -562,6 +566,10 @@ class CTCHeadFn(torch.autograd.Function):
             stash["logits"] = logits
             stash["loss_b"] = loss_b
             stash["layout"] = (B, T, sb, stt)
+            consumer = stash.get("consumer_stream")
+            if consumer is not None:      # produced on a side stream, consumed on `consumer`
+                for t_ in (logits, lse, alpha_ws, loss_b, grad, loss):
+                    t_.record_stream(consumer)
         return loss.view(())
 
     @staticmethod

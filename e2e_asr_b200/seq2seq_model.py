@@ -75,6 +75,7 @@ class Seq2SeqModel(BaseParams):
         self._sq_emb = torch.zeros(1, dtype=torch.float32, device=self.device)
         self.grad_norm = torch.zeros(1, dtype=torch.float32, device=self.device)
         self.ctc_stash = {}
+        self._side_stream = None
         if data_iter is not None:
             self.create_computational_graph()
 
@@ -158,6 +159,30 @@ class Seq2SeqModel(BaseParams):
             self.encoder_hidden_states, self.time_major_states, self.seq_len_encs = \
                 self.encoder(self.encoder_inputs, self.seq_len, depth_of)
 
+            # The auxiliary CTC heads only need the encoder states: they run on a side stream,
+            # concurrently with the (latency-bound) attention decoders; autograd replays their
+            # backward on the same side stream.
+            self.losses = {}
+            main = torch.cuda.current_stream()
+            side = None
+            if self.isTraining and params.ctc_tasks:
+                if self._side_stream is None:
+                    self._side_stream = torch.cuda.Stream(device=self.device)
+                    if ops.get_gemm_mode() != 0:
+                        ops.ensure_workspace(self.device, stream=self._side_stream)
+                side = self._side_stream
+                side.wait_stream(main)
+                with torch.cuda.stream(side):
+                    for task, vocab in params.ctc_tasks.items():
+                        d = params.num_layers[task]
+                        D = self.time_major_states[d].shape[2]
+                        k = self.variables.get("model/ctc_%s/kernel" % task, (D, vocab + 1))
+                        b = self.variables.get("model/ctc_%s/bias" % task, (vocab + 1,), ("zeros",))
+                        self.ctc_stash[task] = {"consumer_stream": main}
+                        self.losses[task] = LossUtils.ctc_head_loss(
+                            self.time_major_states[d], k, b, self.seq_len_encs[d], self.decoder_inputs[task],
+                            self.seq_len_target[task], self.ctc_stash[task])
+
             self.outputs = {}
             for task in params.tasks:
                 d = params.num_layers[task]
@@ -167,19 +192,12 @@ class Seq2SeqModel(BaseParams):
 
             if not self.isTraining:
                 return
-            self.losses = {}
             for task in params.tasks:
                 self.losses[task] = LossUtils.cross_entropy_loss(
                     self.outputs[task], self.targets[task], self.seq_len_target[task])
-            for task, vocab in params.ctc_tasks.items():
-                d = params.num_layers[task]
-                D = self.time_major_states[d].shape[2]
-                k = self.variables.get("model/ctc_%s/kernel" % task, (D, vocab + 1))
-                b = self.variables.get("model/ctc_%s/bias" % task, (vocab + 1,), ("zeros",))
-                self.ctc_stash[task] = {}
-                self.losses[task] = LossUtils.ctc_head_loss(
-                    self.time_major_states[d], k, b, self.seq_len_encs[d], self.decoder_inputs[task],
-                    self.seq_len_target[task], self.ctc_stash[task])
+            if side is not None:
+                main.wait_stream(side)
+                self.losses = {t: self.losses[t] for t in list(params.tasks) + list(params.ctc_tasks)}
 
             # Add losses across the tasks (:140-144)
             self.total_loss = 0.0

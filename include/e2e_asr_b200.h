@@ -48,6 +48,8 @@ int e2e_gemm(void* stream, int mode, int transA, int transB, int M, int N, int K
  * bf16 copies): a caller-owned device buffer; GEMMs whose operands do not fit run
  * the FFMA kernel.  NOT a stream argument: plain (ptr, bytes). */
 int e2e_set_workspace(void* ptr, size_t bytes);
+/* scratch used instead for GEMMs enqueued on `stream` (streams that run concurrently must not share one) */
+int e2e_set_stream_workspace(void* stream, void* ptr, size_t bytes);
 /* test hook: dump buffer for the tensor-core kernel (or NULL) and the minimum M*N*K it takes */
 int e2e_set_tc_debug(float* dbg, long long min_work);
 
