@@ -363,7 +363,13 @@ static size_t rec_smem(bool bwd, int RT, int UPC, int H) {
 
 int lstm_rec_cluster(cudaStream_t, bool, int, int, int, int, int, long long, long long, float*, float*, float*,
                      const float*, const float*, const int*);
-int g_rec_mode = 0;     // 0 = cluster/DSMEM kernel when eligible, 1 = always the L2 / global-barrier kernel
+int lstm_rec_mc(cudaStream_t, bool, int, int, int, int, int, long long, long long, float*, float*, float*,
+                const float*, const float*, const int*, void*, size_t);
+extern int g_rec_mc_ns;
+// 0 = fastest eligible kernel (register-resident multicast kernel for H in {128,256}, else the cluster/DSMEM
+// kernel, else the L2 kernel); 1 = always the L2 / global-barrier kernel; 2 = skip the multicast kernel;
+// 3 / 4 = multicast kernel with 1 / 2 interleaved batch slices per cluster forced (tests)
+int g_rec_mode = 0;
 
 // workspace: ctr_ws must hold >= 4*ceil(B/4) unsigned + 1 int, zeroed by this function.
 int lstm_rec(cudaStream_t st, bool bwd, int B, int T, int Tp, int H, int ndir, long long sb, long long stt,
@@ -373,7 +379,12 @@ int lstm_rec(cudaStream_t st, bool bwd, int B, int T, int Tp, int H, int ndir, l
     E2E_REQUIRE(ndir == 1 || ndir == 2, "lstm_rec: ndir must be 1 or 2");
     E2E_REQUIRE(Tp >= T, "lstm_rec: Tp (%d) must be >= T (%d)", Tp, T);
     if (B <= 0 || T <= 0) return 0;
-    if (g_rec_mode == 0) {
+    if (g_rec_mode == 0 || g_rec_mode == 3 || g_rec_mode == 4) {
+        g_rec_mc_ns = g_rec_mode == 0 ? 0 : g_rec_mode - 2;
+        int rc = lstm_rec_mc(st, bwd, B, T, Tp, H, ndir, sb, stt, G, Hout, Cst, Wh, dOut, lens, ctr_ws, ctr_ws_bytes);
+        if (rc >= 0) return rc;
+    }
+    if (g_rec_mode != 1) {
         int rc = lstm_rec_cluster(st, bwd, B, T, Tp, H, ndir, sb, stt, G, Hout, Cst, Wh, dOut, lens);
         if (rc >= 0) return rc;     // launched (0) or failed (>0); -1 = not eligible -> fall through
     }

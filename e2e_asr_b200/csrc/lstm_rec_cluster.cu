@@ -108,6 +108,48 @@ __device__ __forceinline__ void dsmem_bulk_copy(uint32_t dst_local_addr, uint32_
                  ::"r"(dst), "r"(s_u32(src)), "r"(bytes), "r"(bar) : "memory");
 }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+// direct DSMEM exchange: remote vector store + remote mbarrier arrive (a few hundred cycles end to end,
+// against ~3000 for a cp.async.bulk round trip measured on B200)
+__device__ __forceinline__ void st_cluster_v4(uint32_t cluster_addr, float4 v) {
+    asm volatile("st.shared::cluster.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(cluster_addr), "f"(v.x), "f"(v.y), "f"(v.z),
+                 "f"(v.w) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void fence_cluster() { asm volatile("fence.acq_rel.cluster;" ::: "memory"); }
+__device__ __forceinline__ bool mbar_try_wait_cluster(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n.reg .pred p;\n"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n}\n"
+        : "=r"(ok) : "r"(s_u32(bar)), "r"(parity) : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
+    if (mbar_try_wait_cluster(bar, parity)) return;
+    const long long t0 = clock64();
+    while (!mbar_try_wait_cluster(bar, parity)) {
+        if (clock64() - t0 > (1ll << 33)) __trap();
+    }
+}
+// all threads: push this CTA's [R][UPC] tile (local rows of HSTR floats at `src`) into slot `slot_addr`
+// (local address of the same slot in every peer) of the CS peers, then one arrival per peer
+template <int CS>
+__device__ __forceinline__ void push_tile(const float* src, uint32_t slot_addr, uint32_t bar_addr, int tid) {
+    const int chunk = tid % 64, row = chunk / 4, c4 = chunk % 4, dg = tid / 64;
+    const float4 v = *reinterpret_cast<const float4*>(src + row * HSTR + c4 * 4);
+    const uint32_t off = (uint32_t)(row * HSTR + c4 * 4) * 4u;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const int dest = dg * 4 + j;
+        if (dest < CS) st_cluster_v4(mapa(slot_addr + off, dest), v);
+    }
+    // the CTA barrier orders every thread's remote stores before the release-arrives below
+    __syncthreads();
+    if (tid < CS) mbar_arrive_cluster(mapa(bar_addr, tid));
+}
 
 // ---------------------------------------------------------------- forward
 // Per step: z[16 rows x 64 own gate columns] = h_{t-1}[16 x H] . W_hh[:, own columns] as
@@ -131,8 +173,8 @@ __global__ void __launch_bounds__(NTH, 1) rec_fwd_cluster_kernel(CParams p) {
     const int w = tid / 32, lane = tid % 32, g = lane / 4, tq = lane % 4;
 
     if (tid == 0) {
-        mbar_init(&full[0], 1);
-        mbar_init(&full[1], 1);
+        mbar_init(&full[0], CS);
+        mbar_init(&full[1], CS);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     {
@@ -164,7 +206,7 @@ __global__ void __launch_bounds__(NTH, 1) rec_fwd_cluster_kernel(CParams p) {
         if (t < plen) gx = reinterpret_cast<const float4*>(p.G)[(row * ndir + dir) * H + unit];
         float d[4] = {0.f, 0.f, 0.f, 0.f};
         if (s > 0) {
-            mbar_wait(&full[buf], ph[buf]);
+            mbar_wait_cluster(&full[buf], ph[buf]);
             ph[buf] ^= 1u;
             if (rec) p.dbg[s * 5 + 1] = clock64();
             const float* hb = h_s + (size_t)buf * CS * TILE_FLOATS;
@@ -220,18 +262,11 @@ __global__ void __launch_bounds__(NTH, 1) rec_fwd_cluster_kernel(CParams p) {
         // critical path first: publish h_t (state h: carried through for masked rows)
         stage[(size_t)buf * TILE_FLOATS + prow * HSTR + ul] = h_reg;
         if (rec) p.dbg[s * 5 + 3] = clock64();
-        fence_proxy_async();
         __syncthreads();
         if (rec) p.dbg[s * 5 + 4] = clock64();
-        // every warp issues its share of the CS peer copies (lane i of warp w -> rank w + 8 i), so the
-        // copy-engine requests go out in parallel instead of serialising inside one warp
-        if (s + 1 < T) {
-            if (tid == 0) mbar_expect_tx(&full[buf ^ 1], CS * TILE_BYTES);
-            const int dst_rank = w + 8 * lane;
-            if (lane < (CS + 7) / 8 && dst_rank < CS)
-                dsmem_bulk_copy(s_u32(h_s + ((size_t)(buf ^ 1) * CS + rank) * TILE_FLOATS), s_u32(&full[buf ^ 1]),
-                                dst_rank, stage + (size_t)buf * TILE_FLOATS, TILE_BYTES);
-        }
+        if (s + 1 < T)
+            push_tile<CS>(stage + (size_t)buf * TILE_FLOATS,
+                          s_u32(h_s + ((size_t)(buf ^ 1) * CS + rank) * TILE_FLOATS), s_u32(&full[buf ^ 1]), tid);
         if (active) {
             reinterpret_cast<float4*>(p.G)[(row * ndir + dir) * H + unit] = act;
             p.Cst[(row * ndir + dir) * H + unit] = cn;
@@ -266,8 +301,8 @@ __global__ void __launch_bounds__(NTH, 1) rec_bwd_cluster_kernel(CParams p) {
     const int w = tid / 32, lane = tid % 32, g = lane / 4, tq = lane % 4;
 
     if (tid == 0) {
-        mbar_init(&full[0], 1);
-        mbar_init(&full[1], 1);
+        mbar_init(&full[0], CS);
+        mbar_init(&full[1], CS);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     {
@@ -347,16 +382,25 @@ __global__ void __launch_bounds__(NTH, 1) rec_bwd_cluster_kernel(CParams p) {
                     *reinterpret_cast<float2*>(ps + (size_t)(dest * R + g + 8) * HSTR + du) = make_float2(d[i][2], d[i][3]);
                 }
             }
-            fence_proxy_async();
             __syncthreads();
             {
-                if (tid == 0) mbar_expect_tx(&full[buf], CS * TILE_BYTES);
-                const int dst_rank = w + 8 * lane;
-                if (lane < (CS + 7) / 8 && dst_rank < CS)
-                    dsmem_bulk_copy(s_u32(red_s + ((size_t)buf * CS + rank) * TILE_FLOATS), s_u32(&full[buf]),
-                                    dst_rank, ps + (size_t)dst_rank * TILE_FLOATS, TILE_BYTES);
+                // reduce-scatter: tile `dest` of my partials goes to slot `rank` of peer `dest`
+                const int chunk = tid % 64, prow_c = chunk / 4, c4 = chunk % 4, dg = tid / 64;
+                const uint32_t slot = s_u32(red_s + ((size_t)buf * CS + rank) * TILE_FLOATS) +
+                                      (uint32_t)(prow_c * HSTR + c4 * 4) * 4u;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int dest = dg * 4 + j;
+                    if (dest < CS) {
+                        const float4 v = *reinterpret_cast<const float4*>(ps + (size_t)dest * TILE_FLOATS +
+                                                                           prow_c * HSTR + c4 * 4);
+                        st_cluster_v4(mapa(slot, dest), v);
+                    }
+                }
+                __syncthreads();
+                if (tid < CS) mbar_arrive_cluster(mapa(s_u32(&full[buf]), tid));
             }
-            mbar_wait(&full[buf], ph[buf]);
+            mbar_wait_cluster(&full[buf], ph[buf]);
             ph[buf] ^= 1u;
             const float* rb = red_s + (size_t)buf * CS * TILE_FLOATS;
 #pragma unroll

@@ -45,7 +45,7 @@ def _dev_state(device):
     """Per-device scratch: recurrence step counters, barrier error flag, reduction partials."""
     key = str(device)
     if key not in _state:
-        _state[key] = dict(ctr=torch.zeros(4096, dtype=torch.int32, device=device),
+        _state[key] = dict(ctr=torch.zeros(1 << 20, dtype=torch.int32, device=device),
                            err=torch.zeros(1, dtype=torch.int32, device=device),
                            partials=torch.zeros(512, dtype=torch.float32, device=device),
                            one=torch.ones(1, dtype=torch.float32, device=device))
