@@ -159,7 +159,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--config", default="cfg2")
-    ap.add_argument("--gemm", default=None, help="fp32 | tf32x3 | bf16 (default: library default)")
+    ap.add_argument("--gemm", default="tf32x3", help="fp32 | tf32x3 | bf16 (default: tf32x3, the fp32-accurate tensor-core mode)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -21,6 +21,8 @@
 //     step by step, so the exchange of one slice is hidden behind the arithmetic of the
 //     other and cfg-2 (8 slices) needs 4 clusters = 64 SMs.
 // Layouts and length semantics are those documented in lstm_rec.cu.
+#include <cuda_bf16.h>
+
 #include "common.cuh"
 
 namespace e2e {
@@ -135,6 +137,48 @@ __device__ __forceinline__ void ktile_mma(float (&acc)[NTL][4], float (&accx)[NT
     for (int nt = 0; nt < NTL; ++nt) mma_tf32(accx[nt], ah, bl[nt][0], bl[nt][1]);
 }
 
+// Mixed scheme (kMixed): bf16 m16n8k16 issues at the same 8 cycles / SMSP as tf32 m16n8k8, so the two
+// cross terms of a k16 pair cost one MMA each instead of two: per k16 and n-tile
+//     acc  += tf32(a) * tf32(W)            (2 x m16n8k8, a = raw fp32 words)
+//     accx += bf16(a - tf32(a)) * bf16(W)  (1 x m16n8k16)
+//     accx += bf16(a) * bf16(W - tf32(W))  (1 x m16n8k16)
+// 4 MMAs instead of 6.  Error per product ~2^-19 (bf16 rounding, 2^-9, of an operand of a term that is
+// itself 2^-10..2^-12 of the product), the same class as 3xTF32 with a truncating split.
+// The bf16 MMA's logical k index (2tq, 2tq+1 | 2tq+8, 2tq+9) is mapped to the physical
+// (tq, tq+4 of k8-tile 0 | tq, tq+4 of k8-tile 1), i.e. to exactly the values the thread already holds.
+constexpr bool kMixed = true;
+
+__device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
+    __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+    return *reinterpret_cast<uint32_t*>(&v);
+}
+__device__ __forceinline__ void mma_bf16(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+    asm("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+        : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+        : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+// a0 / a1: the thread's A fragments of the pair's two k8-tiles; bh0 / bh1: tf32 W of the two tiles;
+// wb / wl: bf16 W and bf16 (W - tf32 W) of the pair
+template <int NTL>
+__device__ __forceinline__ void k16_mma(float (&acc)[NTL][4], float (&accx)[NTL][4], const float4 a0, const float4 a1,
+                                        const uint32_t (&bh0)[NTL][2], const uint32_t (&bh1)[NTL][2],
+                                        const uint32_t (&wb)[NTL][2], const uint32_t (&wl)[NTL][2]) {
+    uint32_t h0[4], l0[4], h1[4], l1[4];
+    split_tf32(a0.x, h0[0], l0[0]); split_tf32(a0.y, h0[1], l0[1]); split_tf32(a0.z, h0[2], l0[2]); split_tf32(a0.w, h0[3], l0[3]);
+    split_tf32(a1.x, h1[0], l1[0]); split_tf32(a1.y, h1[1], l1[1]); split_tf32(a1.z, h1[2], l1[2]); split_tf32(a1.w, h1[3], l1[3]);
+    const uint32_t al[4] = {pack_bf16(__uint_as_float(l0[0]), __uint_as_float(l0[2])), pack_bf16(__uint_as_float(l0[1]), __uint_as_float(l0[3])),
+                            pack_bf16(__uint_as_float(l1[0]), __uint_as_float(l1[2])), pack_bf16(__uint_as_float(l1[1]), __uint_as_float(l1[3]))};
+    const uint32_t ab[4] = {pack_bf16(a0.x, a0.z), pack_bf16(a0.y, a0.w), pack_bf16(a1.x, a1.z), pack_bf16(a1.y, a1.w)};
+#pragma unroll
+    for (int nt = 0; nt < NTL; ++nt) mma_tf32(acc[nt], h0, bh0[nt][0], bh0[nt][1]);
+#pragma unroll
+    for (int nt = 0; nt < NTL; ++nt) mma_bf16(accx[nt], al, wb[nt][0], wb[nt][1]);
+#pragma unroll
+    for (int nt = 0; nt < NTL; ++nt) mma_tf32(acc[nt], h1, bh1[nt][0], bh1[nt][1]);
+#pragma unroll
+    for (int nt = 0; nt < NTL; ++nt) mma_bf16(accx[nt], ab, wl[nt][0], wl[nt][1]);
+}
+
 // ---------------------------------------------------------------- forward
 // Warp w = (n-group ng = w % 4, k-half kh = w / 4): gate columns of the CTA's units [4ng, 4ng+4)
 // (n-tile 0 = gates i,j, n-tile 1 = gates f,o), source tiles [kh*CS/2, (kh+1)*CS/2).  After the
@@ -146,8 +190,9 @@ __global__ void __launch_bounds__(NTH, 1) rec_fwd_mc_kernel(MParams p) {
     constexpr int KT = CS;                                       // k8-tiles per k-half (H / 2 / 8)
     extern __shared__ __align__(128) float smem[];
     float* h_s = smem;                                           // [NS][2][CS][TILE]
-    float4* xchg = reinterpret_cast<float4*>(h_s + NS * 2 * CS * TILE);   // [8 warps][32 lanes]
+    float4* xchg = reinterpret_cast<float4*>(h_s + NS * 2 * CS * TILE);   // [2][8 warps][32 lanes]
     __shared__ __align__(8) uint64_t full[NS][2];
+    __shared__ unsigned pubcnt[NS];                              // warps that have written their part of the tile
 
     const int ndir = p.ndir, T = p.T;
     const uint32_t rank = cluster_rank();
@@ -160,7 +205,7 @@ __global__ void __launch_bounds__(NTH, 1) rec_fwd_mc_kernel(MParams p) {
 
     if (tid == 0) {
 #pragma unroll
-        for (int sl = 0; sl < NS; ++sl) { mbar_init(&full[sl][0], 1); mbar_init(&full[sl][1], 1); }
+        for (int sl = 0; sl < NS; ++sl) { mbar_init(&full[sl][0], 1); mbar_init(&full[sl][1], 1); pubcnt[sl] = 0u; }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 #pragma unroll
         for (int sl = 0; sl < NS; ++sl) { mbar_expect_tx(&full[sl][0], CS * TILE * 4); mbar_expect_tx(&full[sl][1], CS * TILE * 4); }
@@ -181,6 +226,27 @@ __global__ void __launch_bounds__(NTH, 1) rec_fwd_mc_kernel(MParams p) {
                     bh[kt][nt][e] = cvt_tf32(x);
                     bl[kt][nt][e] = cvt_tf32(x - __uint_as_float(bh[kt][nt][e]));
                 }
+        if (kMixed) {
+            // bl[2q][nt] := bf16 W of pair q (b0 = tile 2q rows tq, tq+4; b1 = tile 2q+1), bl[2q+1][nt] := bf16 (W - tf32 W)
+#pragma unroll
+            for (int q = 0; q < KT / 2; ++q)
+#pragma unroll
+                for (int nt = 0; nt < 2; ++nt) {
+                    float x[2][2], r[2][2];
+#pragma unroll
+                    for (int j = 0; j < 2; ++j)
+#pragma unroll
+                        for (int e = 0; e < 2; ++e) {
+                            const int k = 8 * (kh * KT + 2 * q + j) + tq + 4 * e;
+                            x[j][e] = Wg[((size_t)k * H + ncol_unit) * 4 + 2 * nt + (g & 1)];
+                            r[j][e] = x[j][e] - __uint_as_float(bh[2 * q + j][nt][e]);
+                        }
+                    bl[2 * q][nt][0] = pack_bf16(x[0][0], x[0][1]);
+                    bl[2 * q][nt][1] = pack_bf16(x[1][0], x[1][1]);
+                    bl[2 * q + 1][nt][0] = pack_bf16(r[0][0], r[0][1]);
+                    bl[2 * q + 1][nt][1] = pack_bf16(r[1][0], r[1][1]);
+                }
+        }
     }
     // this thread's pointwise element of every slice: row g + 8 kh, unit 4 ng + tq
     const int prow = g + 8 * kh;
@@ -200,13 +266,17 @@ __global__ void __launch_bounds__(NTH, 1) rec_fwd_mc_kernel(MParams p) {
     uint32_t phase = 0;                                          // bit (2 sl + buf)
     const bool rec = p.dbg != nullptr && blockIdx.x == 0 && tid == 0;
     // x-projection pre-activations, prefetched one step ahead
+    // element (b, t, dir, unit) of G (float4), Cst and Hout is idx = ((b sb + t st) ndir + dir) H + unit: kept as a
+    // running index so the step loop carries no 64-bit address arithmetic
     float4 gxn[NS];
+    long long idx[NS];
+    const long long tstep = (dir == 0 ? 1 : -1) * p.st * ndir * H;
 #pragma unroll
     for (int sl = 0; sl < NS; ++sl) {
         gxn[sl] = make_float4(0.f, 0.f, 0.f, 0.f);
         const int t0 = dir == 0 ? 0 : T - 1;
-        if (t0 < plen[sl])
-            gxn[sl] = reinterpret_cast<const float4*>(p.G)[(((size_t)pb[sl] * p.sb + (size_t)t0 * p.st) * ndir + dir) * H + unit];
+        idx[sl] = (((long long)pb[sl] * p.sb + (long long)t0 * p.st) * ndir + dir) * H + unit;
+        if (t0 < plen[sl]) gxn[sl] = reinterpret_cast<const float4*>(p.G)[idx[sl]];
     }
     __syncthreads();
     cluster_sync_all();
@@ -219,7 +289,8 @@ __global__ void __launch_bounds__(NTH, 1) rec_fwd_mc_kernel(MParams p) {
         for (int sl = 0; sl < NS; ++sl) {
             if (!live[sl]) continue;
             const bool active = t < plen[sl];
-            const size_t row = (size_t)pb[sl] * p.sb + (size_t)t * p.st;
+            const long long ix = idx[sl];
+            idx[sl] = ix + tstep;
             const float4 gx = gxn[sl];
             if (rec) p.dbg[(s * NS + sl) * 8 + 0] = clock64();
             float z[4] = {0.f, 0.f, 0.f, 0.f};
@@ -234,12 +305,24 @@ __global__ void __launch_bounds__(NTH, 1) rec_fwd_mc_kernel(MParams p) {
                 if (tid == 0) mbar_expect_tx(&full[sl][buf], CS * TILE * 4);     // arm this buffer's next phase
                 if (rec) p.dbg[(s * NS + sl) * 8 + 1] = clock64();
                 const float* hb = h_s + (size_t)(sl * 2 + buf) * CS * TILE + kh * KT * 128 + lane * 4;
-                float4 a_cur = *reinterpret_cast<const float4*>(hb);
+                if (kMixed) {
+                    float4 a0 = *reinterpret_cast<const float4*>(hb), a1 = *reinterpret_cast<const float4*>(hb + 128);
 #pragma unroll
-                for (int kt = 0; kt < KT; ++kt) {
-                    const float4 a_nxt = *reinterpret_cast<const float4*>(hb + (kt + 1 < KT ? kt + 1 : kt) * 128);
-                    ktile_mma<2>(acc, accx, a_cur, bh[kt], bl[kt]);
-                    a_cur = a_nxt;
+                    for (int q = 0; q < KT / 2; ++q) {
+                        const int qn = q + 1 < KT / 2 ? q + 1 : q;
+                        const float4 n0 = *reinterpret_cast<const float4*>(hb + (2 * qn) * 128);
+                        const float4 n1 = *reinterpret_cast<const float4*>(hb + (2 * qn + 1) * 128);
+                        k16_mma<2>(acc, accx, a0, a1, bh[2 * q], bh[2 * q + 1], bl[2 * q], bl[2 * q + 1]);
+                        a0 = n0; a1 = n1;
+                    }
+                } else {
+                    float4 a_cur = *reinterpret_cast<const float4*>(hb);
+#pragma unroll
+                    for (int kt = 0; kt < KT; ++kt) {
+                        const float4 a_nxt = *reinterpret_cast<const float4*>(hb + (kt + 1 < KT ? kt + 1 : kt) * 128);
+                        ktile_mma<2>(acc, accx, a_cur, bh[kt], bl[kt]);
+                        a_cur = a_nxt;
+                    }
                 }
 #pragma unroll
                 for (int nt = 0; nt < 2; ++nt)
@@ -249,9 +332,11 @@ __global__ void __launch_bounds__(NTH, 1) rec_fwd_mc_kernel(MParams p) {
                 // k-half combine: send the partials of the row the partner warp finishes
                 const float4 send = kh == 0 ? make_float4(acc[0][2], acc[0][3], acc[1][2], acc[1][3])
                                             : make_float4(acc[0][0], acc[0][1], acc[1][0], acc[1][1]);
-                xchg[w * 32 + lane] = send;
+                // double-buffered by slice-step parity: the pair barrier of the step in between orders the reuse
+                float4* xb = xchg + (((s * NS + sl) & 1) * 8) * 32;
+                xb[w * 32 + lane] = send;
                 pair_barrier(1 + ng);
-                const float4 recv = xchg[(w ^ 4) * 32 + lane];
+                const float4 recv = xb[(w ^ 4) * 32 + lane];
                 z[0] = (kh == 0 ? acc[0][0] : acc[0][2]) + recv.x;
                 z[1] = (kh == 0 ? acc[0][1] : acc[0][3]) + recv.y;
                 z[2] = (kh == 0 ? acc[1][0] : acc[1][2]) + recv.z;
@@ -277,18 +362,25 @@ __global__ void __launch_bounds__(NTH, 1) rec_fwd_mc_kernel(MParams p) {
                 gt[(ng >> 1) * 128 + lane * 4 + 2 * (ng & 1) + kh] = h_reg[sl];      // fragment order
                 asm volatile("fence.proxy.async.global;" ::: "memory");
                 if (rec) p.dbg[(s * NS + sl) * 8 + 5] = clock64();
-                __syncthreads();
-                if (tid == 0)
-                    bulk_multicast(s_u32(h_s + ((size_t)(sl * 2 + (buf ^ 1)) * CS + rank) * TILE), gt, TILE * 4,
-                                   s_u32(&full[sl][buf ^ 1]), (uint16_t)((1u << CS) - 1u));
+                __syncwarp();
+                // no CTA barrier: the warp that completes the tile (8th arrival of this slice-step) multicasts it
+                if (lane == 0) {
+                    unsigned old;
+                    asm volatile("atom.acq_rel.cta.shared::cta.add.u32 %0, [%1], 1;" : "=r"(old) : "r"(s_u32(&pubcnt[sl])) : "memory");
+                    if ((old & 7u) == 7u) {
+                        asm volatile("fence.proxy.async.global;" ::: "memory");
+                        bulk_multicast(s_u32(h_s + ((size_t)(sl * 2 + (buf ^ 1)) * CS + rank) * TILE), gt, TILE * 4,
+                                       s_u32(&full[sl][buf ^ 1]), (uint16_t)((1u << CS) - 1u));
+                    }
+                }
             }
             if (rec) p.dbg[(s * NS + sl) * 8 + 6] = clock64();
             if (s + 1 < T && tn < plen[sl])
-                gxn[sl] = reinterpret_cast<const float4*>(p.G)[(((size_t)pb[sl] * p.sb + (size_t)tn * p.st) * ndir + dir) * H + unit];
+                gxn[sl] = reinterpret_cast<const float4*>(p.G)[ix + tstep];
             if (active) {
-                reinterpret_cast<float4*>(p.G)[(row * ndir + dir) * H + unit] = act;
-                p.Cst[(row * ndir + dir) * H + unit] = cn;
-                p.Hout[row * ndir * H + dir * H + unit] = h_reg[sl];
+                reinterpret_cast<float4*>(p.G)[ix] = act;
+                p.Cst[ix] = cn;
+                p.Hout[ix] = h_reg[sl];
             }
             if (rec) p.dbg[(s * NS + sl) * 8 + 7] = clock64();
         }
@@ -344,6 +436,27 @@ __global__ void __launch_bounds__(NTH, 1) rec_bwd_mc_kernel(MParams p) {
                     bh[kt][nt][e] = cvt_tf32(x);
                     bl[kt][nt][e] = cvt_tf32(x - __uint_as_float(bh[kt][nt][e]));
                 }
+        if (kMixed) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+#pragma unroll
+                for (int nt = 0; nt < NTL; ++nt) {
+                    const int n_unit = 16 * (w * ND + nt / 2) + 4 * (g >> 1) + 2 * (nt & 1) + (g & 1);
+                    float x[2][2], r[2][2];
+#pragma unroll
+                    for (int j = 0; j < 2; ++j)
+#pragma unroll
+                        for (int e = 0; e < 2; ++e) {
+                            const int kcol = 8 * (2 * q + j) + tq + 4 * e;
+                            x[j][e] = Wg[(size_t)n_unit * H * 4 + rank * 4 * UPC + kcol];
+                            r[j][e] = x[j][e] - __uint_as_float(bh[2 * q + j][nt][e]);
+                        }
+                    bl[2 * q][nt][0] = pack_bf16(x[0][0], x[0][1]);
+                    bl[2 * q][nt][1] = pack_bf16(x[1][0], x[1][1]);
+                    bl[2 * q + 1][nt][0] = pack_bf16(r[0][0], r[0][1]);
+                    bl[2 * q + 1][nt][1] = pack_bf16(r[1][0], r[1][1]);
+                }
+        }
     }
     // pointwise element of this thread: row = tid / UPC, unit ul = tid % UPC
     const int prow = tid / UPC, ul = tid % UPC;
@@ -367,21 +480,26 @@ __global__ void __launch_bounds__(NTH, 1) rec_bwd_mc_kernel(MParams p) {
     // saved activations / states / upstream gradient of a step, prefetched one step ahead
     float4 act_n[NS];
     float cst_n[NS], cprev_n[NS], dout_n[NS];
-    auto prefetch = [&](int sl, int t) {
+    // running element index of (b, t, dir, unit) in G (float4) / Cst / dOut; the walk goes against the forward one
+    long long idx[NS];
+    const long long tstep = (dir == 0 ? -1 : 1) * p.st * ndir * H;
+    auto prefetch = [&](int sl, int t, long long ix) {
         act_n[sl] = make_float4(0.f, 0.f, 0.f, 0.f);
         cst_n[sl] = 0.f; cprev_n[sl] = 0.f; dout_n[sl] = 0.f;
         if (t >= 0 && t < plen[sl]) {
-            const size_t row = (size_t)pb[sl] * p.sb + (size_t)t * p.st;
             const int t_cprev = dir == 0 ? t - 1 : t + 1;
-            act_n[sl] = reinterpret_cast<const float4*>(p.G)[(row * ndir + dir) * H + unit];
-            cst_n[sl] = p.Cst[(row * ndir + dir) * H + unit];
-            if (t_cprev >= 0 && t_cprev < plen[sl])
-                cprev_n[sl] = p.Cst[(((size_t)pb[sl] * p.sb + (size_t)t_cprev * p.st) * ndir + dir) * H + unit];
-            dout_n[sl] = __ldg(p.dOut + row * ndir * H + dir * H + unit);
+            act_n[sl] = reinterpret_cast<const float4*>(p.G)[ix];
+            cst_n[sl] = p.Cst[ix];
+            if (t_cprev >= 0 && t_cprev < plen[sl]) cprev_n[sl] = p.Cst[ix + tstep];
+            dout_n[sl] = __ldg(p.dOut + ix);
         }
     };
 #pragma unroll
-    for (int sl = 0; sl < NS; ++sl) prefetch(sl, dir == 0 ? T - 1 : 0);
+    for (int sl = 0; sl < NS; ++sl) {
+        const int t0 = dir == 0 ? T - 1 : 0;
+        idx[sl] = (((long long)pb[sl] * p.sb + (long long)t0 * p.st) * ndir + dir) * H + unit;
+        prefetch(sl, t0, idx[sl]);
+    }
     __syncthreads();
     cluster_sync_all();
 
@@ -392,7 +510,8 @@ __global__ void __launch_bounds__(NTH, 1) rec_bwd_mc_kernel(MParams p) {
         for (int sl = 0; sl < NS; ++sl) {
             if (!live[sl]) continue;
             const bool active = t < plen[sl];
-            const size_t row = (size_t)pb[sl] * p.sb + (size_t)t * p.st;
+            const long long ix = idx[sl];
+            idx[sl] = ix + tstep;
             const float4 act = act_n[sl];
             const float cst = cst_n[sl], cprev = cprev_n[sl], dout = dout_n[sl];
             if (rec) p.dbg[(s * NS + sl) * 8 + 0] = clock64();
@@ -431,8 +550,8 @@ __global__ void __launch_bounds__(NTH, 1) rec_bwd_mc_kernel(MParams p) {
                 dq[((c0 + 2) ^ kx) * 4] = dz.z;
                 dq[((c0 + 3) ^ kx) * 4] = dz.w;
             }
-            if (pb[sl] < p.B) reinterpret_cast<float4*>(p.G)[(row * ndir + dir) * H + unit] = dz;
-            if (s + 1 < T) prefetch(sl, dir == 0 ? t - 1 : t + 1);
+            if (pb[sl] < p.B) reinterpret_cast<float4*>(p.G)[ix] = dz;
+            if (s + 1 < T) prefetch(sl, dir == 0 ? t - 1 : t + 1, ix + tstep);
             if (rec) p.dbg[(s * NS + sl) * 8 + 3] = clock64();
             __syncthreads();
             if (rec) p.dbg[(s * NS + sl) * 8 + 4] = clock64();
@@ -442,13 +561,26 @@ __global__ void __launch_bounds__(NTH, 1) rec_bwd_mc_kernel(MParams p) {
                 for (int nt = 0; nt < NTL; ++nt)
 #pragma unroll
                     for (int q = 0; q < 4; ++q) { acc[nt][q] = 0.f; accx[nt][q] = 0.f; }
-                float4 a_cur = *reinterpret_cast<const float4*>(dzs + lane * 4);
+                if (kMixed) {
+                    float4 a0 = *reinterpret_cast<const float4*>(dzs + lane * 4);
+                    float4 a1 = *reinterpret_cast<const float4*>(dzs + 128 + ((lane ^ 1) * 4));
 #pragma unroll
-                for (int kt = 0; kt < 8; ++kt) {
-                    const int kn = kt + 1 < 8 ? kt + 1 : kt;
-                    const float4 a_nxt = *reinterpret_cast<const float4*>(dzs + kn * 128 + ((lane ^ kn) * 4));
-                    ktile_mma<NTL>(acc, accx, a_cur, bh[kt], bl[kt]);
-                    a_cur = a_nxt;
+                    for (int q = 0; q < 4; ++q) {
+                        const int k0 = q + 1 < 4 ? 2 * q + 2 : 2 * q, k1 = k0 + 1;
+                        const float4 n0 = *reinterpret_cast<const float4*>(dzs + k0 * 128 + ((lane ^ k0) * 4));
+                        const float4 n1 = *reinterpret_cast<const float4*>(dzs + k1 * 128 + ((lane ^ k1) * 4));
+                        k16_mma<NTL>(acc, accx, a0, a1, bh[2 * q], bh[2 * q + 1], bl[2 * q], bl[2 * q + 1]);
+                        a0 = n0; a1 = n1;
+                    }
+                } else {
+                    float4 a_cur = *reinterpret_cast<const float4*>(dzs + lane * 4);
+#pragma unroll
+                    for (int kt = 0; kt < 8; ++kt) {
+                        const int kn = kt + 1 < 8 ? kt + 1 : kt;
+                        const float4 a_nxt = *reinterpret_cast<const float4*>(dzs + kn * 128 + ((lane ^ kn) * 4));
+                        ktile_mma<NTL>(acc, accx, a_cur, bh[kt], bl[kt]);
+                        a_cur = a_nxt;
+                    }
                 }
                 if (rec) p.dbg[(s * NS + sl) * 8 + 5] = clock64();
                 float* sg = stage + ((size_t)(sl * 2 + buf) * CS + w * ND) * TILE + g * UPC + 4 * tq;
@@ -478,7 +610,7 @@ __global__ void __launch_bounds__(NTH, 1) rec_bwd_mc_kernel(MParams p) {
     cluster_sync_all();
 }
 
-size_t fwd_smem(int CS, int NS) { return sizeof(float) * ((size_t)NS * 2 * CS * TILE) + 8 * 32 * 16; }
+size_t fwd_smem(int CS, int NS) { return sizeof(float) * ((size_t)NS * 2 * CS * TILE) + 2 * 8 * 32 * 16; }
 size_t bwd_smem(int CS, int NS) { return sizeof(float) * ((size_t)NS * 4 * CS * TILE + (size_t)NS * 4 * TILE); }
 
 template <int CS, int NS>
