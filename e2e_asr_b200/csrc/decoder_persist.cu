@@ -21,6 +21,8 @@
 
 namespace e2e {
 
+extern long long* g_rec_dbg;
+
 namespace {
 
 constexpr int NTH = 256;
@@ -86,6 +88,10 @@ __device__ __forceinline__ void grid_barrier(unsigned* ctr, unsigned& epoch, int
 
 __device__ __forceinline__ float ldcg(const float* p) { return __ldcg(p); }
 
+// profiling aid (e2e_set_rec_debug): clock64 stamps of CTA 0 / thread 0, 8 per step
+__device__ long long* d_dec_dbg = nullptr;
+#define DEC_STAMP(step, i) do { if (dbg) dbg[(step) * 8 + (i)] = clock64(); } while (0)
+
 }  // namespace
 
 // ======================================================================= forward
@@ -113,7 +119,9 @@ __global__ void __launch_bounds__(NTH, 1) dec_fwd_persist_kernel(e2e_dec_persist
     if (resident && (int)blockIdx.x < gtiles) load_wt(blockIdx.x % NCB);
     __syncthreads();
 
+    long long* dbg = (blockIdx.x == 0 && threadIdx.x == 0) ? d_dec_dbg : nullptr;
     for (int t = 0; t < U; ++t) {
+        DEC_STAMP(t, 0);
         // ------------------------------------------------------------ phase G
         for (int tile = blockIdx.x; tile < gtiles; tile += gridDim.x) {
             const int rb = tile / NCB, cb = tile % NCB;
@@ -176,7 +184,9 @@ __global__ void __launch_bounds__(NTH, 1) dec_fwd_persist_kernel(e2e_dec_persist
             }
             __syncthreads();
         }
+        DEC_STAMP(t, 1);
         grid_barrier(p.ctr, epoch, p.err);
+        DEC_STAMP(t, 2);
         // ------------------------------------------------------------ phase Y: y = c_new . q_k + q_b
         {
             const int ytiles = nrb * (A / 8);
@@ -221,7 +231,9 @@ __global__ void __launch_bounds__(NTH, 1) dec_fwd_persist_kernel(e2e_dec_persist
                 }
             }
         }
+        DEC_STAMP(t, 3);
         grid_barrier(p.ctr, epoch, p.err);
+        DEC_STAMP(t, 4);
         // ------------------------------------------------------------ phase A: attention read-out
         {
             float* y_s = a_s;                       // [A]
@@ -319,7 +331,9 @@ __global__ void __launch_bounds__(NTH, 1) dec_fwd_persist_kernel(e2e_dec_persist
                 }
             }
         }
+        DEC_STAMP(t, 5);
         grid_barrier(p.ctr, epoch, p.err);
+        DEC_STAMP(t, 6);
     }
 }
 
@@ -352,7 +366,9 @@ __global__ void __launch_bounds__(NTH, 1) dec_bwd_persist_kernel(e2e_dec_persist
     if (resident && (int)blockIdx.x < xtiles) load_wt2(blockIdx.x % NXB);
     __syncthreads();
 
+    long long* dbg = (blockIdx.x == 0 && threadIdx.x == 0) ? d_dec_dbg : nullptr;
     for (int t = U - 1; t >= 0; --t) {
+        DEC_STAMP(t, 0);
         // ------------------------------------------------------------ phase A': attention backward (CTA per row)
         {
             float* y_s = z_s;                   // [A]
@@ -412,7 +428,9 @@ __global__ void __launch_bounds__(NTH, 1) dec_bwd_persist_kernel(e2e_dec_persist
                 }
             }
         }
+        DEC_STAMP(t, 1);
         grid_barrier(p.ctr, epoch, p.err);
+        DEC_STAMP(t, 2);
         // ------------------------------------------------------------ phase P: dc_new += dy . q_k^T ; pointwise backward
         {
             const int NCB = Hd / 8, ptiles = nrb * NCB;
@@ -471,7 +489,9 @@ __global__ void __launch_bounds__(NTH, 1) dec_bwd_persist_kernel(e2e_dec_persist
                 }
             }
         }
+        DEC_STAMP(t, 3);
         grid_barrier(p.ctr, epoch, p.err);
+        DEC_STAMP(t, 4);
         // ------------------------------------------------------------ phase X: [dctx_{t-1} | dh_{t-1}] = dz_t . W_ch^T
         for (int tile = blockIdx.x; tile < xtiles; tile += gridDim.x) {
             const int rb = tile / NXB, xb = tile % NXB;
@@ -510,7 +530,9 @@ __global__ void __launch_bounds__(NTH, 1) dec_bwd_persist_kernel(e2e_dec_persist
                 }
             }
         }
+        DEC_STAMP(t, 5);
         grid_barrier(p.ctr, epoch, p.err);
+        DEC_STAMP(t, 6);
     }
 }
 
@@ -587,6 +609,13 @@ int dec_persist(cudaStream_t st, bool bwd, const e2e_dec_persist_args* a, float*
                    : max(max(2 * p.B, nrb * (p.Hd / 8)), nrb * (p.A / 8));
     int grid = min(nsm, want);
     E2E_CHECK_CUDA(cudaMemsetAsync(p.ctr, 0, sizeof(unsigned), st));
+    {
+        static long long* last_dbg = nullptr;
+        if (g_rec_dbg != last_dbg) {
+            last_dbg = g_rec_dbg;
+            E2E_CHECK_CUDA(cudaMemcpyToSymbolAsync(d_dec_dbg, &last_dbg, sizeof(last_dbg), 0, cudaMemcpyHostToDevice, st));
+        }
+    }
     void* args[] = {&p};
     E2E_CHECK_CUDA(cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(NTH), args, smem, st));
     ++g_launches;

@@ -12,6 +12,7 @@ from ._lib import call
 
 # 0 = fp32 FFMA, 1 = 3xTF32 tcgen05 (fp32-accurate), 2 = bf16 tcgen05
 _GEMM_MODE = 0
+TAG_GEMM_SHAPES = False      # profiling aid: one profiler entry per GEMM shape instead of one "e2e_gemm"
 
 
 def set_gemm_mode(mode):
@@ -102,7 +103,8 @@ def gemm(a, b, out=None, ta=False, tb=False, bias=None, z=None, accumulate=False
     if mode != 0 and str(a.device) not in _workspace:
         ensure_workspace(a.device)
     call("e2e_gemm", mode, int(ta), int(tb), M, N, K, a, lda, b, ldb, out, ldc,
-         bias, z, ldz, int(accumulate), work=2.0 * M * N * K)
+         bias, z, ldz, int(accumulate), work=2.0 * M * N * K,
+         tag=("gemm M=%d N=%d K=%d t%d%d" % (M, N, K, ta, tb)) if TAG_GEMM_SHAPES else None)
     return out
 
 

@@ -9,7 +9,8 @@ def main(path):
     rows = list(csv.DictReader(l for l in open(path) if l.startswith('"')))
     agg = collections.defaultdict(lambda: [0, 0.0])
     for r in rows:
-        name = re.sub(r"\(.*", "", r["Kernel Name"]).replace("e2e::", "").replace("void ", "")
+        name = r["Kernel Name"].replace("(anonymous namespace)::", "").replace("<unnamed>::", "")
+        name = re.sub(r"\(.*", "", name).replace("e2e::", "").replace("void ", "")
         name = re.sub(r"<.*", "", name)
         agg[name][0] += 1
         agg[name][1] += float(r["Metric Value"]) / 1e3
