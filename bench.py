@@ -173,9 +173,22 @@ def main():
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device (the product path has no CPU fallback)")
-    rank, world, local = edist.init_from_env()
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
+    # NCCL prints its version banner on stdout at communicator creation: keep stdout for the ONE JSON line
+    sys.stdout.flush()
+    saved_stdout = os.dup(1)
+    os.dup2(2, 1)
+    try:
+        rank, world, local = edist.init_from_env()
+        torch.cuda.set_device(local)
+        dev = torch.device("cuda", local)
+        if world > 1:
+            warm = torch.zeros(1, device=dev)
+            dist.all_reduce(warm)
+            torch.cuda.synchronize()
+    finally:
+        sys.stdout.flush()
+        os.dup2(saved_stdout, 1)
+        os.close(saved_stdout)
     if args.gemm:
         ops.set_gemm_mode(args.gemm)
     W = max(args.warmup, 3)
@@ -298,6 +311,7 @@ def main():
                       "(oracle/model.py), mean of 2 steps after 1 warm-up, %.1f s/step"
                       % (args.config, sample_B, cfg.B, fr, sec)}
     print(json.dumps(line))
+    sys.stdout.flush()
 
 
 if __name__ == "__main__":

@@ -47,6 +47,7 @@ def _dev_state(device):
     key = str(device)
     if key not in _state:
         _state[key] = dict(ctr=torch.zeros(1 << 20, dtype=torch.int32, device=device),
+                           ctr_side=torch.zeros(1 << 20, dtype=torch.int32, device=device),
                            err=torch.zeros(1, dtype=torch.int32, device=device),
                            partials=torch.zeros(512, dtype=torch.float32, device=device),
                            one=torch.ones(1, dtype=torch.float32, device=device))
@@ -170,6 +171,32 @@ def _unpack_lstm(dWx, dWh, dbp, I, H, nd, device):
     return outs
 
 
+# Weight-gradient side stream.  The dW GEMMs of a layer (x^T dz, h^T dz, bias column sums) are off the
+# backward critical path: only dX feeds the layer below.  When enabled (Seq2SeqModel does, for
+# VariableStore parameters whose .grad is a view of the flat gradient buffer) they are enqueued on a
+# second stream, accumulate straight into the flat buffer and overlap the next layer's latency-bound
+# recurrence, which occupies 64 of the 148 SMs.  `sync_wgrad_stream` joins it before clipping.
+_WGRAD = {}
+
+
+def enable_wgrad_stream(device, enabled=True):
+    key = str(torch.device(device))
+    if not enabled:
+        _WGRAD.pop(key, None)
+        return None
+    if key not in _WGRAD:
+        _WGRAD[key] = torch.cuda.Stream(device=device)
+    if _GEMM_MODE != 0:
+        ensure_workspace(device, stream=_WGRAD[key])
+    return _WGRAD[key]
+
+
+def sync_wgrad_stream(device):
+    s = _WGRAD.get(str(torch.device(device)))
+    if s is not None:
+        torch.cuda.current_stream().wait_stream(s)
+
+
 class BiLSTMLayerFn(torch.autograd.Function):
     """One bidirectional LSTM encoder layer over a zero-padded batch-major buffer
     (reference Encoder._layer_encoder_input, encoder.py:55-91).
@@ -194,6 +221,8 @@ class BiLSTMLayerFn(torch.autograd.Function):
              st["ctr"].numel() * 4, st["err"], work=float(T), tag="enc_rec_fwd")
         ctx.save_for_backward(x, Wx, Wh, G, Cst, out, lens_i32)
         ctx.dims = (B, Tp, I, H, T)
+        # flat-gradient-buffer views of the four parameters (None for plain tensors)
+        ctx.grad_dst = tuple(getattr(t, "grad", None) for t in (k_fw, b_fw, k_bw, b_bw))
         return out
 
     @staticmethod
@@ -208,13 +237,31 @@ class BiLSTMLayerFn(torch.autograd.Function):
         N = B * Tp
         x2, o2 = x.view(N, I), out.view(N, 2 * H)
         dX = gemm(G, Wx, tb=True).view(B, Tp, I) if ctx.needs_input_grad[0] else None
-        dWx = gemm(x2, G, ta=True)                                  # [I, 8H]
-        dWh = torch.empty((2, H, 4 * H), dtype=torch.float32, device=dev)
-        # h_{t-1}^T dz_t: fw pairs out[t-1] with dz[t], bw pairs out[t+1] with dz[t]; the flat
-        # one-row shift never crosses an utterance because out[b, Tp-1] == 0 and dz[b, Tp-1] == 0.
-        gemm(o2[:N - 1, 0:H], G[1:, 0:4 * H], ta=True, out=dWh[0])
-        gemm(o2[1:, H:2 * H], G[:N - 1, 4 * H:8 * H], ta=True, out=dWh[1])
-        dbp = colsum(G)
+
+        def weight_grads():
+            dWx = gemm(x2, G, ta=True)                                  # [I, 8H]
+            dWh = torch.empty((2, H, 4 * H), dtype=torch.float32, device=dev)
+            # h_{t-1}^T dz_t: fw pairs out[t-1] with dz[t], bw pairs out[t+1] with dz[t]; the flat
+            # one-row shift never crosses an utterance because out[b, Tp-1] == 0 and dz[b, Tp-1] == 0.
+            gemm(o2[:N - 1, 0:H], G[1:, 0:4 * H], ta=True, out=dWh[0])
+            gemm(o2[1:, H:2 * H], G[:N - 1, 4 * H:8 * H], ta=True, out=dWh[1])
+            dbp = colsum(G)
+            return dWx, dWh, dbp
+
+        side = _WGRAD.get(str(dev))
+        dst = ctx.grad_dst
+        if side is not None and all(d is not None for d in dst) and all(ctx.needs_input_grad[1:5]):
+            main = torch.cuda.current_stream()
+            side.wait_stream(main)
+            with torch.cuda.stream(side):
+                dWx, dWh, dbp = weight_grads()
+                for d in range(2):      # += into the flat gradient buffer (what AccumulateGrad would do)
+                    call("e2e_lstm_unpack_grads", I, H, dst[2 * d], dst[2 * d + 1], dWx, 8 * H, d * 4 * H, dWh[d],
+                         dbp, 1)
+            for t_ in (x, G, out):
+                t_.record_stream(side)
+            return dX, None, None, None, None, None, None
+        dWx, dWh, dbp = weight_grads()
         dk_fw, db_fw, dk_bw, db_bw = _unpack_lstm(dWx, dWh, dbp, I, H, 2, dev)
         return dX, dk_fw, db_fw, dk_bw, db_bw, None, None
 
@@ -424,6 +471,11 @@ class AttnDecoderFnV2(torch.autograd.Function):
                               bufs["alpha"])
         ctx.dims = (B, Tn, D, V, E, Hl, Hd, A, U, Tp)
         ctx.stash = stash
+        # flat-gradient-buffer views of the 17 parameters, in the order backward returns their gradients
+        ctx.grad_dst = tuple(None if t is None else getattr(t, "grad", None) for t in
+                             (emb, attn_w, attn_v, lm_k, lm_b, dec_k, dec_b, q_k, q_b, ap_k, ap_b, out_k, out_b,
+                              in_k, in_b, sp_k, sp_b))
+        ctx.has_sp = sp_k is not None
         return logits
 
     @staticmethod
@@ -438,11 +490,8 @@ class AttnDecoderFnV2(torch.autograd.Function):
         dlogits = dlogits.contiguous()
         enc_flat, _, _ = flat_rows(enc)
         nrows = enc_flat.shape[0]
-        dout_k = gemm(proj, dlogits, ta=True)
-        dout_b = colsum(dlogits)
+        # ---- critical path (main stream): dlogits -> dcat -> sequential backward -> d enc
         dproj = gemm(dlogits, out_k, tb=True)
-        dap_k = gemm(cat, dproj, ta=True)
-        dap_b = colsum(dproj)
         dcat = gemm(dproj, ap_k, tb=True)                             # [U*B, Hd+D]
         out = dict(dcat=dcat, dz=torch.empty((U * B, 4 * Hd), **f32), dch=torch.empty((U * B, D + Hd), **f32),
                    dy=torch.empty((U * B, A), **f32), ds=torch.empty((U * B, Tn), **f32),
@@ -458,47 +507,75 @@ class AttnDecoderFnV2(torch.autograd.Function):
             setattr(a, k, v.data_ptr())
         call("e2e_decoder_persist_bwd", a, denc, dHF, dv_part, work=float(U))
         dz, dy = out["dz"], out["dy"]
-        dq_k = gemm(cat[:, :Hd], dy, ta=True)
-        dq_b = colsum(dy)
-        dattn_v = colsum(dv_part)
-        # gates = pre.Wx + ctx_prev.(W_in_c.Wx) + h_prev.Wh + b   (columns gate-interleaved)
-        dW_cx = torch.zeros((D, 4 * Hd), **f32)
-        if U > 1:
-            gemm(cat[:(U - 1) * B, Hd:], dz[B:], ta=True, out=dW_cx)   # ctx_{t-1} pairs with dz_t
-        dWh_dec = gemm(hprev, dz, ta=True).view(1, Hd, 4 * Hd)
-        dWx_dec = gemm(pre, dz, ta=True)
-        gemm(in_k[Hd:], dW_cx, ta=True, out=dWx_dec, accumulate=True)  # + W_in_c^T . dW_cx
-        dbp_dec = colsum(dz)
-        ddec_k, ddec_b = _unpack_lstm(dWx_dec, dWh_dec, dbp_dec, E, Hd, 1, dev)
-        dpre = gemm(dz, Wx_dec, tb=True)                              # [U*B, E]
-        din_k = torch.empty((Hd + D, E), **f32)
-        gemm(m, dpre, ta=True, out=din_k[:Hd])
-        gemm(dW_cx, Wx_dec, tb=True, out=din_k[Hd:])                  # dW_in_c = dW_cx . Wx^T
-        din_b = colsum(dpre)
-        dm = gemm(dpre, in_k[:Hd], tb=True)
-        dsp_k = dsp_b = None
-        if sp_k is not None:
-            dsp_k = gemm(hl, dm, ta=True)
-            dsp_b = colsum(dm)
-            dm = gemm(dm, sp_k, tb=True)
-        call("e2e_lstm_rec_bwd", B, U, U, Hl, 1, 1, B, G_lm, C_lm, Wh_lm, dm, lens_i32, st["ctr"],
-             st["ctr"].numel() * 4, st["err"], work=float(U), tag="lm_rec_bwd")
-        dWx_lm = gemm(u, G_lm, ta=True)
-        dWh_lm = torch.zeros((1, Hl, 4 * Hl), **f32)
-        if U > 1:
-            gemm(hl[:(U - 1) * B], G_lm[B:], ta=True, out=dWh_lm[0])
-        dbp_lm = colsum(G_lm)
-        dlm_k, dlm_b = _unpack_lstm(dWx_lm, dWh_lm, dbp_lm, E, Hl, 1, dev)
-        du = gemm(G_lm, Wx_lm, tb=True)
-        demb = torch.zeros((V, E), **f32)
-        call("e2e_embed_scatter_add", U * B, E, demb, ids, du, E)
-        if ctx.stash is not None:
-            ctx.stash["emb_values"] = du
-        dattn_w = gemm(enc_flat, dHF, ta=True).view(attn_w.shape)
         gemm(dHF, attn_w.view(D, A), tb=True, out=denc, accumulate=True)
         denc_view = torch.as_strided(denc, (B, Tn, D), (Tp * D, D, 1)) if ctx.needs_input_grad[0] else None
-        return (denc_view, demb, dattn_w, dattn_v, dlm_k, dlm_b, ddec_k, ddec_b, dq_k, dq_b, dap_k, dap_b, dout_k,
-                dout_b, din_k, din_b, dsp_k, dsp_b, None, None, None, None, None)
+
+        # ---- parameter gradients (nothing downstream waits for them): 17 tensors in input order
+        def param_grads(ctr):
+            dout_k = gemm(proj, dlogits, ta=True)
+            dout_b = colsum(dlogits)
+            dap_k = gemm(cat, dproj, ta=True)
+            dap_b = colsum(dproj)
+            dq_k = gemm(cat[:, :Hd], dy, ta=True)
+            dq_b = colsum(dy)
+            dattn_v = colsum(dv_part)
+            # gates = pre.Wx + ctx_prev.(W_in_c.Wx) + h_prev.Wh + b   (columns gate-interleaved)
+            dW_cx = torch.zeros((D, 4 * Hd), **f32)
+            if U > 1:
+                gemm(cat[:(U - 1) * B, Hd:], dz[B:], ta=True, out=dW_cx)   # ctx_{t-1} pairs with dz_t
+            dWh_dec = gemm(hprev, dz, ta=True).view(1, Hd, 4 * Hd)
+            dWx_dec = gemm(pre, dz, ta=True)
+            gemm(in_k[Hd:], dW_cx, ta=True, out=dWx_dec, accumulate=True)  # + W_in_c^T . dW_cx
+            dbp_dec = colsum(dz)
+            ddec_k, ddec_b = _unpack_lstm(dWx_dec, dWh_dec, dbp_dec, E, Hd, 1, dev)
+            dpre = gemm(dz, Wx_dec, tb=True)                              # [U*B, E]
+            din_k = torch.empty((Hd + D, E), **f32)
+            gemm(m, dpre, ta=True, out=din_k[:Hd])
+            gemm(dW_cx, Wx_dec, tb=True, out=din_k[Hd:])                  # dW_in_c = dW_cx . Wx^T
+            din_b = colsum(dpre)
+            dm = gemm(dpre, in_k[:Hd], tb=True)
+            dsp_k = dsp_b = None
+            if sp_k is not None:
+                dsp_k = gemm(hl, dm, ta=True)
+                dsp_b = colsum(dm)
+                dm = gemm(dm, sp_k, tb=True)
+            call("e2e_lstm_rec_bwd", B, U, U, Hl, 1, 1, B, G_lm, C_lm, Wh_lm, dm, lens_i32, ctr,
+                 ctr.numel() * 4, st["err"], work=float(U), tag="lm_rec_bwd")
+            dWx_lm = gemm(u, G_lm, ta=True)
+            dWh_lm = torch.zeros((1, Hl, 4 * Hl), **f32)
+            if U > 1:
+                gemm(hl[:(U - 1) * B], G_lm[B:], ta=True, out=dWh_lm[0])
+            dbp_lm = colsum(G_lm)
+            dlm_k, dlm_b = _unpack_lstm(dWx_lm, dWh_lm, dbp_lm, E, Hl, 1, dev)
+            du = gemm(G_lm, Wx_lm, tb=True)
+            demb = torch.zeros((V, E), **f32)
+            call("e2e_embed_scatter_add", U * B, E, demb, ids, du, E)
+            if ctx.stash is not None:
+                ctx.stash["emb_values"] = du
+            dattn_w = gemm(enc_flat, dHF, ta=True).view(attn_w.shape)
+            return [demb, dattn_w, dattn_v, dlm_k, dlm_b, ddec_k, ddec_b, dq_k, dq_b, dap_k, dap_b, dout_k,
+                    dout_b, din_k, din_b, dsp_k, dsp_b]
+
+        side = _WGRAD.get(str(dev))
+        dst = ctx.grad_dst
+        need = [True] * 15 + [ctx.has_sp, ctx.has_sp]
+        if (side is not None and all((d is not None) or (not n) for d, n in zip(dst, need))
+                and all(ctx.needs_input_grad[1 + i] or not need[i] for i in range(17))):
+            main = torch.cuda.current_stream()
+            side.wait_stream(main)
+            with torch.cuda.stream(side):
+                grads = param_grads(st["ctr_side"])
+                for d, g in zip(dst, grads):
+                    if g is not None:
+                        d.add_(g.view(d.shape))     # what AccumulateGrad would do, on the side stream
+            if ctx.stash is not None and ctx.stash.get("emb_values") is not None:
+                ctx.stash["emb_values"].record_stream(main)      # read by clip_gradients after the join
+            for t_ in list(ctx.saved_tensors) + [dlogits, dproj, dz, dy, dv_part, dHF] + [g for g in grads if g is not None]:
+                if t_ is not None:
+                    t_.record_stream(side)
+            return (denc_view,) + (None,) * 22
+        grads = param_grads(st["ctr"])
+        return (denc_view,) + tuple(grads) + (None, None, None, None, None)
 
 
 # ---------------------------------------------------------------------------

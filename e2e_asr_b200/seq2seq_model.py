@@ -207,7 +207,10 @@ class Seq2SeqModel(BaseParams):
                 self.total_loss = self.total_loss / float(len(self.losses))
 
         # Gradients, clipping (:148-151).  Adam (:137,153-155) is the "next" row.
+        if getattr(params, "overlap_weight_grads", True):
+            ops.enable_wgrad_stream(self.device)
         self.total_loss.backward()
+        ops.sync_wgrad_stream(self.device)
         if self.reducer is not None:
             self.reducer.allreduce_mean(self.variables.flat_grads())
         self.clip_gradients()
