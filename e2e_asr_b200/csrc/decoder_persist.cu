@@ -74,8 +74,50 @@ __device__ __forceinline__ void mma_block(float (&d)[4], const float* a_s, int l
     for (int j = 0; j < 4; ++j) d[j] += (dx[0][j] + dx[1][j]) + (dm[0][j] + dm[1][j]);
 }
 
+__device__ __forceinline__ void mma_tf32_nv(float (&d)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
+    asm("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+        : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+        : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+}
+// D[nt][16 x 8] += A[16 x K-range] . B for NT n-tiles: the A fragment of a k-tile is loaded and split ONCE and
+// reused by every n-tile (the warps of a CTA split K, not N).  B[k][n] = bt[n*ldb + k].
+template <int NT>
+__device__ __forceinline__ void mma_ksplit(float (&d)[NT][4], const float* a_s, int lda, const float* bt, int ldb,
+                                           int k_begin, int k_end, int g, int tq) {
+    const float* a0 = a_s + g * lda;
+    const float* a1 = a_s + (g + 8) * lda;
+    float dm[NT][4], dx[NT][4];
+#pragma unroll
+    for (int i = 0; i < NT; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { dm[i][j] = 0.f; dx[i][j] = 0.f; }
+#pragma unroll 2
+    for (int k = k_begin + tq; k < k_end; k += 8) {
+        uint32_t ah[4], al[4];
+        split_tf32(a0[k], ah[0], al[0]);
+        split_tf32(a1[k], ah[1], al[1]);
+        split_tf32(a0[k + 4], ah[2], al[2]);
+        split_tf32(a1[k + 4], ah[3], al[3]);
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt) {
+            const float* b0 = bt + (8 * nt + g) * ldb;
+            uint32_t bh[2], bl[2];
+            split_tf32(b0[k], bh[0], bl[0]);
+            split_tf32(b0[k + 4], bh[1], bl[1]);
+            mma_tf32_nv(dx[nt], al, bh);
+            mma_tf32_nv(dm[nt], ah, bh);
+            mma_tf32_nv(dx[nt], ah, bl);
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < NT; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) d[i][j] = dm[i][j] + dx[i][j];
+}
+
 // grid-wide barrier on a monotonically increasing counter (cooperative launch => co-resident)
 __device__ __forceinline__ void grid_barrier(unsigned* ctr, unsigned& epoch, int* err) {
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // generic smem writes before later bulk copies
     __syncthreads();
     if (threadIdx.x == 0) {
         __threadfence();
@@ -87,27 +129,80 @@ __device__ __forceinline__ void grid_barrier(unsigned* ctr, unsigned& epoch, int
 }
 
 __device__ __forceinline__ float ldcg(const float* p) { return __ldcg(p); }
+// ex2.approx + rcp.approx: absolute error ~2e-7, inside the 1e-4 parity budget
+__device__ __forceinline__ float sigmoid_fast(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
+__device__ __forceinline__ float tanh_fast(float x) { return 2.0f * __fdividef(1.0f, 1.0f + __expf(-2.0f * x)) - 1.0f; }
+
+__device__ __forceinline__ uint32_t s_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(s_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(s_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_par(uint64_t* bar, uint32_t parity) {
+    uint32_t ok = 0;
+    const long long t0 = clock64();
+    while (true) {
+        asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n"
+                     : "=r"(ok) : "r"(s_u32(bar)), "r"(parity) : "memory");
+        if (ok) break;
+        if (clock64() - t0 > (1ll << 33)) __trap();      // never hang the GPU on a protocol bug
+    }
+}
+// global -> own shared memory, completion (bytes) on an mbarrier of this CTA
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(s_u32(dst)), "l"(src), "r"(bytes), "r"(s_u32(bar)) : "memory");
+}
 
 // profiling aid (e2e_set_rec_debug): clock64 stamps of CTA 0 / thread 0, 8 per step
 __device__ long long* d_dec_dbg = nullptr;
-#define DEC_STAMP(step, i) do { if (dbg) dbg[(step) * 8 + (i)] = clock64(); } while (0)
+#define DEC_STAMP(step, i) do { if (dbg) dbg[(step) * 32 + (i)] = clock64(); } while (0)
 
 }  // namespace
 
 // ======================================================================= forward
-__global__ void __launch_bounds__(NTH, 1) dec_fwd_persist_kernel(e2e_dec_persist_args p) {
-    extern __shared__ __align__(16) float smem[];
+__global__ void __launch_bounds__(NTH, 1) dec_fwd_persist_kernel(e2e_dec_persist_args p, int attn_cap) {
+    extern __shared__ __align__(128) float smem[];
     const int B = p.B, U = p.U, Hd = p.Hd, A = p.A, D = p.D, Tn = p.Tn, Tp = p.Tp;
     const int K = D + Hd, G4 = 4 * Hd, CAT = Hd + D;
-    const int KS = K + 8;                      // Wt row stride
+    const int KS = K + 4;                      // Wt row stride (== 4 mod 32: conflict-free fragment loads)
     const int AS = K + 4;                      // A tile row stride
-    float* Wt = smem;                          // [32][KS]   W_ch^T slice of this CTA's column block
-    float* a_s = Wt + 32 * KS;                 // [16][AS]   A tile / scratch of the other phases
-    float* red = a_s + 16 * AS;                // [4][32][4] cross-warp partials (also 8 warps x 128 in phase Y)
+    const int QS_ = Hd + 4;                    // q_s row stride
+    float* Wt = smem;                          // [32][K+8]  W_ch^T slice of this CTA's column block
+    float* a_s = Wt + 32 * (K + 8);            // [16][AS]   A tile / scratch of the other phases
+    float* red = a_s + 16 * AS;                // [8][32][4] cross-warp partials of phase Y
+    float* gred = red + 8 * 32 * 4;            // [8][16][40] per-warp partial gate tiles of phase G
+    float* qres = gred + 8 * 16 * 40;          // [8][Hd+4]  resident q_k^T slice of this CTA's phase-Y tile
     const int tid = threadIdx.x, w = tid / 32, lane = tid % 32, g = lane / 4, tq = lane % 4;
     const int NCB = Hd / 8, nrb = (B + 15) / 16, gtiles = nrb * NCB;
     const bool resident = gtiles <= (int)gridDim.x;
     unsigned epoch = 0;
+    // fast attention read-out: one (row, half) item per CTA and HF[b] / half of enc[b] fit the staging buffers
+    // attn_cap: floats in attn_buf (0: not provisioned by the launcher)
+    float* attn_buf = qres + 8 * (Hd + 4);
+    const bool fastA = attn_cap > 0 && 2 * B <= (int)gridDim.x && Tn <= 128 && A % 4 == 0 && A <= 128 && D % 8 == 0 &&
+                       D / 8 <= NTH && NTH % (D / 8) == 0 && Tn * A <= 16 * AS &&
+                       ((Tn + 1) / 2) * (D / 2) <= 16 * AS && Tn * A <= attn_cap &&
+                       ((Tn + 1) / 2) * (D / 2) <= attn_cap;
+    __shared__ __align__(8) uint64_t abar[3];   // bulk-copy completion: [0] bufX (two uses per step), [1] bufY, [2] row tiles
+    uint32_t aph0 = 0, aph1 = 0, lph = 0;
+    if (tid == 0) {
+        mbar_init(&abar[0], 1);
+        mbar_init(&abar[1], 1);
+        mbar_init(&abar[2], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    const int ytiles = nrb * (A / 8);
+    const bool yres = ytiles <= (int)gridDim.x;
+    auto load_q = [&](int nt) {                  // qres[n][k] = q_k[k][8*nt + n]
+        for (int i = tid; i < 8 * Hd; i += NTH) {
+            int k = i / 8, n = i % 8;
+            qres[n * QS_ + k] = p.q_k[(size_t)k * A + 8 * nt + n];
+        }
+    };
+    if (yres && (int)blockIdx.x < ytiles) load_q(blockIdx.x % (A / 8));
 
     auto load_wt = [&](int cb) {
         // Wt[n][k] = W_ch[k][32*cb + n]
@@ -126,60 +221,78 @@ __global__ void __launch_bounds__(NTH, 1) dec_fwd_persist_kernel(e2e_dec_persist
         for (int tile = blockIdx.x; tile < gtiles; tile += gridDim.x) {
             const int rb = tile / NCB, cb = tile % NCB;
             if (!resident) { __syncthreads(); load_wt(cb); }
-            // A tile: [ctx_{t-1} (D) | h_{t-1} (Hd)] for rows rb*16 .. +16
-            for (int i = tid; i < 16 * (K / 4); i += NTH) {
-                int r = i / (K / 4), k = (i % (K / 4)) * 4;
-                int b = rb * 16 + r;
-                const float* src = nullptr;
+            // A tile: [ctx_{t-1} (D) | h_{t-1} (Hd)] for rows rb*16 .. +16: one bulk copy per row segment
+            const int nvalid = min(16, B - rb * 16);
+            if (tid == 0) mbar_expect_tx(&abar[2], (uint32_t)(nvalid * (Hd + (t > 0 ? D : 0)) * 4));
+            __syncwarp();
+            if (lane * 8 + w < 32) {
+                const int slot = lane * 8 + w, r = slot >> 1, part = slot & 1, b = rb * 16 + r;
                 if (b < B) {
-                    if (k < D) {
-                        if (t > 0) src = p.cat + ((size_t)(t - 1) * B + b) * CAT + Hd + k;
+                    if (part == 0) {
+                        if (t > 0) bulk_g2s(a_s + r * AS, p.cat + ((size_t)(t - 1) * B + b) * CAT + Hd, (uint32_t)(D * 4), &abar[2]);
                     } else {
-                        src = p.hprev + ((size_t)t * B + b) * Hd + (k - D);
+                        bulk_g2s(a_s + r * AS + D, p.hprev + ((size_t)t * B + b) * Hd, (uint32_t)(Hd * 4), &abar[2]);
                     }
                 }
-                if (src) cp_async16(a_s + r * AS + k, src);       // L2 -> smem, all requests in flight
-                else *reinterpret_cast<float4*>(a_s + r * AS + k) = make_float4(0.f, 0.f, 0.f, 0.f);
             }
-            cp_async_commit();
-            cp_async_wait_all();
-            __syncthreads();
-            const int nt = w % 4, kh = w / 4;
-            float d[4] = {0.f, 0.f, 0.f, 0.f};
+            if (t == 0 || nvalid < 16) {             // rows / segments no copy fills
+                for (int i = tid; i < 16 * K; i += NTH) {
+                    const int r = i / K, k = i % K;
+                    if (rb * 16 + r >= B || (t == 0 && k < D)) a_s[r * AS + k] = 0.f;
+                }
+            }
+            // epilogue operands of this thread's (row, unit) element, in flight during the product
+            const int prow = tid >> 3, ul = tid & 7;
+            const int eb = rb * 16 + prow, unit = cb * 8 + ul;
+            const bool own = tid < 128 && eb < B;
+            const size_t row = (size_t)t * B + eb;
+            float4 pg = make_float4(0.f, 0.f, 0.f, 0.f);
+            float cp = 0.f;
+            if (own) {
+                pg = __ldg(reinterpret_cast<const float4*>(p.pre_g + row * G4 + unit * 4));
+                cp = __ldcg(p.cprev + row * Hd + unit);
+            }
+            DEC_STAMP(t, 16);
+            mbar_wait_par(&abar[2], lph);
+            lph ^= 1u;
+            if (t == 0 || nvalid < 16) __syncthreads();
+            DEC_STAMP(t, 17);
             {
-                int kmid = (K / 16) * 8;       // split K (multiple of 8) between the two warps of an n-tile
-                mma_block(d, a_s, AS, Wt + (8 * nt) * KS, KS, kh ? kmid : 0, kh ? K : kmid, g, tq);
+                // the 8 warps split K; every warp produces a partial [16 x 32] gate tile
+                float d[4][4];
+                const int ksteps = K / 8, per = (ksteps + 7) / 8;
+                const int k0 = min(ksteps, w * per) * 8, k1 = min(ksteps, (w + 1) * per) * 8;
+                mma_ksplit<4>(d, a_s, AS, Wt, KS, k0, k1, g, tq);
+                float* gw = gred + w * (16 * 40);
+#pragma unroll
+                for (int nt = 0; nt < 4; ++nt) {
+                    *reinterpret_cast<float2*>(gw + g * 40 + 8 * nt + 2 * tq) = make_float2(d[nt][0], d[nt][1]);
+                    *reinterpret_cast<float2*>(gw + (g + 8) * 40 + 8 * nt + 2 * tq) = make_float2(d[nt][2], d[nt][3]);
+                }
             }
-            if (kh == 1) *reinterpret_cast<float4*>(red + (nt * 32 + lane) * 4) = make_float4(d[0], d[1], d[2], d[3]);
+            DEC_STAMP(t, 18);
             __syncthreads();
-            if (kh == 0) {
-                float4 o = *reinterpret_cast<const float4*>(red + (nt * 32 + lane) * 4);
-                d[0] += o.x; d[1] += o.y; d[2] += o.z; d[3] += o.w;
-                const bool even = (tq & 1) == 0;
-                const float s0 = even ? d[2] : d[0], s1 = even ? d[3] : d[1];
-                const float r0 = __shfl_xor_sync(0xffffffffu, s0, 1), r1 = __shfl_xor_sync(0xffffffffu, s1, 1);
-                float z0 = even ? d[0] : r0, z1 = even ? d[1] : r1, z2 = even ? r0 : d[2], z3 = even ? r1 : d[3];
-                const int prow = g + 8 * (tq & 1);
-                const int unit = cb * 8 + 2 * nt + (tq >> 1);
-                const int b = rb * 16 + prow;
-                if (b < B) {
-                    const size_t row = (size_t)t * B + b;
-                    float4 pg = __ldg(reinterpret_cast<const float4*>(p.pre_g + row * G4 + unit * 4));
-                    float si = sigmoidf_acc(z0 + pg.x);
-                    float tj = tanhf(z1 + pg.y);
-                    float sf = sigmoidf_acc(z2 + pg.z + 1.0f);
-                    float so = sigmoidf_acc(z3 + pg.w);
-                    float cp = __ldcg(p.cprev + row * Hd + unit);
-                    float cn = cp * sf + si * tj;
-                    float hn = tanhf(cn) * so;
-                    *reinterpret_cast<float4*>(p.acts + row * G4 + unit * 4) = make_float4(si, tj, sf, so);
-                    p.cat[row * CAT + unit] = cn;
-                    if (t + 1 < U) {      // committed state: finished rows keep (c, h)  (raw_rnn)
-                        const bool live = t < p.lens[b];
-                        float hp = a_s[prow * AS + D + unit];
-                        p.cprev[(row + B) * Hd + unit] = live ? cn : cp;
-                        p.hprev[(row + B) * Hd + unit] = live ? hn : hp;
-                    }
+            DEC_STAMP(t, 19);
+            if (own) {
+                float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+                for (int ww = 0; ww < 8; ++ww) {
+                    const float4 o = *reinterpret_cast<const float4*>(gred + ww * (16 * 40) + prow * 40 + 4 * ul);
+                    z.x += o.x; z.y += o.y; z.z += o.z; z.w += o.w;
+                }
+                const float si = sigmoid_fast(z.x + pg.x);
+                const float tj = tanh_fast(z.y + pg.y);
+                const float sf = sigmoid_fast(z.z + pg.z + 1.0f);
+                const float so = sigmoid_fast(z.w + pg.w);
+                const float cn = cp * sf + si * tj;
+                const float hn = tanh_fast(cn) * so;
+                *reinterpret_cast<float4*>(p.acts + row * G4 + unit * 4) = make_float4(si, tj, sf, so);
+                p.cat[row * CAT + unit] = cn;
+                if (t + 1 < U) {      // committed state: finished rows keep (c, h)  (raw_rnn)
+                    const bool live = t < p.lens[eb];
+                    const float hp = a_s[prow * AS + D + unit];
+                    p.cprev[(row + B) * Hd + unit] = live ? cn : cp;
+                    p.hprev[(row + B) * Hd + unit] = live ? hn : hp;
                 }
             }
             __syncthreads();
@@ -189,36 +302,36 @@ __global__ void __launch_bounds__(NTH, 1) dec_fwd_persist_kernel(e2e_dec_persist
         DEC_STAMP(t, 2);
         // ------------------------------------------------------------ phase Y: y = c_new . q_k + q_b
         {
-            const int ytiles = nrb * (A / 8);
             float* c_s = a_s;                       // [16][Hd+4]
-            float* q_s = a_s + 16 * (Hd + 4);       // [8][Hd+8]   q_s[n][k] = q_k[k][8*nt + n]
-            const int CS_ = Hd + 4, QS_ = Hd + 8;
+            const int CS_ = Hd + 4;
             for (int tile = blockIdx.x; tile < ytiles; tile += gridDim.x) {
                 const int rb = tile / (A / 8), nt = tile % (A / 8);
+                const int nvalid = min(16, B - rb * 16);
                 __syncthreads();
-                for (int i = tid; i < 16 * (Hd / 4); i += NTH) {
-                    int r = i / (Hd / 4), k = (i % (Hd / 4)) * 4;
-                    int b = rb * 16 + r;
-                    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (b < B) v = __ldcg(reinterpret_cast<const float4*>(p.cat + ((size_t)t * B + b) * CAT + k));
-                    *reinterpret_cast<float4*>(c_s + r * CS_ + k) = v;
+                if (tid == 0) mbar_expect_tx(&abar[2], (uint32_t)(nvalid * Hd * 4));
+                __syncwarp();
+                if (lane * 8 + w < nvalid) {
+                    const int r = lane * 8 + w;
+                    bulk_g2s(c_s + r * CS_, p.cat + ((size_t)t * B + rb * 16 + r) * CAT, (uint32_t)(Hd * 4), &abar[2]);
                 }
-                for (int i = tid; i < 8 * Hd; i += NTH) {
-                    int k = i / 8, n = i % 8;
-                    q_s[n * QS_ + k] = p.q_k[(size_t)k * A + 8 * nt + n];
-                }
-                __syncthreads();
+                if (nvalid < 16)
+                    for (int i = tid; i < 16 * Hd; i += NTH)
+                        if (i / Hd >= nvalid) c_s[(i / Hd) * CS_ + i % Hd] = 0.f;
+                if (!yres) load_q(nt);
+                mbar_wait_par(&abar[2], lph);
+                lph ^= 1u;
+                if (nvalid < 16 || !yres) __syncthreads();
                 // 8 warps split K
                 const int ksteps = Hd / 8, per = (ksteps + 7) / 8;
                 const int k0 = min(ksteps, w * per) * 8, k1 = min(ksteps, (w + 1) * per) * 8;
                 float d[4] = {0.f, 0.f, 0.f, 0.f};
-                mma_block(d, c_s, CS_, q_s, QS_, k0, k1, g, tq);
-                __syncthreads();
+                mma_block(d, c_s, CS_, qres, QS_, k0, k1, g, tq);
                 float* part = red;                  // [8 warps][32 lanes][4]
                 *reinterpret_cast<float4*>(part + (w * 32 + lane) * 4) = make_float4(d[0], d[1], d[2], d[3]);
                 __syncthreads();
                 if (w == 0) {
                     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
                     for (int ww = 0; ww < 8; ++ww) {
                         float4 o = *reinterpret_cast<const float4*>(part + (ww * 32 + lane) * 4);
                         acc.x += o.x; acc.y += o.y; acc.z += o.z; acc.w += o.w;
@@ -235,6 +348,149 @@ __global__ void __launch_bounds__(NTH, 1) dec_fwd_persist_kernel(e2e_dec_persist
         grid_barrier(p.ctr, epoch, p.err);
         DEC_STAMP(t, 4);
         // ------------------------------------------------------------ phase A: attention read-out
+        if (fastA) {
+          if ((int)blockIdx.x < 2 * B) {
+            // CTA = (row b, half of D), fixed for the whole sequence.  HF[b] and the CTA's half of enc[b] are
+            // streamed L2 -> shared memory by bulk copies (mbarrier completion) in three transfers:
+            // HF + y -> bufX | enc rows [0,TC) -> bufY | enc rows [TC,len) -> bufX once the scores are done.
+            const int b = blockIdx.x / 2, half = blockIdx.x % 2;
+            const int len = min(p.enc_len[b], Tn);
+            const int dh = D / 2, TC = (Tn + 1) / 2;
+            float* bufX = a_s;
+            float* bufY = attn_buf;
+            float* y_s = attn_buf + attn_cap;       // [A]
+            float* v_s = y_s + A;                   // [A]
+            float* s_s = v_s + A;                   // [Tn + pad]
+            float* part_s = bufX;                   // [4][dh] partial read-outs (bufX is free again by then)
+            const float* HFb = p.HF + (size_t)b * Tp * A;
+            const float* encb = p.enc + (size_t)b * Tp * D + half * dh;
+            const int c0 = min(TC, len), c1 = max(len - TC, 0);
+            if (tid == 0) {
+                mbar_expect_tx(&abar[0], (uint32_t)((len + 1) * A * 4));
+                bulk_g2s(bufX, HFb, (uint32_t)(len * A * 4), &abar[0]);
+                bulk_g2s(y_s, p.y + ((size_t)t * B + b) * A, (uint32_t)(A * 4), &abar[0]);
+                mbar_expect_tx(&abar[1], (uint32_t)(c0 * dh * 4));
+            }
+            __syncwarp();
+            // one bulk copy per enc row (dh floats), spread over the lanes of all warps
+            // (a lane issues its copies serially, ~100 cycles each: slot = lane*8 + warp keeps that to a few per warp)
+            for (int r = lane * 8 + w; r < c0; r += NTH) bulk_g2s(bufY + r * dh, encb + (size_t)r * D, (uint32_t)(dh * 4), &abar[1]);
+            if (t == 0) for (int a = tid; a < A; a += NTH) v_s[a] = p.attn_v[a];
+            DEC_STAMP(t, 8);
+            mbar_wait_par(&abar[0], aph0);
+            aph0 ^= 1u;
+            if (t == 0) __syncthreads();
+            DEC_STAMP(t, 9);
+            // scores: 8 lanes per tau (4 taus per warp pass), lane covers float4 columns sub, sub+8, ...
+            {
+                const int sub = lane & 7, tl = lane >> 3, nq = A / 4;
+                float4 yy[4], vv[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int q = sub + 8 * j;
+                    yy[j] = q < nq ? *reinterpret_cast<const float4*>(y_s + q * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    vv[j] = q < nq ? *reinterpret_cast<const float4*>(v_s + q * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+                for (int tau0 = 4 * w; tau0 < len; tau0 += 32) {
+                    const int tau = tau0 + tl;
+                    float acc = 0.f;
+                    if (tau < len) {
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            const int q = sub + 8 * j;
+                            if (q < nq) {
+                                const float4 hf = *reinterpret_cast<const float4*>(bufX + tau * A + q * 4);
+                                acc += vv[j].x * tanh_fast(hf.x + yy[j].x) + vv[j].y * tanh_fast(hf.y + yy[j].y) +
+                                       vv[j].z * tanh_fast(hf.z + yy[j].z) + vv[j].w * tanh_fast(hf.w + yy[j].w);
+                            }
+                        }
+                    }
+                    acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+                    acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+                    acc += __shfl_xor_sync(0xffffffffu, acc, 4);
+                    if (sub == 0 && tau < len) s_s[tau] = acc;
+                }
+            }
+            __syncthreads();
+            DEC_STAMP(t, 10);
+            // bufX (HF) is free: the second half of the enc rows goes there while the softmax runs
+            if (tid == 0) mbar_expect_tx(&abar[0], (uint32_t)(c1 * dh * 4));
+            __syncwarp();
+            if (c1 > 0)
+                for (int r = lane * 8 + w; r < c1; r += NTH)
+                    bulk_g2s(bufX + r * dh, encb + (size_t)(TC + r) * D, (uint32_t)(dh * 4), &abar[0]);
+            // masked softmax over tau by warp 0 (Tn <= 128: at most 4 values per lane)
+            if (w == 0) {
+                float sv[4], mx = -INFINITY;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int tau = lane + 32 * j;
+                    sv[j] = tau < len ? s_s[tau] : -INFINITY;
+                    mx = fmaxf(mx, sv[j]);
+                }
+                mx = warp_max(mx);
+                float sum = 0.f;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    sv[j] = lane + 32 * j < len ? __expf(sv[j] - mx) : 0.f;
+                    sum += sv[j];
+                }
+                sum = warp_sum(sum);
+                const float inv = 1.0f / sum;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int tau = lane + 32 * j;
+                    if (tau < Tn) {
+                        const float al = sv[j] * inv;
+                        s_s[tau] = al;
+                        if (half == 0) p.alpha[((size_t)t * B + b) * Tn + tau] = al;
+                    }
+                }
+            }
+            __syncthreads();
+            DEC_STAMP(t, 11);
+            // read-out: thread = (float4 column cq, tau group tg); 4 tau groups when dh <= 256
+            const int ncq = dh / 4;                              // float4 columns of the half
+            const int ntg = min(NTH / ncq, 4);                   // tau groups (ncq <= NTH guaranteed by fastA)
+            const int cq = tid % ncq, tg = tid / ncq;
+            float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+            mbar_wait_par(&abar[1], aph1);
+            aph1 ^= 1u;
+            DEC_STAMP(t, 12);
+            if (tg < ntg) {
+#pragma unroll 4
+                for (int tau = tg; tau < c0; tau += ntg) {
+                    const float al = s_s[tau];
+                    const float4 e = *reinterpret_cast<const float4*>(bufY + tau * dh + cq * 4);
+                    acc.x = fmaf(al, e.x, acc.x); acc.y = fmaf(al, e.y, acc.y);
+                    acc.z = fmaf(al, e.z, acc.z); acc.w = fmaf(al, e.w, acc.w);
+                }
+            }
+            DEC_STAMP(t, 13);
+            mbar_wait_par(&abar[0], aph0);
+            aph0 ^= 1u;
+            DEC_STAMP(t, 14);
+            if (tg < ntg) {
+#pragma unroll 4
+                for (int tau = tg; tau < c1; tau += ntg) {
+                    const float al = s_s[TC + tau];
+                    const float4 e = *reinterpret_cast<const float4*>(bufX + tau * dh + cq * 4);
+                    acc.x = fmaf(al, e.x, acc.x); acc.y = fmaf(al, e.y, acc.y);
+                    acc.z = fmaf(al, e.z, acc.z); acc.w = fmaf(al, e.w, acc.w);
+                }
+            }
+            __syncthreads();                         // every thread is done with bufX
+            if (tg < ntg) *reinterpret_cast<float4*>(part_s + tg * dh + cq * 4) = acc;
+            __syncthreads();
+            for (int dd = tid; dd < dh; dd += NTH) {
+                float c = 0.f;
+                for (int j = 0; j < ntg; ++j) c += part_s[j * dh + dd];
+                p.cat[((size_t)t * B + b) * CAT + Hd + half * dh + dd] = c;
+            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            __syncthreads();                         // bufX = a_s is the next step's A tile
+          }
+        } else
         {
             float* y_s = a_s;                       // [A]
             float* v_s = a_s + A;                   // [A]
@@ -334,6 +590,7 @@ __global__ void __launch_bounds__(NTH, 1) dec_fwd_persist_kernel(e2e_dec_persist
         DEC_STAMP(t, 5);
         grid_barrier(p.ctr, epoch, p.err);
         DEC_STAMP(t, 6);
+        if (dbg) dbg[t * 32 + 7] = fastA ? 1 : 0;
     }
 }
 
@@ -343,11 +600,16 @@ __global__ void __launch_bounds__(NTH, 1) dec_bwd_persist_kernel(e2e_dec_persist
     const int B = p.B, U = p.U, Hd = p.Hd, A = p.A, D = p.D, Tn = p.Tn, Tp = p.Tp;
     const int K = D + Hd, G4 = 4 * Hd, CAT = Hd + D;
     const int NX = 24;                          // output columns of [dctx|dh] per CTA tile (3 n-tiles)
-    const int WS = G4 + 8;                      // Wt2 row stride
+    const int WS = G4 + 4;                      // Wt2 row stride (== 4 mod 32: conflict-free fragment loads)
     const int ZS = G4 + 4;                      // dz tile row stride
-    float* Wt2 = smem;                          // [NX][WS]  rows of W_ch owned by this CTA (phase X)
-    float* z_s = Wt2 + NX * WS;                 // [16][ZS]  dz tile / scratch of the other phases
+    const int QS_ = A + 4;                      // q_s row stride
+    float* Wt2 = smem;                          // [NX][G4+8] rows of W_ch owned by this CTA (phase X)
+    float* z_s = Wt2 + NX * (G4 + 8);           // [16][ZS]  dz tile / scratch of the other phases
     float* red = z_s + 16 * ZS;                 // [8][32][4]
+    float* xred = red + 8 * 32 * 4;             // [8][16][40] per-warp partial tiles of phase X
+    float* pres = xred + 8 * 16 * 40;           // [8][A+4]  resident q_k slice of this CTA's phase-P tile
+    __shared__ __align__(8) uint64_t lbar;      // bulk-copy completion of the row tiles
+    uint32_t lph = 0;
     const int tid = threadIdx.x, w = tid / 32, lane = tid % 32, g = lane / 4, tq = lane % 4;
     const int nrb = (B + 15) / 16;
     const int NXB = (K + NX - 1) / NX, xtiles = nrb * NXB;
@@ -364,6 +626,19 @@ __global__ void __launch_bounds__(NTH, 1) dec_bwd_persist_kernel(e2e_dec_persist
         }
     };
     if (resident && (int)blockIdx.x < xtiles) load_wt2(blockIdx.x % NXB);
+    const int NCBp = Hd / 8, ptiles = nrb * NCBp;
+    const bool pres_ok = ptiles <= (int)gridDim.x;
+    auto load_qp = [&](int cb) {                 // pres[n][k] = q_k[8*cb + n][k]
+        for (int i = tid; i < 8 * A; i += NTH) {
+            int n = i / A, k = i % A;
+            pres[n * QS_ + k] = p.q_k[(size_t)(8 * cb + n) * A + k];
+        }
+    };
+    if (pres_ok && (int)blockIdx.x < ptiles) load_qp(blockIdx.x % NCBp);
+    if (tid == 0) {
+        mbar_init(&lbar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
     __syncthreads();
 
     long long* dbg = (blockIdx.x == 0 && threadIdx.x == 0) ? d_dec_dbg : nullptr;
@@ -433,59 +708,68 @@ __global__ void __launch_bounds__(NTH, 1) dec_bwd_persist_kernel(e2e_dec_persist
         DEC_STAMP(t, 2);
         // ------------------------------------------------------------ phase P: dc_new += dy . q_k^T ; pointwise backward
         {
-            const int NCB = Hd / 8, ptiles = nrb * NCB;
             float* dy_s = z_s;                       // [16][A+4]
-            float* q_s = z_s + 16 * (A + 4);         // [8][A+8]   q_s[n][k] = q_k[8*cb + n][k]
-            const int DS_ = A + 4, QS_ = A + 8;
+            const int DS_ = A + 4;
             for (int tile = blockIdx.x; tile < ptiles; tile += gridDim.x) {
-                const int rb = tile / NCB, cb = tile % NCB;
+                const int rb = tile / NCBp, cb = tile % NCBp;
+                const int nvalid = min(16, B - rb * 16);
                 __syncthreads();
-                for (int i = tid; i < 16 * (A / 4); i += NTH) {
-                    int r = i / (A / 4), k = (i % (A / 4)) * 4;
-                    int b = rb * 16 + r;
-                    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (b < B) v = __ldcg(reinterpret_cast<const float4*>(p.dy + ((size_t)t * B + b) * A + k));
-                    *reinterpret_cast<float4*>(dy_s + r * DS_ + k) = v;
+                if (tid == 0) mbar_expect_tx(&lbar, (uint32_t)(nvalid * A * 4));
+                __syncwarp();
+                if (lane * 8 + w < nvalid) {
+                    const int r = lane * 8 + w;
+                    bulk_g2s(dy_s + r * DS_, p.dy + ((size_t)t * B + rb * 16 + r) * A, (uint32_t)(A * 4), &lbar);
                 }
-                for (int i = tid; i < 8 * A; i += NTH) {
-                    int n = i / A, k = i % A;
-                    q_s[n * QS_ + k] = p.q_k[(size_t)(8 * cb + n) * A + k];
+                if (nvalid < 16)
+                    for (int i = tid; i < 16 * A; i += NTH)
+                        if (i / A >= nvalid) dy_s[(i / A) * DS_ + i % A] = 0.f;
+                if (!pres_ok) load_qp(cb);
+                // operands of this thread's (row, unit) element: in flight during the product
+                const int prow = tid / 8, ul = tid % 8;
+                const int eb = rb * 16 + prow, unit = cb * 8 + ul;
+                const bool own = tid < 128 && eb < B;
+                const size_t row = (size_t)t * B + eb;
+                const bool live = own && t < p.lens[eb];
+                float4 act = make_float4(0.f, 0.f, 0.f, 0.f);
+                float cnew = 0.f, dhn = 0.f, dcin = 0.f, carry = 0.f, cpv = 0.f;
+                if (live) {
+                    act = *reinterpret_cast<const float4*>(p.acts + row * G4 + unit * 4);
+                    cnew = p.cat[row * CAT + unit];
+                    dhn = (t + 1 < U) ? __ldcg(p.dch + (row + B) * K + D + unit) : 0.f;
+                    dcin = __ldcg(p.dcat + row * CAT + unit);
+                    carry = p.dc_carry[(size_t)eb * Hd + unit];
+                    cpv = p.cprev[row * Hd + unit];
                 }
-                __syncthreads();
+                mbar_wait_par(&lbar, lph);
+                lph ^= 1u;
+                if (nvalid < 16 || !pres_ok) __syncthreads();
                 const int ksteps = A / 8, per = (ksteps + 7) / 8;
                 const int k0 = min(ksteps, w * per) * 8, k1 = min(ksteps, (w + 1) * per) * 8;
                 float d[4] = {0.f, 0.f, 0.f, 0.f};
-                mma_block(d, dy_s, DS_, q_s, QS_, k0, k1, g, tq);
+                mma_block(d, dy_s, DS_, pres, QS_, k0, k1, g, tq);
                 *reinterpret_cast<float4*>(red + (w * 32 + lane) * 4) = make_float4(d[0], d[1], d[2], d[3]);
                 __syncthreads();
                 // 16 rows x 8 units = 128 (row, unit) elements: thread tid < 128
-                if (tid < 128) {
-                    const int prow = tid / 8, ul = tid % 8;
+                if (own) {
                     // fragment element (prow, ul): lane = (prow % 8) * 4 + ul / 2, reg = (prow / 8) * 2 + ul % 2
                     const int fl = (prow % 8) * 4 + ul / 2, fr = (prow / 8) * 2 + (ul % 2);
                     float dcq = 0.f;
+#pragma unroll
                     for (int ww = 0; ww < 8; ++ww) dcq += red[(ww * 32 + fl) * 4 + fr];
-                    const int b = rb * 16 + prow, unit = cb * 8 + ul;
-                    if (b < B) {
-                        const size_t row = (size_t)t * B + b;
-                        float4 dz = make_float4(0.f, 0.f, 0.f, 0.f);
-                        float dcc = 0.f;
-                        if (t < p.lens[b]) {
-                            float4 act = *reinterpret_cast<const float4*>(p.acts + row * G4 + unit * 4);
-                            float si = act.x, tj = act.y, sf = act.z, so = act.w;
-                            float tc = tanhf(p.cat[row * CAT + unit]);
-                            float dh = (t + 1 < U) ? __ldcg(p.dch + (row + B) * K + D + unit) : 0.f;
-                            float dc = __ldcg(p.dcat + row * CAT + unit) + dcq + p.dc_carry[(size_t)b * Hd + unit] +
-                                       dh * so * (1.f - tc * tc);
-                            dz.x = dc * tj * si * (1.f - si);
-                            dz.y = dc * si * (1.f - tj * tj);
-                            dz.z = dc * p.cprev[row * Hd + unit] * sf * (1.f - sf);
-                            dz.w = dh * tc * so * (1.f - so);
-                            dcc = dc * sf;
-                        }
-                        p.dc_carry[(size_t)b * Hd + unit] = dcc;
-                        *reinterpret_cast<float4*>(p.dz + row * G4 + unit * 4) = dz;
+                    float4 dz = make_float4(0.f, 0.f, 0.f, 0.f);
+                    float dcc = 0.f;
+                    if (live) {
+                        const float si = act.x, tj = act.y, sf = act.z, so = act.w;
+                        const float tc = tanh_fast(cnew);
+                        const float dc = dcin + dcq + carry + dhn * so * (1.f - tc * tc);
+                        dz.x = dc * tj * si * (1.f - si);
+                        dz.y = dc * si * (1.f - tj * tj);
+                        dz.z = dc * cpv * sf * (1.f - sf);
+                        dz.w = dhn * tc * so * (1.f - so);
+                        dcc = dc * sf;
                     }
+                    p.dc_carry[(size_t)eb * Hd + unit] = dcc;
+                    *reinterpret_cast<float4*>(p.dz + row * G4 + unit * 4) = dz;
                 }
             }
         }
@@ -495,38 +779,46 @@ __global__ void __launch_bounds__(NTH, 1) dec_bwd_persist_kernel(e2e_dec_persist
         // ------------------------------------------------------------ phase X: [dctx_{t-1} | dh_{t-1}] = dz_t . W_ch^T
         for (int tile = blockIdx.x; tile < xtiles; tile += gridDim.x) {
             const int rb = tile / NXB, xb = tile % NXB;
+            const int nvalid = min(16, B - rb * 16);
             __syncthreads();
             if (!resident) load_wt2(xb);
-            for (int i = tid; i < 16 * (G4 / 4); i += NTH) {
-                int r = i / (G4 / 4), k = (i % (G4 / 4)) * 4;
-                int b = rb * 16 + r;
-                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (b < B) v = __ldcg(reinterpret_cast<const float4*>(p.dz + ((size_t)t * B + b) * G4 + k));
-                *reinterpret_cast<float4*>(z_s + r * ZS + k) = v;
+            if (tid == 0) mbar_expect_tx(&lbar, (uint32_t)(nvalid * G4 * 4));
+            __syncwarp();
+            if (lane * 8 + w < nvalid) {
+                const int r = lane * 8 + w;
+                bulk_g2s(z_s + r * ZS, p.dz + ((size_t)t * B + rb * 16 + r) * G4, (uint32_t)(G4 * 4), &lbar);
             }
-            __syncthreads();
-            // 3 n-tiles x K split over warps: warp w -> n-tile w % 3 (warps 0..5), k-half w / 3; warps 6,7 idle
-            float d[4] = {0.f, 0.f, 0.f, 0.f};
-            const int nt = w % 3, kh = w / 3;
-            if (w < 6) {
-                int kmid = (G4 / 16) * 8;
-                mma_block(d, z_s, ZS, Wt2 + (8 * nt) * WS, WS, kh ? kmid : 0, kh ? G4 : kmid, g, tq);
-                if (kh == 1) *reinterpret_cast<float4*>(red + (nt * 32 + lane) * 4) = make_float4(d[0], d[1], d[2], d[3]);
-            }
-            __syncthreads();
-            if (w < 3) {
-                float4 o = *reinterpret_cast<const float4*>(red + (nt * 32 + lane) * 4);
-                d[0] += o.x; d[1] += o.y; d[2] += o.z; d[3] += o.w;
+            if (nvalid < 16)
+                for (int i = tid; i < 16 * G4; i += NTH)
+                    if (i / G4 >= nvalid) z_s[(i / G4) * ZS + i % G4] = 0.f;
+            mbar_wait_par(&lbar, lph);
+            lph ^= 1u;
+            if (nvalid < 16 || !resident) __syncthreads();
+            {
+                // the 8 warps split K = 4 Hd; every warp produces a partial [16 x 24] tile (3 n-tiles)
+                float d[3][4];
+                const int ksteps = G4 / 8, per = (ksteps + 7) / 8;
+                const int k0 = min(ksteps, w * per) * 8, k1 = min(ksteps, (w + 1) * per) * 8;
+                mma_ksplit<3>(d, z_s, ZS, Wt2, WS, k0, k1, g, tq);
+                float* xw = xred + w * (16 * 40);
 #pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                    const int r = g + 8 * (e / 2), col = xb * NX + 8 * nt + 2 * tq + (e % 2);
-                    const int b = rb * 16 + r;
-                    if (b < B && col < K) {
-                        const size_t row = (size_t)t * B + b;
-                        p.dch[row * K + col] = d[e];
-                        // dctx_{t-1} joins the AttnProjection part already in dcat[t-1]
-                        if (col < D && t > 0) p.dcat[(row - B) * CAT + Hd + col] += d[e];
-                    }
+                for (int nt = 0; nt < 3; ++nt) {
+                    *reinterpret_cast<float2*>(xw + g * 40 + 8 * nt + 2 * tq) = make_float2(d[nt][0], d[nt][1]);
+                    *reinterpret_cast<float2*>(xw + (g + 8) * 40 + 8 * nt + 2 * tq) = make_float2(d[nt][2], d[nt][3]);
+                }
+            }
+            __syncthreads();
+            for (int idx = tid; idx < 16 * NX; idx += NTH) {
+                const int r = idx / NX, c = idx % NX;
+                const int b = rb * 16 + r, col = xb * NX + c;
+                if (b < B && col < K) {
+                    float v = 0.f;
+#pragma unroll
+                    for (int ww = 0; ww < 8; ++ww) v += xred[ww * (16 * 40) + r * 40 + c];
+                    const size_t row = (size_t)t * B + b;
+                    p.dch[row * K + col] = v;
+                    // dctx_{t-1} joins the AttnProjection part already in dcat[t-1]
+                    if (col < D && t > 0) p.dcat[(row - B) * CAT + Hd + col] += v;
                 }
             }
         }
@@ -577,16 +869,31 @@ __global__ void __launch_bounds__(128) dec_dhf_kernel(e2e_dec_persist_args p, fl
     }
 }
 
+// floats before attn_buf: Wt | a_s | red | gred | qres
+static size_t fwd_base_floats(const e2e_dec_persist_args& p) {
+    int K = p.D + p.Hd;
+    return (size_t)32 * (K + 8) + 16 * (K + 4) + 8 * 32 * 4 + 8 * 16 * 40 + 8 * (p.Hd + 4);
+}
 static size_t fwd_smem_bytes(const e2e_dec_persist_args& p) {
     int K = p.D + p.Hd;
-    size_t g = (size_t)32 * (K + 8) + 16 * (K + 4) + 8 * 32 * 4;
-    size_t yph = (size_t)32 * (K + 8) + 16 * (p.Hd + 4) + 8 * (p.Hd + 8) + 8 * 32 * 4;
-    size_t aph = (size_t)32 * (K + 8) + 2 * p.A + p.Tn + 16;
-    return sizeof(float) * (max(g, max(yph, aph)) + 64);
+    size_t aph = (size_t)32 * (K + 8) + 2 * p.A + p.Tn + 16;      // streaming attention fallback scratch (in a_s)
+    return sizeof(float) * (max(fwd_base_floats(p), aph) + 64);
+}
+// staging buffer (floats) of the fast attention read-out, 0 when the shapes do not qualify
+static int fwd_attn_cap(const e2e_dec_persist_args& p, size_t* smem) {
+    int K = p.D + p.Hd;
+    if (p.Tn > 128 || p.A > 128 || p.D / 8 > NTH || NTH % (p.D / 8) != 0) return 0;
+    int cap = max(p.Tn * p.A, ((p.Tn + 1) / 2) * (p.D / 2));
+    cap = (cap + 3) / 4 * 4;
+    if (cap > 16 * (K + 4)) return 0;
+    size_t total = sizeof(float) * (fwd_base_floats(p) + cap + 2 * p.A + p.Tn + 64);
+    if (total > 227 * 1024) return 0;
+    *smem = max(*smem, total);
+    return cap;
 }
 static size_t bwd_smem_bytes(const e2e_dec_persist_args& p) {
     int G4 = 4 * p.Hd;
-    size_t x = (size_t)24 * (G4 + 8) + 16 * (G4 + 4) + 8 * 32 * 4;
+    size_t x = (size_t)24 * (G4 + 8) + 16 * (G4 + 4) + 8 * 32 * 4 + 8 * 16 * 40 + 8 * (p.A + 4);
     size_t a = (size_t)24 * (G4 + 8) + 2 * p.A + p.D + p.Tn + 8 * p.A + 16;
     size_t pp = (size_t)24 * (G4 + 8) + 16 * (p.A + 4) + 8 * (p.A + 8) + 16 * (G4 + 4) + 8 * 32 * 4;
     return sizeof(float) * (max(x, max(a, pp)) + 64);
@@ -616,7 +923,9 @@ int dec_persist(cudaStream_t st, bool bwd, const e2e_dec_persist_args* a, float*
             E2E_CHECK_CUDA(cudaMemcpyToSymbolAsync(d_dec_dbg, &last_dbg, sizeof(last_dbg), 0, cudaMemcpyHostToDevice, st));
         }
     }
-    void* args[] = {&p};
+    int attn_cap = bwd ? 0 : fwd_attn_cap(p, &smem);
+    E2E_CHECK_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    void* args[] = {&p, &attn_cap};
     E2E_CHECK_CUDA(cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(NTH), args, smem, st));
     ++g_launches;
     if (bwd) {
