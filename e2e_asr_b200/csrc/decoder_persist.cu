@@ -595,7 +595,7 @@ __global__ void __launch_bounds__(NTH, 1) dec_fwd_persist_kernel(e2e_dec_persist
 }
 
 // ======================================================================= backward
-__global__ void __launch_bounds__(NTH, 1) dec_bwd_persist_kernel(e2e_dec_persist_args p) {
+__global__ void __launch_bounds__(NTH, 1) dec_bwd_persist_kernel(e2e_dec_persist_args p, int attn_fast) {
     extern __shared__ __align__(16) float smem[];
     const int B = p.B, U = p.U, Hd = p.Hd, A = p.A, D = p.D, Tn = p.Tn, Tp = p.Tp;
     const int K = D + Hd, G4 = 4 * Hd, CAT = Hd + D;
@@ -608,8 +608,16 @@ __global__ void __launch_bounds__(NTH, 1) dec_bwd_persist_kernel(e2e_dec_persist
     float* red = z_s + 16 * ZS;                 // [8][32][4]
     float* xred = red + 8 * 32 * 4;             // [8][16][40] per-warp partial tiles of phase X
     float* pres = xred + 8 * 16 * 40;           // [8][A+4]  resident q_k slice of this CTA's phase-P tile
+    float* abuf = pres + 8 * (A + 4);           // fast attention backward: HF rows, y, v, dctx, alpha, ...
     __shared__ __align__(8) uint64_t lbar;      // bulk-copy completion of the row tiles
-    uint32_t lph = 0;
+    __shared__ __align__(8) uint64_t ebar, hbar;  // ... of the enc rows + dctx / of the HF rows + y
+    uint32_t lph = 0, eph = 0, hph = 0;
+    // fast attention backward: CTA = (row b, half of the TIME axis); the two halves leave partial sums
+    // S1_a = sum_tau alpha dalpha (1 - th^2), S2_a = sum_tau alpha (1 - th^2), dot = sum_tau alpha dalpha in an L2
+    // scratch; phase P combines them:  dy_a = v_a (S1_a - dot S2_a)   (softmax backward folded in)
+    const bool fastAp = attn_fast != 0 && 2 * B <= (int)gridDim.x;
+    float* apart = reinterpret_cast<float*>(p.ctr) + 64;          // [B][2][2A+4]
+    float* adots = apart + (size_t)B * 2 * (2 * A + 4);           // [U][B][2]
     const int tid = threadIdx.x, w = tid / 32, lane = tid % 32, g = lane / 4, tq = lane % 4;
     const int nrb = (B + 15) / 16;
     const int NXB = (K + NX - 1) / NX, xtiles = nrb * NXB;
@@ -637,6 +645,8 @@ __global__ void __launch_bounds__(NTH, 1) dec_bwd_persist_kernel(e2e_dec_persist
     if (pres_ok && (int)blockIdx.x < ptiles) load_qp(blockIdx.x % NCBp);
     if (tid == 0) {
         mbar_init(&lbar, 1);
+        mbar_init(&ebar, 1);
+        mbar_init(&hbar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
@@ -644,8 +654,108 @@ __global__ void __launch_bounds__(NTH, 1) dec_bwd_persist_kernel(e2e_dec_persist
     long long* dbg = (blockIdx.x == 0 && threadIdx.x == 0) ? d_dec_dbg : nullptr;
     for (int t = U - 1; t >= 0; --t) {
         DEC_STAMP(t, 0);
-        // ------------------------------------------------------------ phase A': attention backward (CTA per row)
-        {
+        // ------------------------------------------------------------ phase A': attention backward
+        if (fastAp) {
+          if ((int)blockIdx.x < 2 * B) {
+            const int b = blockIdx.x / 2, half = blockIdx.x % 2;
+            const int len = min(p.enc_len[b], Tn);
+            const int TC = (Tn + 1) / 2, TCp = (TC + 3) & ~3, tau0 = half * TC;
+            const int n = max(0, min(len - tau0, TC));
+            const size_t row = (size_t)t * B + b;
+            float* encbuf = z_s;                    // [TC][D] (spans z_s | red | xred)
+            float* hfbuf = abuf;                    // [TC][A]
+            float* y_s = hfbuf + TCp * A;           // [A]
+            float* v_s = y_s + A;                   // [A]
+            float* dctx_s = v_s + A;                // [D]
+            float* al_s = dctx_s + D;               // [TCp] alpha
+            float* w_s = al_s + TCp;                // [TCp] alpha * dalpha
+            float* dal_s = w_s + TCp;               // [TCp] dalpha
+            float* sred = dal_s + TCp;              // [4][2A] + [4]
+            if (tid == 0) {
+                mbar_expect_tx(&ebar, (uint32_t)((n + 1) * D * 4));
+                if (n > 0) bulk_g2s(encbuf, p.enc + ((size_t)b * Tp + tau0) * D, (uint32_t)(n * D * 4), &ebar);
+                bulk_g2s(dctx_s, p.dcat + row * CAT + Hd, (uint32_t)(D * 4), &ebar);
+            }
+            if (tid == 32) {
+                mbar_expect_tx(&hbar, (uint32_t)((n + 1) * A * 4));
+                if (n > 0) bulk_g2s(hfbuf, p.HF + ((size_t)b * Tp + tau0) * A, (uint32_t)(n * A * 4), &hbar);
+                bulk_g2s(y_s, p.y + row * A, (uint32_t)(A * 4), &hbar);
+            }
+            if (tid >= 64 && tid - 64 < n) al_s[tid - 64] = p.alpha[row * Tn + tau0 + tid - 64];
+            if (t == U - 1) for (int a = tid; a < A; a += NTH) v_s[a] = p.attn_v[a];
+            mbar_wait_par(&ebar, eph);
+            eph ^= 1u;
+            // dalpha_tau = dctx . enc[tau]: 8 lanes per tau, 4 taus per warp pass
+            {
+                const int sub = lane & 7, tl = lane >> 3, nq = D / 4;
+                for (int tb = 4 * w; tb < n; tb += 32) {
+                    const int tau = tb + tl;
+                    float acc = 0.f;
+                    if (tau < n) {
+                        const float* er = encbuf + (size_t)tau * D;
+#pragma unroll 4
+                        for (int q = sub; q < nq; q += 8) {
+                            const float4 e = *reinterpret_cast<const float4*>(er + q * 4);
+                            const float4 dc = *reinterpret_cast<const float4*>(dctx_s + q * 4);
+                            acc = fmaf(dc.x, e.x, acc); acc = fmaf(dc.y, e.y, acc);
+                            acc = fmaf(dc.z, e.z, acc); acc = fmaf(dc.w, e.w, acc);
+                        }
+                    }
+                    acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+                    acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+                    acc += __shfl_xor_sync(0xffffffffu, acc, 4);
+                    if (sub == 0 && tau < n) dal_s[tau] = acc;
+                }
+            }
+            __syncthreads();
+            if (w == 0) {
+                float part = 0.f;
+                for (int tl = lane; tl < n; tl += 32) {
+                    const float wv = al_s[tl] * dal_s[tl];
+                    w_s[tl] = wv;
+                    part += wv;
+                }
+                part = warp_sum(part);
+                if (lane == 0) sred[8 * A] = part;
+            }
+            mbar_wait_par(&hbar, hph);
+            hph ^= 1u;
+            __syncthreads();
+            {
+                const int nsub = min(NTH / A, 4);
+                const int a = tid % A, sg = tid / A;
+                if (sg < nsub) {
+                    const float ya = y_s[a];
+                    float s1 = 0.f, s2 = 0.f;
+#pragma unroll 4
+                    for (int tl = sg; tl < n; tl += nsub) {
+                        const float th = tanh_fast(hfbuf[tl * A + a] + ya);
+                        const float om = 1.f - th * th;
+                        s1 = fmaf(w_s[tl], om, s1);
+                        s2 = fmaf(al_s[tl], om, s2);
+                    }
+                    sred[sg * 2 * A + a] = s1;
+                    sred[sg * 2 * A + A + a] = s2;
+                }
+                __syncthreads();
+                float* pp = apart + ((size_t)b * 2 + half) * (2 * A + 4);
+                for (int i = tid; i < 2 * A; i += NTH) {
+                    float v = 0.f;
+                    for (int j = 0; j < nsub; ++j) v += sred[j * 2 * A + i];
+                    pp[i] = v;
+                }
+                if (tid == 0) {
+                    pp[2 * A] = sred[8 * A];
+                    adots[((size_t)t * B + b) * 2 + half] = sred[8 * A];
+                }
+                // raw alpha * dalpha; dec_dhf_kernel subtracts alpha * dot (the row total is not known here)
+                const int hi = half == 0 ? TC : Tn - TC;
+                for (int tl = tid; tl < hi; tl += NTH) p.ds[row * Tn + tau0 + tl] = tl < n ? w_s[tl] : 0.f;
+            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            __syncthreads();
+          }
+        } else {
             float* y_s = z_s;                   // [A]
             float* v_s = y_s + A;               // [A]
             float* dctx_s = v_s + A;            // [D]
@@ -714,15 +824,42 @@ __global__ void __launch_bounds__(NTH, 1) dec_bwd_persist_kernel(e2e_dec_persist
                 const int rb = tile / NCBp, cb = tile % NCBp;
                 const int nvalid = min(16, B - rb * 16);
                 __syncthreads();
-                if (tid == 0) mbar_expect_tx(&lbar, (uint32_t)(nvalid * A * 4));
-                __syncwarp();
-                if (lane * 8 + w < nvalid) {
-                    const int r = lane * 8 + w;
-                    bulk_g2s(dy_s + r * DS_, p.dy + ((size_t)t * B + rb * 16 + r) * A, (uint32_t)(A * 4), &lbar);
+                if (fastAp) {
+                    // dy_a = v_a (S1_a - dot S2_a) from the two time-halves' partial sums (L2 scratch); float4
+                    // columns, every load of a thread in flight together
+                    const int nq = A / 4;
+#pragma unroll 2
+                    for (int i = tid; i < 16 * nq; i += NTH) {
+                        const int r = i / nq, q = i % nq, b = rb * 16 + r;
+                        float4 dyv = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (b < B) {
+                            const float* p0 = apart + (size_t)b * 2 * (2 * A + 4);
+                            const float* p1 = p0 + (2 * A + 4);
+                            const float4 s10 = __ldcg(reinterpret_cast<const float4*>(p0) + q);
+                            const float4 s11 = __ldcg(reinterpret_cast<const float4*>(p1) + q);
+                            const float4 s20 = __ldcg(reinterpret_cast<const float4*>(p0 + A) + q);
+                            const float4 s21 = __ldcg(reinterpret_cast<const float4*>(p1 + A) + q);
+                            const float dot = __ldcg(p0 + 2 * A) + __ldcg(p1 + 2 * A);
+                            const float4 vv = __ldg(reinterpret_cast<const float4*>(p.attn_v) + q);
+                            dyv.x = vv.x * ((s10.x + s11.x) - dot * (s20.x + s21.x));
+                            dyv.y = vv.y * ((s10.y + s11.y) - dot * (s20.y + s21.y));
+                            dyv.z = vv.z * ((s10.z + s11.z) - dot * (s20.z + s21.z));
+                            dyv.w = vv.w * ((s10.w + s11.w) - dot * (s20.w + s21.w));
+                            if (cb == 0) *reinterpret_cast<float4*>(p.dy + ((size_t)t * B + b) * A + q * 4) = dyv;
+                        }
+                        *reinterpret_cast<float4*>(dy_s + r * DS_ + q * 4) = dyv;
+                    }
+                } else {
+                    if (tid == 0) mbar_expect_tx(&lbar, (uint32_t)(nvalid * A * 4));
+                    __syncwarp();
+                    if (lane * 8 + w < nvalid) {
+                        const int r = lane * 8 + w;
+                        bulk_g2s(dy_s + r * DS_, p.dy + ((size_t)t * B + rb * 16 + r) * A, (uint32_t)(A * 4), &lbar);
+                    }
+                    if (nvalid < 16)
+                        for (int i = tid; i < 16 * A; i += NTH)
+                            if (i / A >= nvalid) dy_s[(i / A) * DS_ + i % A] = 0.f;
                 }
-                if (nvalid < 16)
-                    for (int i = tid; i < 16 * A; i += NTH)
-                        if (i / A >= nvalid) dy_s[(i / A) * DS_ + i % A] = 0.f;
                 if (!pres_ok) load_qp(cb);
                 // operands of this thread's (row, unit) element: in flight during the product
                 const int prow = tid / 8, ul = tid % 8;
@@ -740,9 +877,11 @@ __global__ void __launch_bounds__(NTH, 1) dec_bwd_persist_kernel(e2e_dec_persist
                     carry = p.dc_carry[(size_t)eb * Hd + unit];
                     cpv = p.cprev[row * Hd + unit];
                 }
-                mbar_wait_par(&lbar, lph);
-                lph ^= 1u;
-                if (nvalid < 16 || !pres_ok) __syncthreads();
+                if (!fastAp) {
+                    mbar_wait_par(&lbar, lph);
+                    lph ^= 1u;
+                }
+                if (nvalid < 16 || !pres_ok || fastAp) __syncthreads();
                 const int ksteps = A / 8, per = (ksteps + 7) / 8;
                 const int k0 = min(ksteps, w * per) * 8, k1 = min(ksteps, (w + 1) * per) * 8;
                 float d[4] = {0.f, 0.f, 0.f, 0.f};
@@ -845,11 +984,18 @@ __global__ void __launch_bounds__(256) dec_denc_kernel(e2e_dec_persist_args p, f
 }
 // dHF[b,tau,a] = sum_t ds_t[b,tau] v_a (1 - th^2), th = tanh(HF[b,tau,a] + y_t[b,a]); dv_part[b*Tn+tau, a] = sum_t ds th
 __global__ void __launch_bounds__(128) dec_dhf_kernel(e2e_dec_persist_args p, float* __restrict__ dHF,
-                                                      float* __restrict__ dv_part) {
+                                                      float* __restrict__ dv_part, int attn_fast) {
     const int b = blockIdx.x / p.Tn, tau = blockIdx.x % p.Tn;
     const bool valid = tau < min(p.enc_len[b], p.Tn);
     extern __shared__ float ds_sm[];         // [U]
-    for (int t = threadIdx.x; t < p.U; t += blockDim.x) ds_sm[t] = valid ? p.ds[((size_t)t * p.B + b) * p.Tn + tau] : 0.f;
+    // fast attention backward stored alpha*dalpha: ds = alpha (dalpha - dot), dot = sum of the two halves' partials
+    const float* adots = reinterpret_cast<const float*>(p.ctr) + 64 + (size_t)p.B * 2 * (2 * p.A + 4);
+    for (int t = threadIdx.x; t < p.U; t += blockDim.x) {
+        const size_t row = (size_t)t * p.B + b;
+        float v = valid ? p.ds[row * p.Tn + tau] : 0.f;
+        if (valid && attn_fast) v -= p.alpha[row * p.Tn + tau] * (adots[row * 2] + adots[row * 2 + 1]);
+        ds_sm[t] = v;
+    }
     __syncthreads();
     for (int a = threadIdx.x; a < p.A; a += blockDim.x) {
         float acc = 0.f, accv = 0.f;
@@ -899,6 +1045,21 @@ static size_t bwd_smem_bytes(const e2e_dec_persist_args& p) {
     return sizeof(float) * (max(x, max(a, pp)) + 64);
 }
 
+// 1 when the time-split attention backward fits: shared-memory carve-up of dec_bwd_persist_kernel + L2 scratch
+static int bwd_attn_fast(const e2e_dec_persist_args& p, size_t* smem) {
+    const int G4 = 4 * p.Hd, TC = (p.Tn + 1) / 2, TCp = (TC + 3) & ~3;
+    if (p.Tn > 128 || p.A > NTH || p.A % 4 != 0 || p.D % 4 != 0) return 0;
+    const size_t enc_cap = (size_t)16 * (G4 + 4) + 8 * 32 * 4 + 8 * 16 * 40;     // z_s | red | xred
+    if ((size_t)TC * p.D > enc_cap) return 0;
+    const size_t base = (size_t)24 * (G4 + 8) + enc_cap + 8 * (p.A + 4);
+    const size_t extra = (size_t)TCp * p.A + 2 * p.A + p.D + 3 * TCp + 8 * p.A + 8;
+    const size_t total = sizeof(float) * (base + extra + 64);
+    if (total > 227 * 1024) return 0;
+    if ((size_t)p.B * 2 * (2 * p.A + 4) + (size_t)p.U * p.B * 2 + 64 > (size_t)(1 << 18)) return 0;   // ctr scratch >= 1 MB
+    *smem = max(*smem, total);
+    return 1;
+}
+
 int dec_persist(cudaStream_t st, bool bwd, const e2e_dec_persist_args* a, float* denc, float* dHF, float* dv_part) {
     e2e_dec_persist_args p = *a;
     E2E_REQUIRE(p.Hd % 8 == 0 && p.A % 8 == 0 && p.D % 8 == 0, "decoder_persist: Hd, A, D must be multiples of 8");
@@ -923,7 +1084,7 @@ int dec_persist(cudaStream_t st, bool bwd, const e2e_dec_persist_args* a, float*
             E2E_CHECK_CUDA(cudaMemcpyToSymbolAsync(d_dec_dbg, &last_dbg, sizeof(last_dbg), 0, cudaMemcpyHostToDevice, st));
         }
     }
-    int attn_cap = bwd ? 0 : fwd_attn_cap(p, &smem);
+    int attn_cap = bwd ? bwd_attn_fast(p, &smem) : fwd_attn_cap(p, &smem);
     E2E_CHECK_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     void* args[] = {&p, &attn_cap};
     E2E_CHECK_CUDA(cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(NTH), args, smem, st));
@@ -931,7 +1092,7 @@ int dec_persist(cudaStream_t st, bool bwd, const e2e_dec_persist_args* a, float*
     if (bwd) {
         dec_denc_kernel<<<p.B * p.Tn, 256, sizeof(float) * p.U, st>>>(p, denc);
         E2E_LAUNCH_CHECK();
-        dec_dhf_kernel<<<p.B * p.Tn, 128, sizeof(float) * p.U, st>>>(p, dHF, dv_part);
+        dec_dhf_kernel<<<p.B * p.Tn, 128, sizeof(float) * p.U, st>>>(p, dHF, dv_part, attn_cap != 0 && 2 * p.B <= grid);
         E2E_LAUNCH_CHECK();
     }
     return 0;
