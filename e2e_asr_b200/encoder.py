@@ -94,6 +94,7 @@ class Encoder(BaseParams):
             max_depth = max(max_depth, num_layer)
 
         dev = encoder_input.device
+        self.layer_done = {}
         lens_host = np.asarray(ops.host_array(seq_len), np.int64)
         B, T, F = encoder_input.shape
         res = params.initial_res_fac
@@ -118,6 +119,11 @@ class Encoder(BaseParams):
             lens_dev = torch.from_numpy(lens_host.astype(np.int32)).to(dev, non_blocking=True)
             max_len = int(lens_host.max()) if B else 0
             out = self._layer_encoder_input(x, lens_dev, max_len, layer_depth)       # [B, Tp, 2H]
+            if out.is_cuda:
+                # consumers on other streams (auxiliary heads) may start as soon as THIS layer is done
+                ev = torch.cuda.Event()
+                ev.record()
+                self.layer_done[layer_depth] = ev
             view = out[:, :T_l]
             if layer_depth in time_major_states:
                 time_major_states[layer_depth] = view.transpose(0, 1)
