@@ -39,6 +39,8 @@ _SIGS = {
     "e2e_scale": "pzppf",
     "e2e_mean": "pipp",
     "e2e_axpy": "pzfpp",
+    "e2e_adam": "pzppppffff",
+    "e2e_dropout": "pzppfQI",
     "e2e_gemm_f64": "piiipipipip",
     "e2e_lstm_step_f64": "piippppi",
     "e2e_attn_beam_f64": "piiiipppppppi",
@@ -46,7 +48,7 @@ _SIGS = {
     "e2e_embed_gather_f64": "piipppi",
 }
 _CT = {"p": ctypes.c_void_p, "i": ctypes.c_int, "l": ctypes.c_longlong, "z": ctypes.c_size_t, "f": ctypes.c_float,
-       "d": ctypes.c_double}
+       "d": ctypes.c_double, "Q": ctypes.c_ulonglong, "I": ctypes.c_uint}
 
 
 class DecLoopFwdArgs(ctypes.Structure):

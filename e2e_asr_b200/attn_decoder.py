@@ -68,10 +68,17 @@ class AttnDecoder(Decoder):
         lens = ops.to_i32(seq_len, dev)
         enc_len = ops.to_i32(seq_len_inp, dev)
         if self.input_rule() == "teacher":
+            # DropoutWrapper(output_keep_prob=out_prob_dec) iff training (decoder.py:60-63) acts on lm_cell's
+            # output only: raw_loop_function reads the decoder cell through get_state(state) = state.c and never
+            # uses cell_output (attn_decoder.py:114-118), so the decoder-LSTM wrapper has no effect on the result.
+            lm_drop = None
+            if self.isTraining and self.params.out_prob_dec < 1.0:
+                lm_drop = (self.params.out_prob_dec, getattr(self, "dropout_seed", 0),
+                           100 + getattr(self, "dropout_stream", 0))
             return ops.attn_decoder_apply(
                 enc, v["emb"], v["attn_w"], v["attn_v"], v["lm_k"], v["lm_b"], v["dec_k"], v["dec_b"], v["q_k"],
                 v["q_b"], v["ap_k"], v["ap_b"], v["out_k"], v["out_b"], v["in_k"], v["in_b"], v["sp_k"], v["sp_b"],
-                decoder_inp, lens, enc_len, U, self.stash)
+                decoder_inp, lens, enc_len, U, self.stash, lm_drop=lm_drop)
         from .inference import greedy_decode_logits
         with torch.no_grad():
             return greedy_decode_logits(v, decoder_inp, lens, U, enc, enc_len)

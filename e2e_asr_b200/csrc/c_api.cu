@@ -67,6 +67,8 @@ int clip_by_norm(cudaStream_t, size_t, float*, const float*, float, float*);
 int scale_inplace(cudaStream_t, size_t, float*, const float*, float);
 int mean_vec(cudaStream_t, int, const float*, float*);
 int axpy(cudaStream_t, size_t, float, const float*, float*);
+int adam_update(cudaStream_t, size_t, float*, const float*, float*, float*, float, float, float, float);
+int dropout(cudaStream_t, size_t, const float*, float*, float, unsigned long long, unsigned);
 int dec_persist(cudaStream_t, bool, const e2e_dec_persist_args*, float*, float*, float*);
 int gemm_f64(cudaStream_t, int, int, int, const double*, int, const float*, int, double*, int, const float*);
 int lstm_step_f64(cudaStream_t, int, int, const double*, const double*, double*, double*, int);
@@ -292,6 +294,14 @@ int e2e_scale(void* stream, size_t n, float* x, const float* dev_scalar, float a
 }
 int e2e_mean(void* stream, int n, const float* x, float* out) { return mean_vec(ST(stream), n, x, out); }
 int e2e_axpy(void* stream, size_t n, float a, const float* x, float* y) { return axpy(ST(stream), n, a, x, y); }
+int e2e_adam(void* stream, size_t n, float* param, const float* grad, float* m, float* v, float lr_t, float beta1,
+             float beta2, float eps) {
+    return adam_update(ST(stream), n, param, grad, m, v, lr_t, beta1, beta2, eps);
+}
+int e2e_dropout(void* stream, size_t n, const float* x, float* y, float keep, unsigned long long seed,
+                unsigned offset) {
+    return dropout(ST(stream), n, x, y, keep, seed, offset);
+}
 
 int e2e_gemm_f64(void* stream, int M, int N, int K, const double* A, int lda, const float* B, int ldb, double* C,
                  int ldc, const float* bias) {

@@ -135,4 +135,68 @@ int mean_vec(cudaStream_t st, int n, const float* x, float* out) {
     return 0;
 }
 
+// ---- Adam (tf.train.AdamOptimizer defaults, seq2seq_model.py:137,153-155) on the flat buffers ----
+//   m = b1 m + (1-b1) g ; v = b2 v + (1-b2) g^2 ; p -= lr_t m / (sqrt(v) + eps),  lr_t = lr sqrt(1-b2^t)/(1-b1^t)
+// (TF's "epsilon hat" form: eps is added to sqrt(v), the bias corrections are folded into lr_t on the host).
+__global__ void adam_kernel(size_t n4, float4* __restrict__ p, const float4* __restrict__ g, float4* __restrict__ m,
+                            float4* __restrict__ v, float lr_t, float b1, float b2, float eps) {
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
+        float4 pp = p[i], gg = g[i], mm = m[i], vv = v[i];
+        mm.x = b1 * mm.x + (1.f - b1) * gg.x; mm.y = b1 * mm.y + (1.f - b1) * gg.y;
+        mm.z = b1 * mm.z + (1.f - b1) * gg.z; mm.w = b1 * mm.w + (1.f - b1) * gg.w;
+        vv.x = b2 * vv.x + (1.f - b2) * gg.x * gg.x; vv.y = b2 * vv.y + (1.f - b2) * gg.y * gg.y;
+        vv.z = b2 * vv.z + (1.f - b2) * gg.z * gg.z; vv.w = b2 * vv.w + (1.f - b2) * gg.w * gg.w;
+        pp.x -= lr_t * mm.x / (sqrtf(vv.x) + eps); pp.y -= lr_t * mm.y / (sqrtf(vv.y) + eps);
+        pp.z -= lr_t * mm.z / (sqrtf(vv.z) + eps); pp.w -= lr_t * mm.w / (sqrtf(vv.w) + eps);
+        p[i] = pp; m[i] = mm; v[i] = vv;
+    }
+}
+int adam_update(cudaStream_t st, size_t n, float* p, const float* g, float* m, float* v, float lr_t, float b1,
+                float b2, float eps) {
+    E2E_REQUIRE(n % 4 == 0, "adam: the flat buffers are padded to multiples of 4 floats (got %zu)", n);
+    if (n == 0) return 0;
+    adam_kernel<<<min((size_t)SUMSQ_BLOCKS * 4, (n / 4 + 255) / 256), 256, 0, st>>>(
+        n / 4, (float4*)p, (const float4*)g, (float4*)m, (float4*)v, lr_t, b1, b2, eps);
+    E2E_LAUNCH_CHECK();
+    return 0;
+}
+
+// ---- output dropout of the recurrent cells (DropoutWrapper(output_keep_prob), encoder.py:50-52, decoder.py:60-63)
+// y = x * keep_mask / keep with keep_mask ~ Bernoulli(keep) from the counter-based Philox4x32-10 generator:
+// element 4q+j takes word j of philox(counter = (q, offset, 0, 0), key = (seed_lo, seed_hi)); keep iff
+// word * 2^-32 < keep.  Stateless, so forward and backward (dy = dout * same mask) regenerate it.
+__device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0,
+                                              uint32_t k1, uint32_t (&out)[4]) {
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+        const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+        const uint32_t n0 = hi1 ^ c1 ^ k0, n1 = lo1, n2 = hi0 ^ c3 ^ k1, n3 = lo0;
+        c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+    out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+__global__ void dropout_kernel(size_t n, const float* __restrict__ x, float* __restrict__ y, float keep,
+                               unsigned long long seed, unsigned offset) {
+    const float inv = 1.0f / keep;
+    for (size_t q = blockIdx.x * (size_t)blockDim.x + threadIdx.x; q * 4 < n; q += (size_t)gridDim.x * blockDim.x) {
+        uint32_t r[4];
+        philox4x32_10((uint32_t)q, offset, (uint32_t)(q >> 32), 0u, (uint32_t)seed, (uint32_t)(seed >> 32), r);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const size_t i = q * 4 + j;
+            if (i < n) y[i] = ((float)r[j] * 2.3283064365386963e-10f < keep) ? x[i] * inv : 0.f;
+        }
+    }
+}
+int dropout(cudaStream_t st, size_t n, const float* x, float* y, float keep, unsigned long long seed,
+            unsigned offset) {
+    E2E_REQUIRE(keep > 0.f && keep <= 1.f, "dropout: keep probability %f out of (0, 1]", keep);
+    if (n == 0) return 0;
+    dropout_kernel<<<min((size_t)SUMSQ_BLOCKS * 8, (n / 4 + 256) / 256), 256, 0, st>>>(n, x, y, keep, seed, offset);
+    E2E_LAUNCH_CHECK();
+    return 0;
+}
+
 }  // namespace e2e

@@ -36,9 +36,8 @@ class Decoder(BaseParams):
             raise NotImplementedError("Decoder: use_lstm=False (GRUCell, decoder.py:58) is not built yet")
         if p.num_layers_dec != 1:
             raise NotImplementedError("Decoder: num_layers_dec > 1 (MultiRNNCell, decoder.py:64-68) is not built yet")
-        if self.isTraining and p.out_prob_dec != 1.0:
-            raise NotImplementedError("Decoder: dropout (out_prob_dec=%g) is not built yet; parity and benchmark "
-                                      "runs use 1.0 (SURVEY.md section 7)" % p.out_prob_dec)
+        if not (0.0 < p.out_prob_dec <= 1.0):
+            raise ValueError("Decoder: out_prob_dec=%g must be in (0, 1]" % p.out_prob_dec)
         if self.isTraining and p.samp_prob > 0:
             raise NotImplementedError("Decoder: scheduled sampling (samp_prob=%g, decoder.py:155-180) is not built "
                                       "yet; parity and benchmark runs use samp_prob=0" % p.samp_prob)

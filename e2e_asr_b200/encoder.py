@@ -48,9 +48,8 @@ class Encoder(BaseParams):
                                       "pass use_lstm=True (the reference CLI default, encoder.py:187)")
         if not p.bi_dir:
             raise NotImplementedError("Encoder: bi_dir=False is not built yet")
-        if self.isTraining and p.out_prob != 1.0:
-            raise NotImplementedError("Encoder: output dropout (out_prob=%g) is not built yet; parity and "
-                                      "benchmark runs use out_prob=1.0 (SURVEY.md section 7)" % p.out_prob)
+        if not (0.0 < p.out_prob <= 1.0):
+            raise ValueError("Encoder: out_prob=%g must be in (0, 1]" % p.out_prob)
         if p.skip_step not in (1, 2):
             raise NotImplementedError("Encoder: skip_step must be 1 or 2")
 
@@ -68,7 +67,12 @@ class Encoder(BaseParams):
     def _layer_encoder_input(self, x_padded, lens_i32, max_len, layer_depth=1):
         """Run one BiLSTM layer on a padded batch-major buffer (encoder.py:55-91)."""
         k_fw, b_fw, k_bw, b_bw = self._layer_vars(layer_depth, x_padded.shape[2])
-        return ops.BiLSTMLayerFn.apply(x_padded, k_fw, b_fw, k_bw, b_bw, lens_i32, max_len)
+        out = ops.BiLSTMLayerFn.apply(x_padded, k_fw, b_fw, k_bw, b_bw, lens_i32, max_len)
+        if self.isTraining and self.params.out_prob < 1.0:
+            # DropoutWrapper(cell, output_keep_prob=out_prob) iff training (encoder.py:49-52): the per-step outputs
+            # of both directions are dropped, the recurrent state is not.  Mask stream = layer depth.
+            out = ops.DropoutFn.apply(out, self.params.out_prob, self.dropout_seed, layer_depth)
+        return out
 
     def __call__(self, encoder_input, seq_len, num_layers):
         """Run the encoder (encoder.py:122-180).
@@ -95,6 +99,8 @@ class Encoder(BaseParams):
 
         dev = encoder_input.device
         self.layer_done = {}
+        if not hasattr(self, "dropout_seed"):
+            self.dropout_seed = 0
         lens_host = np.asarray(ops.host_array(seq_len), np.int64)
         B, T, F = encoder_input.shape
         res = params.initial_res_fac

@@ -171,6 +171,27 @@ def _unpack_lstm(dWx, dWh, dbp, I, H, nd, device):
     return outs
 
 
+class DropoutFn(torch.autograd.Function):
+    """DropoutWrapper(output_keep_prob) on a recurrent cell's outputs (encoder.py:50-52, decoder.py:60-63):
+    y = x * mask / keep with the stateless Philox mask of e2e_dropout; backward regenerates the mask."""
+
+    @staticmethod
+    def forward(ctx, x, keep, seed, offset):
+        x = x.contiguous()
+        y = torch.empty_like(x)
+        call("e2e_dropout", x.numel(), x, y, float(keep), int(seed), int(offset))
+        ctx.cfg = (float(keep), int(seed), int(offset))
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        keep, seed, offset = ctx.cfg
+        dy = dy.contiguous()
+        dx = torch.empty_like(dy)
+        call("e2e_dropout", dy.numel(), dy, dx, keep, seed, offset)
+        return dx, None, None, None
+
+
 # Weight-gradient side stream.  The dW GEMMs of a layer (x^T dz, h^T dz, bias column sums) are off the
 # backward critical path: only dX feeds the layer below.  When enabled (Seq2SeqModel does, for
 # VariableStore parameters whose .grad is a view of the flat gradient buffer) they are enqueued on a
@@ -409,9 +430,12 @@ def set_decoder_impl(name):
     _DECODER_IMPL = name
 
 
-def attn_decoder_apply(*args):
-    fn = AttnDecoderFnV2 if _DECODER_IMPL == "persist" else AttnDecoderFn
-    return fn.apply(*args)
+def attn_decoder_apply(*args, lm_drop=None):
+    if _DECODER_IMPL == "persist":
+        return AttnDecoderFnV2.apply(*(args + (lm_drop,)))
+    if lm_drop is not None:
+        raise NotImplementedError("decoder dropout is served by the persistent decoder kernels only")
+    return AttnDecoderFn.apply(*args)
 
 
 class AttnDecoderFnV2(torch.autograd.Function):
@@ -424,7 +448,7 @@ class AttnDecoderFnV2(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, enc, emb, attn_w, attn_v, lm_k, lm_b, dec_k, dec_b, q_k, q_b, ap_k, ap_b, out_k, out_b,
-                in_k, in_b, sp_k, sp_b, ids, lens_i32, enc_len_i32, U, stash):
+                in_k, in_b, sp_k, sp_b, ids, lens_i32, enc_len_i32, U, stash, lm_drop=None):
         dev = enc.device
         st = _dev_state(dev)
         B, Tn, D = enc.shape
@@ -443,7 +467,12 @@ class AttnDecoderFnV2(torch.autograd.Function):
         C_lm = torch.empty((U * B, Hl), **f32)
         call("e2e_lstm_rec_fwd", B, U, U, Hl, 1, 1, B, G_lm, hl, C_lm, Wh_lm, lens_i32, st["ctr"],
              st["ctr"].numel() * 4, st["err"], work=float(U), tag="lm_rec_fwd")
-        m = gemm(hl, sp_k, bias=sp_b) if sp_k is not None else hl
+        # DropoutWrapper on lm_cell: its OUTPUT is dropped, the recurrent state is not (decoder.py:60-63)
+        hl_out = hl
+        if lm_drop is not None:
+            hl_out = torch.empty_like(hl)
+            call("e2e_dropout", hl.numel(), hl, hl_out, float(lm_drop[0]), int(lm_drop[1]), int(lm_drop[2]))
+        m = gemm(hl_out, sp_k, bias=sp_b) if sp_k is not None else hl_out
         pre = gemm(m, in_k[:Hd], bias=in_b)                          # [U*B, E]
         # decoder-LSTM kernel in gate-interleaved layout, with the ctx half of InputProjection folded in
         W_ch = torch.empty((D + Hd, 4 * Hd), **f32)
@@ -476,6 +505,8 @@ class AttnDecoderFnV2(torch.autograd.Function):
                              (emb, attn_w, attn_v, lm_k, lm_b, dec_k, dec_b, q_k, q_b, ap_k, ap_b, out_k, out_b,
                               in_k, in_b, sp_k, sp_b))
         ctx.has_sp = sp_k is not None
+        ctx.lm_drop = lm_drop
+        ctx.hl_out = hl_out if lm_drop is not None else None
         return logits
 
     @staticmethod
@@ -536,9 +567,14 @@ class AttnDecoderFnV2(torch.autograd.Function):
             dm = gemm(dpre, in_k[:Hd], tb=True)
             dsp_k = dsp_b = None
             if sp_k is not None:
-                dsp_k = gemm(hl, dm, ta=True)
+                dsp_k = gemm(hl if ctx.hl_out is None else ctx.hl_out, dm, ta=True)
                 dsp_b = colsum(dm)
                 dm = gemm(dm, sp_k, tb=True)
+            if ctx.lm_drop is not None:
+                dmd = torch.empty_like(dm)
+                call("e2e_dropout", dm.numel(), dm.contiguous(), dmd, float(ctx.lm_drop[0]), int(ctx.lm_drop[1]),
+                     int(ctx.lm_drop[2]))
+                dm = dmd
             call("e2e_lstm_rec_bwd", B, U, U, Hl, 1, 1, B, G_lm, C_lm, Wh_lm, dm, lens_i32, ctr,
                  ctr.numel() * 4, st["err"], work=float(U), tag="lm_rec_bwd")
             dWx_lm = gemm(u, G_lm, ta=True)
@@ -573,9 +609,9 @@ class AttnDecoderFnV2(torch.autograd.Function):
             for t_ in list(ctx.saved_tensors) + [dlogits, dproj, dz, dy, dv_part, dHF] + [g for g in grads if g is not None]:
                 if t_ is not None:
                     t_.record_stream(side)
-            return (denc_view,) + (None,) * 22
+            return (denc_view,) + (None,) * 23
         grads = param_grads(st["ctr"])
-        return (denc_view,) + tuple(grads) + (None, None, None, None, None)
+        return (denc_view,) + tuple(grads) + (None, None, None, None, None, None)
 
 
 # ---------------------------------------------------------------------------

@@ -52,6 +52,11 @@ class Seq2SeqModel(BaseParams):
         params['ctc_tasks'] = {}
         # tf.clip_by_global_norm sees the embedding gradient as IndexedSlices
         params['tf_indexed_slices_norm'] = True
+        # opt.apply_gradients (seq2seq_model.py:137,153-155) inside run_step; off by default so that the
+        # parity tests and the fwd+bwd benchmark see the clipped gradients of fixed parameters
+        params['apply_updates'] = False
+        # seed of the (builder-defined) Philox dropout masks; the step counter is mixed in
+        params['dropout_seed'] = 0
         return params
 
     def __init__(self, data_iter, isTraining=True, params=None, variables=None, device="cuda", reducer=None):
@@ -79,6 +84,7 @@ class Seq2SeqModel(BaseParams):
         self._loss_scale = None
         self._loss_scale_value = None
         self._inflight = []
+        self._adam = None
         if data_iter is not None:
             self.create_computational_graph()
 
@@ -162,6 +168,12 @@ class Seq2SeqModel(BaseParams):
                 if len(self._inflight) >= 2:
                     self._inflight.pop(0).synchronize()
             self.variables.zero_grad()
+        # one Philox key per step: seed * 1000003 + global_step (see oracle train_step(dropout_seed=...))
+        step_seed = int(params.get('dropout_seed', 0)) * 1000003 + int(self.global_step)
+        self.encoder.dropout_seed = step_seed
+        for i, task in enumerate(params.tasks):
+            self.decoder[task].dropout_seed = step_seed
+            self.decoder[task].dropout_stream = i
         depth_of = dict((t, params.num_layers[t]) for t in list(params.tasks) + list(params.ctc_tasks))
         ctx = torch.enable_grad() if self.isTraining else torch.no_grad()
         with ctx:
@@ -236,6 +248,8 @@ class Seq2SeqModel(BaseParams):
             self.reducer.allreduce_mean(self.variables.flat_grads())
         self.clip_gradients()
         self.updates = self.variables
+        if params.get('apply_updates', False):
+            self.apply_gradients()
         self.global_step += 1
         if torch.cuda.is_available():
             ev = torch.cuda.Event()
@@ -269,6 +283,21 @@ class Seq2SeqModel(BaseParams):
                     n = self.reducer.world_size
                 call("e2e_axpy", 1, 1.0 / (n * n), self._sq_emb, self._sq)
         call("e2e_clip_by_norm", g.numel(), g, self._sq, float(self.params.max_gradient_norm), self.grad_norm)
+
+    def apply_gradients(self, beta1=0.9, beta2=0.999, epsilon=1e-8):
+        """tf.train.AdamOptimizer(self.learning_rate).apply_gradients(clipped gradients) (seq2seq_model.py:137,
+        153-155) as ONE fused kernel over the flat parameter / gradient / moment buffers.  TF applies the embedding
+        gradient as IndexedSlices with duplicate indices summed first, which equals the dense update used here."""
+        vs = self.variables
+        n = vs.used
+        if self._adam is None or self._adam["m"].numel() < n:
+            self._adam = dict(m=torch.zeros(vs.capacity, dtype=torch.float32, device=self.device),
+                              v=torch.zeros(vs.capacity, dtype=torch.float32, device=self.device), t=0)
+        a = self._adam
+        a["t"] += 1
+        lr_t = self.learning_rate * (1.0 - beta2 ** a["t"]) ** 0.5 / (1.0 - beta1 ** a["t"])
+        call("e2e_adam", (n + 3) // 4 * 4, vs.flat, vs.gflat, a["m"], a["v"], float(lr_t), float(beta1), float(beta2),
+             float(epsilon))
 
     def gradients(self):
         """Clipped gradients keyed by TF variable name (host copies)."""

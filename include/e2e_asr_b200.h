@@ -226,6 +226,18 @@ int e2e_scale(void* stream, size_t n, float* x, const float* dev_scalar, float a
 int e2e_mean(void* stream, int n, const float* x, float* out);
 int e2e_axpy(void* stream, size_t n, float a, const float* x, float* y);   /* y += a*x */
 
+/* tf.train.AdamOptimizer.apply_gradients (seq2seq_model.py:137,153-155) on the flat parameter / gradient /
+ * moment buffers (n a multiple of 4): m = b1 m + (1-b1) g; v = b2 v + (1-b2) g^2; p -= lr_t m / (sqrt(v) + eps),
+ * with lr_t = lr sqrt(1-b2^t) / (1-b1^t) computed by the caller. */
+int e2e_adam(void* stream, size_t n, float* param, const float* grad, float* m, float* v, float lr_t, float beta1,
+             float beta2, float eps);
+
+/* DropoutWrapper(output_keep_prob=keep) on a recurrent cell's outputs (encoder.py:50-52, decoder.py:60-63):
+ * y[i] = x[i] / keep if philox4x32_10(counter = (i/4, offset, 0, 0), key = seed)[i%4] * 2^-32 < keep else 0.
+ * Stateless: the backward pass calls it again on the upstream gradient with the same (seed, offset). */
+int e2e_dropout(void* stream, size_t n, const float* x, float* y, float keep, unsigned long long seed,
+                unsigned offset);
+
 #ifdef __cplusplus
 }
 #endif

@@ -102,3 +102,46 @@ def test_greedy_decode_ids_bit_exact(cname):
     np.testing.assert_array_equal(ids, ref_ids)
     e = np.abs(logits - ref_logits).max() / np.abs(ref_logits).max()
     assert e < 1e-4
+
+
+@pytest.mark.parametrize("cname", ["tiny_b", "cfg1"])
+def test_train_step_with_dropout_matches_oracle(cname):
+    """out_prob / out_prob_dec < 1 (the reference's training defaults are 0.9): the Philox masks are a builder-defined
+    stateless function of (seed, stream, flat index), restated in the oracle, so the dropped step must meet the same
+    1e-4 bar.  The second step uses another key (global_step is mixed in)."""
+    cfg = synth.get_config(cname)
+    w = synth.make_weights(cfg, bias_noise=0.1)
+    batch = synth.make_batch(cfg)
+    model = build_model(cfg, w, device="cuda:0")
+    model.params.encoder_params.out_prob = 0.8
+    model.params.decoder_params["char"].out_prob_dec = 0.7
+    model.params.dropout_seed = 11
+    for step in range(2):
+        model.run_step(batch)
+        ops.check_device_errors("cuda:0")
+        ref = om.train_step(w, batch, num_layers={"char": cfg.L}, ctc_tasks=cfg.ctc, out_prob=0.8, out_prob_dec=0.7,
+                            dropout_seed=11 * 1000003 + step)
+        compare_step(model, ref, rtol=RTOL)
+    nodrop = om.train_step(w, batch, num_layers={"char": cfg.L}, ctc_tasks=cfg.ctc)
+    assert abs(ref["total_loss"] - nodrop["total_loss"]) > 1e-3
+
+
+def test_adam_updates_match_oracle():
+    """apply_updates=True: three Adam steps (fused flat-buffer kernel) against the oracle's TF-formula Adam."""
+    cfg = synth.get_config("tiny_b")
+    w = synth.make_weights(cfg, bias_noise=0.1)
+    batch = synth.make_batch(cfg)
+    model = build_model(cfg, w, device="cuda:0")
+    model.params.apply_updates = True
+    wref = {k: v.astype(np.float64) for k, v in w.items()}
+    state = {}
+    for step in range(3):
+        model.run_step(batch)
+        ref = om.train_step(wref, batch, num_layers={"char": cfg.L}, ctc_tasks=cfg.ctc)
+        wref = om.adam_step(wref, ref["clipped"], state, 1e-3)
+    got = model.variables.state_dict()
+    for k, v in wref.items():
+        err = float(np.abs(got[k] - v).max())
+        # a step moves a weight by ~lr = 1e-3: 1e-6 absolute = 1e-3 of the update
+        assert err < 2e-6, (k, err)
+        assert float(np.abs(got[k] - w[k]).max()) > 1e-4      # the parameters really moved

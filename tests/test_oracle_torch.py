@@ -231,3 +231,60 @@ def test_cross_entropy_matches_reference_formula():
     ref.backward()
     assert abs(float(ref) - loss) < 1e-12
     np.testing.assert_allclose(dl, lt.grad.numpy(), rtol=1e-10, atol=1e-14)
+
+
+# ---------------------------------------------------------------- dropout / Adam
+def test_philox_known_answers():
+    """Random123 known-answer vectors for philox4x32_10 (kat_vectors)."""
+    r = om.philox4x32_10([0], [0], [0], [0], 0, 0)
+    assert [int(x[0]) for x in r] == [0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8]
+    r = om.philox4x32_10([0xffffffff], [0xffffffff], [0xffffffff], [0xffffffff], 0xffffffff, 0xffffffff)
+    assert [int(x[0]) for x in r] == [0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd]
+    r = om.philox4x32_10([0x243f6a88], [0x85a308d3], [0x13198a2e], [0x03707344], 0xa4093822, 0x299f31d0)
+    assert [int(x[0]) for x in r] == [0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1]
+    m = om.dropout_mask(200003, 0.9, 77, 2)
+    assert abs((m > 0).mean() - 0.9) < 5e-3 and abs(m.mean() - 1.0) < 1e-2
+    assert not np.array_equal(m, om.dropout_mask(200003, 0.9, 77, 3))      # streams differ
+    np.testing.assert_array_equal(m, om.dropout_mask(200003, 0.9, 77, 2))  # stateless
+
+
+def test_finite_differences_with_dropout():
+    """Masks are a fixed function of (seed, stream, index): the dropped graph is still differentiable."""
+    cfg = synth.get_config("tiny")
+    w = synth.make_weights(cfg, bias_noise=0.1)
+    batch = synth.make_batch(cfg)
+    kw = dict(num_layers={"char": 4}, ctc_tasks=cfg.ctc, out_prob=0.7, out_prob_dec=0.6, dropout_seed=5)
+    out = om.train_step(w, batch, **kw)
+    base = om.train_step(w, batch, num_layers={"char": 4}, ctc_tasks=cfg.ctc)
+    assert abs(out["total_loss"] - base["total_loss"]) > 1e-3        # dropout is really applied
+    rng = np.random.Generator(np.random.PCG64(3))
+    eps = 1e-6
+    for k in sorted(w.keys()):
+        idx = tuple(int(rng.integers(0, s)) for s in w[k].shape)
+        wp = {n: v.astype(np.float64).copy() for n, v in w.items()}
+        wm = {n: v.astype(np.float64).copy() for n, v in w.items()}
+        wp[k][idx] += eps
+        wm[k][idx] -= eps
+        fd = (om.train_step(wp, batch, want_grads=False, **kw)["total_loss"]
+              - om.train_step(wm, batch, want_grads=False, **kw)["total_loss"]) / (2 * eps)
+        assert abs(fd - out["grads"][k][idx]) < 1e-6 * max(1.0, abs(fd)), (k, idx, fd, out["grads"][k][idx])
+
+
+def test_adam_matches_tf_formula():
+    """tf.train.AdamOptimizer: lr_t = lr sqrt(1-b2^t)/(1-b1^t); p -= lr_t m / (sqrt(v) + eps)."""
+    rng = np.random.Generator(np.random.PCG64(4))
+    p = {"a": rng.standard_normal((3, 4)), "b": rng.standard_normal(5)}
+    st = {}
+    m = {k: np.zeros_like(v) for k, v in p.items()}
+    v_ = {k: np.zeros_like(v) for k, v in p.items()}
+    ref = {k: x.copy() for k, x in p.items()}
+    for t in range(1, 4):
+        g = {k: rng.standard_normal(x.shape) for k, x in p.items()}
+        p = om.adam_step(p, g, st, 1e-3)
+        for k in ref:
+            m[k] = 0.9 * m[k] + 0.1 * g[k]
+            v_[k] = 0.999 * v_[k] + 0.001 * g[k] ** 2
+            ref[k] = ref[k] - 1e-3 * np.sqrt(1 - 0.999 ** t) / (1 - 0.9 ** t) * m[k] / (np.sqrt(v_[k]) + 1e-8)
+            np.testing.assert_allclose(p[k], ref[k], rtol=1e-12)
+    # first step moves every coordinate by ~lr * sign(g)
+    assert st["t"] == 3
