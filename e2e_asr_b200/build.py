@@ -7,7 +7,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libe2e_asr_b200.so")
-SOURCES = ["c_api.cu", "gemm_simt.cu", "gemm_tc.cu", "lstm_rec.cu", "lstm_rec_cluster.cu", "lstm_rec_mc.cu", "decoder.cu", "decoder_persist.cu", "beam.cu", "loss.cu", "misc.cu"]
+SOURCES = ["c_api.cu", "gemm_simt.cu", "gemm_tc.cu", "lstm_rec.cu", "lstm_rec_cluster.cu", "lstm_rec_mc.cu", "lstm_rec_ws.cu", "decoder.cu", "decoder_persist.cu", "beam.cu", "loss.cu", "misc.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr"]
 
@@ -20,7 +20,8 @@ def build(force=False, verbose=False):
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
     objdir = os.path.join(HERE, "build")
     os.makedirs(objdir, exist_ok=True)
-    deps = [os.path.join(CSRC, "common.cuh"), os.path.join(HERE, "..", "include", "e2e_asr_b200.h")]
+    deps = [os.path.join(CSRC, "common.cuh"), os.path.join(CSRC, "rec_frag.cuh"),
+            os.path.join(HERE, "..", "include", "e2e_asr_b200.h")]
     objs, procs = [], []
     for src in SOURCES:
         s = os.path.join(CSRC, src)

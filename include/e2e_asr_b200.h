@@ -74,11 +74,12 @@ int e2e_lstm_unpack_grads(void* stream, int I, int H, float* dkernel, float* dbi
  * Hout [rows][ndir*H] must be zero-initialised (rows with t >= len stay 0).
  * ctr_ws: >= max(4*ndir*ceil(B/4), 4096*ndir*16*ceil(B/16)) bytes of scratch; err_flag: device int set to 1 if a
  * step barrier ever times out. */
-/* 0 (default): fastest eligible kernel -- the register-resident multicast-cluster recurrence for
- * H in {128, 256} (needs ctr_ws >= 512 KB), else the cluster / DSMEM recurrence when H/16 is
- * 1,2,4,8 or 16, else the L2-exchange kernel with per-group global counters;
- * 1: always the L2-exchange kernel; 2: never the multicast kernel;
- * 3 / 4: multicast kernel with 1 / 2 interleaved batch slices per cluster (test hooks). */
+/* 0 (default): fastest eligible kernel -- the warp-specialised register-resident multicast-cluster
+ * recurrence for H in {128, 256} (needs ctr_ws >= 512 KB), else the cluster / DSMEM recurrence when H/16
+ * is 1,2,4,8 or 16, else the L2-exchange kernel with per-group global counters;
+ * 1: always the L2-exchange kernel; 2: cluster / DSMEM or L2 kernel only;
+ * 3 / 4: non-specialised register-resident kernel with 1 / 2 interleaved batch slices per cluster;
+ * 5 / 6: warp-specialised kernel with 1 / 2 slices (test hooks). */
 int e2e_set_rec_mode(int mode);
 /* test hook: device buffer (>= 5*T int64) receiving per-step clock64 stamps of the forward cluster kernel, or NULL */
 int e2e_set_rec_debug(long long* dbg);
