@@ -201,21 +201,25 @@ _WGRAD = {}
 
 
 def enable_wgrad_stream(device, enabled=True):
+    """Two streams: "enc" (encoder layer dW GEMMs, large) and "dec" (the ~80 small launches of the decoder /
+    embedding / LM-LSTM gradients), so the small launches do not queue behind the large ones."""
     key = str(torch.device(device))
     if not enabled:
         _WGRAD.pop(key, None)
         return None
     if key not in _WGRAD:
-        _WGRAD[key] = torch.cuda.Stream(device=device)
+        _WGRAD[key] = {"enc": torch.cuda.Stream(device=device), "dec": torch.cuda.Stream(device=device)}
     if _GEMM_MODE != 0:
-        ensure_workspace(device, stream=_WGRAD[key])
+        ensure_workspace(device, nbytes=1 << 30, stream=_WGRAD[key]["enc"])
+        ensure_workspace(device, nbytes=256 << 20, stream=_WGRAD[key]["dec"])
     return _WGRAD[key]
 
 
 def sync_wgrad_stream(device):
-    s = _WGRAD.get(str(torch.device(device)))
-    if s is not None:
-        torch.cuda.current_stream().wait_stream(s)
+    ss = _WGRAD.get(str(torch.device(device)))
+    if ss is not None:
+        for s in ss.values():
+            torch.cuda.current_stream().wait_stream(s)
 
 
 class BiLSTMLayerFn(torch.autograd.Function):
@@ -269,7 +273,7 @@ class BiLSTMLayerFn(torch.autograd.Function):
             dbp = colsum(G)
             return dWx, dWh, dbp
 
-        side = _WGRAD.get(str(dev))
+        side = _WGRAD.get(str(dev), {}).get("enc")
         dst = ctx.grad_dst
         if side is not None and all(d is not None for d in dst) and all(ctx.needs_input_grad[1:5]):
             main = torch.cuda.current_stream()
@@ -592,7 +596,7 @@ class AttnDecoderFnV2(torch.autograd.Function):
             return [demb, dattn_w, dattn_v, dlm_k, dlm_b, ddec_k, ddec_b, dq_k, dq_b, dap_k, dap_b, dout_k,
                     dout_b, din_k, din_b, dsp_k, dsp_b]
 
-        side = _WGRAD.get(str(dev))
+        side = _WGRAD.get(str(dev), {}).get("dec")
         dst = ctx.grad_dst
         need = [True] * 15 + [ctx.has_sp, ctx.has_sp]
         if (side is not None and all((d is not None) or (not n) for d, n in zip(dst, need))
