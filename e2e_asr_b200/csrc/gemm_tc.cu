@@ -408,9 +408,33 @@ void set_tc_debug(float* dbg, long long min_work) {
 }
 
 // Returns with *handled = false when the shape/alignment is not eligible (caller falls back to FFMA).
+// x_lo = x - (x with the low 13 mantissa bits cleared): the "small" half of the 3xTF32 split.  The "big" half
+// needs no copy: kind::tf32 ignores the low 13 bits of its operands (measured), so the raw fp32 tensor serves.
+__global__ void split_lo_kernel(size_t n4, const float4* __restrict__ x, float4* __restrict__ lo) {
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
+        const float4 v = x[i];
+        float4 o;
+        o.x = v.x - __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u);
+        o.y = v.y - __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u);
+        o.z = v.z - __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u);
+        o.w = v.w - __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u);
+        lo[i] = o;
+    }
+}
+int split_lo(cudaStream_t st, size_t n, const float* x, float* lo) {
+    E2E_REQUIRE(n % 4 == 0 && ((uintptr_t)x & 15) == 0 && ((uintptr_t)lo & 15) == 0,
+                "split_lo: buffers must be 16-byte aligned with a multiple of 4 elements");
+    if (n == 0) return 0;
+    split_lo_kernel<<<(unsigned)min((size_t)148 * 8, (n / 4 + 255) / 256), 256, 0, st>>>(n / 4, (const float4*)x, (float4*)lo);
+    E2E_LAUNCH_CHECK();
+    return 0;
+}
+
+// A_lo / B_lo (optional, tf32x3 mode): precomputed split_lo() of the operand with the operand's own layout.  When
+// given (and TMA-addressable) the operand's pre-pass is skipped: the tensor maps point at the caller's buffers.
 int gemm_tc(cudaStream_t st, int mode, int transA, int transB, int M, int N, int K, const float* A, int lda,
             const float* B, int ldb, float* C, int ldc, const float* bias, const float* Z, int ldz, int accumulate,
-            bool* handled) {
+            bool* handled, const float* A_lo, const float* B_lo) {
     *handled = false;
     if (mode != 1 && mode != 2) return 0;
     const bool bf16 = mode == 2;
@@ -428,22 +452,36 @@ int gemm_tc(cudaStream_t st, int mode, int transA, int transB, int M, int N, int
     const size_t a_ld = (a_cols + eper - 1) / eper * eper, b_ld = (b_cols + eper - 1) / eper * eper;
     const size_t esz = bf16 ? 2 : 4, nparts = bf16 ? 1 : 2;
     size_t a_bytes = (a_rows * a_ld * esz + 1023) / 1024 * 1024, b_bytes = (b_rows * b_ld * esz + 1023) / 1024 * 1024;
+    // operands whose split the caller already holds: used in place when TMA can address them
+    auto direct_ok = [&](const float* x, const float* lo, int ld) {
+        return !bf16 && lo != nullptr && ld % 4 == 0 && ((uintptr_t)x & 15) == 0 && ((uintptr_t)lo & 15) == 0;
+    };
+    const bool a_direct = direct_ok(A, A_lo, lda), b_direct = direct_ok(B, B_lo, ldb);
+    if (a_direct) a_bytes = 0;
+    if (b_direct) b_bytes = 0;
     if (nparts * (a_bytes + b_bytes) > ws_bytes) return 0;
     uint8_t* ws = (uint8_t*)ws_ptr;
     void* A0 = ws;
     void* A1 = ws + a_bytes;
     void* B0 = ws + nparts * a_bytes;
     void* B1 = ws + nparts * a_bytes + b_bytes;
+    size_t a_ld_eff = a_ld, b_ld_eff = b_ld;
+    if (a_direct) { A0 = const_cast<float*>(A); A1 = const_cast<float*>(A_lo); a_ld_eff = lda; }
+    if (b_direct) { B0 = const_cast<float*>(B); B1 = const_cast<float*>(B_lo); b_ld_eff = ldb; }
     if (bf16) {
         cvt_bf16_kernel<<<cdiv(a_rows * (a_ld / 8), 256), 256, 0, st>>>(a_rows, (int)a_cols, A, lda, (__nv_bfloat16*)A0, (int)a_ld);
         E2E_LAUNCH_CHECK();
         cvt_bf16_kernel<<<cdiv(b_rows * (b_ld / 8), 256), 256, 0, st>>>(b_rows, (int)b_cols, B, ldb, (__nv_bfloat16*)B0, (int)b_ld);
         E2E_LAUNCH_CHECK();
     } else {
-        split_tf32_kernel<<<cdiv(a_rows * (a_ld / 4), 256), 256, 0, st>>>(a_rows, (int)a_cols, A, lda, (float*)A0, (float*)A1, (int)a_ld);
-        E2E_LAUNCH_CHECK();
-        split_tf32_kernel<<<cdiv(b_rows * (b_ld / 4), 256), 256, 0, st>>>(b_rows, (int)b_cols, B, ldb, (float*)B0, (float*)B1, (int)b_ld);
-        E2E_LAUNCH_CHECK();
+        if (!a_direct) {
+            split_tf32_kernel<<<cdiv(a_rows * (a_ld / 4), 256), 256, 0, st>>>(a_rows, (int)a_cols, A, lda, (float*)A0, (float*)A1, (int)a_ld);
+            E2E_LAUNCH_CHECK();
+        }
+        if (!b_direct) {
+            split_tf32_kernel<<<cdiv(b_rows * (b_ld / 4), 256), 256, 0, st>>>(b_rows, (int)b_cols, B, ldb, (float*)B0, (float*)B1, (int)b_ld);
+            E2E_LAUNCH_CHECK();
+        }
     }
     const int bke = bf16 ? 64 : 32;           // elements per 128-byte span
     // A: K-major when the stored matrix is [M][K] (not transposed); B: K-major when stored [N][K] (transposed)
@@ -451,11 +489,11 @@ int gemm_tc(cudaStream_t st, int mode, int transA, int transB, int M, int N, int
     CUtensorMap mA0, mA1, mB0, mB1;
     bool ok = true;
     const bool a32 = !bf16 && a_mn, b32 = !bf16 && b_mn;      // tf32 MN-major: 32-byte-atom swizzle
-    ok &= make_map(&mA0, bf16, A0, a_rows, a_cols, a_ld, bke, a_mn ? bke : TBM, a32);
-    ok &= make_map(&mB0, bf16, B0, b_rows, b_cols, b_ld, bke, b_mn ? bke : TBN, b32);
+    ok &= make_map(&mA0, bf16, A0, a_rows, a_cols, a_ld_eff, bke, a_mn ? bke : TBM, a32);
+    ok &= make_map(&mB0, bf16, B0, b_rows, b_cols, b_ld_eff, bke, b_mn ? bke : TBN, b32);
     if (!bf16) {
-        ok &= make_map(&mA1, bf16, A1, a_rows, a_cols, a_ld, bke, a_mn ? bke : TBM, a32);
-        ok &= make_map(&mB1, bf16, B1, b_rows, b_cols, b_ld, bke, b_mn ? bke : TBN, b32);
+        ok &= make_map(&mA1, bf16, A1, a_rows, a_cols, a_ld_eff, bke, a_mn ? bke : TBM, a32);
+        ok &= make_map(&mB1, bf16, B1, b_rows, b_cols, b_ld_eff, bke, b_mn ? bke : TBN, b32);
     } else {
         mA1 = mA0;
         mB1 = mB0;

@@ -82,7 +82,18 @@ def to_i32(t, device):
     return r
 
 
-def gemm(a, b, out=None, ta=False, tb=False, bias=None, z=None, accumulate=False, mode=None):
+def split_lo(x):
+    """The "small" half of the 3xTF32 split of a contiguous tensor (x - tf32_trunc(x)), or None when the GEMM mode
+    does not use it.  Views of the result, taken like the views of x, are passed to gemm(..., a_lo= / b_lo=) so one
+    pass serves every product the tensor enters."""
+    if _GEMM_MODE != 1 or x.numel() % 4 != 0 or not x.is_contiguous():
+        return None
+    lo = torch.empty_like(x)
+    call("e2e_split_lo", x.numel(), x, lo)
+    return lo
+
+
+def gemm(a, b, out=None, ta=False, tb=False, bias=None, z=None, accumulate=False, mode=None, a_lo=None, b_lo=None):
     """out = op(a) @ op(b) (+bias) (+z) (+out).  2-D tensors with unit inner stride;
     the leading dimension is the row stride, so column-sliced views work."""
     assert a.dim() == 2 and b.dim() == 2 and a.stride(1) == 1 and b.stride(1) == 1
@@ -103,9 +114,15 @@ def gemm(a, b, out=None, ta=False, tb=False, bias=None, z=None, accumulate=False
     mode = _GEMM_MODE if mode is None else mode
     if mode != 0 and str(a.device) not in _workspace:
         ensure_workspace(a.device)
+    tag = ("gemm M=%d N=%d K=%d t%d%d" % (M, N, K, ta, tb)) if TAG_GEMM_SHAPES else "e2e_gemm"
+    if mode == 1 and (a_lo is not None or b_lo is not None):
+        assert a_lo is None or (a_lo.shape == a.shape and a_lo.stride() == a.stride())
+        assert b_lo is None or (b_lo.shape == b.shape and b_lo.stride() == b.stride())
+        call("e2e_gemm_lo", mode, int(ta), int(tb), M, N, K, a, a_lo, lda, b, b_lo, ldb, out, ldc,
+             bias, z, ldz, int(accumulate), work=2.0 * M * N * K, tag=tag)
+        return out
     call("e2e_gemm", mode, int(ta), int(tb), M, N, K, a, lda, b, ldb, out, ldc,
-         bias, z, ldz, int(accumulate), work=2.0 * M * N * K,
-         tag=("gemm M=%d N=%d K=%d t%d%d" % (M, N, K, ta, tb)) if TAG_GEMM_SHAPES else None)
+         bias, z, ldz, int(accumulate), work=2.0 * M * N * K, tag=tag)
     return out
 
 
@@ -239,12 +256,15 @@ class BiLSTMLayerFn(torch.autograd.Function):
         st = _dev_state(dev)
         Wx, Wh, bp = _pack_lstm([k_fw, k_bw], [b_fw, b_bw], I, H, dev)
         x2 = x.view(B * Tp, I)
-        G = gemm(x2, Wx, bias=bp)                                   # [B*Tp, 8H]
+        # 3xTF32 "small" halves, computed once per tensor and shared by every product it enters (fwd + bwd)
+        x_lo, Wx_lo = split_lo(x2), split_lo(Wx)
+        G = gemm(x2, Wx, bias=bp, a_lo=x_lo, b_lo=Wx_lo)            # [B*Tp, 8H]
         out = torch.zeros((B, Tp, 2 * H), dtype=torch.float32, device=dev)
         Cst = torch.empty((B, Tp, 2, H), dtype=torch.float32, device=dev)
         call("e2e_lstm_rec_fwd", B, T, Tp, H, 2, Tp, 1, G, out, Cst, Wh, lens_i32, st["ctr"],
              st["ctr"].numel() * 4, st["err"], work=float(T), tag="enc_rec_fwd")
         ctx.save_for_backward(x, Wx, Wh, G, Cst, out, lens_i32)
+        ctx.los = (x_lo, Wx_lo)
         ctx.dims = (B, Tp, I, H, T)
         # flat-gradient-buffer views of the four parameters (None for plain tensors)
         ctx.grad_dst = tuple(getattr(t, "grad", None) for t in (k_fw, b_fw, k_bw, b_bw))
@@ -261,15 +281,19 @@ class BiLSTMLayerFn(torch.autograd.Function):
              st["ctr"].numel() * 4, st["err"], work=float(T), tag="enc_rec_bwd")   # G now holds d(pre-activations)
         N = B * Tp
         x2, o2 = x.view(N, I), out.view(N, 2 * H)
-        dX = gemm(G, Wx, tb=True).view(B, Tp, I) if ctx.needs_input_grad[0] else None
+        x_lo, Wx_lo = ctx.los
+        G_lo = split_lo(G)            # one split of dz serves the dX, dW_x and both dW_h products
+        dX = gemm(G, Wx, tb=True, a_lo=G_lo, b_lo=Wx_lo).view(B, Tp, I) if ctx.needs_input_grad[0] else None
 
         def weight_grads():
-            dWx = gemm(x2, G, ta=True)                                  # [I, 8H]
+            dWx = gemm(x2, G, ta=True, a_lo=x_lo, b_lo=G_lo)            # [I, 8H]
             dWh = torch.empty((2, H, 4 * H), dtype=torch.float32, device=dev)
             # h_{t-1}^T dz_t: fw pairs out[t-1] with dz[t], bw pairs out[t+1] with dz[t]; the flat
             # one-row shift never crosses an utterance because out[b, Tp-1] == 0 and dz[b, Tp-1] == 0.
-            gemm(o2[:N - 1, 0:H], G[1:, 0:4 * H], ta=True, out=dWh[0])
-            gemm(o2[1:, H:2 * H], G[:N - 1, 4 * H:8 * H], ta=True, out=dWh[1])
+            gemm(o2[:N - 1, 0:H], G[1:, 0:4 * H], ta=True, out=dWh[0],
+                 b_lo=None if G_lo is None else G_lo[1:, 0:4 * H])
+            gemm(o2[1:, H:2 * H], G[:N - 1, 4 * H:8 * H], ta=True, out=dWh[1],
+                 b_lo=None if G_lo is None else G_lo[:N - 1, 4 * H:8 * H])
             dbp = colsum(G)
             return dWx, dWh, dbp
 
@@ -283,8 +307,9 @@ class BiLSTMLayerFn(torch.autograd.Function):
                 for d in range(2):      # += into the flat gradient buffer (what AccumulateGrad would do)
                     call("e2e_lstm_unpack_grads", I, H, dst[2 * d], dst[2 * d + 1], dWx, 8 * H, d * 4 * H, dWh[d],
                          dbp, 1)
-            for t_ in (x, G, out):
-                t_.record_stream(side)
+            for t_ in (x, G, out, x_lo, G_lo):
+                if t_ is not None:
+                    t_.record_stream(side)
             return dX, None, None, None, None, None, None
         dWx, dWh, dbp = weight_grads()
         dk_fw, db_fw, dk_bw, db_bw = _unpack_lstm(dWx, dWh, dbp, I, H, 2, dev)

@@ -43,6 +43,14 @@ unsigned long long e2e_launch_count(int reset);
 int e2e_gemm(void* stream, int mode, int transA, int transB, int M, int N, int K,
              const float* A, int lda, const float* B, int ldb, float* C, int ldc,
              const float* bias, const float* Z, int ldz, int accumulate);
+/* e2e_gemm with the caller holding the "small" half of the 3xTF32 split of an operand (either may be NULL):
+ * X_lo = e2e_split_lo(X), same layout as X.  An operand with X_lo given, ld % 4 == 0 and 16-byte aligned
+ * pointers skips its pre-pass (the tensor core ignores the low 13 mantissa bits of the raw fp32 "big" half).
+ * Lets one split of dz serve the dX, dW_x and dW_h products of a layer. */
+int e2e_gemm_lo(void* stream, int mode, int transA, int transB, int M, int N, int K, const float* A,
+                const float* A_lo, int lda, const float* B, const float* B_lo, int ldb, float* C, int ldc,
+                const float* bias, const float* Z, int ldz, int accumulate);
+int e2e_split_lo(void* stream, size_t n, const float* x, float* lo);   /* lo[i] = x[i] - tf32_trunc(x[i]) */
 
 /* Scratch for the tensor-core modes' operand pre-pass (TF32 big/small split or
  * bf16 copies): a caller-owned device buffer; GEMMs whose operands do not fit run
