@@ -71,6 +71,7 @@ int axpy(cudaStream_t, size_t, float, const float*, float*);
 int adam_update(cudaStream_t, size_t, float*, const float*, float*, float*, float, float, float, float);
 int dropout(cudaStream_t, size_t, const float*, float*, float, unsigned long long, unsigned);
 int dec_persist(cudaStream_t, bool, const e2e_dec_persist_args*, float*, float*, float*);
+int dec_persist_fits(const e2e_dec_persist_args*);
 int gemm_f64(cudaStream_t, int, int, int, const double*, int, const float*, int, double*, int, const float*);
 int lstm_step_f64(cudaStream_t, int, int, const double*, const double*, double*, double*, int);
 int attn_beam_f64(cudaStream_t, int, int, int, int, const float*, const float*, const int*, const int*, const double*,
@@ -252,6 +253,7 @@ int e2e_decoder_loop_bwd(void* stream, const e2e_dec_loop_bwd_args* g) {
     return 0;
 }
 
+int e2e_decoder_persist_fits(const e2e_dec_persist_args* a) { return dec_persist_fits(a); }
 int e2e_decoder_persist_fwd(void* stream, const e2e_dec_persist_args* a) {
     return dec_persist(ST(stream), false, a, nullptr, nullptr, nullptr);
 }

@@ -1060,6 +1060,16 @@ static int bwd_attn_fast(const e2e_dec_persist_args& p, size_t* smem) {
     return 1;
 }
 
+// 1 when both persistent kernels fit the 227 KB of shared memory for these shapes (else the caller uses the
+// per-step kernels of decoder.cu): e.g. cfg-5's D = 1024 needs 280 KB for the W_ch^T slice + [ctx|h] tile.
+int dec_persist_fits(const e2e_dec_persist_args* a) {
+    const e2e_dec_persist_args& p = *a;
+    if (p.Hd % 8 != 0 || p.A % 8 != 0 || p.D % 8 != 0) return 0;
+    if (!(2 * p.A + p.Tn + 32 + 4 * p.D <= 16 * (p.D + p.Hd + 4) && 10 * p.A + p.D + p.Tn + 16 <= 16 * (4 * p.Hd + 4)))
+        return 0;
+    return fwd_smem_bytes(p) <= 227 * 1024 && bwd_smem_bytes(p) <= 227 * 1024;
+}
+
 int dec_persist(cudaStream_t st, bool bwd, const e2e_dec_persist_args* a, float* denc, float* dHF, float* dv_part) {
     e2e_dec_persist_args p = *a;
     E2E_REQUIRE(p.Hd % 8 == 0 && p.A % 8 == 0 && p.D % 8 == 0, "decoder_persist: Hd, A, D must be multiples of 8");

@@ -5,6 +5,8 @@ graph between modules only; every FLOP of the hot path runs in
 libe2e_asr_b200.so.  There is no eager/CPU fallback.
 """
 import numpy as np
+import ctypes
+
 import torch
 
 from . import _lib
@@ -459,8 +461,16 @@ def set_decoder_impl(name):
     _DECODER_IMPL = name
 
 
+def _persist_fits(enc, dec_k, q_k, U):
+    a = _lib.DecPersistArgs()
+    a.B, a.Tn, a.D = enc.shape
+    a.U, a.Hd, a.A, a.Tp = int(U), dec_k.shape[1] // 4, q_k.shape[1], flat_rows(enc)[1]
+    return bool(_lib.lib().e2e_decoder_persist_fits(ctypes.addressof(a)))
+
+
 def attn_decoder_apply(*args, lm_drop=None):
-    if _DECODER_IMPL == "persist":
+    # args: enc, emb, attn_w, attn_v, lm_k, lm_b, dec_k, dec_b, q_k, ...
+    if _DECODER_IMPL == "persist" and _persist_fits(args[0], args[6], args[8], args[21]):
         return AttnDecoderFnV2.apply(*(args + (lm_drop,)))
     if lm_drop is not None:
         raise NotImplementedError("decoder dropout is served by the persistent decoder kernels only")

@@ -27,6 +27,9 @@ CONFIGS = {
                  ctc={"phone_ctc": (3, 5), "state": (2, 9)}),
     "tiny_b": dict(B=5, T=37, F=12, H=16, L=4, V=23, U=9, E=12, A=8, Hd=16, Hl=8,
                    ctc={"phone_ctc": (3, 6)}),
+    # wide_small: cfg-5's widths at unit-test size (H=512 -> L2-exchange recurrence, D=1024 -> per-step decoder)
+    "wide_small": dict(B=3, T=24, F=8, H=512, L=2, V=17, U=5, E=16, A=16, Hd=32, Hl=16,
+                       ctc={"phone_ctc": (1, 5)}),
     # cfg-1: base_params defaults, CPU parity
     "cfg1": dict(B=4, T=200, F=40, H=256, L=4, V=1000, U=25, E=256, A=128,
                  Hd=256, Hl=256, ctc={"phone_ctc": (3, 48)}),

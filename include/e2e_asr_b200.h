@@ -181,6 +181,9 @@ typedef struct {
     unsigned* ctr;         /* 1 counter of scratch */
     int* err;              /* barrier-timeout flag */
 } e2e_dec_persist_args;
+/* 1 if the shapes in `a` (B, U, Hd, A, D, Tn, Tp; pointers unused) fit the persistent kernels' shared memory,
+ * else 0: the caller then runs the per-step kernels (e2e_decoder_loop_fwd/bwd). */
+int e2e_decoder_persist_fits(const e2e_dec_persist_args* a);
 int e2e_decoder_persist_fwd(void* stream, const e2e_dec_persist_args* a);
 /* also accumulates denc [B,Tp,D] += sum_t alpha_t dctx_t, writes dHF [B,Tp,A] (z) and dv_part [B*Tn, A] */
 int e2e_decoder_persist_bwd(void* stream, const e2e_dec_persist_args* a, float* denc, float* dHF, float* dv_part);

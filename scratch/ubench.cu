@@ -44,6 +44,57 @@ __global__ void __launch_bounds__(256, 1) mma_rate_kernel(float* out, long long*
     if (threadIdx.x == 0 && blockIdx.x == 0) *cyc = t1 - t0;
 }
 
+// mixed tf32 / bf16 issue patterns: PAT 0 = TTBB TTBB (the recurrence k-loop), 1 = TBTB, 2 = 8T then 8B
+template <int PAT>
+__global__ void __launch_bounds__(256, 1) mma_mix_kernel(float* out, long long* cyc, int iters) {
+    float d[4][4];
+    for (int i = 0; i < 4; ++i) for (int j = 0; j < 4; ++j) d[i][j] = 0.f;
+    uint32_t a[4] = {threadIdx.x, threadIdx.x * 3u, 7u, 9u}, b[2] = {threadIdx.x * 5u, 11u};
+#define TMMA(c) asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};" \
+                             : "+f"(d[c][0]), "+f"(d[c][1]), "+f"(d[c][2]), "+f"(d[c][3]) : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]))
+#define BMMA(c) asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};" \
+                             : "+f"(d[c][0]), "+f"(d[c][1]), "+f"(d[c][2]), "+f"(d[c][3]) : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]))
+    __syncthreads();
+    long long t0 = clock64();
+    for (int it = 0; it < iters; ++it) {
+        if (PAT == 0) { TMMA(0); TMMA(1); BMMA(2); BMMA(3); TMMA(0); TMMA(1); BMMA(2); BMMA(3); }
+        if (PAT == 1) { TMMA(0); BMMA(2); TMMA(1); BMMA(3); TMMA(0); BMMA(2); TMMA(1); BMMA(3); }
+        if (PAT == 2) { TMMA(0); TMMA(1); TMMA(0); TMMA(1); BMMA(2); BMMA(3); BMMA(2); BMMA(3); }
+    }
+    long long t1 = clock64();
+    float s = 0.f;
+    for (int i = 0; i < 4; ++i) for (int j = 0; j < 4; ++j) s += d[i][j];
+    out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+    if (threadIdx.x == 0 && blockIdx.x == 0) *cyc = t1 - t0;
+}
+
+// realistic operand traffic: 32 distinct B fragments and 4 distinct A fragments held in registers
+__global__ void __launch_bounds__(256, 1) mma_regs_kernel(const uint32_t* src, float* out, long long* cyc, int iters) {
+    float d[4][4];
+    for (int i = 0; i < 4; ++i) for (int j = 0; j < 4; ++j) d[i][j] = 0.f;
+    uint32_t a[4][4], b[32][2];
+    for (int i = 0; i < 4; ++i) for (int j = 0; j < 4; ++j) a[i][j] = src[(threadIdx.x * 16 + i * 4 + j) % 4096];
+    for (int i = 0; i < 32; ++i) for (int j = 0; j < 2; ++j) b[i][j] = src[(threadIdx.x * 64 + i * 2 + j + 7) % 4096];
+    __syncthreads();
+    long long t0 = clock64();
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+#define TM(c, ai, bi) asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};" \
+                             : "+f"(d[c][0]), "+f"(d[c][1]), "+f"(d[c][2]), "+f"(d[c][3]) : "r"(a[ai][0]), "r"(a[ai][1]), "r"(a[ai][2]), "r"(a[ai][3]), "r"(b[bi][0]), "r"(b[bi][1]))
+#define BM(c, ai, bi) asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};" \
+                             : "+f"(d[c][0]), "+f"(d[c][1]), "+f"(d[c][2]), "+f"(d[c][3]) : "r"(a[ai][0]), "r"(a[ai][1]), "r"(a[ai][2]), "r"(a[ai][3]), "r"(b[bi][0]), "r"(b[bi][1]))
+            TM(0, 0, 4 * k + 0); TM(1, 0, 4 * k + 1); BM(2, 1, 4 * k + 2); BM(3, 1, 4 * k + 3);
+            TM(0, 2, 4 * k + 1); TM(1, 2, 4 * k + 0); BM(2, 3, 4 * k + 3); BM(3, 3, 4 * k + 2);
+        }
+    }
+    long long t1 = clock64();
+    float s = 0.f;
+    for (int i = 0; i < 4; ++i) for (int j = 0; j < 4; ++j) s += d[i][j];
+    out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+    if (threadIdx.x == 0 && blockIdx.x == 0) *cyc = t1 - t0;
+}
+
 // ------------------------------------------------------------------ 2. tcgen05 TS
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(s_u32(bar)), "r"(count));
@@ -392,6 +443,22 @@ int main() {
         // 8 warps / CTA = 2 per SMSP, 4 MMAs per iter per warp
         printf("mma.sync %s: %.2f cycles per MMA per SMSP (2 warps/SMSP, 4 independent chains)\n", kind == 0 ? "m16n8k8 tf32" : "m16n8k16 bf16",
                (double)c / (iters * 4 * 2));
+    }
+    for (int pat = 0; pat < 3; ++pat) {
+        const int iters = 2000;
+        if (pat == 0) mma_mix_kernel<0><<<148, 256>>>(d_out, d_cyc, iters);
+        if (pat == 1) mma_mix_kernel<1><<<148, 256>>>(d_out, d_cyc, iters);
+        if (pat == 2) mma_mix_kernel<2><<<148, 256>>>(d_out, d_cyc, iters);
+        CK(cudaDeviceSynchronize());
+        long long c; CK(cudaMemcpy(&c, d_cyc, 8, cudaMemcpyDeviceToHost));
+        printf("mma.sync mixed pattern %d: %.2f cycles per MMA per SMSP\n", pat, (double)c / (iters * 8 * 2));
+    }
+    {
+        uint32_t* d_src; CK(cudaMalloc(&d_src, 4096 * 4)); CK(cudaMemset(d_src, 0x3c, 4096 * 4));
+        mma_regs_kernel<<<148, 256>>>(d_src, d_out, d_cyc, 500);
+        CK(cudaDeviceSynchronize());
+        long long c; CK(cudaMemcpy(&c, d_cyc, 8, cudaMemcpyDeviceToHost));
+        printf("mma.sync 32 distinct B fragments in registers: %.2f cycles per MMA per SMSP\n", (double)c / (500 * 64 * 2));
     }
     run_ts<16>();
     run_ts<32>();

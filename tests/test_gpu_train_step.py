@@ -13,7 +13,8 @@ pytestmark = pytest.mark.gpu
 RTOL = 1e-4    # north-star tolerance for fp32 losses / logits / gradients
 
 
-@pytest.mark.parametrize("cname,ctc", [("tiny", True), ("tiny_b", True), ("tiny", False), ("cfg1", True)])
+@pytest.mark.parametrize("cname,ctc", [("tiny", True), ("tiny_b", True), ("tiny", False), ("cfg1", True),
+                                       ("wide_small", True)])
 def test_train_step_matches_oracle(cname, ctc):
     cfg = synth.get_config(cname)
     w = synth.make_weights(cfg, bias_noise=0.1)
