@@ -161,6 +161,7 @@ def main():
     ap.add_argument("--config", default="cfg2")
     ap.add_argument("--gemm", default="tf32x3", help="fp32 | tf32x3 | bf16 (default: tf32x3, the fp32-accurate tensor-core mode)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-beam", action="store_true", help="skip the beam-decode utt/s side measurement")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -327,8 +328,46 @@ def main():
             "sample": "%s shapes, batch %d of %d utterances (%d valid frames), float32 NumPy restatement "
                       "(oracle/model.py), mean of 2 steps after 1 warm-up, %.1f s/step"
                       % (args.config, sample_B, cfg.B, fr, sec)}
+    if world == 1 and not args.no_beam and args.config == "cfg2":
+        line["beam_decode"] = beam_decode_rate(args.config, dev, cpu=not args.no_cpu_baseline)
     print(json.dumps(line))
     sys.stdout.flush()
+
+
+def beam_decode_rate(cfg_name, dev, n_utts=256, beam=10, cpu=True):
+    """Second half of BASELINE.json's metric: beam-search decoding (BASELINE configs[2]: beam width 10, a synthetic
+    eval batch of 256 utterances with T_enc in [50, 88]) in utterances/s through BeamSearch.decode_batch, next to the
+    CPU restatement of beam_search.py (serial over utterances like eval_model.py:194-195) on ONE utterance."""
+    import torch
+    from e2e_asr_b200 import synth
+    from e2e_asr_b200.beam_search import BeamSearch
+    cfg = synth.get_config(cfg_name)
+    w = synth.make_weights(cfg)
+    rng = np.random.Generator(np.random.PCG64(17))
+    encs = [(np.tanh(rng.standard_normal((int(rng.integers(50, 89)), 2 * cfg.H))) * 0.8).astype(np.float32)
+            for _ in range(n_utts)]
+    sp = BeamSearch.class_params()
+    sp.beam_size = beam
+    bs = BeamSearch(w, sp, device=dev)
+    bs.decode_batch(encs[:8])
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    out = bs.decode_batch(encs)
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    res = {"value": n_utts / dt, "unit": "utt/s", "beam_size": beam, "n_utts": n_utts,
+           "mean_output_len": float(np.mean([len(o) for o in out])),
+           "note": "random-init weights: hypotheses run to the 120-step limit (worst case); wall clock incl. the "
+                   "host-side k^2 candidate merge"}
+    if cpu:
+        from oracle import beam as ob
+        t0 = time.perf_counter()
+        ref = ob.beam_search(w, encs[0], beam_size=beam)
+        dt1 = time.perf_counter() - t0
+        res["cpu_baseline"] = {"value": 1.0 / dt1, "unit": "utt/s", "cores": 1, "kind": "port",
+                               "sample": "1 utterance, Python restatement of beam_search.py (oracle/beam.py)",
+                               "ids_equal": bool(np.array_equal(ref, out[0]))}
+    return res
 
 
 if __name__ == "__main__":
