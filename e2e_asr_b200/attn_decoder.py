@@ -67,7 +67,8 @@ class AttnDecoder(Decoder):
         U = int(lens_host.max()) if len(lens_host) else 0        # raw_rnn stops when all rows are finished
         lens = ops.to_i32(seq_len, dev)
         enc_len = ops.to_i32(seq_len_inp, dev)
-        if self.input_rule() == "teacher":
+        rule = self.input_rule()
+        if rule in ("teacher", "sample"):
             # DropoutWrapper(output_keep_prob=out_prob_dec) iff training (decoder.py:60-63) acts on lm_cell's
             # output only: raw_loop_function reads the decoder cell through get_state(state) = state.c and never
             # uses cell_output (attn_decoder.py:114-118), so the decoder-LSTM wrapper has no effect on the result.
@@ -75,6 +76,14 @@ class AttnDecoder(Decoder):
             if self.isTraining and self.params.out_prob_dec < 1.0:
                 lm_drop = (self.params.out_prob_dec, getattr(self, "dropout_seed", 0),
                            100 + getattr(self, "dropout_stream", 0))
+            if rule == "sample":
+                # scheduled sampling: realise the input ids without a tape, then take the teacher-forced step on them
+                from .inference import sample_decode_ids
+                with torch.no_grad():
+                    ids = sample_decode_ids(v, decoder_inp, lens, U, enc.detach(), enc_len, self.params.samp_prob,
+                                            getattr(self, "dropout_seed", 0), getattr(self, "dropout_stream", 0),
+                                            lm_drop=lm_drop)
+                decoder_inp = self.stash["realized_ids"] = ids
             return ops.attn_decoder_apply(
                 enc, v["emb"], v["attn_w"], v["attn_v"], v["lm_k"], v["lm_b"], v["dec_k"], v["dec_b"], v["q_k"],
                 v["q_b"], v["ap_k"], v["ap_b"], v["out_k"], v["out_b"], v["in_k"], v["in_b"], v["sp_k"], v["sp_b"],

@@ -69,7 +69,8 @@ int scale_inplace(cudaStream_t, size_t, float*, const float*, float);
 int mean_vec(cudaStream_t, int, const float*, float*);
 int axpy(cudaStream_t, size_t, float, const float*, float*);
 int adam_update(cudaStream_t, size_t, float*, const float*, float*, float*, float, float, float, float);
-int dropout(cudaStream_t, size_t, const float*, float*, float, unsigned long long, unsigned);
+int dropout(cudaStream_t, size_t, const float*, float*, float, unsigned long long, unsigned, size_t);
+int sample_rows(cudaStream_t, int, int, const float*, int, unsigned long long, unsigned, unsigned, long long*);
 int dec_persist(cudaStream_t, bool, const e2e_dec_persist_args*, float*, float*, float*);
 int dec_persist_fits(const e2e_dec_persist_args*);
 int gemm_f64(cudaStream_t, int, int, int, const double*, int, const float*, int, double*, int, const float*);
@@ -310,8 +311,12 @@ int e2e_adam(void* stream, size_t n, float* param, const float* grad, float* m, 
     return adam_update(ST(stream), n, param, grad, m, v, lr_t, beta1, beta2, eps);
 }
 int e2e_dropout(void* stream, size_t n, const float* x, float* y, float keep, unsigned long long seed,
-                unsigned offset) {
-    return dropout(ST(stream), n, x, y, keep, seed, offset);
+                unsigned offset, size_t first) {
+    return dropout(ST(stream), n, x, y, keep, seed, offset, first);
+}
+int e2e_sample_rows(void* stream, int rows, int V, const float* logits, int ldl, unsigned long long seed,
+                    unsigned offset, unsigned first_row, long long* out) {
+    return sample_rows(ST(stream), rows, V, logits, ldl, seed, offset, first_row, out);
 }
 
 int e2e_gemm_f64(void* stream, int M, int N, int K, const double* A, int lda, const float* B, int ldb, double* C,

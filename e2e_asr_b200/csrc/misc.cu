@@ -178,11 +178,12 @@ __device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t
     out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
 }
 __global__ void dropout_kernel(size_t n, const float* __restrict__ x, float* __restrict__ y, float keep,
-                               unsigned long long seed, unsigned offset) {
+                               unsigned long long seed, unsigned offset, size_t first4) {
     const float inv = 1.0f / keep;
     for (size_t q = blockIdx.x * (size_t)blockDim.x + threadIdx.x; q * 4 < n; q += (size_t)gridDim.x * blockDim.x) {
         uint32_t r[4];
-        philox4x32_10((uint32_t)q, offset, (uint32_t)(q >> 32), 0u, (uint32_t)seed, (uint32_t)(seed >> 32), r);
+        const size_t qg = q + first4;       // counter = global quad index: a slice of a buffer draws the buffer's mask
+        philox4x32_10((uint32_t)qg, offset, (uint32_t)(qg >> 32), 0u, (uint32_t)seed, (uint32_t)(seed >> 32), r);
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             const size_t i = q * 4 + j;
@@ -191,10 +192,56 @@ __global__ void dropout_kernel(size_t n, const float* __restrict__ x, float* __r
     }
 }
 int dropout(cudaStream_t st, size_t n, const float* x, float* y, float keep, unsigned long long seed,
-            unsigned offset) {
+            unsigned offset, size_t first) {
     E2E_REQUIRE(keep > 0.f && keep <= 1.f, "dropout: keep probability %f out of (0, 1]", keep);
+    E2E_REQUIRE(first % 4 == 0, "dropout: the slice must start at a multiple of 4 elements (got %zu)", first);
     if (n == 0) return 0;
-    dropout_kernel<<<min((size_t)SUMSQ_BLOCKS * 8, (n / 4 + 256) / 256), 256, 0, st>>>(n, x, y, keep, seed, offset);
+    dropout_kernel<<<min((size_t)SUMSQ_BLOCKS * 8, (n / 4 + 256) / 256), 256, 0, st>>>(n, x, y, keep, seed, offset,
+                                                                                        first / 4);
+    E2E_LAUNCH_CHECK();
+    return 0;
+}
+
+// ---- scheduled sampling: tf.multinomial(logits, 1) (decoder.py:155-180) with the builder-defined Philox stream ----
+// Row r draws u = word0(philox(counter = (first_row + r, offset, 0, 0), key = seed)) * 2^-32 and takes the first
+// index whose inclusive cumulative sum of exp(logit - max) (float64, index order) exceeds u * total.
+// One warp per row; lane l scans the contiguous chunk [l*ch, (l+1)*ch).
+__global__ void sample_rows_kernel(int rows, int V, const float* __restrict__ logits, int ldl, unsigned long long seed,
+                                   unsigned offset, unsigned first_row, long long* __restrict__ out) {
+    const int r = blockIdx.x * (blockDim.x / 32) + threadIdx.x / 32, lane = threadIdx.x % 32;
+    if (r >= rows) return;
+    const float* x = logits + (size_t)r * ldl;
+    float mx = -INFINITY;
+    for (int i = lane; i < V; i += 32) mx = fmaxf(mx, x[i]);
+    mx = warp_max(mx);
+    const int ch = (V + 31) / 32, i0 = lane * ch, i1 = min(V, i0 + ch);
+    double loc = 0.0;
+    for (int i = i0; i < i1; ++i) loc += exp((double)x[i] - (double)mx);
+    // inclusive scan of the lane sums (in lane = index order)
+    double inc = loc;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const double v = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += v;
+    }
+    const double total = __shfl_sync(0xffffffffu, inc, 31);
+    uint32_t w[4];
+    philox4x32_10(first_row + (unsigned)r, offset, 0u, 0u, (uint32_t)seed, (uint32_t)(seed >> 32), w);
+    const double target = (double)w[0] * 2.3283064365386963e-10 * total;
+    double cum = inc - loc;
+    int pick = V;                              // first index with cum > target, V if none in this chunk
+    for (int i = i0; i < i1; ++i) {
+        cum += exp((double)x[i] - (double)mx);
+        if (cum > target) { pick = i; break; }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) pick = min(pick, __shfl_xor_sync(0xffffffffu, pick, o));
+    if (lane == 0) out[r] = pick < V ? pick : V - 1;
+}
+int sample_rows(cudaStream_t st, int rows, int V, const float* logits, int ldl, unsigned long long seed,
+                unsigned offset, unsigned first_row, long long* out) {
+    if (rows <= 0) return 0;
+    sample_rows_kernel<<<cdiv(rows, 4), 128, 0, st>>>(rows, V, logits, ldl, seed, offset, first_row, out);
     E2E_LAUNCH_CHECK();
     return 0;
 }

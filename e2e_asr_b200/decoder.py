@@ -38,9 +38,8 @@ class Decoder(BaseParams):
             raise NotImplementedError("Decoder: num_layers_dec > 1 (MultiRNNCell, decoder.py:64-68) is not built yet")
         if not (0.0 < p.out_prob_dec <= 1.0):
             raise ValueError("Decoder: out_prob_dec=%g must be in (0, 1]" % p.out_prob_dec)
-        if self.isTraining and p.samp_prob > 0:
-            raise NotImplementedError("Decoder: scheduled sampling (samp_prob=%g, decoder.py:155-180) is not built "
-                                      "yet; parity and benchmark runs use samp_prob=0" % p.samp_prob)
+        if not (0.0 <= p.samp_prob <= 1.0):
+            raise ValueError("Decoder: samp_prob=%g must be in [0, 1]" % p.samp_prob)
 
     def get_state(self, state):
         """The attention query / projection input is the LSTM CELL state c of the

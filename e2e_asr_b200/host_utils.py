@@ -54,3 +54,16 @@ class BeamEntry(_Entry):
     get_dec_state = property(lambda self: (lambda: self.dec_state))
     get_context_vec = property(lambda self: (lambda: self.context_vec))
     get_cum_attn_probs = property(lambda self: (lambda: self.cum_attn_probs))
+
+
+def philox_uniform(counter, offset, seed):
+    """Word 0 of Philox4x32-10(counter=(counter, offset, 0, 0), key=(seed lo, seed hi)) * 2^-32: the host-side scalar
+    draw of the same counter-based generator the CUDA dropout / sampling kernels use (csrc/misc.cu)."""
+    M0, M1, W0, W1, MASK = 0xD2511F53, 0xCD9E8D57, 0x9E3779B9, 0xBB67AE85, 0xFFFFFFFF
+    c0, c1, c2, c3 = counter & MASK, offset & MASK, 0, 0
+    k0, k1 = seed & MASK, (seed >> 32) & MASK
+    for _ in range(10):
+        p0, p1 = M0 * c0, M1 * c2
+        c0, c1, c2, c3 = ((p1 >> 32) ^ c1 ^ k0) & MASK, p1 & MASK, ((p0 >> 32) ^ c3 ^ k1) & MASK, p0 & MASK
+        k0, k1 = (k0 + W0) & MASK, (k1 + W1) & MASK
+    return c0 * 2.0 ** -32

@@ -198,7 +198,7 @@ class DropoutFn(torch.autograd.Function):
     def forward(ctx, x, keep, seed, offset):
         x = x.contiguous()
         y = torch.empty_like(x)
-        call("e2e_dropout", x.numel(), x, y, float(keep), int(seed), int(offset))
+        call("e2e_dropout", x.numel(), x, y, float(keep), int(seed), int(offset), 0)
         ctx.cfg = (float(keep), int(seed), int(offset))
         return y
 
@@ -207,7 +207,7 @@ class DropoutFn(torch.autograd.Function):
         keep, seed, offset = ctx.cfg
         dy = dy.contiguous()
         dx = torch.empty_like(dy)
-        call("e2e_dropout", dy.numel(), dy, dx, keep, seed, offset)
+        call("e2e_dropout", dy.numel(), dy, dx, keep, seed, offset, 0)
         return dx, None, None, None
 
 
@@ -510,7 +510,7 @@ class AttnDecoderFnV2(torch.autograd.Function):
         hl_out = hl
         if lm_drop is not None:
             hl_out = torch.empty_like(hl)
-            call("e2e_dropout", hl.numel(), hl, hl_out, float(lm_drop[0]), int(lm_drop[1]), int(lm_drop[2]))
+            call("e2e_dropout", hl.numel(), hl, hl_out, float(lm_drop[0]), int(lm_drop[1]), int(lm_drop[2]), 0)
         m = gemm(hl_out, sp_k, bias=sp_b) if sp_k is not None else hl_out
         pre = gemm(m, in_k[:Hd], bias=in_b)                          # [U*B, E]
         # decoder-LSTM kernel in gate-interleaved layout, with the ctx half of InputProjection folded in
@@ -612,7 +612,7 @@ class AttnDecoderFnV2(torch.autograd.Function):
             if ctx.lm_drop is not None:
                 dmd = torch.empty_like(dm)
                 call("e2e_dropout", dm.numel(), dm.contiguous(), dmd, float(ctx.lm_drop[0]), int(ctx.lm_drop[1]),
-                     int(ctx.lm_drop[2]))
+                     int(ctx.lm_drop[2]), 0)
                 dm = dmd
             call("e2e_lstm_rec_bwd", B, U, U, Hl, 1, 1, B, G_lm, C_lm, Wh_lm, dm, lens_i32, ctr,
                  ctr.numel() * 4, st["err"], work=float(U), tag="lm_rec_bwd")

@@ -245,10 +245,17 @@ int e2e_adam(void* stream, size_t n, float* param, const float* grad, float* m, 
              float beta2, float eps);
 
 /* DropoutWrapper(output_keep_prob=keep) on a recurrent cell's outputs (encoder.py:50-52, decoder.py:60-63):
- * y[i] = x[i] / keep if philox4x32_10(counter = (i/4, offset, 0, 0), key = seed)[i%4] * 2^-32 < keep else 0.
+ * with i = first + (index into x), y = x / keep if philox4x32_10(counter = (i/4, offset, 0, 0), key = seed)[i%4]
+ * * 2^-32 < keep else 0 (`first`, a multiple of 4, lets a slice of a buffer draw the buffer's mask).
  * Stateless: the backward pass calls it again on the upstream gradient with the same (seed, offset). */
 int e2e_dropout(void* stream, size_t n, const float* x, float* y, float keep, unsigned long long seed,
-                unsigned offset);
+                unsigned offset, size_t first);
+
+/* Scheduled sampling (decoder.py:155-180, tf.multinomial(logits, 1)): out[r] = first index whose cumulative
+ * exp(logit - max) (float64, index order) exceeds u_r * total, u_r = word 0 of
+ * philox4x32_10(counter = (first_row + r, offset, 0, 0), key = seed) * 2^-32. */
+int e2e_sample_rows(void* stream, int rows, int V, const float* logits, int ldl, unsigned long long seed,
+                    unsigned offset, unsigned first_row, long long* out);
 
 #ifdef __cplusplus
 }

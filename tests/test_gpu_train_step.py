@@ -127,6 +127,52 @@ def test_train_step_with_dropout_matches_oracle(cname):
     assert abs(ref["total_loss"] - nodrop["total_loss"]) > 1e-3
 
 
+@pytest.mark.parametrize("cname,keep", [("tiny_b", 1.0), ("tiny_b", 0.7), ("cfg1", 0.9)])
+def test_scheduled_sampling_matches_oracle(cname, keep):
+    """samp_prob > 0 (attn_decoder.py:130-139, reference default 0.1): the per-step scalar draw and the multinomial
+    draw are builder-defined Philox functions restated in the oracle, so the realised input ids must be IDENTICAL
+    and the step on them must meet the 1e-4 bar (with and without LM-output dropout in the sampling pass)."""
+    cfg = synth.get_config(cname)
+    w = synth.make_weights(cfg, bias_noise=0.1)
+    batch = synth.make_batch(cfg)
+    model = build_model(cfg, w, device="cuda:0")
+    model.params.decoder_params["char"].samp_prob = 0.5
+    model.params.decoder_params["char"].out_prob_dec = keep
+    model.params.dropout_seed = 5
+    sampled_any = False
+    for step in range(3):
+        model.run_step(batch)
+        ops.check_device_errors("cuda:0")
+        ref = om.train_step(w, batch, num_layers={"char": cfg.L}, ctc_tasks=cfg.ctc, out_prob_dec=keep,
+                            dropout_seed=5 * 1000003 + step, samp_prob=0.5)
+        ids = model.decoder["char"].stash["realized_ids"].cpu().numpy()
+        assert np.array_equal(ids, ref["realized_ids"]["char"])
+        teacher = np.asarray(batch["char"]).T[:ids.shape[0]]
+        sampled_any |= bool((ids != teacher).any())
+        compare_step(model, ref, rtol=RTOL)
+    assert sampled_any          # the rule really replaced ground-truth inputs
+
+
+def test_sample_rows_kernel_matches_oracle():
+    """e2e_sample_rows against the oracle's inverse-CDF draw, plus the empirical distribution of many draws."""
+    from e2e_asr_b200._lib import call
+    g = torch.Generator().manual_seed(0)
+    B, V = 64, 37
+    lg = (torch.randn(B, V, generator=g) * 2.0).cuda()
+    out = torch.empty(B, dtype=torch.int64, device="cuda")
+    call("e2e_sample_rows", B, V, lg, V, 1234567891011, 301, 640, out)
+    assert np.array_equal(out.cpu().numpy(), om.sample_rows(lg.cpu().numpy(), 1234567891011, 301, 640))
+    # distribution: 20000 rows of the same logits
+    n = 20000
+    one = torch.tensor([0.0, 1.0, 2.0, -1.0, 0.5]).cuda()
+    rows = one.repeat(n, 1).contiguous()
+    out = torch.empty(n, dtype=torch.int64, device="cuda")
+    call("e2e_sample_rows", n, 5, rows, 5, 7, 300, 0, out)
+    freq = np.bincount(out.cpu().numpy(), minlength=5) / n
+    p = torch.softmax(one.cpu().double(), 0).numpy()
+    assert np.abs(freq - p).max() < 0.015
+
+
 def test_adam_updates_match_oracle():
     """apply_updates=True: three Adam steps (fused flat-buffer kernel) against the oracle's TF-formula Adam."""
     cfg = synth.get_config("tiny_b")
