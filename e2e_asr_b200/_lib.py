@@ -14,8 +14,8 @@ LIB_PATH = os.path.join(_HERE, "libe2e_asr_b200.so")
 # signature codes: p = device/host pointer, i = int, l = long long, z = size_t, f = float
 _SIGS = {
     "e2e_gemm": "piiiiiipipipippii",
-    "e2e_gemm_lo": "piiiiiippippipippii",
-    "e2e_split_lo": "pzpp",
+    "e2e_gemm_lo": "piiiiiippippipippiizz",
+    "e2e_split_lo": "pizpp",
     "e2e_colsum": "piipipi",
     "e2e_lstm_pack_weights": "piipppiipp",
     "e2e_lstm_unpack_grads": "piipppiippi",

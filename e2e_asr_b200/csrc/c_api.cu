@@ -32,8 +32,8 @@ int sm_count() {
 int gemm_simt(cudaStream_t, int, int, int, int, int, const float*, int, const float*, int, float*, int,
               const float*, const float*, int, int);
 int gemm_tc(cudaStream_t, int mode, int, int, int, int, int, const float*, int, const float*, int, float*, int,
-            const float*, const float*, int, int, bool*, const float*, const float*);
-int split_lo(cudaStream_t, size_t, const float*, float*);
+            const float*, const float*, int, int, bool*, const float*, const float*, size_t, size_t);
+int split_lo(cudaStream_t, int, size_t, const float*, float*);
 void set_workspace(void*, size_t);
 void set_stream_workspace(cudaStream_t, void*, size_t);
 extern int g_rec_mode;
@@ -83,11 +83,12 @@ int embed_gather_f64(cudaStream_t, int, int, const float*, const long long*, dou
 
 static int gemm_any(cudaStream_t st, int mode, int tA, int tB, int M, int N, int K, const float* A, int lda,
                     const float* B, int ldb, float* C, int ldc, const float* bias, const float* Z, int ldz,
-                    int accumulate, const float* A_lo = nullptr, const float* B_lo = nullptr) {
+                    int accumulate, const float* A_lo = nullptr, const float* B_lo = nullptr, size_t a_plane = 0,
+                    size_t b_plane = 0) {
     if (mode != 0) {
         bool handled = false;
         int rc = gemm_tc(st, mode, tA, tB, M, N, K, A, lda, B, ldb, C, ldc, bias, Z, ldz, accumulate, &handled, A_lo,
-                         B_lo);
+                         B_lo, a_plane, b_plane);
         if (rc) return rc;
         if (handled) return 0;
     }
@@ -124,11 +125,13 @@ int e2e_gemm(void* stream, int mode, int transA, int transB, int M, int N, int K
 }
 int e2e_gemm_lo(void* stream, int mode, int transA, int transB, int M, int N, int K, const float* A, const float* A_lo,
                 int lda, const float* B, const float* B_lo, int ldb, float* C, int ldc, const float* bias,
-                const float* Z, int ldz, int accumulate) {
+                const float* Z, int ldz, int accumulate, size_t a_plane, size_t b_plane) {
     return gemm_any(ST(stream), mode, transA, transB, M, N, K, A, lda, B, ldb, C, ldc, bias, Z, ldz, accumulate, A_lo,
-                    B_lo);
+                    B_lo, a_plane, b_plane);
 }
-int e2e_split_lo(void* stream, size_t n, const float* x, float* lo) { return split_lo(ST(stream), n, x, lo); }
+int e2e_split_lo(void* stream, int mode, size_t n, const float* x, float* lo) {
+    return split_lo(ST(stream), mode, n, x, lo);
+}
 int e2e_set_tc_debug(float* dbg, long long min_work) {
     set_tc_debug(dbg, min_work);
     return 0;

@@ -11,6 +11,10 @@
 //          big*big + big*small + small*big in the fp32 TMEM accumulator
 //          (kind::tf32), error ~2^-21 relative -- the north-star's 1e-4 budget.
 //   mode 2 "bf16":   operands rounded to bf16 by the pre-pass, one kind::f16 MMA.
+//   mode 3 "bf16x2": each fp32 operand is split into hi = bf16(x) and lo = bf16(x - hi) (16 significand bits);
+//          the kernel accumulates hi*hi + hi*lo + lo*hi with three kind::f16 MMAs: error ~2^-17 relative per
+//          product (well inside the 1e-4 budget) at HALF the tensor-pipe cost of 3xTF32, because kind::f16 runs
+//          at twice the kind::tf32 rate.
 // All four transpose combinations are native: a row-major operand whose
 // contiguous dimension is K is a K-major UMMA operand, otherwise an MN-major one
 // (instruction-descriptor bits 15/16); TMA boxes always follow the contiguous
@@ -135,13 +139,15 @@ struct TcParams {
 };
 
 // BF16: element = 2 bytes, 64 elements per 128 B, UMMA_K = 16;  TF32: 4 bytes, 32 per 128 B, UMMA_K = 8.
-template <bool BF16>
+// MODE 1 = 3xTF32, 2 = bf16, 3 = bf16x2 (two bf16 parts per operand, three products).
+template <int MODE>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA1,
                const __grid_constant__ CUtensorMap mapB0, const __grid_constant__ CUtensorMap mapB1, TcParams p) {
+    constexpr bool BF16 = MODE >= 2;
+    constexpr int PARTS = MODE == 2 ? 1 : 2;       // operand parts staged per k-block
     constexpr int BKE = BF16 ? 64 : 32;            // K elements per stage (one 128-byte swizzle span)
     constexpr int ELT = BF16 ? 2 : 4;
-    constexpr int NPROD = BF16 ? 1 : 3;            // MMAs per k-step
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     __shared__ __align__(8) uint64_t full_bar[STAGES], empty_bar[STAGES], tmem_full_bar;
@@ -174,9 +180,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
                 mbar_wait(&empty_bar[s], ph ^ 1);
                 uint8_t* st = smem + (size_t)s * STAGE_BYTES;
                 const int k0 = (kb_begin + i) * BKE;
-                mbar_expect_tx(&full_bar[s], (BF16 ? 2 : 4) * OPER_BYTES);
+                mbar_expect_tx(&full_bar[s], 2 * PARTS * OPER_BYTES);
 #pragma unroll
-                for (int part = 0; part < (BF16 ? 1 : 2); ++part) {
+                for (int part = 0; part < PARTS; ++part) {
                     const CUtensorMap* ma = part ? &mapA1 : &mapA0;
                     const CUtensorMap* mb = part ? &mapB1 : &mapB0;
                     uint8_t* sa = st + part * OPER_BYTES;
@@ -227,14 +233,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
                 for (int k = 0; k < KSTEPS; ++k) {
                     const uint64_t a0 = make_sdesc(st + k * a_step, a_lbo, a_sbo, a_lt);
                     const uint64_t b0 = make_sdesc(st + 2 * OPER_BYTES + k * b_step, b_lbo, b_sbo, b_lt);
-                    if (BF16) {
+                    if (PARTS == 1) {
                         umma<true>(tmem_d, a0, b0, idesc, (i | k) != 0);
                     } else {
                         const uint64_t a1 = make_sdesc(st + OPER_BYTES + k * a_step, a_lbo, a_sbo, a_lt);
                         const uint64_t b1 = make_sdesc(st + 3 * OPER_BYTES + k * b_step, b_lbo, b_sbo, b_lt);
-                        umma<false>(tmem_d, a1, b0, idesc, (i | k) != 0);     // small * big
-                        umma<false>(tmem_d, a0, b1, idesc, 1);                // big * small
-                        umma<false>(tmem_d, a0, b0, idesc, 1);                // big * big
+                        umma<BF16>(tmem_d, a1, b0, idesc, (i | k) != 0);      // small * big
+                        umma<BF16>(tmem_d, a0, b1, idesc, 1);                 // big * small
+                        umma<BF16>(tmem_d, a0, b0, idesc, 1);                 // big * big
                     }
                 }
                 umma_commit(&empty_bar[s]);            // frees the smem stage when these MMAs retire
@@ -346,6 +352,25 @@ __global__ void cvt_bf16_kernel(size_t rows, int cols, const float* __restrict__
     *reinterpret_cast<uint4*>(out + r * ldo + c) = *reinterpret_cast<const uint4*>(o);
 }
 
+// hi = bf16(x) (round to nearest), lo = bf16(x - hi): x = hi + lo up to 2^-17 |x|.
+__global__ void split_bf16x2_kernel(size_t rows, int cols, const float* __restrict__ x, int ldx,
+                                    __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo, int ldo) {
+    size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    size_t total = rows * (size_t)(ldo / 8);
+    if (i >= total) return;
+    size_t r = i / (ldo / 8);
+    int c = (int)(i % (ldo / 8)) * 8;
+    __align__(16) __nv_bfloat16 h[8], l[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const float v = (c + j < cols) ? x[r * ldx + c + j] : 0.f;
+        h[j] = __float2bfloat16(v);
+        l[j] = __float2bfloat16(v - __bfloat162float(h[j]));
+    }
+    *reinterpret_cast<uint4*>(hi + r * ldo + c) = *reinterpret_cast<const uint4*>(h);
+    *reinterpret_cast<uint4*>(lo + r * ldo + c) = *reinterpret_cast<const uint4*>(l);
+}
+
 // ------------------------------------------------------------------ host side
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
@@ -421,10 +446,33 @@ __global__ void split_lo_kernel(size_t n4, const float4* __restrict__ x, float4*
         lo[i] = o;
     }
 }
-int split_lo(cudaStream_t st, size_t n, const float* x, float* lo) {
-    E2E_REQUIRE(n % 4 == 0 && ((uintptr_t)x & 15) == 0 && ((uintptr_t)lo & 15) == 0,
-                "split_lo: buffers must be 16-byte aligned with a multiple of 4 elements");
+// bf16x2: the 4n bytes of `lo` hold two bf16 planes, hi[n] then lo[n]
+__global__ void split_planes_kernel(size_t n8, const float4* __restrict__ x, uint4* __restrict__ hi,
+                                    uint4* __restrict__ lo) {
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n8; i += (size_t)gridDim.x * blockDim.x) {
+        const float4 a = x[2 * i], b = x[2 * i + 1];
+        const float v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+        __align__(16) __nv_bfloat16 h[8], l[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            h[j] = __float2bfloat16(v[j]);
+            l[j] = __float2bfloat16(v[j] - __bfloat162float(h[j]));
+        }
+        hi[i] = *reinterpret_cast<const uint4*>(h);
+        lo[i] = *reinterpret_cast<const uint4*>(l);
+    }
+}
+int split_lo(cudaStream_t st, int mode, size_t n, const float* x, float* lo) {
+    E2E_REQUIRE(mode == 1 || mode == 3, "split_lo: mode %d has no operand split (1 = tf32x3, 3 = bf16x2)", mode);
+    E2E_REQUIRE(n % 8 == 0 && ((uintptr_t)x & 15) == 0 && ((uintptr_t)lo & 15) == 0,
+                "split_lo: buffers must be 16-byte aligned with a multiple of 8 elements");
     if (n == 0) return 0;
+    if (mode == 3) {
+        split_planes_kernel<<<(unsigned)min((size_t)148 * 8, (n / 8 + 255) / 256), 256, 0, st>>>(
+            n / 8, (const float4*)x, (uint4*)lo, (uint4*)((__nv_bfloat16*)lo + n));
+        E2E_LAUNCH_CHECK();
+        return 0;
+    }
     split_lo_kernel<<<(unsigned)min((size_t)148 * 8, (n / 4 + 255) / 256), 256, 0, st>>>(n / 4, (const float4*)x, (float4*)lo);
     E2E_LAUNCH_CHECK();
     return 0;
@@ -434,10 +482,10 @@ int split_lo(cudaStream_t st, size_t n, const float* x, float* lo) {
 // given (and TMA-addressable) the operand's pre-pass is skipped: the tensor maps point at the caller's buffers.
 int gemm_tc(cudaStream_t st, int mode, int transA, int transB, int M, int N, int K, const float* A, int lda,
             const float* B, int ldb, float* C, int ldc, const float* bias, const float* Z, int ldz, int accumulate,
-            bool* handled, const float* A_lo, const float* B_lo) {
+            bool* handled, const float* A_lo, const float* B_lo, size_t a_plane, size_t b_plane) {
     *handled = false;
-    if (mode != 1 && mode != 2) return 0;
-    const bool bf16 = mode == 2;
+    if (mode < 1 || mode > 3) return 0;
+    const bool bf16 = mode >= 2;
     // big enough to pay for the pre-pass and to fill tiles; K >= one stage
     if (M < 96 || N < 64 || K < 32 || (long long)M * N * K < g_min_work) return 0;
     void* ws_ptr = g_ws;
@@ -450,13 +498,16 @@ int gemm_tc(cudaStream_t st, int mode, int transA, int transB, int M, int N, int
     const size_t b_rows = transB ? N : K, b_cols = transB ? K : N;
     const int eper = bf16 ? 8 : 4;                                  // elements per 16 bytes
     const size_t a_ld = (a_cols + eper - 1) / eper * eper, b_ld = (b_cols + eper - 1) / eper * eper;
-    const size_t esz = bf16 ? 2 : 4, nparts = bf16 ? 1 : 2;
+    const size_t esz = bf16 ? 2 : 4, nparts = mode == 2 ? 1 : 2;
     size_t a_bytes = (a_rows * a_ld * esz + 1023) / 1024 * 1024, b_bytes = (b_rows * b_ld * esz + 1023) / 1024 * 1024;
     // operands whose split the caller already holds: used in place when TMA can address them
-    auto direct_ok = [&](const float* x, const float* lo, int ld) {
-        return !bf16 && lo != nullptr && ld % 4 == 0 && ((uintptr_t)x & 15) == 0 && ((uintptr_t)lo & 15) == 0;
+    // (tf32x3: x itself + its fp32 "small" half; bf16x2: the two bf16 planes of split_lo, `plane` elements apart)
+    auto direct_ok = [&](const float* x, const float* lo, int ld, size_t plane) {
+        if (mode == 1) return lo != nullptr && ld % 4 == 0 && ((uintptr_t)x & 15) == 0 && ((uintptr_t)lo & 15) == 0;
+        if (mode == 3) return lo != nullptr && ld % 8 == 0 && plane % 8 == 0 && plane > 0 && ((uintptr_t)lo & 15) == 0;
+        return false;
     };
-    const bool a_direct = direct_ok(A, A_lo, lda), b_direct = direct_ok(B, B_lo, ldb);
+    const bool a_direct = direct_ok(A, A_lo, lda, a_plane), b_direct = direct_ok(B, B_lo, ldb, b_plane);
     if (a_direct) a_bytes = 0;
     if (b_direct) b_bytes = 0;
     if (nparts * (a_bytes + b_bytes) > ws_bytes) return 0;
@@ -468,7 +519,18 @@ int gemm_tc(cudaStream_t st, int mode, int transA, int transB, int M, int N, int
     size_t a_ld_eff = a_ld, b_ld_eff = b_ld;
     if (a_direct) { A0 = const_cast<float*>(A); A1 = const_cast<float*>(A_lo); a_ld_eff = lda; }
     if (b_direct) { B0 = const_cast<float*>(B); B1 = const_cast<float*>(B_lo); b_ld_eff = ldb; }
-    if (bf16) {
+    if (mode == 3) {
+        if (a_direct) { A0 = const_cast<float*>(A_lo); A1 = (__nv_bfloat16*)A0 + a_plane; }
+        if (b_direct) { B0 = const_cast<float*>(B_lo); B1 = (__nv_bfloat16*)B0 + b_plane; }
+        if (!a_direct) {
+            split_bf16x2_kernel<<<cdiv(a_rows * (a_ld / 8), 256), 256, 0, st>>>(a_rows, (int)a_cols, A, lda, (__nv_bfloat16*)A0, (__nv_bfloat16*)A1, (int)a_ld);
+            E2E_LAUNCH_CHECK();
+        }
+        if (!b_direct) {
+            split_bf16x2_kernel<<<cdiv(b_rows * (b_ld / 8), 256), 256, 0, st>>>(b_rows, (int)b_cols, B, ldb, (__nv_bfloat16*)B0, (__nv_bfloat16*)B1, (int)b_ld);
+            E2E_LAUNCH_CHECK();
+        }
+    } else if (bf16) {
         cvt_bf16_kernel<<<cdiv(a_rows * (a_ld / 8), 256), 256, 0, st>>>(a_rows, (int)a_cols, A, lda, (__nv_bfloat16*)A0, (int)a_ld);
         E2E_LAUNCH_CHECK();
         cvt_bf16_kernel<<<cdiv(b_rows * (b_ld / 8), 256), 256, 0, st>>>(b_rows, (int)b_cols, B, ldb, (__nv_bfloat16*)B0, (int)b_ld);
@@ -491,7 +553,7 @@ int gemm_tc(cudaStream_t st, int mode, int transA, int transB, int M, int N, int
     const bool a32 = !bf16 && a_mn, b32 = !bf16 && b_mn;      // tf32 MN-major: 32-byte-atom swizzle
     ok &= make_map(&mA0, bf16, A0, a_rows, a_cols, a_ld_eff, bke, a_mn ? bke : TBM, a32);
     ok &= make_map(&mB0, bf16, B0, b_rows, b_cols, b_ld_eff, bke, b_mn ? bke : TBN, b32);
-    if (!bf16) {
+    if (nparts == 2) {
         ok &= make_map(&mA1, bf16, A1, a_rows, a_cols, a_ld_eff, bke, a_mn ? bke : TBM, a32);
         ok &= make_map(&mB1, bf16, B1, b_rows, b_cols, b_ld_eff, bke, b_mn ? bke : TBN, b32);
     } else {
@@ -517,12 +579,15 @@ int gemm_tc(cudaStream_t st, int mode, int transA, int transB, int M, int N, int
     }
     const size_t smem = (size_t)STAGES * STAGE_BYTES + 1024;
     dim3 grid(gn, gm, splits);
-    if (bf16) {
-        E2E_CHECK_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        gemm_tc_kernel<true><<<grid, TC_THREADS, smem, st>>>(mA0, mA1, mB0, mB1, p);
+    if (mode == 3) {
+        E2E_CHECK_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        gemm_tc_kernel<3><<<grid, TC_THREADS, smem, st>>>(mA0, mA1, mB0, mB1, p);
+    } else if (mode == 2) {
+        E2E_CHECK_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        gemm_tc_kernel<2><<<grid, TC_THREADS, smem, st>>>(mA0, mA1, mB0, mB1, p);
     } else {
-        E2E_CHECK_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        gemm_tc_kernel<false><<<grid, TC_THREADS, smem, st>>>(mA0, mA1, mB0, mB1, p);
+        E2E_CHECK_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        gemm_tc_kernel<1><<<grid, TC_THREADS, smem, st>>>(mA0, mA1, mB0, mB1, p);
     }
     E2E_LAUNCH_CHECK();
     *handled = true;

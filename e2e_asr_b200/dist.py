@@ -24,7 +24,10 @@ def init_from_env(backend=None):
             torch.cuda.set_device(local)
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         os.environ.setdefault("MASTER_PORT", "29500")
-        dist.init_process_group(backend=backend, rank=rank, world_size=world)
+        # a mismatched collective must abort the job, not hang it
+        import datetime
+        dist.init_process_group(backend=backend, rank=rank, world_size=world,
+                                timeout=datetime.timedelta(seconds=int(os.environ.get("E2E_DIST_TIMEOUT_S", "180"))))
     return rank, world, local
 
 

@@ -12,14 +12,14 @@ import torch
 from . import _lib
 from ._lib import call
 
-# 0 = fp32 FFMA, 1 = 3xTF32 tcgen05 (fp32-accurate), 2 = bf16 tcgen05
+# 0 = fp32 FFMA, 1 = 3xTF32 tcgen05 (fp32-accurate), 2 = bf16 tcgen05, 3 = bf16x2 tcgen05 (hi+lo bf16, 3 products)
 _GEMM_MODE = 0
 TAG_GEMM_SHAPES = False      # profiling aid: one profiler entry per GEMM shape instead of one "e2e_gemm"
 
 
 def set_gemm_mode(mode):
     global _GEMM_MODE
-    _GEMM_MODE = {"fp32": 0, "tf32x3": 1, "bf16": 2}.get(mode, mode)
+    _GEMM_MODE = {"fp32": 0, "tf32x3": 1, "bf16": 2, "bf16x2": 3}.get(mode, mode)
 
 
 _workspace = {}
@@ -84,14 +84,33 @@ def to_i32(t, device):
     return r
 
 
+class SplitPlanes:
+    """bf16x2 operand split of a tensor: `planes` is a bf16 tensor [2, *x.shape] (hi = bf16(x), lo = bf16(x - hi)).
+    Indexing takes the same view of both planes, as the caller indexes x."""
+
+    def __init__(self, planes):
+        self.planes = planes
+
+    def __getitem__(self, idx):
+        idx = idx if isinstance(idx, tuple) else (idx,)
+        return SplitPlanes(self.planes[(slice(None),) + idx])
+
+    def record_stream(self, stream):
+        self.planes.record_stream(stream)
+
+
 def split_lo(x):
-    """The "small" half of the 3xTF32 split of a contiguous tensor (x - tf32_trunc(x)), or None when the GEMM mode
-    does not use it.  Views of the result, taken like the views of x, are passed to gemm(..., a_lo= / b_lo=) so one
-    pass serves every product the tensor enters."""
-    if _GEMM_MODE != 1 or x.numel() % 4 != 0 or not x.is_contiguous():
+    """The operand split of a contiguous tensor for the current GEMM mode, or None when the mode does not use one:
+    tf32x3 -> x - tf32_trunc(x) (fp32, x's layout); bf16x2 -> SplitPlanes.  Views of the result, taken like the views
+    of x, are passed to gemm(..., a_lo= / b_lo=) so one pass serves every product the tensor enters."""
+    if _GEMM_MODE not in (1, 3) or x.numel() % 8 != 0 or not x.is_contiguous():
         return None
+    if _GEMM_MODE == 3:
+        planes = torch.empty((2,) + tuple(x.shape), dtype=torch.bfloat16, device=x.device)
+        call("e2e_split_lo", 3, x.numel(), x, planes)
+        return SplitPlanes(planes)
     lo = torch.empty_like(x)
-    call("e2e_split_lo", x.numel(), x, lo)
+    call("e2e_split_lo", 1, x.numel(), x, lo)
     return lo
 
 
@@ -117,11 +136,20 @@ def gemm(a, b, out=None, ta=False, tb=False, bias=None, z=None, accumulate=False
     if mode != 0 and str(a.device) not in _workspace:
         ensure_workspace(a.device)
     tag = ("gemm M=%d N=%d K=%d t%d%d" % (M, N, K, ta, tb)) if TAG_GEMM_SHAPES else "e2e_gemm"
-    if mode == 1 and (a_lo is not None or b_lo is not None):
-        assert a_lo is None or (a_lo.shape == a.shape and a_lo.stride() == a.stride())
-        assert b_lo is None or (b_lo.shape == b.shape and b_lo.stride() == b.stride())
-        call("e2e_gemm_lo", mode, int(ta), int(tb), M, N, K, a, a_lo, lda, b, b_lo, ldb, out, ldc,
-             bias, z, ldz, int(accumulate), work=2.0 * M * N * K, tag=tag)
+    if mode in (1, 3) and (a_lo is not None or b_lo is not None):
+        planes = [0, 0]
+        los = [a_lo, b_lo]
+        for i, (x, lo) in enumerate(((a, a_lo), (b, b_lo))):
+            if lo is None:
+                continue
+            if isinstance(lo, SplitPlanes) != (mode == 3):
+                los[i] = None           # split made for another mode: let the GEMM redo its pre-pass
+                continue
+            if mode == 3:
+                los[i], planes[i] = lo.planes[0], lo.planes.stride(0)
+            assert los[i].shape == x.shape and los[i].stride() == x.stride()
+        call("e2e_gemm_lo", mode, int(ta), int(tb), M, N, K, a, los[0], lda, b, los[1], ldb, out, ldc,
+             bias, z, ldz, int(accumulate), planes[0], planes[1], work=2.0 * M * N * K, tag=tag)
         return out
     call("e2e_gemm", mode, int(ta), int(tb), M, N, K, a, lda, b, ldb, out, ldc,
          bias, z, ldz, int(accumulate), work=2.0 * M * N * K, tag=tag)

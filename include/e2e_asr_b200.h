@@ -38,19 +38,26 @@ unsigned long long e2e_launch_count(int reset);
  * x-part of BasicLSTMCell's [x,h].K (encoder.py:77-81); and their gradients
  * (tf.gradients, seq2seq_model.py:148).
  * mode: 0 = fp32 FFMA (exact fp32), 1 = 3xTF32 tcgen05 (fp32-accurate tensor
- * core), 2 = bf16 tcgen05.  Shapes a tensor-core mode cannot take fall back to
- * mode 0 (still on the GPU). */
+ * core), 2 = bf16 tcgen05, 3 = bf16x2 tcgen05 (operands as hi + lo bf16 pairs, three kind::f16 products:
+ * ~2^-17 relative error per product at half the tensor-pipe cost of mode 1).  Shapes a tensor-core mode
+ * cannot take fall back to mode 0 (still on the GPU). */
 int e2e_gemm(void* stream, int mode, int transA, int transB, int M, int N, int K,
              const float* A, int lda, const float* B, int ldb, float* C, int ldc,
              const float* bias, const float* Z, int ldz, int accumulate);
-/* e2e_gemm with the caller holding the "small" half of the 3xTF32 split of an operand (either may be NULL):
- * X_lo = e2e_split_lo(X), same layout as X.  An operand with X_lo given, ld % 4 == 0 and 16-byte aligned
- * pointers skips its pre-pass (the tensor core ignores the low 13 mantissa bits of the raw fp32 "big" half).
- * Lets one split of dz serve the dX, dW_x and dW_h products of a layer. */
+/* e2e_gemm with the caller holding the operand split of an operand (either X_lo may be NULL), made once by
+ * e2e_split_lo(mode, n, X, buf) over the whole n-element buffer X lives in and shared by every product X enters
+ * (one split of dz serves the dX, dW_x and dW_h products of a layer).  The operand's pre-pass is then skipped:
+ *   mode 1: buf[i] = X[i] - tf32_trunc(X[i]) (fp32, X's layout); X_lo points at the element matching X's first
+ *           element; needs ld % 4 == 0 and 16-byte aligned pointers (the tensor core ignores the low 13 mantissa
+ *           bits of the raw fp32 "big" half, so X itself is the other part); x_plane is ignored;
+ *   mode 3: buf holds two bf16 planes of n elements, hi = bf16(X) then lo = bf16(X - hi), each in X's layout;
+ *           X_lo points at the hi-plane element matching X's first element and x_plane = n (elements between
+ *           the planes); needs ld % 8 == 0, x_plane % 8 == 0 and a 16-byte aligned X_lo.
+ * n must be a multiple of 8 and the buffers 16-byte aligned. */
 int e2e_gemm_lo(void* stream, int mode, int transA, int transB, int M, int N, int K, const float* A,
                 const float* A_lo, int lda, const float* B, const float* B_lo, int ldb, float* C, int ldc,
-                const float* bias, const float* Z, int ldz, int accumulate);
-int e2e_split_lo(void* stream, size_t n, const float* x, float* lo);   /* lo[i] = x[i] - tf32_trunc(x[i]) */
+                const float* bias, const float* Z, int ldz, int accumulate, size_t a_plane, size_t b_plane);
+int e2e_split_lo(void* stream, int mode, size_t n, const float* x, float* lo);
 
 /* Scratch for the tensor-core modes' operand pre-pass (TF32 big/small split or
  * bf16 copies): a caller-owned device buffer; GEMMs whose operands do not fit run

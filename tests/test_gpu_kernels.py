@@ -198,12 +198,39 @@ def test_prepare_input_stack_stride():
         assert np.all(out[:, ref.shape[1]:] == 0)
 
 
-@pytest.mark.parametrize("mode,tol", [(1, 2e-5), (2, 2e-2)])
+@pytest.mark.parametrize("mode", ["tf32x3", "bf16x2"])
+def test_gemm_shared_operand_split(mode):
+    """e2e_split_lo / e2e_gemm_lo: one split of a tensor serves products on the tensor and on row / column views of
+    it (the dX, dW_x and shifted dW_h products of a layer), with the same result as the GEMM's own pre-pass."""
+    rng = np.random.default_rng(3)
+    N_, I, G4 = 520, 96, 256
+    x, g, w = (T(rng.standard_normal(s).astype(np.float32)) for s in ((N_, I), (N_, 2 * G4), (I, 2 * G4)))
+    ops.set_gemm_mode(mode)
+    try:
+        x_lo, g_lo, w_lo = ops.split_lo(x), ops.split_lo(g), ops.split_lo(w)
+        assert x_lo is not None and g_lo is not None
+        cases = [(dict(a=g, b=w, tb=True), dict(a_lo=g_lo, b_lo=w_lo)),
+                 (dict(a=x, b=g, ta=True), dict(a_lo=x_lo, b_lo=g_lo)),
+                 (dict(a=x[:N_ - 1], b=g[1:, :G4], ta=True), dict(a_lo=x_lo[:N_ - 1], b_lo=g_lo[1:, :G4])),
+                 (dict(a=x[1:], b=g[:N_ - 1, G4:], ta=True), dict(b_lo=g_lo[:N_ - 1, G4:]))]
+        for kw, los in cases:
+            plain = ops.gemm(**kw)
+            shared = ops.gemm(**kw, **los)
+            a64 = kw["a"].double().T if kw.get("ta") else kw["a"].double()
+            b64 = kw["b"].double().T if kw.get("tb") else kw["b"].double()
+            assert relerr(shared, (a64 @ b64).cpu().numpy()) < 3e-5
+            assert float((shared - plain).abs().max()) <= 1e-5 * float(plain.abs().max())
+    finally:
+        ops.set_gemm_mode("fp32")
+
+
+@pytest.mark.parametrize("mode,tol", [(1, 2e-5), (2, 2e-2), (3, 3e-5)])
 @pytest.mark.parametrize("M,N,K", [(128, 128, 32), (256, 384, 96), (1000, 520, 264), (4480, 2048, 120),
                                    (256, 1024, 5000), (777, 333, 1111)])
 @pytest.mark.parametrize("ta,tb", [(False, False), (True, False), (False, True), (True, True)])
 def test_gemm_tensor_core(mode, tol, M, N, K, ta, tb):
-    """tcgen05 paths: mode 1 = 3xTF32 (fp32-accurate), mode 2 = bf16 (looser, stated tolerance)."""
+    """tcgen05 paths: mode 1 = 3xTF32 (fp32-accurate), mode 2 = bf16 (looser, stated tolerance), mode 3 = bf16x2
+    (hi + lo bf16 pairs, three products: 16 significand bits per operand)."""
     rng = np.random.default_rng(M + N + K + mode)
     a = rng.standard_normal((K, M) if ta else (M, K)).astype(np.float32)
     b = rng.standard_normal((N, K) if tb else (K, N)).astype(np.float32)

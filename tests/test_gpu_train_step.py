@@ -50,10 +50,10 @@ def test_clipping_active_and_dense_norm_option():
     assert abs(float(model.grad_norm) - ref["dense_norm"]) < 1e-4 * ref["dense_norm"]
 
 
-@pytest.mark.parametrize("mode,rtol", [("tf32x3", 1e-4), ("bf16", 5e-2)])
+@pytest.mark.parametrize("mode,rtol", [("tf32x3", 1e-4), ("bf16x2", 1e-4), ("bf16", 5e-2)])
 def test_train_step_tensor_core_modes(mode, rtol):
     """cfg1 through the tcgen05 GEMMs.  tf32x3 is the fp32-accurate mode and must meet
-    the same 1e-4 bar as FFMA; bf16 is the reduced-precision mode: stated tolerance
+    the same 1e-4 bar as FFMA, and so must bf16x2 (hi + lo bf16 operands, three products); bf16 is the reduced-precision mode: stated tolerance
     5e-2 on gradients/logits (relative to each tensor's max), 1e-2 on the loss."""
     cfg = synth.get_config("cfg1")
     w = synth.make_weights(cfg, bias_noise=0.1)
