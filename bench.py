@@ -162,6 +162,7 @@ def main():
     ap.add_argument("--gemm", default="tf32x3", help="fp32 | tf32x3 | bf16x2 | bf16 (default: tf32x3, the fp32-accurate tensor-core mode)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-beam", action="store_true", help="skip the beam-decode utt/s side measurement")
+    ap.add_argument("--no-graph", action="store_true", help="time the eager step instead of its CUDA-graph replay")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -222,7 +223,7 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.SUM)
         return float(t.item())
 
-    # ---------------- device-resident inputs ("value")
+    # ---------------- eager pass: per-kernel CUDA events (breakdown, roofline) + host enqueue cost
     prepared = model.get_batch(batch)
     for _ in range(W):
         model.run_step(prepared=prepared)
@@ -239,33 +240,56 @@ def main():
             break
     barrier()
     ops.check_device_errors(dev)
-    prof = _lib.Profiler()
-    _lib.PROFILER = prof
-    _lib.launch_count(reset=True)
-    sampler = ClockSampler(local) if rank == 0 else None
+    use_graph = not args.no_graph
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    e0.record()
-    for _ in range(K):
-        model.run_step(prepared=prepared)
-    e1.record()
-    barrier()
-    ms = max_over_ranks(e0.elapsed_time(e1))
-    clocks = sampler.stop() if sampler else None
-    launches = _lib.launch_count()
-    _lib.PROFILER = None
+
+    def timed_loop(step_fn, profile):
+        """K steps between barriers; returns (ms max over ranks, host enqueue ms/step, launches, clocks)."""
+        prof = _lib.Profiler() if profile else None
+        _lib.PROFILER = prof
+        _lib.launch_count(reset=True)
+        sampler = ClockSampler(local) if rank == 0 else None
+        barrier()
+        e0.record()
+        model.host_wait_s = 0.0
+        h0 = time.perf_counter()
+        for _ in range(K):
+            step_fn()
+        host_s = time.perf_counter() - h0
+        e1.record()
+        barrier()
+        t_ms = max_over_ranks(e0.elapsed_time(e1))
+        host_ms = max_over_ranks((host_s - model.host_wait_s) * 1e3 / K)   # enqueue work, excluding waits on the GPU
+        clk = sampler.stop() if sampler else None
+        n = _lib.launch_count()
+        _lib.PROFILER = None
+        return t_ms, host_ms, n, clk, prof
+
+    ms_eager, host_eager_ms, launches, clocks, prof = timed_loop(lambda: model.run_step(prepared=prepared), True)
+    ms, host_busy_ms = ms_eager, host_eager_ms
+    step_host = lambda: model.run_step(batch)
+    mode = "eager (~200 launches per step from Python)"
+    if use_graph:
+        # ---------------- device-resident inputs ("value"): the step replayed from its CUDA graph
+        gs = model.graphed_step(batch)
+        for _ in range(W):
+            gs.step()
+        ms, host_busy_ms, n_tail, clocks, _ = timed_loop(gs.step, False)
+        launches = n_tail + gs.launches_per_step * K         # kernels in the replayed graph + the eager tail
+        step_host = lambda: gs.step(batch)
+        mode = "CUDA graph replay of fwd+bwd (%d kernels) + eager all-reduce/clip" % gs.launches_per_step
     loss_val = float(model.total_loss)
     total_frames = sum_over_ranks(frames)
     value = total_frames * K / (ms * 1e-3)
 
     # ---------------- end to end from host buffers ("e2e")
     for _ in range(2):
-        model.run_step(batch)
+        step_host()
         float(model.total_loss)
     barrier()
     e0.record()
     for _ in range(K):
-        model.run_step(batch)                   # H2D of the batch from pinned staging inside
+        step_host()                             # H2D of the batch from pinned staging inside
         _ = float(model.total_loss)             # D2H of the step's result
     e1.record()
     barrier()
@@ -323,6 +347,10 @@ def main():
         "config": workload_config(args.config, world), "frames_per_step_per_gpu": frames,
         "padded_frames_per_step_per_gpu": cfg.B * cfg.T, "loss": loss_val,
         "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "launches_per_step": launches / K,
+        "step_mode": mode, "host_enqueue_ms_per_step": host_busy_ms,
+        "eager": {"ms_per_step": ms_eager / K, "host_enqueue_ms_per_step": host_eager_ms,
+                  "note": "same K steps launched kernel by kernel; the per-kernel events of breakdown/roofline come "
+                          "from this pass (a graph replay runs the identical kernels)"},
         "roofline": roof, "breakdown": breakdown, "sequential_kernels": extra,
     }
     if world == 1 and not args.no_cpu_baseline:

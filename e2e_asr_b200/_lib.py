@@ -5,6 +5,7 @@ CUDA device is present, every op raises.
 """
 import ctypes
 import os
+import sys
 
 import torch
 
@@ -92,6 +93,8 @@ def lib():
         l.e2e_last_error.restype = ctypes.c_char_p
         l.e2e_version.restype = ctypes.c_int
         l.e2e_sm_count.restype = ctypes.c_int
+        l.e2e_capture_status.restype = ctypes.c_int
+        l.e2e_capture_status.argtypes = [ctypes.c_void_p]
         l.e2e_launch_count.restype = ctypes.c_ulonglong
         l.e2e_launch_count.argtypes = [ctypes.c_int]
         l.e2e_set_workspace.restype = ctypes.c_int
@@ -111,7 +114,7 @@ def lib():
 
 
 def exported_symbols():
-    return sorted(list(_SIGS.keys()) + ["e2e_last_error", "e2e_version", "e2e_sm_count", "e2e_launch_count",
+    return sorted(list(_SIGS.keys()) + ["e2e_last_error", "e2e_version", "e2e_sm_count", "e2e_launch_count", "e2e_capture_status",
                    "e2e_set_workspace", "e2e_decoder_persist_fits", "e2e_set_tc_debug", "e2e_set_rec_mode", "e2e_set_rec_debug", "e2e_set_stream_workspace"])
 
 
@@ -125,6 +128,27 @@ def _ptr(x):
 
 def stream_ptr():
     return torch.cuda.current_stream().cuda_stream
+
+
+# E2E_DEBUG_CAPTURE=1: report the first C-ABI call / checkpoint after which a CUDA-graph capture is found invalidated
+DEBUG_CAPTURE = bool(os.environ.get("E2E_DEBUG_CAPTURE"))
+_capture_reported = False
+
+
+def capture_checkpoint(where):
+    global _capture_reported
+    if not DEBUG_CAPTURE or _capture_reported:
+        return
+    st = lib().e2e_capture_status(stream_ptr())
+    if os.environ.get("E2E_DEBUG_CAPTURE") == "2":
+        import threading
+        sys.stderr.write("[e2e] capture status %d stream %x thread %s after %s\n"
+                         % (st, stream_ptr(), threading.current_thread().name, where))
+    if st == 2 or st == -1:
+        _capture_reported = True
+        import traceback
+        sys.stderr.write("[e2e] capture found INVALIDATED (status %d) after: %s\n" % (st, where))
+        traceback.print_stack(limit=8, file=sys.stderr)
 
 
 class Profiler(object):
@@ -174,3 +198,5 @@ def call(name, *args, work=0.0, tag=None):
         prof.records.append((tag or name, e0, e1, work))
     if rc != 0:
         raise RuntimeError("%s failed (%d): %s" % (name, rc, l.e2e_last_error().decode()))
+    if DEBUG_CAPTURE:
+        capture_checkpoint(tag or name)

@@ -103,6 +103,12 @@ using namespace e2e;
 extern "C" {
 
 int e2e_version(void) { return 1; }
+/* 0 = not capturing, 1 = capture active, 2 = capture invalidated, -1 = query failed */
+int e2e_capture_status(void* stream) {
+    cudaStreamCaptureStatus s;
+    if (cudaStreamIsCapturing((cudaStream_t)stream, &s) != cudaSuccess) { cudaGetLastError(); return -1; }
+    return (int)s;
+}
 unsigned long long e2e_launch_count(int reset) {
     unsigned long long n = e2e::g_launches;
     if (reset) e2e::g_launches = 0;

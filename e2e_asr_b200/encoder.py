@@ -104,8 +104,13 @@ class Encoder(BaseParams):
         lens_host = np.asarray(ops.host_array(seq_len), np.int64)
         B, T, F = encoder_input.shape
         res = params.initial_res_fac
+        # per-layer lengths are derived ON THE DEVICE from the batch's length tensor (a handful of tiny kernels), so a
+        # captured step (GraphedStep) follows the lengths of the batch it is replayed on; the host copy only feeds
+        # shape decisions (the maximum length)
+        lens_dev = ops.to_i32(seq_len, dev)
         if res > 1:
             lens_host = -(-lens_host // res)
+            lens_dev = (lens_dev + (res - 1)) // res
             T = -(-T // res)
         # number of pyramid reductions that will be applied (encoder.py:172)
         n_red, r = 0, res
@@ -122,7 +127,6 @@ class Encoder(BaseParams):
         T_l = T
         for i in range(max_depth):
             layer_depth = i + 1
-            lens_dev = torch.from_numpy(lens_host.astype(np.int32)).to(dev, non_blocking=True)
             max_len = int(lens_host.max()) if B else 0
             out = self._layer_encoder_input(x, lens_dev, max_len, layer_depth)       # [B, Tp, 2H]
             if out.is_cuda:
@@ -135,7 +139,7 @@ class Encoder(BaseParams):
                 time_major_states[layer_depth] = view.transpose(0, 1)
             if layer_depth in attention_states:
                 attention_states[layer_depth] = view
-            sl = torch.from_numpy(lens_host.copy()).to(dev, non_blocking=True)
+            sl = lens_dev.to(torch.int64)
             sl._host = lens_host.copy()
             sl._i32 = lens_dev
             seq_len_inps[layer_depth] = sl
@@ -145,6 +149,7 @@ class Encoder(BaseParams):
                 Tp //= 2
                 T_l = -(-T_l // 2)
                 lens_host = -(-lens_host // 2)
+                lens_dev = (lens_dev + 1) // 2
                 res *= params.skip_step
             else:
                 x = out

@@ -113,6 +113,14 @@ class Seq2SeqModel(BaseParams):
             buf = torch.empty(t.shape, dtype=dtype).pin_memory()
             self._pinned[key] = buf
         buf.copy_(t)
+        static = getattr(self, "_static_inputs", None)
+        if static is not None:
+            # graphed step: the captured kernels read these very buffers, so refill them in place
+            dev = static.get(key)
+            if dev is None or dev.shape != buf.shape or dev.dtype != dtype:
+                dev = static[key] = torch.empty(buf.shape, dtype=dtype, device=self.device)
+            dev.copy_(buf, non_blocking=True)
+            return dev
         return buf.to(self.device, non_blocking=True)
 
     def _len_tensor(self, key, arr):
@@ -155,11 +163,6 @@ class Seq2SeqModel(BaseParams):
             prepared = self.get_batch(batch)
         self.encoder_inputs, self.decoder_inputs, self.seq_len, self.seq_len_target = prepared
 
-        self.targets, self.target_weights = {}, {}
-        for task in params.tasks:
-            self.targets[task], self.target_weights[task] = create_shifted_targets(
-                self.decoder_inputs[task], self.seq_len_target[task]) if self.isTraining else (None, None)
-
         if self.isTraining:
             # Bound the host's run-ahead to ONE step (step N+1 is enqueued while step N runs): tensors handed to
             # the side streams return to the caching allocator through record_stream events; with an unbounded
@@ -167,8 +170,25 @@ class Seq2SeqModel(BaseParams):
             # cudaMalloc calls (measured: 34-66 ms per 17 ms GPU step).
             if torch.cuda.is_available():
                 while len(self._inflight) >= 2:
-                    self._inflight.pop(0).synchronize()
+                    self._wait(self._inflight.pop(0))
+        self._step_core()
+        if self.isTraining:
+            self._step_tail()
+
+    def _step_core(self):
+        """Forward, losses and backward of one step on the inputs held in self.encoder_inputs / decoder_inputs:
+        everything up to the complete local gradient in the flat buffer.  No host synchronisation and no per-step
+        host state inside, so it can be captured in a CUDA graph (GraphedStep)."""
+        params = self.params
+        self.targets, self.target_weights = {}, {}
+        for task in params.tasks:
+            self.targets[task], self.target_weights[task] = create_shifted_targets(
+                self.decoder_inputs[task], self.seq_len_target[task]) if self.isTraining else (None, None)
+        from ._lib import capture_checkpoint as ck
+        ck("step start")
+        if self.isTraining:
             self.variables.zero_grad()
+        ck("zero_grad")
         # one Philox key per step: seed * 1000003 + global_step (see oracle train_step(dropout_seed=...))
         step_seed = int(params.get('dropout_seed', 0)) * 1000003 + int(self.global_step)
         self.encoder.dropout_seed = step_seed
@@ -180,6 +200,7 @@ class Seq2SeqModel(BaseParams):
         with ctx:
             self.encoder_hidden_states, self.time_major_states, self.seq_len_encs = \
                 self.encoder(self.encoder_inputs, self.seq_len, depth_of)
+            ck("encoder forward")
 
             # The auxiliary CTC heads only need the encoder states: they run on a side stream,
             # concurrently with the (latency-bound) attention decoders; autograd replays their
@@ -213,6 +234,7 @@ class Seq2SeqModel(BaseParams):
                             self.time_major_states[d], k, b, self.seq_len_encs[d], self.decoder_inputs[task],
                             self.seq_len_target[task], self.ctc_stash[task])
 
+            ck("ctc heads forward")
             self.outputs = {}
             for task in params.tasks:
                 d = params.num_layers[task]
@@ -220,6 +242,7 @@ class Seq2SeqModel(BaseParams):
                     self.decoder_inputs[task], self.seq_len_target[task],
                     self.encoder_hidden_states[d], self.seq_len_encs[d])
 
+            ck("decoders forward")
             if not self.isTraining:
                 return
             for task in params.tasks:
@@ -239,12 +262,20 @@ class Seq2SeqModel(BaseParams):
             self._loss_scale = torch.full((), scale, dtype=torch.float32, device=self.device)
             self._loss_scale_value = scale
         roots = [self.losses[t] for t in self.losses]
+        ck("losses")
         torch.autograd.backward(roots, [self._loss_scale] * len(roots))
+        ck("backward")
         for side in sides:
             main.wait_stream(side)
         ops.sync_wgrad_stream(self.device)
+        ck("joins")
         with torch.no_grad():
             self.total_loss = torch.stack([l.detach() for l in roots]).sum() * scale
+        ck("total_loss")
+
+    def _step_tail(self):
+        """Gradient all-reduce, clipping, optional Adam, step bookkeeping (seq2seq_model.py:148-155)."""
+        params = self.params
         if self.reducer is not None:
             self.reducer.allreduce_mean(self.variables.flat_grads())
         self.clip_gradients()
@@ -257,9 +288,20 @@ class Seq2SeqModel(BaseParams):
             ev.record()
             self._inflight.append(ev)
             if len(self._inflight) >= 2:          # step N-1 must be done before step N+1 is enqueued
-                self._inflight.pop(0).synchronize()
+                self._wait(self._inflight.pop(0))
 
     run_step = create_computational_graph
+
+    def graphed_step(self, batch):
+        """Captures the step for batches of this batch's shape in a CUDA graph; see GraphedStep."""
+        return GraphedStep(self, batch)
+
+    def _wait(self, event):
+        """Blocks the host on a step-completion event; the time spent here is the host's slack (host_wait_s)."""
+        import time
+        t0 = time.perf_counter()
+        event.synchronize()
+        self.host_wait_s = getattr(self, "host_wait_s", 0.0) + time.perf_counter() - t0
 
     def clip_gradients(self):
         """tf.clip_by_global_norm(gradients, max_gradient_norm) over the flat buffer.
@@ -321,3 +363,95 @@ class Seq2SeqModel(BaseParams):
         parser.add_argument("-lr_decay", "--learning_rate_decay_factor", default=0.5, type=float,
                             help="Learning rate decay factor")
         parser.add_argument("-avg", "--avg", default=False, action="store_true", help="Average the loss")
+
+
+class GraphedStep(object):
+    """One training step replayed from a CUDA graph.
+
+    The eager step issues ~200 kernel launches and ~12 ms of host work on several streams; when the host is slower
+    than the 15 ms device step (8 ranks sharing the host's cores) the GPU waits for it.  The step's kernel sequence
+    is a pure function of the batch SHAPE (B, padded T, U = max target length, max CTC label length), so it is
+    captured once -- forward, losses, backward with its weight-gradient and CTC side streams as parallel graph
+    branches -- and replayed with one launch.  Inputs are refilled in place (pinned staging -> the static device
+    buffers the captured kernels read); the gradient all-reduce, clipping and Adam stay eager after the replay.
+
+    Valid for batches with the captured shapes and the same maximum lengths; requires out_prob = out_prob_dec = 1
+    and samp_prob = 0 (their Philox keys are per-step kernel arguments).  `step(batch)` = Seq2SeqModel.run_step(batch).
+    """
+
+    def __init__(self, model, batch, warmup=2):
+        if not model.isTraining:
+            raise ValueError("GraphedStep captures the training step")
+        p = model.params
+        if p.encoder_params.out_prob < 1.0 or any(d.out_prob_dec < 1.0 or d.samp_prob > 0 for d in
+                                                   p.decoder_params.values()):
+            raise NotImplementedError("GraphedStep: dropout / scheduled sampling draw from per-step Philox keys "
+                                      "passed by value; use the eager run_step")
+        self.model = model
+        model._static_inputs = {}
+        self.prepared = model.get_batch(batch)
+        self.signature = self._signature(self.prepared)
+        cur = torch.cuda.current_stream()
+        # eager warm-up ON THE CAPTURE STREAM: lazy variables, workspaces, side streams and the allocator reach their
+        # steady state, and autograd's cached gradient accumulators are bound to the stream that will be captured
+        # (an accumulator created on the default stream would run -- uncaptured -- on the default stream)
+        self.stream = torch.cuda.Stream(device=model.device)
+        self.stream.wait_stream(cur)
+        with torch.cuda.stream(self.stream):
+            for _ in range(warmup):
+                model.run_step(prepared=self.prepared)
+        while model._inflight:
+            model._inflight.pop(0).synchronize()
+        torch.cuda.synchronize()
+        # drop the eager step's autograd graph before capturing
+        model.losses, model.outputs, model.total_loss = {}, {}, None
+        model.encoder_hidden_states = model.time_major_states = model.seq_len_encs = None
+        for d in model.decoder.values():
+            d.stash.clear()
+        for st_ in getattr(model, "ctc_stash", {}).values():
+            st_.clear()
+        import gc
+        gc.collect()
+        self.graph = torch.cuda.CUDAGraph()
+        n0 = _launch_count()
+        model.encoder_inputs, model.decoder_inputs, model.seq_len, model.seq_len_target = self.prepared
+        failure = None
+        try:
+            with torch.cuda.graph(self.graph, stream=self.stream, capture_error_mode="relaxed"):
+                try:
+                    model._step_core()
+                except BaseException as e:      # ending an aborted capture raises too and would mask this one
+                    failure = e
+        except BaseException as e:
+            failure = failure or e
+        if failure is not None:
+            raise RuntimeError("GraphedStep: capturing the step failed: %r" % (failure,)) from failure
+        self.launches_per_step = _launch_count() - n0
+        cur.synchronize()
+
+    @staticmethod
+    def _signature(prepared):
+        enc_in, dec_in, enc_len, dec_len = prepared
+        sig = [tuple(enc_in.shape), int(enc_len._host.max())]
+        for k in sorted(dec_len):
+            sig.append((k, tuple(dec_in[k].shape), int(dec_len[k]._host.max())))
+        return sig
+
+    def step(self, batch=None):
+        model = self.model
+        if batch is not None:
+            prepared = model.get_batch(batch)          # refills the static buffers in place
+            if self._signature(prepared) != self.signature or prepared[0] is not self.prepared[0]:
+                raise ValueError("GraphedStep: batch shape / maximum lengths differ from the captured step; capture "
+                                 "one GraphedStep per shape bucket or use run_step")
+        while len(model._inflight) >= 2:
+            model._wait(model._inflight.pop(0))
+        self.graph.replay()
+        model._step_tail()
+
+    __call__ = step
+
+
+def _launch_count():
+    from ._lib import launch_count
+    return launch_count()

@@ -26,6 +26,8 @@ extern "C" {
 #endif
 
 int e2e_version(void);
+/* CUDA-graph capture state of a stream (debug aid for GraphedStep): 0 none, 1 active, 2 invalidated, -1 error */
+int e2e_capture_status(void* stream);
 const char* e2e_last_error(void);
 int e2e_sm_count(void);
 /* number of kernels this library has launched (host counter); reset != 0 clears it */

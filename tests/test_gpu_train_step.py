@@ -173,6 +173,37 @@ def test_sample_rows_kernel_matches_oracle():
     assert np.abs(freq - p).max() < 0.015
 
 
+@pytest.mark.parametrize("cname", ["tiny_b", "cfg1"])
+def test_graphed_step_matches_eager_and_oracle(cname):
+    """GraphedStep: the step captured in a CUDA graph (side streams included) and replayed (a) on the captured batch
+    and (b) on another batch of the same shape refilled into the static input buffers must reproduce the eager step,
+    which is itself checked against the oracle.  A batch with other maximum lengths must be refused."""
+    cfg = synth.get_config(cname)
+    w = synth.make_weights(cfg, bias_noise=0.1)
+    batch = synth.make_batch(cfg)
+    perm = np.roll(np.arange(cfg.B), 1)
+    batch2 = {k: (np.asarray(v)[perm].copy() if hasattr(v, "shape") and np.asarray(v).shape[:1] == (cfg.B,) else v)
+              for k, v in batch.items()}
+    batch2["logmel"] = (batch2["logmel"] * 0.9 + 0.05).astype(batch["logmel"].dtype)
+    model = build_model(cfg, w, device="cuda:0")
+    gs = model.graphed_step(batch)
+    assert gs.launches_per_step > 20
+    for b in (batch, batch2, batch):
+        gs.step(b)
+        ops.check_device_errors("cuda:0")
+        ref = om.train_step(w, b, num_layers={"char": cfg.L}, ctc_tasks=cfg.ctc)
+        compare_step(model, ref, rtol=RTOL)
+    eager = build_model(cfg, w, device="cuda:0")
+    eager.run_step(batch)
+    g0, g1 = eager.gradients(), model.gradients()
+    for k in g0:
+        assert np.abs(g0[k] - g1[k]).max() <= 1e-5 * max(np.abs(g0[k]).max(), 1e-6), k
+    short = {k: v for k, v in batch.items()}
+    short["logmel_len"] = np.maximum(np.asarray(batch["logmel_len"]) - 1, 1)
+    with pytest.raises(ValueError):
+        gs.step(short)
+
+
 def test_adam_updates_match_oracle():
     """apply_updates=True: three Adam steps (fused flat-buffer kernel) against the oracle's TF-formula Adam."""
     cfg = synth.get_config("tiny_b")
