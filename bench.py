@@ -282,7 +282,14 @@ def main():
     total_frames = sum_over_ranks(frames)
     value = total_frames * K / (ms * 1e-3)
 
-    # ---------------- end to end from host buffers ("e2e")
+    # ---------------- end to end from host buffers ("e2e"): the batch lives in PINNED host memory (what a loader with
+    # pinned output buffers hands over); every step copies it host -> device and reads the loss back
+    host_batch = dict(batch)
+    host_batch["logmel"] = torch.from_numpy(np.ascontiguousarray(batch["logmel"], np.float32)).pin_memory()
+    if use_graph:
+        step_host = lambda: gs.step(host_batch)
+    else:
+        step_host = lambda: model.run_step(host_batch)
     for _ in range(2):
         step_host()
         float(model.total_loss)
@@ -300,6 +307,9 @@ def main():
            "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / K}
     ops.check_device_errors(dev)
 
+    if world > 1:
+        barrier()
+        dist.destroy_process_group()
     if rank != 0:
         return
     # ---------------- per-kernel-class breakdown and roofline (CUDA events of the timed region)

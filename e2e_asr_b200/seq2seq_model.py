@@ -100,19 +100,24 @@ class Seq2SeqModel(BaseParams):
     # ------------------------------------------------------------------
     def _to_device(self, key, arr, dtype):
         """Host array -> device through a reusable pinned staging buffer."""
+        buf = None
         if isinstance(arr, torch.Tensor):
             if arr.device == self.device:
                 return arr.to(dtype)
-            arr = arr.numpy()
-        arr = np.ascontiguousarray(arr)
-        t = torch.from_numpy(arr)
-        if t.dtype != dtype:
-            t = t.to(dtype)
-        buf = self._pinned.get(key)
-        if buf is None or buf.shape != t.shape or buf.dtype != dtype:
-            buf = torch.empty(t.shape, dtype=dtype).pin_memory()
-            self._pinned[key] = buf
-        buf.copy_(t)
+            if arr.dtype == dtype and arr.is_contiguous() and arr.is_pinned():
+                buf = arr               # a loader that hands out pinned batches: copy straight from its buffer
+            else:
+                arr = arr.numpy()
+        if buf is None:
+            arr = np.ascontiguousarray(arr)
+            t = torch.from_numpy(arr)
+            if t.dtype != dtype:
+                t = t.to(dtype)
+            buf = self._pinned.get(key)
+            if buf is None or buf.shape != t.shape or buf.dtype != dtype:
+                buf = torch.empty(t.shape, dtype=dtype).pin_memory()
+                self._pinned[key] = buf
+            buf.copy_(t)
         static = getattr(self, "_static_inputs", None)
         if static is not None:
             # graphed step: the captured kernels read these very buffers, so refill them in place
@@ -395,7 +400,9 @@ class GraphedStep(object):
         # eager warm-up ON THE CAPTURE STREAM: lazy variables, workspaces, side streams and the allocator reach their
         # steady state, and autograd's cached gradient accumulators are bound to the stream that will be captured
         # (an accumulator created on the default stream would run -- uncaptured -- on the default stream)
-        self.stream = torch.cuda.Stream(device=model.device)
+        # high priority: the captured kernel nodes of the critical path (recurrences, decoder loop) inherit it and
+        # are scheduled ahead of the weight-gradient / CTC branches that only have to finish by the end of the step
+        self.stream = torch.cuda.Stream(device=model.device, priority=-1)
         self.stream.wait_stream(cur)
         with torch.cuda.stream(self.stream):
             for _ in range(warmup):
