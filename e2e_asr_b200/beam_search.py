@@ -12,7 +12,7 @@ hypothesis of every utterance is one row of a float64 batch on the device
 (e2e_*_f64 kernels keep the reference's dtype flow); only the
 O(k^2) candidate merge per utterance -- `np.argpartition` over k*k scores,
 back-pointers `idx // k`, EOS bookkeeping (beam_search.py:294-329) -- runs on the
-host, on k-sized arrays, exactly as the reference does it.
+host as the reference does it, vectorised over utterances (`merge_candidates`).
 """
 import numpy as np
 import torch
@@ -22,6 +22,54 @@ from ._lib import call
 from .base_params import BaseParams, Bunch
 from .data_utils import EOS_ID, GO_ID
 from .host_utils import BeamEntry  # noqa: F401  (record type kept for API parity)
+
+
+def merge_candidates(utt, scores, k_u, idx_h, val_h, step, word_ins_penalty):
+    """Candidate merge of one step for every utterance at once (beam_search.py:255-266 for the GO step, :294-329
+    after it), vectorised over utterances with NumPy.
+
+    utt [n] (ascending): utterance of each hypothesis row; scores [n]: its score; k_u [N]: current beam size per
+    utterance; idx_h / val_h [n, beam]: per-row top tokens and their log-probabilities (entries >= k_u are unused).
+    Per utterance the reference concatenates `val[i, :k] + score[i]` over its rows, takes `np.argpartition(., -k)[-k:]`
+    IN THAT ORDER, derives back-pointers `idx // k`, adds `word_ins_penalty * len(seq)` and retires EOS candidates
+    (the beam shrinks).  Utterances with the same (rows, k) are stacked and partitioned row-wise -- the same
+    introselect on the same 1-D data, so the selection and its order are the reference's.
+
+    Returns (rows, finished): rows = dict(utt, parent, tok, score) of the surviving hypotheses ordered by
+    (utterance, candidate position); finished = list of (utterance, parent row, score) of candidates that emitted
+    EOS, in the reference's append order within each utterance.  k_u is decremented in place."""
+    n = len(utt)
+    starts = np.flatnonzero(np.r_[True, utt[1:] != utt[:-1]]) if n else np.zeros(0, np.int64)
+    counts = np.diff(np.r_[starts, n])
+    us = utt[starts]
+    ks = k_u[us]
+    parts = []
+    for c, k in sorted(set(zip(counts.tolist(), ks.tolist()))):
+        if k <= 0:
+            continue
+        g = np.flatnonzero((counts == c) & (ks == k))
+        rows = starts[g][:, None] + np.arange(c)[None, :]                    # [G, c]
+        flat = (val_h[rows][:, :, :k] + scores[rows][:, :, None]).reshape(len(g), c * k)
+        toks = idx_h[rows][:, :, :k].reshape(len(g), c * k)
+        if step == 0:                                                        # single GO row: candidates in order
+            sel = np.tile(np.arange(k), (len(g), 1))
+        else:
+            sel = np.argpartition(flat, -k, axis=1)[:, -k:]
+        par = starts[g][:, None] + sel // k
+        parts.append((np.repeat(us[g], k), np.tile(np.arange(k), len(g)), par.reshape(-1),
+                      np.take_along_axis(toks, sel, 1).reshape(-1).astype(np.int64),
+                      np.take_along_axis(flat, sel, 1).reshape(-1) + word_ins_penalty * (step + 1)))
+    if not parts:
+        e = np.zeros(0, np.int64)
+        return dict(utt=e, parent=e, tok=e, score=np.zeros(0)), []
+    u_all, j_all, par_all, tok_all, sc_all = [np.concatenate(x) for x in zip(*parts)]
+    order = np.lexsort((j_all, u_all))
+    u_all, par_all, tok_all, sc_all = u_all[order], par_all[order], tok_all[order], sc_all[order]
+    eos = tok_all == EOS_ID
+    finished = [(int(u), int(p_), float(s_)) for u, p_, s_ in zip(u_all[eos], par_all[eos], sc_all[eos])]
+    np.subtract.at(k_u, u_all[eos], 1)
+    keep = ~eos
+    return dict(utt=u_all[keep], parent=par_all[keep], tok=tok_all[keep], score=sc_all[keep]), finished
 
 
 class BeamSearch(BaseParams):
@@ -117,11 +165,11 @@ class BeamSearch(BaseParams):
         HF = ops.gemm(enc_all, p.attn_enc_w, mode=0)                      # float32 x float32 (beam_search.py:148)
         Tmax = int(Ts.max())
 
-        # hypothesis rows (host bookkeeping): utterance, token sequence, model score
-        utt = list(range(N))
-        seqs = [[] for _ in range(N)]
-        scores = [0.0] * N
-        k_u = [beam] * N                  # current beam size per utterance (shrinks at EOS)
+        # hypothesis rows (host bookkeeping, NumPy arrays): utterance, token history, model score
+        utt = np.arange(N)
+        hist = np.zeros((N, 0), np.int64)     # tokens emitted so far, one row per hypothesis
+        scores = np.zeros(N, np.float64)
+        k_u = np.full(N, beam, np.int64)      # current beam size per utterance (shrinks at EOS)
         final = [[] for _ in range(N)]
         tok = np.full(N, GO_ID, np.int64)
         st = dict(dc=torch.zeros((N, Hd), **f64), dh=torch.zeros((N, Hd), **f64),
@@ -133,7 +181,7 @@ class BeamSearch(BaseParams):
         step = 0
         while step < self.MAX_STEPS and len(utt) > 0:
             n = len(utt)
-            tok_d = torch.from_numpy(tok).to(dev)
+            tok_d = torch.from_numpy(np.ascontiguousarray(tok)).to(dev)
             x = torch.empty((n, E), **f64)
             call("e2e_embed_gather_f64", n, E, p.embedding, tok_d, x, E)
             # decoder's LM-LSTM, SimpleProjection, InputProjection, decoder LSTM (beam_search.py:182-191)
@@ -144,7 +192,7 @@ class BeamSearch(BaseParams):
             # attention with the CELL state as query (beam_search.py:193), AttnProjection, OutputProjection
             y = self._gemm64(dc, p.attn_dec_w, p.attn_dec_b)
             ctx = torch.empty((n, D), **f64)
-            uidx = np.asarray(utt)
+            uidx = utt
             call("e2e_attn_beam_f64", n, A, D, Tmax, HF, enc_all, torch.from_numpy(offs[uidx]).to(dev),
                  torch.from_numpy(Ts[uidx]).to(dev), y, p.attn_v, ctx, D)
             proj = self._gemm64(torch.cat([dc, ctx], dim=1), p.attn_proj_w, p.attn_proj_b)
@@ -156,7 +204,7 @@ class BeamSearch(BaseParams):
                 mc, mh = self._lstm(x_lm, st["mc"], st["mh"], lp.lm_lstm_w, lp.lm_lstm_b)
                 lo = mh if lp.simple_w is None else self._gemm64(mh, lp.simple_w, lp.simple_b)
                 lm_logits = self._gemm64(lo, lp.out_w, lp.out_b)
-            krow = np.array([k_u[u] for u in utt], np.int32)
+            krow = k_u[utt].astype(np.int32)
             out_idx = torch.empty((n, beam), dtype=torch.int32, device=dev)
             out_val = torch.empty((n, beam), **f64)
             scratch = torch.empty((n, V), **f64)
@@ -164,57 +212,30 @@ class BeamSearch(BaseParams):
                  torch.from_numpy(krow).to(dev), beam, out_idx, out_val, scratch)
             idx_h = out_idx.cpu().numpy()
             val_h = out_val.cpu().numpy()
-            # ---- host: merge candidates per utterance (beam_search.py:294-329)
-            new_utt, new_seqs, new_scores, new_tok, parents = [], [], [], [], []
-            r = 0
-            while r < n:
-                u = utt[r]
-                r1 = r
-                while r1 < n and utt[r1] == u:
-                    r1 += 1
-                k = k_u[u]
-                if step == 0:                                              # single GO hypothesis (:255-266)
-                    cand_scores = val_h[r, :k]
-                    cand_tokens = idx_h[r, :k]
-                    sel = np.arange(k)
-                    par = np.zeros(k, np.int64)
-                    model_scores = cand_scores
-                else:
-                    all_scores = np.concatenate([val_h[i, :k] + scores[i] for i in range(r, r1)])
-                    cand_tokens = np.concatenate([idx_h[i, :k] for i in range(r, r1)])
-                    sel = np.argpartition(all_scores, -k)[-k:]
-                    par = sel // k
-                    model_scores = all_scores
-                for j in range(k):                                         # bound fixed before k shrinks (:310)
-                    pr = r + int(par[j])
-                    t_new = int(cand_tokens[sel[j]])
-                    seq = seqs[pr] + [t_new]
-                    sc = float(model_scores[sel[j]]) + sp.word_ins_penalty * len(seq)
-                    if t_new == EOS_ID:
-                        final[u].append((seq, sc))
-                        k_u[u] -= 1
-                    else:
-                        new_utt.append(u); new_seqs.append(seq); new_scores.append(sc)
-                        new_tok.append(t_new); parents.append(pr)
-                r = r1
+            # ---- host: merge candidates per utterance (beam_search.py:294-329), all utterances at once
+            new, finished = merge_candidates(utt, scores, k_u, idx_h, val_h, step, sp.word_ins_penalty)
+            for u, pr, sc in finished:
+                final[u].append((np.append(hist[pr], EOS_ID), sc))
             step += 1
-            if step >= self.MAX_STEPS or not new_utt:
+            parents = new["parent"]
+            hist = np.concatenate([hist[parents], new["tok"][:, None]], axis=1)
+            if step >= self.MAX_STEPS or len(parents) == 0:
                 # leftovers join the final list (beam_search.py:332)
-                for u, seq, sc in zip(new_utt, new_seqs, new_scores):
-                    final[u].append((seq, sc))
+                for u, seq, sc in zip(new["utt"], hist, new["score"]):
+                    final[int(u)].append((seq, float(sc)))
                 break
-            sel_rows = torch.from_numpy(np.asarray(parents, np.int64)).to(dev)
+            sel_rows = torch.from_numpy(parents).to(dev)
             st = dict(dc=dc.index_select(0, sel_rows), dh=dh.index_select(0, sel_rows),
                       lc=lc.index_select(0, sel_rows), lh=lh.index_select(0, sel_rows),
                       ctx=ctx.index_select(0, sel_rows))
             if self.use_lm:
                 st["mc"] = mc.index_select(0, sel_rows)
                 st["mh"] = mh.index_select(0, sel_rows)
-            utt, seqs, scores, tok = new_utt, new_seqs, new_scores, np.asarray(new_tok, np.int64)
+            utt, scores, tok = new["utt"], new["score"], new["tok"]
         outs, outs_sc = [], []
         for u in range(N):
             best = max(final[u], key=lambda e: e[1])                        # first maximum, no length norm (:336)
-            outs.append(np.stack(best[0], axis=0))
+            outs.append(np.asarray(best[0], np.int64))
             outs_sc.append(best[1])
         return (outs, outs_sc) if return_scores else outs
 

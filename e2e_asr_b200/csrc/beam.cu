@@ -9,41 +9,63 @@
 
 namespace e2e {
 
-// C[M,N] (f64) = A[M,K] (f64) . B[K,N] (f32 weights) + bias[N] (f32)       32x32 tile, 4x1 per thread... simple
-constexpr int DT = 32, DK = 16;
-__global__ void __launch_bounds__(256)
+// C[M,N] (f64) = A[M,K] (f64) . B[K,N] (f32 weights) + bias[N] (f32)
+// Register-tiled DFMA kernel: CTA = 64 x 64 output tile, 64 threads, 8 x 8 accumulators per thread (one k-step =
+// 8 + 8 shared-memory operands for 64 FMAs), several CTAs resident per SM to hide the global-load latency.
+// Thread (ty, tx) owns rows {16 i + 2 ty + e} and columns {16 j + 2 tx + e} (i, j < 4; e < 2): a quarter warp reads
+// 128 contiguous bytes of the B tile (conflict-free LDS.128) and one broadcast address of the A tile.
+constexpr int GT = 64, GK = 16;
+__global__ void __launch_bounds__(64)
 gemm_f64_kernel(int M, int N, int K, const double* __restrict__ A, int lda, const float* __restrict__ B, int ldb,
                 double* __restrict__ C, int ldc, const float* __restrict__ bias) {
-    __shared__ double As[DK][DT + 1];
-    __shared__ double Bs[DK][DT + 1];
-    const int tx = threadIdx.x % 32, ty = threadIdx.x / 32;      // 32 x 8 threads, 4 rows each
-    const int m0 = blockIdx.y * DT, n0 = blockIdx.x * DT;
-    double acc[4] = {0.0, 0.0, 0.0, 0.0};
-    for (int k0 = 0; k0 < K; k0 += DK) {
-        for (int i = threadIdx.x; i < DT * DK; i += 256) {
-            int r = i / DK, k = i % DK;
-            As[k][r] = (m0 + r < M && k0 + k < K) ? A[(size_t)(m0 + r) * lda + k0 + k] : 0.0;
+    __shared__ __align__(16) double As[GT][GK + 1];      // [m][k]
+    __shared__ __align__(16) double Bs[GK][GT];          // [k][n]
+    const int tid = threadIdx.x, tx = tid % 8, ty = tid / 8;
+    const int m0 = blockIdx.y * GT, n0 = blockIdx.x * GT;
+    double acc[8][8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[i][j] = 0.0;
+    for (int k0 = 0; k0 < K; k0 += GK) {
+        // A tile: 64 rows x 16 k (each row 128 contiguous bytes); B tile: 16 k x 64 columns of fp32
+#pragma unroll 4
+        for (int it = 0; it < GT * GK / 64; ++it) {
+            const int i = it * 64 + tid, r = i / GK, k = i % GK;
+            As[r][k] = (m0 + r < M && k0 + k < K) ? A[(size_t)(m0 + r) * lda + k0 + k] : 0.0;
         }
-        for (int i = threadIdx.x; i < DT * DK; i += 256) {
-            int k = i / DT, c = i % DT;
+#pragma unroll 4
+        for (int it = 0; it < GK * GT / 64; ++it) {
+            const int i = it * 64 + tid, k = i / GT, c = i % GT;
             Bs[k][c] = (k0 + k < K && n0 + c < N) ? (double)B[(size_t)(k0 + k) * ldb + n0 + c] : 0.0;
         }
         __syncthreads();
 #pragma unroll
-        for (int k = 0; k < DK; ++k) {
-            double b = Bs[k][tx];
+        for (int k = 0; k < GK; ++k) {
+            double a[8], b[8];
 #pragma unroll
-            for (int j = 0; j < 4; ++j) acc[j] = fma(As[k][ty * 4 + j], b, acc[j]);
+            for (int i = 0; i < 4; ++i) {
+                a[2 * i] = As[16 * i + 2 * ty][k];
+                a[2 * i + 1] = As[16 * i + 2 * ty + 1][k];
+                const double2 bv = *reinterpret_cast<const double2*>(&Bs[k][16 * i + 2 * tx]);
+                b[2 * i] = bv.x;
+                b[2 * i + 1] = bv.y;
+            }
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+#pragma unroll
+                for (int j = 0; j < 8; ++j) acc[i][j] = fma(a[i], b[j], acc[i][j]);
         }
         __syncthreads();
     }
-    const int n = n0 + tx;
-    if (n < N) {
-        double bv = bias ? (double)bias[n] : 0.0;
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            int m = m0 + ty * 4 + j;
-            if (m < M) C[(size_t)m * ldc + n] = acc[j] + bv;
+    for (int i = 0; i < 8; ++i) {
+        const int m = m0 + 16 * (i / 2) + 2 * ty + (i % 2);
+        if (m >= M) continue;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int n = n0 + 16 * (j / 2) + 2 * tx + (j % 2);
+            if (n < N) C[(size_t)m * ldc + n] = acc[i][j] + (bias ? (double)bias[n] : 0.0);
         }
     }
 }
@@ -51,7 +73,7 @@ gemm_f64_kernel(int M, int N, int K, const double* __restrict__ A, int lda, cons
 int gemm_f64(cudaStream_t st, int M, int N, int K, const double* A, int lda, const float* B, int ldb, double* C,
              int ldc, const float* bias) {
     if (M <= 0 || N <= 0) return 0;
-    gemm_f64_kernel<<<dim3(cdiv(N, DT), cdiv(M, DT)), 256, 0, st>>>(M, N, K, A, lda, B, ldb, C, ldc, bias);
+    gemm_f64_kernel<<<dim3(cdiv(N, GT), cdiv(M, GT)), 64, 0, st>>>(M, N, K, A, lda, B, ldb, C, ldc, bias);
     E2E_LAUNCH_CHECK();
     return 0;
 }

@@ -16,3 +16,12 @@ for n in (32, 256):
 from oracle import beam as ob
 t0 = time.perf_counter(); ref = ob.beam_search(w, encs[0], beam_size=10); dt = time.perf_counter() - t0
 print("oracle 1 utt: %.2f s, len %d, match %s" % (dt, len(ref), np.array_equal(ref, out[0])))
+from e2e_asr_b200 import _lib
+prof = _lib.Profiler(); _lib.PROFILER = prof
+e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+e0.record(); out = bs.decode_batch(encs[:256]); e1.record(); torch.cuda.synchronize()
+_lib.PROFILER = None
+summ = prof.summary()
+print("total ms", e0.elapsed_time(e1))
+for k, v in sorted(summ.items(), key=lambda kv: -kv[1]["ms"]):
+    print("%-28s %8.2f ms %6d calls" % (k, v["ms"], v["calls"]))
