@@ -70,10 +70,97 @@ gemm_f64_kernel(int M, int N, int K, const double* __restrict__ A, int lda, cons
     }
 }
 
+// Same product with a 2-stage cp.async pipeline (needs 16-byte-aligned rows: lda % 2 == 0, ldb % 4 == 0, K % 16 == 0):
+// 128 threads, thread (ty, tx) owns rows {16 i + 2 ty + e} (i < 4) and columns {32 j + 2 tx + e} (j < 2); the next
+// k-tile streams into the other shared-memory stage while this one is multiplied; B stays fp32 in shared memory and is
+// widened at the read.  Out-of-range rows / columns are zero-filled by cp.async's src-size operand.
+constexpr int PT = 64, PK = 16, PAS = PK + 2;      // A row stride in doubles: 18 (16-byte aligned rows, banks spread)
+__device__ __forceinline__ void cp_async16(void* dst, const void* src, int src_bytes) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"((uint32_t)__cvta_generic_to_shared(dst)),
+                 "l"(src), "r"(src_bytes) : "memory");
+}
+__global__ void __launch_bounds__(128)
+gemm_f64_pipe_kernel(int M, int N, int K, const double* __restrict__ A, int lda, const float* __restrict__ B, int ldb,
+                     double* __restrict__ C, int ldc, const float* __restrict__ bias) {
+    __shared__ __align__(16) double As[2][PT][PAS];
+    __shared__ __align__(16) float Bs[2][PK][PT];
+    const int tid = threadIdx.x, tx = tid % 16, ty = tid / 16;
+    const int m0 = blockIdx.y * PT, n0 = blockIdx.x * PT;
+    auto issue = [&](int stage, int k0) {
+        // A: 64 rows x 16 doubles = 512 chunks of 16 B; B: 16 rows x 64 floats = 256 chunks of 16 B
+#pragma unroll
+        for (int it = 0; it < 4; ++it) {
+            const int i = it * 128 + tid, r = i / 8, c = (i % 8) * 2;
+            const bool ok = m0 + r < M;
+            cp_async16(&As[stage][r][c], A + (size_t)(ok ? m0 + r : 0) * lda + k0 + c, ok ? 16 : 0);
+        }
+#pragma unroll
+        for (int it = 0; it < 2; ++it) {
+            const int i = it * 128 + tid, k = i / 16, c = (i % 16) * 4;
+            const int rem = N - (n0 + c);                       // columns left in this row of B
+            const int bytes = rem >= 4 ? 16 : (rem > 0 ? rem * 4 : 0);
+            cp_async16(&Bs[stage][k][c], B + (size_t)(k0 + k) * ldb + (rem > 0 ? n0 + c : 0), bytes);
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    double acc[8][4];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0.0;
+    const int nk = K / PK;
+    issue(0, 0);
+    for (int t = 0; t < nk; ++t) {
+        if (t + 1 < nk) {
+            issue((t + 1) & 1, (t + 1) * PK);
+            asm volatile("cp.async.wait_group 1;" ::: "memory");
+        } else {
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
+        }
+        __syncthreads();
+        const int s = t & 1;
+#pragma unroll
+        for (int k = 0; k < PK; ++k) {
+            double a[8], b[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                a[2 * i] = As[s][16 * i + 2 * ty][k];
+                a[2 * i + 1] = As[s][16 * i + 2 * ty + 1][k];
+            }
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+                const float2 bv = *reinterpret_cast<const float2*>(&Bs[s][k][32 * j + 2 * tx]);
+                b[2 * j] = (double)bv.x;
+                b[2 * j + 1] = (double)bv.y;
+            }
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[i][j] = fma(a[i], b[j], acc[i][j]);
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int m = m0 + 16 * (i / 2) + 2 * ty + (i % 2);
+        if (m >= M) continue;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int n = n0 + 32 * (j / 2) + 2 * tx + (j % 2);
+            if (n < N) C[(size_t)m * ldc + n] = acc[i][j] + (bias ? (double)bias[n] : 0.0);
+        }
+    }
+}
+
 int gemm_f64(cudaStream_t st, int M, int N, int K, const double* A, int lda, const float* B, int ldb, double* C,
              int ldc, const float* bias) {
     if (M <= 0 || N <= 0) return 0;
-    gemm_f64_kernel<<<dim3(cdiv(N, GT), cdiv(M, GT)), 64, 0, st>>>(M, N, K, A, lda, B, ldb, C, ldc, bias);
+    const bool aligned = K > 0 && K % PK == 0 && lda % 2 == 0 && ldb % 4 == 0 && ((uintptr_t)A & 15) == 0 &&
+                         ((uintptr_t)B & 15) == 0;
+    if (aligned)
+        gemm_f64_pipe_kernel<<<dim3(cdiv(N, PT), cdiv(M, PT)), 128, 0, st>>>(M, N, K, A, lda, B, ldb, C, ldc, bias);
+    else
+        gemm_f64_kernel<<<dim3(cdiv(N, GT), cdiv(M, GT)), 64, 0, st>>>(M, N, K, A, lda, B, ldb, C, ldc, bias);
     E2E_LAUNCH_CHECK();
     return 0;
 }

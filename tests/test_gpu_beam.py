@@ -53,3 +53,23 @@ def test_beam_k10_eval_batch_vs_oracle_and_lm_weight():
             np.testing.assert_array_equal(out[u], ref)
             # scores agree to float32 rounding of enc.AttnW (computed in float32 by the reference too)
             assert abs(sc[u] - rs) <= 1e-6 * max(1.0, abs(rs))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("M,N,K,lda_pad", [(2560, 1024, 512, 0), (2560, 1000, 256, 0), (37, 64, 16, 0),
+                                           (130, 257, 768, 2), (65, 129, 50, 0), (70, 40, 33, 1), (1, 8, 16, 0)])
+def test_gemm_f64_matches_numpy(M, N, K, lda_pad):
+    """e2e_gemm_f64 (float64 hypotheses x float32 weights + float32 bias, beam_search.py:182-199): both kernels --
+    the cp.async pipeline for 16-byte-aligned operands and the plain register-tiled one -- against NumPy float64."""
+    import torch
+    from e2e_asr_b200._lib import call
+    rng = np.random.default_rng(M * 31 + N * 7 + K)
+    a = rng.standard_normal((M, K + lda_pad))
+    b = rng.standard_normal((K, N)).astype(np.float32)
+    bias = rng.standard_normal(N).astype(np.float32)
+    ad = torch.from_numpy(a).cuda()[:, :K]
+    bd, biasd = torch.from_numpy(b).cuda(), torch.from_numpy(bias).cuda()
+    out = torch.full((M, N), float("nan"), dtype=torch.float64, device="cuda")
+    call("e2e_gemm_f64", M, N, K, ad, ad.stride(0), bd, bd.stride(0), out, out.stride(0), biasd)
+    ref = a[:, :K] @ b.astype(np.float64) + bias.astype(np.float64)
+    assert np.abs(out.cpu().numpy() - ref).max() <= 1e-12 * max(1.0, np.abs(ref).max())
