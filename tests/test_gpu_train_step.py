@@ -195,9 +195,11 @@ def test_graphed_step_matches_eager_and_oracle(cname):
         compare_step(model, ref, rtol=RTOL)
     eager = build_model(cfg, w, device="cuda:0")
     eager.run_step(batch)
+    # eager vs replay: the same kernels; split-K sums use atomics, so not bit-identical (same floor as compare_step)
     g0, g1 = eager.gradients(), model.gradients()
+    gmax = max(float(np.abs(g).max()) for g in g0.values())
     for k in g0:
-        assert np.abs(g0[k] - g1[k]).max() <= 1e-5 * max(np.abs(g0[k]).max(), 1e-6), k
+        assert np.abs(g0[k] - g1[k]).max() <= 2e-5 * max(np.abs(g0[k]).max(), 1e-4 * gmax), k
     short = {k: v for k, v in batch.items()}
     short["logmel_len"] = np.maximum(np.asarray(batch["logmel_len"]) - 1, 1)
     with pytest.raises(ValueError):
