@@ -444,8 +444,40 @@ class GraphedStep(object):
             sig.append((k, tuple(dec_in[k].shape), int(dec_len[k]._host.max())))
         return sig
 
+    def prefetch(self, batch):
+        """Starts the host -> device copy of the NEXT batch on a copy stream (into staging buffers, so it overlaps the
+        step that is running); the following `step()` without argument consumes it with device-to-device copies."""
+        model = self.model
+        if getattr(self, "_copy_stream", None) is None:
+            self._copy_stream = torch.cuda.Stream(device=model.device)
+            self._staging, self._staged, self._consumed = {}, None, None
+        if self._staged is not None:
+            self._staged[1].synchronize()       # the pinned staging buffers are about to be rewritten
+        if self._consumed is not None:
+            self._copy_stream.wait_event(self._consumed)    # the previous staged batch has been copied out
+        static = model._static_inputs
+        model._static_inputs = self._staging
+        try:
+            with torch.cuda.stream(self._copy_stream):
+                prepared = model.get_batch(batch)
+                done = torch.cuda.Event()
+                done.record()
+        finally:
+            model._static_inputs = static
+        if self._signature(prepared) != self.signature:
+            raise ValueError("GraphedStep: batch shape / maximum lengths differ from the captured step")
+        self._staged = (prepared, done)
+
     def step(self, batch=None):
         model = self.model
+        if batch is None and getattr(self, "_staged", None) is not None:
+            _, done = self._staged
+            torch.cuda.current_stream().wait_event(done)
+            for key, src in self._staging.items():
+                model._static_inputs[key].copy_(src, non_blocking=True)
+            self._consumed = torch.cuda.Event()
+            self._consumed.record()
+            self._staged = None
         if batch is not None:
             prepared = model.get_batch(batch)          # refills the static buffers in place
             if self._signature(prepared) != self.signature or prepared[0] is not self.prepared[0]:

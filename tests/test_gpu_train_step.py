@@ -193,6 +193,14 @@ def test_graphed_step_matches_eager_and_oracle(cname):
         ops.check_device_errors("cuda:0")
         ref = om.train_step(w, b, num_layers={"char": cfg.L}, ctc_tasks=cfg.ctc)
         compare_step(model, ref, rtol=RTOL)
+    # double-buffered input pipeline: prefetch() stages the next batch on a copy stream, step() consumes it
+    ref2 = om.train_step(w, batch2, num_layers={"char": cfg.L}, ctc_tasks=cfg.ctc)
+    gs.prefetch(batch2)
+    gs.step()
+    gs.prefetch(batch)
+    compare_step(model, ref2, rtol=RTOL)
+    gs.step()
+    compare_step(model, ref, rtol=RTOL)
     eager = build_model(cfg, w, device="cuda:0")
     eager.run_step(batch)
     # eager vs replay: the same kernels; split-K sums use atomics, so not bit-identical (same floor as compare_step)
