@@ -84,6 +84,8 @@ class AttnDecoder(Decoder):
                                             getattr(self, "dropout_seed", 0), getattr(self, "dropout_stream", 0),
                                             lm_drop=lm_drop)
                 decoder_inp = self.stash["realized_ids"] = ids
+            # teacher-forced ids are known when the step starts: the LM side may run ahead of the encoder
+            self.stash["early_lm"] = rule == "teacher"
             return ops.attn_decoder_apply(
                 enc, v["emb"], v["attn_w"], v["attn_v"], v["lm_k"], v["lm_b"], v["dec_k"], v["dec_b"], v["q_k"],
                 v["q_b"], v["ap_k"], v["ap_b"], v["out_k"], v["out_b"], v["in_k"], v["in_b"], v["sp_k"], v["sp_b"],

@@ -4,8 +4,10 @@ PyTorch is used for device-memory allocation, stream plumbing and the autograd
 graph between modules only; every FLOP of the hot path runs in
 libe2e_asr_b200.so.  There is no eager/CPU fallback.
 """
-import numpy as np
+import contextlib
 import ctypes
+
+import numpy as np
 
 import torch
 
@@ -260,6 +262,18 @@ def enable_wgrad_stream(device, enabled=True):
         ensure_workspace(device, nbytes=1 << 30, stream=_WGRAD[key]["enc"])
         ensure_workspace(device, nbytes=256 << 20, stream=_WGRAD[key]["dec"])
     return _WGRAD[key]
+
+
+_STEP_START = {}
+
+
+def mark_step_start(device):
+    """Records "the step's inputs and parameters are ready" on the current stream.  Work that depends on nothing
+    else -- the decoder's LM-LSTM over the teacher-forced ids -- may start from this event on a side stream instead of
+    queueing behind the encoder."""
+    ev = torch.cuda.Event()
+    ev.record()
+    _STEP_START[str(torch.device(device))] = ev
 
 
 def sync_wgrad_stream(device):
@@ -526,28 +540,45 @@ class AttnDecoderFnV2(torch.autograd.Function):
         assert r1 == 1, "encoder states must be batch-major"
         Tp = r0
         ids = ids[:U].contiguous()
-        u = torch.empty((U * B, E), **f32)
-        call("e2e_embed_gather", U * B, E, emb, ids, u)
-        Wx_lm, Wh_lm, bp_lm = _pack_lstm([lm_k], [lm_b], E, Hl, dev)
-        G_lm = gemm(u, Wx_lm, bias=bp_lm)
-        hl = torch.zeros((U * B, Hl), **f32)
-        C_lm = torch.empty((U * B, Hl), **f32)
-        call("e2e_lstm_rec_fwd", B, U, U, Hl, 1, 1, B, G_lm, hl, C_lm, Wh_lm, lens_i32, st["ctr"],
-             st["ctr"].numel() * 4, st["err"], work=float(U), tag="lm_rec_fwd")
-        # DropoutWrapper on lm_cell: its OUTPUT is dropped, the recurrent state is not (decoder.py:60-63)
-        hl_out = hl
-        if lm_drop is not None:
-            hl_out = torch.empty_like(hl)
-            call("e2e_dropout", hl.numel(), hl, hl_out, float(lm_drop[0]), int(lm_drop[1]), int(lm_drop[2]), 0)
-        m = gemm(hl_out, sp_k, bias=sp_b) if sp_k is not None else hl_out
-        pre = gemm(m, in_k[:Hd], bias=in_b)                          # [U*B, E]
-        # decoder-LSTM kernel in gate-interleaved layout, with the ctx half of InputProjection folded in
-        W_ch = torch.empty((D + Hd, 4 * Hd), **f32)
-        Wx_dec = torch.empty((E, 4 * Hd), **f32)
-        bp_dec = torch.empty((4 * Hd,), **f32)
-        call("e2e_lstm_pack_weights", E, Hd, dec_k, dec_b, Wx_dec, 4 * Hd, 0, W_ch[D:], bp_dec)
-        gemm(in_k[Hd:], Wx_dec, out=W_ch[:D])                        # W_cx = W_in_c . Wx
-        pre_g = gemm(pre, Wx_dec, bias=bp_dec)                       # [U*B, 4Hd]
+        # The LM side of the decoder (embedding -> LM-LSTM -> InputProjection -> decoder-gate pre-activations) reads only
+        # the teacher-forced ids and parameters: with the side streams on, it runs on the "dec" stream from the step's
+        # start event, concurrently with the encoder, and the main stream joins it here.
+        side = _WGRAD.get(str(dev), {}).get("dec")
+        main = torch.cuda.current_stream()
+        start = _STEP_START.pop(str(dev), None) if stash is not None and stash.get("early_lm") else None
+        if side is not None:
+            if start is not None:
+                side.wait_event(start)
+            else:
+                side.wait_stream(main)
+        ctr = st["ctr_side"] if side is not None else st["ctr"]
+        with (torch.cuda.stream(side) if side is not None else contextlib.nullcontext()):
+            u = torch.empty((U * B, E), **f32)
+            call("e2e_embed_gather", U * B, E, emb, ids, u)
+            Wx_lm, Wh_lm, bp_lm = _pack_lstm([lm_k], [lm_b], E, Hl, dev)
+            G_lm = gemm(u, Wx_lm, bias=bp_lm)
+            hl = torch.zeros((U * B, Hl), **f32)
+            C_lm = torch.empty((U * B, Hl), **f32)
+            call("e2e_lstm_rec_fwd", B, U, U, Hl, 1, 1, B, G_lm, hl, C_lm, Wh_lm, lens_i32, ctr,
+                 ctr.numel() * 4, st["err"], work=float(U), tag="lm_rec_fwd")
+            # DropoutWrapper on lm_cell: its OUTPUT is dropped, the recurrent state is not (decoder.py:60-63)
+            hl_out = hl
+            if lm_drop is not None:
+                hl_out = torch.empty_like(hl)
+                call("e2e_dropout", hl.numel(), hl, hl_out, float(lm_drop[0]), int(lm_drop[1]), int(lm_drop[2]), 0)
+            m = gemm(hl_out, sp_k, bias=sp_b) if sp_k is not None else hl_out
+            pre = gemm(m, in_k[:Hd], bias=in_b)                          # [U*B, E]
+            # decoder-LSTM kernel in gate-interleaved layout, with the ctx half of InputProjection folded in
+            W_ch = torch.empty((D + Hd, 4 * Hd), **f32)
+            Wx_dec = torch.empty((E, 4 * Hd), **f32)
+            bp_dec = torch.empty((4 * Hd,), **f32)
+            call("e2e_lstm_pack_weights", E, Hd, dec_k, dec_b, Wx_dec, 4 * Hd, 0, W_ch[D:], bp_dec)
+            gemm(in_k[Hd:], Wx_dec, out=W_ch[:D])                        # W_cx = W_in_c . Wx
+            pre_g = gemm(pre, Wx_dec, bias=bp_dec)                       # [U*B, 4Hd]
+        if side is not None:
+            main.wait_stream(side)
+            for t_ in (u, Wx_lm, Wh_lm, bp_lm, G_lm, hl, C_lm, hl_out, m, pre, W_ch, Wx_dec, bp_dec, pre_g):
+                t_.record_stream(main)
         HF = gemm(enc_flat, attn_w.view(D, A))
         bufs = dict(cat=torch.empty((U * B, Hd + D), **f32), hprev=torch.zeros((U * B, Hd), **f32),
                     cprev=torch.zeros((U * B, Hd), **f32), acts=torch.empty((U * B, 4 * Hd), **f32),

@@ -194,6 +194,9 @@ class Seq2SeqModel(BaseParams):
         if self.isTraining:
             self.variables.zero_grad()
         ck("zero_grad")
+        if self.isTraining and getattr(params, "overlap_weight_grads", True):
+            ops.enable_wgrad_stream(self.device)
+            ops.mark_step_start(self.device)
         # one Philox key per step: seed * 1000003 + global_step (see oracle train_step(dropout_seed=...))
         step_seed = int(params.get('dropout_seed', 0)) * 1000003 + int(self.global_step)
         self.encoder.dropout_seed = step_seed
