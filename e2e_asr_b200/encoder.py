@@ -46,8 +46,6 @@ class Encoder(BaseParams):
         if not p.use_lstm:
             raise NotImplementedError("Encoder: use_lstm=False (GRUCell, encoder.py:48) is not built yet; "
                                       "pass use_lstm=True (the reference CLI default, encoder.py:187)")
-        if not p.bi_dir:
-            raise NotImplementedError("Encoder: bi_dir=False is not built yet")
         if not (0.0 < p.out_prob <= 1.0):
             raise ValueError("Encoder: out_prob=%g must be in (0, 1]" % p.out_prob)
         if p.skip_step not in (1, 2):
@@ -58,14 +56,18 @@ class Encoder(BaseParams):
         vs = self.variables if self.variables is not None else default_store()
         H = self.params.hidden_size
         out = []
-        for d in ("fw", "bw"):
-            base = "model/encoder/RNNLayer%d/bidirectional_rnn/%s/basic_lstm_cell/" % (layer_depth, d)
+        if self.params.bi_dir:
+            bases = ["model/encoder/RNNLayer%d/bidirectional_rnn/%s/basic_lstm_cell/" % (layer_depth, d)
+                     for d in ("fw", "bw")]
+        else:   # tf.nn.dynamic_rnn(..., scope=str(layer_depth)) inside the RNNLayer<d> scope (encoder.py:86-89)
+            bases = ["model/encoder/RNNLayer%d/%d/basic_lstm_cell/" % (layer_depth, layer_depth)]
+        for base in bases:
             out.append(vs.get(base + "kernel", (in_size + H, 4 * H), ("uniform", 0.075)))
             out.append(vs.get(base + "bias", (4 * H,), ("zeros",)))
-        return out
+        return out + [None] * (4 - len(out))
 
     def _layer_encoder_input(self, x_padded, lens_i32, max_len, layer_depth=1):
-        """Run one BiLSTM layer on a padded batch-major buffer (encoder.py:55-91)."""
+        """Run one (Bi)LSTM layer on a padded batch-major buffer (encoder.py:55-91)."""
         k_fw, b_fw, k_bw, b_bw = self._layer_vars(layer_depth, x_padded.shape[2])
         out = ops.BiLSTMLayerFn.apply(x_padded, k_fw, b_fw, k_bw, b_bw, lens_i32, max_len)
         if self.isTraining and self.params.out_prob < 1.0:

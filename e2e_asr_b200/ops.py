@@ -284,80 +284,83 @@ def sync_wgrad_stream(device):
 
 
 class BiLSTMLayerFn(torch.autograd.Function):
-    """One bidirectional LSTM encoder layer over a zero-padded batch-major buffer
-    (reference Encoder._layer_encoder_input, encoder.py:55-91).
+    """One LSTM encoder layer over a zero-padded batch-major buffer (reference
+    Encoder._layer_encoder_input, encoder.py:55-91): bidirectional (bidirectional_dynamic_rnn, fw | bw
+    concatenated) or, with k_bw = b_bw = None, forward only (dynamic_rnn, bi_dir=False).
 
-    x: [B, Tp, I] contiguous with Tp >= max(len)+1; returns [B, Tp, 2H] (fw | bw),
-    zero for t >= len.  The pyramid (encoder.py:94-119) is then a free reshape.
+    x: [B, Tp, I] contiguous with Tp >= max(len)+1; returns [B, Tp, nd*H], zero for t >= len.
+    The pyramid (encoder.py:94-119) is then a free reshape.
     """
 
     @staticmethod
     def forward(ctx, x, k_fw, b_fw, k_bw, b_bw, lens_i32, T):
         B, Tp, I = x.shape
         H = k_fw.shape[1] // 4
+        nd = 1 if k_bw is None else 2
         dev = x.device
         assert x.is_contiguous() and Tp >= T + 1
         st = _dev_state(dev)
-        Wx, Wh, bp = _pack_lstm([k_fw, k_bw], [b_fw, b_bw], I, H, dev)
+        Wx, Wh, bp = _pack_lstm([k_fw, k_bw][:nd], [b_fw, b_bw][:nd], I, H, dev)
         x2 = x.view(B * Tp, I)
         # 3xTF32 "small" halves, computed once per tensor and shared by every product it enters (fwd + bwd)
         x_lo, Wx_lo = split_lo(x2), split_lo(Wx)
-        G = gemm(x2, Wx, bias=bp, a_lo=x_lo, b_lo=Wx_lo)            # [B*Tp, 8H]
-        out = torch.zeros((B, Tp, 2 * H), dtype=torch.float32, device=dev)
-        Cst = torch.empty((B, Tp, 2, H), dtype=torch.float32, device=dev)
-        call("e2e_lstm_rec_fwd", B, T, Tp, H, 2, Tp, 1, G, out, Cst, Wh, lens_i32, st["ctr"],
+        G = gemm(x2, Wx, bias=bp, a_lo=x_lo, b_lo=Wx_lo)            # [B*Tp, nd*4H]
+        out = torch.zeros((B, Tp, nd * H), dtype=torch.float32, device=dev)
+        Cst = torch.empty((B, Tp, nd, H), dtype=torch.float32, device=dev)
+        call("e2e_lstm_rec_fwd", B, T, Tp, H, nd, Tp, 1, G, out, Cst, Wh, lens_i32, st["ctr"],
              st["ctr"].numel() * 4, st["err"], work=float(T), tag="enc_rec_fwd")
         ctx.save_for_backward(x, Wx, Wh, G, Cst, out, lens_i32)
         ctx.los = (x_lo, Wx_lo)
-        ctx.dims = (B, Tp, I, H, T)
-        # flat-gradient-buffer views of the four parameters (None for plain tensors)
-        ctx.grad_dst = tuple(getattr(t, "grad", None) for t in (k_fw, b_fw, k_bw, b_bw))
+        ctx.dims = (B, Tp, I, H, T, nd)
+        # flat-gradient-buffer views of the parameters (None for plain tensors)
+        ctx.grad_dst = tuple(getattr(t, "grad", None) for t in (k_fw, b_fw, k_bw, b_bw)[:2 * nd])
         return out
 
     @staticmethod
     def backward(ctx, dout):
         x, Wx, Wh, G, Cst, out, lens_i32 = ctx.saved_tensors
-        B, Tp, I, H, T = ctx.dims
+        B, Tp, I, H, T, nd = ctx.dims
         dev = x.device
         st = _dev_state(dev)
         dout = dout.contiguous()
-        call("e2e_lstm_rec_bwd", B, T, Tp, H, 2, Tp, 1, G, Cst, Wh, dout, lens_i32, st["ctr"],
+        call("e2e_lstm_rec_bwd", B, T, Tp, H, nd, Tp, 1, G, Cst, Wh, dout, lens_i32, st["ctr"],
              st["ctr"].numel() * 4, st["err"], work=float(T), tag="enc_rec_bwd")   # G now holds d(pre-activations)
         N = B * Tp
-        x2, o2 = x.view(N, I), out.view(N, 2 * H)
+        x2, o2 = x.view(N, I), out.view(N, nd * H)
         x_lo, Wx_lo = ctx.los
-        G_lo = split_lo(G)            # one split of dz serves the dX, dW_x and both dW_h products
+        G_lo = split_lo(G)            # one split of dz serves the dX, dW_x and the dW_h products
         dX = gemm(G, Wx, tb=True, a_lo=G_lo, b_lo=Wx_lo).view(B, Tp, I) if ctx.needs_input_grad[0] else None
 
         def weight_grads():
-            dWx = gemm(x2, G, ta=True, a_lo=x_lo, b_lo=G_lo)            # [I, 8H]
-            dWh = torch.empty((2, H, 4 * H), dtype=torch.float32, device=dev)
+            dWx = gemm(x2, G, ta=True, a_lo=x_lo, b_lo=G_lo)            # [I, nd*4H]
+            dWh = torch.empty((nd, H, 4 * H), dtype=torch.float32, device=dev)
             # h_{t-1}^T dz_t: fw pairs out[t-1] with dz[t], bw pairs out[t+1] with dz[t]; the flat
             # one-row shift never crosses an utterance because out[b, Tp-1] == 0 and dz[b, Tp-1] == 0.
             gemm(o2[:N - 1, 0:H], G[1:, 0:4 * H], ta=True, out=dWh[0],
                  b_lo=None if G_lo is None else G_lo[1:, 0:4 * H])
-            gemm(o2[1:, H:2 * H], G[:N - 1, 4 * H:8 * H], ta=True, out=dWh[1],
-                 b_lo=None if G_lo is None else G_lo[:N - 1, 4 * H:8 * H])
+            if nd == 2:
+                gemm(o2[1:, H:2 * H], G[:N - 1, 4 * H:8 * H], ta=True, out=dWh[1],
+                     b_lo=None if G_lo is None else G_lo[:N - 1, 4 * H:8 * H])
             dbp = colsum(G)
             return dWx, dWh, dbp
 
         side = _WGRAD.get(str(dev), {}).get("enc")
         dst = ctx.grad_dst
-        if side is not None and all(d is not None for d in dst) and all(ctx.needs_input_grad[1:5]):
+        pad = (None,) * (2 * (2 - nd))
+        if side is not None and all(d is not None for d in dst) and all(ctx.needs_input_grad[1:1 + 2 * nd]):
             main = torch.cuda.current_stream()
             side.wait_stream(main)
             with torch.cuda.stream(side):
                 dWx, dWh, dbp = weight_grads()
-                for d in range(2):      # += into the flat gradient buffer (what AccumulateGrad would do)
-                    call("e2e_lstm_unpack_grads", I, H, dst[2 * d], dst[2 * d + 1], dWx, 8 * H, d * 4 * H, dWh[d],
-                         dbp, 1)
+                for d in range(nd):     # += into the flat gradient buffer (what AccumulateGrad would do)
+                    call("e2e_lstm_unpack_grads", I, H, dst[2 * d], dst[2 * d + 1], dWx, nd * 4 * H, d * 4 * H,
+                         dWh[d], dbp, 1)
             for t_ in (x, G, out, x_lo, G_lo):
                 if t_ is not None:
                     t_.record_stream(side)
             return dX, None, None, None, None, None, None
         dWx, dWh, dbp = weight_grads()
-        dk_fw, db_fw, dk_bw, db_bw = _unpack_lstm(dWx, dWh, dbp, I, H, 2, dev)
-        return dX, dk_fw, db_fw, dk_bw, db_bw, None, None
+        return (dX,) + tuple(_unpack_lstm(dWx, dWh, dbp, I, H, nd, dev)) + pad + (None, None)
 
 
 # ---------------------------------------------------------------------------

@@ -27,6 +27,11 @@ CONFIGS = {
                  ctc={"phone_ctc": (3, 5), "state": (2, 9)}),
     "tiny_b": dict(B=5, T=37, F=12, H=16, L=4, V=23, U=9, E=12, A=8, Hd=16, Hl=8,
                    ctc={"phone_ctc": (3, 6)}),
+    # tiny_uni / uni256: forward-only encoder (bi_dir=False, tf.nn.dynamic_rnn)
+    "tiny_uni": dict(B=4, T=29, F=10, H=16, L=3, V=19, U=7, E=12, A=8, Hd=16, Hl=8, bi_dir=False,
+                     ctc={"phone_ctc": (2, 6)}),
+    "uni256": dict(B=3, T=40, F=16, H=256, L=2, V=31, U=6, E=32, A=16, Hd=32, Hl=32, bi_dir=False,
+                   ctc={"phone_ctc": (2, 6)}),
     # wide_small: cfg-5's widths at unit-test size (H=512 -> L2-exchange recurrence, D=1024 -> per-step decoder)
     "wide_small": dict(B=3, T=24, F=8, H=512, L=2, V=17, U=5, E=16, A=16, Hd=32, Hl=16,
                        ctc={"phone_ctc": (1, 5)}),
@@ -58,13 +63,14 @@ def layer_input_sizes(cfg, skip_step=2, max_scaling_down=8):
     """Input width of every encoder layer (reference encoder.py:154-178)."""
     sizes, res = [], 1
     width = cfg.F
+    nd = 2 if cfg.get("bi_dir", True) else 1
     for i in range(cfg.L):
         sizes.append(width)
         if skip_step > 1 and i != cfg.L - 1 and res < max_scaling_down:
-            width = 2 * cfg.H * skip_step
+            width = nd * cfg.H * skip_step
             res *= skip_step
         else:
-            width = 2 * cfg.H
+            width = nd * cfg.H
     return sizes
 
 
@@ -94,12 +100,14 @@ def make_weights(cfg, seed=WEIGHT_SEED, tasks=("char",), bias_noise=0.0):
             return rng.uniform(-bias_noise, bias_noise, size=(n,)).astype(np.float32)
         return np.zeros((n,), np.float32)
 
+    bi_dir = cfg.get("bi_dir", True)
     for l, I in enumerate(layer_input_sizes(cfg), start=1):
-        for d in ("fw", "bw"):
-            base = "model/encoder/RNNLayer%d/bidirectional_rnn/%s/basic_lstm_cell/" % (l, d)
+        bases = ["model/encoder/RNNLayer%d/bidirectional_rnn/%s/basic_lstm_cell/" % (l, d) for d in ("fw", "bw")] \
+            if bi_dir else ["model/encoder/RNNLayer%d/%d/basic_lstm_cell/" % (l, l)]
+        for base in bases:
             w[base + "kernel"] = rng.uniform(-0.075, 0.075, size=(I + H, 4 * H)).astype(np.float32)
             w[base + "bias"] = bias(4 * H)
-    D = 2 * H
+    D = (2 if bi_dir else 1) * H
     for task in tasks:
         V = cfg.V if task == "char" else cfg.get("V_" + task, cfg.V)
         p = "model/rnn_decoder_%s/" % task

@@ -214,6 +214,28 @@ def test_graphed_step_matches_eager_and_oracle(cname):
         gs.step(short)
 
 
+@pytest.mark.parametrize("cname,mode", [("tiny_uni", "fp32"), ("uni256", "fp32"), ("uni256", "tf32x3")])
+def test_unidirectional_encoder_matches_oracle(cname, mode):
+    """bi_dir=False (encoder.py:86-89): forward-only tf.nn.dynamic_rnn layers, D = H, variables named
+    RNNLayer<d>/<d>/basic_lstm_cell/*; the recurrence kernels run with one direction (H=16: generic kernel, H=256:
+    the cluster kernel)."""
+    cfg = synth.get_config(cname)
+    w = synth.make_weights(cfg, bias_noise=0.1)
+    batch = synth.make_batch(cfg)
+    ref = om.train_step(w, batch, num_layers={"char": cfg.L}, ctc_tasks=cfg.ctc, enc_params={"bi_dir": False})
+    ops.set_gemm_mode(mode)
+    try:
+        model = build_model(cfg, w, device="cuda:0")
+        assert not model.params.encoder_params.bi_dir
+        for _ in range(2):
+            model.run_step(batch)
+            ops.check_device_errors("cuda:0")
+            compare_step(model, ref, rtol=RTOL)
+        assert model.encoder_hidden_states[cfg.L].shape[2] == cfg.H
+    finally:
+        ops.set_gemm_mode("fp32")
+
+
 def test_adam_updates_match_oracle():
     """apply_updates=True: three Adam steps (fused flat-buffer kernel) against the oracle's TF-formula Adam."""
     cfg = synth.get_config("tiny_b")

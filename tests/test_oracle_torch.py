@@ -288,3 +288,50 @@ def test_adam_matches_tf_formula():
             np.testing.assert_allclose(p[k], ref[k], rtol=1e-12)
     # first step moves every coordinate by ~lr * sign(g)
     assert st["t"] == 3
+
+
+def test_unidirectional_encoder_forward_vs_torch_and_finite_differences():
+    """bi_dir=False (encoder.py:86-89, tf.nn.dynamic_rnn): the forward-only layer against torch.nn.LSTM on packed
+    sequences, and the whole forward-only step against float64 central differences."""
+    rng = np.random.Generator(np.random.PCG64(11))
+    B, T, I, H = 4, 11, 5, 6
+    X = rng.standard_normal((B, T, I))
+    lens = np.array([11, 7, 2, 9])
+    for b in range(B):
+        X[b, lens[b]:] = 0
+    k = rng.uniform(-0.5, 0.5, (I + H, 4 * H))
+    bvec = rng.uniform(-0.5, 0.5, (4 * H,))
+    out, _ = om.birnn_layer_fwd(X, lens, k, bvec)
+    assert out.shape == (B, T, H)
+    lstm = torch.nn.LSTM(I, H, batch_first=True).double()
+
+    def reorder(m):
+        i, j, f, o = np.split(m, 4, axis=-1)
+        return np.concatenate([i, f, j, o], axis=-1)
+    with torch.no_grad():
+        kk, bb = reorder(k), reorder(bvec.copy())
+        bb[H:2 * H] += 1.0
+        lstm.weight_ih_l0.copy_(_t(kk[:I].T)); lstm.weight_hh_l0.copy_(_t(kk[I:].T))
+        lstm.bias_ih_l0.copy_(_t(bb)); lstm.bias_hh_l0.zero_()
+        packed = torch.nn.utils.rnn.pack_padded_sequence(_t(X), torch.tensor(lens), batch_first=True,
+                                                         enforce_sorted=False)
+        o, _ = lstm(packed)
+        o, _ = torch.nn.utils.rnn.pad_packed_sequence(o, batch_first=True, total_length=T)
+    np.testing.assert_allclose(out, o.numpy(), rtol=1e-10, atol=1e-12)
+
+    cfg = synth.get_config("tiny_uni")
+    w = synth.make_weights(cfg, bias_noise=0.1)
+    batch = synth.make_batch(cfg)
+    kw = dict(num_layers={"char": cfg.L}, ctc_tasks=cfg.ctc, enc_params={"bi_dir": False})
+    res = om.train_step(w, batch, **kw)
+    assert res["states"][cfg.L].shape[2] == cfg.H
+    eps = 1e-6
+    for name in sorted(w.keys()):
+        idx = tuple(int(rng.integers(0, s)) for s in w[name].shape)
+        wp = {n: v.astype(np.float64).copy() for n, v in w.items()}
+        wm = {n: v.astype(np.float64).copy() for n, v in w.items()}
+        wp[name][idx] += eps
+        wm[name][idx] -= eps
+        fd = (om.train_step(wp, batch, want_grads=False, **kw)["total_loss"]
+              - om.train_step(wm, batch, want_grads=False, **kw)["total_loss"]) / (2 * eps)
+        assert abs(fd - res["grads"][name][idx]) < 1e-6 * max(1.0, abs(fd)), (name, idx, fd)
