@@ -269,9 +269,20 @@ def main():
     ms, host_busy_ms = ms_eager, host_eager_ms
     step_host = lambda: model.run_step(batch)
     mode = "eager (~200 launches per step from Python)"
+    gs = None
     if use_graph:
         # ---------------- device-resident inputs ("value"): the step replayed from its CUDA graph
-        gs = model.graphed_step(batch)
+        # (a capture failure must not cost the run its number: every rank then times the eager step instead)
+        try:
+            gs = model.graphed_step(batch)
+            failed = 0.0
+        except Exception as e:          # noqa: BLE001
+            sys.stderr.write("bench.py: CUDA-graph capture failed (%r); timing the eager step\n" % (e,))
+            mode = "eager (graph capture failed: %s)" % (str(e)[:120],)
+            failed = 1.0
+        if max_over_ranks(failed) > 0.0:
+            gs, use_graph = None, False
+    if use_graph:
         for _ in range(W):
             gs.step()
         ms, host_busy_ms, n_tail, clocks, _ = timed_loop(gs.step, False)
