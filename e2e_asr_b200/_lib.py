@@ -44,6 +44,8 @@ _SIGS = {
     "e2e_axpy": "pzfpp",
     "e2e_adam": "pzppppffff",
     "e2e_dropout": "pzppfQIz",
+    "e2e_gru_rec_fwd": "piiiiippppppp",
+    "e2e_gru_rec_bwd": "piiiiippppppp",
     "e2e_sample_rows": "piipiQIIp",
     "e2e_gemm_f64": "piiipipipip",
     "e2e_lstm_step_f64": "piippppi",

@@ -71,6 +71,8 @@ int axpy(cudaStream_t, size_t, float, const float*, float*);
 int adam_update(cudaStream_t, size_t, float*, const float*, float*, float*, float, float, float, float);
 int dropout(cudaStream_t, size_t, const float*, float*, float, unsigned long long, unsigned, size_t);
 int sample_rows(cudaStream_t, int, int, const float*, int, unsigned long long, unsigned, unsigned, long long*);
+int gru_rec(cudaStream_t, bool, int, int, int, int, int, float*, float*, float*, float*, const float*, const float*,
+            const float*, const int*);
 int dec_persist(cudaStream_t, bool, const e2e_dec_persist_args*, float*, float*, float*);
 int dec_persist_fits(const e2e_dec_persist_args*);
 int gemm_f64(cudaStream_t, int, int, int, const double*, int, const float*, int, double*, int, const float*);
@@ -137,6 +139,15 @@ int e2e_gemm_lo(void* stream, int mode, int transA, int transB, int M, int N, in
 }
 int e2e_split_lo(void* stream, int mode, size_t n, const float* x, float* lo) {
     return split_lo(ST(stream), mode, n, x, lo);
+}
+int e2e_gru_rec_fwd(void* stream, int B, int T, int Tp, int H, int ndir, float* Gg, float* Gc, float* out, float* RH,
+                    const float* Wg_h, const float* Wc_h, const int* lens) {
+    return gru_rec(ST(stream), false, B, T, Tp, H, ndir, Gg, Gc, out, RH, nullptr, Wg_h, Wc_h, lens);
+}
+int e2e_gru_rec_bwd(void* stream, int B, int T, int Tp, int H, int ndir, float* Gg, float* Gc, const float* out,
+                    const float* dout, const float* Wg_hT, const float* Wc_hT, const int* lens) {
+    return gru_rec(ST(stream), true, B, T, Tp, H, ndir, Gg, Gc, const_cast<float*>(out), nullptr, dout, Wg_hT, Wc_hT,
+                   lens);
 }
 int e2e_set_tc_debug(float* dbg, long long min_work) {
     set_tc_debug(dbg, min_work);

@@ -43,9 +43,8 @@ class Encoder(BaseParams):
 
     def _check_supported(self):
         p = self.params
-        if not p.use_lstm:
-            raise NotImplementedError("Encoder: use_lstm=False (GRUCell, encoder.py:48) is not built yet; "
-                                      "pass use_lstm=True (the reference CLI default, encoder.py:187)")
+        if not p.use_lstm and p.hidden_size > 512:
+            raise NotImplementedError("Encoder: GRU cells (use_lstm=False) are built for hidden_size <= 512")
         if not (0.0 < p.out_prob <= 1.0):
             raise ValueError("Encoder: out_prob=%g must be in (0, 1]" % p.out_prob)
         if p.skip_step not in (1, 2):
@@ -57,19 +56,29 @@ class Encoder(BaseParams):
         H = self.params.hidden_size
         out = []
         if self.params.bi_dir:
-            bases = ["model/encoder/RNNLayer%d/bidirectional_rnn/%s/basic_lstm_cell/" % (layer_depth, d)
-                     for d in ("fw", "bw")]
+            scopes = ["model/encoder/RNNLayer%d/bidirectional_rnn/%s/" % (layer_depth, d) for d in ("fw", "bw")]
         else:   # tf.nn.dynamic_rnn(..., scope=str(layer_depth)) inside the RNNLayer<d> scope (encoder.py:86-89)
-            bases = ["model/encoder/RNNLayer%d/%d/basic_lstm_cell/" % (layer_depth, layer_depth)]
-        for base in bases:
-            out.append(vs.get(base + "kernel", (in_size + H, 4 * H), ("uniform", 0.075)))
-            out.append(vs.get(base + "bias", (4 * H,), ("zeros",)))
+            scopes = ["model/encoder/RNNLayer%d/%d/" % (layer_depth, layer_depth)]
+        if not self.params.use_lstm:
+            # tf.nn.rnn_cell.GRUCell: gates/{kernel,bias} (bias initialised to 1.0), candidate/{kernel,bias}
+            for sc in scopes:
+                out.append(vs.get(sc + "gru_cell/gates/kernel", (in_size + H, 2 * H), ("uniform", 0.075)))
+                out.append(vs.get(sc + "gru_cell/gates/bias", (2 * H,), ("ones",)))
+                out.append(vs.get(sc + "gru_cell/candidate/kernel", (in_size + H, H), ("uniform", 0.075)))
+                out.append(vs.get(sc + "gru_cell/candidate/bias", (H,), ("zeros",)))
+            return out
+        for sc in scopes:
+            out.append(vs.get(sc + "basic_lstm_cell/kernel", (in_size + H, 4 * H), ("uniform", 0.075)))
+            out.append(vs.get(sc + "basic_lstm_cell/bias", (4 * H,), ("zeros",)))
         return out + [None] * (4 - len(out))
 
     def _layer_encoder_input(self, x_padded, lens_i32, max_len, layer_depth=1):
         """Run one (Bi)LSTM layer on a padded batch-major buffer (encoder.py:55-91)."""
-        k_fw, b_fw, k_bw, b_bw = self._layer_vars(layer_depth, x_padded.shape[2])
-        out = ops.BiLSTMLayerFn.apply(x_padded, k_fw, b_fw, k_bw, b_bw, lens_i32, max_len)
+        if self.params.use_lstm:
+            k_fw, b_fw, k_bw, b_bw = self._layer_vars(layer_depth, x_padded.shape[2])
+            out = ops.BiLSTMLayerFn.apply(x_padded, k_fw, b_fw, k_bw, b_bw, lens_i32, max_len)
+        else:
+            out = ops.BiGRULayerFn.apply(x_padded, lens_i32, max_len, *self._layer_vars(layer_depth, x_padded.shape[2]))
         if self.isTraining and self.params.out_prob < 1.0:
             # DropoutWrapper(cell, output_keep_prob=out_prob) iff training (encoder.py:49-52): the per-step outputs
             # of both directions are dropped, the recurrent state is not.  Mask stream = layer depth.

@@ -363,6 +363,72 @@ class BiLSTMLayerFn(torch.autograd.Function):
         return (dX,) + tuple(_unpack_lstm(dWx, dWh, dbp, I, H, nd, dev)) + pad + (None, None)
 
 
+class BiGRULayerFn(torch.autograd.Function):
+    """One GRU encoder layer (reference encoder.py:48 `GRUCell` when use_lstm=False, under
+    (bidirectional_)dynamic_rnn, encoder.py:77-89) over a zero-padded batch-major buffer.
+
+    x: [B, Tp, I]; per direction the TF variables gates/{kernel [(I+H), 2H], bias [2H]} and
+    candidate/{kernel [(I+H), H], bias [H]}; returns [B, Tp, nd*H] (fw | bw), zero for t >= len.
+    The x halves of both kernels are batched GEMMs over all frames, the recurrence is e2e_gru_rec_fwd/bwd (one CTA
+    per 4 utterances, no inter-CTA synchronisation); the parameter gradients are GEMMs over the stored
+    pre-activation gradients, returned through autograd."""
+
+    @staticmethod
+    def forward(ctx, x, lens_i32, T, *params):
+        B, Tp, I = x.shape
+        nd = len(params) // 4
+        H = params[2].shape[1]
+        dev = x.device
+        assert x.is_contiguous() and Tp >= T + 1 and len(params) in (4, 8)
+        gk, gb, ck, cb = (params[0::4], params[1::4], params[2::4], params[3::4])
+        Wg_x = torch.cat([k[:I] for k in gk], dim=1).contiguous()          # [I, nd*2H]
+        Wc_x = torch.cat([k[:I] for k in ck], dim=1).contiguous()          # [I, nd*H]
+        Wg_h = torch.stack([k[I:] for k in gk]).contiguous()               # [nd, H, 2H]
+        Wc_h = torch.stack([k[I:] for k in ck]).contiguous()               # [nd, H, H]
+        x2 = x.view(B * Tp, I)
+        Gg = gemm(x2, Wg_x, bias=torch.cat(list(gb)))
+        Gc = gemm(x2, Wc_x, bias=torch.cat(list(cb)))
+        out = torch.zeros((B, Tp, nd * H), dtype=torch.float32, device=dev)
+        RH = torch.zeros((B * Tp, nd * H), dtype=torch.float32, device=dev)
+        call("e2e_gru_rec_fwd", B, T, Tp, H, nd, Gg, Gc, out, RH, Wg_h, Wc_h, lens_i32, work=float(T),
+             tag="enc_gru_fwd")
+        ctx.save_for_backward(x, Wg_x, Wc_x, Wg_h, Wc_h, Gg, Gc, out, RH, lens_i32)
+        ctx.dims = (B, Tp, I, H, T, nd)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        x, Wg_x, Wc_x, Wg_h, Wc_h, Gg, Gc, out, RH, lens_i32 = ctx.saved_tensors
+        B, Tp, I, H, T, nd = ctx.dims
+        dout = dout.contiguous()
+        call("e2e_gru_rec_bwd", B, T, Tp, H, nd, Gg, Gc, out, dout, Wg_h.transpose(1, 2).contiguous(),
+             Wc_h.transpose(1, 2).contiguous(), lens_i32, work=float(T), tag="enc_gru_bwd")
+        # Gg / Gc now hold d(gate pre-activations) / d(candidate pre-activation), zero past each length
+        N = B * Tp
+        x2, o2 = x.view(N, I), out.view(N, nd * H)
+        dX = None
+        if ctx.needs_input_grad[0]:
+            dX = gemm(Gg, Wg_x, tb=True)
+            gemm(Gc, Wc_x, tb=True, out=dX, accumulate=True)
+            dX = dX.view(B, Tp, I)
+        dWg_x = gemm(x2, Gg, ta=True)                                      # [I, nd*2H]
+        dWc_x = gemm(x2, Gc, ta=True)                                      # [I, nd*H]
+        dbg, dbc = colsum(Gg), colsum(Gc)
+        grads = []
+        for d in range(nd):
+            cg, cc = slice(d * 2 * H, (d + 1) * 2 * H), slice(d * H, (d + 1) * H)
+            # h_{t-1}^T d(gates)_t: fw pairs out[t-1] with row t, bw pairs out[t+1] with row t (one-row shift of the
+            # flat buffer; it never crosses an utterance because the last padded frame of every utterance is zero)
+            if d == 0:
+                dWg_h = gemm(o2[:N - 1, cc], Gg[1:, cg], ta=True)
+            else:
+                dWg_h = gemm(o2[1:, cc], Gg[:N - 1, cg], ta=True)
+            dWc_h = gemm(RH[:, cc], Gc[:, cc], ta=True)                    # (r * h_{t-1})^T d(candidate)
+            grads += [torch.cat([dWg_x[:, cg], dWg_h], dim=0), dbg[cg].clone(),
+                      torch.cat([dWc_x[:, cc], dWc_h], dim=0), dbc[cc].clone()]
+        return (dX, None, None) + tuple(grads)
+
+
 # ---------------------------------------------------------------------------
 # Attention decoder (teacher forced)
 # ---------------------------------------------------------------------------

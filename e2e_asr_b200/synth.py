@@ -32,6 +32,11 @@ CONFIGS = {
                      ctc={"phone_ctc": (2, 6)}),
     "uni256": dict(B=3, T=40, F=16, H=256, L=2, V=31, U=6, E=32, A=16, Hd=32, Hl=32, bi_dir=False,
                    ctc={"phone_ctc": (2, 6)}),
+    # tiny_gru / gru256: GRU encoder cells (the reference's Encoder.class_params() default, encoder.py:27,48)
+    "tiny_gru": dict(B=5, T=31, F=10, H=16, L=3, V=19, U=7, E=12, A=8, Hd=16, Hl=8, enc_lstm=False,
+                     ctc={"phone_ctc": (2, 6)}),
+    "gru256": dict(B=6, T=44, F=16, H=256, L=2, V=31, U=6, E=32, A=16, Hd=32, Hl=32, enc_lstm=False,
+                   ctc={"phone_ctc": (2, 6)}),
     # wide_small: cfg-5's widths at unit-test size (H=512 -> L2-exchange recurrence, D=1024 -> per-step decoder)
     "wide_small": dict(B=3, T=24, F=8, H=512, L=2, V=17, U=5, E=16, A=16, Hd=32, Hl=16,
                        ctc={"phone_ctc": (1, 5)}),
@@ -102,11 +107,17 @@ def make_weights(cfg, seed=WEIGHT_SEED, tasks=("char",), bias_noise=0.0):
 
     bi_dir = cfg.get("bi_dir", True)
     for l, I in enumerate(layer_input_sizes(cfg), start=1):
-        bases = ["model/encoder/RNNLayer%d/bidirectional_rnn/%s/basic_lstm_cell/" % (l, d) for d in ("fw", "bw")] \
-            if bi_dir else ["model/encoder/RNNLayer%d/%d/basic_lstm_cell/" % (l, l)]
-        for base in bases:
-            w[base + "kernel"] = rng.uniform(-0.075, 0.075, size=(I + H, 4 * H)).astype(np.float32)
-            w[base + "bias"] = bias(4 * H)
+        scopes = ["model/encoder/RNNLayer%d/bidirectional_rnn/%s/" % (l, d) for d in ("fw", "bw")] \
+            if bi_dir else ["model/encoder/RNNLayer%d/%d/" % (l, l)]
+        for sc in scopes:
+            if cfg.get("enc_lstm", True):
+                w[sc + "basic_lstm_cell/kernel"] = rng.uniform(-0.075, 0.075, size=(I + H, 4 * H)).astype(np.float32)
+                w[sc + "basic_lstm_cell/bias"] = bias(4 * H)
+            else:   # GRUCell: gates bias initialised to 1.0, candidate bias to 0 (tf.nn.rnn_cell.GRUCell)
+                w[sc + "gru_cell/gates/kernel"] = rng.uniform(-0.075, 0.075, size=(I + H, 2 * H)).astype(np.float32)
+                w[sc + "gru_cell/gates/bias"] = (1.0 + bias(2 * H)).astype(np.float32)
+                w[sc + "gru_cell/candidate/kernel"] = rng.uniform(-0.075, 0.075, size=(I + H, H)).astype(np.float32)
+                w[sc + "gru_cell/candidate/bias"] = bias(H)
     D = (2 if bi_dir else 1) * H
     for task in tasks:
         V = cfg.V if task == "char" else cfg.get("V_" + task, cfg.V)

@@ -18,7 +18,7 @@ def model_params(cfg, tasks=("char",), ctc=True, avg=True):
     p.max_output = {t: cfg.U for t in tasks}
     p.avg = avg
     ep = p.encoder_params
-    ep.hidden_size, ep.use_lstm, ep.out_prob = cfg.H, True, 1.0
+    ep.hidden_size, ep.use_lstm, ep.out_prob = cfg.H, bool(cfg.get("enc_lstm", True)), 1.0
     ep.bi_dir = bool(cfg.get("bi_dir", True))
     dp = {}
     for t in tasks:

@@ -48,6 +48,8 @@ class VariableStore(object):
             return self.rng.uniform(-init[1], init[1], size=shape).astype(np.float32)
         if init[0] == "zeros":
             return np.zeros(shape, np.float32)
+        if init[0] == "ones":
+            return np.ones(shape, np.float32)
         if init[0] == "glorot":
             if len(shape) == 1:
                 fan_in = fan_out = shape[0]

@@ -253,6 +253,19 @@ int e2e_axpy(void* stream, size_t n, float a, const float* x, float* y);   /* y 
 int e2e_adam(void* stream, size_t n, float* param, const float* grad, float* m, float* v, float lr_t, float beta1,
              float beta2, float eps);
 
+/* GRU recurrence of an encoder layer (encoder.py:48 GRUCell under (bidirectional_)dynamic_rnn, encoder.py:77-89),
+ * batch-major rows n = b*Tp + t, directions side by side in the feature axis (fw | bw):
+ *   Gg [B*Tp, ndir*2H]: x . gates/kernel[:I] + gates/bias on entry (r | u per direction); (r | u) activations after
+ *                       the forward pass; d(gate pre-activations) after the backward pass (zero for t >= len);
+ *   Gc [B*Tp, ndir*H] : x . candidate/kernel[:I] + candidate/bias -> c -> d(candidate pre-activation);
+ *   out [B*Tp, ndir*H]: h_t, must be zero-initialised (frames t >= len stay zero);  RH: r_t * h_{t-1}, likewise;
+ *   Wg_h [ndir][H][2H], Wc_h [ndir][H][H]: the recurrent halves of the TF kernels; the backward pass takes their
+ *   transposes Wg_hT [ndir][2H][H], Wc_hT [ndir][H][H].  H <= 512.  One CTA per 4 utterances and direction. */
+int e2e_gru_rec_fwd(void* stream, int B, int T, int Tp, int H, int ndir, float* Gg, float* Gc, float* out, float* RH,
+                    const float* Wg_h, const float* Wc_h, const int* lens);
+int e2e_gru_rec_bwd(void* stream, int B, int T, int Tp, int H, int ndir, float* Gg, float* Gc, const float* out,
+                    const float* dout, const float* Wg_hT, const float* Wc_hT, const int* lens);
+
 /* DropoutWrapper(output_keep_prob=keep) on a recurrent cell's outputs (encoder.py:50-52, decoder.py:60-63):
  * with i = first + (index into x), y = x / keep if philox4x32_10(counter = (i/4, offset, 0, 0), key = seed)[i%4]
  * * 2^-32 < keep else 0 (`first`, a multiple of 4, lets a slice of a buffer draw the buffer's mask).

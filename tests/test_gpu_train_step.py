@@ -236,6 +236,27 @@ def test_unidirectional_encoder_matches_oracle(cname, mode):
         ops.set_gemm_mode("fp32")
 
 
+@pytest.mark.parametrize("cname,mode", [("tiny_gru", "fp32"), ("gru256", "fp32"), ("gru256", "tf32x3")])
+def test_gru_encoder_matches_oracle(cname, mode):
+    """use_lstm=False in the encoder (encoder.py:27,48: tf.nn.rnn_cell.GRUCell -- the reference's class_params
+    default): gates / candidate kernels with TF's variable names, recurrence in e2e_gru_rec_fwd/bwd, against the
+    oracle's GRU restatement (itself checked by finite differences)."""
+    cfg = synth.get_config(cname)
+    w = synth.make_weights(cfg, bias_noise=0.1)
+    batch = synth.make_batch(cfg)
+    ref = om.train_step(w, batch, num_layers={"char": cfg.L}, ctc_tasks=cfg.ctc, enc_params={"use_lstm": False})
+    ops.set_gemm_mode(mode)
+    try:
+        model = build_model(cfg, w, device="cuda:0")
+        assert not model.params.encoder_params.use_lstm
+        for _ in range(2):
+            model.run_step(batch)
+            ops.check_device_errors("cuda:0")
+            compare_step(model, ref, rtol=RTOL)
+    finally:
+        ops.set_gemm_mode("fp32")
+
+
 def test_adam_updates_match_oracle():
     """apply_updates=True: three Adam steps (fused flat-buffer kernel) against the oracle's TF-formula Adam."""
     cfg = synth.get_config("tiny_b")

@@ -335,3 +335,52 @@ def test_unidirectional_encoder_forward_vs_torch_and_finite_differences():
         fd = (om.train_step(wp, batch, want_grads=False, **kw)["total_loss"]
               - om.train_step(wm, batch, want_grads=False, **kw)["total_loss"]) / (2 * eps)
         assert abs(fd - res["grads"][name][idx]) < 1e-6 * max(1.0, abs(fd)), (name, idx, fd)
+
+
+def test_gru_encoder_oracle_vs_torch_autograd_and_finite_differences():
+    """use_lstm=False (encoder.py:48, tf.nn.rnn_cell.GRUCell): one direction of the oracle's GRU layer against torch
+    autograd on the TF-1.x cell formula ([r, u] = sigmoid([x, h] Wg + bg); c = tanh([x, r*h] Wc + bc);
+    h' = u h + (1 - u) c; frozen state and zero output past the length), then the whole GRU-encoder step against
+    float64 central differences."""
+    rng = np.random.Generator(np.random.PCG64(5))
+    B, T, I, H = 4, 9, 5, 6
+    X = rng.standard_normal((B, T, I))
+    lens = np.array([9, 5, 1, 7])
+    gk, gb = rng.uniform(-0.5, 0.5, (I + H, 2 * H)), rng.uniform(-0.5, 0.5, 2 * H) + 1.0
+    ck, cb = rng.uniform(-0.5, 0.5, (I + H, H)), rng.uniform(-0.5, 0.5, H)
+    dout = rng.standard_normal((B, T, H))
+    for rev in (False, True):
+        out, cache = om._gru_dir_fwd(X, gk, gb, ck, cb, lens, rev)
+        dX, (dgk, dgb, dck, dcb) = om._gru_dir_bwd(dout, cache)
+        tX, tgk, tgb, tck, tcb = [_t(a).requires_grad_(True) for a in (X, gk, gb, ck, cb)]
+        outs = [None] * T
+        h = torch.zeros(B, H, dtype=torch.float64)
+        for t in (range(T - 1, -1, -1) if rev else range(T)):
+            m = torch.tensor(t < lens)[:, None]
+            g = torch.sigmoid(torch.cat([tX[:, t], h], 1) @ tgk + tgb)
+            r, u = g[:, :H], g[:, H:]
+            c = torch.tanh(torch.cat([tX[:, t], r * h], 1) @ tck + tcb)
+            hn = u * h + (1 - u) * c
+            outs[t] = torch.where(m, hn, torch.zeros_like(hn))
+            h = torch.where(m, hn, h)
+        tout = torch.stack(outs, 1)
+        np.testing.assert_allclose(out, tout.detach().numpy(), rtol=1e-12, atol=1e-13)
+        (tout * _t(dout)).sum().backward()
+        for got, want in ((dX, tX), (dgk, tgk), (dgb, tgb), (dck, tck), (dcb, tcb)):
+            np.testing.assert_allclose(got, want.grad.numpy(), rtol=1e-10, atol=1e-12)
+
+    cfg = synth.get_config("tiny_gru")
+    w = synth.make_weights(cfg, bias_noise=0.1)
+    batch = synth.make_batch(cfg)
+    kw = dict(num_layers={"char": cfg.L}, ctc_tasks=cfg.ctc, enc_params={"use_lstm": False})
+    res = om.train_step(w, batch, **kw)
+    eps = 1e-6
+    for name in sorted(w.keys()):
+        idx = tuple(int(rng.integers(0, s)) for s in w[name].shape)
+        wp = {n: v.astype(np.float64).copy() for n, v in w.items()}
+        wm = {n: v.astype(np.float64).copy() for n, v in w.items()}
+        wp[name][idx] += eps
+        wm[name][idx] -= eps
+        fd = (om.train_step(wp, batch, want_grads=False, **kw)["total_loss"]
+              - om.train_step(wm, batch, want_grads=False, **kw)["total_loss"]) / (2 * eps)
+        assert abs(fd - res["grads"][name][idx]) < 1e-6 * max(1.0, abs(fd)), (name, idx, fd)
