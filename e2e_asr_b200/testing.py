@@ -11,10 +11,10 @@ from .seq2seq_model import Seq2SeqModel
 from .variables import VariableStore
 
 
-def model_params(cfg, tasks=("char",), ctc=True, avg=True):
+def model_params(cfg, tasks=("char",), ctc=True, avg=True, num_layers=None):
     p = Seq2SeqModel.class_params()
     p.tasks = list(tasks)
-    p.num_layers = {t: cfg.L for t in tasks}
+    p.num_layers = {t: (num_layers or {}).get(t, cfg.L) for t in tasks}
     p.max_output = {t: cfg.U for t in tasks}
     p.avg = avg
     ep = p.encoder_params
@@ -24,7 +24,8 @@ def model_params(cfg, tasks=("char",), ctc=True, avg=True):
     for t in tasks:
         d = copy.deepcopy(p.decoder_params["char"])
         d.out_prob_dec, d.samp_prob = 1.0, 0.0
-        d.hidden_size_dec, d.emb_size, d.vocab_size = cfg.Hd, cfg.E, cfg.V
+        d.hidden_size_dec, d.emb_size = cfg.Hd, cfg.E
+        d.vocab_size = cfg.V if t == "char" else cfg.get("V_" + t, cfg.V)
         d.attention_vec_size, d.lm_hidden_size, d.max_output = cfg.A, cfg.Hl, cfg.U
         dp[t] = d
     p.decoder_params = dp
@@ -36,14 +37,16 @@ def model_params(cfg, tasks=("char",), ctc=True, avg=True):
     return p
 
 
-def build_model(cfg, weights=None, device="cuda", isTraining=True, ctc=True, reducer=None, capacity=None):
+def build_model(cfg, weights=None, device="cuda", isTraining=True, ctc=True, reducer=None, capacity=None,
+                tasks=("char",), num_layers=None):
     if capacity is None:
         n = sum(int(np.prod(v.shape)) + 4 for v in (weights or synth.make_weights(cfg)).values())
         capacity = n + 1024
     vs = VariableStore(device, capacity=capacity)
     if weights is not None:
         vs.load(weights)
-    return Seq2SeqModel(None, isTraining=isTraining, params=model_params(cfg, ctc=ctc), variables=vs,
+    return Seq2SeqModel(None, isTraining=isTraining,
+                        params=model_params(cfg, tasks=tasks, ctc=ctc, num_layers=num_layers), variables=vs,
                         device=device, reducer=reducer)
 
 

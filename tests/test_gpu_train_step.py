@@ -257,6 +257,28 @@ def test_gru_encoder_matches_oracle(cname, mode):
         ops.set_gemm_mode("fp32")
 
 
+@pytest.mark.parametrize("cname,ctc", [("tiny_b", True), ("cfg1", False)])
+def test_multitask_char_and_phone_decoders_match_oracle(cname, ctc):
+    """The reference's multitask setup (main.py:89-93): a character attention decoder on the top encoder layer and a
+    PHONE attention decoder on a lower one (own vocabulary, own variables under rnn_decoder_phone), losses averaged
+    over tasks (seq2seq_model.py:140-144) -- eager and replayed from the CUDA graph."""
+    cfg = synth.get_config(cname, V_phone=13 if cname == "tiny_b" else 48)
+    tasks = ("char", "phone")
+    depth = {"char": cfg.L, "phone": cfg.L - 1}
+    w = synth.make_weights(cfg, tasks=tasks, bias_noise=0.1)
+    batch = synth.make_batch(cfg, tasks=tasks)
+    ref = om.train_step(w, batch, tasks=tasks, num_layers=depth, ctc_tasks=cfg.ctc if ctc else {})
+    assert abs(ref["losses"]["char"] - ref["losses"]["phone"]) > 1e-3
+    model = build_model(cfg, w, device="cuda:0", tasks=tasks, num_layers=depth, ctc=ctc)
+    for _ in range(2):
+        model.run_step(batch)
+        ops.check_device_errors("cuda:0")
+        compare_step(model, ref, rtol=RTOL)
+    gs = model.graphed_step(batch)
+    gs.step(batch)
+    compare_step(model, ref, rtol=RTOL)
+
+
 def test_adam_updates_match_oracle():
     """apply_updates=True: three Adam steps (fused flat-buffer kernel) against the oracle's TF-formula Adam."""
     cfg = synth.get_config("tiny_b")
