@@ -44,6 +44,13 @@ _SIGS = {
     "e2e_axpy": "pzfpp",
     "e2e_adam": "pzppppffff",
     "e2e_dropout": "pzppfQIz",
+    "e2e_lstm_point_fwd": "piipppp",
+    "e2e_lstm_point_bwd": "piippppppp",
+    "e2e_gru_gate_fwd": "piipppp",
+    "e2e_gru_gate_bwd": "piipppppp",
+    "e2e_gru_out_fwd": "piipppp",
+    "e2e_gru_out_bwd": "piippppppp",
+    "e2e_attn_bwd": "piiiiipppppppipppp",
     "e2e_gru_rec_fwd": "piiiiippppppp",
     "e2e_gru_rec_bwd": "piiiiippppppp",
     "e2e_sample_rows": "piipiQIIp",

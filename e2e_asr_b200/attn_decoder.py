@@ -34,6 +34,8 @@ class AttnDecoder(Decoder):
         E, Hd, Hl, A, V = p.emb_size, p.hidden_size_dec, p.lm_hidden_size, p.attention_vec_size, p.vocab_size
         D = attn_size
         out_name = "OutputProjection2" if p.ind_softmax else "OutputProjection"   # attn_decoder.py:119-125
+        if self.general_cells():
+            return self._general_variables(vs, s, E, Hd, Hl, A, V, D, out_name)
         v = dict(
             emb=vs.get(s + "decoder/embedding", (V, E), ("uniform", 1.0)),          # decoder.py:97-99
             attn_w=vs.get(s + "AttnW", (1, 1, D, A)),
@@ -56,6 +58,47 @@ class AttnDecoder(Decoder):
             v["sp_b"] = vs.get(s + "rnn/SimpleProjection/bias", (Hd,), ("zeros",))
         return v
 
+    def _general_variables(self, vs, s, E, Hd, Hl, A, V, D, out_name):
+        """Variables when lm_cell / the decoder cell are MultiRNNCell stacks and / or GRU cells (decoder.py:49-72).
+        lm_cell is called first inside the raw_rnn loop, the decoder cell second, so TF's scope uniquifier gives
+        rnn/<cell>/... and rnn/<cell>_1/... (the single-cell names beam_search.py:56-98 reads), resp.
+        rnn/multi_rnn_cell/cell_<l>/<cell>/... and rnn/multi_rnn_cell_1/cell_<l>/<cell>/... for stacks."""
+        p = self.params
+        nl, lstm = p.num_layers_dec, p.use_lstm
+        cell = "basic_lstm_cell" if lstm else "gru_cell"
+        stacks = []
+        for sfx, Hc in (("", Hl), ("_1", Hd)):
+            layers = []
+            for l in range(nl):
+                base = s + "rnn/" + (cell + sfx + "/" if nl == 1 else "multi_rnn_cell%s/cell_%d/%s/" % (sfx, l, cell))
+                I_ = E if l == 0 else Hc
+                if lstm:
+                    layers.append((vs.get(base + "kernel", (I_ + Hc, 4 * Hc)), vs.get(base + "bias", (4 * Hc,), ("zeros",))))
+                else:
+                    layers.append((vs.get(base + "gates/kernel", (I_ + Hc, 2 * Hc)),
+                                   vs.get(base + "gates/bias", (2 * Hc,), ("ones",)),
+                                   vs.get(base + "candidate/kernel", (I_ + Hc, Hc)),
+                                   vs.get(base + "candidate/bias", (Hc,), ("zeros",))))
+            stacks.append(layers)
+        v = dict(
+            emb=vs.get(s + "decoder/embedding", (V, E), ("uniform", 1.0)),
+            attn_w=vs.get(s + "AttnW", (1, 1, D, A)),
+            attn_v=vs.get(s + "AttnV", (A,)),
+            lm_cells=stacks[0], dec_cells=stacks[1],
+            q_k=vs.get(s + "rnn/Attention/kernel", (Hd, A)),
+            q_b=vs.get(s + "rnn/Attention/bias", (A,), ("zeros",)),
+            ap_k=vs.get(s + "rnn/AttnProjection/kernel", (Hd + D, Hd)),
+            ap_b=vs.get(s + "rnn/AttnProjection/bias", (Hd,), ("zeros",)),
+            out_k=vs.get(s + "rnn/%s/kernel" % out_name, (Hd, V)),
+            out_b=vs.get(s + "rnn/%s/bias" % out_name, (V,), ("zeros",)),
+            in_k=vs.get(s + "rnn/InputProjection/kernel", (Hd + D, E)),
+            in_b=vs.get(s + "rnn/InputProjection/bias", (E,), ("zeros",)),
+            sp_k=None, sp_b=None)
+        if Hl != Hd:
+            v["sp_k"] = vs.get(s + "rnn/SimpleProjection/kernel", (Hl, Hd))
+            v["sp_b"] = vs.get(s + "rnn/SimpleProjection/bias", (Hd,), ("zeros",))
+        return v
+
     def __call__(self, decoder_inp, seq_len, encoder_hidden_states, seq_len_inp):
         """decoder_inp: [U+1, B] int64 ids (row 0 = GO); seq_len: [B] number of
         targets; encoder_hidden_states: [B, T_enc, D]; seq_len_inp: [B]."""
@@ -68,6 +111,9 @@ class AttnDecoder(Decoder):
         lens = ops.to_i32(seq_len, dev)
         enc_len = ops.to_i32(seq_len_inp, dev)
         rule = self.input_rule()
+        if self.general_cells():
+            return ops.attn_decoder_stepwise(enc, v, v["lm_cells"], v["dec_cells"], self.params.use_lstm, decoder_inp,
+                                             lens, enc_len, U, self.stash)
         if rule in ("teacher", "sample"):
             # DropoutWrapper(output_keep_prob=out_prob_dec) iff training (decoder.py:60-63) acts on lm_cell's
             # output only: raw_loop_function reads the decoder cell through get_state(state) = state.c and never

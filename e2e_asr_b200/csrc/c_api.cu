@@ -73,6 +73,15 @@ int dropout(cudaStream_t, size_t, const float*, float*, float, unsigned long lon
 int sample_rows(cudaStream_t, int, int, const float*, int, unsigned long long, unsigned, unsigned, long long*);
 int gru_rec(cudaStream_t, bool, int, int, int, int, int, float*, float*, float*, float*, const float*, const float*,
             const float*, const int*);
+int lstm_point_fwd(cudaStream_t, int, int, const float*, const float*, float*, float*);
+int lstm_point_bwd(cudaStream_t, int, int, const float*, const float*, const float*, const float*, const float*, float*,
+                   float*);
+int gru_gate_fwd(cudaStream_t, int, int, const float*, const float*, float*, float*);
+int gru_gate_bwd(cudaStream_t, int, int, const float*, const float*, const float*, const float*, float*, float*);
+int gru_out_fwd(cudaStream_t, int, int, const float*, const float*, const float*, float*);
+int gru_out_bwd(cudaStream_t, int, int, const float*, const float*, const float*, const float*, float*, float*, float*);
+int attn_bwd(cudaStream_t, int, int, int, int, int, const float*, const float*, const int*, const float*, const float*,
+             const float*, const float*, int, float*, float*, float*, float*);
 int dec_persist(cudaStream_t, bool, const e2e_dec_persist_args*, float*, float*, float*);
 int dec_persist_fits(const e2e_dec_persist_args*);
 int gemm_f64(cudaStream_t, int, int, int, const double*, int, const float*, int, double*, int, const float*);
@@ -148,6 +157,32 @@ int e2e_gru_rec_bwd(void* stream, int B, int T, int Tp, int H, int ndir, float* 
                     const float* dout, const float* Wg_hT, const float* Wc_hT, const int* lens) {
     return gru_rec(ST(stream), true, B, T, Tp, H, ndir, Gg, Gc, const_cast<float*>(out), nullptr, dout, Wg_hT, Wc_hT,
                    lens);
+}
+int e2e_lstm_point_fwd(void* stream, int n, int H, const float* z, const float* c_prev, float* c_new, float* h_new) {
+    return lstm_point_fwd(ST(stream), n, H, z, c_prev, c_new, h_new);
+}
+int e2e_lstm_point_bwd(void* stream, int n, int H, const float* z, const float* c_prev, const float* c_new,
+                       const float* dc_new, const float* dh_new, float* dz, float* dc_prev) {
+    return lstm_point_bwd(ST(stream), n, H, z, c_prev, c_new, dc_new, dh_new, dz, dc_prev);
+}
+int e2e_gru_gate_fwd(void* stream, int n, int H, const float* zg, const float* h_prev, float* rh, float* u) {
+    return gru_gate_fwd(ST(stream), n, H, zg, h_prev, rh, u);
+}
+int e2e_gru_gate_bwd(void* stream, int n, int H, const float* zg, const float* h_prev, const float* drh,
+                     const float* du, float* dzg, float* dh_prev) {
+    return gru_gate_bwd(ST(stream), n, H, zg, h_prev, drh, du, dzg, dh_prev);
+}
+int e2e_gru_out_fwd(void* stream, int n, int H, const float* zc, const float* u, const float* h_prev, float* h_new) {
+    return gru_out_fwd(ST(stream), n, H, zc, u, h_prev, h_new);
+}
+int e2e_gru_out_bwd(void* stream, int n, int H, const float* zc, const float* u, const float* h_prev,
+                    const float* dh_new, float* dzc, float* du, float* dh_prev) {
+    return gru_out_bwd(ST(stream), n, H, zc, u, h_prev, dh_new, dzc, du, dh_prev);
+}
+int e2e_attn_bwd(void* stream, int B, int Tn, int Tp, int A, int D, const float* HF, const float* enc,
+                 const int* enc_len, const float* y, const float* v, const float* alpha, const float* dctx,
+                 int lddctx, float* dHF, float* denc, float* dy, float* dv_part) {
+    return attn_bwd(ST(stream), B, Tn, Tp, A, D, HF, enc, enc_len, y, v, alpha, dctx, lddctx, dHF, denc, dy, dv_part);
 }
 int e2e_set_tc_debug(float* dbg, long long min_work) {
     set_tc_debug(dbg, min_work);

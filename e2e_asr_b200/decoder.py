@@ -32,14 +32,24 @@ class Decoder(BaseParams):
 
     def _check_supported(self):
         p = self.params
-        if not p.use_lstm:
-            raise NotImplementedError("Decoder: use_lstm=False (GRUCell, decoder.py:58) is not built yet")
-        if p.num_layers_dec != 1:
-            raise NotImplementedError("Decoder: num_layers_dec > 1 (MultiRNNCell, decoder.py:64-68) is not built yet")
+        if p.num_layers_dec < 1:
+            raise ValueError("Decoder: num_layers_dec=%d must be >= 1" % p.num_layers_dec)
+        if self.general_cells():
+            # MultiRNNCell stacks / GRU cells run the step-by-step path (ops.attn_decoder_stepwise): teacher forcing
+            # without dropout; the per-step Philox draws and the eval-mode loop are built for the single LSTM cell
+            if self.isTraining and (p.out_prob_dec < 1.0 or p.samp_prob > 0):
+                raise NotImplementedError("Decoder: num_layers_dec > 1 / use_lstm=False are built for "
+                                          "out_prob_dec=1 and samp_prob=0")
+            if not self.isTraining:
+                raise NotImplementedError("Decoder: greedy decoding is built for the single LSTM cell")
         if not (0.0 < p.out_prob_dec <= 1.0):
             raise ValueError("Decoder: out_prob_dec=%g must be in (0, 1]" % p.out_prob_dec)
         if not (0.0 <= p.samp_prob <= 1.0):
             raise ValueError("Decoder: samp_prob=%g must be in [0, 1]" % p.samp_prob)
+
+    def general_cells(self):
+        """True when lm_cell / the decoder cell are not single LSTM cells (decoder.py:49-72)."""
+        return self.params.num_layers_dec > 1 or not self.params.use_lstm
 
     def get_state(self, state):
         """The attention query / projection input is the LSTM CELL state c of the

@@ -430,6 +430,204 @@ class BiGRULayerFn(torch.autograd.Function):
 
 
 # ---------------------------------------------------------------------------
+# General decoder cells (decoder.py:49-82): MultiRNNCell stacks (num_layers_dec > 1) and GRU cells (use_lstm=False).
+# Autograd composes single steps; every step's arithmetic is an e2e_gemm or a pointwise kernel of cell_point.cu.
+# A functional path: the benchmarked single-layer LSTM decoder runs the persistent kernels (AttnDecoderFnV2).
+# ---------------------------------------------------------------------------
+
+class LinearFn(torch.autograd.Function):
+    """tf `_linear(x, n_out, True)`: x . W + b."""
+
+    @staticmethod
+    def forward(ctx, x, W, b):
+        x = x.contiguous()
+        ctx.save_for_backward(x, W)
+        ctx.has_bias = b is not None
+        return gemm(x, W, bias=b)
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, W = ctx.saved_tensors
+        dy = dy.contiguous()
+        return gemm(dy, W, tb=True), gemm(x, dy, ta=True), colsum(dy) if ctx.has_bias else None
+
+
+class LSTMPointFn(torch.autograd.Function):
+    """BasicLSTMCell after the matmul: (z [n,4H], c) -> (c', h')."""
+
+    @staticmethod
+    def forward(ctx, z, c_prev):
+        z, c_prev = z.contiguous(), c_prev.contiguous()
+        n, H = c_prev.shape
+        c_new, h_new = torch.empty_like(c_prev), torch.empty_like(c_prev)
+        call("e2e_lstm_point_fwd", n, H, z, c_prev, c_new, h_new)
+        ctx.save_for_backward(z, c_prev, c_new)
+        return c_new, h_new
+
+    @staticmethod
+    def backward(ctx, dc_new, dh_new):
+        z, c_prev, c_new = ctx.saved_tensors
+        n, H = c_prev.shape
+        dz, dc_prev = torch.empty_like(z), torch.empty_like(c_prev)
+        call("e2e_lstm_point_bwd", n, H, z, c_prev, c_new, None if dc_new is None else dc_new.contiguous(),
+             None if dh_new is None else dh_new.contiguous(), dz, dc_prev)
+        return dz, dc_prev
+
+
+class GRUGateFn(torch.autograd.Function):
+    """GRUCell gates: (zg [n,2H] = (r|u), h) -> (sig(r) * h, sig(u))."""
+
+    @staticmethod
+    def forward(ctx, zg, h_prev):
+        zg, h_prev = zg.contiguous(), h_prev.contiguous()
+        n, H = h_prev.shape
+        rh, u = torch.empty_like(h_prev), torch.empty_like(h_prev)
+        call("e2e_gru_gate_fwd", n, H, zg, h_prev, rh, u)
+        ctx.save_for_backward(zg, h_prev)
+        return rh, u
+
+    @staticmethod
+    def backward(ctx, drh, du):
+        zg, h_prev = ctx.saved_tensors
+        n, H = h_prev.shape
+        dzg, dh_prev = torch.empty_like(zg), torch.empty_like(h_prev)
+        call("e2e_gru_gate_bwd", n, H, zg, h_prev, None if drh is None else drh.contiguous(),
+             None if du is None else du.contiguous(), dzg, dh_prev)
+        return dzg, dh_prev
+
+
+class GRUOutFn(torch.autograd.Function):
+    """GRUCell output: h' = u h + (1 - u) tanh(zc)."""
+
+    @staticmethod
+    def forward(ctx, zc, u, h_prev):
+        zc, u, h_prev = zc.contiguous(), u.contiguous(), h_prev.contiguous()
+        n, H = h_prev.shape
+        h_new = torch.empty_like(h_prev)
+        call("e2e_gru_out_fwd", n, H, zc, u, h_prev, h_new)
+        ctx.save_for_backward(zc, u, h_prev)
+        return h_new
+
+    @staticmethod
+    def backward(ctx, dh_new):
+        zc, u, h_prev = ctx.saved_tensors
+        n, H = h_prev.shape
+        dzc, du, dh_prev = torch.empty_like(zc), torch.empty_like(u), torch.empty_like(h_prev)
+        call("e2e_gru_out_bwd", n, H, zc, u, h_prev, dh_new.contiguous(), dzc, du, dh_prev)
+        return dzc, du, dh_prev
+
+
+class EmbedFn(torch.autograd.Function):
+    """embedding_lookup (decoder.py:101) with its IndexedSlices gradient (scatter-add; the per-occurrence rows are kept
+    in `stash["emb_values"]` for tf.global_norm's view of them)."""
+
+    @staticmethod
+    def forward(ctx, emb, ids, stash):
+        ids = ids.contiguous()
+        n, E = ids.numel(), emb.shape[1]
+        out = torch.empty((n, E), dtype=torch.float32, device=emb.device)
+        call("e2e_embed_gather", n, E, emb, ids, out)
+        ctx.save_for_backward(ids)
+        ctx.shape, ctx.stash = emb.shape, stash
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        (ids,) = ctx.saved_tensors
+        dout = dout.contiguous()
+        demb = torch.zeros(ctx.shape, dtype=torch.float32, device=dout.device)
+        call("e2e_embed_scatter_add", ids.numel(), ctx.shape[1], demb, ids, dout, dout.shape[1])
+        if ctx.stash is not None:
+            ctx.stash["emb_values"] = dout
+        return demb, None, None
+
+
+class AttnStepFn(torch.autograd.Function):
+    """attention() of attn_decoder.py:77-93 for one step: (y [B,A], HF [B*Tp,A], enc [B*Tp,D], v) -> ctx [B,D]."""
+
+    @staticmethod
+    def forward(ctx, y, HF, enc_flat, v, enc_len_i32, dims):
+        B, Tn, Tp, A, D = dims
+        y = y.contiguous()
+        alpha = torch.empty((B, Tn), dtype=torch.float32, device=y.device)
+        out = torch.empty((B, D), dtype=torch.float32, device=y.device)
+        call("e2e_attn_fwd", B, Tn, Tp, A, D, HF, enc_flat, enc_len_i32, y, v, alpha, out, D)
+        ctx.save_for_backward(y, HF, enc_flat, v, enc_len_i32, alpha)
+        ctx.dims = dims
+        return out
+
+    @staticmethod
+    def backward(ctx, dctx):
+        y, HF, enc_flat, v, enc_len_i32, alpha = ctx.saved_tensors
+        B, Tn, Tp, A, D = ctx.dims
+        dctx = dctx.contiguous()
+        dHF, denc = torch.zeros_like(HF), torch.zeros_like(enc_flat)
+        dy = torch.empty_like(y)
+        dv_part = torch.zeros((B, A), dtype=torch.float32, device=y.device)
+        call("e2e_attn_bwd", B, Tn, Tp, A, D, HF, enc_flat, enc_len_i32, y, v, alpha, dctx, D, dHF, denc, dy, dv_part)
+        return dy, dHF, denc, colsum(dv_part), None, None
+
+
+def _cell_step(use_lstm, x, state, ws):
+    """One TF cell step on rows: LSTM state = (c, h), GRU state = (h,).  Returns (output h', new state)."""
+    if use_lstm:
+        c, h = state
+        c2, h2 = LSTMPointFn.apply(LinearFn.apply(torch.cat([x, h], dim=1), ws[0], ws[1]), c)
+        return h2, (c2, h2)
+    (h,) = state
+    rh, u = GRUGateFn.apply(LinearFn.apply(torch.cat([x, h], dim=1), ws[0], ws[1]), h)
+    h2 = GRUOutFn.apply(LinearFn.apply(torch.cat([x, rh], dim=1), ws[2], ws[3]), u, h)
+    return h2, (h2,)
+
+
+def attn_decoder_stepwise(enc, v, lm_cells, dec_cells, use_lstm, ids, lens_i32, enc_len_i32, U, stash=None):
+    """AttnDecoder.__call__ (attn_decoder.py:37-172) under teacher forcing for ANY decoder.py cell configuration:
+    `lm_cells` / `dec_cells` are lists (one entry per stacked layer) of the cell's variables -- (kernel, bias) for
+    BasicLSTMCell, (gates kernel, gates bias, candidate kernel, candidate bias) for GRUCell.  The attention query and
+    the projection input are get_state(state): the last layer's c (LSTM) or state (GRU), decoder.py:74-82; raw_rnn
+    copies the decoder state through for finished rows and zeroes their emit; the lm state is never frozen.
+    Returns logits [(U*B), V]."""
+    dev = enc.device
+    B, Tn, D = enc.shape
+    A = v["q_k"].shape[1]
+    enc_flat, Tp = enc.contiguous().view(B * Tn, D), Tn          # plain differentiable copy: autograd composes this path
+    f32 = dict(dtype=torch.float32, device=dev)
+    Hl = lm_cells[0][-1].shape[0] // (4 if use_lstm else 1)
+    Hd = dec_cells[0][-1].shape[0] // (4 if use_lstm else 1)
+    HF = LinearFn.apply(enc_flat, v["attn_w"].view(D, A), None)
+    u_all = EmbedFn.apply(v["emb"], ids[:U], stash).view(U, B, -1)
+    zero = (lambda H: (torch.zeros((B, H), **f32), torch.zeros((B, H), **f32))) if use_lstm else \
+        (lambda H: (torch.zeros((B, H), **f32),))
+    lm_state = [zero(Hl) for _ in lm_cells]
+    dec_state = [zero(Hd) for _ in dec_cells]
+    ctx_vec = torch.zeros((B, D), **f32)
+    steps_t = torch.arange(U, device=dev, dtype=torch.int32)
+    live_all = (steps_t[:, None] < lens_i32[None, :]).unsqueeze(2)           # [U, B, 1]
+    dims = (B, Tn, Tp, A, D)
+    outs = []
+    for t in range(U):
+        x = u_all[t]
+        for l, ws in enumerate(lm_cells):                                     # lm_cell stack (attn_decoder.py:148)
+            x, lm_state[l] = _cell_step(use_lstm, x, lm_state[l], ws)
+        m = LinearFn.apply(x, v["sp_k"], v["sp_b"]) if v["sp_k"] is not None else x
+        x = LinearFn.apply(torch.cat([m, ctx_vec], dim=1), v["in_k"], v["in_b"])       # InputProjection (:157-158)
+        new_state = []
+        for l, ws in enumerate(dec_cells):                                    # decoder cell stack (raw_rnn body)
+            x, st_new = _cell_step(use_lstm, x, dec_state[l], ws)
+            new_state.append(st_new)
+        q = new_state[-1][0]
+        y = LinearFn.apply(q, v["q_k"], v["q_b"])
+        ctx_vec = AttnStepFn.apply(y, HF, enc_flat, v["attn_v"], enc_len_i32, dims)
+        proj = LinearFn.apply(torch.cat([q, ctx_vec], dim=1), v["ap_k"], v["ap_b"])
+        lg = LinearFn.apply(proj, v["out_k"], v["out_b"])
+        live = live_all[t]
+        outs.append(torch.where(live, lg, torch.zeros_like(lg)))
+        dec_state = [tuple(torch.where(live, a_, b_) for a_, b_ in zip(new_state[l], dec_state[l]))
+                     for l in range(len(dec_cells))]
+    return torch.cat(outs, dim=0)
+
+
+# ---------------------------------------------------------------------------
 # Attention decoder (teacher forced)
 # ---------------------------------------------------------------------------
 

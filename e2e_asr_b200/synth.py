@@ -37,6 +37,13 @@ CONFIGS = {
                      ctc={"phone_ctc": (2, 6)}),
     "gru256": dict(B=6, T=44, F=16, H=256, L=2, V=31, U=6, E=32, A=16, Hd=32, Hl=32, enc_lstm=False,
                    ctc={"phone_ctc": (2, 6)}),
+    # decoder cell variants (decoder.py:49-82): stacked cells (MultiRNNCell) and GRU cells in lm_cell + decoder cell
+    "tiny_dec2": dict(B=4, T=26, F=10, H=16, L=3, V=19, U=7, E=12, A=8, Hd=16, Hl=8, dec_layers=2,
+                      ctc={"phone_ctc": (2, 6)}),
+    "tiny_decgru": dict(B=4, T=26, F=10, H=16, L=3, V=19, U=7, E=12, A=8, Hd=16, Hl=8, dec_lstm=False,
+                        ctc={"phone_ctc": (2, 6)}),
+    "tiny_decgru2": dict(B=4, T=26, F=10, H=16, L=3, V=19, U=7, E=12, A=8, Hd=16, Hl=16, dec_layers=2,
+                         dec_lstm=False, ctc={}),
     # wide_small: cfg-5's widths at unit-test size (H=512 -> L2-exchange recurrence, D=1024 -> per-step decoder)
     "wide_small": dict(B=3, T=24, F=8, H=512, L=2, V=17, U=5, E=16, A=16, Hd=32, Hl=16,
                        ctc={"phone_ctc": (1, 5)}),
@@ -125,10 +132,22 @@ def make_weights(cfg, seed=WEIGHT_SEED, tasks=("char",), bias_noise=0.0):
         w[p + "decoder/embedding"] = rng.uniform(-1.0, 1.0, size=(V, cfg.E)).astype(np.float32)
         w[p + "AttnW"] = _glorot(rng, (1, 1, D, cfg.A))
         w[p + "AttnV"] = _glorot(rng, (cfg.A,))
-        w[p + "rnn/basic_lstm_cell/kernel"] = _glorot(rng, (cfg.E + cfg.Hl, 4 * cfg.Hl))
-        w[p + "rnn/basic_lstm_cell/bias"] = bias(4 * cfg.Hl)
-        w[p + "rnn/basic_lstm_cell_1/kernel"] = _glorot(rng, (cfg.E + cfg.Hd, 4 * cfg.Hd))
-        w[p + "rnn/basic_lstm_cell_1/bias"] = bias(4 * cfg.Hd)
+        # lm_cell (called first in the raw_rnn loop) and the decoder cell: single cells or MultiRNNCell stacks of
+        # LSTM / GRU cells (decoder.py:49-72); names as in oracle _cell_names
+        nl, lstm = cfg.get("dec_layers", 1), cfg.get("dec_lstm", True)
+        for which, (sfx, Hc) in enumerate((("", cfg.Hl), ("_1", cfg.Hd))):
+            for l in range(nl):
+                cell = "basic_lstm_cell" if lstm else "gru_cell"
+                base = p + "rnn/" + (cell + sfx + "/" if nl == 1 else "multi_rnn_cell%s/cell_%d/%s/" % (sfx, l, cell))
+                I_ = cfg.E if l == 0 else Hc
+                if lstm:
+                    w[base + "kernel"] = _glorot(rng, (I_ + Hc, 4 * Hc))
+                    w[base + "bias"] = bias(4 * Hc)
+                else:
+                    w[base + "gates/kernel"] = _glorot(rng, (I_ + Hc, 2 * Hc))
+                    w[base + "gates/bias"] = (1.0 + bias(2 * Hc)).astype(np.float32)
+                    w[base + "candidate/kernel"] = _glorot(rng, (I_ + Hc, Hc))
+                    w[base + "candidate/bias"] = bias(Hc)
         w[p + "rnn/Attention/kernel"] = _glorot(rng, (cfg.Hd, cfg.A))
         w[p + "rnn/Attention/bias"] = bias(cfg.A)
         w[p + "rnn/AttnProjection/kernel"] = _glorot(rng, (cfg.Hd + D, cfg.Hd))

@@ -27,6 +27,7 @@ def model_params(cfg, tasks=("char",), ctc=True, avg=True, num_layers=None):
         d.hidden_size_dec, d.emb_size = cfg.Hd, cfg.E
         d.vocab_size = cfg.V if t == "char" else cfg.get("V_" + t, cfg.V)
         d.attention_vec_size, d.lm_hidden_size, d.max_output = cfg.A, cfg.Hl, cfg.U
+        d.num_layers_dec, d.use_lstm = int(cfg.get("dec_layers", 1)), bool(cfg.get("dec_lstm", True))
         dp[t] = d
     p.decoder_params = dp
     p.ctc_tasks = {}

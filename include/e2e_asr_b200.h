@@ -200,6 +200,25 @@ int e2e_decoder_persist_bwd(void* stream, const e2e_dec_persist_args* a, float* 
 /* single kernels of the loop, exposed for inference (greedy / beam) and tests */
 int e2e_attn_fwd(void* stream, int B, int Tn, int Tp, int A, int D, const float* HF, const float* enc,
                  const int* enc_len, const float* y, const float* v, float* alpha, float* ctx, int ldctx);
+/* backward of e2e_attn_fwd for one decoder step: dHF [B,Tp,A], denc [B,Tp,D] and dv_part [B,A] are ACCUMULATED
+ * (zero them first), dy [B,A] is written */
+int e2e_attn_bwd(void* stream, int B, int Tn, int Tp, int A, int D, const float* HF, const float* enc,
+                 const int* enc_len, const float* y, const float* v, const float* alpha, const float* dctx,
+                 int lddctx, float* dHF, float* denc, float* dy, float* dv_part);
+/* Pointwise halves of single cell steps for the general decoder (decoder.py:49-82: MultiRNNCell stacks when
+ * num_layers_dec > 1, GRUCell when use_lstm=False); contiguous [n, *] buffers; the matrix halves are e2e_gemm.
+ *   LSTM (BasicLSTMCell): z [n,4H] = (i|j|f|o); c' = c sig(f+1) + sig(i) tanh(j); h' = tanh(c') sig(o);
+ *        backward takes dc', dh' (either may be NULL = zero) and writes dz, dc.
+ *   GRU (GRUCell): gate: zg [n,2H] = (r|u) -> rh = sig(r) h, u = sig(u); out: h' = u h + (1-u) tanh(zc). */
+int e2e_lstm_point_fwd(void* stream, int n, int H, const float* z, const float* c_prev, float* c_new, float* h_new);
+int e2e_lstm_point_bwd(void* stream, int n, int H, const float* z, const float* c_prev, const float* c_new,
+                       const float* dc_new, const float* dh_new, float* dz, float* dc_prev);
+int e2e_gru_gate_fwd(void* stream, int n, int H, const float* zg, const float* h_prev, float* rh, float* u);
+int e2e_gru_gate_bwd(void* stream, int n, int H, const float* zg, const float* h_prev, const float* drh,
+                     const float* du, float* dzg, float* dh_prev);
+int e2e_gru_out_fwd(void* stream, int n, int H, const float* zc, const float* u, const float* h_prev, float* h_new);
+int e2e_gru_out_bwd(void* stream, int n, int H, const float* zc, const float* u, const float* h_prev,
+                    const float* dh_new, float* dzc, float* du, float* dh_prev);
 int e2e_dec_pointwise_fwd(void* stream, int B, int H, int t, const float* gates_pre, const float* cprev,
                           const float* hprev, int ldh, const int* lens, float* acts, float* cnew_out,
                           int ldc, float* c_next, float* h_next, int ldhn, float* h_new_out);

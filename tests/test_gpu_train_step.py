@@ -279,6 +279,25 @@ def test_multitask_char_and_phone_decoders_match_oracle(cname, ctc):
     compare_step(model, ref, rtol=RTOL)
 
 
+@pytest.mark.parametrize("cname", ["tiny_dec2", "tiny_decgru", "tiny_decgru2"])
+def test_general_decoder_cells_match_oracle(cname):
+    """decoder.py:49-82: lm_cell and the decoder cell as MultiRNNCell stacks (num_layers_dec = 2) and / or GRU cells
+    (use_lstm=False); the attention query is the last layer's c (LSTM) or state (GRU).  Step-by-step path
+    (ops.attn_decoder_stepwise) against the oracle's general restatement, which is bit-identical to the pinned one
+    for the single LSTM cell and checked by finite differences otherwise."""
+    cfg = synth.get_config(cname)
+    w = synth.make_weights(cfg, bias_noise=0.1)
+    batch = synth.make_batch(cfg)
+    dec = {"num_layers_dec": cfg.get("dec_layers", 1), "use_lstm": cfg.get("dec_lstm", True)}
+    ref = om.train_step(w, batch, num_layers={"char": cfg.L}, ctc_tasks=cfg.ctc, dec_params=dec)
+    model = build_model(cfg, w, device="cuda:0")
+    assert model.decoder["char"].general_cells()
+    for _ in range(2):
+        model.run_step(batch)
+        ops.check_device_errors("cuda:0")
+        compare_step(model, ref, rtol=RTOL)
+
+
 def test_adam_updates_match_oracle():
     """apply_updates=True: three Adam steps (fused flat-buffer kernel) against the oracle's TF-formula Adam."""
     cfg = synth.get_config("tiny_b")

@@ -384,3 +384,35 @@ def test_gru_encoder_oracle_vs_torch_autograd_and_finite_differences():
         fd = (om.train_step(wp, batch, want_grads=False, **kw)["total_loss"]
               - om.train_step(wm, batch, want_grads=False, **kw)["total_loss"]) / (2 * eps)
         assert abs(fd - res["grads"][name][idx]) < 1e-6 * max(1.0, abs(fd)), (name, idx, fd)
+
+
+def test_general_decoder_oracle_consistency_and_finite_differences():
+    """oracle attn_decoder_general (MultiRNNCell stacks, GRU cells; decoder.py:49-82): bit-identical to the pinned
+    single-LSTM restatement for num_layers_dec=1, and float64 central differences for a 2-layer LSTM decoder, a GRU
+    decoder and a 2-layer GRU decoder."""
+    cfg = synth.get_config("tiny_b")
+    w = synth.make_weights(cfg, bias_noise=0.1)
+    batch = synth.make_batch(cfg)
+    a = om.train_step(w, batch, num_layers={"char": cfg.L}, ctc_tasks=cfg.ctc)
+    b = om.train_step(w, batch, num_layers={"char": cfg.L}, ctc_tasks=cfg.ctc,
+                      dec_params={"num_layers_dec": 1, "use_lstm": True})
+    assert a["total_loss"] == b["total_loss"] and a["norm"] == b["norm"]
+    assert all(np.array_equal(a["grads"][k], b["grads"][k]) for k in a["grads"])
+    rng = np.random.Generator(np.random.PCG64(3))
+    eps = 1e-6
+    for cname in ("tiny_dec2", "tiny_decgru", "tiny_decgru2"):
+        cfg = synth.get_config(cname)
+        w = synth.make_weights(cfg, bias_noise=0.1)
+        batch = synth.make_batch(cfg)
+        kw = dict(num_layers={"char": cfg.L}, ctc_tasks=cfg.ctc,
+                  dec_params={"num_layers_dec": cfg.get("dec_layers", 1), "use_lstm": cfg.get("dec_lstm", True)})
+        res = om.train_step(w, batch, **kw)
+        for name in sorted(k for k in w if "rnn_decoder" in k):
+            idx = tuple(int(rng.integers(0, s)) for s in w[name].shape)
+            wp = {n: v.astype(np.float64).copy() for n, v in w.items()}
+            wm = {n: v.astype(np.float64).copy() for n, v in w.items()}
+            wp[name][idx] += eps
+            wm[name][idx] -= eps
+            fd = (om.train_step(wp, batch, want_grads=False, **kw)["total_loss"]
+                  - om.train_step(wm, batch, want_grads=False, **kw)["total_loss"]) / (2 * eps)
+            assert abs(fd - res["grads"][name][idx]) < 1e-6 * max(1.0, abs(fd)), (cname, name, idx, fd)
