@@ -165,16 +165,23 @@ class Profiler(object):
     stream around every C call (bench.py turns this on for the timed region)."""
 
     def __init__(self):
-        self.records = []      # (name, start_event, end_event, work)
+        self.records = []      # (name, start_event, end_event, work, stream)
 
-    def summary(self):
+    def summary(self, main_stream=None):
+        """Per entry point: total event time, calls, algorithmic work; `main_ms` / `main_calls` / `main_work` count
+        only the calls enqueued on `main_stream` (the critical path: side-stream events include waiting for SMs)."""
         torch.cuda.synchronize()
         out = {}
-        for name, e0, e1, work in self.records:
-            d = out.setdefault(name, dict(ms=0.0, calls=0, work=0.0))
-            d["ms"] += e0.elapsed_time(e1)
+        for name, e0, e1, work, stream in self.records:
+            d = out.setdefault(name, dict(ms=0.0, calls=0, work=0.0, main_ms=0.0, main_calls=0, main_work=0.0))
+            t = e0.elapsed_time(e1)
+            d["ms"] += t
             d["calls"] += 1
             d["work"] += work
+            if main_stream is not None and stream == main_stream:
+                d["main_ms"] += t
+                d["main_calls"] += 1
+                d["main_work"] += work
         return out
 
 
@@ -204,7 +211,7 @@ def call(name, *args, work=0.0, tag=None):
     rc = getattr(l, name)(stream_ptr(), *conv)
     if prof is not None:
         e1.record()
-        prof.records.append((tag or name, e0, e1, work))
+        prof.records.append((tag or name, e0, e1, work, stream_ptr()))
     if rc != 0:
         raise RuntimeError("%s failed (%d): %s" % (name, rc, l.e2e_last_error().decode()))
     if DEBUG_CAPTURE:
