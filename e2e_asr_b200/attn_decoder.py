@@ -112,8 +112,11 @@ class AttnDecoder(Decoder):
         enc_len = ops.to_i32(seq_len_inp, dev)
         rule = self.input_rule()
         if self.general_cells():
+            drop = None
+            if self.isTraining and self.params.out_prob_dec < 1.0:
+                drop = (self.params.out_prob_dec, getattr(self, "dropout_seed", 0), getattr(self, "dropout_stream", 0))
             return ops.attn_decoder_stepwise(enc, v, v["lm_cells"], v["dec_cells"], self.params.use_lstm, decoder_inp,
-                                             lens, enc_len, U, self.stash)
+                                             lens, enc_len, U, self.stash, drop=drop)
         if rule in ("teacher", "sample"):
             # DropoutWrapper(output_keep_prob=out_prob_dec) iff training (decoder.py:60-63) acts on lm_cell's
             # output only: raw_loop_function reads the decoder cell through get_state(state) = state.c and never

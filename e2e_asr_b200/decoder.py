@@ -36,10 +36,11 @@ class Decoder(BaseParams):
             raise ValueError("Decoder: num_layers_dec=%d must be >= 1" % p.num_layers_dec)
         if self.general_cells():
             # MultiRNNCell stacks / GRU cells run the step-by-step path (ops.attn_decoder_stepwise): teacher forcing
-            # without dropout; the per-step Philox draws and the eval-mode loop are built for the single LSTM cell
-            if self.isTraining and (p.out_prob_dec < 1.0 or p.samp_prob > 0):
-                raise NotImplementedError("Decoder: num_layers_dec > 1 / use_lstm=False are built for "
-                                          "out_prob_dec=1 and samp_prob=0")
+            # (with output dropout); scheduled sampling and the eval-mode loop are built for the single LSTM cell
+            if self.isTraining and p.samp_prob > 0:
+                raise NotImplementedError("Decoder: num_layers_dec > 1 / use_lstm=False are built for samp_prob=0")
+            if self.isTraining and p.out_prob_dec < 1.0 and (p.lm_hidden_size % 4 or p.hidden_size_dec % 4):
+                raise NotImplementedError("Decoder: dropout needs hidden sizes that are multiples of 4")
             if not self.isTraining:
                 raise NotImplementedError("Decoder: greedy decoding is built for the single LSTM cell")
         if not (0.0 < p.out_prob_dec <= 1.0):

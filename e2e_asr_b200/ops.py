@@ -225,20 +225,22 @@ class DropoutFn(torch.autograd.Function):
     y = x * mask / keep with the stateless Philox mask of e2e_dropout; backward regenerates the mask."""
 
     @staticmethod
-    def forward(ctx, x, keep, seed, offset):
+    def forward(ctx, x, keep, seed, offset, first=0):
+        """`first`: index of x's first element in the buffer the mask is defined over (a per-step slice of a
+        [U*B, H] tensor draws that tensor's mask); a multiple of 4."""
         x = x.contiguous()
         y = torch.empty_like(x)
-        call("e2e_dropout", x.numel(), x, y, float(keep), int(seed), int(offset), 0)
-        ctx.cfg = (float(keep), int(seed), int(offset))
+        call("e2e_dropout", x.numel(), x, y, float(keep), int(seed), int(offset), int(first))
+        ctx.cfg = (float(keep), int(seed), int(offset), int(first))
         return y
 
     @staticmethod
     def backward(ctx, dy):
-        keep, seed, offset = ctx.cfg
+        keep, seed, offset, first = ctx.cfg
         dy = dy.contiguous()
         dx = torch.empty_like(dy)
-        call("e2e_dropout", dy.numel(), dy, dx, keep, seed, offset, 0)
-        return dx, None, None, None
+        call("e2e_dropout", dy.numel(), dy, dx, keep, seed, offset, first)
+        return dx, None, None, None, None
 
 
 # Weight-gradient side stream.  The dW GEMMs of a layer (x^T dz, h^T dz, bias column sums) are off the
@@ -580,12 +582,18 @@ def _cell_step(use_lstm, x, state, ws):
     return h2, (h2,)
 
 
-def attn_decoder_stepwise(enc, v, lm_cells, dec_cells, use_lstm, ids, lens_i32, enc_len_i32, U, stash=None):
+def attn_decoder_stepwise(enc, v, lm_cells, dec_cells, use_lstm, ids, lens_i32, enc_len_i32, U, stash=None,
+                          drop=None):
     """AttnDecoder.__call__ (attn_decoder.py:37-172) under teacher forcing for ANY decoder.py cell configuration:
     `lm_cells` / `dec_cells` are lists (one entry per stacked layer) of the cell's variables -- (kernel, bias) for
     BasicLSTMCell, (gates kernel, gates bias, candidate kernel, candidate bias) for GRUCell.  The attention query and
     the projection input are get_state(state): the last layer's c (LSTM) or state (GRU), decoder.py:74-82; raw_rnn
     copies the decoder state through for finished rows and zeroes their emit; the lm state is never frozen.
+    drop = (keep, seed, task index) in training with out_prob_dec < 1: DropoutWrapper(output_keep_prob) on every
+    single cell (decoder.py:60-63) -- each layer's OUTPUT is dropped on its way to the next layer / to
+    InputProjection, the states are not; the top decoder layer's output is never read.  Philox streams: 100 + task
+    for the top lm layer (as for the single cell), 500 + 16 task + l for lower lm layers, 400 + 16 task + l for the
+    decoder layers; the mask of step t is the slice [t*B, (t+1)*B) of a [U*B, H] mask.
     Returns logits [(U*B), V]."""
     dev = enc.device
     B, Tn, D = enc.shape
@@ -609,12 +617,17 @@ def attn_decoder_stepwise(enc, v, lm_cells, dec_cells, use_lstm, ids, lens_i32, 
         x = u_all[t]
         for l, ws in enumerate(lm_cells):                                     # lm_cell stack (attn_decoder.py:148)
             x, lm_state[l] = _cell_step(use_lstm, x, lm_state[l], ws)
+            if drop is not None:
+                stream = 100 + drop[2] if l == len(lm_cells) - 1 else 500 + 16 * drop[2] + l
+                x = DropoutFn.apply(x, drop[0], drop[1], stream, t * B * Hl)
         m = LinearFn.apply(x, v["sp_k"], v["sp_b"]) if v["sp_k"] is not None else x
         x = LinearFn.apply(torch.cat([m, ctx_vec], dim=1), v["in_k"], v["in_b"])       # InputProjection (:157-158)
         new_state = []
         for l, ws in enumerate(dec_cells):                                    # decoder cell stack (raw_rnn body)
             x, st_new = _cell_step(use_lstm, x, dec_state[l], ws)
             new_state.append(st_new)
+            if drop is not None and l < len(dec_cells) - 1:
+                x = DropoutFn.apply(x, drop[0], drop[1], 400 + 16 * drop[2] + l, t * B * Hd)
         q = new_state[-1][0]
         y = LinearFn.apply(q, v["q_k"], v["q_b"])
         ctx_vec = AttnStepFn.apply(y, HF, enc_flat, v["attn_v"], enc_len_i32, dims)

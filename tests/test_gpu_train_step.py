@@ -279,8 +279,9 @@ def test_multitask_char_and_phone_decoders_match_oracle(cname, ctc):
     compare_step(model, ref, rtol=RTOL)
 
 
-@pytest.mark.parametrize("cname", ["tiny_dec2", "tiny_decgru", "tiny_decgru2"])
-def test_general_decoder_cells_match_oracle(cname):
+@pytest.mark.parametrize("cname,keep", [("tiny_dec2", 1.0), ("tiny_decgru", 1.0), ("tiny_decgru2", 1.0),
+                                        ("tiny_dec2", 0.7), ("tiny_decgru2", 0.6)])
+def test_general_decoder_cells_match_oracle(cname, keep):
     """decoder.py:49-82: lm_cell and the decoder cell as MultiRNNCell stacks (num_layers_dec = 2) and / or GRU cells
     (use_lstm=False); the attention query is the last layer's c (LSTM) or state (GRU).  Step-by-step path
     (ops.attn_decoder_stepwise) against the oracle's general restatement, which is bit-identical to the pinned one
@@ -289,10 +290,13 @@ def test_general_decoder_cells_match_oracle(cname):
     w = synth.make_weights(cfg, bias_noise=0.1)
     batch = synth.make_batch(cfg)
     dec = {"num_layers_dec": cfg.get("dec_layers", 1), "use_lstm": cfg.get("dec_lstm", True)}
-    ref = om.train_step(w, batch, num_layers={"char": cfg.L}, ctc_tasks=cfg.ctc, dec_params=dec)
     model = build_model(cfg, w, device="cuda:0")
     assert model.decoder["char"].general_cells()
-    for _ in range(2):
+    model.params.decoder_params["char"].out_prob_dec = keep      # DropoutWrapper on every single cell's output
+    model.params.dropout_seed = 3
+    for step in range(2):
+        ref = om.train_step(w, batch, num_layers={"char": cfg.L}, ctc_tasks=cfg.ctc, dec_params=dec,
+                            out_prob_dec=keep, dropout_seed=3 * 1000003 + step)
         model.run_step(batch)
         ops.check_device_errors("cuda:0")
         compare_step(model, ref, rtol=RTOL)

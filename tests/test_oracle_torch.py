@@ -398,13 +398,19 @@ def test_general_decoder_oracle_consistency_and_finite_differences():
                       dec_params={"num_layers_dec": 1, "use_lstm": True})
     assert a["total_loss"] == b["total_loss"] and a["norm"] == b["norm"]
     assert all(np.array_equal(a["grads"][k], b["grads"][k]) for k in a["grads"])
+    # ... also with output dropout on (the single cell's mask stream is shared by both restatements)
+    kwd = dict(num_layers={"char": cfg.L}, ctc_tasks=cfg.ctc, out_prob_dec=0.7, dropout_seed=9)
+    a = om.train_step(w, batch, **kwd)
+    b = om.train_step(w, batch, dec_params={"num_layers_dec": 1, "use_lstm": True}, **kwd)
+    assert a["total_loss"] == b["total_loss"]
+    assert all(np.array_equal(a["grads"][k], b["grads"][k]) for k in a["grads"])
     rng = np.random.Generator(np.random.PCG64(3))
     eps = 1e-6
-    for cname in ("tiny_dec2", "tiny_decgru", "tiny_decgru2"):
+    for cname, keep in (("tiny_dec2", 1.0), ("tiny_decgru", 1.0), ("tiny_decgru2", 1.0), ("tiny_dec2", 0.6)):
         cfg = synth.get_config(cname)
         w = synth.make_weights(cfg, bias_noise=0.1)
         batch = synth.make_batch(cfg)
-        kw = dict(num_layers={"char": cfg.L}, ctc_tasks=cfg.ctc,
+        kw = dict(num_layers={"char": cfg.L}, ctc_tasks=cfg.ctc, out_prob_dec=keep, dropout_seed=4,
                   dec_params={"num_layers_dec": cfg.get("dec_layers", 1), "use_lstm": cfg.get("dec_lstm", True)})
         res = om.train_step(w, batch, **kw)
         for name in sorted(k for k in w if "rnn_decoder" in k):
