@@ -1034,10 +1034,19 @@ class CTCHeadFn(torch.autograd.Function):
         dev = states.device
         f32 = dict(dtype=torch.float32, device=dev)
         flat, r0, r1 = flat_rows(states)
-        if r0 >= r1:     # batch-major [B,T,D]
+        # batch-major [B,T,D] or the time-major view [T,B,D]?  The strides tell, except when a dimension is 1
+        # (a single utterance: [T,1,D] vs [1,T,D]) -- then the number of utterances (lengths) decides.
+        nb = in_lens_i32.shape[0]
+        if states.shape[0] == nb and states.shape[1] != nb:
+            batch_major = True
+        elif states.shape[1] == nb and states.shape[0] != nb:
+            batch_major = False
+        else:
+            batch_major = r0 >= r1
+        if batch_major:
             B, T = states.shape[0], states.shape[1]
             sb, stt = r0, r1
-        else:            # time-major view [T,B,D]
+        else:
             T, B = states.shape[0], states.shape[1]
             sb, stt = r1, r0
         C = kernel.shape[1]

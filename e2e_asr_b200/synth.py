@@ -71,9 +71,12 @@ def get_config(name, **overrides):
     return cfg
 
 
-def layer_input_sizes(cfg, skip_step=2, max_scaling_down=8):
-    """Input width of every encoder layer (reference encoder.py:154-178)."""
-    sizes, res = [], 1
+def layer_input_sizes(cfg, skip_step=None, max_scaling_down=None):
+    """Input width of every encoder layer (reference encoder.py:154-178); cfg may carry the encoder options
+    skip_step / max_scaling_down / initial_res_fac (cfg.F is the width AFTER frame stacking)."""
+    skip_step = cfg.get("skip_step", 2) if skip_step is None else skip_step
+    max_scaling_down = cfg.get("max_scaling_down", 8) if max_scaling_down is None else max_scaling_down
+    sizes, res = [], cfg.get("initial_res_fac", 1)
     width = cfg.F
     nd = 2 if cfg.get("bi_dir", True) else 1
     for i in range(cfg.L):

@@ -1,0 +1,79 @@
+"""Edge cases of the training step against the oracle: single-utterance batches, one-frame utterances (every pyramid
+level has length 1), one-token targets (EOS only), ragged lengths with odd maxima, and the encoder's input options
+(frame stacking seq2seq_model.py:164-183, initial stride encoder.py:149-153, no pyramid skip_step=1)."""
+import numpy as np
+import pytest
+
+from e2e_asr_b200 import ops, synth
+from e2e_asr_b200.data_utils import EOS_ID, GO_ID, PAD_ID
+from e2e_asr_b200.testing import build_model, compare_step
+from oracle import model as om
+
+pytestmark = pytest.mark.gpu
+
+
+def crafted_batch(cfg, frame_lens, target_lens, seed=0):
+    """A batch with exactly these lengths (logmel zero past each length, ids GO .. EOS PAD..)."""
+    rng = np.random.Generator(np.random.PCG64(seed))
+    B, T, U = len(frame_lens), max(frame_lens), max(target_lens)
+    logmel = rng.standard_normal((B, T, cfg.F)).astype(np.float32)
+    ids = np.full((B, U + 1), PAD_ID, np.int64)
+    for b in range(B):
+        logmel[b, frame_lens[b]:] = 0.0
+        n = target_lens[b]
+        ids[b, 0] = GO_ID
+        ids[b, 1:n] = rng.integers(3, cfg.V, size=n - 1)
+        ids[b, n] = EOS_ID
+    batch = {"logmel": logmel, "logmel_len": np.asarray(frame_lens, np.int64), "char": ids,
+             "char_len": np.asarray(target_lens, np.int64), "utt_id": np.array(["u%d" % b for b in range(B)])}
+    for task, (depth, vocab) in cfg.ctc.items():
+        dl = synth.pyramid_lens(frame_lens, synth.depth_reductions(cfg, depth))
+        ll = np.maximum(1, np.minimum(dl // 2, 3)).astype(np.int64)       # feasible: label length <= frames
+        lab = np.zeros((B, int(ll.max())), np.int64)
+        for b in range(B):
+            lab[b, :ll[b]] = rng.integers(0, vocab, size=int(ll[b]))
+        batch[task], batch[task + "_len"] = lab, ll
+    return batch
+
+
+@pytest.mark.parametrize("frame_lens,target_lens", [
+    ([1], [1]),                          # one utterance, one frame, EOS only
+    ([9], [4]),                          # one utterance
+    ([1, 2, 23], [1, 6, 2]),             # one-frame and two-frame utterances next to a long one; odd maximum
+    ([17, 17, 17, 17], [3, 3, 3, 3]),    # no padding at all
+    ([5, 31, 8, 31, 2], [6, 1, 6, 2, 5]),
+])
+def test_ragged_and_degenerate_lengths(frame_lens, target_lens):
+    cfg = synth.get_config("tiny_b")
+    w = synth.make_weights(cfg, bias_noise=0.1)
+    batch = crafted_batch(cfg, frame_lens, target_lens)
+    ref = om.train_step(w, batch, num_layers={"char": cfg.L}, ctc_tasks=cfg.ctc)
+    assert np.isfinite(ref["total_loss"])
+    model = build_model(cfg, w, device="cuda:0")
+    for _ in range(2):
+        model.run_step(batch)
+        ops.check_device_errors("cuda:0")
+        compare_step(model, ref, rtol=1e-4)
+    # the same step replayed from its CUDA graph
+    gs = model.graphed_step(batch)
+    gs.step(batch)
+    compare_step(model, ref, rtol=1e-4)
+
+
+@pytest.mark.parametrize("enc", [dict(stack_cons=3), dict(initial_res_fac=2), dict(skip_step=1),
+                                 dict(stack_cons=2, initial_res_fac=3, max_scaling_down=2)])
+def test_encoder_input_options(enc):
+    """stack_cons (frame stacking), initial_res_fac (input stride), skip_step=1 (no pyramid), max_scaling_down."""
+    base = synth.get_config("tiny_b")
+    stack = enc.get("stack_cons", 1)
+    # weights for the architecture these options produce: stacked feature width, fewer / no pyramid steps
+    cfg = synth.get_config("tiny_b", F=base.F * stack, ctc={}, **{k: v for k, v in enc.items() if k != "stack_cons"})
+    w = synth.make_weights(cfg, bias_noise=0.1)
+    batch = crafted_batch(base, [37, 20, 9, 33, 1], [5, 9, 2, 1, 4])
+    ref = om.train_step(w, batch, num_layers={"char": cfg.L}, ctc_tasks={}, enc_params=enc)
+    model = build_model(cfg, w, device="cuda:0", ctc=False)
+    for k, v in enc.items():
+        model.params.encoder_params[k] = v
+    model.run_step(batch)
+    ops.check_device_errors("cuda:0")
+    compare_step(model, ref, rtol=1e-4)
