@@ -77,3 +77,30 @@ def test_encoder_input_options(enc):
     model.run_step(batch)
     ops.check_device_errors("cuda:0")
     compare_step(model, ref, rtol=1e-4)
+
+
+@pytest.mark.parametrize("frame_lens,target_lens", [
+    ([57], [9]),                                             # one utterance through the flagship kernels
+    ([40, 3, 64, 17, 1, 64, 33, 8, 21, 5, 64, 2, 47, 30, 11, 64, 9], [12, 1, 3, 12, 2, 7, 1, 12, 5, 9, 4, 12, 6, 2, 8, 3, 10]),
+])
+@pytest.mark.parametrize("mode", ["fp32", "tf32x3"])
+def test_ragged_batches_at_reference_widths(frame_lens, target_lens, mode):
+    """The reference's default widths (H = Hd = Hl = 256, A = 128, V = 1000: the cluster-resident recurrence, the
+    persistent decoder loop, tcgen05 GEMMs) on a single utterance and on 17 utterances (not a multiple of the 16-row
+    batch slices) with lengths from 1 frame / 1 token to the maximum."""
+    cfg = synth.get_config("cfg1")
+    w = synth.make_weights(cfg, bias_noise=0.1)
+    batch = crafted_batch(cfg, frame_lens, target_lens)
+    ref = om.train_step(w, batch, num_layers={"char": cfg.L}, ctc_tasks=cfg.ctc)
+    ops.set_gemm_mode(mode)
+    try:
+        model = build_model(cfg, w, device="cuda:0")
+        for _ in range(2):
+            model.run_step(batch)
+            ops.check_device_errors("cuda:0")
+            compare_step(model, ref, rtol=1e-4)
+        gs = model.graphed_step(batch)
+        gs.step(batch)
+        compare_step(model, ref, rtol=1e-4)
+    finally:
+        ops.set_gemm_mode("fp32")
