@@ -152,4 +152,22 @@ def main():
 
 
 if __name__ == "__main__":
+    gen_relevant_words()
     main()
+
+
+def gen_relevant_words():
+    """tests/golden/relevant_words.json: the reference's own data_utils.get_relevant_words (data_utils.py:20-33,
+    `tensorflow` stubbed) on sample transcripts -- pins e2e_asr_b200/scoring.py."""
+    import importlib
+    import json
+    sys.modules.setdefault("tensorflow", types.ModuleType("tensorflow"))
+    if REF not in sys.path:
+        sys.path.insert(0, REF)
+    du = importlib.import_module("data_utils")
+    samples = ["hello<sp>world", "uh i mean um the the-  cat", "[noise] yeah [laughter] right-", "", "  a   b  ",
+               "ha-ha haha ha", "well<sp>uh<sp>y-<sp>you know", "mm hm okay", "eee-<sp>ew<sp>er<sp>error",
+               "[vocalized-noise]<sp>so<sp>-"]
+    out = [{"in": s_, "words": du.get_relevant_words(s_)[0], "rel": du.get_relevant_words(s_)[1]} for s_ in samples]
+    with open(os.path.join(HERE, "relevant_words.json"), "w") as f:
+        json.dump(out, f, indent=0)
