@@ -151,11 +151,6 @@ def main():
         print("wrote beam_%s.npz" % tag, {k: [len(res["ids_k%d_u%d" % (k, u)]) for u in range(n_utt)] for k in beams})
 
 
-if __name__ == "__main__":
-    gen_relevant_words()
-    main()
-
-
 def gen_relevant_words():
     """tests/golden/relevant_words.json: the reference's own data_utils.get_relevant_words (data_utils.py:20-33,
     `tensorflow` stubbed) on sample transcripts -- pins e2e_asr_b200/scoring.py."""
@@ -171,3 +166,8 @@ def gen_relevant_words():
     out = [{"in": s_, "words": du.get_relevant_words(s_)[0], "rel": du.get_relevant_words(s_)[1]} for s_ in samples]
     with open(os.path.join(HERE, "relevant_words.json"), "w") as f:
         json.dump(out, f, indent=0)
+
+
+if __name__ == "__main__":
+    gen_relevant_words()
+    main()
