@@ -390,9 +390,39 @@ def main():
                 "us_per_timestep": tv["ms"] * 1e3 / max(steps_total, 1.0), "note": "latency-bound sequential kernel"}
     rec = {k: summ[k] for k in summ if "rec" in k}
     extra = {k: {"us_per_timestep": v["ms"] * 1e3 / max(v["work"], 1.0)} for k, v in rec.items()}
-    for k in ("e2e_decoder_loop_fwd", "e2e_decoder_loop_bwd"):
+    for k in ("e2e_decoder_loop_fwd", "e2e_decoder_loop_bwd", "e2e_decoder_persist_fwd", "e2e_decoder_persist_bwd"):
         if k in summ:
             extra[k] = {"us_per_timestep": summ[k]["ms"] * 1e3 / max(summ[k]["work"], 1.0)}
+    memory_bound = {}
+    try:
+        # memory-bound kernels: ALGORITHMIC bytes per call / event time, against the measured HBM peak
+        D_, T_enc = 2 * cfg.H, synth.pyramid_lens([cfg.T], synth.depth_reductions(cfg, cfg.L))[0]
+        rows_ce = cfg.U * cfg.B * cfg.V * 4
+        mem_bytes = {"e2e_ce_fwd": rows_ce,                         # reads the logits once (lse, picked cost)
+                     "e2e_ce_bwd": 2 * rows_ce,                     # reads logits, writes d logits
+                     # attention(): HF [B,T_enc,A] + enc [B,T_enc,D] read once per decoder step (14.4 MB at cfg-2; the
+                     # working set fits the 126 MB L2, so this is L2 -> SM traffic, not HBM)
+                     "e2e_decoder_persist_fwd": cfg.U * 4 * cfg.B * int(T_enc) * (cfg.A + D_)}
+        ctc_bytes = 0
+        for t_, (depth, vocab) in cfg.ctc.items():
+            Td = int(synth.pyramid_lens([cfg.T], synth.depth_reductions(cfg, depth))[0])
+            ctc_bytes += 2 * 4 * Td * cfg.B * (vocab + 1)           # read the logits, write their gradient
+        n_heads = max(len(cfg.ctc), 1)
+        mem_bytes["e2e_ctc_fwd_grad"] = ctc_bytes / n_heads         # per call (one call per head)
+        for k, bytes_per_call in mem_bytes.items():
+            if k in summ and summ[k]["ms"] > 0:
+                gbs = bytes_per_call * summ[k]["calls"] / (summ[k]["ms"] * 1e-3) / 1e9
+                memory_bound[k] = {"algorithmic_mb_per_call": bytes_per_call / 1e6, "achieved_gbs": gbs,
+                                   "frac_of_hbm_peak": gbs / peaks["hbm"]}
+        if "e2e_ctc_fwd_grad" in memory_bound:
+            memory_bound["e2e_ctc_fwd_grad"]["note"] = ("alpha/beta sweep = T_l sequential frames per utterance (one warp "
+                                                        "each): latency-bound, on its own stream beside the decoder")
+        if "e2e_decoder_persist_fwd" in memory_bound:
+            memory_bound["e2e_decoder_persist_fwd"]["note"] = ("attention operands only; L2-resident; the kernel also "
+                                                               "runs the gate GEMMs and 3 grid barriers per step")
+
+    except Exception as e:          # supplementary section: never cost the run its JSON line
+        memory_bound = {"error": repr(e)}
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
@@ -405,7 +435,7 @@ def main():
         "eager": {"ms_per_step": ms_eager / K, "host_enqueue_ms_per_step": host_eager_ms,
                   "note": "same K steps launched kernel by kernel; the per-kernel events of breakdown/roofline come "
                           "from this pass (a graph replay runs the identical kernels)"},
-        "roofline": roof, "breakdown": breakdown, "sequential_kernels": extra,
+        "roofline": roof, "breakdown": breakdown, "sequential_kernels": extra, "memory_bound_kernels": memory_bound,
     }
     if world == 1 and not args.no_cpu_baseline:
         cores = os.cpu_count() or 1
