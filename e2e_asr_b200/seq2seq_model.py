@@ -407,9 +407,16 @@ class GraphedStep(object):
         # are scheduled ahead of the weight-gradient / CTC branches that only have to finish by the end of the step
         self.stream = torch.cuda.Stream(device=model.device, priority=-1)
         self.stream.wait_stream(cur)
-        with torch.cuda.stream(self.stream):
-            for _ in range(warmup):
-                model.run_step(prepared=self.prepared)
+        # (the warm-up steps must leave the training state alone: no optimiser update, same step counter)
+        apply_updates, global_step = p.get('apply_updates', False), model.global_step
+        p['apply_updates'] = False
+        try:
+            with torch.cuda.stream(self.stream):
+                for _ in range(warmup):
+                    model.run_step(prepared=self.prepared)
+        finally:
+            p['apply_updates'] = apply_updates
+            model.global_step = global_step
         while model._inflight:
             model._inflight.pop(0).synchronize()
         torch.cuda.synchronize()

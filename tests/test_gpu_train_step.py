@@ -302,17 +302,26 @@ def test_general_decoder_cells_match_oracle(cname, keep):
         compare_step(model, ref, rtol=RTOL)
 
 
-def test_adam_updates_match_oracle():
-    """apply_updates=True: three Adam steps (fused flat-buffer kernel) against the oracle's TF-formula Adam."""
+@pytest.mark.parametrize("graphed", [False, True])
+def test_adam_updates_match_oracle(graphed):
+    """apply_updates=True: three Adam steps (fused flat-buffer kernel) against the oracle's TF-formula Adam, eager and
+    with the step replayed from its CUDA graph (capturing must not touch the parameters or the optimiser state; the
+    replays read the updated weights in place)."""
     cfg = synth.get_config("tiny_b")
     w = synth.make_weights(cfg, bias_noise=0.1)
     batch = synth.make_batch(cfg)
     model = build_model(cfg, w, device="cuda:0")
     model.params.apply_updates = True
+    gs = model.graphed_step(batch) if graphed else None
+    if graphed:
+        assert model.global_step == 0 and model._adam is None
     wref = {k: v.astype(np.float64) for k, v in w.items()}
     state = {}
     for step in range(3):
-        model.run_step(batch)
+        if graphed:
+            gs.step(batch)
+        else:
+            model.run_step(batch)
         ref = om.train_step(wref, batch, num_layers={"char": cfg.L}, ctc_tasks=cfg.ctc)
         wref = om.adam_step(wref, ref["clipped"], state, 1e-3)
     got = model.variables.state_dict()
