@@ -330,3 +330,26 @@ def test_adam_updates_match_oracle(graphed):
         # a step moves a weight by ~lr = 1e-3: 1e-6 absolute = 1e-3 of the update
         assert err < 2e-6, (k, err)
         assert float(np.abs(got[k] - w[k]).max()) > 1e-4      # the parameters really moved
+
+
+def test_training_loop_overfits_one_batch_like_the_oracle():
+    """60 Adam steps (lr 1e-2) on one batch through graph replays: the loss must fall from ~7.6 to ~0.2 and follow the
+    float64 oracle's own trajectory (fp32 rounding is amplified along 60 updates, hence the loose 5 % band)."""
+    cfg = synth.get_config("tiny_b")
+    w = synth.make_weights(cfg)
+    batch = synth.make_batch(cfg)
+    model = build_model(cfg, w, device="cuda:0")
+    model.params.apply_updates = True
+    model.learning_rate = 1e-2
+    gs = model.graphed_step(batch)
+    wref = {k: v.astype(np.float64) for k, v in w.items()}
+    state = {}
+    for step in range(60):
+        gs.step(batch)
+        ref = om.train_step(wref, batch, num_layers={"char": cfg.L}, ctc_tasks=cfg.ctc)
+        wref = om.adam_step(wref, ref["clipped"], state, 1e-2)
+        if step in (0, 20, 40, 59):
+            got = float(model.total_loss)
+            assert abs(got - ref["total_loss"]) <= 0.05 * max(1.0, ref["total_loss"]), (step, got, ref["total_loss"])
+    assert float(model.total_loss) < 0.5
+    ops.check_device_errors("cuda:0")
