@@ -62,7 +62,7 @@ def compare_step(model, ref, rtol=1e-4, check_logits=True):
     oracle dict `ref` within `rtol` (max-abs error relative to the tensor's max-abs,
     the north-star's "1e-4 relative").  Returns the worst gradient error."""
     for t, l in ref["losses"].items():
-        got = float(model.losses[t])
+        got = float(model.losses[t].detach())
         assert abs(got - l) <= rtol * max(1.0, abs(l)), ("loss", t, got, l)
     assert abs(float(model.total_loss) - ref["total_loss"]) <= rtol * max(1.0, abs(ref["total_loss"]))
     if check_logits:
