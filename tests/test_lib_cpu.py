@@ -39,3 +39,34 @@ def test_no_cpu_fallback(libpath):
     with pytest.raises(RuntimeError, match="no CUDA device"):
         _lib.call("e2e_mean", 1, None, None)
     assert _lib.lib().e2e_sm_count() == -1
+
+
+def test_binding_signatures_match_the_header():
+    """Every ctypes signature string in _lib._SIGS has one letter per parameter of the header's declaration, and the
+    letter's class (pointer / integer / float / size) matches the declared C type."""
+    header = open(os.path.join(ROOT, "include", "e2e_asr_b200.h")).read()
+    header = re.sub(r"/\*.*?\*/", " ", header, flags=re.S)
+    decls = dict(re.findall(r"\bint\s+(e2e_[a-z0-9_]+)\s*\(([^;{]*?)\)\s*;", header, flags=re.S))
+    kinds = {"p": "ptr", "i": "int", "I": "uint", "l": "longlong", "z": "size", "f": "float", "d": "double",
+             "Q": "ulonglong"}
+
+    def classify(param):
+        p = " ".join(param.split())
+        if "*" in p:
+            return "ptr"
+        for key, pat in (("ulonglong", r"\bunsigned long long\b"), ("longlong", r"\blong long\b"),
+                         ("size", r"\bsize_t\b"), ("uint", r"\bunsigned\b"), ("float", r"\bfloat\b"),
+                         ("double", r"\bdouble\b"), ("int", r"\bint\b")):
+            if re.search(pat, p):
+                return key
+        raise AssertionError("unclassified parameter %r" % param)
+
+    checked = 0
+    for name, sig in _lib._SIGS.items():
+        assert name in decls, name
+        params = [p for p in decls[name].split(",") if p.strip() and p.strip() != "void"]
+        assert len(params) == len(sig), (name, len(params), sig)
+        for letter, param in zip(sig, params):
+            assert kinds[letter] == classify(param), (name, letter, param.strip())
+        checked += 1
+    assert checked >= 40
