@@ -99,8 +99,13 @@ class BeamSearch(BaseParams):
         self.use_lm = not (self.search_params.lm_path is None or self.search_params.lm_weight == 0.0)
 
     def get_model_params(self, ckpt_path):
+        """Weights by TF variable name (beam_search.py:36-47 reads them with tf.train.NewCheckpointReader): a dict, a
+        TF V2 checkpoint prefix (`<prefix>.index` + data shards, read by tf_checkpoint.py) or an .npz file."""
         if isinstance(ckpt_path, dict):
             return ckpt_path
+        from .tf_checkpoint import checkpoint_exists, read_checkpoint
+        if checkpoint_exists(ckpt_path):
+            return read_checkpoint(ckpt_path)
         return dict(np.load(ckpt_path))
 
     def map_dec_variables(self, var_dict, task="char"):

@@ -32,7 +32,12 @@ class VariableStore(object):
     def load(self, weights):
         """Provide values (numpy, keyed by TF variable name) used instead of the
         random initialisers when the variables are first requested; variables
-        that already exist are overwritten."""
+        that already exist are overwritten.  `weights` may also be the prefix of a
+        TF V2 checkpoint (tf_utils.py:66-90 restores by these names), read by
+        tf_checkpoint.py; non-float entries (global_step, ...) are skipped."""
+        if isinstance(weights, str):
+            from .tf_checkpoint import read_checkpoint
+            weights = {k: v for k, v in read_checkpoint(weights).items() if v.dtype.kind == "f"}
         for k, v in weights.items():
             self.preloaded[k] = np.asarray(v, np.float32)
             if k in self.vars:
@@ -105,6 +110,12 @@ class VariableStore(object):
         for n, v in self.vars.items():     # re-attach (autograd may have replaced .grad)
             o, shp = self.specs[n]
             v.grad = self.gflat.data[o:o + int(np.prod(shp))].view(shp)
+
+    def save_checkpoint(self, prefix):
+        """Writes the variables as a TF V2 checkpoint (`<prefix>.index`, `<prefix>.data-00000-of-00001`) under their
+        TF names."""
+        from .tf_checkpoint import write_checkpoint
+        write_checkpoint(prefix, self.state_dict())
 
     def state_dict(self):
         return {n: self.vars[n].detach().cpu().numpy().copy() for n in self.order}
