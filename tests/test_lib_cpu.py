@@ -70,3 +70,10 @@ def test_binding_signatures_match_the_header():
             assert kinds[letter] == classify(param), (name, letter, param.strip())
         checked += 1
     assert checked >= 40
+
+
+def test_every_entry_point_is_documented_in_integration_md():
+    header = open(os.path.join(ROOT, "include", "e2e_asr_b200.h")).read()
+    doc = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    declared = set(re.findall(r"\b(e2e_[a-z0-9_]+)\s*\(", header))
+    assert not [f for f in sorted(declared) if f not in doc]
