@@ -48,6 +48,10 @@ class Decoder(BaseParams):
         if not (0.0 <= p.samp_prob <= 1.0):
             raise ValueError("Decoder: samp_prob=%g must be in [0, 1]" % p.samp_prob)
 
+    def __call__(self, decoder_inp, seq_len, encoder_hidden_states, seq_len_inp):
+        """Abstract in the reference too (decoder.py:117-137): implemented by AttnDecoder."""
+        raise NotImplementedError("Decoder.__call__ is abstract: use AttnDecoder")
+
     def general_cells(self):
         """True when lm_cell / the decoder cell are not single LSTM cells (decoder.py:49-72)."""
         return self.params.num_layers_dec > 1 or not self.params.use_lstm

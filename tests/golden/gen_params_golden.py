@@ -60,11 +60,21 @@ def main():
             return [plain(x) for x in v]
         return v
 
+    import inspect
     out = {}
     for mod, cls in [("encoder", "Encoder"), ("decoder", "Decoder"), ("attn_decoder", "AttnDecoder"),
-                     ("seq2seq_model", "Seq2SeqModel"), ("beam_search", "BeamSearch")]:
+                     ("seq2seq_model", "Seq2SeqModel"), ("beam_search", "BeamSearch"), ("losses", "LossUtils"),
+                     ("basic_lstm", "BasicLSTM")]:
         C = getattr(importlib.import_module(mod), cls)
-        entry = {"class_params": plain(dict(C.class_params()))}
+        entry = {"class_params": plain(dict(C.class_params()))} if hasattr(C, "class_params") else {}
+        sigs = {}
+        for meth in ("__init__", "__call__", "get_state", "get_batch", "cross_entropy_loss"):
+            f = C.__dict__.get(meth)
+            f = f.__func__ if isinstance(f, (staticmethod, classmethod)) else f
+            if f is not None and inspect.isfunction(f):
+                sigs[meth] = [[n, None if prm.default is inspect.Parameter.empty else repr(prm.default)]
+                              for n, prm in inspect.signature(f).parameters.items()]
+        entry["signatures"] = sigs
         if hasattr(C, "add_parse_options"):
             p = argparse.ArgumentParser()
             C.add_parse_options(p)
@@ -79,4 +89,4 @@ def main():
 
 if __name__ == "__main__":
     for k, v in main().items():
-        print(k, len(v["class_params"]), len(v.get("flags", {})))
+        print(k, len(v.get("class_params", {})), len(v.get("flags", {})), sorted(v["signatures"]))

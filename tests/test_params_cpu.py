@@ -27,6 +27,23 @@ def plain(v):
 
 
 @pytest.mark.parametrize("cls", sorted(GOLD))
+def test_call_signatures_extend_the_reference(cls):
+    """Constructor / call / helper signatures: the reference's parameters come first, same names, same defaults; only
+    optional keyword parameters (variables=, device=, reducer=, task=) are appended."""
+    import inspect
+    C = getattr(pkg, cls)
+    for meth, ref_params in GOLD[cls]["signatures"].items():
+        f = C.__dict__.get(meth)
+        if f is None:                      # inherited (e.g. AttnDecoder.get_state from Decoder)
+            f = getattr(C, meth)
+        f = f.__func__ if isinstance(f, (staticmethod, classmethod)) else f
+        ours = [[n, None if prm.default is inspect.Parameter.empty else repr(prm.default)]
+                for n, prm in inspect.signature(f).parameters.items()]
+        assert ours[:len(ref_params)] == ref_params, (cls, meth, ours, ref_params)
+        assert all(d is not None for _, d in ours[len(ref_params):]), (cls, meth, ours)
+
+
+@pytest.mark.parametrize("cls", sorted(c for c in GOLD if "class_params" in GOLD[c]))
 def test_class_params_equal_the_reference(cls):
     ours = plain(dict(getattr(pkg, cls).class_params()))
     ref = GOLD[cls]["class_params"]
