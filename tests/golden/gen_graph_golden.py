@@ -1,0 +1,109 @@
+"""tests/golden/graph_*.npz: encoder states, decoder logits and losses produced by EXECUTING the reference's own
+Encoder.__call__ (encoder.py:122-180), AttnDecoder.__call__ (attn_decoder.py:37-172, incl. raw_loop_function and
+attention()), Decoder.prepare_decoder_input / get_cell / get_state (decoder.py) and LossUtils.cross_entropy_loss on
+the NumPy stand-in for TensorFlow of np_tf.py, with the synthetic weights of e2e_asr_b200.synth keyed by TF variable
+name.  The generator also asserts that the reference consumed EVERY weight under exactly the name synth / the product
+give it (scope structure of the reference + TF's naming rules as restated in np_tf.py).
+
+Configurations: bidirectional LSTM encoder + single-LSTM decoder (the benchmarked model), forward-only encoder, GRU
+encoder, 2-layer LSTM decoder, GRU decoder, 2-layer GRU decoder.  Run in the build container only; the reference
+sources are copied to a temporary directory with one mechanical Python-2 fix (dict.has_key -> in)."""
+import builtins
+import importlib
+import os
+import re
+import shutil
+import sys
+import tempfile
+import types
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, HERE)
+sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
+import np_tf  # noqa: E402
+from e2e_asr_b200 import synth  # noqa: E402
+from e2e_asr_b200.base_params import Bunch  # noqa: E402
+
+REF = "/root/reference"
+CASES = {   # name -> (synth config, encoder params, decoder params)
+    "lstm": ("tiny_b", {}, {}),
+    "uni": ("tiny_uni", {"bi_dir": False}, {}),
+    "gru_enc": ("tiny_gru", {"use_lstm": False}, {}),
+    "dec2": ("tiny_dec2", {}, {"num_layers_dec": 2}),
+    "decgru": ("tiny_decgru", {}, {"use_lstm": False}),
+    "decgru2": ("tiny_decgru2", {}, {"num_layers_dec": 2, "use_lstm": False}),
+}
+
+
+def load_reference(tf):
+    tmp = tempfile.mkdtemp(prefix="ref_py3_")
+    for name in ("encoder", "decoder", "attn_decoder", "losses", "tf_utils", "base_params"):
+        src = open(os.path.join(REF, name + ".py")).read()
+        src = re.sub(r"(\w+)\.has_key\(([^)]*)\)", r"(\2 in \1)", src)
+        open(os.path.join(tmp, name + ".py"), "w").write(src)
+    sys.modules["tensorflow"] = tf
+    for name in ("tensorflow.contrib", "tensorflow.contrib.rnn", "tensorflow.contrib.rnn.python",
+                 "tensorflow.contrib.rnn.python.ops", "tensorflow.contrib.rnn.python.ops.core_rnn_cell"):
+        m = types.ModuleType(name)
+        m._linear = tf._linear
+        sys.modules[name] = m
+    b = types.ModuleType("bunch")
+    b.Bunch = Bunch
+    sys.modules["bunch"] = b
+    builtins.xrange = range
+    sys.path.insert(0, tmp)
+    mods = {}
+    for name in ("base_params", "encoder", "decoder", "attn_decoder", "losses", "tf_utils"):
+        sys.modules.pop(name, None)
+        mods[name] = importlib.import_module(name)
+    sys.path.remove(tmp)
+    shutil.rmtree(tmp)
+    return mods
+
+
+def run_case(case):
+    cname, enc_over, dec_over = CASES[case]
+    cfg = synth.get_config(cname)
+    w = synth.make_weights(cfg, bias_noise=0.1)
+    batch = synth.make_batch(cfg)
+    tf = np_tf.make_tf(w)
+    mods = load_reference(tf)
+    ep = mods["encoder"].Encoder.class_params()
+    ep.hidden_size, ep.use_lstm, ep.out_prob = cfg.H, True, 1.0
+    ep.update(enc_over)
+    dp = mods["attn_decoder"].AttnDecoder.class_params()
+    dp.hidden_size_dec, dp.emb_size, dp.vocab_size = cfg.Hd, cfg.E, cfg.V
+    dp.attention_vec_size, dp.lm_hidden_size, dp.max_output = cfg.A, cfg.Hl, cfg.U
+    dp.out_prob_dec, dp.samp_prob = 1.0, 0.0
+    dp.update(dec_over)
+    out = {}
+    with tf.variable_scope("model"):
+        enc = mods["encoder"].Encoder(params=ep, isTraining=True)
+        att, tm, lens = enc(np_tf.t(batch["logmel"].astype(np.float64)), np_tf.t(batch["logmel_len"]),
+                            {"char": cfg.L, "state": max(1, cfg.L - 1)})
+        for d, v in att.items():
+            out["states/%d" % d] = np.asarray(v)
+        for d, v in tm.items():
+            out["time_major/%d" % d] = np.asarray(v)
+        for d, v in lens.items():
+            out["lens/%d" % d] = np.asarray(v)
+        dec = mods["attn_decoder"].AttnDecoder(isTraining=True, params=dp, scope="char")
+        dec_inp = np_tf.t(np.ascontiguousarray(batch["char"].T))
+        seq_len = np_tf.t(batch["char_len"])
+        logits = dec(dec_inp, seq_len, att[cfg.L], lens[cfg.L])
+        targets, weights = mods["tf_utils"].create_shifted_targets(dec_inp, seq_len)
+        loss = mods["losses"].LossUtils.cross_entropy_loss(logits, targets, seq_len)
+    out["logits"], out["loss"] = np.asarray(logits), np.asarray(loss)
+    used = set(tf._graph.used)
+    expect = {k for k in w if not k.startswith("model/ctc_")}
+    assert used == expect, (sorted(expect - used), sorted(used - expect))
+    np.savez(os.path.join(HERE, "graph_%s.npz" % case), **out)
+    return out, len(used)
+
+
+if __name__ == "__main__":
+    for case in CASES:
+        o, n = run_case(case)
+        print(case, "loss", float(o["loss"]), "logits", o["logits"].shape, "variables consumed", n)
