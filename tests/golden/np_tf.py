@@ -389,4 +389,21 @@ def make_tf(weights):
             y = y + g.get_variable("bias", [int(output_size)])
         return t(y)
     tf._linear = _linear
+
+    # Randomness of scheduled sampling (attn_decoder.py:131-136, decoder.py:176): TF's generators cannot be reproduced,
+    # so a generator may inject draws -- tf._draws = dict(uniform=fn(step) -> scalar, multinomial=fn(step, logits) ->
+    # ids); tf.random_uniform([]) is evaluated once per loop step (step = number of calls so far), tf.multinomial uses
+    # the step of the preceding uniform draw.
+    tf._draws, tf._step = None, [0]
+
+    def random_uniform(shape, *a, **k):
+        assert list(shape) == [] and tf._draws is not None
+        tf._step[0] += 1
+        return t(tf._draws["uniform"](tf._step[0]))
+    tf.random_uniform = random_uniform
+
+    def multinomial(logits, num_samples, *a, **k):
+        assert num_samples == 1 and tf._draws is not None
+        return t(np.asarray(tf._draws["multinomial"](tf._step[0], np.asarray(logits))).reshape(-1, 1))
+    tf.multinomial = multinomial
     return tf

@@ -39,3 +39,39 @@ def test_oracle_forward_equals_the_executed_reference_graph(case):
             assert np.array_equal(res["lens"][int(key.split("/")[1])], G[key])
     np.testing.assert_allclose(res["logits"]["char"], G["logits"], rtol=0, atol=1e-12)
     assert abs(res["losses"]["char"] - float(G["loss"])) < 1e-12
+
+
+def _decoder_inputs():
+    cfg = synth.get_config("tiny_b")
+    w = synth.make_weights(cfg, bias_noise=0.1)
+    w["model/rnn_decoder_char/rnn/OutputProjection/kernel"] = w["model/rnn_decoder_char/rnn/OutputProjection/kernel"] * 6.0
+    batch = synth.make_batch(cfg)
+    W64 = {k: v.astype(np.float64) for k, v in w.items()}
+    states, lens_d, _ = om.encoder_fwd(W64, batch["logmel"].astype(np.float64), batch["logmel_len"], {"char": cfg.L})
+    return cfg, W64, batch, states[cfg.L], lens_d[cfg.L]
+
+
+def test_greedy_mode_equals_the_executed_reference_eval_graph():
+    """isTraining=False: the reference's loop function embeds argmax(previous logits) (decoder.py:139-153,
+    attn_decoder.py:128-129) and runs max_output steps for every row (seq2seq_model.py:191-193)."""
+    G = np.load(os.path.join(os.path.dirname(__file__), "golden", "graph_modes.npz"))
+    cfg, W, batch, enc, enc_len = _decoder_inputs()
+    logits, _ = om.attn_decoder_fwd(W, "char", batch["char"].T, np.full(cfg.B, cfg.U), enc, enc_len, mode="greedy",
+                                    max_steps=cfg.U)
+    np.testing.assert_allclose(logits, G["eval/logits"], rtol=0, atol=1e-11)
+    assert np.array_equal(logits.reshape(cfg.U, cfg.B, -1).argmax(2), G["eval/logits"].reshape(cfg.U, cfg.B, -1).argmax(2))
+
+
+def test_scheduled_sampling_equals_the_executed_reference_training_graph():
+    """samp_prob = 0.5: the reference's own branching (one scalar draw per step, tf.less(random_prob, 1 - samp_prob),
+    multinomial over the previous logits; attn_decoder.py:130-139, decoder.py:155-180) executed with the oracle's
+    Philox draws injected for tf.random_uniform / tf.multinomial."""
+    G = np.load(os.path.join(os.path.dirname(__file__), "golden", "graph_modes.npz"))
+    cfg, W, batch, enc, enc_len = _decoder_inputs()
+    seed = int(G["seed"])
+    logits, cache = om.attn_decoder_fwd(W, "char", batch["char"].T, batch["char_len"], enc, enc_len, mode="sample",
+                                        samp=(0.5, seed, 0))
+    assert G["sample/use"][1:logits.shape[0] // cfg.B].any()                # some steps really sampled
+    teacher = batch["char"].T[:len(cache["toks"])]
+    assert (np.stack(cache["toks"]) != teacher).any()
+    np.testing.assert_allclose(logits, G["sample/logits"], rtol=0, atol=1e-11)
