@@ -39,7 +39,8 @@ CASES = {   # name -> (synth config, encoder params, decoder params)
 
 def load_reference(tf):
     tmp = tempfile.mkdtemp(prefix="ref_py3_")
-    for name in ("encoder", "decoder", "attn_decoder", "losses", "tf_utils", "base_params"):
+    for name in ("encoder", "decoder", "attn_decoder", "losses", "tf_utils", "base_params", "seq2seq_model",
+                 "data_utils"):
         src = open(os.path.join(REF, name + ".py")).read()
         src = re.sub(r"(\w+)\.has_key\(([^)]*)\)", r"(\2 in \1)", src)
         open(os.path.join(tmp, name + ".py"), "w").write(src)
@@ -55,8 +56,10 @@ def load_reference(tf):
     builtins.xrange = range
     sys.path.insert(0, tmp)
     mods = {}
-    for name in ("base_params", "encoder", "decoder", "attn_decoder", "losses", "tf_utils"):
+    for name in ("base_params", "data_utils", "encoder", "decoder", "attn_decoder", "losses", "tf_utils",
+                 "seq2seq_model"):
         sys.modules.pop(name, None)
+    for name in ("base_params", "encoder", "decoder", "attn_decoder", "losses", "tf_utils", "seq2seq_model"):
         mods[name] = importlib.import_module(name)
     sys.path.remove(tmp)
     shutil.rmtree(tmp)
@@ -99,6 +102,52 @@ def run_decoder_modes():
         out[mode + "/logits"] = np.asarray(logits)
     out["seed"] = np.array(77)
     np.savez(os.path.join(HERE, "graph_modes.npz"), **out)
+    return out
+
+
+def run_multitask():
+    """graph_multitask.npz: Seq2SeqModel.__init__ + create_computational_graph (seq2seq_model.py:50-144) executed for
+    the reference's multitask setup -- a char decoder on the top layer and a phone decoder one layer below (main.py:
+    89-93), frame stacking on -- with avg = True and False: per-task losses and total_loss."""
+    cfg = synth.get_config("tiny_b", V_phone=13)
+    base_F = cfg.F
+    cfg.F = base_F * 2                       # weights for stack_cons = 2
+    tasks = ("char", "phone")
+    w = synth.make_weights(cfg, tasks=tasks, bias_noise=0.1)
+    cfg.F = base_F
+    batch = synth.make_batch(cfg, tasks=tasks)
+    out = {}
+    for avg in (True, False):
+        tf = np_tf.make_tf(w)
+        mods = load_reference(tf)
+        S = mods["seq2seq_model"].Seq2SeqModel
+        p = S.class_params()
+        p.tasks, p.num_layers, p.max_output, p.avg = list(tasks), {"char": cfg.L, "phone": cfg.L - 1}, \
+            {"char": cfg.U, "phone": cfg.U}, avg
+        p.encoder_params.hidden_size, p.encoder_params.use_lstm, p.encoder_params.out_prob = cfg.H, True, 1.0
+        p.encoder_params.stack_cons = 2
+        dps = {}
+        for task in tasks:
+            dp = mods["attn_decoder"].AttnDecoder.class_params()
+            dp.hidden_size_dec, dp.emb_size = cfg.Hd, cfg.E
+            dp.vocab_size = cfg.V if task == "char" else 13
+            dp.attention_vec_size, dp.lm_hidden_size, dp.max_output = cfg.A, cfg.Hl, cfg.U
+            dp.out_prob_dec, dp.samp_prob = 1.0, 0.0
+            dps[task] = dp
+        p.decoder_params = dps
+        feed = {k: (np_tf.t(v.astype(np.float64)) if k == "logmel" else (np_tf.t(v) if v.dtype.kind in "if" else v))
+                for k, v in batch.items()}
+        it = types.SimpleNamespace(get_next=lambda: feed)
+        with tf.variable_scope("model"):
+            model = S(it, isTraining=True, params=p)
+        key = "avg" if avg else "sum"
+        for task in tasks:
+            out["%s/loss/%s" % (key, task)] = np.asarray(model.losses[task])
+            out["%s/logits/%s" % (key, task)] = np.asarray(model.outputs[task])
+        out["%s/total_loss" % key] = np.asarray(model.total_loss)
+        expect = {k for k in w if not k.startswith("model/ctc_")}         # (the CTC heads are not the reference's)
+        assert set(tf._graph.used) == expect, sorted(expect ^ set(tf._graph.used))
+    np.savez(os.path.join(HERE, "graph_multitask.npz"), **out)
     return out
 
 
@@ -145,6 +194,8 @@ def run_case(case):
 if __name__ == "__main__":
     o = run_decoder_modes()
     print("modes", {k: v.shape for k, v in o.items()})
+    o = run_multitask()
+    print("multitask", {k: float(v) for k, v in o.items() if "loss" in k})
     for case in CASES:
         o, n = run_case(case)
         print(case, "loss", float(o["loss"]), "logits", o["logits"].shape, "variables consumed", n)

@@ -390,6 +390,28 @@ def make_tf(weights):
         return t(y)
     tf._linear = _linear
 
+    # Training-graph plumbing of Seq2SeqModel.__init__ / create_computational_graph (seq2seq_model.py:74-157): state
+    # variables, summaries, the optimiser and tf.gradients are inert here -- only the forward composition is executed.
+    class _Var(object):
+        def __init__(self, value, trainable=True, **kw):
+            self.value = value
+
+        def assign(self, v):
+            return None
+
+        def __mul__(self, o):
+            return self.value * o
+
+        def __add__(self, o):
+            return self.value + o
+    tf.Variable = _Var
+    tf.summary = types.SimpleNamespace(scalar=lambda *a, **k: None, merge_all=lambda: None)
+    tf.trainable_variables = lambda: []
+    tf.gradients = lambda loss, variables: []
+    tf.clip_by_global_norm = lambda grads, clip: ([], 0.0)
+    tf.train = types.SimpleNamespace(AdamOptimizer=lambda lr: types.SimpleNamespace(
+        apply_gradients=lambda gv, global_step=None: None))
+
     # Randomness of scheduled sampling (attn_decoder.py:131-136, decoder.py:176): TF's generators cannot be reproduced,
     # so a generator may inject draws -- tf._draws = dict(uniform=fn(step) -> scalar, multinomial=fn(step, logits) ->
     # ids); tf.random_uniform([]) is evaluated once per loop step (step = number of calls so far), tf.multinomial uses

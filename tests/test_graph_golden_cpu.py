@@ -75,3 +75,24 @@ def test_scheduled_sampling_equals_the_executed_reference_training_graph():
     teacher = batch["char"].T[:len(cache["toks"])]
     assert (np.stack(cache["toks"]) != teacher).any()
     np.testing.assert_allclose(logits, G["sample/logits"], rtol=0, atol=1e-11)
+
+
+def test_multitask_model_equals_the_executed_reference_seq2seq_graph():
+    """Seq2SeqModel.__init__ + create_computational_graph (seq2seq_model.py:50-144) executed for char + phone attention
+    decoders on different encoder layers with frame stacking: per-task logits / losses and total_loss (avg on / off)."""
+    G = np.load(os.path.join(os.path.dirname(__file__), "golden", "graph_multitask.npz"))
+    cfg = synth.get_config("tiny_b", V_phone=13)
+    base_F = cfg.F
+    cfg.F = base_F * 2
+    tasks = ("char", "phone")
+    w = synth.make_weights(cfg, tasks=tasks, bias_noise=0.1)
+    cfg.F = base_F
+    batch = synth.make_batch(cfg, tasks=tasks)
+    for avg, key in ((True, "avg"), (False, "sum")):
+        res = om.train_step(w, batch, tasks=tasks, num_layers={"char": cfg.L, "phone": cfg.L - 1}, ctc_tasks={}, avg=avg,
+                            enc_params={"stack_cons": 2}, want_grads=False)
+        for task in tasks:
+            np.testing.assert_allclose(res["logits"][task], G["%s/logits/%s" % (key, task)], rtol=0, atol=1e-12)
+            assert abs(res["losses"][task] - float(G["%s/loss/%s" % (key, task)])) < 1e-12
+        assert abs(res["total_loss"] - float(G["%s/total_loss" % key])) < 1e-12
+    assert abs(float(G["sum/total_loss"]) - 2 * float(G["avg/total_loss"])) < 1e-12
