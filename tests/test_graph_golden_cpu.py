@@ -96,3 +96,24 @@ def test_multitask_model_equals_the_executed_reference_seq2seq_graph():
             assert abs(res["losses"][task] - float(G["%s/loss/%s" % (key, task)])) < 1e-12
         assert abs(res["total_loss"] - float(G["%s/total_loss" % key])) < 1e-12
     assert abs(float(G["sum/total_loss"]) - 2 * float(G["avg/total_loss"])) < 1e-12
+
+
+@pytest.mark.parametrize("case", sorted(CASES))
+def test_oracle_backward_equals_autograd_through_the_executed_reference_graph(case):
+    """The oracle's hand-derived backward pass against torch.autograd differentiating the reference's OWN forward code
+    (encoder.py / decoder.py / attn_decoder.py / losses.py executed on the torch-backed TensorFlow stand-in,
+    tests/golden/gen_grad_golden.py) -- what tf.gradients(total_loss, trainable_vars) computes (seq2seq_model.py:148) --
+    for every weight of every cell configuration."""
+    cname, enc_params, dec_params = CASES[case]
+    G = np.load(os.path.join(os.path.dirname(__file__), "golden", "grad_%s.npz" % case))
+    cfg = synth.get_config(cname)
+    w = synth.make_weights(cfg, bias_noise=0.1)
+    batch = synth.make_batch(cfg)
+    res = om.train_step(w, batch, num_layers={"char": cfg.L}, tasks=("char",), ctc_tasks={}, max_gradient_norm=1e9,
+                        enc_params=enc_params or None, dec_params=dec_params)
+    assert abs(res["total_loss"] - float(G["loss"])) < 1e-12
+    names = [k[len("grad/"):] for k in G.files if k.startswith("grad/")]
+    assert sorted(names) == sorted(res["grads"])
+    gmax = max(float(np.abs(G["grad/" + k]).max()) for k in names)
+    for k in names:
+        np.testing.assert_allclose(res["grads"][k], G["grad/" + k], rtol=0, atol=1e-11 * max(1.0, gmax), err_msg=k)
