@@ -151,6 +151,34 @@ def run_multitask():
     return out
 
 
+ENC_OPTS = {"res2": dict(initial_res_fac=2), "noskip": dict(skip_step=1),
+            "res3_down2": dict(initial_res_fac=3, max_scaling_down=2), "down4": dict(max_scaling_down=4)}
+
+
+def run_encoder_options():
+    """graph_encopts.npz: Encoder.__call__ with the input-stride / pyramid options (encoder.py:149-153,170-176):
+    initial_res_fac, skip_step = 1, max_scaling_down; states and lengths at every depth."""
+    out = {}
+    for name, opts in ENC_OPTS.items():
+        cfg = synth.get_config("tiny_b", ctc={}, **opts)
+        w = synth.make_weights(cfg, bias_noise=0.1)
+        batch = synth.make_batch(cfg)
+        tf = np_tf.make_tf(w)
+        mods = load_reference(tf)
+        ep = mods["encoder"].Encoder.class_params()
+        ep.hidden_size, ep.use_lstm, ep.out_prob = cfg.H, True, 1.0
+        ep.update(opts)
+        with tf.variable_scope("model"):
+            enc = mods["encoder"].Encoder(params=ep, isTraining=True)
+            att, _, lens = enc(np_tf.t(batch["logmel"].astype(np.float64)), np_tf.t(batch["logmel_len"]),
+                               {"t%d" % d: d for d in range(1, cfg.L + 1)})
+        for d in att:
+            out["%s/states/%d" % (name, d)] = np.asarray(att[d])
+            out["%s/lens/%d" % (name, d)] = np.asarray(lens[d])
+    np.savez(os.path.join(HERE, "graph_encopts.npz"), **out)
+    return out
+
+
 def run_case(case):
     cname, enc_over, dec_over = CASES[case]
     cfg = synth.get_config(cname)
@@ -194,6 +222,8 @@ def run_case(case):
 if __name__ == "__main__":
     o = run_decoder_modes()
     print("modes", {k: v.shape for k, v in o.items()})
+    o = run_encoder_options()
+    print("encoder options", sorted({k.split("/")[0] for k in o}), len(o), "arrays")
     o = run_multitask()
     print("multitask", {k: float(v) for k, v in o.items() if "loss" in k})
     for case in CASES:

@@ -117,3 +117,20 @@ def test_oracle_backward_equals_autograd_through_the_executed_reference_graph(ca
     gmax = max(float(np.abs(G["grad/" + k]).max()) for k in names)
     for k in names:
         np.testing.assert_allclose(res["grads"][k], G["grad/" + k], rtol=0, atol=1e-11 * max(1.0, gmax), err_msg=k)
+
+
+def test_encoder_options_equal_the_executed_reference_encoder():
+    """initial_res_fac (input stride + ceil lengths), skip_step = 1 (no pyramid), max_scaling_down (where the pyramid
+    stops): encoder.py:149-153,170-176 executed; states and lengths at every depth."""
+    G = np.load(os.path.join(os.path.dirname(__file__), "golden", "graph_encopts.npz"))
+    opts = {"res2": dict(initial_res_fac=2), "noskip": dict(skip_step=1),
+            "res3_down2": dict(initial_res_fac=3, max_scaling_down=2), "down4": dict(max_scaling_down=4)}
+    for name, o in opts.items():
+        cfg = synth.get_config("tiny_b", ctc={}, **o)
+        w = {k: v.astype(np.float64) for k, v in synth.make_weights(cfg, bias_noise=0.1).items()}
+        batch = synth.make_batch(cfg)
+        depths = {"t%d" % d: d for d in range(1, cfg.L + 1)}
+        states, lens, _ = om.encoder_fwd(w, batch["logmel"].astype(np.float64), batch["logmel_len"], depths, o)
+        for d in range(1, cfg.L + 1):
+            np.testing.assert_allclose(states[d], G["%s/states/%d" % (name, d)], rtol=0, atol=1e-13, err_msg="%s %d" % (name, d))
+            assert np.array_equal(lens[d], G["%s/lens/%d" % (name, d)]), (name, d)
