@@ -151,6 +151,61 @@ def run_multitask():
     return out
 
 
+def run_dropout():
+    """graph_dropout.npz: the reference graph in training mode with out_prob = 0.8 and out_prob_dec = 0.7
+    (DropoutWrapper on every encoder cell, on lm_cell and on the decoder cell: encoder.py:49-52, decoder.py:60-63), the
+    oracle's Philox keep-masks injected at the positions the oracle uses: encoder layer l -> mask [B, Tp, 2H] of
+    stream l (fw | bw halves, the bw cell sees reversed time); lm_cell -> mask [U, B, Hl] of stream 100 + task.  The
+    DECODER cell's output is multiplied by ZERO: the reference never reads it (raw_loop_function takes the cell state,
+    attn_decoder.py:114-118), so the result must not change -- which is why the oracle applies no mask there."""
+    from oracle import model as om
+    cfg = synth.get_config("tiny_b")
+    w = synth.make_weights(cfg, bias_noise=0.1)
+    batch = synth.make_batch(cfg)
+    keep_e, keep_d, seed = 0.8, 0.7, 31
+    tf = np_tf.make_tf(w)
+    mods = load_reference(tf)
+    B, T = batch["logmel"].shape[:2]
+    Tp = om.padded_len(T, {"char": cfg.L})
+    U = int(batch["char_len"].max())
+
+    def inject(wr, out):
+        scope = wr.cell._scope.name
+        if "/encoder/" in scope:
+            layer = int(scope.split("RNNLayer")[1].split("/")[0])
+            tp_l = Tp >> (layer - 1)
+            C = 2 * cfg.H
+            mk = om.dropout_mask(B * tp_l * C, keep_e, seed, layer).reshape(B, tp_l, C)
+            half = slice(cfg.H, 2 * cfg.H) if "/bw/" in scope else slice(0, cfg.H)
+            step, lens = wr.ctx["step"], wr.ctx["lens"]
+            tt = np.where(step < lens, lens - 1 - step, 0) if wr.ctx["reverse"] else np.full(B, step)
+            return mk[np.arange(B), tt][:, half]
+        if scope.endswith("rnn/basic_lstm_cell"):                       # lm_cell: one call per decoder step
+            mk = om.dropout_mask(U * B * cfg.Hl, keep_d, seed, 100).reshape(U, B, cfg.Hl)
+            return mk[min(wr.calls, U - 1)]
+        assert scope.endswith("rnn/basic_lstm_cell_1")                  # the decoder cell: its output is never read
+        return np.zeros_like(out)
+    tf._dropout = inject
+    ep = mods["encoder"].Encoder.class_params()
+    ep.hidden_size, ep.use_lstm, ep.out_prob = cfg.H, True, keep_e
+    dp = mods["attn_decoder"].AttnDecoder.class_params()
+    dp.hidden_size_dec, dp.emb_size, dp.vocab_size = cfg.Hd, cfg.E, cfg.V
+    dp.attention_vec_size, dp.lm_hidden_size, dp.max_output = cfg.A, cfg.Hl, cfg.U
+    dp.out_prob_dec, dp.samp_prob = keep_d, 0.0
+    with tf.variable_scope("model"):
+        enc = mods["encoder"].Encoder(params=ep, isTraining=True)
+        att, _, lens = enc(np_tf.t(batch["logmel"].astype(np.float64)), np_tf.t(batch["logmel_len"]), {"char": cfg.L})
+        dec = mods["attn_decoder"].AttnDecoder(isTraining=True, params=dp, scope="char")
+        dec_inp, seq_len = np_tf.t(np.ascontiguousarray(batch["char"].T)), np_tf.t(batch["char_len"])
+        logits = dec(dec_inp, seq_len, att[cfg.L], lens[cfg.L])
+        targets, _ = mods["tf_utils"].create_shifted_targets(dec_inp, seq_len)
+        loss = mods["losses"].LossUtils.cross_entropy_loss(logits, targets, seq_len)
+    out = {"states": np.asarray(att[cfg.L]), "logits": np.asarray(logits), "loss": np.asarray(loss),
+           "seed": np.array(seed), "keep": np.array([keep_e, keep_d])}
+    np.savez(os.path.join(HERE, "graph_dropout.npz"), **out)
+    return out
+
+
 ENC_OPTS = {"res2": dict(initial_res_fac=2), "noskip": dict(skip_step=1),
             "res3_down2": dict(initial_res_fac=3, max_scaling_down=2), "down4": dict(max_scaling_down=4)}
 
@@ -222,6 +277,8 @@ def run_case(case):
 if __name__ == "__main__":
     o = run_decoder_modes()
     print("modes", {k: v.shape for k, v in o.items()})
+    o = run_dropout()
+    print("dropout", "loss", float(o["loss"]))
     o = run_encoder_options()
     print("encoder options", sorted({k.split("/")[0] for k in o}), len(o), "arrays")
     o = run_multitask()

@@ -186,17 +186,25 @@ class GRUCell(_Cell):
 
 
 class DropoutWrapper(object):
-    """output_keep_prob == 1.0 (a Python float) disables dropout, as in TF; other values are not executable here."""
+    """tf.nn.rnn_cell.DropoutWrapper(cell, output_keep_prob=p): the cell's OUTPUT is multiplied by a fresh keep-mask / p
+    at every call, the state passes through untouched; p == 1.0 (a Python float) disables it, as in TF.  TF's random
+    masks cannot be reproduced, so with p < 1 the generator injects them: hook(wrapper, output) -> mask (already
+    scaled by 1/p).  `calls` counts this wrapper's invocations; `ctx` is set by dynamic_rnn before each call (step,
+    reverse, lens); `cell._scope.name` is the wrapped cell's variable scope once it has been called."""
 
-    def __init__(self, cell, output_keep_prob=1.0, **kw):
-        assert float(output_keep_prob) == 1.0, "the generators run the reference with dropout off"
-        self.cell = cell
+    def __init__(self, cell, output_keep_prob=1.0, hook=None, **kw):
+        self.cell, self.keep, self.hook, self.calls, self.ctx = cell, float(output_keep_prob), hook, 0, None
 
     def zero_state(self, *a, **k):
         return self.cell.zero_state(*a, **k)
 
     def __call__(self, x, state):
-        return self.cell(x, state)
+        out, new_state = self.cell(x, state)
+        if self.keep < 1.0:
+            assert self.hook is not None, "dropout masks must be injected (tf._dropout)"
+            out = t(out * self.hook(self, out))
+        self.calls += 1
+        return out, new_state
 
 
 class MultiRNNCell(_Cell):
@@ -312,7 +320,9 @@ def make_tf(weights):
     nn.rnn_cell = rc
     rc.BasicLSTMCell = lambda n, **k: BasicLSTMCell(g, n, **k)
     rc.GRUCell = lambda n, **k: GRUCell(g, n)
-    rc.DropoutWrapper = DropoutWrapper
+    tf._dropout = None
+    rc.DropoutWrapper = lambda cell, output_keep_prob=1.0, **k: DropoutWrapper(
+        cell, output_keep_prob, hook=lambda wr, out: tf._dropout(wr, out))
     rc.MultiRNNCell = lambda cells, **k: MultiRNNCell(g, cells)
     rc.LSTMStateTuple = LSTMStateTuple
 
@@ -330,6 +340,8 @@ def make_tf(weights):
             state = cell.zero_state(B, dtype)
             outs = []
             for step in range(Tn):
+                if isinstance(cell, DropoutWrapper):
+                    cell.ctx = dict(step=step, reverse=reverse, lens=lens)
                 out, new_state = cell(t(x[step]), state)
                 live = (step < lens)[:, None]
                 outs.append(np.where(live, out, 0.0))                               # zero output past the length

@@ -200,7 +200,7 @@ def make_tf(weights):
     nn.rnn_cell = rc
     rc.BasicLSTMCell = lambda n, **k: BasicLSTMCell(g, n, **k)
     rc.GRUCell = lambda n, **k: GRUCell(g, n)
-    rc.DropoutWrapper = np_tf.DropoutWrapper
+    rc.DropoutWrapper = lambda cell, output_keep_prob=1.0, **k: np_tf.DropoutWrapper(cell, output_keep_prob)
     rc.MultiRNNCell = lambda cells, **k: MultiRNNCell(g, cells)
     rc.LSTMStateTuple = LSTMStateTuple
 

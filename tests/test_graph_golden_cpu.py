@@ -134,3 +134,21 @@ def test_encoder_options_equal_the_executed_reference_encoder():
         for d in range(1, cfg.L + 1):
             np.testing.assert_allclose(states[d], G["%s/states/%d" % (name, d)], rtol=0, atol=1e-13, err_msg="%s %d" % (name, d))
             assert np.array_equal(lens[d], G["%s/lens/%d" % (name, d)]), (name, d)
+
+
+def test_dropout_placement_equals_the_executed_reference_training_graph():
+    """out_prob = 0.8 / out_prob_dec = 0.7 (the reference trains with 0.9): its own get_cell / DropoutWrapper wiring
+    executed with the oracle's Philox keep-masks injected on the encoder cells' and lm_cell's outputs and ZEROS on the
+    decoder cell's output -- the reference never reads that output (attn_decoder.py:114-118 takes the cell state), so
+    the oracle, which applies no mask there, must still reproduce states, logits and loss."""
+    G = np.load(os.path.join(os.path.dirname(__file__), "golden", "graph_dropout.npz"))
+    cfg = synth.get_config("tiny_b")
+    w = synth.make_weights(cfg, bias_noise=0.1)
+    batch = synth.make_batch(cfg)
+    res = om.train_step(w, batch, num_layers={"char": cfg.L}, ctc_tasks={}, want_grads=False,
+                        out_prob=float(G["keep"][0]), out_prob_dec=float(G["keep"][1]), dropout_seed=int(G["seed"]))
+    np.testing.assert_allclose(res["states"][cfg.L], G["states"], rtol=0, atol=1e-13)
+    np.testing.assert_allclose(res["logits"]["char"], G["logits"], rtol=0, atol=1e-12)
+    assert abs(res["losses"]["char"] - float(G["loss"])) < 1e-12
+    plain = om.train_step(w, batch, num_layers={"char": cfg.L}, ctc_tasks={}, want_grads=False)
+    assert abs(plain["losses"]["char"] - float(G["loss"])) > 1e-4            # the masks really acted
