@@ -206,6 +206,51 @@ def run_dropout():
     return out
 
 
+def run_dropout_stacked():
+    """graph_dropout_dec2.npz: a 2-layer LSTM decoder (MultiRNNCell of DropoutWrapper-ed cells, decoder.py:53-68) with
+    out_prob_dec = 0.7: the oracle's masks injected on every lm layer's output (stream 100 + task for the top layer,
+    500 + 16 task + l below it) and on the lower decoder layers' outputs (400 + 16 task + l); ZEROS on the top decoder
+    layer's output, which the reference never reads."""
+    from oracle import model as om
+    cfg = synth.get_config("tiny_dec2")
+    w = synth.make_weights(cfg, bias_noise=0.1)
+    batch = synth.make_batch(cfg)
+    keep, seed, L = 0.7, 13, 2
+    tf = np_tf.make_tf(w)
+    mods = load_reference(tf)
+    B = batch["logmel"].shape[0]
+    U = int(batch["char_len"].max())
+
+    def inject(wr, out):
+        scope = wr.cell._scope.name
+        layer = int(scope.split("/cell_")[1].split("/")[0])
+        if "/multi_rnn_cell/" in scope:                                  # lm_cell stack
+            stream = 100 if layer == L - 1 else 500 + layer
+            return om.dropout_mask(U * B * cfg.Hl, keep, seed, stream).reshape(U, B, cfg.Hl)[min(wr.calls, U - 1)]
+        assert "/multi_rnn_cell_1/" in scope                             # decoder cell stack
+        if layer == L - 1:
+            return np.zeros_like(out)
+        return om.dropout_mask(U * B * cfg.Hd, keep, seed, 400 + layer).reshape(U, B, cfg.Hd)[min(wr.calls, U - 1)]
+    tf._dropout = inject
+    ep = mods["encoder"].Encoder.class_params()
+    ep.hidden_size, ep.use_lstm, ep.out_prob = cfg.H, True, 1.0
+    dp = mods["attn_decoder"].AttnDecoder.class_params()
+    dp.hidden_size_dec, dp.emb_size, dp.vocab_size = cfg.Hd, cfg.E, cfg.V
+    dp.attention_vec_size, dp.lm_hidden_size, dp.max_output = cfg.A, cfg.Hl, cfg.U
+    dp.out_prob_dec, dp.samp_prob, dp.num_layers_dec = keep, 0.0, L
+    with tf.variable_scope("model"):
+        enc = mods["encoder"].Encoder(params=ep, isTraining=True)
+        att, _, lens = enc(np_tf.t(batch["logmel"].astype(np.float64)), np_tf.t(batch["logmel_len"]), {"char": cfg.L})
+        dec = mods["attn_decoder"].AttnDecoder(isTraining=True, params=dp, scope="char")
+        dec_inp, seq_len = np_tf.t(np.ascontiguousarray(batch["char"].T)), np_tf.t(batch["char_len"])
+        logits = dec(dec_inp, seq_len, att[cfg.L], lens[cfg.L])
+        targets, _ = mods["tf_utils"].create_shifted_targets(dec_inp, seq_len)
+        loss = mods["losses"].LossUtils.cross_entropy_loss(logits, targets, seq_len)
+    out = {"logits": np.asarray(logits), "loss": np.asarray(loss), "seed": np.array(seed), "keep": np.array(keep)}
+    np.savez(os.path.join(HERE, "graph_dropout_dec2.npz"), **out)
+    return out
+
+
 ENC_OPTS = {"res2": dict(initial_res_fac=2), "noskip": dict(skip_step=1),
             "res3_down2": dict(initial_res_fac=3, max_scaling_down=2), "down4": dict(max_scaling_down=4)}
 
@@ -279,6 +324,8 @@ if __name__ == "__main__":
     print("modes", {k: v.shape for k, v in o.items()})
     o = run_dropout()
     print("dropout", "loss", float(o["loss"]))
+    o = run_dropout_stacked()
+    print("dropout, 2-layer decoder", "loss", float(o["loss"]))
     o = run_encoder_options()
     print("encoder options", sorted({k.split("/")[0] for k in o}), len(o), "arrays")
     o = run_multitask()

@@ -152,3 +152,17 @@ def test_dropout_placement_equals_the_executed_reference_training_graph():
     assert abs(res["losses"]["char"] - float(G["loss"])) < 1e-12
     plain = om.train_step(w, batch, num_layers={"char": cfg.L}, ctc_tasks={}, want_grads=False)
     assert abs(plain["losses"]["char"] - float(G["loss"])) > 1e-4            # the masks really acted
+
+
+def test_stacked_decoder_dropout_equals_the_executed_reference_training_graph():
+    """2-layer LSTM decoder with out_prob_dec = 0.7: every single cell of lm_cell and of the decoder cell is wrapped
+    (decoder.py:53-68); masks injected per layer, zeros on the top decoder layer's never-read output."""
+    G = np.load(os.path.join(os.path.dirname(__file__), "golden", "graph_dropout_dec2.npz"))
+    cfg = synth.get_config("tiny_dec2")
+    w = synth.make_weights(cfg, bias_noise=0.1)
+    batch = synth.make_batch(cfg)
+    res = om.train_step(w, batch, num_layers={"char": cfg.L}, ctc_tasks={}, want_grads=False,
+                        out_prob_dec=float(G["keep"]), dropout_seed=int(G["seed"]),
+                        dec_params={"num_layers_dec": 2, "use_lstm": True})
+    np.testing.assert_allclose(res["logits"]["char"], G["logits"], rtol=0, atol=1e-12)
+    assert abs(res["losses"]["char"] - float(G["loss"])) < 1e-12
