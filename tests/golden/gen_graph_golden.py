@@ -251,6 +251,35 @@ def run_dropout_stacked():
     return out
 
 
+def run_cfg1():
+    """graph_cfg1.npz: the reference graph at its default widths (cfg-1: B=4, T=200, F=40, H=Hd=Hl=256, A=128, V=1000,
+    4 pyramid layers) -- loss, and every 97th logit / 89th top-layer state value (the full tensors would be megabytes)."""
+    cfg = synth.get_config("cfg1")
+    w = synth.make_weights(cfg, bias_noise=0.1)
+    batch = synth.make_batch(cfg)
+    tf = np_tf.make_tf(w)
+    mods = load_reference(tf)
+    ep = mods["encoder"].Encoder.class_params()
+    ep.hidden_size, ep.use_lstm, ep.out_prob = cfg.H, True, 1.0
+    dp = mods["attn_decoder"].AttnDecoder.class_params()
+    dp.hidden_size_dec, dp.emb_size, dp.vocab_size = cfg.Hd, cfg.E, cfg.V
+    dp.attention_vec_size, dp.lm_hidden_size, dp.max_output = cfg.A, cfg.Hl, cfg.U
+    dp.out_prob_dec, dp.samp_prob = 1.0, 0.0
+    with tf.variable_scope("model"):
+        enc = mods["encoder"].Encoder(params=ep, isTraining=True)
+        att, _, lens = enc(np_tf.t(batch["logmel"].astype(np.float64)), np_tf.t(batch["logmel_len"]), {"char": cfg.L})
+        dec = mods["attn_decoder"].AttnDecoder(isTraining=True, params=dp, scope="char")
+        dec_inp, seq_len = np_tf.t(np.ascontiguousarray(batch["char"].T)), np_tf.t(batch["char_len"])
+        logits = dec(dec_inp, seq_len, att[cfg.L], lens[cfg.L])
+        targets, _ = mods["tf_utils"].create_shifted_targets(dec_inp, seq_len)
+        loss = mods["losses"].LossUtils.cross_entropy_loss(logits, targets, seq_len)
+    out = {"loss": np.asarray(loss), "logits_shape": np.array(logits.shape),
+           "logits_sub": np.asarray(logits).reshape(-1)[::97].copy(),
+           "states_sub": np.asarray(att[cfg.L]).reshape(-1)[::89].copy(), "lens": np.asarray(lens[cfg.L])}
+    np.savez(os.path.join(HERE, "graph_cfg1.npz"), **out)
+    return out
+
+
 ENC_OPTS = {"res2": dict(initial_res_fac=2), "noskip": dict(skip_step=1),
             "res3_down2": dict(initial_res_fac=3, max_scaling_down=2), "down4": dict(max_scaling_down=4)}
 
@@ -322,6 +351,8 @@ def run_case(case):
 if __name__ == "__main__":
     o = run_decoder_modes()
     print("modes", {k: v.shape for k, v in o.items()})
+    o = run_cfg1()
+    print("cfg1", "loss", float(o["loss"]), o["logits_shape"])
     o = run_dropout()
     print("dropout", "loss", float(o["loss"]))
     o = run_dropout_stacked()

@@ -166,3 +166,18 @@ def test_stacked_decoder_dropout_equals_the_executed_reference_training_graph():
                         dec_params={"num_layers_dec": 2, "use_lstm": True})
     np.testing.assert_allclose(res["logits"]["char"], G["logits"], rtol=0, atol=1e-12)
     assert abs(res["losses"]["char"] - float(G["loss"])) < 1e-12
+
+
+def test_reference_default_widths_equal_the_executed_reference_graph():
+    """cfg-1 (the reference's base_params defaults: H = Hd = Hl = 256, A = 128, V = 1000, 4 pyramid layers): loss and
+    sub-sampled logits / top-layer states of the executed reference graph."""
+    G = np.load(os.path.join(os.path.dirname(__file__), "golden", "graph_cfg1.npz"))
+    cfg = synth.get_config("cfg1")
+    w = synth.make_weights(cfg, bias_noise=0.1)
+    batch = synth.make_batch(cfg)
+    res = om.train_step(w, batch, num_layers={"char": cfg.L}, ctc_tasks={}, want_grads=False)
+    assert tuple(res["logits"]["char"].shape) == tuple(G["logits_shape"])
+    np.testing.assert_allclose(res["logits"]["char"].reshape(-1)[::97], G["logits_sub"], rtol=0, atol=1e-11)
+    np.testing.assert_allclose(res["states"][cfg.L].reshape(-1)[::89], G["states_sub"], rtol=0, atol=1e-12)
+    assert np.array_equal(res["lens"][cfg.L], G["lens"])
+    assert abs(res["losses"]["char"] - float(G["loss"])) < 1e-11
