@@ -75,6 +75,12 @@ def main():
                 sigs[meth] = [[n, None if prm.default is inspect.Parameter.empty else repr(prm.default)]
                               for n, prm in inspect.signature(f).parameters.items()]
         entry["signatures"] = sigs
+        if hasattr(C, "get_updated_params") and hasattr(C, "class_params"):
+            # base_params.py:21-28: an option overrides a default only when it has exactly the default's Python type
+            opts = {"hidden_size": 128, "out_prob": 1, "use_lstm": True, "hidden_size_dec": 64.0, "samp_prob": 0.25,
+                    "beam_size": 7, "lm_weight": 1, "avg": False, "learning_rate": 3, "bogus": 5, "emb_size": 32}
+            entry["updated"] = plain(dict(C.get_updated_params(opts)))
+            entry["update_options"] = opts
         if hasattr(C, "add_parse_options"):
             p = argparse.ArgumentParser()
             C.add_parse_options(p)

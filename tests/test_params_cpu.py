@@ -69,3 +69,14 @@ def test_argparse_flags_equal_the_reference(cls):
         else:
             assert a.default == spec["default"], (cls, dest, a.default, spec["default"])
         assert getattr(a.type, "__name__", None) == spec["type"], (cls, dest)
+
+
+@pytest.mark.parametrize("cls", sorted(c for c in GOLD if "updated" in GOLD[c]))
+def test_get_updated_params_type_rule_equals_the_reference(cls):
+    """BaseParams.get_updated_params (base_params.py:21-28): an option replaces a default only if it has exactly the
+    default's Python type (an int offered for a float default is ignored), unknown options are dropped."""
+    ours = plain(dict(getattr(pkg, cls).get_updated_params(GOLD[cls]["update_options"])))
+    ref = GOLD[cls]["updated"]
+    for k, v in ref.items():
+        assert ours[k] == v and type(ours[k]) is type(v), (cls, k, ours[k], v)
+    assert "bogus" not in ours
