@@ -90,8 +90,10 @@ class ClockSampler(object):
 
 
 def cpu_reference_step(cfg_name, sample_B, steps, warmup, threads=None):
-    """Times the CPU restatement (oracle/) on a bounded sample: the first sample_B
-    utterances' worth of the workload (same T/F/H/U, batch reduced)."""
+    """Times the CPU restatement (oracle/) on `sample_B` utterances of the workload (same T/F/H/U; sample_B = the
+    config's batch size is the whole step).  threads = 1 is what the reference itself configures
+    (intra_op_parallelism_threads=1, train.py:178); None = all host cores.  Returns the MEDIAN step."""
+    from threadpoolctl import threadpool_limits
     from e2e_asr_b200 import synth
     from oracle import model as om
     cfg = synth.get_config(cfg_name, B=sample_B)
@@ -100,33 +102,49 @@ def cpu_reference_step(cfg_name, sample_B, steps, warmup, threads=None):
     frames = int(batch["logmel_len"].sum())
     kw = dict(num_layers={"char": cfg.L}, ctc_tasks=cfg.ctc, dtype=np.float32)
     times = []
-    for i in range(warmup + steps):
-        t0 = time.perf_counter()
-        om.train_step(w, batch, **kw)
-        dt = time.perf_counter() - t0
-        if i >= warmup:
-            times.append(dt)
-    sec = float(np.mean(times))
+    with threadpool_limits(limits=threads):
+        for i in range(warmup + steps):
+            t0 = time.perf_counter()
+            om.train_step(w, batch, **kw)
+            dt = time.perf_counter() - t0
+            if i >= warmup:
+                times.append(dt)
+    sec = float(np.median(times))
     return frames / sec, sec, frames, cfg
 
 
 def run_reference(args):
+    """The reference arm: the reference's own CPU implementation of the path on the box's host cores.  TensorFlow-1.x /
+    Python 2 cannot run in this image, so it is the NumPy restatement (oracle/model.py, "port"), float32, on the FULL
+    batch of the workload with all host cores: 2 warm-up steps + the median of 5, bounded by
+    --steps / --warmup from above; plus one single-thread figure (the reference's own train.py:178 setting) on an
+    8-utterance sample so that the whole arm still ends within a few minutes."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     cores = os.cpu_count() or 1
-    sample_B = 8
-    steps, warmup = max(1, min(args.steps, 3)), min(args.warmup, 1)
-    fps, sec, frames, cfg = cpu_reference_step(args.config, sample_B, steps, warmup)
-    sample = ("%s shapes with batch %d of %d utterances (%d valid frames/step), float32 NumPy restatement "
-              "of the reference graph (oracle/model.py), %d step(s) after %d warm-up"
-              % (args.config, sample_B, cfg_B(args.config), frames, steps, warmup))
+    full_B = cfg_B(args.config)
+    steps, warmup = max(1, min(args.steps, 5)), max(0, min(args.warmup, 2))
+    fps, sec, frames, cfg = cpu_reference_step(args.config, full_B, steps, warmup)
+    sample = ("%s at FULL batch %d (%d valid frames/step), float32 NumPy restatement of the reference graph "
+              "(oracle/model.py; restated reference, not TF), all %d host cores, median of %d step(s) after %d warm-up, "
+              "%.1f s/step" % (args.config, full_B, frames, cores, steps, warmup, sec))
+    one = None
+    try:
+        sB = min(8, full_B)
+        f1, s1, fr1, _ = cpu_reference_step(args.config, sB, 1, 0, threads=1)
+        one = {"value": f1, "unit": UNIT, "cores": 1, "kind": "port",
+               "sample": "%d of %d utterances (%d valid frames), ONE thread (the reference's own "
+                         "intra_op_parallelism_threads=1, train.py:178), 1 step, %.1f s" % (sB, full_B, fr1, s1)}
+    except Exception as e:          # noqa: BLE001
+        one = {"error": repr(e)}
     line = {
         "impl": "reference", "metric": METRIC, "value": fps, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
-        "warmup": warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak",
+        "warmup": warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": args.scaling,
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": workload_config(args.config, 1, note="CPU arm runs a bounded sample"),
-        "cpu_baseline": {"value": fps, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "config": workload_config(args.config, 1, note="CPU arm: the same full batch on the host cores"),
+        "cpu_baseline": {"value": fps, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample,
+                         "single_thread": one},
         "e2e": {"value": fps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -138,18 +156,202 @@ def cfg_B(name):
     return synth.CONFIGS[name]["B"]
 
 
-def workload_config(name, n_gpus, note=None):
+WORKLOADS = {"cfg1": "BASELINE.json configs[0] (cfg1): base_params defaults, batch 4 x ~200 frames",
+             "cfg2": "BASELINE.json configs[1] (cfg2): Switchboard-300h-shaped teacher-forced fwd+bwd+clip",
+             "cfg4": "BASELINE.json configs[3] (cfg4): long-utterance stress, batch 32 x 2000 frames",
+             "cfg5": "BASELINE.json configs[4] (cfg5): wide encoder, 5-layer BiLSTM 512/dir, batch 256"}
+
+
+def workload_config(name, n_gpus, note=None, batch_per_gpu=None, settings=None):
     from e2e_asr_b200 import synth
     c = synth.CONFIGS[name]
-    d = {"workload": "BASELINE.json configs[1] (%s): Switchboard-300h-shaped teacher-forced fwd+bwd+clip" % name,
-         "batch_per_gpu": c["B"], "global_batch": c["B"] * n_gpus, "frames_T": c["T"], "feat_F": c["F"],
+    bpg = c["B"] if batch_per_gpu is None else batch_per_gpu
+    d = {"workload": WORKLOADS.get(name, name),
+         "batch_per_gpu": bpg, "global_batch": bpg * n_gpus, "frames_T": c["T"], "feat_F": c["F"],
          "hidden_per_dir": c["H"], "enc_layers": c["L"], "vocab": c["V"], "target_len_U": c["U"],
          "aux_ctc": {k: {"depth": v[0], "vocab": v[1]} for k, v in c["ctc"].items()},
          "parallelism": "dp%d" % n_gpus, "dropout": "off (out_prob=1)", "samp_prob": 0.0,
          "l2": "activations per step (~2 GB) exceed the 126 MB L2; no explicit flush"}
+    if settings:
+        d.update(settings)
     if note:
         d["note"] = note
     return d
+
+
+
+# Latency floors of the sequential kernels, in SM cycles per timestep, from the micro-benchmarks behind DESIGN.md 4.1 /
+# 4.2 (scratch/ubench.cu and in-kernel clock64 stamps):
+#   recurrence, two interleaved slices per cluster (NS = 2, the encoder layers at B = 64): the MMA warps must issue
+#     2 x 1024 cycles of mma.sync per timestep (64 MMAs per warp and slice at 8 cycles/SMSP, 2 warps per SMSP); the
+#     h_t exchange (L2 tile + one multicast: 910 cycles; backward: bulk DSMEM reduce-scatter, 1416) hides behind the
+#     other slice -> max(2048, 1416) = 2048
+#   recurrence, one slice per cluster (NS = 1, the LM-LSTM): k-loop 1024 + exchange 910 back to back = 1934
+#   decoder loop: three grid-wide barriers per step, 2600 cycles each (128 co-resident CTAs, one L2 atomic + poll)
+FLOOR_CYCLES = {"enc_rec_fwd": 2048, "enc_rec_bwd": 2048, "lm_rec_fwd": 1934, "lm_rec_bwd": 1934,
+                "e2e_decoder_persist_fwd": 7800, "e2e_decoder_persist_bwd": 7800}
+KERNEL_OF = {"enc_rec_fwd": "rec_fwd_ws_kernel<16,2,8>", "enc_rec_bwd": "rec_bwd_ws_kernel<16,2,8>",
+             "lm_rec_fwd": "rec_fwd_ws_kernel<16,1,4>", "lm_rec_bwd": "rec_bwd_ws_kernel<16,1,4>",
+             "e2e_decoder_persist_fwd": "dec_fwd_persist_kernel", "e2e_decoder_persist_bwd": "dec_bwd_persist_kernel"}
+
+
+def load_traffic():
+    """Per-launch DRAM traffic (dram__bytes_read.sum + dram__bytes_write.sum) of the profiled kernels, from the
+    `ncu --set full` captures summarised under profiles/ (never measured inside a bench run)."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
+            return json.load(f)
+    except Exception:
+        return {}
+
+
+def roofline_report(raw, cfg, peaks, K, ms_per_step, clocks, gemm_mode):
+    """Folds the per-call CUDA events of the eager pass into: the per-class breakdown, the `roofline` object of the
+    DOMINANT kernel (largest time on the main stream = the critical path), the latency-floor fractions of the four
+    sequential kernels, the memory-bound kernels' achieved GB/s, and SURVEY.md 8(d)'s end-to-end figure
+    pct_of_roofline = sum_k (algorithmic time of kernel k at its bound) / measured step time."""
+    from e2e_asr_b200 import synth
+    shapes = {k: v for k, v in raw.items() if k.startswith("gemm M=")}
+    summ = {k: v for k, v in raw.items() if k not in shapes}
+    if shapes:
+        summ["e2e_gemm"] = {k2: sum(v[k2] for v in shapes.values()) for k2 in
+                            ("ms", "calls", "work", "main_ms", "main_calls", "main_work")}
+    tot = sum(v["ms"] for v in summ.values())
+    breakdown = {k: {"ms_per_step": v["ms"] / K, "calls_per_step": v["calls"] / K,
+                     "main_stream_ms_per_step": v["main_ms"] / K, "share": v["ms"] / tot if tot else 0.0}
+                 for k, v in sorted(summ.items(), key=lambda kv: -kv[1]["ms"])}
+    sm_mhz = float((clocks or {}).get("sm_mhz") or (clocks or {}).get("sm_max_mhz") or 1965.0)
+    peak_tc = peaks["tc_sustained"]
+    # tensor-pipe cost of one algorithmic product: 3xTF32 = 3 MMAs (SURVEY.md 8d: "divides the peak by its split count")
+    # which moreover run at half the bf16 rate (kind::tf32) -> issue ceiling peak / 6; bf16x2 = 3 bf16 MMAs
+    split = {0: 1, 1: 3, 2: 1, 3: 3}[gemm_mode]
+    units = {0: 1, 1: 6, 2: 1, 3: 3}[gemm_mode]
+    traffic = load_traffic()
+    H, Bn = cfg.H, cfg.B
+    nd = 2 if cfg.get("bi_dir", True) else 1
+
+    # ---- sequential kernels: measured us / timestep against the latency floor, and their tensor-pipe rate
+    flop_per_step = {"enc_rec_fwd": 2.0 * Bn * H * 4 * H * nd, "enc_rec_bwd": 2.0 * Bn * H * 4 * H * nd,
+                     "lm_rec_fwd": 2.0 * Bn * cfg.Hl * 4 * cfg.Hl, "lm_rec_bwd": 2.0 * Bn * cfg.Hl * 4 * cfg.Hl,
+                     # gates [B, D+Hd] x [D+Hd, 4Hd] + query [B, Hd] x [Hd, A]; backward: the two transposed products
+                     "e2e_decoder_persist_fwd": 2.0 * Bn * ((2 * H + cfg.Hd) * 4 * cfg.Hd + cfg.Hd * cfg.A),
+                     "e2e_decoder_persist_bwd": 2.0 * Bn * ((2 * H + cfg.Hd) * 4 * cfg.Hd + cfg.Hd * cfg.A)}
+    seq, floor_ms = {}, 0.0
+    for k, v in summ.items():
+        if not ("rec" in k or k.startswith("e2e_decoder")):
+            continue
+        steps = max(v["work"], 1.0)
+        us = v["ms"] * 1e3 / steps
+        d = {"kernel": KERNEL_OF.get(k, k), "us_per_timestep": us, "timesteps_per_step": steps / K,
+             "ms_per_step": v["ms"] / K, "share_of_step": v["ms"] / K / ms_per_step}
+        if k in FLOOR_CYCLES and (H == 256 or not k.startswith("enc_rec")):
+            fl_us = FLOOR_CYCLES[k] / sm_mhz
+            d.update(floor_cycles=FLOOR_CYCLES[k], floor_us=fl_us, frac_of_latency_floor=fl_us / us)
+            floor_ms += fl_us * steps / K * 1e-3
+        if k in flop_per_step:
+            d["tensor_tflops"] = flop_per_step[k] * steps / (v["ms"] * 1e-3) / 1e12
+            d["frac_of_tensor_peak"] = d["tensor_tflops"] / peak_tc
+        seq[k] = d
+
+    # ---- memory-bound kernels: ALGORITHMIC bytes per call (SURVEY.md 8d) / event time vs the measured HBM peak
+    memory_bound, mem_ms = {}, 0.0
+    D_, T_enc = 2 * H, int(synth.pyramid_lens([cfg.T], synth.depth_reductions(cfg, cfg.L))[0])
+    rows_ce = cfg.U * Bn * cfg.V * 4
+    attn_fwd = cfg.U * 4.0 * Bn * T_enc * (cfg.A + D_)
+    mem_bytes = {"e2e_ce_fwd": rows_ce, "e2e_ce_bwd": 2 * rows_ce,
+                 # attention(): HF [B,T_enc,A] + enc [B,T_enc,D] read once per decoder step; backward re-reads both and
+                 # read-modify-writes dHF / dEnc = 3x (the working set fits the 126 MB L2: L2 -> SM traffic, not HBM)
+                 "e2e_decoder_persist_fwd": attn_fwd, "e2e_decoder_persist_bwd": 3.0 * attn_fwd}
+    ctc_bytes = []
+    for t_, (depth, vocab) in cfg.ctc.items():
+        Td = int(synth.pyramid_lens([cfg.T], synth.depth_reductions(cfg, depth))[0])
+        ctc_bytes.append(2.0 * 4 * Td * Bn * (vocab + 1))           # read the logits, write their gradient
+    if ctc_bytes:
+        mem_bytes["e2e_ctc_fwd_grad"] = sum(ctc_bytes) / len(ctc_bytes)     # per call (one call per head)
+    for k, bytes_per_call in mem_bytes.items():
+        if k in summ and summ[k]["ms"] > 0:
+            gbs = bytes_per_call * summ[k]["calls"] / (summ[k]["ms"] * 1e-3) / 1e9
+            memory_bound[k] = {"algorithmic_mb_per_call": bytes_per_call / 1e6, "achieved_gbs": gbs,
+                               "frac_of_hbm_peak": gbs / peaks["hbm"]}
+            mem_ms += bytes_per_call * summ[k]["calls"] / K / (peaks["hbm"] * 1e9) * 1e3
+    if "e2e_ctc_fwd_grad" in memory_bound:
+        memory_bound["e2e_ctc_fwd_grad"]["note"] = (
+            "three launches per head: emission gather (parallel), alpha/beta sweep (T_l sequential frames, two warps "
+            "per utterance, 4-8 utterances per CTA), occupancy + gradient (parallel); on its own stream")
+    for k in ("e2e_decoder_persist_fwd", "e2e_decoder_persist_bwd"):
+        if k in memory_bound:
+            memory_bound[k]["note"] = "attention operands only; L2-resident; the kernel also runs the gate GEMMs"
+
+    # ---- dense GEMMs (tensor bound)
+    gemm = None
+    gemm_ms_at_bound = 0.0
+    if shapes:
+        tv = summ["e2e_gemm"]
+        gemm_ms_at_bound = tv["work"] / K / (peak_tc / split * 1e12) * 1e3
+        on_main = {k: v for k, v in shapes.items() if v["main_calls"] > 0} or shapes
+        sname, sv = max(on_main.items(), key=lambda kv: kv[1]["main_ms"] if kv[1]["main_calls"] else kv[1]["ms"])
+        if sv["main_calls"]:
+            sv = {"ms": sv["main_ms"], "calls": sv["main_calls"], "work": sv["main_work"]}
+        ach = sv["work"] / (sv["ms"] * 1e-3) / 1e12
+        ach_class = tv["work"] / (tv["ms"] * 1e-3) / 1e12
+        gemm = {"kernel": "gemm_tc_kernel<%d> %s (the GEMM shape with the largest time on the main stream, incl. its "
+                          "operand split passes if any)" % (gemm_mode, sname),
+                "bound": "tensor", "achieved": ach, "peak": peak_tc, "unit": "TFLOP/s", "frac": ach / peak_tc,
+                "frac_of_peak_over_splits": ach / (peak_tc / split), "mma_products_per_flop": split,
+                "issue_ceiling_tflops": peak_tc / units, "frac_of_issue_ceiling": ach / (peak_tc / units),
+                "algorithmic_gflop_per_launch": sv["work"] / sv["calls"] / 1e9, "avg_launch_ms": sv["ms"] / sv["calls"],
+                "launches_per_step": sv["calls"] / K, "main_stream_ms_per_step": tv["main_ms"] / K,
+                "traffic": traffic.get("gemm_tc_kernel"),
+                "class_aggregate": {"kernel": "all e2e_gemm calls (every dense projection incl. dX/dW, %d shapes)"
+                                              % len(shapes),
+                                    "algorithmic_gflop_per_step": tv["work"] / K / 1e9, "achieved": ach_class,
+                                    "frac": ach_class / peak_tc, "frac_of_peak_over_splits": ach_class / (peak_tc / split),
+                                    "avg_launch_ms": tv["ms"] / tv["calls"]},
+                "top_shapes": [{"shape": k, "ms_per_step": v["ms"] / K, "on_main_stream": v["main_calls"] > 0,
+                                "tflops": v["work"] / (v["ms"] * 1e-3) / 1e12}
+                               for k, v in sorted(shapes.items(), key=lambda kv: -kv[1]["ms"])[:6]],
+                "note": "events of GEMMs on the weight-gradient / CTC side streams overlap the main stream and wait "
+                        "for SMs held by the persistent kernels: the class total exceeds its share of the step"}
+
+    # ---- the dominant kernel: the kernel with the largest time ON THE MAIN STREAM (a GEMM shape counts as one kernel)
+    cand = {k: v["main_ms"] for k, v in summ.items() if k != "e2e_gemm"}
+    for k, v in shapes.items():
+        cand[k] = v["main_ms"]
+    name = max(cand, key=cand.get) if cand else None
+    if name in seq and name in flop_per_step:
+        v, d = summ[name], seq[name]
+        launches = max(v["calls"], 1)
+        roof = {"kernel": "%s (entry point %s; the kernel with the largest time on the main stream: %.2f ms = %.0f %% "
+                          "of the step in %d launches)" % (d["kernel"], name, v["main_ms"] / K, 100 * d["share_of_step"],
+                                                            launches // K),
+                "bound": "tensor", "achieved": d["tensor_tflops"], "peak": peak_tc, "unit": "TFLOP/s",
+                "frac": d["frac_of_tensor_peak"], "traffic": traffic.get(d["kernel"].split("<")[0]),
+                "peak_source": peaks["source"] + ", sustained bf16 (the kernel sits inside a long step)",
+                "algorithmic_gflop_per_launch": flop_per_step[name] * v["work"] / launches / 1e9,
+                "avg_launch_ms": v["ms"] / launches, "launches_per_step": launches / K,
+                "us_per_timestep": d["us_per_timestep"],
+                "latency_floor": {"cycles_per_timestep": d.get("floor_cycles"), "us_per_timestep": d.get("floor_us"),
+                                  "frac": d.get("frac_of_latency_floor"), "sm_mhz": sm_mhz,
+                                  "source": "scratch/ubench.cu + in-kernel clock64 stamps (DESIGN.md 4.1/4.2)"},
+                "note": "a sequential kernel: T_l dependent timesteps of a [B x H] . [H x 4H] product per direction, M = "
+                        "16-row tiles on mma.sync; its ALGORITHMIC tensor rate is far below the tensor peak by "
+                        "construction, so the fraction that says how good the kernel is is latency_floor.frac = "
+                        "(timesteps x floor) / measured"}
+    elif gemm is not None and name in shapes:
+        roof = dict(gemm)
+        roof["peak_source"] = peaks["source"] + ", sustained bf16"
+    else:
+        roof = {"kernel": name, "bound": "hbm", "achieved": memory_bound.get(name, {}).get("achieved_gbs"),
+                "peak": peaks["hbm"], "unit": "GB/s", "frac": memory_bound.get(name, {}).get("frac_of_hbm_peak"),
+                "traffic": traffic.get(name), "peak_source": peaks["source"]}
+
+    at_bound = {"dense_gemms_ms": gemm_ms_at_bound, "sequential_floors_ms": floor_ms, "memory_bound_ms": mem_ms}
+    pct = {"value": sum(at_bound.values()) / ms_per_step, "terms_ms": at_bound, "step_ms": ms_per_step,
+           "definition": "SURVEY.md 8(d): sum over kernels of the algorithmic time at the kernel's bound / measured step: "
+                         "GEMM FLOPs at peak/%d (mode %s), sequential timesteps x latency floor, attention / CE / CTC "
+                         "bytes at the HBM peak" % (split, {0: "fp32", 1: "tf32x3", 2: "bf16", 3: "bf16x2"}[gemm_mode])}
+    return {"roofline": roof, "breakdown": breakdown, "sequential_kernels": seq, "memory_bound_kernels": memory_bound,
+            "gemm": gemm, "pct_of_roofline": pct}
 
 
 def main():
@@ -158,7 +360,9 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200")
-    ap.add_argument("--config", default="cfg2")
+    ap.add_argument("--config", default="cfg2", help="cfg2 (default, BASELINE configs[1]) | cfg4 | cfg5 | cfg1")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="weak: the config's batch PER GPU (default); strong: the config's batch split over the GPUs")
     ap.add_argument("--gemm", default="tf32x3", help="fp32 | tf32x3 | bf16x2 | bf16 (default: tf32x3, the fp32-accurate tensor-core mode)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-beam", action="store_true", help="skip the beam-decode utt/s side measurement")
@@ -199,7 +403,14 @@ def main():
 
     cfg = synth.get_config(args.config)
     weights = synth.make_weights(cfg)
-    batch = synth.make_batch(cfg, seed=synth.DATA_SEED + rank)      # weak scaling: every rank its own batch
+    if args.scaling == "strong" and world > 1:
+        # strong scaling: the config's batch is the GLOBAL batch, utterances dealt round-robin to the ranks
+        if cfg.B % world:
+            raise SystemExit("bench.py: --scaling strong needs the batch (%d) divisible by the GPUs (%d)" % (cfg.B, world))
+        batch = edist.shard_batch(synth.make_batch(cfg), rank, world)
+        cfg = synth.get_config(args.config, B=cfg.B // world)
+    else:
+        batch = synth.make_batch(cfg, seed=synth.DATA_SEED + rank)      # weak scaling: every rank its own batch
     frames = int(batch["logmel_len"].sum())
     reducer = edist.GradAllReducer() if world > 1 else None
     model = build_model(cfg, weights, device=dev, reducer=reducer)
@@ -332,120 +543,35 @@ def main():
         return
     # ---------------- per-kernel-class breakdown and roofline (CUDA events of the eager timed pass)
     raw = prof.summary(main_stream=torch.cuda.current_stream().cuda_stream)
-    # GEMM calls were tagged per shape: fold them into one class for the breakdown, keep the shapes for the roofline
-    shapes = {k: v for k, v in raw.items() if k.startswith("gemm M=")}
-    summ = {k: v for k, v in raw.items() if k not in shapes}
-    if shapes:
-        summ["e2e_gemm"] = {"ms": sum(v["ms"] for v in shapes.values()), "calls": sum(v["calls"] for v in shapes.values()),
-                            "work": sum(v["work"] for v in shapes.values())}
-    tot = sum(v["ms"] for v in summ.values())
-    breakdown = {k: {"ms_per_step": v["ms"] / K, "calls_per_step": v["calls"] / K,
-                     "share": v["ms"] / tot if tot else 0.0} for k, v in sorted(summ.items(), key=lambda kv: -kv[1]["ms"])}
-    top = max(summ.items(), key=lambda kv: kv[1]["ms"])
-    name, tv = top
-    if name == "e2e_gemm":
-        peak = peaks["tc_sustained"]
-        gm = ops.get_gemm_mode()
-        nprod = {0: 1, 1: 3, 2: 1, 3: 3}[gm]
-        # tensor-pipe cost of one algorithmic product in bf16-MMA units: 3xTF32 issues 3 kind::tf32 MMAs and tf32 runs
-        # at half the bf16 rate (6 units); bf16x2 issues 3 kind::f16 MMAs (3 units).  "achieved"/"frac" stay
-        # ALGORITHMIC FLOPs against the bf16 peak as the contract asks; the mode ceiling is peak / units.
-        units = {0: 1, 1: 6, 2: 1, 3: 3}[gm]
-        # the dominant KERNEL = the GEMM shape with the largest time ON THE MAIN STREAM (the critical path; one launch
-        # configuration of gemm_tc_kernel).  Event durations of side-stream GEMMs include the time they wait for SMs
-        # held by the persistent decoder / recurrence kernels, so they say little about the kernel; the whole class
-        # (all shapes, all streams) is reported next to it.
-        on_main = {k: v for k, v in shapes.items() if v["main_calls"] > 0} or shapes
-        sname, sv = max(on_main.items(), key=lambda kv: kv[1]["main_ms"] if kv[1]["main_calls"] else kv[1]["ms"])
-        if sv["main_calls"]:
-            sv = {"ms": sv["main_ms"], "calls": sv["main_calls"], "work": sv["main_work"]}
-        ach = sv["work"] / (sv["ms"] * 1e-3) / 1e12
-        ach_class = tv["work"] / (tv["ms"] * 1e-3) / 1e12
-        roof = {"kernel": "gemm_tc_kernel<%d> %s (the GEMM shape with the largest time on the main stream; incl. its "
-                          "operand split passes if any)" % (gm, sname),
-                "bound": "tensor",
-                "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak, "traffic": None,
-                "peak_source": peaks["source"] + ", sustained bf16",
-                "algorithmic_gflop_per_launch": sv["work"] / sv["calls"] / 1e9,
-                "avg_launch_ms": sv["ms"] / sv["calls"], "launches_per_step": sv["calls"] / K,
-                "mma_products_per_flop": nprod,
-                "mode_ceiling_tflops": peak / units,
-                "frac_of_mode_ceiling": ach / (peak / units),
-                "class_aggregate": {"kernel": "all e2e_gemm calls (every dense projection incl. dX/dW, %d shapes)"
-                                              % len(shapes),
-                                    "algorithmic_gflop_per_step": tv["work"] / K / 1e9,
-                                    "achieved": ach_class, "frac": ach_class / peak,
-                                    "frac_of_mode_ceiling": ach_class / (peak / units),
-                                    "avg_launch_ms": tv["ms"] / tv["calls"]},
-                "top_shapes": [{"shape": k, "ms_per_step": v["ms"] / K, "on_main_stream": v["main_calls"] > 0,
-                                "tflops": v["work"] / (v["ms"] * 1e-3) / 1e12}
-                               for k, v in sorted(shapes.items(), key=lambda kv: -kv[1]["ms"])[:6]],
-                "note": "events of GEMMs on the weight-gradient / CTC side streams overlap the main stream and wait "
-                        "for SMs held by the persistent kernels: the class total exceeds its share of the step"}
-    else:
-        # recurrence / decoder loop: latency bound; algorithmic HBM bytes are small, report per-timestep latency
-        steps_total = tv["work"]
-        roof = {"kernel": name, "bound": "hbm", "achieved": None, "peak": peaks["hbm"], "unit": "GB/s",
-                "frac": None, "traffic": None, "peak_source": peaks["source"],
-                "us_per_timestep": tv["ms"] * 1e3 / max(steps_total, 1.0), "note": "latency-bound sequential kernel"}
-    rec = {k: summ[k] for k in summ if "rec" in k}
-    extra = {k: {"us_per_timestep": v["ms"] * 1e3 / max(v["work"], 1.0)} for k, v in rec.items()}
-    for k in ("e2e_decoder_loop_fwd", "e2e_decoder_loop_bwd", "e2e_decoder_persist_fwd", "e2e_decoder_persist_bwd"):
-        if k in summ:
-            extra[k] = {"us_per_timestep": summ[k]["ms"] * 1e3 / max(summ[k]["work"], 1.0)}
-    memory_bound = {}
-    try:
-        # memory-bound kernels: ALGORITHMIC bytes per call / event time, against the measured HBM peak
-        D_, T_enc = 2 * cfg.H, synth.pyramid_lens([cfg.T], synth.depth_reductions(cfg, cfg.L))[0]
-        rows_ce = cfg.U * cfg.B * cfg.V * 4
-        mem_bytes = {"e2e_ce_fwd": rows_ce,                         # reads the logits once (lse, picked cost)
-                     "e2e_ce_bwd": 2 * rows_ce,                     # reads logits, writes d logits
-                     # attention(): HF [B,T_enc,A] + enc [B,T_enc,D] read once per decoder step (14.4 MB at cfg-2; the
-                     # working set fits the 126 MB L2, so this is L2 -> SM traffic, not HBM)
-                     "e2e_decoder_persist_fwd": cfg.U * 4 * cfg.B * int(T_enc) * (cfg.A + D_)}
-        ctc_bytes = 0
-        for t_, (depth, vocab) in cfg.ctc.items():
-            Td = int(synth.pyramid_lens([cfg.T], synth.depth_reductions(cfg, depth))[0])
-            ctc_bytes += 2 * 4 * Td * cfg.B * (vocab + 1)           # read the logits, write their gradient
-        n_heads = max(len(cfg.ctc), 1)
-        mem_bytes["e2e_ctc_fwd_grad"] = ctc_bytes / n_heads         # per call (one call per head)
-        for k, bytes_per_call in mem_bytes.items():
-            if k in summ and summ[k]["ms"] > 0:
-                gbs = bytes_per_call * summ[k]["calls"] / (summ[k]["ms"] * 1e-3) / 1e9
-                memory_bound[k] = {"algorithmic_mb_per_call": bytes_per_call / 1e6, "achieved_gbs": gbs,
-                                   "frac_of_hbm_peak": gbs / peaks["hbm"]}
-        if "e2e_ctc_fwd_grad" in memory_bound:
-            memory_bound["e2e_ctc_fwd_grad"]["note"] = ("alpha/beta sweep = T_l sequential frames per utterance (one warp "
-                                                        "each): latency-bound, on its own stream beside the decoder")
-        if "e2e_decoder_persist_fwd" in memory_bound:
-            memory_bound["e2e_decoder_persist_fwd"]["note"] = ("attention operands only; L2-resident; the kernel also "
-                                                               "runs the gate GEMMs and 3 grid barriers per step")
-
-    except Exception as e:          # supplementary section: never cost the run its JSON line
-        memory_bound = {"error": repr(e)}
+    report = roofline_report(raw, cfg, peaks, K, ms / K, clocks, ops.get_gemm_mode())
+    roof, breakdown, extra, memory_bound = (report["roofline"], report["breakdown"], report["sequential_kernels"],
+                                            report["memory_bound_kernels"])
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
-        "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "ms_per_step": ms / K, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
         "dtype": {0: "f32", 1: "tf32x3", 2: "bf16", 3: "bf16x2"}[ops.get_gemm_mode()], "data": "synthetic",
-        "config": workload_config(args.config, world), "frames_per_step_per_gpu": frames,
+        "config": workload_config(args.config, world, batch_per_gpu=cfg.B), "frames_per_step_per_gpu": frames,
         "padded_frames_per_step_per_gpu": cfg.B * cfg.T, "loss": loss_val,
         "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "launches_per_step": launches / K,
         "step_mode": mode, "host_enqueue_ms_per_step": host_busy_ms,
         "eager": {"ms_per_step": ms_eager / K, "host_enqueue_ms_per_step": host_eager_ms,
                   "note": "same K steps launched kernel by kernel; the per-kernel events of breakdown/roofline come "
                           "from this pass (a graph replay runs the identical kernels)"},
-        "roofline": roof, "breakdown": breakdown, "sequential_kernels": extra, "memory_bound_kernels": memory_bound,
+        "roofline": roof, "pct_of_roofline": report["pct_of_roofline"], "breakdown": breakdown,
+        "sequential_kernels": extra, "memory_bound_kernels": memory_bound, "gemm": report["gemm"],
     }
     if world == 1 and not args.no_cpu_baseline:
+        # bounded sample (the whole default run must end within minutes): 8 of the batch's utterances, all host cores,
+        # median of 3 after 1 warm-up; `bench.py --impl reference` times the FULL batch (median of 5)
         cores = os.cpu_count() or 1
-        sample_B = 8
-        fps, sec, fr, _ = cpu_reference_step(args.config, sample_B, 2, 1)
+        sample_B = min(8, cfg.B)
+        fps, sec, fr, _ = cpu_reference_step(args.config, sample_B, 3, 1)
         line["cpu_baseline"] = {
             "value": fps, "unit": UNIT, "cores": cores, "kind": "port",
             "sample": "%s shapes, batch %d of %d utterances (%d valid frames), float32 NumPy restatement "
-                      "(oracle/model.py), mean of 2 steps after 1 warm-up, %.1f s/step"
-                      % (args.config, sample_B, cfg.B, fr, sec)}
+                      "(oracle/model.py; restated reference, not TF), all host cores, median of 3 steps after 1 warm-up, "
+                      "%.1f s/step; full batch: bench.py --impl reference" % (args.config, sample_B, cfg.B, fr, sec)}
     if world == 1 and not args.no_beam and args.config == "cfg2":
         line["beam_decode"] = beam_decode_rate(args.config, dev, cpu=not args.no_cpu_baseline)
     print(json.dumps(line))

@@ -58,7 +58,9 @@ def merge_candidates(utt, scores, k_u, idx_h, val_h, step, word_ins_penalty):
         par = starts[g][:, None] + sel // k
         parts.append((np.repeat(us[g], k), np.tile(np.arange(k), len(g)), par.reshape(-1),
                       np.take_along_axis(toks, sel, 1).reshape(-1).astype(np.int64),
-                      np.take_along_axis(flat, sel, 1).reshape(-1) + word_ins_penalty * (step + 1)))
+                      # the step-0 candidates carry the bare model score (beam_search.py:258-260); later ones add
+                      # word_ins_penalty * len(new_index_seq) (:321-322)
+                      np.take_along_axis(flat, sel, 1).reshape(-1) + (word_ins_penalty * (step + 1) if step else 0)))
     if not parts:
         e = np.zeros(0, np.int64)
         return dict(utt=e, parent=e, tok=e, score=np.zeros(0)), []
@@ -93,10 +95,26 @@ class BeamSearch(BaseParams):
         self.dec_params = self.map_dec_variables(self.get_model_params(ckpt_path), task)
         # the reference always loads "LM" weights too (beam_search.py:45-46); with lm_path pointing at the
         # same checkpoint they are the decoder's own LM-LSTM / projections
-        lm_src = self.search_params.lm_path
-        self.lm_params = self.dec_params if not lm_src or isinstance(lm_src, str) else \
-            self.map_dec_variables(self.get_model_params(lm_src), task)
         self.use_lm = not (self.search_params.lm_path is None or self.search_params.lm_weight == 0.0)
+        self.lm_params = self._load_lm(self.search_params.lm_path, ckpt_path, task)
+
+    def _load_lm(self, lm_src, ckpt_path, task):
+        """`map_lm_variables(get_model_params(lm_path))` (beam_search.py:45-46,111-134): the LM-LSTM, SimpleProjection,
+        OutputProjection and embedding of the checkpoint at `lm_path` (a dict of weights is accepted like for
+        `ckpt_path`).  The same checkpoint (or none, while lm_weight == 0 leaves the LM branch unused) reuses the
+        decoder's tensors; a path that cannot be read is an error whenever the LM is used."""
+        import os
+        if isinstance(lm_src, dict):
+            return self.dec_params if lm_src is ckpt_path else self.map_dec_variables(lm_src, task, lm_only=True)
+        if not lm_src or (isinstance(ckpt_path, str) and lm_src == ckpt_path):
+            return self.dec_params
+        from .tf_checkpoint import checkpoint_exists
+        if checkpoint_exists(lm_src) or os.path.exists(lm_src):
+            return self.map_dec_variables(self.get_model_params(lm_src), task, lm_only=True)
+        if self.use_lm:
+            raise FileNotFoundError("BeamSearch: lm_path %r is not a readable checkpoint (lm_weight = %g)"
+                                    % (lm_src, self.search_params.lm_weight))
+        return self.dec_params
 
     def get_model_params(self, ckpt_path):
         """Weights by TF variable name (beam_search.py:36-47 reads them with tf.train.NewCheckpointReader): a dict, a
@@ -108,10 +126,13 @@ class BeamSearch(BaseParams):
             return read_checkpoint(ckpt_path)
         return dict(np.load(ckpt_path))
 
-    def map_dec_variables(self, var_dict, task="char"):
-        """Name -> device tensor mapping (beam_search.py:53-109); float32 like the checkpoint."""
+    def map_dec_variables(self, var_dict, task="char", lm_only=False):
+        """Name -> device tensor mapping (beam_search.py:53-109); float32 like the checkpoint.  lm_only: the subset
+        map_lm_variables reads (beam_search.py:111-134), under the decoder's field names."""
         pre = "model/rnn_decoder_%s/" % task
         names = dict(lm_lstm_w="rnn/basic_lstm_cell/kernel", lm_lstm_b="rnn/basic_lstm_cell/bias",
+                     out_w="rnn/OutputProjection/kernel", out_b="rnn/OutputProjection/bias",
+                     embedding="decoder/embedding") if lm_only else dict(lm_lstm_w="rnn/basic_lstm_cell/kernel", lm_lstm_b="rnn/basic_lstm_cell/bias",
                      dec_lstm_w="rnn/basic_lstm_cell_1/kernel", dec_lstm_b="rnn/basic_lstm_cell_1/bias",
                      attn_dec_w="rnn/Attention/kernel", attn_dec_b="rnn/Attention/bias",
                      inp_w="rnn/InputProjection/kernel", inp_b="rnn/InputProjection/bias",
@@ -121,7 +142,8 @@ class BeamSearch(BaseParams):
         p = Bunch()
         for k, n in names.items():
             p[k] = torch.as_tensor(np.asarray(var_dict[pre + n], np.float32)).contiguous().to(self.device)
-        p.attn_enc_w = torch.as_tensor(np.squeeze(np.asarray(var_dict[pre + "AttnW"], np.float32))).contiguous().to(self.device)
+        if not lm_only:
+            p.attn_enc_w = torch.as_tensor(np.squeeze(np.asarray(var_dict[pre + "AttnW"], np.float32))).contiguous().to(self.device)
         if pre + "rnn/SimpleProjection/kernel" in var_dict:
             p.simple_w = torch.as_tensor(np.asarray(var_dict[pre + "rnn/SimpleProjection/kernel"], np.float32)).to(self.device)
             p.simple_b = torch.as_tensor(np.asarray(var_dict[pre + "rnn/SimpleProjection/bias"], np.float32)).to(self.device)
@@ -181,8 +203,9 @@ class BeamSearch(BaseParams):
                   lc=torch.zeros((N, Hl), **f64), lh=torch.zeros((N, Hl), **f64),
                   ctx=torch.zeros((N, D), **f64))
         if self.use_lm:
-            st["mc"] = torch.zeros((N, Hl), **f64)
-            st["mh"] = torch.zeros((N, Hl), **f64)
+            Hm = lp.lm_lstm_w.shape[1] // 4
+            st["mc"] = torch.zeros((N, Hm), **f64)
+            st["mh"] = torch.zeros((N, Hm), **f64)
         step = 0
         while step < self.MAX_STEPS and len(utt) > 0:
             n = len(utt)

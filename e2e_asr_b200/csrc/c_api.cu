@@ -63,6 +63,7 @@ int ce_bwd(cudaStream_t, int, int, int, const float*, const long long*, const in
            float*);
 int ctc_fwd_grad(cudaStream_t, int, int, int, long long, long long, const float*, const float*, const int*,
                  const long long*, int, const int*, int, float*, float*, float*, float);
+size_t ctc_workspace_floats(int, int, int);
 int sumsq(cudaStream_t, size_t, const float*, float*, float*, float, int);
 int clip_by_norm(cudaStream_t, size_t, float*, const float*, float, float*);
 int scale_inplace(cudaStream_t, size_t, float*, const float*, float);
@@ -345,11 +346,12 @@ int e2e_row_lse(void* stream, int rows, int V, const float* x, int ldx, float* l
 }
 int e2e_ctc_fwd_grad(void* stream, int T, int B, int C, long long sb, long long stt, const float* logits,
                      const float* lse_rows, const int* in_lens, const long long* labels, int ldl,
-                     const int* label_lens, int max_label_len, float* alpha_ws, float* loss_b, float* grad,
+                     const int* label_lens, int max_label_len, float* ws, float* loss_b, float* grad,
                      float out_scale) {
     return ctc_fwd_grad(ST(stream), T, B, C, sb, stt, logits, lse_rows, in_lens, labels, ldl, label_lens,
-                        max_label_len, alpha_ws, loss_b, grad, out_scale);
+                        max_label_len, ws, loss_b, grad, out_scale);
 }
+size_t e2e_ctc_workspace_floats(int T, int B, int max_label_len) { return ctc_workspace_floats(T, B, max_label_len); }
 int e2e_sumsq(void* stream, size_t n, const float* x, float* partials296, float* out, float sign, int accumulate) {
     return sumsq(ST(stream), n, x, partials296, out, sign, accumulate);
 }

@@ -27,10 +27,18 @@ def set_gemm_mode(mode):
 _workspace = {}
 
 
+def _devkey(device):
+    """Registry key of a device: always indexed ("cuda" and "cuda:0" name the same device)."""
+    d = torch.device(device)
+    if d.type == "cuda" and d.index is None:
+        d = torch.device("cuda", torch.cuda.current_device())
+    return str(d)
+
+
 def ensure_workspace(device, nbytes=2 << 30, stream=None):
     """Registers the operand pre-pass scratch of the tensor-core GEMM modes (the default one,
     or a private one for GEMMs enqueued on a side `stream`)."""
-    key = str(device) if stream is None else "%s/%d" % (device, stream.cuda_stream)
+    key = _devkey(device) if stream is None else "%s/%d" % (_devkey(device), stream.cuda_stream)
     if key not in _workspace or _workspace[key].numel() < nbytes:
         _workspace[key] = torch.empty((nbytes,), dtype=torch.uint8, device=device)
     if stream is None:
@@ -48,7 +56,7 @@ _state = {}
 
 def _dev_state(device):
     """Per-device scratch: recurrence step counters, barrier error flag, reduction partials."""
-    key = str(device)
+    key = _devkey(device)
     if key not in _state:
         _state[key] = dict(ctr=torch.zeros(1 << 20, dtype=torch.int32, device=device),
                            ctr_side=torch.zeros(1 << 20, dtype=torch.int32, device=device),
@@ -135,7 +143,7 @@ def gemm(a, b, out=None, ta=False, tb=False, bias=None, z=None, accumulate=False
         assert z.stride(1) == 1
         ldz = z.stride(0) if z.shape[0] > 1 else z.shape[1]
     mode = _GEMM_MODE if mode is None else mode
-    if mode != 0 and str(a.device) not in _workspace:
+    if mode != 0 and _devkey(a.device) not in _workspace:
         ensure_workspace(a.device)
     tag = ("gemm M=%d N=%d K=%d t%d%d" % (M, N, K, ta, tb)) if TAG_GEMM_SHAPES else "e2e_gemm"
     if mode in (1, 3) and (a_lo is not None or b_lo is not None):
@@ -254,7 +262,7 @@ _WGRAD = {}
 def enable_wgrad_stream(device, enabled=True):
     """Two streams: "enc" (encoder layer dW GEMMs, large) and "dec" (the ~80 small launches of the decoder /
     embedding / LM-LSTM gradients), so the small launches do not queue behind the large ones."""
-    key = str(torch.device(device))
+    key = _devkey(device)
     if not enabled:
         _WGRAD.pop(key, None)
         return None
@@ -275,11 +283,11 @@ def mark_step_start(device):
     queueing behind the encoder."""
     ev = torch.cuda.Event()
     ev.record()
-    _STEP_START[str(torch.device(device))] = ev
+    _STEP_START[_devkey(device)] = ev
 
 
 def sync_wgrad_stream(device):
-    ss = _WGRAD.get(str(torch.device(device)))
+    ss = _WGRAD.get(_devkey(device))
     if ss is not None:
         for s in ss.values():
             torch.cuda.current_stream().wait_stream(s)
@@ -346,7 +354,7 @@ class BiLSTMLayerFn(torch.autograd.Function):
             dbp = colsum(G)
             return dWx, dWh, dbp
 
-        side = _WGRAD.get(str(dev), {}).get("enc")
+        side = _WGRAD.get(_devkey(dev), {}).get("enc")
         dst = ctx.grad_dst
         pad = (None,) * (2 * (2 - nd))
         if side is not None and all(d is not None for d in dst) and all(ctx.needs_input_grad[1:1 + 2 * nd]):
@@ -823,9 +831,9 @@ class AttnDecoderFnV2(torch.autograd.Function):
         # The LM side of the decoder (embedding -> LM-LSTM -> InputProjection -> decoder-gate pre-activations) reads only
         # the teacher-forced ids and parameters: with the side streams on, it runs on the "dec" stream from the step's
         # start event, concurrently with the encoder, and the main stream joins it here.
-        side = _WGRAD.get(str(dev), {}).get("dec")
+        side = _WGRAD.get(_devkey(dev), {}).get("dec")
         main = torch.cuda.current_stream()
-        start = _STEP_START.pop(str(dev), None) if stash is not None and stash.get("early_lm") else None
+        start = _STEP_START.pop(_devkey(dev), None) if stash is not None and stash.get("early_lm") else None
         if side is not None:
             if start is not None:
                 side.wait_event(start)
@@ -970,7 +978,7 @@ class AttnDecoderFnV2(torch.autograd.Function):
             return [demb, dattn_w, dattn_v, dlm_k, dlm_b, ddec_k, ddec_b, dq_k, dq_b, dap_k, dap_b, dout_k,
                     dout_b, din_k, din_b, dsp_k, dsp_b]
 
-        side = _WGRAD.get(str(dev), {}).get("dec")
+        side = _WGRAD.get(_devkey(dev), {}).get("dec")
         dst = ctx.grad_dst
         need = [True] * 15 + [ctx.has_sp, ctx.has_sp]
         if (side is not None and all((d is not None) or (not n) for d, n in zip(dst, need))
@@ -1055,8 +1063,7 @@ class CTCHeadFn(torch.autograd.Function):
         lse = torch.empty((rows,), **f32)
         call("e2e_row_lse", rows, C, logits, C, lse)
         labels = labels.contiguous()
-        S = 2 * max_label_len + 1
-        alpha_ws = torch.empty((B * T * S,), **f32)
+        alpha_ws = torch.empty((_lib.lib().e2e_ctc_workspace_floats(T, B, int(max_label_len)),), **f32)
         loss_b = torch.empty((B,), **f32)
         grad = torch.zeros((rows, C), **f32)
         call("e2e_ctc_fwd_grad", T, B, C, sb, stt, logits, lse, in_lens_i32, labels, labels.stride(0),

@@ -63,6 +63,10 @@ class Seq2SeqModel(BaseParams):
         self.params = self.class_params() if params is None else params
         params = self.params
         self.device = torch.device(device)
+        if self.device.type == "cuda" and self.device.index is None:
+            # an indexed device everywhere: per-device registries (side streams, step-start events) are keyed by
+            # str(tensor.device) = "cuda:N"
+            self.device = torch.device("cuda", torch.cuda.current_device() if torch.cuda.is_available() else 0)
         self.variables = variables if variables is not None else VariableStore(self.device)
         self.encoder = Encoder(isTraining=isTraining, params=params.encoder_params, variables=self.variables)
         self.decoder = {}
@@ -99,7 +103,10 @@ class Seq2SeqModel(BaseParams):
 
     # ------------------------------------------------------------------
     def _to_device(self, key, arr, dtype):
-        """Host array -> device through a reusable pinned staging buffer."""
+        """Host array -> device through reusable pinned staging buffers.  The H2D copy is asynchronous, so a staging
+        buffer must not be rewritten before the copy that reads it has finished: every key owns TWO pinned buffers
+        used alternately, each with the event of its last copy, which the host waits on before refilling it (with a
+        run-ahead of one step that wait is already satisfied)."""
         buf = None
         if isinstance(arr, torch.Tensor):
             if arr.device == self.device:
@@ -108,15 +115,21 @@ class Seq2SeqModel(BaseParams):
                 buf = arr               # a loader that hands out pinned batches: copy straight from its buffer
             else:
                 arr = arr.numpy()
+        slot = None
         if buf is None:
             arr = np.ascontiguousarray(arr)
             t = torch.from_numpy(arr)
             if t.dtype != dtype:
                 t = t.to(dtype)
-            buf = self._pinned.get(key)
-            if buf is None or buf.shape != t.shape or buf.dtype != dtype:
-                buf = torch.empty(t.shape, dtype=dtype).pin_memory()
-                self._pinned[key] = buf
+            ring = self._pinned.get(key)
+            if ring is None or ring["bufs"][0].shape != t.shape or ring["bufs"][0].dtype != dtype:
+                ring = self._pinned[key] = {"bufs": [torch.empty(t.shape, dtype=dtype).pin_memory() for _ in range(2)],
+                                            "events": [None, None], "next": 0}
+            slot = ring["next"]
+            ring["next"] = 1 - slot
+            if ring["events"][slot] is not None:
+                ring["events"][slot].synchronize()
+            buf = ring["bufs"][slot]
             buf.copy_(t)
         static = getattr(self, "_static_inputs", None)
         if static is not None:
@@ -125,8 +138,13 @@ class Seq2SeqModel(BaseParams):
             if dev is None or dev.shape != buf.shape or dev.dtype != dtype:
                 dev = static[key] = torch.empty(buf.shape, dtype=dtype, device=self.device)
             dev.copy_(buf, non_blocking=True)
-            return dev
-        return buf.to(self.device, non_blocking=True)
+        else:
+            dev = buf.to(self.device, non_blocking=True)
+        if slot is not None:
+            ev = torch.cuda.Event()
+            ev.record()
+            ring["events"][slot] = ev
+        return dev
 
     def _len_tensor(self, key, arr):
         host = np.asarray(arr.cpu().numpy() if isinstance(arr, torch.Tensor) else arr, np.int64)

@@ -220,3 +220,11 @@ def make_batch(cfg, seed=DATA_SEED, tasks=("char",)):
         batch[task] = lab
         batch[task + "_len"] = ll
     return batch
+
+
+def make_beam_eval_batch(cfg, n_utts=256, seed=17):
+    """BASELINE.json configs[2]: a synthetic eval batch of encoder top-layer states, T_enc uniform in [50, 88]
+    (what eval_model.py:141-143 hands to BeamSearch one utterance at a time)."""
+    rng = np.random.Generator(np.random.PCG64(seed))
+    return [(np.tanh(rng.standard_normal((int(rng.integers(50, 89)), 2 * cfg.H))) * 0.8).astype(np.float32)
+            for _ in range(n_utts)]

@@ -235,12 +235,15 @@ int e2e_ce_bwd(void* stream, int U, int B, int V, const float* logits, const lon
 /* Auxiliary CTC on a lower encoder layer (north-star requirement; the reference
  * only keeps the hook, encoder.py:143-144,160-161 / seq2seq_model.py:104).
  * TF-1.x tf.nn.ctc_loss semantics, blank = C-1.  logits row (b,t) = b*sb + t*st.
- * Writes loss_b[B] (= -log p) and grad = out_scale * d(loss_b)/dlogits. */
+ * Writes loss_b[B] (= -log p) and grad = out_scale * d(loss_b)/dlogits.
+ * ws: caller-provided scratch of e2e_ctc_workspace_floats(T, B, max_label_len) floats
+ * (gathered emissions, scaled alpha, scaled beta; three launches: emit, sweep, grad). */
 int e2e_row_lse(void* stream, int rows, int V, const float* x, int ldx, float* lse);
 int e2e_ctc_fwd_grad(void* stream, int T, int B, int C, long long sb, long long st, const float* logits,
                      const float* lse_rows, const int* in_lens, const long long* labels, int ldl,
-                     const int* label_lens, int max_label_len, float* alpha_ws, float* loss_b,
+                     const int* label_lens, int max_label_len, float* ws, float* loss_b,
                      float* grad, float out_scale);
+size_t e2e_ctc_workspace_floats(int T, int B, int max_label_len);
 
 /* Beam search decoder step in float64 (beam_search.py:137-221; dtype flow of SURVEY.md
  * A.6: fp32 weights / embeddings / encoder states widened at load, fp64 arithmetic),

@@ -51,9 +51,10 @@ class DecParams(object):
         self.embedding = g("decoder/embedding")
 
 
-def make_step_fn(p, enc, lm_weight=0.0):
-    """top_k_setup_with_lm (beam_search.py:163-221); the LM weights are the
-    decoder's own (lm_path == same checkpoint)."""
+def make_step_fn(p, enc, lm_weight=0.0, lp=None):
+    """top_k_setup_with_lm (beam_search.py:163-221); lp = the LM checkpoint's variables (map_lm_variables,
+    beam_search.py:111-134), by default the decoder's own (lm_path == same checkpoint)."""
+    lp = p if lp is None else lp
     if enc.ndim == 3:
         enc = np.squeeze(enc, axis=0)
     attn_enc_term = np.matmul(enc, p.attn_enc_w)               # :148 (float32)
@@ -76,11 +77,11 @@ def make_step_fn(p, enc, lm_weight=0.0):
         context_vec, _ = attention(dec_state[0])               # query = new_c (:193)
         proj = np.matmul(np.concatenate((dec_state[0], context_vec), axis=0), p.attn_proj_w) + p.attn_proj_b
         log_dec = np.log(softmax(np.matmul(proj, p.out_w) + p.out_b))
-        lm_state = basic_lstm(x_lm, lm_state, p.lm_lstm_w, p.lm_lstm_b)   # LM branch always runs (:200)
+        lm_state = basic_lstm(x_lm, lm_state, lp.lm_lstm_w, lp.lm_lstm_b)   # LM branch always runs (:200)
         lm_output = lm_state[1]
-        if p.simple_w is not None:
-            lm_output = np.matmul(lm_output, p.simple_w) + p.simple_b
-        log_lm = np.log(softmax(np.matmul(lm_output, p.out_w) + p.out_b))
+        if lp.simple_w is not None:
+            lm_output = np.matmul(lm_output, lp.simple_w) + lp.simple_b
+        log_lm = np.log(softmax(np.matmul(lm_output, lp.out_w) + lp.out_b))
         combined = log_dec + lm_weight * log_lm
         top = np.argpartition(combined, -beam_size)[-beam_size:]
         return top, combined[top], combined[top], [dec_state, dec_lm_state, lm_state], context_vec, combined
@@ -89,11 +90,14 @@ def make_step_fn(p, enc, lm_weight=0.0):
 
 
 def beam_search(weights, enc, beam_size=4, lm_weight=0.0, word_ins_penalty=0, task="char",
-                return_score=False):
-    """BeamSearch.__call__ (beam_search.py:224-338), SURVEY.md A.7."""
+                return_score=False, lm_weights=None):
+    """BeamSearch.__call__ (beam_search.py:224-338), SURVEY.md A.7.  lm_weights: the variables of a separate LM
+    checkpoint (search_params.lm_path, beam_search.py:45-46); None = the decoder's own."""
     p = DecParams(weights, task)
-    step = make_step_fn(p, enc, lm_weight)
+    lp = p if lm_weights is None else DecParams(lm_weights, task)
+    step = make_step_fn(p, enc, lm_weight, lp)
     x = p.embedding[GO_ID]
+    x_lm0 = lp.embedding[GO_ID]
     hs = p.dec_lstm_w.shape[1] // 4
     ls = p.lm_lstm_w.shape[1] // 4
     zero_dec = (np.zeros(hs), np.zeros(hs))
@@ -101,7 +105,8 @@ def beam_search(weights, enc, beam_size=4, lm_weight=0.0, word_ins_penalty=0, ta
     zero_attn = np.zeros(enc.shape[-1])
     k = beam_size
     live, final = [], []
-    top, ms, _, states, ctx, _ = step(x, x, [zero_dec, zero_lm, zero_lm], zero_attn, k)
+    zero_lm2 = (np.zeros(lp.lm_lstm_w.shape[1] // 4), np.zeros(lp.lm_lstm_w.shape[1] // 4))
+    top, ms, _, states, ctx, _ = step(x, x_lm0, [zero_dec, zero_lm, zero_lm2], zero_attn, k)
     for idx in range(top.shape[0]):
         ent = ([int(top[idx])], states, ctx, ms[idx])
         if top[idx] == EOS_ID:
@@ -114,7 +119,7 @@ def beam_search(weights, enc, beam_size=4, lm_weight=0.0, word_ins_penalty=0, ta
         nstates, nctx, scores, mscores, indices = [], [], [], [], []
         for seq, st, cx, sc in live:
             e = p.embedding[seq[-1]]
-            top, ms, ts, st2, cx2, _ = step(e, e, st, cx, k)
+            top, ms, ts, st2, cx2, _ = step(e, lp.embedding[seq[-1]], st, cx, k)
             nstates.append(st2); nctx.append(cx2)
             indices.append(top); scores.append(ts + sc); mscores.append(ms + sc)
         all_scores = np.concatenate(scores)

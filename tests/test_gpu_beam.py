@@ -46,13 +46,46 @@ def test_beam_k10_eval_batch_vs_oracle_and_lm_weight():
             for _ in range(12)]
     for k, lmw in ((10, 0.0), (4, 0.3)):
         sp = BeamSearch.class_params()
-        sp.beam_size, sp.lm_weight, sp.lm_path = k, lmw, "same-checkpoint"
+        sp.beam_size, sp.lm_weight, sp.lm_path = k, lmw, w        # the same "checkpoint" 
         out, sc = BeamSearch(w, sp, device="cuda:0").decode_batch(encs, return_scores=True)
         for u, enc in enumerate(encs):
             ref, rs = ob.beam_search(w, enc, beam_size=k, lm_weight=lmw, return_score=True)
             np.testing.assert_array_equal(out[u], ref)
             # scores agree to float32 rounding of enc.AttnW (computed in float32 by the reference too)
             assert abs(sc[u] - rs) <= 1e-6 * max(1.0, abs(rs))
+
+
+def test_beam_separate_lm_checkpoint_and_word_insertion_penalty(tmp_path):
+    """search_params.lm_path names ANOTHER checkpoint (beam_search.py:45-46: map_lm_variables(get_model_params(lm_path)))
+    -- its LM-LSTM / OutputProjection / embedding drive the fusion term -- given as a dict, as an .npz path, and as a
+    TF-bundle prefix; word_ins_penalty is added from step 1 on (beam_search.py:321-322), not to the step-0 scores."""
+    from e2e_asr_b200.beam_search import BeamSearch
+    from e2e_asr_b200.tf_checkpoint import write_checkpoint
+    cfg = synth.get_config("cfg1")
+    w = gg.dec_weights(cfg, 21, 2.5, 10.0)
+    w_lm = gg.dec_weights(cfg, 33, 1.0, 6.0)
+    rng = np.random.Generator(np.random.PCG64(5))
+    encs = [(np.tanh(rng.standard_normal((int(rng.integers(20, 40)), 2 * cfg.H))) * 0.8).astype(np.float32)
+            for _ in range(5)]
+    npz = str(tmp_path / "lm.npz")
+    np.savez(npz, **w_lm)
+    prefix = str(tmp_path / "lm_ckpt")
+    write_checkpoint(prefix, w_lm)
+    refs = [ob.beam_search(w, e, beam_size=4, lm_weight=0.4, word_ins_penalty=0.3, return_score=True, lm_weights=w_lm)
+            for e in encs]
+    same = [ob.beam_search(w, e, beam_size=4, lm_weight=0.4, word_ins_penalty=0.3) for e in encs]
+    assert any(not np.array_equal(a[0], b) for a, b in zip(refs, same)), "the separate LM must matter in this test"
+    for src in (w_lm, npz, prefix):
+        sp = BeamSearch.class_params()
+        sp.beam_size, sp.lm_weight, sp.lm_path, sp.word_ins_penalty = 4, 0.4, src, 0.3
+        out, sc = BeamSearch(w, sp, device="cuda:0").decode_batch(encs, return_scores=True)
+        for u in range(len(encs)):
+            np.testing.assert_array_equal(out[u], refs[u][0])
+            assert abs(sc[u] - refs[u][1]) <= 1e-6 * max(1.0, abs(refs[u][1]))
+    sp = BeamSearch.class_params()
+    sp.beam_size, sp.lm_weight, sp.lm_path = 4, 0.4, str(tmp_path / "missing")
+    with pytest.raises(FileNotFoundError):
+        BeamSearch(w, sp, device="cuda:0")
 
 
 @pytest.mark.gpu

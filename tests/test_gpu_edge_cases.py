@@ -104,3 +104,44 @@ def test_ragged_batches_at_reference_widths(frame_lens, target_lens, mode):
         compare_step(model, ref, rtol=1e-4)
     finally:
         ops.set_gemm_mode("fp32")
+
+
+@pytest.mark.parametrize("graph", [False, True], ids=["eager", "graph"])
+def test_distinct_batches_back_to_back_from_host(graph):
+    """The host -> device staging is asynchronous (pinned buffer -> non_blocking copy) and the host runs one step ahead:
+    step N must train on batch N even though batch N+1 is staged while it runs.  Different batches of the same shape
+    are fed back to back WITHOUT any synchronisation in between; every step's loss must equal the loss of that batch
+    fed from device-resident (`prepared=`) inputs."""
+    import torch
+    cfg = synth.get_config("cfg1", B=8, T=120)
+    w = synth.make_weights(cfg)
+    base = synth.make_batch(cfg, seed=100)
+    batches = []
+    for i in range(4):          # same shapes, lengths and maxima; other features and other (valid) token ids
+        b = {k: (v.copy() if hasattr(v, "copy") else v) for k, v in base.items()}
+        b["logmel"] = (base["logmel"] * (1.0 + 0.25 * i)).astype(np.float32)
+        tok = b["char"] >= 3
+        b["char"][tok] = (b["char"][tok] - 3 + 7 * i) % (cfg.V - 3) + 3
+        batches.append(b)
+    ops.set_gemm_mode("tf32x3")
+    try:
+        model = build_model(cfg, w, device="cuda:0")
+        expect = []
+        for b in batches:
+            model.run_step(b)
+            torch.cuda.synchronize()
+            expect.append(float(model.total_loss))
+        assert len(set(round(e, 6) for e in expect)) == len(expect), "the batches must differ"
+        step = model.graphed_step(batches[0]) if graph else model.run_step
+        got = []
+        for rep in range(3):
+            for b in batches:
+                step(b)
+                got.append(model.total_loss.clone())  # device scalars (a replayed graph rewrites ONE tensor): no host
+                                                      # synchronisation between steps
+        torch.cuda.synchronize()
+        got = [float(g) for g in got]
+        for i, g in enumerate(got):
+            assert abs(g - expect[i % 4]) <= 1e-6 * abs(expect[i % 4]), (i, g, expect[i % 4])
+    finally:
+        ops.set_gemm_mode("fp32")

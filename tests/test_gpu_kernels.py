@@ -154,7 +154,11 @@ def _attn_decoder_case(cname):
 def test_ctc_head():
     from e2e_asr_b200.losses import LossUtils
     rng = np.random.default_rng(8)
-    for (T_, B, D, C, Lmax) in [(12, 4, 6, 5, 4), (40, 3, 8, 11, 19), (150, 2, 8, 30, 70), (9, 5, 4, 3, 1)]:
+    # S = 2 Lmax + 1 selects the sweep kernel's states-per-lane variant: 1, 2, 8, 1, 4, 12, 16, 24, 32; B > 8 spans
+    # several sweep CTAs (8 utterances each)
+    for (T_, B, D, C, Lmax) in [(12, 4, 6, 5, 4), (40, 3, 8, 11, 19), (150, 2, 8, 30, 70), (9, 5, 4, 3, 1),
+                                (90, 11, 6, 9, 40), (400, 3, 6, 40, 180), (520, 2, 6, 50, 250),
+                                (760, 2, 4, 20, 370), (1050, 2, 4, 12, 500)]:
         st = rng.standard_normal((B, T_, D))
         in_lens = rng.integers(max(2 * Lmax + 1, 2), T_ + 1, size=B)
         lab_lens = rng.integers(1, Lmax + 1, size=B)
