@@ -34,7 +34,8 @@ def loop_merge(utt, seqs, scores, k_u, final, idx_h, val_h, step, wip):
             pr = r + int(par[j])
             t_new = int(cand_tokens[sel[j]])
             seq = seqs[pr] + [t_new]
-            sc = float(model_scores[sel[j]]) + wip * len(seq)
+            # step 0 keeps the bare model score (beam_search.py:258-260); later steps add the penalty (:321-322)
+            sc = float(model_scores[sel[j]]) + (wip * len(seq) if step else 0.0)
             if t_new == EOS_ID:
                 final[u].append((seq, sc))
                 k_u[u] -= 1
