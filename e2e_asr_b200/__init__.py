@@ -15,7 +15,7 @@ def __getattr__(name):
     import importlib
     table = {"Encoder": ".encoder", "Decoder": ".decoder", "AttnDecoder": ".attn_decoder",
              "LossUtils": ".losses", "Seq2SeqModel": ".seq2seq_model", "BeamSearch": ".beam_search",
-             "VariableStore": ".variables"}
+             "VariableStore": ".variables", "SpeechDataset": ".speech_dataset"}
     if name in table:
         return getattr(importlib.import_module(table[name], __name__), name)
     raise AttributeError(name)

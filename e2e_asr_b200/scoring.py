@@ -39,9 +39,10 @@ def word_errors(hyp_words, ref_words):
     """Levenshtein alignment turning `hyp_words` into `ref_words` (eval_model.py:219: ed(decoded_words, gold_words)).
     Returns (distance, insertions, deletions, substitutions) with the reference's opcode meaning: "insert" = words of
     the reference missing from the hypothesis, "delete" = extra hypothesis words, "replace" = substitutions.  The
-    distance is unique; among optimal alignments, matches / substitutions are preferred over deletions over
-    insertions when backtracking (the split may differ from the third-party edit_distance package, the total may
-    not)."""
+    distance is unique; the split depends on which optimal alignment is taken: like the third-party `edit_distance`
+    package the reference imports (SequenceMatcher with lowest_cost_action: equal / replace when the diagonal is
+    cheapest, else insert, else delete -- restated from the published source, the package is absent here, so the
+    tie-breaking is unpinned; the total is not affected)."""
     n, m = len(hyp_words), len(ref_words)
     d = [[0] * (m + 1) for _ in range(n + 1)]
     for i in range(1, n + 1):
@@ -59,12 +60,12 @@ def word_errors(hyp_words, ref_words):
         if i > 0 and j > 0 and d[i][j] == d[i - 1][j - 1] + (0 if hyp_words[i - 1] == ref_words[j - 1] else 1):
             subs += hyp_words[i - 1] != ref_words[j - 1]
             i, j = i - 1, j - 1
-        elif i > 0 and d[i][j] == d[i - 1][j] + 1:
-            dele += 1
-            i -= 1
-        else:
+        elif j > 0 and d[i][j] == d[i][j - 1] + 1:
             ins += 1
             j -= 1
+        else:
+            dele += 1
+            i -= 1
     return d[n][m], ins, dele, subs
 
 
