@@ -43,7 +43,7 @@ _SIGS = {
     "e2e_mean": "pipp",
     "e2e_axpy": "pzfpp",
     "e2e_adam": "pzppppffff",
-    "e2e_dropout": "pzppfQIz",
+    "e2e_dropout": "pzppfQIzp",
     "e2e_lstm_point_fwd": "piipppp",
     "e2e_lstm_point_bwd": "piippppppp",
     "e2e_gru_gate_fwd": "piipppp",

@@ -108,6 +108,8 @@ class AttnDecoder(Decoder):
         v = self.get_variables(enc.shape[2])
         lens_host = np.asarray(ops.host_array(seq_len))
         U = int(lens_host.max()) if len(lens_host) else 0        # raw_rnn stops when all rows are finished
+        if getattr(self, "shape_bounds", False):                 # bucket-captured step: all padded steps, masked
+            U = int(decoder_inp.shape[0]) - 1
         lens = ops.to_i32(seq_len, dev)
         enc_len = ops.to_i32(seq_len_inp, dev)
         rule = self.input_rule()

@@ -70,7 +70,8 @@ int scale_inplace(cudaStream_t, size_t, float*, const float*, float);
 int mean_vec(cudaStream_t, int, const float*, float*);
 int axpy(cudaStream_t, size_t, float, const float*, float*);
 int adam_update(cudaStream_t, size_t, float*, const float*, float*, float*, float, float, float, float);
-int dropout(cudaStream_t, size_t, const float*, float*, float, unsigned long long, unsigned, size_t);
+int dropout(cudaStream_t, size_t, const float*, float*, float, unsigned long long, unsigned, size_t,
+            const unsigned long long*);
 int sample_rows(cudaStream_t, int, int, const float*, int, unsigned long long, unsigned, unsigned, long long*);
 int gru_rec(cudaStream_t, bool, int, int, int, int, int, float*, float*, float*, float*, const float*, const float*,
             const float*, const int*);
@@ -368,8 +369,8 @@ int e2e_adam(void* stream, size_t n, float* param, const float* grad, float* m, 
     return adam_update(ST(stream), n, param, grad, m, v, lr_t, beta1, beta2, eps);
 }
 int e2e_dropout(void* stream, size_t n, const float* x, float* y, float keep, unsigned long long seed,
-                unsigned offset, size_t first) {
-    return dropout(ST(stream), n, x, y, keep, seed, offset, first);
+                unsigned offset, size_t first, const unsigned long long* seed_dev) {
+    return dropout(ST(stream), n, x, y, keep, seed, offset, first, seed_dev);
 }
 int e2e_sample_rows(void* stream, int rows, int V, const float* logits, int ldl, unsigned long long seed,
                     unsigned offset, unsigned first_row, long long* out) {

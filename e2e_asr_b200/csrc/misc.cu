@@ -178,8 +178,10 @@ __device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t
     out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
 }
 __global__ void dropout_kernel(size_t n, const float* __restrict__ x, float* __restrict__ y, float keep,
-                               unsigned long long seed, unsigned offset, size_t first4) {
+                               unsigned long long seed, unsigned offset, size_t first4,
+                               const unsigned long long* __restrict__ seed_dev) {
     const float inv = 1.0f / keep;
+    if (seed_dev != nullptr) seed = *seed_dev;      // the key of THIS replay of a captured step
     for (size_t q = blockIdx.x * (size_t)blockDim.x + threadIdx.x; q * 4 < n; q += (size_t)gridDim.x * blockDim.x) {
         uint32_t r[4];
         const size_t qg = q + first4;       // counter = global quad index: a slice of a buffer draws the buffer's mask
@@ -192,12 +194,12 @@ __global__ void dropout_kernel(size_t n, const float* __restrict__ x, float* __r
     }
 }
 int dropout(cudaStream_t st, size_t n, const float* x, float* y, float keep, unsigned long long seed,
-            unsigned offset, size_t first) {
+            unsigned offset, size_t first, const unsigned long long* seed_dev) {
     E2E_REQUIRE(keep > 0.f && keep <= 1.f, "dropout: keep probability %f out of (0, 1]", keep);
     E2E_REQUIRE(first % 4 == 0, "dropout: the slice must start at a multiple of 4 elements (got %zu)", first);
     if (n == 0) return 0;
     dropout_kernel<<<min((size_t)SUMSQ_BLOCKS * 8, (n / 4 + 256) / 256), 256, 0, st>>>(n, x, y, keep, seed, offset,
-                                                                                        first / 4);
+                                                                                        first / 4, seed_dev);
     E2E_LAUNCH_CHECK();
     return 0;
 }

@@ -57,6 +57,7 @@ class GradAllReducer(object):
     def __init__(self, group=None, bucket_elems=16 * 1024 * 1024):
         self.group = group
         self.world_size = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
         self.bucket_elems = bucket_elems
         self.stream = torch.cuda.Stream() if torch.cuda.is_available() else None
 

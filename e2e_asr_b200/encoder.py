@@ -138,7 +138,9 @@ class Encoder(BaseParams):
         T_l = T
         for i in range(max_depth):
             layer_depth = i + 1
-            max_len = int(lens_host.max()) if B else 0
+            # loop bound of the recurrence: the longest utterance of the batch, or -- for a step captured once per
+            # length bucket (GraphedStep(bucket=True)) -- the padded shape, the extra steps being masked
+            max_len = (T_l if getattr(self, "shape_bounds", False) else int(lens_host.max())) if B else 0
             out = self._layer_encoder_input(x, lens_dev, max_len, layer_depth)       # [B, Tp, 2H]
             if out.is_cuda:
                 # consumers on other streams (auxiliary heads) may start as soon as THIS layer is done

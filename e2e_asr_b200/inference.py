@@ -80,7 +80,8 @@ def _stepwise_decode(v, decoder_inp, lens_i32, U, enc, enc_len_i32, lm_drop=None
              xl[:, E:], E + Hl, hl)
         cl, cl2 = cl2, cl
         if lm_drop is not None:     # the [U*B, Hl] mask of the training pass, rows t*B .. t*B+B
-            call("e2e_dropout", B * Hl, hl, hl_d, float(lm_drop[0]), int(lm_drop[1]), int(lm_drop[2]), t * B * Hl)
+            call("e2e_dropout", B * Hl, hl, hl_d, float(lm_drop[0]), int(lm_drop[1]), int(lm_drop[2]), t * B * Hl,
+                 ops.seed_dev(lm_drop[1]))
         m = ops.gemm(hl_d, v["sp_k"], bias=v["sp_b"]) if v["sp_k"] is not None else hl_d
         # xin = [m, ctx_prev] . in_k + in_b
         ops.gemm(m, v["in_k"][:Hd], bias=v["in_b"], out=xh[:, :E])

@@ -228,6 +228,22 @@ def _unpack_lstm(dWx, dWh, dbp, I, H, nd, device):
     return outs
 
 
+class StepSeed(int):
+    """The Philox key of a step: an int (passed to the kernels by value) that may carry `.dev`, a device int64 tensor
+    holding the same key.  Kernels given the device word read the key from it, so a step captured in a CUDA graph
+    draws new masks at every replay: the host rewrites the word before each launch (Seq2SeqModel._stage_step_seed)."""
+    dev = None
+
+    def __new__(cls, value, dev=None):
+        obj = super(StepSeed, cls).__new__(cls, int(value))
+        obj.dev = dev
+        return obj
+
+
+def seed_dev(seed):
+    return getattr(seed, "dev", None)
+
+
 class DropoutFn(torch.autograd.Function):
     """DropoutWrapper(output_keep_prob) on a recurrent cell's outputs (encoder.py:50-52, decoder.py:60-63):
     y = x * mask / keep with the stateless Philox mask of e2e_dropout; backward regenerates the mask."""
@@ -238,16 +254,16 @@ class DropoutFn(torch.autograd.Function):
         [U*B, H] tensor draws that tensor's mask); a multiple of 4."""
         x = x.contiguous()
         y = torch.empty_like(x)
-        call("e2e_dropout", x.numel(), x, y, float(keep), int(seed), int(offset), int(first))
-        ctx.cfg = (float(keep), int(seed), int(offset), int(first))
+        call("e2e_dropout", x.numel(), x, y, float(keep), int(seed), int(offset), int(first), seed_dev(seed))
+        ctx.cfg = (float(keep), int(seed), int(offset), int(first), seed_dev(seed))
         return y
 
     @staticmethod
     def backward(ctx, dy):
-        keep, seed, offset, first = ctx.cfg
+        keep, seed, offset, first, sdev = ctx.cfg
         dy = dy.contiguous()
         dx = torch.empty_like(dy)
-        call("e2e_dropout", dy.numel(), dy, dx, keep, seed, offset, first)
+        call("e2e_dropout", dy.numel(), dy, dx, keep, seed, offset, first, sdev)
         return dx, None, None, None, None
 
 
@@ -661,7 +677,7 @@ class AttnDecoderFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, enc, emb, attn_w, attn_v, lm_k, lm_b, dec_k, dec_b, q_k, q_b, ap_k, ap_b, out_k, out_b,
-                in_k, in_b, sp_k, sp_b, ids, lens_i32, enc_len_i32, U, stash):
+                in_k, in_b, sp_k, sp_b, ids, lens_i32, enc_len_i32, U, stash, lm_drop=None):
         dev = enc.device
         st = _dev_state(dev)
         B, Tn, D = enc.shape
@@ -681,7 +697,13 @@ class AttnDecoderFn(torch.autograd.Function):
         C_lm = torch.empty((U * B, Hl), **f32)
         call("e2e_lstm_rec_fwd", B, U, U, Hl, 1, 1, B, G_lm, hl, C_lm, Wh_lm, lens_i32, st["ctr"],
              st["ctr"].numel() * 4, st["err"], work=float(U), tag="lm_rec_fwd")
-        m = gemm(hl, sp_k, bias=sp_b) if sp_k is not None else hl    # SimpleProjection (:149-151)
+        # DropoutWrapper on lm_cell: its OUTPUT is dropped, the recurrent state is not (decoder.py:60-63)
+        hl_out = hl
+        if lm_drop is not None:
+            hl_out = torch.empty_like(hl)
+            call("e2e_dropout", hl.numel(), hl, hl_out, float(lm_drop[0]), int(lm_drop[1]), int(lm_drop[2]), 0,
+                 seed_dev(lm_drop[1]))
+        m = gemm(hl_out, sp_k, bias=sp_b) if sp_k is not None else hl_out   # SimpleProjection (:149-151)
         pre = gemm(m, in_k[:Hd], bias=in_b)                          # lm half of InputProjection (:157-158)
         HF = gemm(enc_flat, attn_w.view(D, A))                       # hidden_features (:70-73), padded rows too
         # --- sequential loop
@@ -705,6 +727,8 @@ class AttnDecoderFn(torch.autograd.Function):
                               bufs["gates_tmp"])
         ctx.dims = (B, Tn, D, V, E, Hl, Hd, A, U, Tp)
         ctx.stash = stash
+        ctx.lm_drop = lm_drop
+        ctx.hl_out = hl_out if lm_drop is not None else None
         return logits
 
     @staticmethod
@@ -756,9 +780,14 @@ class AttnDecoderFn(torch.autograd.Function):
         dm = gemm(dxin, in_k[:Hd], tb=True)                           # [U*B, Hd]
         dsp_k = dsp_b = None
         if sp_k is not None:
-            dsp_k = gemm(hl, dm, ta=True)
+            dsp_k = gemm(hl if ctx.hl_out is None else ctx.hl_out, dm, ta=True)
             dsp_b = colsum(dm)
             dm = gemm(dm, sp_k, tb=True)
+        if ctx.lm_drop is not None:
+            dmd = torch.empty_like(dm)
+            call("e2e_dropout", dm.numel(), dm.contiguous(), dmd, float(ctx.lm_drop[0]), int(ctx.lm_drop[1]),
+                 int(ctx.lm_drop[2]), 0, seed_dev(ctx.lm_drop[1]))
+            dm = dmd
         # LM-LSTM backward (time-major rows: b stride 1, t stride B)
         call("e2e_lstm_rec_bwd", B, U, U, Hl, 1, 1, B, G_lm, C_lm, Wh_lm, dm, lens_i32, st["ctr"],
              st["ctr"].numel() * 4, st["err"], work=float(U), tag="lm_rec_bwd")
@@ -779,7 +808,7 @@ class AttnDecoderFn(torch.autograd.Function):
         gemm(dHF, attn_w.view(D, A), tb=True, out=denc, accumulate=True)
         denc_view = torch.as_strided(denc, (B, Tn, D), (Tp * D, D, 1)) if ctx.needs_input_grad[0] else None
         return (denc_view, demb, dattn_w, dattn_v, dlm_k, dlm_b, ddec_k, ddec_b, dq_k, dq_b, dap_k, dap_b, dout_k,
-                dout_b, din_k, din_b, dsp_k, dsp_b, None, None, None, None, None)
+                dout_b, din_k, din_b, dsp_k, dsp_b, None, None, None, None, None, None)
 
 
 _DECODER_IMPL = "persist"      # "persist": one cooperative launch per direction; "loop": per-step kernels
@@ -802,9 +831,7 @@ def attn_decoder_apply(*args, lm_drop=None):
     # args: enc, emb, attn_w, attn_v, lm_k, lm_b, dec_k, dec_b, q_k, ...
     if _DECODER_IMPL == "persist" and _persist_fits(args[0], args[6], args[8], args[21]):
         return AttnDecoderFnV2.apply(*(args + (lm_drop,)))
-    if lm_drop is not None:
-        raise NotImplementedError("decoder dropout is served by the persistent decoder kernels only")
-    return AttnDecoderFn.apply(*args)
+    return AttnDecoderFn.apply(*(args + (lm_drop,)))
 
 
 class AttnDecoderFnV2(torch.autograd.Function):
@@ -853,7 +880,8 @@ class AttnDecoderFnV2(torch.autograd.Function):
             hl_out = hl
             if lm_drop is not None:
                 hl_out = torch.empty_like(hl)
-                call("e2e_dropout", hl.numel(), hl, hl_out, float(lm_drop[0]), int(lm_drop[1]), int(lm_drop[2]), 0)
+                call("e2e_dropout", hl.numel(), hl, hl_out, float(lm_drop[0]), int(lm_drop[1]), int(lm_drop[2]), 0,
+                     seed_dev(lm_drop[1]))
             m = gemm(hl_out, sp_k, bias=sp_b) if sp_k is not None else hl_out
             pre = gemm(m, in_k[:Hd], bias=in_b)                          # [U*B, E]
             # decoder-LSTM kernel in gate-interleaved layout, with the ctx half of InputProjection folded in
@@ -959,7 +987,7 @@ class AttnDecoderFnV2(torch.autograd.Function):
             if ctx.lm_drop is not None:
                 dmd = torch.empty_like(dm)
                 call("e2e_dropout", dm.numel(), dm.contiguous(), dmd, float(ctx.lm_drop[0]), int(ctx.lm_drop[1]),
-                     int(ctx.lm_drop[2]), 0)
+                     int(ctx.lm_drop[2]), 0, seed_dev(ctx.lm_drop[1]))
                 dm = dmd
             call("e2e_lstm_rec_bwd", B, U, U, Hl, 1, 1, B, G_lm, C_lm, Wh_lm, dm, lens_i32, ctr,
                  ctr.numel() * 4, st["err"], work=float(U), tag="lm_rec_bwd")

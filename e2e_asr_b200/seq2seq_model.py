@@ -89,6 +89,11 @@ class Seq2SeqModel(BaseParams):
         self._loss_scale_value = None
         self._inflight = []
         self._adam = None
+        self._seed_dev = None
+        # loop bounds of the recurrences / decoder loop: False = the batch's maximum lengths (the reference's
+        # dynamic_rnn / raw_rnn semantics), True = the padded shapes with masked extra steps (one captured step per
+        # length bucket, GraphedStep(bucket=True))
+        self.shape_bounds = False
         if data_iter is not None:
             self.create_computational_graph()
 
@@ -185,6 +190,7 @@ class Seq2SeqModel(BaseParams):
                 batch = self.data_iter.get_next()
             prepared = self.get_batch(batch)
         self.encoder_inputs, self.decoder_inputs, self.seq_len, self.seq_len_target = prepared
+        self._stage_step_seed()
 
         if self.isTraining:
             # Bound the host's run-ahead to ONE step (step N+1 is enqueued while step N runs): tensors handed to
@@ -197,6 +203,27 @@ class Seq2SeqModel(BaseParams):
         self._step_core()
         if self.isTraining:
             self._step_tail()
+
+    def _step_seed_value(self):
+        """One Philox key per step: seed * 1000003 + global_step (see oracle train_step(dropout_seed=...))."""
+        # (data parallel: every rank draws its own masks)
+        rank = int(getattr(self.reducer, "rank", 0)) if self.reducer is not None else 0
+        return (int(self.params.get('dropout_seed', 0)) + 7919 * rank) * 1000003 + int(self.global_step)
+
+    def _stage_step_seed(self):
+        """Writes this step's Philox key into the device word the dropout kernels read (host -> device through the
+        pinned staging ring, asynchronous).  Done OUTSIDE a captured step, before it is launched: the captured kernels
+        hold the word's address, so every replay draws fresh masks."""
+        if self.device.type != "cuda" or not self.isTraining:
+            return
+        static, self._static_inputs = getattr(self, "_static_inputs", None), None
+        try:
+            fresh = self._to_device("step_seed", np.array([self._step_seed_value()], np.int64), torch.int64)
+        finally:
+            self._static_inputs = static
+        if self._seed_dev is None:
+            self._seed_dev = torch.zeros(1, dtype=torch.int64, device=self.device)
+        self._seed_dev.copy_(fresh, non_blocking=True)
 
     def _step_core(self):
         """Forward, losses and backward of one step on the inputs held in self.encoder_inputs / decoder_inputs:
@@ -215,12 +242,14 @@ class Seq2SeqModel(BaseParams):
         if self.isTraining and getattr(params, "overlap_weight_grads", True):
             ops.enable_wgrad_stream(self.device)
             ops.mark_step_start(self.device)
-        # one Philox key per step: seed * 1000003 + global_step (see oracle train_step(dropout_seed=...))
-        step_seed = int(params.get('dropout_seed', 0)) * 1000003 + int(self.global_step)
+        # the key is passed by value AND as the address of the device word holding it (ops.StepSeed)
+        step_seed = ops.StepSeed(self._step_seed_value(), self._seed_dev)
         self.encoder.dropout_seed = step_seed
+        self.encoder.shape_bounds = self.shape_bounds
         for i, task in enumerate(params.tasks):
             self.decoder[task].dropout_seed = step_seed
             self.decoder[task].dropout_stream = i
+            self.decoder[task].shape_bounds = self.shape_bounds
         depth_of = dict((t, params.num_layers[t]) for t in list(params.tasks) + list(params.ctc_tasks))
         ctx = torch.enable_grad() if self.isTraining else torch.no_grad()
         with ctx:
@@ -258,7 +287,8 @@ class Seq2SeqModel(BaseParams):
                         self.ctc_stash[task] = {"consumer_stream": main}
                         self.losses[task] = LossUtils.ctc_head_loss(
                             self.time_major_states[d], k, b, self.seq_len_encs[d], self.decoder_inputs[task],
-                            self.seq_len_target[task], self.ctc_stash[task])
+                            self.seq_len_target[task], self.ctc_stash[task],
+                            max_label_len=self.decoder_inputs[task].shape[1] if self.shape_bounds else None)
 
             ck("ctc heads forward")
             self.outputs = {}
@@ -318,9 +348,10 @@ class Seq2SeqModel(BaseParams):
 
     run_step = create_computational_graph
 
-    def graphed_step(self, batch):
-        """Captures the step for batches of this batch's shape in a CUDA graph; see GraphedStep."""
-        return GraphedStep(self, batch)
+    def graphed_step(self, batch, bucket=False):
+        """Captures the step for batches of this batch's shape in a CUDA graph; see GraphedStep.  bucket=True: one
+        captured step serves every batch that fits the shapes of `batch` (a length bucket)."""
+        return GraphedStep(self, batch, bucket=bucket)
 
     def _wait(self, event):
         """Blocks the host on a step-completion event; the time spent here is the host's slack (host_wait_s)."""
@@ -401,22 +432,27 @@ class GraphedStep(object):
     branches -- and replayed with one launch.  Inputs are refilled in place (pinned staging -> the static device
     buffers the captured kernels read); the gradient all-reduce, clipping and Adam stay eager after the replay.
 
-    Valid for batches with the captured shapes and the same maximum lengths; requires out_prob = out_prob_dec = 1
-    and samp_prob = 0 (their Philox keys are per-step kernel arguments).  `step(batch)` = Seq2SeqModel.run_step(batch).
+    Valid for batches with the captured shapes and the same maximum lengths.  Output dropout (out_prob, out_prob_dec
+    < 1) is captured: the mask kernels read the step's Philox key from a device word the host rewrites before every
+    replay.  Scheduled sampling (samp_prob > 0) is not (its ids are realised step by step from the host).
+    `step(batch)` = Seq2SeqModel.run_step(batch).
     """
 
-    def __init__(self, model, batch, warmup=2):
+    def __init__(self, model, batch, warmup=2, bucket=False):
         if not model.isTraining:
             raise ValueError("GraphedStep captures the training step")
+        self.bucket = bool(bucket)
         p = model.params
-        if p.encoder_params.out_prob < 1.0 or any(d.out_prob_dec < 1.0 or d.samp_prob > 0 for d in
-                                                   p.decoder_params.values()):
-            raise NotImplementedError("GraphedStep: dropout / scheduled sampling draw from per-step Philox keys "
-                                      "passed by value; use the eager run_step")
+        if any(d.samp_prob > 0 for d in p.decoder_params.values()):
+            raise NotImplementedError("GraphedStep: scheduled sampling realises its ids step by step from the host; "
+                                      "use the eager run_step")
         self.model = model
         model._static_inputs = {}
+        self.caps = {k: tuple(np.asarray(v).shape) for k, v in batch.items()
+                     if hasattr(v, "shape") and np.asarray(v).ndim >= 2}
         self.prepared = model.get_batch(batch)
         self.signature = self._signature(self.prepared)
+        model.shape_bounds = self.bucket or model.shape_bounds
         cur = torch.cuda.current_stream()
         # eager warm-up ON THE CAPTURE STREAM: lazy variables, workspaces, side streams and the allocator reach their
         # steady state, and autograd's cached gradient accumulators are bound to the stream that will be captured
@@ -464,13 +500,30 @@ class GraphedStep(object):
         self.launches_per_step = _launch_count() - n0
         cur.synchronize()
 
-    @staticmethod
-    def _signature(prepared):
+    def _signature(self, prepared):
+        """What a batch must share with the captured one: the tensor shapes and -- unless the step was captured for a
+        bucket, with loop bounds from the padded shapes -- the maximum lengths that bound its loops."""
         enc_in, dec_in, enc_len, dec_len = prepared
-        sig = [tuple(enc_in.shape), int(enc_len._host.max())]
+        sig = [tuple(enc_in.shape), None if self.bucket else int(enc_len._host.max())]
         for k in sorted(dec_len):
-            sig.append((k, tuple(dec_in[k].shape), int(dec_len[k]._host.max())))
+            sig.append((k, tuple(dec_in[k].shape), None if self.bucket else int(dec_len[k]._host.max())))
         return sig
+
+    def pad_to_bucket(self, batch):
+        """Zero / PAD-pads the batch's 2-D and 3-D arrays (logmel frames, id and label columns) up to the captured
+        shapes; lengths are untouched, so the padding is masked everywhere.  Raises if the batch does not fit."""
+        out = dict(batch)
+        for k, cap in self.caps.items():
+            v = batch[k]
+            v = v.cpu().numpy() if isinstance(v, torch.Tensor) else np.asarray(v)
+            if v.shape == cap:
+                continue
+            if len(v.shape) != len(cap) or v.shape[0] != cap[0] or any(a > b for a, b in zip(v.shape, cap)):
+                raise ValueError("GraphedStep: %s of shape %s does not fit the captured bucket %s" % (k, v.shape, cap))
+            padded = np.zeros(cap, v.dtype)
+            padded[tuple(slice(0, n) for n in v.shape)] = v
+            out[k] = padded
+        return out
 
     def prefetch(self, batch):
         """Starts the host -> device copy of the NEXT batch on a copy stream (into staging buffers, so it overlaps the
@@ -479,6 +532,8 @@ class GraphedStep(object):
         if getattr(self, "_copy_stream", None) is None:
             self._copy_stream = torch.cuda.Stream(device=model.device)
             self._staging, self._staged, self._consumed = {}, None, None
+        if self.bucket:
+            batch = self.pad_to_bucket(batch)
         if self._staged is not None:
             self._staged[1].synchronize()       # the pinned staging buffers are about to be rewritten
         if self._consumed is not None:
@@ -507,12 +562,15 @@ class GraphedStep(object):
             self._consumed.record()
             self._staged = None
         if batch is not None:
+            if self.bucket:
+                batch = self.pad_to_bucket(batch)
             prepared = model.get_batch(batch)          # refills the static buffers in place
             if self._signature(prepared) != self.signature or prepared[0] is not self.prepared[0]:
                 raise ValueError("GraphedStep: batch shape / maximum lengths differ from the captured step; capture "
                                  "one GraphedStep per shape bucket or use run_step")
         while len(model._inflight) >= 2:
             model._wait(model._inflight.pop(0))
+        model._stage_step_seed()               # this replay's dropout key
         self.graph.replay()
         model._step_tail()
 

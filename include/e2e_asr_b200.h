@@ -291,9 +291,11 @@ int e2e_gru_rec_bwd(void* stream, int B, int T, int Tp, int H, int ndir, float* 
 /* DropoutWrapper(output_keep_prob=keep) on a recurrent cell's outputs (encoder.py:50-52, decoder.py:60-63):
  * with i = first + (index into x), y = x / keep if philox4x32_10(counter = (i/4, offset, 0, 0), key = seed)[i%4]
  * * 2^-32 < keep else 0 (`first`, a multiple of 4, lets a slice of a buffer draw the buffer's mask).
- * Stateless: the backward pass calls it again on the upstream gradient with the same (seed, offset). */
+ * Stateless: the backward pass calls it again on the upstream gradient with the same (seed, offset).
+ * seed_dev (may be NULL): device address of the key; when given it REPLACES `seed`, so a step captured in a CUDA
+ * graph draws a fresh mask at every replay (the host rewrites the device word before launching the graph). */
 int e2e_dropout(void* stream, size_t n, const float* x, float* y, float keep, unsigned long long seed,
-                unsigned offset, size_t first);
+                unsigned offset, size_t first, const unsigned long long* seed_dev);
 
 /* Scheduled sampling (decoder.py:155-180, tf.multinomial(logits, 1)): out[r] = first index whose cumulative
  * exp(logit - max) (float64, index order) exceeds u_r * total, u_r = word 0 of

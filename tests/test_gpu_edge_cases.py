@@ -145,3 +145,33 @@ def test_distinct_batches_back_to_back_from_host(graph):
             assert abs(g - expect[i % 4]) <= 1e-6 * abs(expect[i % 4]), (i, g, expect[i % 4])
     finally:
         ops.set_gemm_mode("fp32")
+
+
+def test_one_captured_step_serves_a_length_bucket():
+    """The reference's training loop draws batches from length buckets (train.py:44,108-119): every batch of a bucket
+    has its own maximum lengths.  GraphedStep(bucket=True) derives the loop bounds of the recurrences, the decoder loop
+    and the CTC state space from the PADDED shapes (the extra steps are masked), so ONE captured step is replayed on
+    batches with different maxima, each padded to the bucket's shapes -- and each must meet the oracle's result for the
+    unpadded batch."""
+    import torch
+    cfg = synth.get_config("tiny_b")
+    w = synth.make_weights(cfg, bias_noise=0.1)
+    cap = crafted_batch(cfg, [37, 30, 21, 37, 12], [9, 4, 9, 2, 6], seed=1)          # the bucket's bounds
+    batches = [crafted_batch(cfg, [29, 30, 21, 8, 12], [5, 4, 7, 2, 6], seed=2),      # shorter maxima (odd)
+               crafted_batch(cfg, [4, 3, 2, 1, 5], [1, 2, 1, 1, 3], seed=3),          # far below the bounds
+               cap]
+    model = build_model(cfg, w, device="cuda:0")
+    step = model.graphed_step(cap, bucket=True)
+    for b in batches * 2:
+        ref = om.train_step(w, b, num_layers={"char": cfg.L}, ctc_tasks=cfg.ctc)
+        step(b)
+        torch.cuda.synchronize()
+        ops.check_device_errors("cuda:0")
+        compare_step(model, ref, rtol=1e-4, check_logits=False)
+        U = int(b["char_len"].max())
+        got = model.outputs["char"].detach().cpu().numpy().reshape(-1, len(b["char_len"]), cfg.V)
+        assert np.abs(got[:U].reshape(-1, cfg.V) - ref["logits"]["char"]).max() <= 1e-4 * np.abs(ref["logits"]["char"]).max()
+        assert not got[U:].any()                       # padded steps emit zeros (finished rows, raw_rnn)
+    too_long = crafted_batch(cfg, [38, 30, 21, 37, 12], [9, 4, 9, 2, 6], seed=4)
+    with pytest.raises(ValueError, match="does not fit"):
+        step(too_long)

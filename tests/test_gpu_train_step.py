@@ -105,8 +105,9 @@ def test_greedy_decode_ids_bit_exact(cname):
     assert e < 1e-4
 
 
+@pytest.mark.parametrize("impl", ["persist", "loop"])
 @pytest.mark.parametrize("cname", ["tiny_b", "cfg1"])
-def test_train_step_with_dropout_matches_oracle(cname):
+def test_train_step_with_dropout_matches_oracle(cname, impl):
     """out_prob / out_prob_dec < 1 (the reference's training defaults are 0.9): the Philox masks are a builder-defined
     stateless function of (seed, stream, flat index), restated in the oracle, so the dropped step must meet the same
     1e-4 bar.  The second step uses another key (global_step is mixed in)."""
@@ -117,14 +118,43 @@ def test_train_step_with_dropout_matches_oracle(cname):
     model.params.encoder_params.out_prob = 0.8
     model.params.decoder_params["char"].out_prob_dec = 0.7
     model.params.dropout_seed = 11
-    for step in range(2):
-        model.run_step(batch)
-        ops.check_device_errors("cuda:0")
-        ref = om.train_step(w, batch, num_layers={"char": cfg.L}, ctc_tasks=cfg.ctc, out_prob=0.8, out_prob_dec=0.7,
-                            dropout_seed=11 * 1000003 + step)
-        compare_step(model, ref, rtol=RTOL)
+    ops.set_decoder_impl(impl)            # the persistent decoder kernels and the per-step fallback (D = 1024 shapes)
+    try:
+        for step in range(2):
+            model.run_step(batch)
+            ops.check_device_errors("cuda:0")
+            ref = om.train_step(w, batch, num_layers={"char": cfg.L}, ctc_tasks=cfg.ctc, out_prob=0.8,
+                                out_prob_dec=0.7, dropout_seed=11 * 1000003 + step)
+            compare_step(model, ref, rtol=RTOL)
+    finally:
+        ops.set_decoder_impl("persist")
     nodrop = om.train_step(w, batch, num_layers={"char": cfg.L}, ctc_tasks=cfg.ctc)
     assert abs(ref["total_loss"] - nodrop["total_loss"]) > 1e-3
+
+
+@pytest.mark.parametrize("cname", ["tiny_b", "cfg1"])
+def test_graphed_step_with_dropout_draws_a_new_mask_every_replay(cname):
+    """The reference's training defaults keep 0.9 of the outputs: the step captured WITH dropout must draw the mask
+    of ITS step at every replay -- the kernels read the Philox key from a device word rewritten before each launch --
+    and each replay must meet the 1e-4 bar against the oracle run with that step's key."""
+    cfg = synth.get_config(cname)
+    w = synth.make_weights(cfg, bias_noise=0.1)
+    batch = synth.make_batch(cfg)
+    model = build_model(cfg, w, device="cuda:0")
+    model.params.encoder_params.out_prob = 0.9
+    model.params.decoder_params["char"].out_prob_dec = 0.9
+    model.params.dropout_seed = 7
+    gs = model.graphed_step(batch)
+    assert model.global_step == 0
+    losses = []
+    for step in range(3):
+        gs.step(batch)
+        ops.check_device_errors("cuda:0")
+        ref = om.train_step(w, batch, num_layers={"char": cfg.L}, ctc_tasks=cfg.ctc, out_prob=0.9, out_prob_dec=0.9,
+                            dropout_seed=7 * 1000003 + step)
+        compare_step(model, ref, rtol=RTOL)
+        losses.append(ref["total_loss"])
+    assert len(set(round(l, 5) for l in losses)) == 3          # three different masks
 
 
 @pytest.mark.parametrize("cname,keep", [("tiny_b", 1.0), ("tiny_b", 0.7), ("cfg1", 0.9)])
