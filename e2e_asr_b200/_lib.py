@@ -38,7 +38,7 @@ _SIGS = {
     "e2e_row_lse": "piipip",
     "e2e_ctc_fwd_grad": "piiillppppipipppf",
     "e2e_sumsq": "pzpppfi",
-    "e2e_clip_by_norm": "pzppfp",
+    "e2e_clip_by_norm": "pzppfpfp",
     "e2e_scale": "pzppf",
     "e2e_mean": "pipp",
     "e2e_axpy": "pzfpp",

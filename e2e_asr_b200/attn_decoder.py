@@ -117,8 +117,25 @@ class AttnDecoder(Decoder):
             drop = None
             if self.isTraining and self.params.out_prob_dec < 1.0:
                 drop = (self.params.out_prob_dec, getattr(self, "dropout_seed", 0), getattr(self, "dropout_stream", 0))
-            return ops.attn_decoder_stepwise(enc, v, v["lm_cells"], v["dec_cells"], self.params.use_lstm, decoder_inp,
-                                             lens, enc_len, U, self.stash, drop=drop)
+            cells = (enc, v, v["lm_cells"], v["dec_cells"], self.params.use_lstm)
+            if rule == "greedy":        # eval mode: U = max_output steps for every row (seq2seq_model.py:191-193)
+                with torch.no_grad():
+                    return ops.attn_decoder_stepwise(*cells, decoder_inp, lens, enc_len, U, None, feedback="greedy")
+            if rule == "sample":
+                # scheduled sampling as for the single cell: realise the input ids without a tape (same Philox
+                # streams), then take the teacher-forced step on them
+                from .host_utils import philox_uniform
+                seed, stream = getattr(self, "dropout_seed", 0), getattr(self, "dropout_stream", 0)
+                use = [False] + [not (philox_uniform(t, 200 + stream, seed) < 1.0 - self.params.samp_prob)
+                                 for t in range(1, U)]
+                ids = decoder_inp[:U].clone()
+                if any(use):
+                    last = max(t for t in range(U) if use[t])
+                    with torch.no_grad():
+                        ops.attn_decoder_stepwise(*cells, decoder_inp, lens, enc_len, last, None, drop=drop,
+                                                  feedback=dict(use_sample=use, seed=seed, offset=300 + stream, ids=ids))
+                decoder_inp = self.stash["realized_ids"] = ids
+            return ops.attn_decoder_stepwise(*cells, decoder_inp, lens, enc_len, U, self.stash, drop=drop)
         if rule in ("teacher", "sample"):
             # DropoutWrapper(output_keep_prob=out_prob_dec) iff training (decoder.py:60-63) acts on lm_cell's
             # output only: raw_loop_function reads the decoder cell through get_state(state) = state.c and never

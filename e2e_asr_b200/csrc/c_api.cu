@@ -65,7 +65,7 @@ int ctc_fwd_grad(cudaStream_t, int, int, int, long long, long long, const float*
                  const long long*, int, const int*, int, float*, float*, float*, float);
 size_t ctc_workspace_floats(int, int, int);
 int sumsq(cudaStream_t, size_t, const float*, float*, float*, float, int);
-int clip_by_norm(cudaStream_t, size_t, float*, const float*, float, float*);
+int clip_by_norm(cudaStream_t, size_t, float*, const float*, float, float*, float, const int*);
 int scale_inplace(cudaStream_t, size_t, float*, const float*, float);
 int mean_vec(cudaStream_t, int, const float*, float*);
 int axpy(cudaStream_t, size_t, float, const float*, float*);
@@ -356,8 +356,9 @@ size_t e2e_ctc_workspace_floats(int T, int B, int max_label_len) { return ctc_wo
 int e2e_sumsq(void* stream, size_t n, const float* x, float* partials296, float* out, float sign, int accumulate) {
     return sumsq(ST(stream), n, x, partials296, out, sign, accumulate);
 }
-int e2e_clip_by_norm(void* stream, size_t n, float* x, const float* sq, float clip, float* norm_out) {
-    return clip_by_norm(ST(stream), n, x, sq, clip, norm_out);
+int e2e_clip_by_norm(void* stream, size_t n, float* x, const float* sq, float clip, float* norm_out, float pre_scale,
+                     const int* err_flag) {
+    return clip_by_norm(ST(stream), n, x, sq, clip, norm_out, pre_scale, err_flag);
 }
 int e2e_scale(void* stream, size_t n, float* x, const float* dev_scalar, float a) {
     return scale_inplace(ST(stream), n, x, dev_scalar, a);

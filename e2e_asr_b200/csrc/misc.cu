@@ -75,17 +75,22 @@ int sumsq(cudaStream_t st, size_t n, const float* x, float* partials, float* out
     return 0;
 }
 
-// tf.clip_by_global_norm: x *= clip / max(sqrt(sumsq), clip); norm_out[0] = sqrt(sumsq)
+// tf.clip_by_global_norm: x *= pre * clip / max(sqrt(sumsq), clip); norm_out[0] = sqrt(sumsq).
+// pre: the 1/n of a data-parallel SUM of rank gradients (sumsq is then the caller's sum of squares / n^2), folded in so
+// that averaging costs no pass of its own.  err (may be NULL): the persistent kernels' barrier-timeout flag -- a step
+// whose recurrence gave up on a barrier has garbage gradients: they are zeroed and the norm reads NaN.
 __global__ void clip_scale_kernel(size_t n, float* __restrict__ x, const float* __restrict__ sq, float clip,
-                                  float* __restrict__ norm_out) {
+                                  float* __restrict__ norm_out, float pre, const int* __restrict__ err) {
     float norm = sqrtf(fmaxf(sq[0], 0.f));
-    float scale = clip / fmaxf(norm, clip);
+    float scale = pre * clip / fmaxf(norm, clip);
+    if (err != nullptr && *err != 0) { scale = 0.f; norm = __int_as_float(0x7fc00000); }
     if (blockIdx.x == 0 && threadIdx.x == 0 && norm_out) norm_out[0] = norm;
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
         x[i] *= scale;
 }
-int clip_by_norm(cudaStream_t st, size_t n, float* x, const float* sq, float clip, float* norm_out) {
-    clip_scale_kernel<<<SUMSQ_BLOCKS, 256, 0, st>>>(n, x, sq, clip, norm_out);
+int clip_by_norm(cudaStream_t st, size_t n, float* x, const float* sq, float clip, float* norm_out, float pre,
+                 const int* err) {
+    clip_scale_kernel<<<SUMSQ_BLOCKS, 256, 0, st>>>(n, x, sq, clip, norm_out, pre, err);
     E2E_LAUNCH_CHECK();
     return 0;
 }

@@ -35,14 +35,10 @@ class Decoder(BaseParams):
         if p.num_layers_dec < 1:
             raise ValueError("Decoder: num_layers_dec=%d must be >= 1" % p.num_layers_dec)
         if self.general_cells():
-            # MultiRNNCell stacks / GRU cells run the step-by-step path (ops.attn_decoder_stepwise): teacher forcing
-            # (with output dropout); scheduled sampling and the eval-mode loop are built for the single LSTM cell
-            if self.isTraining and p.samp_prob > 0:
-                raise NotImplementedError("Decoder: num_layers_dec > 1 / use_lstm=False are built for samp_prob=0")
+            # MultiRNNCell stacks / GRU cells run the step-by-step path (ops.attn_decoder_stepwise) for every input
+            # rule: teacher forcing, scheduled sampling, eval-mode greedy feedback; output dropout
             if self.isTraining and p.out_prob_dec < 1.0 and (p.lm_hidden_size % 4 or p.hidden_size_dec % 4):
                 raise NotImplementedError("Decoder: dropout needs hidden sizes that are multiples of 4")
-            if not self.isTraining:
-                raise NotImplementedError("Decoder: greedy decoding is built for the single LSTM cell")
         if not (0.0 < p.out_prob_dec <= 1.0):
             raise ValueError("Decoder: out_prob_dec=%g must be in (0, 1]" % p.out_prob_dec)
         if not (0.0 <= p.samp_prob <= 1.0):

@@ -48,11 +48,18 @@ def shard_batch(batch, rank, world):
 
 
 class GradAllReducer(object):
-    """Averages the flat gradient buffer across ranks.
+    """Sums the flat gradient buffer across ranks, in the order the gradients become final during backward.
 
-    `allreduce_mean(flat)` issues one NCCL allreduce per bucket on a side stream and
-    makes the compute stream wait for it, so it overlaps whatever the compute stream
-    still has queued (the remaining backward when called per bucket)."""
+    The parameters of the model live in ONE flat buffer laid out in creation order: encoder layer 1 .. L, auxiliary
+    heads, decoder (variables.py).  During backward the decoder's gradients are final first, then encoder layer L ..
+    1; each group's weight-gradient GEMMs run on a side stream and `grad_ready(views, stream)` (the hook of
+    ops.set_grad_ready_hook) starts the all-reduce of THAT span on the reducer's stream as soon as the side stream
+    has produced it -- overlapping the remaining backward.  `finish()` reduces whatever was not
+    covered (auxiliary heads, plain-autograd paths) together with `extra` trailing floats (scalars that ride along,
+    e.g. the IndexedSlices norm term) and joins the compute stream.  The buffer then holds the SUM over ranks; the
+    1/n is folded into the clipping kernel (e2e_clip_by_norm pre_scale).  All of it is plain stream-ordered work:
+    inside a CUDA-graph capture the collectives become graph nodes, so a replayed step contains its all-reduces.
+    """
 
     def __init__(self, group=None, bucket_elems=16 * 1024 * 1024):
         self.group = group
@@ -60,29 +67,72 @@ class GradAllReducer(object):
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
         self.bucket_elems = bucket_elems
         self.stream = torch.cuda.Stream() if torch.cuda.is_available() else None
+        self.flat = None
+        self.covered = []
+        self.collectives = 0
 
+    # ---- overlapped, readiness-ordered path
+    def begin_step(self, flat):
+        """`flat`: the whole flat gradient buffer (views passed to grad_ready are spans of it)."""
+        self.flat = flat
+        self.covered = []
+
+    def _reduce_span(self, lo, hi, after=None):
+        if hi <= lo:
+            return
+        chunk = self.flat[lo:hi]
+        if self.stream is None:
+            dist.all_reduce(chunk, op=dist.ReduceOp.SUM, group=self.group)
+        else:
+            self.stream.wait_stream(after if after is not None else torch.cuda.current_stream())
+            with torch.cuda.stream(self.stream):
+                dist.all_reduce(chunk, op=dist.ReduceOp.SUM, group=self.group)
+        self.collectives += 1
+
+    def grad_ready(self, views, stream=None):
+        """The gradient views (spans of the flat buffer) are final once `stream` reaches this point."""
+        if self.world_size == 1 or self.flat is None or not views:
+            return
+        base = self.flat.storage_offset()
+        lo = min(v.storage_offset() for v in views) - base
+        hi = max(v.storage_offset() + v.numel() for v in views) - base
+        # the span between the first and the last view must belong to this group alone (contiguous creation order)
+        if any(not (hi <= a or b <= lo) for a, b in self.covered):
+            return                                  # overlaps something already reduced: leave it to finish()
+        self.covered.append((lo, hi))
+        self._reduce_span(lo, hi, after=stream)
+
+    def finish(self, used, extra=0):
+        """Reduces every span of [0, used + extra) not covered by grad_ready and makes the current stream wait for all
+        collectives of the step.  Returns the list of spans reduced here."""
+        if self.world_size == 1 or self.flat is None:
+            return []
+        rest, pos = [], 0
+        for a, b in sorted(self.covered):
+            if a > pos:
+                rest.append((pos, a))
+            pos = max(pos, b)
+        if pos < used + extra:
+            rest.append((pos, used + extra))
+        for a, b in rest:
+            for o in range(a, b, self.bucket_elems):
+                self._reduce_span(o, min(b, o + self.bucket_elems))
+        if self.stream is not None:
+            torch.cuda.current_stream().wait_stream(self.stream)
+        self.covered = []
+        return rest
+
+    # ---- plain paths
     def allreduce_sum(self, t):
         if self.world_size > 1:
             dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group)
         return t
 
     def allreduce_mean(self, flat):
+        """One blocking pass: sum over ranks, divided by n (host-logic tests and non-overlapped callers)."""
         if self.world_size == 1:
             return flat
-        n = flat.numel()
-        if self.stream is None:
-            for o in range(0, n, self.bucket_elems):
-                chunk = flat[o:o + self.bucket_elems]
-                dist.all_reduce(chunk, op=dist.ReduceOp.SUM, group=self.group)
-                chunk.div_(self.world_size)
-            return flat
-        from ._lib import call
-        cur = torch.cuda.current_stream()
-        self.stream.wait_stream(cur)
-        with torch.cuda.stream(self.stream):
-            for o in range(0, n, self.bucket_elems):
-                chunk = flat[o:o + self.bucket_elems]
-                dist.all_reduce(chunk, op=dist.ReduceOp.SUM, group=self.group)
-                call("e2e_scale", chunk.numel(), chunk, None, 1.0 / self.world_size)
-        cur.wait_stream(self.stream)
+        self.begin_step(flat)
+        self.finish(flat.numel())
+        flat.div_(self.world_size)
         return flat

@@ -292,6 +292,17 @@ def enable_wgrad_stream(device, enabled=True):
 
 _STEP_START = {}
 
+# Data parallelism: called as hook(grad_views, stream) when a group of parameter gradients is FINAL in the flat gradient
+# buffer (all accumulation into those views has been enqueued on `stream`): the encoder layers' weight gradients on the
+# "enc" stream, the decoder's on the "dec" stream.  dist.GradAllReducer starts that span's all-reduce from there, so the
+# collective overlaps the rest of the backward pass.
+_GRAD_READY_HOOK = None
+
+
+def set_grad_ready_hook(fn):
+    global _GRAD_READY_HOOK
+    _GRAD_READY_HOOK = fn
+
 
 def mark_step_start(device):
     """Records "the step's inputs and parameters are ready" on the current stream.  Work that depends on nothing
@@ -384,6 +395,8 @@ class BiLSTMLayerFn(torch.autograd.Function):
             for t_ in (x, G, out, x_lo, G_lo):
                 if t_ is not None:
                     t_.record_stream(side)
+            if _GRAD_READY_HOOK is not None:
+                _GRAD_READY_HOOK(dst, side)
             return dX, None, None, None, None, None, None
         dWx, dWh, dbp = weight_grads()
         return (dX,) + tuple(_unpack_lstm(dWx, dWh, dbp, I, H, nd, dev)) + pad + (None, None)
@@ -607,7 +620,7 @@ def _cell_step(use_lstm, x, state, ws):
 
 
 def attn_decoder_stepwise(enc, v, lm_cells, dec_cells, use_lstm, ids, lens_i32, enc_len_i32, U, stash=None,
-                          drop=None):
+                          drop=None, feedback=None):
     """AttnDecoder.__call__ (attn_decoder.py:37-172) under teacher forcing for ANY decoder.py cell configuration:
     `lm_cells` / `dec_cells` are lists (one entry per stacked layer) of the cell's variables -- (kernel, bias) for
     BasicLSTMCell, (gates kernel, gates bias, candidate kernel, candidate bias) for GRUCell.  The attention query and
@@ -618,6 +631,10 @@ def attn_decoder_stepwise(enc, v, lm_cells, dec_cells, use_lstm, ids, lens_i32, 
     InputProjection, the states are not; the top decoder layer's output is never read.  Philox streams: 100 + task
     for the top lm layer (as for the single cell), 500 + 16 task + l for lower lm layers, 400 + 16 task + l for the
     decoder layers; the mask of step t is the slice [t*B, (t+1)*B) of a [U*B, H] mask.
+    feedback: None = teacher forcing (step t reads ids[t]); "greedy" = eval mode, step t+1 embeds argmax of step t's
+    emit (decoder.py:139-153); a dict(use_sample, seed, offset, ids) = the scheduled-sampling rule of
+    inference.sample_decode_ids: after step t the input of step t+1 is written to feedback["ids"][t+1] (run without a
+    tape; the training step then takes the teacher-forced path on the realised ids).
     Returns logits [(U*B), V]."""
     dev = enc.device
     B, Tn, D = enc.shape
@@ -627,7 +644,9 @@ def attn_decoder_stepwise(enc, v, lm_cells, dec_cells, use_lstm, ids, lens_i32, 
     Hl = lm_cells[0][-1].shape[0] // (4 if use_lstm else 1)
     Hd = dec_cells[0][-1].shape[0] // (4 if use_lstm else 1)
     HF = LinearFn.apply(enc_flat, v["attn_w"].view(D, A), None)
-    u_all = EmbedFn.apply(v["emb"], ids[:U], stash).view(U, B, -1)
+    V = v["out_k"].shape[1]
+    u_all = EmbedFn.apply(v["emb"], ids[:U], stash).view(U, B, -1) if feedback is None else None
+    tok = ids[0].contiguous()
     zero = (lambda H: (torch.zeros((B, H), **f32), torch.zeros((B, H), **f32))) if use_lstm else \
         (lambda H: (torch.zeros((B, H), **f32),))
     lm_state = [zero(Hl) for _ in lm_cells]
@@ -638,7 +657,7 @@ def attn_decoder_stepwise(enc, v, lm_cells, dec_cells, use_lstm, ids, lens_i32, 
     dims = (B, Tn, Tp, A, D)
     outs = []
     for t in range(U):
-        x = u_all[t]
+        x = u_all[t] if feedback is None else EmbedFn.apply(v["emb"], tok, None)
         for l, ws in enumerate(lm_cells):                                     # lm_cell stack (attn_decoder.py:148)
             x, lm_state[l] = _cell_step(use_lstm, x, lm_state[l], ws)
             if drop is not None:
@@ -661,6 +680,14 @@ def attn_decoder_stepwise(enc, v, lm_cells, dec_cells, use_lstm, ids, lens_i32, 
         outs.append(torch.where(live, lg, torch.zeros_like(lg)))
         dec_state = [tuple(torch.where(live, a_, b_) for a_, b_ in zip(new_state[l], dec_state[l]))
                      for l in range(len(dec_cells))]
+        if feedback == "greedy":                       # argmax of the EMIT (zero for finished rows), decoder.py:148-151
+            tok = torch.empty((B,), dtype=torch.int64, device=dev)
+            call("e2e_argmax_rows", B, V, outs[-1].contiguous(), V, tok)
+        elif feedback is not None and t + 1 < feedback["ids"].shape[0]:
+            tok = feedback["ids"][t + 1]
+            if feedback["use_sample"][t + 1]:          # multinomial over the previous step's (unmasked) logits
+                call("e2e_sample_rows", B, V, lg.contiguous(), V, int(feedback["seed"]), int(feedback["offset"]),
+                     (t + 1) * B, tok)
     return torch.cat(outs, dim=0)
 
 
@@ -1018,6 +1045,8 @@ class AttnDecoderFnV2(torch.autograd.Function):
                 for d, g in zip(dst, grads):
                     if g is not None:
                         d.add_(g.view(d.shape))     # what AccumulateGrad would do, on the side stream
+            if _GRAD_READY_HOOK is not None:
+                _GRAD_READY_HOOK([d for d in dst if d is not None], side)
             if ctx.stash is not None and ctx.stash.get("emb_values") is not None:
                 ctx.stash["emb_values"].record_stream(main)      # read by clip_gradients after the join
             for t_ in list(ctx.saved_tensors) + [dlogits, dproj, dz, dy, dv_part, dHF] + [g for g in grads if g is not None]:

@@ -319,21 +319,36 @@ class Seq2SeqModel(BaseParams):
             self._loss_scale_value = scale
         roots = [self.losses[t] for t in self.losses]
         ck("losses")
-        torch.autograd.backward(roots, [self._loss_scale] * len(roots))
+        dp = self.reducer is not None and self.reducer.world_size > 1
+        if dp:
+            # data parallel: every group of weight gradients is all-reduced from the side stream that produced it,
+            # while the rest of the backward pass runs (dist.GradAllReducer)
+            self.reducer.begin_step(self.variables.gflat)
+            ops.set_grad_ready_hook(self.reducer.grad_ready)
+        try:
+            torch.autograd.backward(roots, [self._loss_scale] * len(roots))
+        finally:
+            ops.set_grad_ready_hook(None)
         ck("backward")
         for side in sides:
             main.wait_stream(side)
         ops.sync_wgrad_stream(self.device)
         ck("joins")
+        if dp:
+            # what is left (auxiliary heads, encoder layer 1 if its hook did not fire) + one trailing float: the sum of
+            # squares of the embedding gradient's IndexedSlices values, which tf.global_norm needs summed over ranks
+            vs = self.variables
+            self._emb_sq_local()
+            vs.gflat[vs.used:vs.used + 1].copy_(self._sq_emb)
+            self.reducer.finish(vs.used, extra=1)
         with torch.no_grad():
             self.total_loss = torch.stack([l.detach() for l in roots]).sum() * scale
         ck("total_loss")
 
     def _step_tail(self):
-        """Gradient all-reduce, clipping, optional Adam, step bookkeeping (seq2seq_model.py:148-155)."""
+        """Clipping (with the data-parallel 1/n folded in), optional Adam, step bookkeeping (seq2seq_model.py:148-155).
+        The gradient all-reduce itself is part of _step_core: it overlaps the backward pass."""
         params = self.params
-        if self.reducer is not None:
-            self.reducer.allreduce_mean(self.variables.flat_grads())
         self.clip_gradients()
         self.updates = self.variables
         if params.get('apply_updates', False):
@@ -360,31 +375,50 @@ class Seq2SeqModel(BaseParams):
         event.synchronize()
         self.host_wait_s = getattr(self, "host_wait_s", 0.0) + time.perf_counter() - t0
 
-    def clip_gradients(self):
-        """tf.clip_by_global_norm(gradients, max_gradient_norm) over the flat buffer.
-        With `tf_indexed_slices_norm` the embedding gradient enters the norm as TF's
-        IndexedSlices values (one row per looked-up token, duplicates not summed)."""
-        vs = self.variables
+    def _emb_sq_local(self):
+        """Sum of squares of this rank's embedding-gradient IndexedSlices values (one row per looked-up token,
+        duplicates not summed: what tf.global_norm sees) -> self._sq_emb; False if there are none."""
         st = ops._dev_state(self.device)
-        g = vs.flat_grads()
-        call("e2e_sumsq", g.numel(), g, st["partials"], self._sq, 1.0, 0)
+        first = True
         if self.params.tf_indexed_slices_norm:
-            first = True
             for task in self.params.tasks:
                 du = self.decoder[task].stash.get("emb_values")
                 if du is None:
                     continue
-                ge = vs.grad(self.decoder[task].scope_name() + "/decoder/embedding")
-                call("e2e_sumsq", ge.numel(), ge, st["partials"], self._sq, -1.0, 1)
                 call("e2e_sumsq", du.numel(), du, st["partials"], self._sq_emb, 1.0, 0 if first else 1)
                 first = False
-            if not first:
-                n = 1
-                if self.reducer is not None:       # values of all ranks, each scaled by 1/n
-                    self.reducer.allreduce_sum(self._sq_emb)
-                    n = self.reducer.world_size
-                call("e2e_axpy", 1, 1.0 / (n * n), self._sq_emb, self._sq)
-        call("e2e_clip_by_norm", g.numel(), g, self._sq, float(self.params.max_gradient_norm), self.grad_norm)
+        if first:
+            self._sq_emb.zero_()
+        return not first
+
+    def clip_gradients(self):
+        """tf.clip_by_global_norm(gradients, max_gradient_norm) over the flat buffer.
+        With `tf_indexed_slices_norm` the embedding gradient enters the norm as TF's
+        IndexedSlices values (one row per looked-up token, duplicates not summed).
+        Data parallel: the buffer holds the SUM of the n rank gradients; the norm of their mean is taken with
+        sign = 1/n^2 and the 1/n itself is the clipping kernel's pre-scale (no averaging pass)."""
+        vs = self.variables
+        st = ops._dev_state(self.device)
+        g = vs.flat_grads()
+        n = self.reducer.world_size if self.reducer is not None else 1
+        inv2 = 1.0 / float(n * n)
+        call("e2e_sumsq", g.numel(), g, st["partials"], self._sq, inv2, 0)
+        if self.params.tf_indexed_slices_norm:
+            have = False
+            for task in self.params.tasks:
+                if self.decoder[task].stash.get("emb_values") is None:
+                    continue
+                ge = vs.grad(self.decoder[task].scope_name() + "/decoder/embedding")
+                call("e2e_sumsq", ge.numel(), ge, st["partials"], self._sq, -inv2, 1)
+                have = True
+            if have:
+                if n > 1:       # summed over ranks with the gradients (the float behind the flat buffer)
+                    call("e2e_axpy", 1, inv2, vs.gflat[vs.used:vs.used + 1], self._sq)
+                else:
+                    self._emb_sq_local()
+                    call("e2e_axpy", 1, 1.0, self._sq_emb, self._sq)
+        call("e2e_clip_by_norm", g.numel(), g, self._sq, float(self.params.max_gradient_norm), self.grad_norm,
+             1.0 / float(n), st["err"])
 
     def apply_gradients(self, beta1=0.9, beta2=0.999, epsilon=1e-8):
         """tf.train.AdamOptimizer(self.learning_rate).apply_gradients(clipped gradients) (seq2seq_model.py:137,

@@ -262,9 +262,14 @@ int e2e_logsoftmax_topk_f64(void* stream, int n, int V, const double* logits, co
                             double* scratch);
 int e2e_embed_gather_f64(void* stream, int n, int E, const float* emb, const long long* ids, double* out, int ldo);
 
-/* tf.clip_by_global_norm (seq2seq_model.py:150-151) on the flat gradient buffer */
+/* tf.clip_by_global_norm (seq2seq_model.py:150-151) on the flat gradient buffer:
+ * sumsq: out (+)= sign * sum x^2; clip: x *= pre_scale * clip / max(sqrt(sumsq), clip), norm_out = sqrt(sumsq).
+ * pre_scale = 1/n folds the averaging of a data-parallel SUM of n rank gradients into the clipping pass (sumsq is
+ * then taken with sign = 1/n^2).  err_flag (may be NULL): the persistent kernels' barrier-timeout flag; when set the
+ * gradients are zeroed and norm_out reads NaN instead of garbage being applied. */
 int e2e_sumsq(void* stream, size_t n, const float* x, float* partials296, float* out, float sign, int accumulate);
-int e2e_clip_by_norm(void* stream, size_t n, float* x, const float* sumsq, float clip, float* norm_out);
+int e2e_clip_by_norm(void* stream, size_t n, float* x, const float* sumsq, float clip, float* norm_out,
+                     float pre_scale, const int* err_flag);
 int e2e_scale(void* stream, size_t n, float* x, const float* dev_scalar, float a);
 int e2e_mean(void* stream, int n, const float* x, float* out);
 int e2e_axpy(void* stream, size_t n, float a, const float* x, float* y);   /* y += a*x */

@@ -66,6 +66,43 @@ def load_reference(tf):
     return mods
 
 
+def run_decoder_modes_general():
+    """graph_modes_general.npz: eval mode and scheduled sampling (as run_decoder_modes) for the decoder's OTHER cell
+    configurations (decoder.py:49-72): a 2-layer MultiRNNCell of LSTM cells and GRU cells."""
+    from oracle import model as om
+    out = {}
+    for cname in ("tiny_dec2", "tiny_decgru"):
+        cfg = synth.get_config(cname)
+        w = synth.make_weights(cfg, bias_noise=0.1)
+        w["model/rnn_decoder_char/rnn/OutputProjection/kernel"] = w["model/rnn_decoder_char/rnn/OutputProjection/kernel"] * 6.0
+        batch = synth.make_batch(cfg)
+        W64 = {k: v.astype(np.float64) for k, v in w.items()}
+        states, lens_d, _ = om.encoder_fwd(W64, batch["logmel"].astype(np.float64), batch["logmel_len"], {"char": cfg.L})
+        for mode in ("eval", "sample"):
+            tf = np_tf.make_tf(w)
+            mods = load_reference(tf)
+            dp = mods["attn_decoder"].AttnDecoder.class_params()
+            dp.hidden_size_dec, dp.emb_size, dp.vocab_size = cfg.Hd, cfg.E, cfg.V
+            dp.attention_vec_size, dp.lm_hidden_size, dp.max_output = cfg.A, cfg.Hl, cfg.U
+            dp.num_layers_dec, dp.use_lstm = int(cfg.get("dec_layers", 1)), bool(cfg.get("dec_lstm", True))
+            dp.out_prob_dec, dp.samp_prob = 1.0, 0.5 if mode == "sample" else 0.0
+            seed, task_index, B = 91, 0, cfg.B
+            if mode == "sample":
+                w0 = lambda step: float(om.philox4x32_10(np.array([step], np.uint64), np.array([200 + task_index], np.uint64),
+                                                         np.zeros(1, np.uint64), np.zeros(1, np.uint64), seed & 0xFFFFFFFF,
+                                                         (seed >> 32) & 0xFFFFFFFF)[0][0]) * 2.0 ** -32
+                tf._draws = dict(uniform=w0, multinomial=lambda step, lg: om.sample_rows(lg, seed, 300 + task_index, step * B))
+            seq_len = batch["char_len"] if mode == "sample" else np.full(cfg.B, cfg.U, np.int64)
+            with tf.variable_scope("model"):
+                dec = mods["attn_decoder"].AttnDecoder(isTraining=(mode == "sample"), params=dp, scope="char")
+                logits = dec(np_tf.t(np.ascontiguousarray(batch["char"].T)), np_tf.t(seq_len), np_tf.t(states[cfg.L]),
+                             np_tf.t(lens_d[cfg.L]))
+            out["%s/%s/logits" % (cname, mode)] = np.asarray(logits)
+    out["seed"] = np.array(91)
+    np.savez(os.path.join(HERE, "graph_modes_general.npz"), **out)
+    return out
+
+
 def run_decoder_modes():
     """graph_modes.npz: the reference decoder in eval mode (greedy feedback through _get_argmax, lengths = max_output,
     seq2seq_model.py:191-193) and in training mode with scheduled sampling (samp_prob = 0.5; the scalar uniform draw
@@ -351,6 +388,8 @@ def run_case(case):
 if __name__ == "__main__":
     o = run_decoder_modes()
     print("modes", {k: v.shape for k, v in o.items()})
+    o = run_decoder_modes_general()
+    print("modes (general cells)", {k: v.shape for k, v in o.items()})
     o = run_cfg1()
     print("cfg1", "loss", float(o["loss"]), o["logits_shape"])
     o = run_dropout()

@@ -38,7 +38,20 @@ def _worker(rank, world, port, out_dir):
     flat = torch.from_numpy(np.concatenate([res["grads"][n].reshape(-1) for n in names]))
     red = edist.GradAllReducer(bucket_elems=1000)       # several buckets
     red.stream = None                                    # CPU tensors: plain path
+    # the overlapped protocol of the training step: spans reduced as "their backward finishes" (out of memory order),
+    # the remainder plus one trailing scalar in finish(); the buffer then holds the SUM over ranks
+    n = flat.numel()
+    buf = torch.cat([flat, torch.tensor([float(rank + 1)], dtype=flat.dtype)])
+    red.begin_step(buf)
+    red.grad_ready([buf[n - 500:n - 200], buf[n - 200:n]])          # "decoder": two adjacent views, one span
+    red.grad_ready([buf[300:n - 700]])                                # an "encoder layer"
+    red.grad_ready([buf[n - 600:n - 400]])                            # overlaps a reduced span: must be ignored
+    rest = red.finish(n, extra=1)
+    assert rest == [(0, 300), (n - 700, n - 500), (n, n + 1)], rest
+    assert float(buf[n]) == 3.0                                       # 1 + 2: the scalar rode along
+    flat2 = buf[:n] / world
     red.allreduce_mean(flat)
+    assert torch.equal(flat, flat2)
     loss = torch.tensor([res["total_loss"]], dtype=torch.float64)
     red.allreduce_sum(loss)
     if rank == 0:

@@ -332,6 +332,46 @@ def test_general_decoder_cells_match_oracle(cname, keep):
         compare_step(model, ref, rtol=RTOL)
 
 
+@pytest.mark.parametrize("cname,keep", [("tiny_dec2", 1.0), ("tiny_decgru", 1.0), ("tiny_decgru2", 0.7)])
+def test_general_decoder_cells_scheduled_sampling_and_greedy(cname, keep):
+    """The decoder's other input rules for stacked / GRU cells (decoder.py:139-180, attn_decoder.py:127-139): scheduled
+    sampling (realised input ids IDENTICAL to the oracle's, step within 1e-4) and eval-mode greedy decoding (ids
+    bit-exact); the oracle's general restatement of both is pinned to the executed reference (graph_modes_general)."""
+    from oracle import beam as ob
+    cfg = synth.get_config(cname)
+    w = synth.make_weights(cfg, bias_noise=0.1)
+    w["model/rnn_decoder_char/rnn/OutputProjection/kernel"] = w["model/rnn_decoder_char/rnn/OutputProjection/kernel"] * 6.0
+    batch = synth.make_batch(cfg)
+    dec = {"num_layers_dec": cfg.get("dec_layers", 1), "use_lstm": cfg.get("dec_lstm", True)}
+    model = build_model(cfg, w, device="cuda:0")
+    model.params.decoder_params["char"].samp_prob = 0.5
+    model.params.decoder_params["char"].out_prob_dec = keep
+    model.params.dropout_seed = 9
+    sampled_any = False
+    for step in range(3):
+        model.run_step(batch)
+        ops.check_device_errors("cuda:0")
+        ref = om.train_step(w, batch, num_layers={"char": cfg.L}, ctc_tasks=cfg.ctc, dec_params=dec, out_prob_dec=keep,
+                            dropout_seed=9 * 1000003 + step, samp_prob=0.5)
+        ids = model.decoder["char"].stash["realized_ids"].cpu().numpy()
+        assert np.array_equal(ids, ref["realized_ids"]["char"])
+        sampled_any |= bool((ids != np.asarray(batch["char"]).T[:ids.shape[0]]).any())
+        compare_step(model, ref, rtol=RTOL)
+    assert sampled_any
+    # eval mode
+    ev = build_model(cfg, w, device="cuda:0", isTraining=False, ctc=False)
+    ev.run_step(batch)
+    logits = ev.outputs["char"].detach().cpu().numpy()
+    assert logits.shape == (cfg.U * cfg.B, cfg.V)
+    W64 = {k: v.astype(np.float64) for k, v in w.items()}
+    states, lens_d, _ = om.encoder_fwd(W64, batch["logmel"].astype(np.float64), batch["logmel_len"], {"char": cfg.L})
+    ref_logits, _ = om.attn_decoder_general(W64, "char", batch["char"].T, np.full(cfg.B, cfg.U), states[cfg.L],
+                                            lens_d[cfg.L], dec["num_layers_dec"], dec["use_lstm"], mode="greedy",
+                                            max_steps=cfg.U)
+    np.testing.assert_array_equal(ob.greedy_ids_from_logits(logits, cfg.B), ob.greedy_ids_from_logits(ref_logits, cfg.B))
+    assert np.abs(logits - ref_logits).max() / np.abs(ref_logits).max() < 1e-4
+
+
 @pytest.mark.parametrize("graphed", [False, True])
 def test_adam_updates_match_oracle(graphed):
     """apply_updates=True: three Adam steps (fused flat-buffer kernel) against the oracle's TF-formula Adam, eager and

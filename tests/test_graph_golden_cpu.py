@@ -77,6 +77,29 @@ def test_scheduled_sampling_equals_the_executed_reference_training_graph():
     np.testing.assert_allclose(logits, G["sample/logits"], rtol=0, atol=1e-11)
 
 
+@pytest.mark.parametrize("cname", ["tiny_dec2", "tiny_decgru"])
+def test_general_cell_decoders_eval_and_sampling_equal_the_executed_reference(cname):
+    """The decoder's other cell configurations (2-layer MultiRNNCell, GRU cells; decoder.py:49-72) in eval mode (greedy
+    feedback) and with scheduled sampling (samp_prob = 0.5, the oracle's Philox draws injected): the reference's own
+    graph code executed on the NumPy stand-in."""
+    G = np.load(os.path.join(os.path.dirname(__file__), "golden", "graph_modes_general.npz"))
+    cfg = synth.get_config(cname)
+    w = synth.make_weights(cfg, bias_noise=0.1)
+    w["model/rnn_decoder_char/rnn/OutputProjection/kernel"] = w["model/rnn_decoder_char/rnn/OutputProjection/kernel"] * 6.0
+    batch = synth.make_batch(cfg)
+    W = {k: v.astype(np.float64) for k, v in w.items()}
+    states, lens_d, _ = om.encoder_fwd(W, batch["logmel"].astype(np.float64), batch["logmel_len"], {"char": cfg.L})
+    enc, enc_len = states[cfg.L], lens_d[cfg.L]
+    kw = dict(num_layers_dec=int(cfg.get("dec_layers", 1)), use_lstm=bool(cfg.get("dec_lstm", True)))
+    logits, _ = om.attn_decoder_general(W, "char", batch["char"].T, np.full(cfg.B, cfg.U), enc, enc_len, mode="greedy",
+                                        max_steps=cfg.U, **kw)
+    np.testing.assert_allclose(logits, G[cname + "/eval/logits"], rtol=0, atol=1e-11)
+    logits, bwd = om.attn_decoder_general(W, "char", batch["char"].T, batch["char_len"], enc, enc_len, mode="sample",
+                                          samp=(0.5, int(G["seed"]), 0), **kw)
+    assert (bwd.toks != batch["char"].T[:len(bwd.toks)]).any()              # some inputs really were sampled
+    np.testing.assert_allclose(logits, G[cname + "/sample/logits"], rtol=0, atol=1e-11)
+
+
 def test_multitask_model_equals_the_executed_reference_seq2seq_graph():
     """Seq2SeqModel.__init__ + create_computational_graph (seq2seq_model.py:50-144) executed for char + phone attention
     decoders on different encoder layers with frame stacking: per-task logits / losses and total_loss (avg on / off)."""
