@@ -59,6 +59,8 @@ _SIGS = {
     "e2e_attn_beam_f64": "piiiipppppppi",
     "e2e_logsoftmax_topk_f64": "piippdpippp",
     "e2e_embed_gather_f64": "piipppi",
+    "e2e_beam_merge": "pp",
+    "e2e_beam_gather": "pipp",
 }
 _CT = {"p": ctypes.c_void_p, "i": ctypes.c_int, "l": ctypes.c_longlong, "z": ctypes.c_size_t, "f": ctypes.c_float,
        "d": ctypes.c_double, "Q": ctypes.c_ulonglong, "I": ctypes.c_uint}
@@ -81,6 +83,18 @@ class DecPersistArgs(ctypes.Structure):
                 [(n, ctypes.c_void_p) for n in ("W_ch", "pre_g", "q_k", "q_b", "attn_v", "HF", "enc", "enc_len",
                                                 "lens", "cat", "hprev", "cprev", "acts", "y", "alpha", "dcat", "dz",
                                                 "dch", "dy", "ds", "dc_carry", "ctr", "err")])
+
+
+class BeamMergeArgs(ctypes.Structure):
+    _fields_ = ([(n, ctypes.c_int) for n in ("N", "beam", "R", "eos_id")] + [("word_ins_penalty", ctypes.c_double)] +
+                [(n, ctypes.c_void_p) for n in ("step", "out_idx", "out_val", "score", "alive", "k_u", "new_tok",
+                                                "new_score", "parent", "new_alive", "krow", "par_hist", "tok_hist",
+                                                "fin_cnt", "fin_step", "fin_row", "fin_score", "n_live")])
+
+
+class BeamGatherArgs(ctypes.Structure):
+    _fields_ = [("nmat", ctypes.c_int), ("width", ctypes.c_int * 8), ("src", ctypes.c_void_p * 8),
+                ("dst", ctypes.c_void_p * 8)]
 
 
 _lib = None

@@ -7,12 +7,14 @@ Same surface as the reference `BeamSearch` (beam_search.py:15-350):
 beam_search.py:56-98, or the path of an .npz holding them (TF checkpoint I/O is
 out of scope).
 
-Where the reference loops utterance x step x hypothesis in NumPy, here every live
-hypothesis of every utterance is one row of a float64 batch on the device
-(e2e_*_f64 kernels keep the reference's dtype flow); only the
+Where the reference loops utterance x step x hypothesis in NumPy, here every
+hypothesis slot of every utterance is one row of a float64 batch on the device
+(e2e_*_f64 kernels keep the reference's dtype flow), and the
 O(k^2) candidate merge per utterance -- `np.argpartition` over k*k scores,
-back-pointers `idx // k`, EOS bookkeeping (beam_search.py:294-329) -- runs on the
-host as the reference does it, vectorised over utterances (`merge_candidates`).
+back-pointers `idx // k`, EOS bookkeeping (beam_search.py:294-329) -- is a device
+kernel too (`e2e_beam_merge`), so a decoding step is one CUDA-graph replay.
+`merge_candidates` below is the host restatement of that merge (NumPy, vectorised
+over utterances) the device kernel is tested against.
 """
 import numpy as np
 import torch
@@ -161,20 +163,21 @@ class BeamSearch(BaseParams):
         call("e2e_gemm_f64", a.shape[0], w.shape[1], a.shape[1], a, a.stride(0), w, w.stride(0), out, out.stride(0), b)
         return out
 
-    def _lstm(self, x, c, h, w, b):
-        """BasicLSTM step on rows: [x, h] . w + b -> (new_c, new_h)."""
-        n, H = c.shape
-        z = self._gemm64(torch.cat([x, h], dim=1), w, b)
-        c2 = torch.empty_like(c)
-        h2 = torch.empty_like(h)
-        call("e2e_lstm_step_f64", n, H, z, c, c2, h2, H)
-        return c2, h2
+    def decode_batch(self, enc_list, return_scores=False, use_graph=None):
+        """Decode a list of utterances ([T_i, D] arrays) together; returns a list of id arrays.
 
-    def decode_batch(self, enc_list, return_scores=False):
-        """Decode a list of utterances ([T_i, D] arrays) together; returns a list of id arrays."""
+        Every utterance owns `beam` fixed hypothesis slots (rows u*beam .. u*beam+beam-1 of every state matrix, live
+        ones first), so one decoding step is a fixed sequence of launches on fixed shapes -- the float64 decoder step
+        on all rows, the per-row top-k, the candidate merge per utterance (`e2e_beam_merge`: k*k candidates ->
+        np.argpartition's top-k set, EOS retirement, back-pointers) and the back-pointer gather of the states -- which
+        is captured in a CUDA graph after step 0 and replayed for steps 1..119.  The host only polls the number of
+        live hypotheses every few steps and rebuilds the token sequences from the back-pointers at the end."""
+        import ctypes
+        from ._lib import BeamGatherArgs, BeamMergeArgs
         sp, p, lp, dev = self.search_params, self.dec_params, self.lm_params, self.device
         beam = int(sp.beam_size)
         f64 = dict(dtype=torch.float64, device=dev)
+        i32 = dict(dtype=torch.int32, device=dev)
         encs = []
         for e in enc_list:
             e = e.detach().cpu().numpy() if isinstance(e, torch.Tensor) else np.asarray(e)
@@ -182,6 +185,7 @@ class BeamSearch(BaseParams):
                 e = np.squeeze(e, axis=0)
             encs.append(np.ascontiguousarray(e, np.float32))
         N = len(encs)
+        R = N * beam
         Ts = np.array([e.shape[0] for e in encs], np.int32)
         offs = np.concatenate([[0], np.cumsum(Ts)[:-1]]).astype(np.int32)
         enc_all = torch.from_numpy(np.concatenate(encs, axis=0)).to(dev)
@@ -191,78 +195,131 @@ class BeamSearch(BaseParams):
         Hd, Hl = p.dec_lstm_w.shape[1] // 4, p.lm_lstm_w.shape[1] // 4
         HF = ops.gemm(enc_all, p.attn_enc_w, mode=0)                      # float32 x float32 (beam_search.py:148)
         Tmax = int(Ts.max())
+        S = self.MAX_STEPS
+        row_off = torch.from_numpy(np.repeat(offs, beam)).to(dev)
+        row_T = torch.from_numpy(np.repeat(Ts, beam)).to(dev)
 
-        # hypothesis rows (host bookkeeping, NumPy arrays): utterance, token history, model score
-        utt = np.arange(N)
-        hist = np.zeros((N, 0), np.int64)     # tokens emitted so far, one row per hypothesis
-        scores = np.zeros(N, np.float64)
-        k_u = np.full(N, beam, np.int64)      # current beam size per utterance (shrinks at EOS)
-        final = [[] for _ in range(N)]
-        tok = np.full(N, GO_ID, np.int64)
-        st = dict(dc=torch.zeros((N, Hd), **f64), dh=torch.zeros((N, Hd), **f64),
-                  lc=torch.zeros((N, Hl), **f64), lh=torch.zeros((N, Hl), **f64),
-                  ctx=torch.zeros((N, D), **f64))
-        if self.use_lm:
-            Hm = lp.lm_lstm_w.shape[1] // 4
-            st["mc"] = torch.zeros((N, Hm), **f64)
-            st["mh"] = torch.zeros((N, Hm), **f64)
-        step = 0
-        while step < self.MAX_STEPS and len(utt) > 0:
-            n = len(utt)
-            tok_d = torch.from_numpy(np.ascontiguousarray(tok)).to(dev)
-            x = torch.empty((n, E), **f64)
-            call("e2e_embed_gather_f64", n, E, p.embedding, tok_d, x, E)
+        # ---- slot state (device)
+        slot0 = (torch.arange(R, device=dev) % beam) == 0
+        tok = torch.full((R,), GO_ID, dtype=torch.int64, device=dev)
+        score = torch.zeros((R,), **f64)
+        alive = slot0.to(torch.int32)                                     # step 0: the GO row of every utterance
+        krow = alive * beam
+        k_u = torch.full((N,), beam, **i32)
+        names = ["dc", "dh", "lc", "lh", "ctx"] + (["mc", "mh"] if self.use_lm else [])
+        Hm = lp.lm_lstm_w.shape[1] // 4
+        width = dict(dc=Hd, dh=Hd, lc=Hl, lh=Hl, ctx=D, mc=Hm, mh=Hm)
+        st = {n: torch.zeros((R, width[n]), **f64) for n in names}        # states entering the step
+        nx = {n: torch.empty((R, width[n]), **f64) for n in names}        # states leaving it (before the gather)
+        new_tok = torch.empty((R,), dtype=torch.int64, device=dev)
+        new_score = torch.empty((R,), **f64)
+        new_alive = torch.empty((R,), **i32)
+        parent = torch.empty((R,), **i32)
+        par_hist = torch.full((S, R), -1, **i32)
+        tok_hist = torch.full((S, R), -1, **i32)
+        fin_cnt = torch.zeros((N,), **i32)
+        fin_step = torch.zeros((R,), **i32)
+        fin_row = torch.zeros((R,), **i32)
+        fin_score = torch.zeros((R,), **f64)
+        step_dev = torch.zeros((1,), **i32)
+        n_live = torch.zeros((1,), **i32)
+        out_idx = torch.empty((R, beam), **i32)
+        out_val = torch.empty((R, beam), **f64)
+        scratch = torch.empty((R, V), **f64)
+
+        ma = BeamMergeArgs()
+        ma.N, ma.beam, ma.R, ma.eos_id, ma.word_ins_penalty = N, beam, R, EOS_ID, float(sp.word_ins_penalty)
+        for k, t in dict(step=step_dev, out_idx=out_idx, out_val=out_val, score=score, alive=alive, k_u=k_u,
+                         new_tok=new_tok, new_score=new_score, parent=parent, new_alive=new_alive, krow=krow,
+                         par_hist=par_hist, tok_hist=tok_hist, fin_cnt=fin_cnt, fin_step=fin_step, fin_row=fin_row,
+                         fin_score=fin_score, n_live=n_live).items():
+            setattr(ma, k, t.data_ptr())
+        ga = BeamGatherArgs()
+        ga.nmat = len(names)
+        for m, n in enumerate(names):
+            ga.width[m], ga.src[m], ga.dst[m] = width[n], nx[n].data_ptr(), st[n].data_ptr()
+
+        def lstm(x, c, h, w, b, c_out, h_out):
+            """BasicLSTM step on rows: [x, h] . w + b -> (new_c, new_h) written to c_out / h_out."""
+            z = self._gemm64(torch.cat([x, h], dim=1), w, b)
+            call("e2e_lstm_step_f64", c.shape[0], c.shape[1], z, c, c_out, h_out, c.shape[1])
+
+        def step_fn():
+            x = torch.empty((R, E), **f64)
+            call("e2e_embed_gather_f64", R, E, p.embedding, tok, x, E)
             # decoder's LM-LSTM, SimpleProjection, InputProjection, decoder LSTM (beam_search.py:182-191)
-            lc, lh = self._lstm(x, st["lc"], st["lh"], p.lm_lstm_w, p.lm_lstm_b)
-            m = lh if p.simple_w is None else self._gemm64(lh, p.simple_w, p.simple_b)
+            lstm(x, st["lc"], st["lh"], p.lm_lstm_w, p.lm_lstm_b, nx["lc"], nx["lh"])
+            m = nx["lh"] if p.simple_w is None else self._gemm64(nx["lh"], p.simple_w, p.simple_b)
             x_dec = self._gemm64(torch.cat([m, st["ctx"]], dim=1), p.inp_w, p.inp_b)
-            dc, dh = self._lstm(x_dec, st["dc"], st["dh"], p.dec_lstm_w, p.dec_lstm_b)
+            lstm(x_dec, st["dc"], st["dh"], p.dec_lstm_w, p.dec_lstm_b, nx["dc"], nx["dh"])
             # attention with the CELL state as query (beam_search.py:193), AttnProjection, OutputProjection
-            y = self._gemm64(dc, p.attn_dec_w, p.attn_dec_b)
-            ctx = torch.empty((n, D), **f64)
-            uidx = utt
-            call("e2e_attn_beam_f64", n, A, D, Tmax, HF, enc_all, torch.from_numpy(offs[uidx]).to(dev),
-                 torch.from_numpy(Ts[uidx]).to(dev), y, p.attn_v, ctx, D)
-            proj = self._gemm64(torch.cat([dc, ctx], dim=1), p.attn_proj_w, p.attn_proj_b)
+            y = self._gemm64(nx["dc"], p.attn_dec_w, p.attn_dec_b)
+            call("e2e_attn_beam_f64", R, A, D, Tmax, HF, enc_all, row_off, row_T, y, p.attn_v, nx["ctx"], D)
+            proj = self._gemm64(torch.cat([nx["dc"], nx["ctx"]], dim=1), p.attn_proj_w, p.attn_proj_b)
             logits = self._gemm64(proj, p.out_w, p.out_b)
             lm_logits = None
             if self.use_lm:                                                # LM branch (beam_search.py:200-207)
-                x_lm = torch.empty((n, E), **f64)
-                call("e2e_embed_gather_f64", n, E, lp.embedding, tok_d, x_lm, E)
-                mc, mh = self._lstm(x_lm, st["mc"], st["mh"], lp.lm_lstm_w, lp.lm_lstm_b)
-                lo = mh if lp.simple_w is None else self._gemm64(mh, lp.simple_w, lp.simple_b)
+                x_lm = torch.empty((R, E), **f64)
+                call("e2e_embed_gather_f64", R, E, lp.embedding, tok, x_lm, E)
+                lstm(x_lm, st["mc"], st["mh"], lp.lm_lstm_w, lp.lm_lstm_b, nx["mc"], nx["mh"])
+                lo = nx["mh"] if lp.simple_w is None else self._gemm64(nx["mh"], lp.simple_w, lp.simple_b)
                 lm_logits = self._gemm64(lo, lp.out_w, lp.out_b)
-            krow = k_u[utt].astype(np.int32)
-            out_idx = torch.empty((n, beam), dtype=torch.int32, device=dev)
-            out_val = torch.empty((n, beam), **f64)
-            scratch = torch.empty((n, V), **f64)
-            call("e2e_logsoftmax_topk_f64", n, V, logits, lm_logits, float(sp.lm_weight),
-                 torch.from_numpy(krow).to(dev), beam, out_idx, out_val, scratch)
-            idx_h = out_idx.cpu().numpy()
-            val_h = out_val.cpu().numpy()
-            # ---- host: merge candidates per utterance (beam_search.py:294-329), all utterances at once
-            new, finished = merge_candidates(utt, scores, k_u, idx_h, val_h, step, sp.word_ins_penalty)
-            for u, pr, sc in finished:
-                final[u].append((np.append(hist[pr], EOS_ID), sc))
-            step += 1
-            parents = new["parent"]
-            hist = np.concatenate([hist[parents], new["tok"][:, None]], axis=1)
-            if step >= self.MAX_STEPS or len(parents) == 0:
-                # leftovers join the final list (beam_search.py:332)
-                for u, seq, sc in zip(new["utt"], hist, new["score"]):
-                    final[int(u)].append((seq, float(sc)))
+            call("e2e_logsoftmax_topk_f64", R, V, logits, lm_logits, float(sp.lm_weight), krow, beam, out_idx,
+                 out_val, scratch)
+            n_live.zero_()
+            call("e2e_beam_merge", ma)                                      # -> new rows, back-pointers, finals
+            call("e2e_beam_gather", R, parent, ga)                          # states of the parent hypotheses
+            tok.copy_(new_tok)
+            score.copy_(new_score)
+            alive.copy_(new_alive)
+            step_dev.add_(1)
+
+        step_fn()                                                           # step 0, launched kernel by kernel
+        steps_done = 1
+        graph = None
+        if use_graph is None:
+            use_graph = R >= 64
+        if use_graph and S > 1:
+            cur = torch.cuda.current_stream()
+            cs = torch.cuda.Stream(device=dev)
+            cs.wait_stream(cur)
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph, stream=cs):
+                step_fn()
+            cur.wait_stream(cs)
+        while steps_done < S:
+            if steps_done % 4 == 0 and int(n_live.item()) == 0:             # every hypothesis has emitted EOS
                 break
-            sel_rows = torch.from_numpy(parents).to(dev)
-            st = dict(dc=dc.index_select(0, sel_rows), dh=dh.index_select(0, sel_rows),
-                      lc=lc.index_select(0, sel_rows), lh=lh.index_select(0, sel_rows),
-                      ctx=ctx.index_select(0, sel_rows))
-            if self.use_lm:
-                st["mc"] = mc.index_select(0, sel_rows)
-                st["mh"] = mh.index_select(0, sel_rows)
-            utt, scores, tok = new["utt"], new["score"], new["tok"]
+            if graph is not None:
+                graph.replay()
+            else:
+                step_fn()
+            steps_done += 1
+
+        # ---- host: rebuild the sequences from the back-pointers
+        ph, th = par_hist[:steps_done].cpu().numpy(), tok_hist[:steps_done].cpu().numpy()
+        fc, fs, fr, fsc = (t.cpu().numpy() for t in (fin_cnt, fin_step, fin_row, fin_score))
+        alive_h, score_h = alive.cpu().numpy(), score.cpu().numpy()
+
+        def backtrack(t, row):
+            seq = []
+            while t >= 0:
+                seq.append(int(th[t, row]))
+                row = int(ph[t, row])
+                t -= 1
+            return seq[::-1]
+
         outs, outs_sc = [], []
         for u in range(N):
-            best = max(final[u], key=lambda e: e[1])                        # first maximum, no length norm (:336)
+            final = []
+            for f in range(int(fc[u])):                                     # EOS-retired, in the order they finished
+                i = u * beam + f
+                final.append((backtrack(int(fs[i]) - 1, int(fr[i])) + [EOS_ID], float(fsc[i])))
+            for slot in range(beam):                                        # leftovers (beam_search.py:332)
+                row = u * beam + slot
+                if alive_h[row]:
+                    final.append((backtrack(steps_done - 1, row), float(score_h[row])))
+            best = max(final, key=lambda e: e[1])                           # first maximum, no length norm (:336)
             outs.append(np.asarray(best[0], np.int64))
             outs_sc.append(best[1])
         return (outs, outs_sc) if return_scores else outs

@@ -5,6 +5,7 @@
 // encoder states and enc.AttnW stay float32.  These kernels keep exactly that dtype
 // flow on the device -- fp32 operands are widened at load, all arithmetic is fp64 --
 // and are batched over every live hypothesis of every utterance.
+#include "../../include/e2e_asr_b200.h"
 #include "common.cuh"
 
 namespace e2e {
@@ -339,6 +340,130 @@ __global__ void embed_gather_f64_kernel(int n, int E, const float* __restrict__ 
 int embed_gather_f64(cudaStream_t st, int n, int E, const float* emb, const long long* ids, double* out, int ldo) {
     if (n <= 0) return 0;
     embed_gather_f64_kernel<<<n, 128, 0, st>>>(n, E, emb, ids, out, ldo);
+    E2E_LAUNCH_CHECK();
+    return 0;
+}
+
+// ---- candidate merge of one decoding step, all utterances (beam_search.py:255-266 for the GO step, :294-329) ----
+// Hypotheses live in FIXED slots: utterance u owns rows [u*beam, (u+1)*beam), live ones first.  One CTA (one warp) per
+// utterance: the candidates are val[row][j] + score[row] over the live rows and j < k (k = the utterance's current
+// beam size), in (row, j) order like the reference's concatenation; the k best are taken -- the reference's
+// np.argpartition(all_scores, -k)[-k:] as a SET; the order inside the set only decides float64 ties -- here in
+// descending score order, ties to the lower candidate index.  A candidate that emits EOS retires to the utterance's
+// final list (k shrinks), the others become the new live rows with back-pointers; the histories are reconstructed
+// from par_hist / tok_hist on the host at the end.  `step` is read from device memory so that the launch can be
+// replayed from a CUDA graph.
+__global__ void __launch_bounds__(32)
+beam_merge_kernel(e2e_beam_merge_args a) {
+    extern __shared__ double sm_d[];
+    const int u = blockIdx.x, lane = threadIdx.x, beam = a.beam;
+    const int step = *a.step;
+    double* csc = sm_d;                                  // [beam*beam] candidate scores
+    int* ctok = reinterpret_cast<int*>(csc + beam * beam);
+    int* crow = ctok + beam * beam;
+    const int k = a.k_u[u];
+    const int base = u * beam;
+    // gather the candidates (sequential over rows: at most beam rows)
+    int nc = 0;
+    for (int slot = 0; slot < beam; ++slot) {
+        const int row = base + slot;
+        if (!a.alive[row]) continue;
+        const double sc = a.score[row];
+        for (int j = lane; j < k; j += 32) {
+            csc[nc + j] = a.out_val[(size_t)row * beam + j] + sc;
+            ctok[nc + j] = a.out_idx[(size_t)row * beam + j];
+            crow[nc + j] = row;
+        }
+        nc += k;
+    }
+    __syncwarp();
+    const double pen = step > 0 ? a.word_ins_penalty * (double)(step + 1) : 0.0;
+    int n_new = 0, k_left = k, nfin = a.fin_cnt[u];
+    for (int i = 0; i < k; ++i) {
+        double best = -INFINITY;
+        int bi = 0x7fffffff;
+        for (int c = lane; c < nc; c += 32) {
+            const double v = csc[c];
+            if (ctok[c] >= 0 && (v > best || (v == best && c < bi))) { best = v; bi = c; }
+        }
+        for (int o = 16; o > 0; o >>= 1) {
+            const double ob = __shfl_xor_sync(0xffffffffu, best, o);
+            const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+            if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; }
+        }
+        if (bi == 0x7fffffff) break;                     // fewer candidates than k (cannot happen for k <= beam)
+        const int tok = ctok[bi], prow = crow[bi];
+        __syncwarp();
+        if (lane == 0) {
+            ctok[bi] = -1;                               // taken
+            const double sc = best + pen;
+            if (tok == a.eos_id) {
+                if (nfin < beam) {
+                    a.fin_step[base + nfin] = step;
+                    a.fin_row[base + nfin] = prow;
+                    a.fin_score[base + nfin] = sc;
+                }
+                ++nfin;
+                --k_left;
+            } else {
+                const int row = base + n_new;
+                a.new_tok[row] = tok;
+                a.new_score[row] = sc;
+                a.parent[row] = prow;
+                a.par_hist[(size_t)step * a.R + row] = prow;
+                a.tok_hist[(size_t)step * a.R + row] = tok;
+                ++n_new;
+            }
+        }
+        n_new = __shfl_sync(0xffffffffu, n_new, 0);
+        k_left = __shfl_sync(0xffffffffu, k_left, 0);
+        nfin = __shfl_sync(0xffffffffu, nfin, 0);
+        __syncwarp();
+    }
+    // dead slots: finite dummies (their rows still flow through the batched decoder step)
+    for (int slot = n_new + lane; slot < beam; slot += 32) {
+        const int row = base + slot;
+        a.new_tok[row] = 0;
+        a.new_score[row] = 0.0;
+        a.parent[row] = base;
+        a.par_hist[(size_t)step * a.R + row] = -1;
+        a.tok_hist[(size_t)step * a.R + row] = -1;
+    }
+    for (int slot = lane; slot < beam; slot += 32) {
+        a.new_alive[base + slot] = slot < n_new ? 1 : 0;
+        a.krow[base + slot] = slot < n_new ? k_left : 0;
+    }
+    if (lane == 0) {
+        a.k_u[u] = k_left;
+        a.fin_cnt[u] = nfin;
+        if (k_left > 0) atomicAdd(a.n_live, k_left);
+    }
+}
+
+int beam_merge(cudaStream_t st, const e2e_beam_merge_args* a) {
+    if (a->N <= 0) return 0;
+    E2E_REQUIRE(a->beam >= 1 && a->beam <= 64, "beam_merge: beam size %d out of [1, 64]", a->beam);
+    const size_t smem = (size_t)a->beam * a->beam * (sizeof(double) + 2 * sizeof(int));
+    beam_merge_kernel<<<a->N, 32, smem, st>>>(*a);
+    E2E_LAUNCH_CHECK();
+    return 0;
+}
+
+// out[r, :] = in[parent[r], :] for several float64 state matrices at once (the back-pointer gather of a beam step:
+// BeamEntry state_list / context_vec of the parent hypothesis, beam_search.py:313-318)
+__global__ void beam_gather_kernel(int R, const int* __restrict__ parent, int nmat, e2e_beam_gather_args g) {
+    const int r = blockIdx.x;
+    const int p = parent[r];
+    for (int m = 0; m < nmat; ++m) {
+        const double* src = g.src[m] + (size_t)p * g.width[m];
+        double* dst = g.dst[m] + (size_t)r * g.width[m];
+        for (int i = threadIdx.x; i < g.width[m]; i += blockDim.x) dst[i] = src[i];
+    }
+}
+int beam_gather(cudaStream_t st, int R, const int* parent, const e2e_beam_gather_args* g) {
+    if (R <= 0) return 0;
+    E2E_REQUIRE(g->nmat >= 0 && g->nmat <= 8, "beam_gather: %d matrices (max 8)", g->nmat);
+    beam_gather_kernel<<<R, 128, 0, st>>>(R, parent, g->nmat, *g);
     E2E_LAUNCH_CHECK();
     return 0;
 }

@@ -64,6 +64,8 @@ int ce_bwd(cudaStream_t, int, int, int, const float*, const long long*, const in
 int ctc_fwd_grad(cudaStream_t, int, int, int, long long, long long, const float*, const float*, const int*,
                  const long long*, int, const int*, int, float*, float*, float*, float);
 size_t ctc_workspace_floats(int, int, int);
+int beam_merge(cudaStream_t, const e2e_beam_merge_args*);
+int beam_gather(cudaStream_t, int, const int*, const e2e_beam_gather_args*);
 int sumsq(cudaStream_t, size_t, const float*, float*, float*, float, int);
 int clip_by_norm(cudaStream_t, size_t, float*, const float*, float, float*, float, const int*);
 int scale_inplace(cudaStream_t, size_t, float*, const float*, float);
@@ -353,6 +355,10 @@ int e2e_ctc_fwd_grad(void* stream, int T, int B, int C, long long sb, long long 
                         max_label_len, ws, loss_b, grad, out_scale);
 }
 size_t e2e_ctc_workspace_floats(int T, int B, int max_label_len) { return ctc_workspace_floats(T, B, max_label_len); }
+int e2e_beam_merge(void* stream, const e2e_beam_merge_args* a) { return beam_merge(ST(stream), a); }
+int e2e_beam_gather(void* stream, int R, const int* parent, const e2e_beam_gather_args* g) {
+    return beam_gather(ST(stream), R, parent, g);
+}
 int e2e_sumsq(void* stream, size_t n, const float* x, float* partials296, float* out, float sign, int accumulate) {
     return sumsq(ST(stream), n, x, partials296, out, sign, accumulate);
 }

@@ -262,6 +262,45 @@ int e2e_logsoftmax_topk_f64(void* stream, int n, int V, const double* logits, co
                             double* scratch);
 int e2e_embed_gather_f64(void* stream, int n, int E, const float* emb, const long long* ids, double* out, int ldo);
 
+/* Candidate merge of one beam-search step for all utterances on the device (beam_search.py:255-266, 294-329).
+ * Hypotheses live in fixed slots: utterance u owns rows [u*beam, (u+1)*beam), live ones first; R = N*beam.
+ * Per utterance: candidates val[row][j] + score[row] (live rows, j < k_u[u]) -> the k_u[u] best (the reference's
+ * np.argpartition(., -k)[-k:] as a set) -> EOS candidates retire to the final list (k_u shrinks), the others become
+ * the new live rows.  *step is read on the device (the launch is replayed from a CUDA graph); word_ins_penalty *
+ * (step + 1) is added from step 1 on (beam_search.py:321-322; the step-0 candidates keep the bare score, :258-260). */
+typedef struct {
+    int N, beam, R, eos_id;
+    double word_ins_penalty;
+    const int* step;           /* [1] device: index of this decoding step */
+    const int* out_idx;        /* [R, beam] top tokens per row (e2e_logsoftmax_topk_f64) */
+    const double* out_val;     /* [R, beam] their log-probabilities */
+    const double* score;       /* [R] score of the hypothesis in each row */
+    const int* alive;          /* [R] 1 = the row holds a live hypothesis */
+    int* k_u;                  /* [N] current beam size per utterance (in/out) */
+    long long* new_tok;        /* [R] out: token fed to the next step */
+    double* new_score;         /* [R] out */
+    int* parent;               /* [R] out: row (of this step's input rows) each new row extends */
+    int* new_alive;            /* [R] out */
+    int* krow;                 /* [R] out: k of the row's utterance for live rows, 0 for dead ones */
+    int* par_hist;             /* [max_steps, R] out: row `step` = parent (or -1) */
+    int* tok_hist;             /* [max_steps, R] out: row `step` = token (or -1) */
+    int* fin_cnt;              /* [N] number of finished hypotheses (in/out) */
+    int* fin_step;             /* [R] step at which the f-th finished hypothesis of u (index u*beam+f) emitted EOS */
+    int* fin_row;              /* [R] its parent row */
+    double* fin_score;         /* [R] its score */
+    int* n_live;               /* [1] += number of live hypotheses after this step (caller zeroes it) */
+} e2e_beam_merge_args;
+int e2e_beam_merge(void* stream, const e2e_beam_merge_args* a);
+
+/* dst[m][r, :] = src[m][parent[r], :] for up to 8 float64 state matrices (back-pointer gather of a beam step) */
+typedef struct {
+    int nmat;
+    int width[8];
+    const double* src[8];
+    double* dst[8];
+} e2e_beam_gather_args;
+int e2e_beam_gather(void* stream, int R, const int* parent, const e2e_beam_gather_args* g);
+
 /* tf.clip_by_global_norm (seq2seq_model.py:150-151) on the flat gradient buffer:
  * sumsq: out (+)= sign * sum x^2; clip: x *= pre_scale * clip / max(sqrt(sumsq), clip), norm_out = sqrt(sumsq).
  * pre_scale = 1/n folds the averaging of a data-parallel SUM of n rank gradients into the clipping pass (sumsq is

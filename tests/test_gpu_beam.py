@@ -55,6 +55,66 @@ def test_beam_k10_eval_batch_vs_oracle_and_lm_weight():
             assert abs(sc[u] - rs) <= 1e-6 * max(1.0, abs(rs))
 
 
+@pytest.mark.parametrize("step", [0, 5])
+def test_device_merge_kernel_equals_host_merge(step):
+    """e2e_beam_merge (one warp per utterance, fixed hypothesis slots) against merge_candidates, the NumPy restatement
+    of beam_search.py:255-266 / 294-329 that tests/test_beam_merge_cpu.py checks against the reference's per-utterance
+    loop: same surviving (parent, token, score) set per utterance, same finished hypotheses, same beam sizes; scores
+    bit-exact (the same float64 additions)."""
+    import torch
+    from e2e_asr_b200._lib import BeamMergeArgs, call
+    from e2e_asr_b200.beam_search import merge_candidates
+    from e2e_asr_b200.data_utils import EOS_ID
+    rng = np.random.default_rng(step)
+    N, beam, V, S = 37, 10, 12, 8
+    R = N * beam
+    k_u = rng.integers(0, beam + 1, size=N) if step else np.full(N, beam)
+    alive = np.zeros(R, np.int32)
+    for u in range(N):
+        alive[u * beam:u * beam + (k_u[u] if step else 1)] = 1
+    score = rng.standard_normal(R) * 3.0
+    if step == 0:
+        score[:] = 0.0
+    val = np.log(rng.dirichlet(np.ones(V), size=R))
+    idx = np.argsort(-val, axis=1, kind="stable")[:, :beam].astype(np.int32)          # includes EOS (= 2) now and then
+    val = np.take_along_axis(val, idx.astype(np.int64), 1)
+    rows = np.flatnonzero(alive)
+    k_ref = k_u.astype(np.int64).copy()
+    new, finished = merge_candidates(rows // beam, score[rows], k_ref, idx[rows], val[rows], step, 0.25)
+    dev = "cuda:0"
+    T = lambda a, dt: torch.from_numpy(np.ascontiguousarray(a)).to(dev, dt)
+    t = dict(step=T(np.array([step]), torch.int32), out_idx=T(idx, torch.int32), out_val=T(val, torch.float64),
+             score=T(score, torch.float64), alive=T(alive, torch.int32), k_u=T(k_u, torch.int32),
+             new_tok=torch.zeros(R, dtype=torch.int64, device=dev), new_score=torch.zeros(R, dtype=torch.float64, device=dev),
+             parent=torch.zeros(R, dtype=torch.int32, device=dev), new_alive=torch.zeros(R, dtype=torch.int32, device=dev),
+             krow=torch.zeros(R, dtype=torch.int32, device=dev), par_hist=torch.zeros((S, R), dtype=torch.int32, device=dev),
+             tok_hist=torch.zeros((S, R), dtype=torch.int32, device=dev), fin_cnt=torch.zeros(N, dtype=torch.int32, device=dev),
+             fin_step=torch.zeros(R, dtype=torch.int32, device=dev), fin_row=torch.zeros(R, dtype=torch.int32, device=dev),
+             fin_score=torch.zeros(R, dtype=torch.float64, device=dev), n_live=torch.zeros(1, dtype=torch.int32, device=dev))
+    a = BeamMergeArgs()
+    a.N, a.beam, a.R, a.eos_id, a.word_ins_penalty = N, beam, R, EOS_ID, 0.25
+    for k, v in t.items():
+        setattr(a, k, v.data_ptr())
+    call("e2e_beam_merge", a)
+    torch.cuda.synchronize()
+    h = {k: v.cpu().numpy() for k, v in t.items()}
+    assert list(h["k_u"]) == list(k_ref) and int(h["n_live"][0]) == int(k_ref.sum())
+    for u in range(N):
+        live = [r for r in range(u * beam, (u + 1) * beam) if h["new_alive"][r]]
+        assert live == list(range(u * beam, u * beam + k_ref[u]))                    # live rows first
+        got = sorted((int(h["parent"][r]), int(h["new_tok"][r]), float(h["new_score"][r])) for r in live)
+        sel = new["utt"] == u
+        ref = sorted((int(rows[p_]), int(t_), float(s_)) for p_, t_, s_ in zip(new["parent"][sel], new["tok"][sel], new["score"][sel]))
+        assert got == ref, (u, got, ref)
+        assert all(h["krow"][r] == k_ref[u] for r in live)
+        assert [(int(h["par_hist"][step, r]), int(h["tok_hist"][step, r])) for r in live] == \
+            [(int(h["parent"][r]), int(h["new_tok"][r])) for r in live]
+        fin_ref = sorted((int(rows[p_]), s_) for uu, p_, s_ in finished if uu == u)
+        nf = int(h["fin_cnt"][u])
+        fin_got = sorted((int(h["fin_row"][u * beam + f]), float(h["fin_score"][u * beam + f])) for f in range(nf))
+        assert fin_got == fin_ref and all(h["fin_step"][u * beam + f] == step for f in range(nf))
+
+
 def test_beam_separate_lm_checkpoint_and_word_insertion_penalty(tmp_path):
     """search_params.lm_path names ANOTHER checkpoint (beam_search.py:45-46: map_lm_variables(get_model_params(lm_path)))
     -- its LM-LSTM / OutputProjection / embedding drive the fusion term -- given as a dict, as an .npz path, and as a
