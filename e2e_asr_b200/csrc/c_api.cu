@@ -35,9 +35,10 @@ int gemm_tc(cudaStream_t, int mode, int, int, int, int, int, const float*, int, 
             const float*, const float*, int, int, bool*, const float*, const float*, size_t, size_t);
 int split_lo(cudaStream_t, int, size_t, const float*, float*);
 void set_workspace(void*, size_t);
-void set_stream_workspace(cudaStream_t, void*, size_t);
+bool set_stream_workspace(cudaStream_t, void*, size_t);
 extern int g_rec_mode;
 extern long long* g_rec_dbg;
+extern int g_dec_cluster_log2;
 void set_tc_debug(float*, long long);
 int colsum(cudaStream_t, int, int, const float*, int, float*, int);
 int lstm_rec(cudaStream_t, bool, int, int, int, int, int, long long, long long, float*, float*, float*,
@@ -196,12 +197,19 @@ int e2e_set_rec_mode(int mode) {
     g_rec_mode = mode;
     return 0;
 }
+int e2e_set_dec_cluster(int log2_size) {
+    if (log2_size < 0 || log2_size > 3) return 1;
+    g_dec_cluster_log2 = log2_size;
+    return 0;
+}
 int e2e_set_rec_debug(long long* dbg) {
     g_rec_dbg = dbg;
     return 0;
 }
 int e2e_set_stream_workspace(void* stream, void* ptr, size_t bytes) {
-    set_stream_workspace(ST(stream), ptr, bytes);
+    E2E_REQUIRE(set_stream_workspace(ST(stream), ptr, bytes),
+                "e2e_set_stream_workspace: the per-stream scratch table is full (a GEMM on this stream would race "
+                "with the default scratch)");
     return 0;
 }
 int e2e_set_workspace(void* ptr, size_t bytes) {

@@ -411,7 +411,9 @@ void* g_ws = nullptr;
 size_t g_ws_bytes = 0;
 // per-stream scratch (concurrent streams must not share the operand pre-pass buffers)
 struct StreamWs { cudaStream_t st; void* ptr; size_t bytes; };
-StreamWs g_stream_ws[8];
+// torch hands out streams from pools of 32 per priority and device: every handle a process can see fits
+constexpr int MAX_STREAM_WS = 256;
+StreamWs g_stream_ws[MAX_STREAM_WS];
 int g_n_stream_ws = 0;
 float* g_dbg = nullptr;
 long long g_min_work = 1ll << 27;
@@ -422,10 +424,14 @@ void set_workspace(void* ptr, size_t bytes) {
     g_ws = ptr;
     g_ws_bytes = bytes;
 }
-void set_stream_workspace(cudaStream_t st, void* ptr, size_t bytes) {
+// returns false when the table is full: a GEMM on that stream would silently share the default scratch with the
+// main stream (a data race), so the caller must treat it as an error
+bool set_stream_workspace(cudaStream_t st, void* ptr, size_t bytes) {
     for (int i = 0; i < g_n_stream_ws; ++i)
-        if (g_stream_ws[i].st == st) { g_stream_ws[i].ptr = ptr; g_stream_ws[i].bytes = bytes; return; }
-    if (g_n_stream_ws < 8) g_stream_ws[g_n_stream_ws++] = StreamWs{st, ptr, bytes};
+        if (g_stream_ws[i].st == st) { g_stream_ws[i].ptr = ptr; g_stream_ws[i].bytes = bytes; return true; }
+    if (g_n_stream_ws >= MAX_STREAM_WS) return false;
+    g_stream_ws[g_n_stream_ws++] = StreamWs{st, ptr, bytes};
+    return true;
 }
 void set_tc_debug(float* dbg, long long min_work) {
     g_dbg = dbg;

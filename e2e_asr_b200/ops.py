@@ -43,8 +43,8 @@ def ensure_workspace(device, nbytes=2 << 30, stream=None):
         _workspace[key] = torch.empty((nbytes,), dtype=torch.uint8, device=device)
     if stream is None:
         _lib.lib().e2e_set_workspace(_workspace[key].data_ptr(), _workspace[key].numel())
-    else:
-        _lib.lib().e2e_set_stream_workspace(stream.cuda_stream, _workspace[key].data_ptr(), _workspace[key].numel())
+    elif _lib.lib().e2e_set_stream_workspace(stream.cuda_stream, _workspace[key].data_ptr(), _workspace[key].numel()):
+        raise RuntimeError("e2e_set_stream_workspace failed: %s" % _lib.lib().e2e_last_error().decode())
 
 
 def get_gemm_mode():

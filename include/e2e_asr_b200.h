@@ -100,6 +100,9 @@ int e2e_lstm_unpack_grads(void* stream, int I, int H, float* dkernel, float* dbi
 int e2e_set_rec_mode(int mode);
 /* test hook: device buffer (>= 5*T int64) receiving per-step clock64 stamps of the forward cluster kernel, or NULL */
 int e2e_set_rec_debug(long long* dbg);
+/* test hook: largest thread-block-cluster size (2^log2_size, log2_size in 0..3) the persistent decoder kernels are
+ * launched with; 0 = flat grid barrier */
+int e2e_set_dec_cluster(int log2_size);
 int e2e_lstm_rec_fwd(void* stream, int B, int T, int Tp, int H, int ndir, long long sb, long long st,
                      float* G, float* Hout, float* Cst, const float* Wh, const int* lens,
                      void* ctr_ws, size_t ctr_ws_bytes, int* err_flag);
