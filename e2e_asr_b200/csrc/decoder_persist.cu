@@ -22,7 +22,11 @@
 namespace e2e {
 
 extern long long* g_rec_dbg;
-int g_dec_cluster_log2 = 3;        // largest cluster size tried by the persistent decoder kernels: 2^3 (test hook)
+// largest cluster size (2^n) tried by the persistent decoder kernels (test hook e2e_set_dec_cluster).  Default 0 = flat
+// barrier: measured at cfg-2, clusters of 8 made the step SLOWER (forward 13.8 -> 17.0 us, backward 17.9 -> 21.4 us per
+// decoder step: two hardware cluster barriers + the leader's round trip cost more than 128 same-address arrivals), and
+// a cooperative launch with a cluster dimension costs the host ~7 ms of validation when launched eagerly.
+int g_dec_cluster_log2 = 0;
 
 namespace {
 
@@ -116,11 +120,10 @@ __device__ __forceinline__ void mma_ksplit(float (&d)[NT][4], const float* a_s, 
         for (int j = 0; j < 4; ++j) d[i][j] = dm[i][j] + dx[i][j];
 }
 
-// Grid-wide barrier on a monotonically increasing counter (cooperative launch => co-resident), HIERARCHICAL: the
-// CTAs of a thread-block cluster meet at the hardware cluster barrier, ONE thread per cluster arrives at / polls the
-// L2 counter, and a second cluster barrier releases the cluster.  With 128 CTAs in clusters of 8 the counter sees 16
-// arrivals instead of 128 same-address atomics (the flat barrier measured 2600 cycles, most of it that serialisation).
-// Launched without a cluster dimension every CTA is its own cluster and this is the flat barrier.
+// Grid-wide barrier on a monotonically increasing counter (cooperative launch => co-resident).  Written
+// hierarchically: the CTAs of a thread-block cluster meet at the hardware cluster barrier, ONE thread per cluster
+// arrives at / polls the L2 counter, and a second cluster barrier releases the cluster.  Launched without a cluster
+// dimension (the default, see g_dec_cluster_log2) every CTA is its own cluster and this is the flat barrier.
 __device__ __forceinline__ uint32_t cluster_ctarank_() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
 __device__ __forceinline__ uint32_t cluster_nctarank_() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(r)); return r; }
 __device__ __forceinline__ void cluster_sync_() {

@@ -27,7 +27,9 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
 }
 
 // ---------------------------------------------------------------- forward
-template <int CS, int NS, int EW>
+// F16: the fp16 split scheme of rec_frag.cuh (3 MMAs per k16 and n-tile, h_t exchanged pre-split) instead of the
+// tf32 + bf16 scheme (4 MMAs, kept as test mode 7)
+template <int CS, int NS, int EW, bool F16>
 __global__ void __launch_bounds__(256 + 32 * EW, 1) rec_fwd_ws_kernel(MParams p) {
     constexpr int NR = 8 / EW;                                   // rows per epilogue thread (EW = 4: r0 and r0 + 8)
     constexpr int H = CS * UPC;
@@ -71,7 +73,7 @@ __global__ void __launch_bounds__(256 + 32 * EW, 1) rec_fwd_ws_kernel(MParams p)
         else asm volatile("setmaxnreg.inc.sync.aligned.u32 208;");
         const int g = lane / 4, tq = lane % 4, ng = w % 4, kh = w / 4;
         uint32_t bh[KT][2][2], bl[KT][2][2];
-        {
+        if (!F16) {
             const float* Wg = p.Wh + (size_t)dir * H * H * 4;
             const int ncol_unit = rank * UPC + 4 * ng + (g >> 1);
 #pragma unroll
@@ -103,6 +105,27 @@ __global__ void __launch_bounds__(256 + 32 * EW, 1) rec_fwd_ws_kernel(MParams p)
                     bl[2 * q + 1][nt][1] = pack_bf16(r[1][0], r[1][1]);
                 }
         }
+        if (F16) {
+            // the same registers hold the fp16 fragments: bh[q][nt] := packed fp16 W of pair q, bl[q][nt] := packed
+            // fp16 of (W - fp16 W) 2^11 (only the first KT / 2 entries of each array are used)
+            const float* Wg = p.Wh + (size_t)dir * H * H * 4;
+            const int ncol_unit = rank * UPC + 4 * ng + (g >> 1);
+#pragma unroll
+            for (int q = 0; q < KT / 2; ++q)
+#pragma unroll
+                for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+                    for (int j = 0; j < 2; ++j) {
+                        unsigned short hi[2], lo[2];
+#pragma unroll
+                        for (int e = 0; e < 2; ++e) {
+                            const int k = 8 * (kh * KT + 2 * q + j) + tq + 4 * e;
+                            split_f16(Wg[((size_t)k * H + ncol_unit) * 4 + 2 * nt + (g & 1)], hi[e], lo[e]);
+                        }
+                        bh[q][nt][j] = pack_u16(hi[0], hi[1]);
+                        bl[q][nt][j] = pack_u16(lo[0], lo[1]);
+                    }
+        }
         uint32_t phase = 0;                                      // bit (2 sl + buf)
         const bool rec = p.dbg != nullptr && blockIdx.x == 0 && tid == 0;
         for (int s = 1; s < T; ++s) {
@@ -121,14 +144,31 @@ __global__ void __launch_bounds__(256 + 32 * EW, 1) rec_fwd_ws_kernel(MParams p)
                 if (tid == 0) mbar_expect_tx(&full[sl][buf], CS * TILE * 4);     // arm this buffer's next phase
                 if (rec) p.dbg[(s * NS + sl) * 8 + 1] = clock64();
                 const float* hb = h_s + (size_t)(sl * 2 + buf) * CS * TILE + kh * KT * 128 + lane * 4;
-                float4 a0 = *reinterpret_cast<const float4*>(hb), a1 = *reinterpret_cast<const float4*>(hb + 128);
+                if (F16) {
+                    // source CTA kh*8 + q contributes one k16 pair: [hi fragments 512 B | lo' fragments 512 B]
+                    uint4 a0 = *reinterpret_cast<const uint4*>(hb), a1 = *reinterpret_cast<const uint4*>(hb + 128);
 #pragma unroll
-                for (int q = 0; q < KT / 2; ++q) {
-                    const int qn = q + 1 < KT / 2 ? q + 1 : q;
-                    const float4 n0 = *reinterpret_cast<const float4*>(hb + (2 * qn) * 128);
-                    const float4 n1 = *reinterpret_cast<const float4*>(hb + (2 * qn + 1) * 128);
-                    k16_mma<2>(acc, accx, a0, a1, bh[2 * q], bh[2 * q + 1], bl[2 * q], bl[2 * q + 1]);
-                    a0 = n0; a1 = n1;
+                    for (int q = 0; q < KT / 2; ++q) {
+                        const int qn = q + 1 < KT / 2 ? q + 1 : q;
+                        const uint4 n0 = *reinterpret_cast<const uint4*>(hb + (2 * qn) * 128);
+                        const uint4 n1 = *reinterpret_cast<const uint4*>(hb + (2 * qn + 1) * 128);
+                        k16_mma_f16<2>(acc, accx, a0, a1, bh[q], bl[q]);
+                        a0 = n0; a1 = n1;
+                    }
+#pragma unroll
+                    for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) accx[nt][q] *= kF16LoInv;
+                } else {
+                    float4 a0 = *reinterpret_cast<const float4*>(hb), a1 = *reinterpret_cast<const float4*>(hb + 128);
+#pragma unroll
+                    for (int q = 0; q < KT / 2; ++q) {
+                        const int qn = q + 1 < KT / 2 ? q + 1 : q;
+                        const float4 n0 = *reinterpret_cast<const float4*>(hb + (2 * qn) * 128);
+                        const float4 n1 = *reinterpret_cast<const float4*>(hb + (2 * qn + 1) * 128);
+                        k16_mma<2>(acc, accx, a0, a1, bh[2 * q], bh[2 * q + 1], bl[2 * q], bl[2 * q + 1]);
+                        a0 = n0; a1 = n1;
+                    }
                 }
                 // partial pre-activations of unit 4ng+tq, rows g and g+8 (4 gates each) -> epilogue warps
                 float4* zb = zbuf + (size_t)(sl * 2 + kh) * 16 * ZST + 4 * ng + tq;
@@ -225,7 +265,20 @@ __global__ void __launch_bounds__(256 + 32 * EW, 1) rec_fwd_ws_kernel(MParams p)
                 // publish h_t (state h: carried through for masked rows): tile -> L2 -> multicast to the cluster
                 if (s + 1 < T) {
                     float* gt = p.xg + ((size_t)(sl * 2 + buf) * gridDim.x + blockIdx.x) * TILE;
-                    if (NR == 2) *reinterpret_cast<float2*>(gt + fpos) = make_float2(h_reg[sl][0], h_reg[sl][NR - 1]);
+                    if (F16) {
+                        // the CTA's 16 units are one k16 pair: 16-bit slot of (row, unit) in the packed fragments =
+                        // lane (row % 8, unit % 4) * 8 + (2 * (unit / 8) + row / 8) * 2 + (unit / 4) % 2; hi' plane, then lo'
+                        unsigned short* gh = reinterpret_cast<unsigned short*>(gt);
+#pragma unroll
+                        for (int j = 0; j < NR; ++j) {
+                            const int row = r0 + 8 * j;
+                            const int hp = ((row & 7) * 4 + (ul & 3)) * 8 + (2 * (ul >> 3) + (row >> 3)) * 2 + ((ul >> 2) & 1);
+                            unsigned short hi, lo;
+                            split_f16(h_reg[sl][j], hi, lo);
+                            gh[hp] = hi;
+                            gh[256 + hp] = lo;
+                        }
+                    } else if (NR == 2) *reinterpret_cast<float2*>(gt + fpos) = make_float2(h_reg[sl][0], h_reg[sl][NR - 1]);
                     else gt[fpos] = h_reg[sl][0];
                     asm volatile("fence.proxy.async.global;" ::: "memory");
                     __syncwarp();
@@ -507,9 +560,14 @@ constexpr int ews(int NS) { return NS == 2 ? 8 : 4; }
 size_t fwd_ws_smem(int CS, int NS) { return sizeof(float) * ((size_t)NS * 2 * CS * TILE) + (size_t)NS * 2 * 16 * ZST * 16; }
 size_t bwd_ws_smem(int CS, int NS) { return sizeof(float) * ((size_t)NS * 4 * CS * TILE + (size_t)NS * 2 * 8 * 128); }
 
+}  // namespace
+int g_rec_fwd_f16 = 1;      // forward recurrence: 1 = fp16 split scheme, 0 = tf32 + bf16 scheme (test mode 7)
+
+namespace {
+
 template <int CS, int NS>
 int launch_ws(cudaStream_t st, bool bwd, const MParams& p, int nclusters, int* max_active) {
-    auto kf = rec_fwd_ws_kernel<CS, NS, ews(NS)>;
+    auto kf = g_rec_fwd_f16 ? rec_fwd_ws_kernel<CS, NS, ews(NS), true> : rec_fwd_ws_kernel<CS, NS, ews(NS), false>;
     auto kb = rec_bwd_ws_kernel<CS, NS, ews(NS)>;
     const void* fn = bwd ? (const void*)kb : (const void*)kf;
     size_t smem = bwd ? bwd_ws_smem(CS, NS) : fwd_ws_smem(CS, NS);

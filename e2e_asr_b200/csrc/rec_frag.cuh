@@ -2,6 +2,7 @@
 // cluster / mbarrier / bulk-copy PTX wrappers, the 3xTF32 and mixed tf32+bf16 fragment products.
 #pragma once
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 
 #include "common.cuh"
 
@@ -165,6 +166,37 @@ __device__ __forceinline__ void k16_mma(float (&acc)[NTL][4], float (&accx)[NTL]
     for (int nt = 0; nt < NTL; ++nt) mma_bf16(accx[nt], ab, wl[nt][0], wl[nt][1]);
 }
 
+// fp16 split scheme of the FORWARD recurrence: x = hi + lo' 2^-11 with hi = fp16(x) (11 significand bits) and
+// lo' = fp16((x - hi) 2^11) -- the residual scaled into fp16's normal range, so |x - hi - lo' 2^-11| <= 2^-23 |x|.
+// Per k16 and n-tile THREE m16n8k16 f16 MMAs:  acc += hi_a hi_w;  accx += lo'_a hi_w + hi_a lo'_w;  z = acc + 2^-11 accx
+// (the dropped lo lo term is <= 2^-23 of the product: the accuracy class of 3xTF32) instead of the four of the
+// tf32 + bf16 scheme above, and no per-step operand conversion in the k-loop: the h_t tiles are exchanged already
+// split and packed in fragment order.  Only for operands with a bounded range (|h| < 1, weights): fp16 has 5
+// exponent bits, so the backward pass (gradients span many orders of magnitude) keeps the tf32 + bf16 scheme.
+constexpr float kF16LoScale = 2048.0f, kF16LoInv = 1.0f / 2048.0f;
+__device__ __forceinline__ void split_f16(float x, unsigned short& hi, unsigned short& lo) {
+    const __half h = __float2half_rn(x);
+    const __half l = __float2half_rn((x - __half2float(h)) * kF16LoScale);
+    hi = __half_as_ushort(h);
+    lo = __half_as_ushort(l);
+}
+__device__ __forceinline__ uint32_t pack_u16(unsigned short lo, unsigned short hi) { return (uint32_t)lo | ((uint32_t)hi << 16); }
+__device__ __forceinline__ void mma_f16(float (&d)[4], const uint4 a, uint32_t b0, uint32_t b1) {
+    asm("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+        : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+        : "r"(a.x), "r"(a.y), "r"(a.z), "r"(a.w), "r"(b0), "r"(b1));
+}
+// ah / al: the thread's packed A fragments (hi and lo' halves) of one k16 pair; wh / wl: the resident W fragments
+template <int NTL>
+__device__ __forceinline__ void k16_mma_f16(float (&acc)[NTL][4], float (&accx)[NTL][4], const uint4 ah, const uint4 al,
+                                            const uint32_t (&wh)[NTL][2], const uint32_t (&wl)[NTL][2]) {
+#pragma unroll
+    for (int nt = 0; nt < NTL; ++nt) mma_f16(acc[nt], ah, wh[nt][0], wh[nt][1]);
+#pragma unroll
+    for (int nt = 0; nt < NTL; ++nt) mma_f16(accx[nt], al, wh[nt][0], wh[nt][1]);
+#pragma unroll
+    for (int nt = 0; nt < NTL; ++nt) mma_f16(accx[nt], ah, wl[nt][0], wl[nt][1]);
+}
 
 }  // namespace
 }  // namespace e2e

@@ -53,7 +53,7 @@ def test_gemm_strided_views():
     assert relerr(cs, big[:, 8:24].cpu().numpy().sum(0)) < 2e-5
 
 
-@pytest.mark.parametrize("rec_mode", [0, 1, 2, 3, 4, 5, 6])
+@pytest.mark.parametrize("rec_mode", [0, 1, 2, 3, 4, 5, 6, 7])
 @pytest.mark.parametrize("B,T_,I,H", [(3, 11, 6, 8), (5, 20, 12, 16), (17, 9, 40, 24), (4, 30, 40, 256),
                                       (70, 6, 16, 32), (33, 25, 24, 128), (64, 40, 16, 256), (130, 7, 8, 256)])
 def test_bilstm_layer_fwd_bwd(B, T_, I, H, rec_mode):
