@@ -1,19 +1,29 @@
 #!/usr/bin/env python
 """Benchmark of the hot path: teacher-forced fwd+bwd training step.
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--config cfg2]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--config cfg2|cfg4|cfg5]
+                  [--scaling weak|strong] [--defaults]
 
 Prints ONE JSON line (rank 0).  metric = train frames/sec (valid log-mel frames,
-sum of logmel_len) for fwd + bwd + gradient clipping on BASELINE.json configs[1]
-("cfg2": B=64/GPU, T=700, F=120, 4-layer pyramidal BiLSTM 256/dir, char attention
-decoder, phone+state aux CTC), weak scaling (per-GPU batch fixed).
+sum of logmel_len) for fwd + bwd + gradient all-reduce + clipping on BASELINE.json
+configs[1] ("cfg2": B=64/GPU, T=700, F=120, 4-layer pyramidal BiLSTM 256/dir, char
+attention decoder, phone+state aux CTC).  --scaling weak (default): the config's batch
+per GPU; strong: the config's batch split over the GPUs.
 
-  value : inputs already resident in HBM when the timed region starts
-  e2e   : the same step through the public API from pinned HOST buffers (H2D of
-          the batch + D2H of the loss inside the timed region)
-  --impl reference : the reference's CPU path.  TensorFlow-1.x / Python 2 cannot run
-          in this image, so this is the line-by-line NumPy restatement in oracle/
-          ("port"), float32, all host cores, on a bounded sample of the workload.
+  value            inputs already resident in HBM when the timed region starts
+  e2e              the same step through the public API from pinned HOST buffers (H2D of
+                   the batch + D2H of the loss inside the timed region)
+  roofline         the DOMINANT kernel = the kernel with the largest time on the main
+                   stream (the critical path): algorithmic rate vs the measured peak, its
+                   latency floor for a sequential kernel, DRAM traffic from profiles/
+  pct_of_roofline  SURVEY.md 8(d): sum_k (algorithmic time of kernel k at its bound) / step
+  cpu_baseline     the NumPy restatement (oracle/) on a bounded sample of the workload
+  --impl reference the reference's CPU path on the FULL batch: TensorFlow-1.x / Python 2
+                   cannot run in this image, so this is the line-by-line NumPy restatement in
+                   oracle/ ("port"), float32, all host cores (median of 5), plus a
+                   single-thread figure (the reference's own setting, train.py:178)
+  --defaults       the reference's default training settings (out_prob = out_prob_dec = 0.9
+                   captured in the graph; samp_prob = 0.1 runs the eager step)
 """
 import argparse
 import json
@@ -224,8 +234,8 @@ def roofline_report(raw, cfg, peaks, K, ms_per_step, clocks, gemm_mode):
     peak_tc = peaks["tc_sustained"]
     # tensor-pipe cost of one algorithmic product: 3xTF32 = 3 MMAs ("divides the peak by its split count")
     # which moreover run at half the bf16 rate (kind::tf32) -> issue ceiling peak / 6; bf16x2 = 3 bf16 MMAs
-    split = {0: 1, 1: 3, 2: 1, 3: 3}[gemm_mode]
-    units = {0: 1, 1: 6, 2: 1, 3: 3}[gemm_mode]
+    split = {0: 1, 1: 3, 2: 1, 3: 3, 4: 3}[gemm_mode]
+    units = {0: 1, 1: 6, 2: 1, 3: 3, 4: 3}[gemm_mode]
     traffic = load_traffic()
     H, Bn = cfg.H, cfg.B
     nd = 2 if cfg.get("bi_dir", True) else 1
@@ -349,7 +359,7 @@ def roofline_report(raw, cfg, peaks, K, ms_per_step, clocks, gemm_mode):
     pct = {"value": sum(at_bound.values()) / ms_per_step, "terms_ms": at_bound, "step_ms": ms_per_step,
            "definition": "SURVEY.md 8(d): sum over kernels of the algorithmic time at the kernel's bound / measured step: "
                          "GEMM FLOPs at peak/%d (mode %s), sequential timesteps x latency floor, attention / CE / CTC "
-                         "bytes at the HBM peak" % (split, {0: "fp32", 1: "tf32x3", 2: "bf16", 3: "bf16x2"}[gemm_mode])}
+                         "bytes at the HBM peak" % (split, {0: "fp32", 1: "tf32x3", 2: "bf16", 3: "bf16x2", 4: "f16x2"}[gemm_mode])}
     return {"roofline": roof, "breakdown": breakdown, "sequential_kernels": seq, "memory_bound_kernels": memory_bound,
             "gemm": gemm, "pct_of_roofline": pct}
 
@@ -363,10 +373,15 @@ def main():
     ap.add_argument("--config", default="cfg2", help="cfg2 (default, BASELINE configs[1]) | cfg4 | cfg5 | cfg1")
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
                     help="weak: the config's batch PER GPU (default); strong: the config's batch split over the GPUs")
-    ap.add_argument("--gemm", default="tf32x3", help="fp32 | tf32x3 | bf16x2 | bf16 (default: tf32x3, the fp32-accurate tensor-core mode)")
+    ap.add_argument("--gemm", default="tf32x3", help="fp32 | tf32x3 | f16x2 | bf16x2 | bf16 (tf32x3 and f16x2 are the fp32-accurate tensor-core modes)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-beam", action="store_true", help="skip the beam-decode utt/s side measurement")
     ap.add_argument("--no-graph", action="store_true", help="time the eager step instead of its CUDA-graph replay")
+    ap.add_argument("--dropout", action="store_true",
+                    help="the reference's default output dropout: out_prob = out_prob_dec = 0.9 (captured in the graph)")
+    ap.add_argument("--defaults", action="store_true",
+                    help="the reference's default training settings: --dropout plus samp_prob = 0.1 (scheduled sampling "
+                         "realises its ids from the host: eager step)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -414,6 +429,18 @@ def main():
     frames = int(batch["logmel_len"].sum())
     reducer = edist.GradAllReducer() if world > 1 else None
     model = build_model(cfg, weights, device=dev, reducer=reducer)
+    settings = {}
+    if args.dropout or args.defaults:
+        # encoder.py:24, decoder.py:25: the keep probabilities the reference trains with
+        model.params.encoder_params.out_prob = 0.9
+        for d_ in model.params.decoder_params.values():
+            d_.out_prob_dec = 0.9
+        settings["dropout"] = "out_prob = out_prob_dec = 0.9 (reference defaults)"
+    if args.defaults:
+        for d_ in model.params.decoder_params.values():
+            d_.samp_prob = 0.1                                      # decoder.py:30
+        settings["samp_prob"] = 0.1
+        args.no_graph = True
 
     def barrier():
         if world > 1:
@@ -550,8 +577,9 @@ def main():
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
         "ms_per_step": ms / K, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
-        "dtype": {0: "f32", 1: "tf32x3", 2: "bf16", 3: "bf16x2"}[ops.get_gemm_mode()], "data": "synthetic",
-        "config": workload_config(args.config, world, batch_per_gpu=cfg.B), "frames_per_step_per_gpu": frames,
+        "dtype": {0: "f32", 1: "tf32x3", 2: "bf16", 3: "bf16x2", 4: "f16x2"}[ops.get_gemm_mode()], "data": "synthetic",
+        "config": workload_config(args.config, world, batch_per_gpu=cfg.B, settings=settings),
+        "frames_per_step_per_gpu": frames,
         "padded_frames_per_step_per_gpu": cfg.B * cfg.T, "loss": loss_val,
         "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "launches_per_step": launches / K,
         "step_mode": mode, "host_enqueue_ms_per_step": host_busy_ms,
@@ -581,15 +609,15 @@ def main():
 def beam_decode_rate(cfg_name, dev, n_utts=256, beam=10, cpu=True):
     """Second half of BASELINE.json's metric: beam-search decoding (BASELINE configs[2]: beam width 10, a synthetic
     eval batch of 256 utterances with T_enc in [50, 88]) in utterances/s through BeamSearch.decode_batch, next to the
-    CPU restatement of beam_search.py (serial over utterances like eval_model.py:194-195) on ONE utterance."""
+    CPU restatement of beam_search.py (serial over utterances like eval_model.py:194-195) timed on a 4-utterance
+    sample; the ids of ALL utterances are compared with the oracle's (tests/golden/fullsize_beam.npz, generated once
+    by tests/golden/gen_fullsize_golden.py -- the full CPU run takes minutes)."""
     import torch
     from e2e_asr_b200 import synth
     from e2e_asr_b200.beam_search import BeamSearch
     cfg = synth.get_config(cfg_name)
     w = synth.make_weights(cfg)
-    rng = np.random.Generator(np.random.PCG64(17))
-    encs = [(np.tanh(rng.standard_normal((int(rng.integers(50, 89)), 2 * cfg.H))) * 0.8).astype(np.float32)
-            for _ in range(n_utts)]
+    encs = synth.make_beam_eval_batch(cfg, n_utts)
     sp = BeamSearch.class_params()
     sp.beam_size = beam
     bs = BeamSearch(w, sp, device=dev)
@@ -599,18 +627,32 @@ def beam_decode_rate(cfg_name, dev, n_utts=256, beam=10, cpu=True):
     out = bs.decode_batch(encs)
     torch.cuda.synchronize()
     dt = time.perf_counter() - t0
+    steps = max(len(o) for o in out)
+    Hd, Hl, D, E, A, V = cfg.Hd, cfg.Hl, 2 * cfg.H, cfg.E, cfg.A, cfg.V
+    flop_row = 2.0 * ((E + Hl) * 4 * Hl + (Hd + D) * E + (E + Hd) * 4 * Hd + Hd * A + (Hd + D) * Hd + Hd * V)
     res = {"value": n_utts / dt, "unit": "utt/s", "beam_size": beam, "n_utts": n_utts,
-           "mean_output_len": float(np.mean([len(o) for o in out])),
-           "note": "random-init weights: hypotheses run to the 120-step limit (worst case); wall clock incl. the "
-                   "host-side k^2 candidate merge"}
+           "mean_output_len": float(np.mean([len(o) for o in out])), "ms_per_decoding_step": dt * 1e3 / steps,
+           "fp64_gemm_tflops": flop_row * n_utts * beam * steps / dt / 1e12,
+           "note": "random-init weights: hypotheses run to the 120-step limit (worst case); wall clock of decode_batch: "
+                   "float64 decoder step on all 2560 hypothesis slots + device-side k^2 candidate merge, one CUDA-graph "
+                   "replay per decoding step, sequences rebuilt from back-pointers on the host at the end"}
+    gold = os.path.join(ROOT, "tests", "golden", "fullsize_beam.npz")
+    if os.path.exists(gold) and n_utts == 256 and beam == 10 and cfg_name == "cfg2":
+        g = np.load(gold)
+        off = np.concatenate([[0], np.cumsum(g["lens"])])
+        same = [bool(np.array_equal(out[u], g["ids"][off[u]:off[u + 1]])) for u in range(n_utts)]
+        res["ids_equal"] = bool(all(same))
+        res["ids_equal_utterances"] = "%d of %d (oracle ids: tests/golden/fullsize_beam.npz)" % (sum(same), n_utts)
     if cpu:
         from oracle import beam as ob
+        n_cpu = 4
         t0 = time.perf_counter()
-        ref = ob.beam_search(w, encs[0], beam_size=beam)
+        ref = [ob.beam_search(w, e, beam_size=beam) for e in encs[:n_cpu]]
         dt1 = time.perf_counter() - t0
-        res["cpu_baseline"] = {"value": 1.0 / dt1, "unit": "utt/s", "cores": 1, "kind": "port",
-                               "sample": "1 utterance, Python restatement of beam_search.py (oracle/beam.py)",
-                               "ids_equal": bool(np.array_equal(ref, out[0]))}
+        res["cpu_baseline"] = {"value": n_cpu / dt1, "unit": "utt/s", "cores": 1, "kind": "port",
+                               "sample": "%d utterances, Python restatement of beam_search.py (oracle/beam.py), serial "
+                                         "like eval_model.py:194-195" % n_cpu,
+                               "ids_equal": bool(all(np.array_equal(r, o) for r, o in zip(ref, out)))}
     return res
 
 

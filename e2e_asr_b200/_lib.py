@@ -15,7 +15,8 @@ LIB_PATH = os.path.join(_HERE, "libe2e_asr_b200.so")
 # signature codes: p = device/host pointer, i = int, l = long long, z = size_t, f = float
 _SIGS = {
     "e2e_gemm": "piiiiiipipipippii",
-    "e2e_gemm_lo": "piiiiiippippipippiizz",
+    "e2e_gemm_lo": "piiiiiippippipippiizzp",
+    "e2e_split_rows_f16": "pzippp",
     "e2e_split_lo": "pizpp",
     "e2e_colsum": "piipipi",
     "e2e_lstm_pack_weights": "piipppiipp",
@@ -130,8 +131,6 @@ def lib():
         l.e2e_set_rec_mode.argtypes = [ctypes.c_int]
         l.e2e_decoder_persist_fits.restype = ctypes.c_int
         l.e2e_decoder_persist_fits.argtypes = [ctypes.c_void_p]
-        l.e2e_set_dec_cluster.restype = ctypes.c_int
-        l.e2e_set_dec_cluster.argtypes = [ctypes.c_int]
         l.e2e_ctc_workspace_floats.restype = ctypes.c_size_t
         l.e2e_ctc_workspace_floats.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_int]
         l.e2e_set_tc_debug.restype = ctypes.c_int
@@ -142,7 +141,7 @@ def lib():
 
 def exported_symbols():
     return sorted(list(_SIGS.keys()) + ["e2e_last_error", "e2e_version", "e2e_sm_count", "e2e_launch_count", "e2e_capture_status",
-                   "e2e_set_workspace", "e2e_set_dec_cluster", "e2e_ctc_workspace_floats", "e2e_decoder_persist_fits", "e2e_set_tc_debug", "e2e_set_rec_mode", "e2e_set_rec_debug", "e2e_set_stream_workspace"])
+                   "e2e_set_workspace", "e2e_ctc_workspace_floats", "e2e_decoder_persist_fits", "e2e_set_tc_debug", "e2e_set_rec_mode", "e2e_set_rec_debug", "e2e_set_stream_workspace"])
 
 
 def _ptr(x):

@@ -32,13 +32,13 @@ int sm_count() {
 int gemm_simt(cudaStream_t, int, int, int, int, int, const float*, int, const float*, int, float*, int,
               const float*, const float*, int, int);
 int gemm_tc(cudaStream_t, int mode, int, int, int, int, int, const float*, int, const float*, int, float*, int,
-            const float*, const float*, int, int, bool*, const float*, const float*, size_t, size_t);
+            const float*, const float*, int, int, bool*, const float*, const float*, size_t, size_t, const float*);
+int split_rows_f16(cudaStream_t, size_t, int, const float*, float*, float*);
 int split_lo(cudaStream_t, int, size_t, const float*, float*);
 void set_workspace(void*, size_t);
 bool set_stream_workspace(cudaStream_t, void*, size_t);
 extern int g_rec_mode;
 extern long long* g_rec_dbg;
-extern int g_dec_cluster_log2;
 void set_tc_debug(float*, long long);
 int colsum(cudaStream_t, int, int, const float*, int, float*, int);
 int lstm_rec(cudaStream_t, bool, int, int, int, int, int, long long, long long, float*, float*, float*,
@@ -100,11 +100,11 @@ int embed_gather_f64(cudaStream_t, int, int, const float*, const long long*, dou
 static int gemm_any(cudaStream_t st, int mode, int tA, int tB, int M, int N, int K, const float* A, int lda,
                     const float* B, int ldb, float* C, int ldc, const float* bias, const float* Z, int ldz,
                     int accumulate, const float* A_lo = nullptr, const float* B_lo = nullptr, size_t a_plane = 0,
-                    size_t b_plane = 0) {
+                    size_t b_plane = 0, const float* row_scale = nullptr) {
     if (mode != 0) {
         bool handled = false;
         int rc = gemm_tc(st, mode, tA, tB, M, N, K, A, lda, B, ldb, C, ldc, bias, Z, ldz, accumulate, &handled, A_lo,
-                         B_lo, a_plane, b_plane);
+                         B_lo, a_plane, b_plane, row_scale);
         if (rc) return rc;
         if (handled) return 0;
     }
@@ -147,9 +147,12 @@ int e2e_gemm(void* stream, int mode, int transA, int transB, int M, int N, int K
 }
 int e2e_gemm_lo(void* stream, int mode, int transA, int transB, int M, int N, int K, const float* A, const float* A_lo,
                 int lda, const float* B, const float* B_lo, int ldb, float* C, int ldc, const float* bias,
-                const float* Z, int ldz, int accumulate, size_t a_plane, size_t b_plane) {
+                const float* Z, int ldz, int accumulate, size_t a_plane, size_t b_plane, const float* a_row_scale) {
     return gemm_any(ST(stream), mode, transA, transB, M, N, K, A, lda, B, ldb, C, ldc, bias, Z, ldz, accumulate, A_lo,
-                    B_lo, a_plane, b_plane);
+                    B_lo, a_plane, b_plane, a_row_scale);
+}
+int e2e_split_rows_f16(void* stream, size_t rows, int cols, const float* x, float* planes, float* row_inv) {
+    return split_rows_f16(ST(stream), rows, cols, x, planes, row_inv);
 }
 int e2e_split_lo(void* stream, int mode, size_t n, const float* x, float* lo) {
     return split_lo(ST(stream), mode, n, x, lo);
@@ -195,11 +198,6 @@ int e2e_set_tc_debug(float* dbg, long long min_work) {
 }
 int e2e_set_rec_mode(int mode) {
     g_rec_mode = mode;
-    return 0;
-}
-int e2e_set_dec_cluster(int log2_size) {
-    if (log2_size < 0 || log2_size > 3) return 1;
-    g_dec_cluster_log2 = log2_size;
     return 0;
 }
 int e2e_set_rec_debug(long long* dbg) {

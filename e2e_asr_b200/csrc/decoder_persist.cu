@@ -22,11 +22,6 @@
 namespace e2e {
 
 extern long long* g_rec_dbg;
-// largest cluster size (2^n) tried by the persistent decoder kernels (test hook e2e_set_dec_cluster).  Default 0 = flat
-// barrier: measured at cfg-2, clusters of 8 made the step SLOWER (forward 13.8 -> 17.0 us, backward 17.9 -> 21.4 us per
-// decoder step: two hardware cluster barriers + the leader's round trip cost more than 128 same-address arrivals), and
-// a cooperative launch with a cluster dimension costs the host ~7 ms of validation when launched eagerly.
-int g_dec_cluster_log2 = 0;
 
 namespace {
 
@@ -120,29 +115,18 @@ __device__ __forceinline__ void mma_ksplit(float (&d)[NT][4], const float* a_s, 
         for (int j = 0; j < 4; ++j) d[i][j] = dm[i][j] + dx[i][j];
 }
 
-// Grid-wide barrier on a monotonically increasing counter (cooperative launch => co-resident).  Written
-// hierarchically: the CTAs of a thread-block cluster meet at the hardware cluster barrier, ONE thread per cluster
-// arrives at / polls the L2 counter, and a second cluster barrier releases the cluster.  Launched without a cluster
-// dimension (the default, see g_dec_cluster_log2) every CTA is its own cluster and this is the flat barrier.
-__device__ __forceinline__ uint32_t cluster_ctarank_() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
-__device__ __forceinline__ uint32_t cluster_nctarank_() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(r)); return r; }
-__device__ __forceinline__ void cluster_sync_() {
-    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
-    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
+// grid-wide barrier on a monotonically increasing counter (cooperative launch => co-resident)
 __device__ __forceinline__ void grid_barrier(unsigned* ctr, unsigned& epoch, int* err) {
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // generic smem writes before later bulk copies
     __syncthreads();
-    if (threadIdx.x == 0) __threadfence();                            // this CTA's global writes, gpu scope
-    cluster_sync_();
-    ++epoch;
-    if (threadIdx.x == 0 && cluster_ctarank_() == 0) {
-        __threadfence();
+    if (threadIdx.x == 0) {
+        // red.release.gpu is cumulative over the CTA barrier above (the other threads' writes are ordered before it),
+        // and the polling load is an acquire: no separate fence
         red_release_gpu_add(ctr, 1u);
-        spin_wait_ge(ctr, epoch * (gridDim.x / cluster_nctarank_()), err);
-        __threadfence();
+        ++epoch;
+        spin_wait_ge(ctr, epoch * gridDim.x, err);
     }
-    cluster_sync_();
+    __syncthreads();
 }
 
 __device__ __forceinline__ float ldcg(const float* p) { return __ldcg(p); }
@@ -1113,42 +1097,8 @@ int dec_persist(cudaStream_t st, bool bwd, const e2e_dec_persist_args* a, float*
     }
     int attn_cap = bwd ? bwd_attn_fast(p, &smem) : fwd_attn_cap(p, &smem);
     E2E_CHECK_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    // cooperative launch in clusters of up to 8 CTAs (hierarchical grid barrier); the cluster size must divide the
-    // grid and all clusters must be co-resident, else smaller clusters / the flat barrier
-    static int cluster_ok[2][4] = {{-1, -1, -1, -1}, {-1, -1, -1, -1}};       // [bwd][log2 cs]: launch worked before
-    cudaError_t lerr = cudaErrorUnknown;
-    for (int lg = g_dec_cluster_log2; lg >= 0; --lg) {
-        const int cs = 1 << lg;
-        if (grid % cs != 0 || cluster_ok[bwd][lg] == 0) continue;
-        cudaLaunchConfig_t cfg = {};
-        cfg.gridDim = dim3(grid);
-        cfg.blockDim = dim3(NTH);
-        cfg.dynamicSmemBytes = smem;
-        cfg.stream = st;
-        cudaLaunchAttribute attr[2];
-        attr[0].id = cudaLaunchAttributeCooperative;
-        attr[0].val.cooperative = 1;
-        attr[1].id = cudaLaunchAttributeClusterDimension;
-        attr[1].val.clusterDim.x = cs;
-        attr[1].val.clusterDim.y = 1;
-        attr[1].val.clusterDim.z = 1;
-        cfg.attrs = attr;
-        cfg.numAttrs = cs > 1 ? 2 : 1;
-        if (cs > 1 && cluster_ok[bwd][lg] < 0) {
-            int max_clusters = 0;
-            if (cudaOccupancyMaxActiveClusters(&max_clusters, fn, &cfg) != cudaSuccess || max_clusters * cs < grid) {
-                cudaGetLastError();
-                cluster_ok[bwd][lg] = 0;
-                continue;
-            }
-        }
-        lerr = bwd ? cudaLaunchKernelEx(&cfg, dec_bwd_persist_kernel, p, attn_cap)
-                   : cudaLaunchKernelEx(&cfg, dec_fwd_persist_kernel, p, attn_cap);
-        if (lerr == cudaSuccess) { cluster_ok[bwd][lg] = 1; break; }
-        cudaGetLastError();
-        cluster_ok[bwd][lg] = 0;
-    }
-    E2E_CHECK_CUDA(lerr);
+    void* args[] = {&p, &attn_cap};
+    E2E_CHECK_CUDA(cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(NTH), args, smem, st));
     ++g_launches;
     if (bwd) {
         dec_denc_kernel<<<p.B * p.Tn, 256, sizeof(float) * p.U, st>>>(p, denc);

@@ -15,6 +15,13 @@
 //          the kernel accumulates hi*hi + hi*lo + lo*hi with three kind::f16 MMAs: error ~2^-17 relative per
 //          product (well inside the 1e-4 budget) at HALF the tensor-pipe cost of 3xTF32, because kind::f16 runs
 //          at twice the kind::tf32 rate.
+//   mode 4 "f16x2":  each fp32 operand is split into hi = fp16(x) and lo' = fp16((x - hi) * 2^11) -- the residual scaled
+//          into fp16's normal range, 22 significand bits in all -- and the kernel keeps TWO TMEM accumulators:
+//          main += hi*hi, cross += hi*lo' + lo'*hi, C = main + cross * 2^-11: error ~2^-22 relative, the accuracy
+//          class of 3xTF32, at the kind::f16 rate (twice kind::tf32) -- half the tensor-pipe cost.  fp16 has 5 exponent
+//          bits, so the A operand (activations, or gradients spanning many orders of magnitude ACROSS rows) is scaled
+//          per ROW by a power of two before the split and the output row is scaled back in the epilogue; B must be
+//          bounded (weights).  A transposed A (weight-gradient products, whose K runs over the rows) stays on mode 1.
 // All four transpose combinations are native: a row-major operand whose
 // contiguous dimension is K is a K-major UMMA operand, otherwise an MN-major one
 // (instruction-descriptor bits 15/16); TMA boxes always follow the contiguous
@@ -25,6 +32,7 @@
 // 32 TMEM lanes its warp-id%4 may access).  3-stage mbarrier ring, 64 KB/stage.
 #include <cuda.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 
 #include "common.cuh"
 
@@ -37,7 +45,6 @@ constexpr int STAGES = 3;
 constexpr int OPER_BYTES = 16384;                  // one 128 x (128 B) operand tile
 constexpr int STAGE_BYTES = 4 * OPER_BYTES;        // A_big, A_small, B_big, B_small (bf16: A, -, B, -)
 constexpr int TC_THREADS = 192;
-constexpr int TMEM_COLS = 128;
 
 // ------------------------------------------------------------------ PTX helpers
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -135,16 +142,20 @@ struct TcParams {
     int accumulate;
     int kblocks_per_split;     // K blocks (of BKE elements) handled by one blockIdx.z
     int a_mn_major, b_mn_major;
+    const float* row_scale;    // mode 4: C row m is multiplied by row_scale[m] (undoes the per-row operand scaling), or NULL
     float* dbg;                // debug: if set, stage-0 smem (64 KB) and the raw TMEM tile are dumped here
 };
 
 // BF16: element = 2 bytes, 64 elements per 128 B, UMMA_K = 16;  TF32: 4 bytes, 32 per 128 B, UMMA_K = 8.
-// MODE 1 = 3xTF32, 2 = bf16, 3 = bf16x2 (two bf16 parts per operand, three products).
+// MODE 1 = 3xTF32, 2 = bf16, 3 = bf16x2 (two bf16 parts per operand, three products), 4 = f16x2 (two fp16 parts, the
+// low one scaled by 2^11, cross terms in a second accumulator).
 template <int MODE>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA1,
                const __grid_constant__ CUtensorMap mapB0, const __grid_constant__ CUtensorMap mapB1, TcParams p) {
-    constexpr bool BF16 = MODE >= 2;
+    constexpr bool BF16 = MODE >= 2;               // 2-byte operands (bf16 or fp16): kind::f16
+    constexpr bool F16X2 = MODE == 4;
+    constexpr int TMEM_COLS = F16X2 ? 256 : 128;   // f16x2: main accumulator in columns [0,128), cross terms in [128,256)
     constexpr int PARTS = MODE == 2 ? 1 : 2;       // operand parts staged per k-block
     constexpr int BKE = BF16 ? 64 : 32;            // K elements per stage (one 128-byte swizzle span)
     constexpr int ELT = BF16 ? 2 : 4;
@@ -209,7 +220,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
         // ================= MMA issuer (single thread) =================
         if (lane == 0) {
             // instruction descriptor: D=f32, A/B format, majors, N>>3, M>>4
-            uint32_t idesc = (1u << 4) | ((BF16 ? 1u : 2u) << 7) | ((BF16 ? 1u : 2u) << 10) |
+            constexpr uint32_t FMT = F16X2 ? 0u : (BF16 ? 1u : 2u);      // kind::f16: 0 = F16, 1 = BF16; kind::tf32: 2
+            uint32_t idesc = (1u << 4) | (FMT << 7) | (FMT << 10) |
                              ((uint32_t)(p.a_mn_major ? 1 : 0) << 15) | ((uint32_t)(p.b_mn_major ? 1 : 0) << 16) |
                              ((uint32_t)(TBN >> 3) << 17) | ((uint32_t)(TBM >> 4) << 24);
             constexpr int UK = BF16 ? 16 : 8;                  // K elements per instruction
@@ -238,9 +250,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
                     } else {
                         const uint64_t a1 = make_sdesc(st + OPER_BYTES + k * a_step, a_lbo, a_sbo, a_lt);
                         const uint64_t b1 = make_sdesc(st + 3 * OPER_BYTES + k * b_step, b_lbo, b_sbo, b_lt);
-                        umma<BF16>(tmem_d, a1, b0, idesc, (i | k) != 0);      // small * big
-                        umma<BF16>(tmem_d, a0, b1, idesc, 1);                 // big * small
-                        umma<BF16>(tmem_d, a0, b0, idesc, 1);                 // big * big
+                        if (F16X2) {
+                            umma<true>(tmem_d + 128, a1, b0, idesc, (i | k) != 0);   // lo' * hi  -> cross accumulator
+                            umma<true>(tmem_d + 128, a0, b1, idesc, 1);              // hi * lo'
+                            umma<true>(tmem_d, a0, b0, idesc, (i | k) != 0);         // hi * hi   -> main accumulator
+                        } else {
+                            umma<BF16>(tmem_d, a1, b0, idesc, (i | k) != 0);      // small * big
+                            umma<BF16>(tmem_d, a0, b1, idesc, 1);                 // big * small
+                            umma<BF16>(tmem_d, a0, b0, idesc, 1);                 // big * big
+                        }
                     }
                 }
                 umma_commit(&empty_bar[s]);            // frees the smem stage when these MMAs retire
@@ -270,9 +288,21 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant_
             uint32_t r[32];
             if (nkb > 0) {
                 tmem_ld32(tmem_d + ((uint32_t)(q * 32) << 16) + c0, r);
+                if (F16X2) {
+                    uint32_t rx[32];
+                    tmem_ld32(tmem_d + ((uint32_t)(q * 32) << 16) + 128 + c0, rx);
+#pragma unroll
+                    for (int j = 0; j < 32; ++j)
+                        r[j] = __float_as_uint(fmaf(__uint_as_float(rx[j]), 1.0f / 2048.0f, __uint_as_float(r[j])));
+                }
             } else {
 #pragma unroll
                 for (int j = 0; j < 32; ++j) r[j] = 0u;
+            }
+            if (F16X2 && p.row_scale != nullptr && m < p.M) {
+                const float rs = __ldg(p.row_scale + m);
+#pragma unroll
+                for (int j = 0; j < 32; ++j) r[j] = __float_as_uint(__uint_as_float(r[j]) * rs);
             }
             const bool vec = !split && (p.ldc % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.C) & 15) == 0) &&
                              (n0 + c0 + 32 <= p.N);
@@ -371,6 +401,52 @@ __global__ void split_bf16x2_kernel(size_t rows, int cols, const float* __restri
     *reinterpret_cast<uint4*>(lo + r * ldo + c) = *reinterpret_cast<const uint4*>(l);
 }
 
+// mode 4: hi = fp16(x * s), lo' = fp16((x * s - hi) * 2^11); s = 1, or a per-row power of two that puts the row's
+// largest magnitude into [2^13, 2^14) (one warp per row; row_inv[r] = 1 / s undoes it in the GEMM epilogue).
+__device__ __forceinline__ void f16_parts(float v, __half& h, __half& l) {
+    h = __float2half_rn(v);
+    l = __float2half_rn((v - __half2float(h)) * 2048.0f);
+}
+__global__ void split_f16x2_kernel(size_t rows, int cols, const float* __restrict__ x, int ldx,
+                                   __half* __restrict__ hi, __half* __restrict__ lo, int ldo) {
+    size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    size_t total = rows * (size_t)(ldo / 8);
+    if (i >= total) return;
+    size_t r = i / (ldo / 8);
+    int c = (int)(i % (ldo / 8)) * 8;
+    __align__(16) __half h[8], l[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) f16_parts((c + j < cols) ? x[r * ldx + c + j] : 0.f, h[j], l[j]);
+    *reinterpret_cast<uint4*>(hi + r * ldo + c) = *reinterpret_cast<const uint4*>(h);
+    *reinterpret_cast<uint4*>(lo + r * ldo + c) = *reinterpret_cast<const uint4*>(l);
+}
+__global__ void __launch_bounds__(256)
+split_rows_f16_kernel(size_t rows, int cols, const float* __restrict__ x, int ldx, __half* __restrict__ hi,
+                      __half* __restrict__ lo, int ldo, float* __restrict__ row_inv) {
+    const size_t r = blockIdx.x * (size_t)(blockDim.x / 32) + threadIdx.x / 32;
+    const int lane = threadIdx.x % 32;
+    if (r >= rows) return;
+    const float* xr = x + r * ldx;
+    float amax = 0.f;
+    for (int c = lane; c < cols; c += 32) amax = fmaxf(amax, fabsf(xr[c]));
+    amax = warp_max(amax);
+    // s = 2^(13 - floor(log2 amax)): amax * s in [2^13, 2^14); zero / denormal rows are left alone
+    float s = 1.0f;
+    if (amax >= 1.17549435e-38f && amax < 3.0e38f) {
+        const int e = (int)((__float_as_uint(amax) >> 23) & 0xFF) - 127;
+        const int se = min(max(13 - e, -126), 126);
+        s = __uint_as_float((uint32_t)(se + 127) << 23);
+    }
+    if (lane == 0) row_inv[r] = 1.0f / s;
+    for (int c = lane * 8; c < ldo; c += 256) {
+        __align__(16) __half h[8], l[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) f16_parts((c + j < cols) ? xr[c + j] * s : 0.f, h[j], l[j]);
+        *reinterpret_cast<uint4*>(hi + r * ldo + c) = *reinterpret_cast<const uint4*>(h);
+        *reinterpret_cast<uint4*>(lo + r * ldo + c) = *reinterpret_cast<const uint4*>(l);
+    }
+}
+
 // ------------------------------------------------------------------ host side
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
@@ -391,7 +467,8 @@ EncodeTiledFn get_encode() {
 }
 
 // 2-D row-major tensor [rows][cols] (cols contiguous, row stride ld elements); box = {box_c, box_r}
-bool make_map(CUtensorMap* map, bool bf16, const void* ptr, size_t rows, size_t cols, size_t ld, int box_c,
+// bf16: 0 = fp32 elements, 1 = bf16, 2 = fp16
+bool make_map(CUtensorMap* map, int bf16, const void* ptr, size_t rows, size_t cols, size_t ld, int box_c,
               int box_r, bool atom32) {
     EncodeTiledFn enc = get_encode();
     if (!enc) return false;
@@ -399,7 +476,8 @@ bool make_map(CUtensorMap* map, bool bf16, const void* ptr, size_t rows, size_t 
     cuuint64_t strides[1] = {ld * (bf16 ? 2 : 4)};
     cuuint32_t box[2] = {(cuuint32_t)box_c, (cuuint32_t)box_r};
     cuuint32_t estr[2] = {1, 1};
-    CUresult r = enc(map, bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2,
+    CUresult r = enc(map, bf16 == 2 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16
+                               : (bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32), 2,
                      const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                      atom32 ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
                      CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -468,14 +546,42 @@ __global__ void split_planes_kernel(size_t n8, const float4* __restrict__ x, uin
         lo[i] = *reinterpret_cast<const uint4*>(l);
     }
 }
+// f16x2: the same two-plane layout with fp16 parts (no scaling: bounded operands -- weights, activations)
+__global__ void split_planes_f16_kernel(size_t n8, const float4* __restrict__ x, uint4* __restrict__ hi,
+                                        uint4* __restrict__ lo) {
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n8; i += (size_t)gridDim.x * blockDim.x) {
+        const float4 a = x[2 * i], b = x[2 * i + 1];
+        const float v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+        __align__(16) __half h[8], l[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) f16_parts(v[j], h[j], l[j]);
+        hi[i] = *reinterpret_cast<const uint4*>(h);
+        lo[i] = *reinterpret_cast<const uint4*>(l);
+    }
+}
+// f16x2 split of a contiguous [rows, cols] matrix with per-row power-of-two scaling (gradient operands): planes hi
+// then lo' (rows * cols halves each), row_inv[rows] = the factors that undo the scaling
+int split_rows_f16(cudaStream_t st, size_t rows, int cols, const float* x, float* planes, float* row_inv) {
+    E2E_REQUIRE(cols % 8 == 0 && ((uintptr_t)x & 15) == 0 && ((uintptr_t)planes & 15) == 0,
+                "split_rows_f16: rows must be 16-byte aligned multiples of 8 elements");
+    if (rows == 0) return 0;
+    __half* hi = reinterpret_cast<__half*>(planes);
+    split_rows_f16_kernel<<<cdiv(rows, 8), 256, 0, st>>>(rows, cols, x, cols, hi, hi + rows * (size_t)cols, cols, row_inv);
+    E2E_LAUNCH_CHECK();
+    return 0;
+}
 int split_lo(cudaStream_t st, int mode, size_t n, const float* x, float* lo) {
-    E2E_REQUIRE(mode == 1 || mode == 3, "split_lo: mode %d has no operand split (1 = tf32x3, 3 = bf16x2)", mode);
+    E2E_REQUIRE(mode == 1 || mode == 3 || mode == 4,
+                "split_lo: mode %d has no operand split (1 = tf32x3, 3 = bf16x2, 4 = f16x2)", mode);
     E2E_REQUIRE(n % 8 == 0 && ((uintptr_t)x & 15) == 0 && ((uintptr_t)lo & 15) == 0,
                 "split_lo: buffers must be 16-byte aligned with a multiple of 8 elements");
     if (n == 0) return 0;
-    if (mode == 3) {
-        split_planes_kernel<<<(unsigned)min((size_t)148 * 8, (n / 8 + 255) / 256), 256, 0, st>>>(
-            n / 8, (const float4*)x, (uint4*)lo, (uint4*)((__nv_bfloat16*)lo + n));
+    if (mode == 3 || mode == 4) {
+        const unsigned grid = (unsigned)min((size_t)148 * 8, (n / 8 + 255) / 256);
+        if (mode == 3)
+            split_planes_kernel<<<grid, 256, 0, st>>>(n / 8, (const float4*)x, (uint4*)lo, (uint4*)((__nv_bfloat16*)lo + n));
+        else
+            split_planes_f16_kernel<<<grid, 256, 0, st>>>(n / 8, (const float4*)x, (uint4*)lo, (uint4*)((__half*)lo + n));
         E2E_LAUNCH_CHECK();
         return 0;
     }
@@ -486,11 +592,16 @@ int split_lo(cudaStream_t st, int mode, size_t n, const float* x, float* lo) {
 
 // A_lo / B_lo (optional, tf32x3 mode): precomputed split_lo() of the operand with the operand's own layout.  When
 // given (and TMA-addressable) the operand's pre-pass is skipped: the tensor maps point at the caller's buffers.
+// row_scale (mode 4 with caller-provided A planes): the per-row factors that undo the planes' scaling, or NULL.
 int gemm_tc(cudaStream_t st, int mode, int transA, int transB, int M, int N, int K, const float* A, int lda,
             const float* B, int ldb, float* C, int ldc, const float* bias, const float* Z, int ldz, int accumulate,
-            bool* handled, const float* A_lo, const float* B_lo, size_t a_plane, size_t b_plane) {
+            bool* handled, const float* A_lo, const float* B_lo, size_t a_plane, size_t b_plane,
+            const float* row_scale) {
     *handled = false;
-    if (mode < 1 || mode > 3) return 0;
+    if (mode < 1 || mode > 4) return 0;
+    // f16x2 scales the A operand per output row: a transposed A (K runs over its rows) stays on 3xTF32, whose splits
+    // are not interchangeable with the fp16 planes
+    if (mode == 4 && transA) { mode = 1; A_lo = nullptr; B_lo = nullptr; row_scale = nullptr; }
     const bool bf16 = mode >= 2;
     // big enough to pay for the pre-pass and to fill tiles; K >= one stage
     if (M < 96 || N < 64 || K < 32 || (long long)M * N * K < g_min_work) return 0;
@@ -506,18 +617,21 @@ int gemm_tc(cudaStream_t st, int mode, int transA, int transB, int M, int N, int
     const size_t a_ld = (a_cols + eper - 1) / eper * eper, b_ld = (b_cols + eper - 1) / eper * eper;
     const size_t esz = bf16 ? 2 : 4, nparts = mode == 2 ? 1 : 2;
     size_t a_bytes = (a_rows * a_ld * esz + 1023) / 1024 * 1024, b_bytes = (b_rows * b_ld * esz + 1023) / 1024 * 1024;
+    const size_t rs_bytes = mode == 4 ? ((size_t)M * 4 + 1023) / 1024 * 1024 : 0;       // per-row scales of the pre-pass
     // operands whose split the caller already holds: used in place when TMA can address them
     // (tf32x3: x itself + its fp32 "small" half; bf16x2: the two bf16 planes of split_lo, `plane` elements apart)
     auto direct_ok = [&](const float* x, const float* lo, int ld, size_t plane) {
         if (mode == 1) return lo != nullptr && ld % 4 == 0 && ((uintptr_t)x & 15) == 0 && ((uintptr_t)lo & 15) == 0;
-        if (mode == 3) return lo != nullptr && ld % 8 == 0 && plane % 8 == 0 && plane > 0 && ((uintptr_t)lo & 15) == 0;
+        if (mode == 3 || mode == 4)
+            return lo != nullptr && ld % 8 == 0 && plane % 8 == 0 && plane > 0 && ((uintptr_t)lo & 15) == 0;
         return false;
     };
     const bool a_direct = direct_ok(A, A_lo, lda, a_plane), b_direct = direct_ok(B, B_lo, ldb, b_plane);
     if (a_direct) a_bytes = 0;
     if (b_direct) b_bytes = 0;
-    if (nparts * (a_bytes + b_bytes) > ws_bytes) return 0;
+    if (nparts * (a_bytes + b_bytes) + rs_bytes > ws_bytes) return 0;
     uint8_t* ws = (uint8_t*)ws_ptr;
+    float* rs_ws = reinterpret_cast<float*>(ws + nparts * (a_bytes + b_bytes));
     void* A0 = ws;
     void* A1 = ws + a_bytes;
     void* B0 = ws + nparts * a_bytes;
@@ -525,7 +639,21 @@ int gemm_tc(cudaStream_t st, int mode, int transA, int transB, int M, int N, int
     size_t a_ld_eff = a_ld, b_ld_eff = b_ld;
     if (a_direct) { A0 = const_cast<float*>(A); A1 = const_cast<float*>(A_lo); a_ld_eff = lda; }
     if (b_direct) { B0 = const_cast<float*>(B); B1 = const_cast<float*>(B_lo); b_ld_eff = ldb; }
-    if (mode == 3) {
+    if (mode == 4) {
+        if (a_direct) { A0 = const_cast<float*>(A_lo); A1 = (__half*)A0 + a_plane; }
+        else row_scale = nullptr;
+        if (b_direct) { B0 = const_cast<float*>(B_lo); B1 = (__half*)B0 + b_plane; }
+        if (!a_direct) {       // A is [M][K] here (transA went to mode 1): per-row scaled split, undone in the epilogue
+            split_rows_f16_kernel<<<cdiv(a_rows, 8), 256, 0, st>>>(a_rows, (int)a_cols, A, lda, (__half*)A0, (__half*)A1,
+                                                                  (int)a_ld, rs_ws);
+            E2E_LAUNCH_CHECK();
+            row_scale = rs_ws;
+        }
+        if (!b_direct) {
+            split_f16x2_kernel<<<cdiv(b_rows * (b_ld / 8), 256), 256, 0, st>>>(b_rows, (int)b_cols, B, ldb, (__half*)B0, (__half*)B1, (int)b_ld);
+            E2E_LAUNCH_CHECK();
+        }
+    } else if (mode == 3) {
         if (a_direct) { A0 = const_cast<float*>(A_lo); A1 = (__nv_bfloat16*)A0 + a_plane; }
         if (b_direct) { B0 = const_cast<float*>(B_lo); B1 = (__nv_bfloat16*)B0 + b_plane; }
         if (!a_direct) {
@@ -557,11 +685,12 @@ int gemm_tc(cudaStream_t st, int mode, int transA, int transB, int M, int N, int
     CUtensorMap mA0, mA1, mB0, mB1;
     bool ok = true;
     const bool a32 = !bf16 && a_mn, b32 = !bf16 && b_mn;      // tf32 MN-major: 32-byte-atom swizzle
-    ok &= make_map(&mA0, bf16, A0, a_rows, a_cols, a_ld_eff, bke, a_mn ? bke : TBM, a32);
-    ok &= make_map(&mB0, bf16, B0, b_rows, b_cols, b_ld_eff, bke, b_mn ? bke : TBN, b32);
+    const int dt = mode == 4 ? 2 : (bf16 ? 1 : 0);
+    ok &= make_map(&mA0, dt, A0, a_rows, a_cols, a_ld_eff, bke, a_mn ? bke : TBM, a32);
+    ok &= make_map(&mB0, dt, B0, b_rows, b_cols, b_ld_eff, bke, b_mn ? bke : TBN, b32);
     if (nparts == 2) {
-        ok &= make_map(&mA1, bf16, A1, a_rows, a_cols, a_ld_eff, bke, a_mn ? bke : TBM, a32);
-        ok &= make_map(&mB1, bf16, B1, b_rows, b_cols, b_ld_eff, bke, b_mn ? bke : TBN, b32);
+        ok &= make_map(&mA1, dt, A1, a_rows, a_cols, a_ld_eff, bke, a_mn ? bke : TBM, a32);
+        ok &= make_map(&mB1, dt, B1, b_rows, b_cols, b_ld_eff, bke, b_mn ? bke : TBN, b32);
     } else {
         mA1 = mA0;
         mB1 = mB0;
@@ -571,6 +700,7 @@ int gemm_tc(cudaStream_t st, int mode, int transA, int transB, int M, int N, int
     TcParams p;
     p.M = M; p.N = N; p.K = K; p.C = C; p.ldc = ldc; p.bias = bias; p.Z = Z; p.ldz = ldz;
     p.accumulate = accumulate; p.a_mn_major = a_mn; p.b_mn_major = b_mn; p.dbg = g_dbg;
+    p.row_scale = mode == 4 ? row_scale : nullptr;
     const int gm = cdiv(M, TBM), gn = cdiv(N, TBN), tiles = gm * gn;
     const int kb_total = cdiv(K, bke);
     int splits = 1;
@@ -585,7 +715,10 @@ int gemm_tc(cudaStream_t st, int mode, int transA, int transB, int M, int N, int
     }
     const size_t smem = (size_t)STAGES * STAGE_BYTES + 1024;
     dim3 grid(gn, gm, splits);
-    if (mode == 3) {
+    if (mode == 4) {
+        E2E_CHECK_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        gemm_tc_kernel<4><<<grid, TC_THREADS, smem, st>>>(mA0, mA1, mB0, mB1, p);
+    } else if (mode == 3) {
         E2E_CHECK_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         gemm_tc_kernel<3><<<grid, TC_THREADS, smem, st>>>(mA0, mA1, mB0, mB1, p);
     } else if (mode == 2) {

@@ -14,14 +14,16 @@ import torch
 from . import _lib
 from ._lib import call
 
-# 0 = fp32 FFMA, 1 = 3xTF32 tcgen05 (fp32-accurate), 2 = bf16 tcgen05, 3 = bf16x2 tcgen05 (hi+lo bf16, 3 products)
+# 0 = fp32 FFMA, 1 = 3xTF32 tcgen05 (fp32-accurate), 2 = bf16 tcgen05, 3 = bf16x2 tcgen05 (hi+lo bf16, 3 products),
+# 4 = f16x2 tcgen05 (hi + scaled-lo fp16, cross terms in a second accumulator: fp32-accurate at half the cost of mode 1;
+#     products with a transposed A operand -- the weight gradients -- run mode 1)
 _GEMM_MODE = 0
 TAG_GEMM_SHAPES = False      # profiling aid: one profiler entry per GEMM shape instead of one "e2e_gemm"
 
 
 def set_gemm_mode(mode):
     global _GEMM_MODE
-    _GEMM_MODE = {"fp32": 0, "tf32x3": 1, "bf16": 2, "bf16x2": 3}.get(mode, mode)
+    _GEMM_MODE = {"fp32": 0, "tf32x3": 1, "bf16": 2, "bf16x2": 3, "f16x2": 4}.get(mode, mode)
 
 
 _workspace = {}
@@ -95,33 +97,56 @@ def to_i32(t, device):
 
 
 class SplitPlanes:
-    """bf16x2 operand split of a tensor: `planes` is a bf16 tensor [2, *x.shape] (hi = bf16(x), lo = bf16(x - hi)).
-    Indexing takes the same view of both planes, as the caller indexes x."""
+    """Two-plane operand split of a tensor: `planes` is a 2-byte tensor [2, *x.shape] -- bf16x2: hi = bf16(x),
+    lo = bf16(x - hi); f16x2: hi = fp16(x s), lo' = fp16((x s - hi) 2^11) with s = 1 or, for `row_inv` not None, a
+    power of two per row whose inverse is row_inv[row].  Indexing takes the same view of both planes, as the caller
+    indexes x (row-scaled planes: whole rows only)."""
 
-    def __init__(self, planes):
+    def __init__(self, planes, row_inv=None):
         self.planes = planes
+        self.row_inv = row_inv
+
+    @property
+    def mode(self):
+        return 3 if self.planes.dtype == torch.bfloat16 else 4
 
     def __getitem__(self, idx):
         idx = idx if isinstance(idx, tuple) else (idx,)
-        return SplitPlanes(self.planes[(slice(None),) + idx])
+        rinv = None if self.row_inv is None else self.row_inv[idx[0]]
+        return SplitPlanes(self.planes[(slice(None),) + idx], rinv)
 
     def record_stream(self, stream):
         self.planes.record_stream(stream)
+        if self.row_inv is not None:
+            self.row_inv.record_stream(stream)
 
 
-def split_lo(x):
-    """The operand split of a contiguous tensor for the current GEMM mode, or None when the mode does not use one:
-    tf32x3 -> x - tf32_trunc(x) (fp32, x's layout); bf16x2 -> SplitPlanes.  Views of the result, taken like the views
-    of x, are passed to gemm(..., a_lo= / b_lo=) so one pass serves every product the tensor enters."""
-    if _GEMM_MODE not in (1, 3) or x.numel() % 8 != 0 or not x.is_contiguous():
+def split_lo(x, mode=None):
+    """The operand split of a contiguous tensor for a GEMM mode (default: the current one), or None when the mode does
+    not use one: tf32x3 -> x - tf32_trunc(x) (fp32, x's layout); bf16x2 / f16x2 -> SplitPlanes (f16x2: unscaled, for
+    bounded operands -- weights, activations).  Views of the result, taken like the views of x, are passed to
+    gemm(..., a_lo= / b_lo=) so one pass serves every product the tensor enters."""
+    mode = _GEMM_MODE if mode is None else mode
+    if mode not in (1, 3, 4) or x.numel() % 8 != 0 or not x.is_contiguous():
         return None
-    if _GEMM_MODE == 3:
-        planes = torch.empty((2,) + tuple(x.shape), dtype=torch.bfloat16, device=x.device)
-        call("e2e_split_lo", 3, x.numel(), x, planes)
+    if mode in (3, 4):
+        planes = torch.empty((2,) + tuple(x.shape), dtype=torch.bfloat16 if mode == 3 else torch.float16, device=x.device)
+        call("e2e_split_lo", mode, x.numel(), x, planes)
         return SplitPlanes(planes)
     lo = torch.empty_like(x)
     call("e2e_split_lo", 1, x.numel(), x, lo)
     return lo
+
+
+def split_rows_f16(x):
+    """f16x2 split of a contiguous 2-D gradient tensor used as the (non-transposed) A operand: every row is scaled by
+    its own power of two before the split, the GEMM multiplies the output row by row_inv (e2e_split_rows_f16)."""
+    if x.dim() != 2 or not x.is_contiguous() or x.shape[1] % 8 != 0:
+        return None
+    planes = torch.empty((2,) + tuple(x.shape), dtype=torch.float16, device=x.device)
+    row_inv = torch.empty((x.shape[0],), dtype=torch.float32, device=x.device)
+    call("e2e_split_rows_f16", x.shape[0], x.shape[1], x, planes, row_inv)
+    return SplitPlanes(planes, row_inv)
 
 
 def gemm(a, b, out=None, ta=False, tb=False, bias=None, z=None, accumulate=False, mode=None, a_lo=None, b_lo=None):
@@ -143,23 +168,30 @@ def gemm(a, b, out=None, ta=False, tb=False, bias=None, z=None, accumulate=False
         assert z.stride(1) == 1
         ldz = z.stride(0) if z.shape[0] > 1 else z.shape[1]
     mode = _GEMM_MODE if mode is None else mode
+    if mode == 4 and ta:
+        mode = 1                # f16x2 scales A per output row: weight-gradient products (K over the rows) run 3xTF32
     if mode != 0 and _devkey(a.device) not in _workspace:
         ensure_workspace(a.device)
     tag = ("gemm M=%d N=%d K=%d t%d%d" % (M, N, K, ta, tb)) if TAG_GEMM_SHAPES else "e2e_gemm"
-    if mode in (1, 3) and (a_lo is not None or b_lo is not None):
+    if mode in (1, 3, 4) and (a_lo is not None or b_lo is not None):
         planes = [0, 0]
         los = [a_lo, b_lo]
+        row_scale = None
         for i, (x, lo) in enumerate(((a, a_lo), (b, b_lo))):
             if lo is None:
                 continue
-            if isinstance(lo, SplitPlanes) != (mode == 3):
+            if (lo.mode if isinstance(lo, SplitPlanes) else 1) != mode:
                 los[i] = None           # split made for another mode: let the GEMM redo its pre-pass
                 continue
-            if mode == 3:
+            if mode in (3, 4):
+                if i == 0:
+                    row_scale = lo.row_inv
+                else:
+                    assert lo.row_inv is None, "row-scaled planes serve the A operand only"
                 los[i], planes[i] = lo.planes[0], lo.planes.stride(0)
             assert los[i].shape == x.shape and los[i].stride() == x.stride()
         call("e2e_gemm_lo", mode, int(ta), int(tb), M, N, K, a, los[0], lda, b, los[1], ldb, out, ldc,
-             bias, z, ldz, int(accumulate), planes[0], planes[1], work=2.0 * M * N * K, tag=tag)
+             bias, z, ldz, int(accumulate), planes[0], planes[1], row_scale, work=2.0 * M * N * K, tag=tag)
         return out
     call("e2e_gemm", mode, int(ta), int(tb), M, N, K, a, lda, b, ldb, out, ldc,
          bias, z, ldz, int(accumulate), work=2.0 * M * N * K, tag=tag)
@@ -365,19 +397,27 @@ class BiLSTMLayerFn(torch.autograd.Function):
         N = B * Tp
         x2, o2 = x.view(N, I), out.view(N, nd * H)
         x_lo, Wx_lo = ctx.los
-        G_lo = split_lo(G)            # one split of dz serves the dX, dW_x and the dW_h products
+        f16 = _GEMM_MODE == 4
+        if f16:
+            # f16x2: the critical-path product dX = dz . Wx^T takes dz as fp16 planes scaled per row (gradients span
+            # many orders of magnitude across utterances) and Wx's planes of the forward pass; the weight-gradient
+            # products (K runs over the rows) run 3xTF32 on the side stream with their own splits
+            G_lo = split_rows_f16(G)
+        else:
+            G_lo = split_lo(G)        # one split of dz serves the dX, dW_x and the dW_h products
         dX = gemm(G, Wx, tb=True, a_lo=G_lo, b_lo=Wx_lo).view(B, Tp, I) if ctx.needs_input_grad[0] else None
 
         def weight_grads():
-            dWx = gemm(x2, G, ta=True, a_lo=x_lo, b_lo=G_lo)            # [I, nd*4H]
+            xl, gl = (split_lo(x2, 1), split_lo(G, 1)) if f16 else (x_lo, G_lo)
+            dWx = gemm(x2, G, ta=True, a_lo=xl, b_lo=gl)                # [I, nd*4H]
             dWh = torch.empty((nd, H, 4 * H), dtype=torch.float32, device=dev)
             # h_{t-1}^T dz_t: fw pairs out[t-1] with dz[t], bw pairs out[t+1] with dz[t]; the flat
             # one-row shift never crosses an utterance because out[b, Tp-1] == 0 and dz[b, Tp-1] == 0.
             gemm(o2[:N - 1, 0:H], G[1:, 0:4 * H], ta=True, out=dWh[0],
-                 b_lo=None if G_lo is None else G_lo[1:, 0:4 * H])
+                 b_lo=None if gl is None else gl[1:, 0:4 * H])
             if nd == 2:
                 gemm(o2[1:, H:2 * H], G[:N - 1, 4 * H:8 * H], ta=True, out=dWh[1],
-                     b_lo=None if G_lo is None else G_lo[:N - 1, 4 * H:8 * H])
+                     b_lo=None if gl is None else gl[:N - 1, 4 * H:8 * H])
             dbp = colsum(G)
             return dWx, dWh, dbp
 

@@ -41,8 +41,11 @@ unsigned long long e2e_launch_count(int reset);
  * (tf.gradients, seq2seq_model.py:148).
  * mode: 0 = fp32 FFMA (exact fp32), 1 = 3xTF32 tcgen05 (fp32-accurate tensor
  * core), 2 = bf16 tcgen05, 3 = bf16x2 tcgen05 (operands as hi + lo bf16 pairs, three kind::f16 products:
- * ~2^-17 relative error per product at half the tensor-pipe cost of mode 1).  Shapes a tensor-core mode
- * cannot take fall back to mode 0 (still on the GPU). */
+ * ~2^-17 relative error per product at half the tensor-pipe cost of mode 1), 4 = f16x2 tcgen05 (operands as
+ * hi = fp16(x) and lo' = fp16((x - hi) 2^11), cross terms in a second TMEM accumulator: ~2^-22 relative error --
+ * the accuracy class of mode 1 -- at half its tensor-pipe cost; the A operand is scaled per row by a power of two
+ * before the split (fp16 has 5 exponent bits) and the output row scaled back; B must be bounded (weights); a
+ * transposed A runs mode 1).  Shapes a tensor-core mode cannot take fall back to mode 0 (still on the GPU). */
 int e2e_gemm(void* stream, int mode, int transA, int transB, int M, int N, int K,
              const float* A, int lda, const float* B, int ldb, float* C, int ldc,
              const float* bias, const float* Z, int ldz, int accumulate);
@@ -54,12 +57,18 @@ int e2e_gemm(void* stream, int mode, int transA, int transB, int M, int N, int K
  *           bits of the raw fp32 "big" half, so X itself is the other part); x_plane is ignored;
  *   mode 3: buf holds two bf16 planes of n elements, hi = bf16(X) then lo = bf16(X - hi), each in X's layout;
  *           X_lo points at the hi-plane element matching X's first element and x_plane = n (elements between
- *           the planes); needs ld % 8 == 0, x_plane % 8 == 0 and a 16-byte aligned X_lo.
+ *           the planes); needs ld % 8 == 0, x_plane % 8 == 0 and a 16-byte aligned X_lo;
+ *   mode 4: as mode 3 with fp16 planes hi = fp16(X s), lo' = fp16((X s - hi) 2^11): e2e_split_lo(4, ...) makes them
+ *           with s = 1 (bounded operands); e2e_split_rows_f16 makes the A planes of a contiguous [rows, cols]
+ *           matrix with a power-of-two s per row (gradients) and writes the factors 1/s to row_inv, to be passed
+ *           as a_row_scale (NULL = unscaled planes): C row m is multiplied by a_row_scale[m].
  * n must be a multiple of 8 and the buffers 16-byte aligned. */
 int e2e_gemm_lo(void* stream, int mode, int transA, int transB, int M, int N, int K, const float* A,
                 const float* A_lo, int lda, const float* B, const float* B_lo, int ldb, float* C, int ldc,
-                const float* bias, const float* Z, int ldz, int accumulate, size_t a_plane, size_t b_plane);
+                const float* bias, const float* Z, int ldz, int accumulate, size_t a_plane, size_t b_plane,
+                const float* a_row_scale);
 int e2e_split_lo(void* stream, int mode, size_t n, const float* x, float* lo);
+int e2e_split_rows_f16(void* stream, size_t rows, int cols, const float* x, float* planes, float* row_inv);
 
 /* Scratch for the tensor-core modes' operand pre-pass (TF32 big/small split or
  * bf16 copies): a caller-owned device buffer; GEMMs whose operands do not fit run
@@ -100,9 +109,6 @@ int e2e_lstm_unpack_grads(void* stream, int I, int H, float* dkernel, float* dbi
 int e2e_set_rec_mode(int mode);
 /* test hook: device buffer (>= 5*T int64) receiving per-step clock64 stamps of the forward cluster kernel, or NULL */
 int e2e_set_rec_debug(long long* dbg);
-/* test hook: largest thread-block-cluster size (2^log2_size, log2_size in 0..3) the persistent decoder kernels are
- * launched with; 0 = flat grid barrier */
-int e2e_set_dec_cluster(int log2_size);
 int e2e_lstm_rec_fwd(void* stream, int B, int T, int Tp, int H, int ndir, long long sb, long long st,
                      float* G, float* Hout, float* Cst, const float* Wh, const int* lens,
                      void* ctr_ws, size_t ctr_ws_bytes, int* err_flag);

@@ -64,13 +64,16 @@ def check_against_golden(model, g, cfg, rtol=RTOL):
     return worst
 
 
+@pytest.mark.parametrize("gemm", ["tf32x3", "f16x2"])
 @pytest.mark.parametrize("tag", ["cfg2", "cfg4", "cfg5"])
-def test_fullsize_step_matches_oracle_golden(tag, golden_dir):
+def test_fullsize_step_matches_oracle_golden(tag, gemm, golden_dir):
+    """Both fp32-accurate tensor-core modes: 3xTF32 and f16x2 (fp16 hi + scaled-lo pairs at half the tensor-pipe cost;
+    the weight-gradient products run 3xTF32 there too)."""
     g = np.load(os.path.join(golden_dir, "fullsize_%s.npz" % tag))
     cfg = fg.case_config(tag)
     w = synth.make_weights(cfg)
     batch = synth.make_batch(cfg)
-    ops.set_gemm_mode("tf32x3")
+    ops.set_gemm_mode(gemm)
     try:
         model = build_model(cfg, w, device="cuda:0")
         model.run_step(batch)

@@ -228,13 +228,41 @@ def test_gemm_shared_operand_split(mode):
         ops.set_gemm_mode("fp32")
 
 
-@pytest.mark.parametrize("mode,tol", [(1, 2e-5), (2, 2e-2), (3, 3e-5)])
+def test_gemm_f16x2_rows_of_very_different_magnitude():
+    """Mode 4 scales every row of the A operand by its own power of two before the fp16 split (gradients of different
+    utterances differ by many orders of magnitude) and scales the output row back: every ROW must be accurate
+    relative to ITS OWN magnitude, for the GEMM's own pre-pass and for caller-held planes (e2e_split_rows_f16), and
+    the shared B planes of e2e_split_lo(4) must give the same result."""
+    rng = np.random.default_rng(11)
+    M, N, K = 700, 512, 1024
+    scale = 10.0 ** rng.uniform(-12, 2, size=(M, 1))
+    a = (rng.standard_normal((M, K)) * scale).astype(np.float32)
+    a[5] = 0.0
+    w = (rng.standard_normal((N, K)) * 0.07).astype(np.float32)           # stored [N, K]: the dX = dz . W^T form
+    ref = a.astype(np.float64) @ w.astype(np.float64).T
+    row_mag = np.abs(a).max(1, keepdims=True).astype(np.float64) * np.abs(w).max() * np.sqrt(K)
+    row_mag[row_mag == 0] = 1.0
+    outs = [ops.gemm(T(a), T(w), tb=True, mode=4)]
+    ad, wd = T(a), T(w)
+    outs.append(ops.gemm(ad, wd, tb=True, mode=4, a_lo=ops.split_rows_f16(ad), b_lo=ops.split_lo(wd, 4)))
+    outs.append(ops.gemm(ad, wd, tb=True, mode=4, b_lo=ops.split_lo(wd, 4)))
+    for out in outs:
+        err = np.abs(out.cpu().numpy().astype(np.float64) - ref) / row_mag
+        assert err.max() < 2e-6, err.max()
+        assert float(out[5].abs().max()) == 0.0
+    assert float((outs[0] - outs[1]).abs().max()) == 0.0                  # same planes, same arithmetic
+
+
+@pytest.mark.parametrize("mode,tol", [(1, 2e-5), (2, 2e-2), (3, 3e-5), (4, 5e-6)])
 @pytest.mark.parametrize("M,N,K", [(128, 128, 32), (256, 384, 96), (1000, 520, 264), (4480, 2048, 120),
                                    (256, 1024, 5000), (777, 333, 1111)])
 @pytest.mark.parametrize("ta,tb", [(False, False), (True, False), (False, True), (True, True)])
 def test_gemm_tensor_core(mode, tol, M, N, K, ta, tb):
     """tcgen05 paths: mode 1 = 3xTF32 (fp32-accurate), mode 2 = bf16 (looser, stated tolerance), mode 3 = bf16x2
-    (hi + lo bf16 pairs, three products: 16 significand bits per operand)."""
+    (hi + lo bf16 pairs, three products: 16 significand bits per operand), mode 4 = f16x2 (hi + scaled-lo fp16 pairs,
+    cross terms in a second accumulator: 22 significand bits; a transposed A runs mode 1)."""
+    if mode == 4 and ta:
+        tol = 2e-5
     rng = np.random.default_rng(M + N + K + mode)
     a = rng.standard_normal((K, M) if ta else (M, K)).astype(np.float32)
     b = rng.standard_normal((N, K) if tb else (K, N)).astype(np.float32)

@@ -50,7 +50,7 @@ def test_clipping_active_and_dense_norm_option():
     assert abs(float(model.grad_norm) - ref["dense_norm"]) < 1e-4 * ref["dense_norm"]
 
 
-@pytest.mark.parametrize("mode,rtol", [("tf32x3", 1e-4), ("bf16x2", 1e-4), ("bf16", 5e-2)])
+@pytest.mark.parametrize("mode,rtol", [("tf32x3", 1e-4), ("f16x2", 1e-4), ("bf16x2", 1e-4), ("bf16", 5e-2)])
 def test_train_step_tensor_core_modes(mode, rtol):
     """cfg1 through the tcgen05 GEMMs.  tf32x3 is the fp32-accurate mode and must meet
     the same 1e-4 bar as FFMA, and so must bf16x2 (hi + lo bf16 operands, three products); bf16 is the reduced-precision mode: stated tolerance
