@@ -373,7 +373,7 @@ def main():
     ap.add_argument("--config", default="cfg2", help="cfg2 (default, BASELINE configs[1]) | cfg4 | cfg5 | cfg1")
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
                     help="weak: the config's batch PER GPU (default); strong: the config's batch split over the GPUs")
-    ap.add_argument("--gemm", default="tf32x3", help="fp32 | tf32x3 | f16x2 | bf16x2 | bf16 (tf32x3 and f16x2 are the fp32-accurate tensor-core modes)")
+    ap.add_argument("--gemm", default="f16x2", help="fp32 | tf32x3 | f16x2 | bf16x2 | bf16 (tf32x3 and f16x2 are the fp32-accurate tensor-core modes)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-beam", action="store_true", help="skip the beam-decode utt/s side measurement")
     ap.add_argument("--no-graph", action="store_true", help="time the eager step instead of its CUDA-graph replay")
