@@ -311,7 +311,7 @@ def roofline_report(raw, cfg, peaks, K, ms_per_step, clocks, gemm_mode):
                 "issue_ceiling_tflops": peak_tc / units, "frac_of_issue_ceiling": ach / (peak_tc / units),
                 "algorithmic_gflop_per_launch": sv["work"] / sv["calls"] / 1e9, "avg_launch_ms": sv["ms"] / sv["calls"],
                 "launches_per_step": sv["calls"] / K, "main_stream_ms_per_step": tv["main_ms"] / K,
-                "traffic": traffic.get("gemm_tc_kernel"),
+                "traffic": (traffic.get("gemm_tc_kernel") or {}).get("dram_bytes_per_launch"),
                 "class_aggregate": {"kernel": "all e2e_gemm calls (every dense projection incl. dX/dW, %d shapes)"
                                               % len(shapes),
                                     "algorithmic_gflop_per_step": tv["work"] / K / 1e9, "achieved": ach_class,
@@ -335,7 +335,9 @@ def roofline_report(raw, cfg, peaks, K, ms_per_step, clocks, gemm_mode):
                           "of the step in %d launches)" % (d["kernel"], name, v["main_ms"] / K, 100 * d["share_of_step"],
                                                             launches // K),
                 "bound": "tensor", "achieved": d["tensor_tflops"], "peak": peak_tc, "unit": "TFLOP/s",
-                "frac": d["frac_of_tensor_peak"], "traffic": traffic.get(d["kernel"].split("<")[0]),
+                "frac": d["frac_of_tensor_peak"],
+                "traffic": (traffic.get(d["kernel"].split("<")[0]) or {}).get("dram_bytes_per_launch"),
+                "traffic_source": (traffic.get(d["kernel"].split("<")[0]) or {}).get("source"),
                 "peak_source": peaks["source"] + ", sustained bf16 (the kernel sits inside a long step)",
                 "algorithmic_gflop_per_launch": flop_per_step[name] * v["work"] / launches / 1e9,
                 "avg_launch_ms": v["ms"] / launches, "launches_per_step": launches / K,
@@ -353,7 +355,7 @@ def roofline_report(raw, cfg, peaks, K, ms_per_step, clocks, gemm_mode):
     else:
         roof = {"kernel": name, "bound": "hbm", "achieved": memory_bound.get(name, {}).get("achieved_gbs"),
                 "peak": peaks["hbm"], "unit": "GB/s", "frac": memory_bound.get(name, {}).get("frac_of_hbm_peak"),
-                "traffic": traffic.get(name), "peak_source": peaks["source"]}
+                "traffic": (traffic.get(name) or {}).get("dram_bytes_per_launch"), "peak_source": peaks["source"]}
 
     at_bound = {"dense_gemms_ms": gemm_ms_at_bound, "sequential_floors_ms": floor_ms, "memory_bound_ms": mem_ms}
     pct = {"value": sum(at_bound.values()) / ms_per_step, "terms_ms": at_bound, "step_ms": ms_per_step,

@@ -309,7 +309,11 @@ __global__ void __launch_bounds__(256 + 32 * EW, 1) rec_fwd_ws_kernel(MParams p)
 }
 
 // ---------------------------------------------------------------- backward
-template <int CS, int NS, int EW>
+// F16: the fp16 split scheme for the backward products too.  dz spans many orders of magnitude ACROSS utterances (and
+// fp16 has 5 exponent bits), so every row of the CTA's dz tile is scaled by its own power of two before the split
+// (amax over the CTA's 64 gate columns of the row: a 16-lane shuffle reduction by the epilogue warps) and the MMA warps
+// scale their partial d h rows back before the reduce-scatter -- the partial sums of the 16 CTAs stay in true scale.
+template <int CS, int NS, int EW, bool F16>
 __global__ void __launch_bounds__(256 + 32 * EW, 1) rec_bwd_ws_kernel(MParams p) {
     constexpr int NR = 8 / EW;                                   // rows per epilogue thread (EW = 4: r0 and r0 + 8)
     constexpr int H = CS * UPC;
@@ -321,6 +325,7 @@ __global__ void __launch_bounds__(256 + 32 * EW, 1) rec_bwd_ws_kernel(MParams p)
     float* dz_s = stage + NS * 2 * CS * TILE;                    // [NS][2][8 k-tiles][32 chunks][4] own dz, fragment order
     __shared__ __align__(8) uint64_t full[NS][2];                // the CS partial tiles of a step have arrived
     __shared__ __align__(8) uint64_t dzready[NS];                // the 4 epilogue warps have written dz_t
+    __shared__ float rinv_s[NS][2][R];                           // F16: 1 / (row scale) of the dz tile of (slice, buffer)
 
     const int ndir = p.ndir, T = p.T, Tp = p.Tp;
     const uint32_t rank = cluster_rank();
@@ -354,7 +359,27 @@ __global__ void __launch_bounds__(256 + 32 * EW, 1) rec_bwd_ws_kernel(MParams p)
         const int g = lane / 4, tq = lane % 4;
         // resident fragments: B[k][n] = W_hh[hidden unit n][own gate column k]
         uint32_t bh[8][NTL][2], bl[8][NTL][2];
-        {
+        if (F16) {
+            // bh[q][nt] := packed fp16 W of k16 pair q, bl[q][nt] := packed fp16 of (W - fp16 W) 2^11 (q < 4)
+            const float* Wg = p.Wh + (size_t)dir * H * H * 4;
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+#pragma unroll
+                for (int nt = 0; nt < NTL; ++nt) {
+                    const int n_unit = 16 * (w * ND + nt / 2) + 4 * (g >> 1) + 2 * (nt & 1) + (g & 1);
+#pragma unroll
+                    for (int j = 0; j < 2; ++j) {
+                        unsigned short hi[2], lo[2];
+#pragma unroll
+                        for (int e = 0; e < 2; ++e) {
+                            const int kcol = 8 * (2 * q + j) + tq + 4 * e;
+                            split_f16(Wg[(size_t)n_unit * H * 4 + rank * 4 * UPC + kcol], hi[e], lo[e]);
+                        }
+                        bh[q][nt][j] = pack_u16(hi[0], hi[1]);
+                        bl[q][nt][j] = pack_u16(lo[0], lo[1]);
+                    }
+                }
+        } else {
             const float* Wg = p.Wh + (size_t)dir * H * H * 4;
 #pragma unroll
             for (int kt = 0; kt < 8; ++kt)
@@ -401,15 +426,38 @@ __global__ void __launch_bounds__(256 + 32 * EW, 1) rec_bwd_ws_kernel(MParams p)
                 mbar_wait(&dzready[sl], (dph >> sl) & 1u);
                 dph ^= 1u << sl;
                 const float* dzs = dz_s + (size_t)(sl * 2 + buf) * 8 * 128;
-                float4 a0 = *reinterpret_cast<const float4*>(dzs + lane * 4);
-                float4 a1 = *reinterpret_cast<const float4*>(dzs + 128 + ((lane ^ 1) * 4));
+                if (F16) {
+                    // [hi fragments of the 4 k16 pairs: 4 x 512 B | lo' fragments], already in register order
+                    uint4 a0 = *reinterpret_cast<const uint4*>(dzs + lane * 4);
+                    uint4 a1 = *reinterpret_cast<const uint4*>(dzs + 512 + lane * 4);
 #pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    const int k0 = q + 1 < 4 ? 2 * q + 2 : 2 * q, k1 = k0 + 1;
-                    const float4 n0 = *reinterpret_cast<const float4*>(dzs + k0 * 128 + ((lane ^ k0) * 4));
-                    const float4 n1 = *reinterpret_cast<const float4*>(dzs + k1 * 128 + ((lane ^ k1) * 4));
-                    k16_mma<NTL>(acc, accx, a0, a1, bh[2 * q], bh[2 * q + 1], bl[2 * q], bl[2 * q + 1]);
-                    a0 = n0; a1 = n1;
+                    for (int q = 0; q < 4; ++q) {
+                        const int qn = q + 1 < 4 ? q + 1 : q;
+                        const uint4 n0 = *reinterpret_cast<const uint4*>(dzs + qn * 128 + lane * 4);
+                        const uint4 n1 = *reinterpret_cast<const uint4*>(dzs + 512 + qn * 128 + lane * 4);
+                        k16_mma_f16<NTL>(acc, accx, a0, a1, bh[q], bl[q]);
+                        a0 = n0; a1 = n1;
+                    }
+                    const float r0s = rinv_s[sl][buf][g], r1s = rinv_s[sl][buf][g + 8];
+#pragma unroll
+                    for (int nt = 0; nt < NTL; ++nt) {
+                        acc[nt][0] = fmaf(accx[nt][0], kF16LoInv, acc[nt][0]) * r0s;
+                        acc[nt][1] = fmaf(accx[nt][1], kF16LoInv, acc[nt][1]) * r0s;
+                        acc[nt][2] = fmaf(accx[nt][2], kF16LoInv, acc[nt][2]) * r1s;
+                        acc[nt][3] = fmaf(accx[nt][3], kF16LoInv, acc[nt][3]) * r1s;
+                        accx[nt][0] = accx[nt][1] = accx[nt][2] = accx[nt][3] = 0.f;
+                    }
+                } else {
+                    float4 a0 = *reinterpret_cast<const float4*>(dzs + lane * 4);
+                    float4 a1 = *reinterpret_cast<const float4*>(dzs + 128 + ((lane ^ 1) * 4));
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        const int k0 = q + 1 < 4 ? 2 * q + 2 : 2 * q, k1 = k0 + 1;
+                        const float4 n0 = *reinterpret_cast<const float4*>(dzs + k0 * 128 + ((lane ^ k0) * 4));
+                        const float4 n1 = *reinterpret_cast<const float4*>(dzs + k1 * 128 + ((lane ^ k1) * 4));
+                        k16_mma<NTL>(acc, accx, a0, a1, bh[2 * q], bh[2 * q + 1], bl[2 * q], bl[2 * q + 1]);
+                        a0 = n0; a1 = n1;
+                    }
                 }
                 float* sg = stage + ((size_t)(sl * 2 + buf) * CS + w * ND) * TILE + g * UPC + 4 * tq;
 #pragma unroll
@@ -524,7 +572,36 @@ __global__ void __launch_bounds__(256 + 32 * EW, 1) rec_bwd_ws_kernel(MParams p)
                         dc_reg[sl][j] = dct * sf;
                     }
                 }
-                if (s + 1 < T) {
+                if (F16 && s + 1 < T) {
+                    // fp16 fragments of the CTA's dz tile, every row scaled by its own power of two: k16 pair q = ul / 4
+                    // holds units 4q .. 4q+3; 16-bit slot of (row, unit, gate) = word [q][lane = (row % 8) * 4 + gate]
+                    // [reg = 2 * ((ul % 4) / 2) + row / 8], half ul % 2; hi plane, then lo' plane (+512 words)
+                    unsigned short* dqh = reinterpret_cast<unsigned short*>(dz_s + (size_t)(sl * 2 + buf) * 8 * 128);
+#pragma unroll
+                    for (int j = 0; j < NR; ++j) {
+                        const int row = r0 + 8 * j;
+                        float amax = fmaxf(fmaxf(fabsf(dz[j].x), fabsf(dz[j].y)), fmaxf(fabsf(dz[j].z), fabsf(dz[j].w)));
+#pragma unroll
+                        for (int o = 8; o > 0; o >>= 1) amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, o));
+                        float sc = 1.0f;
+                        if (amax >= 1.17549435e-38f) {
+                            const int ex = (int)((__float_as_uint(amax) >> 23) & 0xFF) - 127;
+                            sc = __uint_as_float((uint32_t)(min(max(13 - ex, -126), 126) + 127) << 23);
+                        }
+                        if (ul == 0) rinv_s[sl][buf][row] = 1.0f / sc;
+                        const float v[4] = {dz[j].x * sc, dz[j].y * sc, dz[j].z * sc, dz[j].w * sc};
+                        const int wbase = (ul >> 2) * 128 + (row & 7) * 16 + 2 * ((ul & 3) >> 1) + (row >> 3);
+#pragma unroll
+                        for (int gt = 0; gt < 4; ++gt) {
+                            unsigned short hi, lo;
+                            split_f16(v[gt], hi, lo);
+                            dqh[(wbase + gt * 4) * 2 + (ul & 1)] = hi;
+                            dqh[(512 + wbase + gt * 4) * 2 + (ul & 1)] = lo;
+                        }
+                    }
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&dzready[sl]);
+                } else if (s + 1 < T) {
                     // own dz tile in fragment order [k-tile = ul/2][16-byte chunk (r0*4 + gate) ^ k-tile][2 (ul%2) + row/8]:
                     // the thread's two rows are the adjacent floats of one slot pair
                     float* dq = dz_s + (size_t)(sl * 2 + buf) * 8 * 128 + (ul >> 1) * 128 + 2 * (ul & 1) + (r0 >> 3);
@@ -561,14 +638,14 @@ size_t fwd_ws_smem(int CS, int NS) { return sizeof(float) * ((size_t)NS * 2 * CS
 size_t bwd_ws_smem(int CS, int NS) { return sizeof(float) * ((size_t)NS * 4 * CS * TILE + (size_t)NS * 2 * 8 * 128); }
 
 }  // namespace
-int g_rec_fwd_f16 = 1;      // forward recurrence: 1 = fp16 split scheme, 0 = tf32 + bf16 scheme (test mode 7)
+int g_rec_fwd_f16 = 1;      // recurrences: 1 = fp16 split scheme, 0 = tf32 + bf16 scheme (test mode 7)
 
 namespace {
 
 template <int CS, int NS>
 int launch_ws(cudaStream_t st, bool bwd, const MParams& p, int nclusters, int* max_active) {
     auto kf = g_rec_fwd_f16 ? rec_fwd_ws_kernel<CS, NS, ews(NS), true> : rec_fwd_ws_kernel<CS, NS, ews(NS), false>;
-    auto kb = rec_bwd_ws_kernel<CS, NS, ews(NS)>;
+    auto kb = g_rec_fwd_f16 ? rec_bwd_ws_kernel<CS, NS, ews(NS), true> : rec_bwd_ws_kernel<CS, NS, ews(NS), false>;
     const void* fn = bwd ? (const void*)kb : (const void*)kf;
     size_t smem = bwd ? bwd_ws_smem(CS, NS) : fwd_ws_smem(CS, NS);
     E2E_CHECK_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

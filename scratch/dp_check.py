@@ -1,11 +1,17 @@
 """2-GPU check of the data-parallel step (run under torchrun): the clipped gradient of the DP step (per-rank shards,
 overlapped span all-reduce, 1/n folded into the clip) must equal the single-GPU step on the GLOBAL batch."""
-import os, sys
+import os, sys, faulthandler
 sys.path.insert(0, '.')
+faulthandler.enable()
+faulthandler.dump_traceback_later(int(os.environ.get("DP_CHECK_DUMP_S", "70")), exit=True)    # a hang prints every thread's stack
 import numpy as np, torch, torch.distributed as dist
 from e2e_asr_b200 import ops, synth
 from e2e_asr_b200 import dist as edist
 from e2e_asr_b200.testing import build_model
+
+def say(*a):
+    print("[rank %s]" % os.environ.get("RANK", "0"), *a, flush=True)
+
 
 rank, world, local = edist.init_from_env()
 torch.cuda.set_device(local)
@@ -17,15 +23,24 @@ w = synth.make_weights(cfg_g)
 gbatch = synth.make_batch(cfg_g)
 shard = edist.shard_batch(gbatch, rank, world)
 cfg_r = synth.get_config(name, B=cfg_g.B // world)
+warm = torch.zeros(1, device=dev)
+dist.all_reduce(warm)
+torch.cuda.synchronize()
+say("communicator up")
 red = edist.GradAllReducer()
 model = build_model(cfg_r, w, device=dev, reducer=red)
 results = {}
 for mode in ("eager", "graph"):
+    say("mode", mode)
     if mode == "graph":
         gs = model.graphed_step(shard)
+        say("captured")
         gs.step(shard); gs.step(shard)
     else:
-        model.run_step(shard); model.run_step(shard)
+        model.run_step(shard)
+        torch.cuda.synchronize()
+        say("first eager step done")
+        model.run_step(shard)
     torch.cuda.synchronize()
     results[mode] = (model.variables.flat_grads().detach().clone(), float(model.grad_norm))
     print("rank %d %s: norm %.6f collectives/step %d" % (rank, mode, results[mode][1], red.collectives), flush=True)
