@@ -372,9 +372,10 @@ extern int g_rec_mc_ns;
 // cluster/DSMEM kernel, else the L2 kernel); 1 = always the L2 / global-barrier kernel; 2 = cluster/DSMEM or L2
 // kernel only; 3 / 4 = the non-specialised register-resident kernel (lstm_rec_mc.cu) with 1 / 2 interleaved
 // batch slices per cluster; 5 / 6 = the warp-specialised kernel with 1 / 2 slices forced (tests); 7 = the
-// warp-specialised kernel with the forward pass on the tf32 + bf16 scheme instead of the fp16 split scheme
+// warp-specialised kernel with the forward pass on the tf32 + bf16 scheme instead of the fp16 split scheme; 8 = the
+// warp-specialised kernel with the fp16 split scheme in the backward pass too
 int g_rec_mode = 0;
-extern int g_rec_fwd_f16;
+extern int g_rec_fwd_f16, g_rec_bwd_f16;
 
 // workspace: ctr_ws must hold >= 4*ceil(B/4) unsigned + 1 int, zeroed by this function.
 int lstm_rec(cudaStream_t st, bool bwd, int B, int T, int Tp, int H, int ndir, long long sb, long long stt,
@@ -384,8 +385,9 @@ int lstm_rec(cudaStream_t st, bool bwd, int B, int T, int Tp, int H, int ndir, l
     E2E_REQUIRE(ndir == 1 || ndir == 2, "lstm_rec: ndir must be 1 or 2");
     E2E_REQUIRE(Tp >= T, "lstm_rec: Tp (%d) must be >= T (%d)", Tp, T);
     if (B <= 0 || T <= 0) return 0;
-    if (g_rec_mode == 0 || g_rec_mode == 5 || g_rec_mode == 6 || g_rec_mode == 7) {
+    if (g_rec_mode == 0 || (g_rec_mode >= 5 && g_rec_mode <= 8)) {
         g_rec_fwd_f16 = g_rec_mode != 7;
+        g_rec_bwd_f16 = g_rec_mode == 8;
         int rc = lstm_rec_ws(st, bwd, B, T, Tp, H, ndir, sb, stt, G, Hout, Cst, Wh, dOut, lens, ctr_ws, ctr_ws_bytes,
                              (g_rec_mode == 5 || g_rec_mode == 6) ? g_rec_mode - 4 : 0);
         if (rc >= 0) return rc;
