@@ -566,8 +566,14 @@ def main():
     ops.check_device_errors(dev)
 
     if world > 1:
+        # The captured step holds NCCL collectives as graph nodes: destroying the process group (or letting the
+        # interpreter tear it down) while such a graph exists blocks forever.  All measurements are done: the other
+        # ranks leave right here, rank 0 reports and leaves the same way.
         barrier()
-        dist.destroy_process_group()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        if rank != 0:
+            os._exit(0)
     if rank != 0:
         return
     # ---------------- per-kernel-class breakdown and roofline (CUDA events of the eager timed pass)
@@ -606,6 +612,8 @@ def main():
         line["beam_decode"] = beam_decode_rate(args.config, dev, cpu=not args.no_cpu_baseline)
     print(json.dumps(line))
     sys.stdout.flush()
+    if world > 1:
+        os._exit(0)
 
 
 def beam_decode_rate(cfg_name, dev, n_utts=256, beam=10, cpu=True):

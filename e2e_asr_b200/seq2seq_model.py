@@ -534,6 +534,16 @@ class GraphedStep(object):
         self.launches_per_step = _launch_count() - n0
         cur.synchronize()
 
+    def release(self):
+        """Drops the captured graph and its memory pool.  With data parallelism the graph holds NCCL collectives as
+        nodes: it MUST be released before torch.distributed.destroy_process_group(), which otherwise blocks forever."""
+        self.graph = None
+        self.prepared = None
+        import gc
+        gc.collect()
+        if torch.cuda.is_available():
+            torch.cuda.synchronize()
+
     def _signature(self, prepared):
         """What a batch must share with the captured one: the tensor shapes and -- unless the step was captured for a
         bucket, with loop bounds from the padded shapes -- the maximum lengths that bound its loops."""

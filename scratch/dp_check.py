@@ -64,4 +64,14 @@ for _ in range(K):
     gs.step()
 e1.record(); torch.cuda.synchronize()
 print("rank %d: %.3f ms/step (graph, dp%d)" % (rank, e0.elapsed_time(e1) / K, world), flush=True)
+# a CUDA graph holding NCCL nodes must be gone before the process group is destroyed (destroy blocks forever otherwise)
+dist.barrier()
+torch.cuda.synchronize()
+del gs
+del model
+import gc
+gc.collect()
+torch.cuda.synchronize()
+say("graph released")
 dist.destroy_process_group()
+say("process group destroyed")
