@@ -524,6 +524,7 @@ def main():
             failed = 1.0
         if max_over_ranks(failed) > 0.0:
             gs, use_graph = None, False
+            model.run_step(prepared=prepared)       # the aborted capture dropped the step's results: redo one
     if use_graph:
         for _ in range(W):
             gs.step()

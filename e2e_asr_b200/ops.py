@@ -345,11 +345,29 @@ def mark_step_start(device):
     _STEP_START[_devkey(device)] = ev
 
 
+_WGRAD_USED = set()      # (device key, name) of side streams that took work since the last join
+
+
+def _side_stream(dev, name):
+    """The "enc" / "dec" side stream of the device (None when the side streams are off).  A caller that enqueues work
+    on it calls _mark_side: only streams that took work are joined by sync_wgrad_stream -- joining an idle stream
+    during a CUDA-graph capture would make the captured stream wait on uncaptured work
+    (cudaErrorStreamCaptureIsolation)."""
+    return _WGRAD.get(_devkey(dev), {}).get(name)
+
+
+def _mark_side(dev, name):
+    _WGRAD_USED.add((_devkey(dev), name))
+
+
 def sync_wgrad_stream(device):
-    ss = _WGRAD.get(_devkey(device))
+    key = _devkey(device)
+    ss = _WGRAD.get(key)
     if ss is not None:
-        for s in ss.values():
-            torch.cuda.current_stream().wait_stream(s)
+        for name, s in ss.items():
+            if (key, name) in _WGRAD_USED:
+                torch.cuda.current_stream().wait_stream(s)
+                _WGRAD_USED.discard((key, name))
 
 
 class BiLSTMLayerFn(torch.autograd.Function):
@@ -421,11 +439,12 @@ class BiLSTMLayerFn(torch.autograd.Function):
             dbp = colsum(G)
             return dWx, dWh, dbp
 
-        side = _WGRAD.get(_devkey(dev), {}).get("enc")
+        side = _side_stream(dev, "enc")
         dst = ctx.grad_dst
         pad = (None,) * (2 * (2 - nd))
         if side is not None and all(d is not None for d in dst) and all(ctx.needs_input_grad[1:1 + 2 * nd]):
             main = torch.cuda.current_stream()
+            _mark_side(dev, "enc")
             side.wait_stream(main)
             with torch.cuda.stream(side):
                 dWx, dWh, dbp = weight_grads()
@@ -925,10 +944,11 @@ class AttnDecoderFnV2(torch.autograd.Function):
         # The LM side of the decoder (embedding -> LM-LSTM -> InputProjection -> decoder-gate pre-activations) reads only
         # the teacher-forced ids and parameters: with the side streams on, it runs on the "dec" stream from the step's
         # start event, concurrently with the encoder, and the main stream joins it here.
-        side = _WGRAD.get(_devkey(dev), {}).get("dec")
+        side = _side_stream(dev, "dec")
         main = torch.cuda.current_stream()
         start = _STEP_START.pop(_devkey(dev), None) if stash is not None and stash.get("early_lm") else None
         if side is not None:
+            _mark_side(dev, "dec")
             if start is not None:
                 side.wait_event(start)
             else:
@@ -1073,12 +1093,13 @@ class AttnDecoderFnV2(torch.autograd.Function):
             return [demb, dattn_w, dattn_v, dlm_k, dlm_b, ddec_k, ddec_b, dq_k, dq_b, dap_k, dap_b, dout_k,
                     dout_b, din_k, din_b, dsp_k, dsp_b]
 
-        side = _WGRAD.get(_devkey(dev), {}).get("dec")
+        side = _side_stream(dev, "dec")
         dst = ctx.grad_dst
         need = [True] * 15 + [ctx.has_sp, ctx.has_sp]
         if (side is not None and all((d is not None) or (not n) for d, n in zip(dst, need))
                 and all(ctx.needs_input_grad[1 + i] or not need[i] for i in range(17))):
             main = torch.cuda.current_stream()
+            _mark_side(dev, "dec")
             side.wait_stream(main)
             with torch.cuda.stream(side):
                 grads = param_grads(st["ctr_side"])

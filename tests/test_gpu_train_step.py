@@ -132,6 +132,26 @@ def test_train_step_with_dropout_matches_oracle(cname, impl):
     assert abs(ref["total_loss"] - nodrop["total_loss"]) > 1e-3
 
 
+@pytest.mark.parametrize("cname", ["tiny_b", "wide_small"])
+def test_graphed_step_with_the_per_step_decoder_kernels(cname):
+    """The capture must also work when the decoder runs the per-step kernels (shapes the persistent loop cannot hold,
+    e.g. cfg-5's D = 1024): that path never touches the "dec" side stream, which the end-of-step join then has to
+    leave alone (waiting on an idle, uncaptured stream aborts a capture)."""
+    cfg = synth.get_config(cname)
+    w = synth.make_weights(cfg, bias_noise=0.1)
+    batch = synth.make_batch(cfg)
+    ref = om.train_step(w, batch, num_layers={"char": cfg.L}, ctc_tasks=cfg.ctc)
+    ops.set_decoder_impl("loop")
+    try:
+        model = build_model(cfg, w, device="cuda:0")
+        gs = model.graphed_step(batch)
+        gs.step(batch)
+        ops.check_device_errors("cuda:0")
+        compare_step(model, ref, rtol=RTOL)
+    finally:
+        ops.set_decoder_impl("persist")
+
+
 @pytest.mark.parametrize("cname", ["tiny_b", "cfg1"])
 def test_graphed_step_with_dropout_draws_a_new_mask_every_replay(cname):
     """The reference's training defaults keep 0.9 of the outputs: the step captured WITH dropout must draw the mask
