@@ -39,6 +39,7 @@ void set_workspace(void*, size_t);
 bool set_stream_workspace(cudaStream_t, void*, size_t);
 extern int g_rec_mode;
 extern long long* g_rec_dbg;
+extern int g_dec_p2p;
 void set_tc_debug(float*, long long);
 int colsum(cudaStream_t, int, int, const float*, int, float*, int);
 int lstm_rec(cudaStream_t, bool, int, int, int, int, int, long long, long long, float*, float*, float*,
@@ -198,6 +199,10 @@ int e2e_set_tc_debug(float* dbg, long long min_work) {
 }
 int e2e_set_rec_mode(int mode) {
     g_rec_mode = mode;
+    return 0;
+}
+int e2e_set_dec_sync(int p2p) {
+    g_dec_p2p = p2p ? 1 : 0;
     return 0;
 }
 int e2e_set_rec_debug(long long* dbg) {

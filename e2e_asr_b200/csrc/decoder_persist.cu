@@ -22,6 +22,7 @@
 namespace e2e {
 
 extern long long* g_rec_dbg;
+int g_dec_p2p = 1;                 // 1 = point-to-point row-block counters, 0 = grid barriers (e2e_set_dec_sync test hook)
 
 namespace {
 
@@ -129,6 +130,28 @@ __device__ __forceinline__ void grid_barrier(unsigned* ctr, unsigned& epoch, int
     __syncthreads();
 }
 
+// Point-to-point synchronisation per 16-row block instead of grid barriers (stride != 0): the batch rows of different
+// row blocks never exchange data, and inside a block every phase only needs the PREVIOUS phase's tiles of that block.
+// Each phase of each row block owns a monotonically increasing L2 counter; a CTA arrives once per tile it finished
+// (release) and, before a tile, waits until the producers' counter reaches (tiles per round) x (rounds so far)
+// (acquire).  16-32 arrivals on 12 different counters replace 128 arrivals on one, and nobody waits for another row
+// block's stragglers.  Deadlock-free for any tile -> CTA mapping: every CTA walks (step, phase) in the same order and
+// the grid is co-resident (cooperative launch).
+struct P2P {
+    unsigned* base;      // p.ctr + 1
+    int stride, nrb;     // stride 0: disabled (grid barriers)
+    __device__ __forceinline__ unsigned* at(int phase, int rb) const { return base + (size_t)stride * (phase * nrb + rb); }
+};
+__device__ __forceinline__ void tile_arrive(unsigned* c) {
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // generic smem writes before later bulk copies
+    __syncthreads();
+    if (threadIdx.x == 0) red_release_gpu_add(c, 1u);
+}
+__device__ __forceinline__ void tile_wait(const unsigned* c, unsigned target, int* err) {
+    if (threadIdx.x == 0) spin_wait_ge(c, target, err);
+    __syncthreads();
+}
+
 __device__ __forceinline__ float ldcg(const float* p) { return __ldcg(p); }
 // ex2.approx + rcp.approx: absolute error ~2e-7, inside the 1e-4 parity budget
 __device__ __forceinline__ float sigmoid_fast(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
@@ -164,7 +187,7 @@ __device__ long long* d_dec_dbg = nullptr;
 }  // namespace
 
 // ======================================================================= forward
-__global__ void __launch_bounds__(NTH, 1) dec_fwd_persist_kernel(e2e_dec_persist_args p, int attn_cap) {
+__global__ void __launch_bounds__(NTH, 1) dec_fwd_persist_kernel(e2e_dec_persist_args p, int attn_cap, int p2p_stride) {
     extern __shared__ __align__(128) float smem[];
     const int B = p.B, U = p.U, Hd = p.Hd, A = p.A, D = p.D, Tn = p.Tn, Tp = p.Tp;
     const int K = D + Hd, G4 = 4 * Hd, CAT = Hd + D;
@@ -180,6 +203,8 @@ __global__ void __launch_bounds__(NTH, 1) dec_fwd_persist_kernel(e2e_dec_persist
     const int NCB = Hd / 8, nrb = (B + 15) / 16, gtiles = nrb * NCB;
     const bool resident = gtiles <= (int)gridDim.x;
     unsigned epoch = 0;
+    const P2P pp{p.ctr + 1, p2p_stride, nrb};      // phases: 0 = G (gates), 1 = Y (query), 2 = A (attention)
+    const bool p2p = p2p_stride != 0;
     // fast attention read-out: one (row, half) item per CTA and HF[b] / half of enc[b] fit the staging buffers
     // attn_cap: floats in attn_buf (0: not provisioned by the launcher)
     float* attn_buf = qres + 8 * (Hd + 4);
@@ -224,6 +249,7 @@ __global__ void __launch_bounds__(NTH, 1) dec_fwd_persist_kernel(e2e_dec_persist
             if (!resident) { __syncthreads(); load_wt(cb); }
             // A tile: [ctx_{t-1} (D) | h_{t-1} (Hd)] for rows rb*16 .. +16: one bulk copy per row segment
             const int nvalid = min(16, B - rb * 16);
+            if (p2p && t > 0) tile_wait(pp.at(2, rb), (unsigned)(2 * nvalid * t), p.err);   // ctx_{t-1} of the block
             if (tid == 0) mbar_expect_tx(&abar[2], (uint32_t)(nvalid * (Hd + (t > 0 ? D : 0)) * 4));
             __syncwarp();
             if (lane * 8 + w < 32) {
@@ -297,9 +323,10 @@ __global__ void __launch_bounds__(NTH, 1) dec_fwd_persist_kernel(e2e_dec_persist
                 }
             }
             __syncthreads();
+            if (p2p) tile_arrive(pp.at(0, rb));
         }
         DEC_STAMP(t, 1);
-        grid_barrier(p.ctr, epoch, p.err);
+        if (!p2p) grid_barrier(p.ctr, epoch, p.err);
         DEC_STAMP(t, 2);
         // ------------------------------------------------------------ phase Y: y = c_new . q_k + q_b
         {
@@ -309,6 +336,7 @@ __global__ void __launch_bounds__(NTH, 1) dec_fwd_persist_kernel(e2e_dec_persist
                 const int rb = tile / (A / 8), nt = tile % (A / 8);
                 const int nvalid = min(16, B - rb * 16);
                 __syncthreads();
+                if (p2p) tile_wait(pp.at(0, rb), (unsigned)(NCB * (t + 1)), p.err);            // c_new of the block
                 if (tid == 0) mbar_expect_tx(&abar[2], (uint32_t)(nvalid * Hd * 4));
                 __syncwarp();
                 if (lane * 8 + w < nvalid) {
@@ -343,10 +371,11 @@ __global__ void __launch_bounds__(NTH, 1) dec_fwd_persist_kernel(e2e_dec_persist
                     if (b0 < B) *reinterpret_cast<float2*>(p.y + ((size_t)t * B + b0) * A + col) = make_float2(acc.x + qb0, acc.y + qb1);
                     if (b1 < B) *reinterpret_cast<float2*>(p.y + ((size_t)t * B + b1) * A + col) = make_float2(acc.z + qb0, acc.w + qb1);
                 }
+                if (p2p) tile_arrive(pp.at(1, rb));
             }
         }
         DEC_STAMP(t, 3);
-        grid_barrier(p.ctr, epoch, p.err);
+        if (!p2p) grid_barrier(p.ctr, epoch, p.err);
         DEC_STAMP(t, 4);
         // ------------------------------------------------------------ phase A: attention read-out
         if (fastA) {
@@ -366,10 +395,11 @@ __global__ void __launch_bounds__(NTH, 1) dec_fwd_persist_kernel(e2e_dec_persist
             const float* HFb = p.HF + (size_t)b * Tp * A;
             const float* encb = p.enc + (size_t)b * Tp * D + half * dh;
             const int c0 = min(TC, len), c1 = max(len - TC, 0);
+            // HF[b] and the first enc rows do not depend on this step: their copies are in flight while the CTA waits
+            // for the row block's query y_t
             if (tid == 0) {
                 mbar_expect_tx(&abar[0], (uint32_t)((len + 1) * A * 4));
                 bulk_g2s(bufX, HFb, (uint32_t)(len * A * 4), &abar[0]);
-                bulk_g2s(y_s, p.y + ((size_t)t * B + b) * A, (uint32_t)(A * 4), &abar[0]);
                 mbar_expect_tx(&abar[1], (uint32_t)(c0 * dh * 4));
             }
             __syncwarp();
@@ -377,6 +407,8 @@ __global__ void __launch_bounds__(NTH, 1) dec_fwd_persist_kernel(e2e_dec_persist
             // (a lane issues its copies serially, ~100 cycles each: slot = lane*8 + warp keeps that to a few per warp)
             for (int r = lane * 8 + w; r < c0; r += NTH) bulk_g2s(bufY + r * dh, encb + (size_t)r * D, (uint32_t)(dh * 4), &abar[1]);
             if (t == 0) for (int a = tid; a < A; a += NTH) v_s[a] = p.attn_v[a];
+            if (p2p) tile_wait(pp.at(1, b / 16), (unsigned)((A / 8) * (t + 1)), p.err);        // y_t of the block
+            if (tid == 0) bulk_g2s(y_s, p.y + ((size_t)t * B + b) * A, (uint32_t)(A * 4), &abar[0]);
             DEC_STAMP(t, 8);
             mbar_wait_par(&abar[0], aph0);
             aph0 ^= 1u;
@@ -490,6 +522,7 @@ __global__ void __launch_bounds__(NTH, 1) dec_fwd_persist_kernel(e2e_dec_persist
             }
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             __syncthreads();                         // bufX = a_s is the next step's A tile
+            if (p2p) tile_arrive(pp.at(2, b / 16));
           }
         } else
         {
@@ -501,6 +534,7 @@ __global__ void __launch_bounds__(NTH, 1) dec_fwd_persist_kernel(e2e_dec_persist
                 const int b = item / 2, half = item % 2;
                 const int len = min(p.enc_len[b], Tn);
                 __syncthreads();
+                if (p2p) tile_wait(pp.at(1, b / 16), (unsigned)((A / 8) * (t + 1)), p.err);
                 for (int a = tid; a < A; a += NTH) { y_s[a] = __ldcg(p.y + ((size_t)t * B + b) * A + a); v_s[a] = p.attn_v[a]; }
                 __syncthreads();
                 const float* HFb = p.HF + (size_t)b * Tp * A;
@@ -586,17 +620,18 @@ __global__ void __launch_bounds__(NTH, 1) dec_fwd_persist_kernel(e2e_dec_persist
                         p.cat[((size_t)t * B + b) * CAT + Hd + dcol] = c;
                     }
                 }
+                if (p2p) tile_arrive(pp.at(2, b / 16));
             }
         }
         DEC_STAMP(t, 5);
-        grid_barrier(p.ctr, epoch, p.err);
+        if (!p2p) grid_barrier(p.ctr, epoch, p.err);
         DEC_STAMP(t, 6);
         if (dbg) dbg[t * 32 + 7] = fastA ? 1 : 0;
     }
 }
 
 // ======================================================================= backward
-__global__ void __launch_bounds__(NTH, 1) dec_bwd_persist_kernel(e2e_dec_persist_args p, int attn_fast) {
+__global__ void __launch_bounds__(NTH, 1) dec_bwd_persist_kernel(e2e_dec_persist_args p, int attn_fast, int p2p_stride) {
     extern __shared__ __align__(16) float smem[];
     const int B = p.B, U = p.U, Hd = p.Hd, A = p.A, D = p.D, Tn = p.Tn, Tp = p.Tp;
     const int K = D + Hd, G4 = 4 * Hd, CAT = Hd + D;
@@ -624,6 +659,9 @@ __global__ void __launch_bounds__(NTH, 1) dec_bwd_persist_kernel(e2e_dec_persist
     const int NXB = (K + NX - 1) / NX, xtiles = nrb * NXB;
     const bool resident = xtiles <= (int)gridDim.x;
     unsigned epoch = 0;
+    const P2P pp{p.ctr + 1, p2p_stride, nrb};      // phases: 0 = A' (attention backward), 1 = P (pointwise), 2 = X
+    const bool p2p = p2p_stride != 0;
+    const int a_arr = fastAp ? 2 : 1;              // A' arrivals per batch row and step
 
     auto load_wt2 = [&](int xb) {
         for (int i = tid; i < NX * (G4 / 4); i += NTH) {
@@ -675,12 +713,18 @@ __global__ void __launch_bounds__(NTH, 1) dec_bwd_persist_kernel(e2e_dec_persist
             if (tid == 0) {
                 mbar_expect_tx(&ebar, (uint32_t)((n + 1) * D * 4));
                 if (n > 0) bulk_g2s(encbuf, p.enc + ((size_t)b * Tp + tau0) * D, (uint32_t)(n * D * 4), &ebar);
-                bulk_g2s(dctx_s, p.dcat + row * CAT + Hd, (uint32_t)(D * 4), &ebar);
+                if (!p2p) bulk_g2s(dctx_s, p.dcat + row * CAT + Hd, (uint32_t)(D * 4), &ebar);
             }
             if (tid == 32) {
                 mbar_expect_tx(&hbar, (uint32_t)((n + 1) * A * 4));
                 if (n > 0) bulk_g2s(hfbuf, p.HF + ((size_t)b * Tp + tau0) * A, (uint32_t)(n * A * 4), &hbar);
                 bulk_g2s(y_s, p.y + row * A, (uint32_t)(A * 4), &hbar);
+            }
+            if (p2p) {
+                // the enc / HF rows and y_t above do not depend on the previous phase: in flight during the wait for
+                // d ctx_t (X of the previous round, all column tiles of the row block)
+                if (t < U - 1) tile_wait(pp.at(2, b / 16), (unsigned)(NXB * (U - 1 - t)), p.err);
+                if (tid == 0) bulk_g2s(dctx_s, p.dcat + row * CAT + Hd, (uint32_t)(D * 4), &ebar);
             }
             if (tid >= 64 && tid - 64 < n) al_s[tid - 64] = p.alpha[row * Tn + tau0 + tid - 64];
             if (t == U - 1) for (int a = tid; a < A; a += NTH) v_s[a] = p.attn_v[a];
@@ -755,6 +799,7 @@ __global__ void __launch_bounds__(NTH, 1) dec_bwd_persist_kernel(e2e_dec_persist
             }
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             __syncthreads();
+            if (p2p) tile_arrive(pp.at(0, b / 16));
           }
         } else {
             float* y_s = z_s;                   // [A]
@@ -767,6 +812,7 @@ __global__ void __launch_bounds__(NTH, 1) dec_bwd_persist_kernel(e2e_dec_persist
                 const int len = min(p.enc_len[b], Tn);
                 const size_t row = (size_t)t * B + b;
                 __syncthreads();
+                if (p2p && t < U - 1) tile_wait(pp.at(2, b / 16), (unsigned)(NXB * (U - 1 - t)), p.err);
                 for (int a = tid; a < A; a += NTH) { y_s[a] = p.y[row * A + a]; v_s[a] = p.attn_v[a]; }
                 for (int dd = tid; dd < D; dd += NTH) dctx_s[dd] = __ldcg(p.dcat + row * CAT + Hd + dd);
                 __syncthreads();
@@ -812,10 +858,11 @@ __global__ void __launch_bounds__(NTH, 1) dec_bwd_persist_kernel(e2e_dec_persist
                     for (int ww = 0; ww < 8; ++ww) dya += acc_s[ww * A + a];
                     p.dy[row * A + a] = dya;
                 }
+                if (p2p) tile_arrive(pp.at(0, b / 16));
             }
         }
         DEC_STAMP(t, 1);
-        grid_barrier(p.ctr, epoch, p.err);
+        if (!p2p) grid_barrier(p.ctr, epoch, p.err);
         DEC_STAMP(t, 2);
         // ------------------------------------------------------------ phase P: dc_new += dy . q_k^T ; pointwise backward
         {
@@ -825,6 +872,7 @@ __global__ void __launch_bounds__(NTH, 1) dec_bwd_persist_kernel(e2e_dec_persist
                 const int rb = tile / NCBp, cb = tile % NCBp;
                 const int nvalid = min(16, B - rb * 16);
                 __syncthreads();
+                if (p2p) tile_wait(pp.at(0, rb), (unsigned)(a_arr * nvalid * (U - t)), p.err);   // A' of the block
                 if (fastAp) {
                     // dy_a = v_a (S1_a - dot S2_a) from the two time-halves' partial sums (L2 scratch); float4
                     // columns, every load of a thread in flight together
@@ -911,10 +959,11 @@ __global__ void __launch_bounds__(NTH, 1) dec_bwd_persist_kernel(e2e_dec_persist
                     p.dc_carry[(size_t)eb * Hd + unit] = dcc;
                     *reinterpret_cast<float4*>(p.dz + row * G4 + unit * 4) = dz;
                 }
+                if (p2p) tile_arrive(pp.at(1, rb));
             }
         }
         DEC_STAMP(t, 3);
-        grid_barrier(p.ctr, epoch, p.err);
+        if (!p2p) grid_barrier(p.ctr, epoch, p.err);
         DEC_STAMP(t, 4);
         // ------------------------------------------------------------ phase X: [dctx_{t-1} | dh_{t-1}] = dz_t . W_ch^T
         for (int tile = blockIdx.x; tile < xtiles; tile += gridDim.x) {
@@ -922,6 +971,7 @@ __global__ void __launch_bounds__(NTH, 1) dec_bwd_persist_kernel(e2e_dec_persist
             const int nvalid = min(16, B - rb * 16);
             __syncthreads();
             if (!resident) load_wt2(xb);
+            if (p2p) tile_wait(pp.at(1, rb), (unsigned)(NCBp * (U - t)), p.err);                 // dz_t of the block
             if (tid == 0) mbar_expect_tx(&lbar, (uint32_t)(nvalid * G4 * 4));
             __syncwarp();
             if (lane * 8 + w < nvalid) {
@@ -961,9 +1011,10 @@ __global__ void __launch_bounds__(NTH, 1) dec_bwd_persist_kernel(e2e_dec_persist
                     if (col < D && t > 0) p.dcat[(row - B) * CAT + Hd + col] += v;
                 }
             }
+            if (p2p) tile_arrive(pp.at(2, rb));
         }
         DEC_STAMP(t, 5);
-        grid_barrier(p.ctr, epoch, p.err);
+        if (!p2p) grid_barrier(p.ctr, epoch, p.err);
         DEC_STAMP(t, 6);
     }
 }
@@ -1087,7 +1138,10 @@ int dec_persist(cudaStream_t st, bool bwd, const e2e_dec_persist_args* a, float*
     int want = bwd ? max(max(p.B, nrb * (p.Hd / 8)), nrb * ((p.D + p.Hd + 23) / 24))
                    : max(max(2 * p.B, nrb * (p.Hd / 8)), nrb * (p.A / 8));
     int grid = min(nsm, want);
-    E2E_CHECK_CUDA(cudaMemsetAsync(p.ctr, 0, sizeof(unsigned), st));
+    E2E_CHECK_CUDA(cudaMemsetAsync(p.ctr, 0, 64 * sizeof(unsigned), st));   // barrier counter + row-block counters
+    // point-to-point row-block counters: 3 phases x nrb counters in words 1 .. 63 of the scratch, `stride` words apart
+    int p2p_stride = 0;
+    if (g_dec_p2p && 3 * nrb <= 62) p2p_stride = max(1, min(8, 62 / (3 * nrb)));
     {
         static long long* last_dbg = nullptr;
         if (g_rec_dbg != last_dbg) {
@@ -1097,7 +1151,7 @@ int dec_persist(cudaStream_t st, bool bwd, const e2e_dec_persist_args* a, float*
     }
     int attn_cap = bwd ? bwd_attn_fast(p, &smem) : fwd_attn_cap(p, &smem);
     E2E_CHECK_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    void* args[] = {&p, &attn_cap};
+    void* args[] = {&p, &attn_cap, &p2p_stride};
     E2E_CHECK_CUDA(cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(NTH), args, smem, st));
     ++g_launches;
     if (bwd) {

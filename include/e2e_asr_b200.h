@@ -109,6 +109,9 @@ int e2e_lstm_unpack_grads(void* stream, int I, int H, float* dkernel, float* dbi
 int e2e_set_rec_mode(int mode);
 /* test hook: device buffer (>= 5*T int64) receiving per-step clock64 stamps of the forward cluster kernel, or NULL */
 int e2e_set_rec_debug(long long* dbg);
+/* test hook: 1 (default) = the persistent decoder kernels synchronise per 16-row block with point-to-point counters,
+ * 0 = three grid-wide barriers per step */
+int e2e_set_dec_sync(int p2p);
 int e2e_lstm_rec_fwd(void* stream, int B, int T, int Tp, int H, int ndir, long long sb, long long st,
                      float* G, float* Hout, float* Cst, const float* Wh, const int* lens,
                      void* ctr_ws, size_t ctr_ws_bytes, int* err_flag);

@@ -105,14 +105,19 @@ def _bilstm_case(B, T_, I, H):
         assert relerr(params[2 * d + 1].grad, ref_g[d][1]) < 2e-5
 
 
-@pytest.mark.parametrize("impl", ["persist", "loop"])
-@pytest.mark.parametrize("cname", ["tiny", "tiny_b"])
+@pytest.mark.parametrize("impl", ["persist", "persist-gridbarrier", "loop"])
+@pytest.mark.parametrize("cname", ["tiny", "tiny_b", "cfg1"])
 def test_attn_decoder_fwd_bwd(cname, impl):
-    ops.set_decoder_impl(impl)
+    """persist: the persistent decoder kernels with point-to-point row-block counters (default) / with three grid
+    barriers per step; loop: the per-step kernels."""
+    from e2e_asr_b200 import _lib
+    ops.set_decoder_impl("loop" if impl == "loop" else "persist")
+    _lib.lib().e2e_set_dec_sync(0 if impl == "persist-gridbarrier" else 1)
     try:
         _attn_decoder_case(cname)
     finally:
         ops.set_decoder_impl("persist")
+        _lib.lib().e2e_set_dec_sync(1)
 
 
 def _attn_decoder_case(cname):
