@@ -141,7 +141,7 @@ def _attn_decoder_case(cname):
     targets = dec_inp[1:int(seq_len.max()) + 1]
     ref_loss, dlog = om.cross_entropy_loss(ref_logits, targets, seq_len)
     ref_g, ref_denc = om.attn_decoder_bwd(dlog, cache)
-    vs = VariableStore(DEV, capacity=1 << 20)
+    vs = VariableStore(DEV, capacity=1 << 23)
     vs.load(w)
     dec = AttnDecoder(True, model_params(cfg).decoder_params["char"], scope="char", variables=vs)
     enc_t = T(enc).requires_grad_()
