@@ -23,6 +23,7 @@ _SIGS = {
     "e2e_lstm_unpack_grads": "piipppiippi",
     "e2e_lstm_rec_fwd": "piiiiillppppppzp",
     "e2e_lstm_rec_bwd": "piiiiillppppppzp",
+    "e2e_lstm_rec_fwd_carry": "piiiillppppppzp",
     "e2e_prepare_input": "piiiiiipp",
     "e2e_embed_gather": "piippp",
     "e2e_embed_scatter_add": "piipppi",
@@ -80,7 +81,7 @@ class DecLoopBwdArgs(ctypes.Structure):
 
 
 class DecPersistArgs(ctypes.Structure):
-    _fields_ = ([(n, ctypes.c_int) for n in ("B", "U", "Hd", "A", "D", "Tn", "Tp")] +
+    _fields_ = ([(n, ctypes.c_int) for n in ("B", "U", "Hd", "A", "D", "Tn", "Tp", "t0", "t1")] +
                 [(n, ctypes.c_void_p) for n in ("W_ch", "pre_g", "q_k", "q_b", "attn_v", "HF", "enc", "enc_len",
                                                 "lens", "cat", "hprev", "cprev", "acts", "y", "alpha", "dcat", "dz",
                                                 "dch", "dy", "ds", "dc_carry", "ctr", "err")])

@@ -144,20 +144,31 @@ class AttnDecoder(Decoder):
             if self.isTraining and self.params.out_prob_dec < 1.0:
                 lm_drop = (self.params.out_prob_dec, getattr(self, "dropout_seed", 0),
                            100 + getattr(self, "dropout_stream", 0))
+            samp = None
             if rule == "sample":
-                # scheduled sampling: realise the input ids without a tape, then take the teacher-forced step on them
-                from .inference import sample_decode_ids
-                with torch.no_grad():
-                    ids = sample_decode_ids(v, decoder_inp, lens, U, enc.detach(), enc_len, self.params.samp_prob,
-                                            getattr(self, "dropout_seed", 0), getattr(self, "dropout_stream", 0),
-                                            lm_drop=lm_drop)
-                decoder_inp = self.stash["realized_ids"] = ids
+                from .host_utils import philox_uniform
+                seed, stream = getattr(self, "dropout_seed", 0), getattr(self, "dropout_stream", 0)
+                if (ops._DECODER_IMPL == "persist" and ops._persist_fits(enc, v["dec_k"], v["q_k"], U)
+                        and v["lm_k"].shape[1] // 4 in (128, 256)):       # the carried-state LM-LSTM entry
+                    # scheduled sampling inside the training forward pass: the persistent loop runs in segments between
+                    # the sampled steps (ops.AttnDecoderFnV2._forward_sampled); one scalar draw per step decides
+                    use = [False] + [not (philox_uniform(t, 200 + stream, seed) < 1.0 - self.params.samp_prob)
+                                     for t in range(1, U)]
+                    samp = (use, seed, 300 + stream)
+                else:
+                    # shapes the persistent kernels cannot hold: realise the input ids without a tape (one decoder step
+                    # at a time), then take the teacher-forced step on them
+                    from .inference import sample_decode_ids
+                    with torch.no_grad():
+                        ids = sample_decode_ids(v, decoder_inp, lens, U, enc.detach(), enc_len, self.params.samp_prob,
+                                                seed, stream, lm_drop=lm_drop)
+                    decoder_inp = self.stash["realized_ids"] = ids
             # teacher-forced ids are known when the step starts: the LM side may run ahead of the encoder
             self.stash["early_lm"] = rule == "teacher"
             return ops.attn_decoder_apply(
                 enc, v["emb"], v["attn_w"], v["attn_v"], v["lm_k"], v["lm_b"], v["dec_k"], v["dec_b"], v["q_k"],
                 v["q_b"], v["ap_k"], v["ap_b"], v["out_k"], v["out_b"], v["in_k"], v["in_b"], v["sp_k"], v["sp_b"],
-                decoder_inp, lens, enc_len, U, self.stash, lm_drop=lm_drop)
+                decoder_inp, lens, enc_len, U, self.stash, lm_drop=lm_drop, samp=samp)
         from .inference import greedy_decode_logits
         with torch.no_grad():
             return greedy_decode_logits(v, decoder_inp, lens, U, enc, enc_len)

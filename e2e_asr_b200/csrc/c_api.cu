@@ -44,6 +44,8 @@ void set_tc_debug(float*, long long);
 int colsum(cudaStream_t, int, int, const float*, int, float*, int);
 int lstm_rec(cudaStream_t, bool, int, int, int, int, int, long long, long long, float*, float*, float*,
              const float*, const float*, const int*, void*, size_t, int*);
+int lstm_rec_fwd_carry(cudaStream_t, int, int, int, int, long long, long long, float*, float*, float*, const float*,
+                       const int*, void*, size_t);
 int lstm_pack_weights(cudaStream_t, int, int, const float*, const float*, float*, int, int, float*, float*);
 int lstm_unpack_grads(cudaStream_t, int, int, float*, float*, const float*, int, int, const float*, const float*, int);
 int prepare_input(cudaStream_t, int, int, int, int, int, int, const float*, float*);
@@ -235,6 +237,12 @@ int e2e_lstm_rec_fwd(void* stream, int B, int T, int Tp, int H, int ndir, long l
                      int* err_flag) {
     return lstm_rec(ST(stream), false, B, T, Tp, H, ndir, sb, st, G, Hout, Cst, Wh, nullptr, lens, ctr_ws,
                     ctr_ws_bytes, err_flag);
+}
+int e2e_lstm_rec_fwd_carry(void* stream, int B, int T, int Tp, int H, long long sb, long long st, float* G, float* Hout,
+                           float* Cst, const float* Wh, const int* lens, void* ctr_ws, size_t ctr_ws_bytes,
+                           int* err_flag) {
+    (void)err_flag;
+    return lstm_rec_fwd_carry(ST(stream), B, T, Tp, H, sb, st, G, Hout, Cst, Wh, lens, ctr_ws, ctr_ws_bytes);
 }
 int e2e_lstm_rec_bwd(void* stream, int B, int T, int Tp, int H, int ndir, long long sb, long long st, float* G,
                      const float* Cst, const float* Wh, const float* dOut, const int* lens, void* ctr_ws,

@@ -241,7 +241,9 @@ __global__ void __launch_bounds__(NTH, 1) dec_fwd_persist_kernel(e2e_dec_persist
     __syncthreads();
 
     long long* dbg = (blockIdx.x == 0 && threadIdx.x == 0) ? d_dec_dbg : nullptr;
-    for (int t = 0; t < U; ++t) {
+    const int t_begin = p.t1 > 0 ? p.t0 : 0, t_end = p.t1 > 0 ? min(p.t1, U) : U;
+    for (int t = t_begin; t < t_end; ++t) {
+        const int rnd = t - t_begin;             // rounds of this launch (the row-block counters start at zero)
         DEC_STAMP(t, 0);
         // ------------------------------------------------------------ phase G
         for (int tile = blockIdx.x; tile < gtiles; tile += gridDim.x) {
@@ -249,7 +251,7 @@ __global__ void __launch_bounds__(NTH, 1) dec_fwd_persist_kernel(e2e_dec_persist
             if (!resident) { __syncthreads(); load_wt(cb); }
             // A tile: [ctx_{t-1} (D) | h_{t-1} (Hd)] for rows rb*16 .. +16: one bulk copy per row segment
             const int nvalid = min(16, B - rb * 16);
-            if (p2p && t > 0) tile_wait(pp.at(2, rb), (unsigned)(2 * nvalid * t), p.err);   // ctx_{t-1} of the block
+            if (p2p && rnd > 0) tile_wait(pp.at(2, rb), (unsigned)(2 * nvalid * rnd), p.err);   // ctx_{t-1} of the block
             if (tid == 0) mbar_expect_tx(&abar[2], (uint32_t)(nvalid * (Hd + (t > 0 ? D : 0)) * 4));
             __syncwarp();
             if (lane * 8 + w < 32) {
@@ -336,7 +338,7 @@ __global__ void __launch_bounds__(NTH, 1) dec_fwd_persist_kernel(e2e_dec_persist
                 const int rb = tile / (A / 8), nt = tile % (A / 8);
                 const int nvalid = min(16, B - rb * 16);
                 __syncthreads();
-                if (p2p) tile_wait(pp.at(0, rb), (unsigned)(NCB * (t + 1)), p.err);            // c_new of the block
+                if (p2p) tile_wait(pp.at(0, rb), (unsigned)(NCB * (rnd + 1)), p.err);            // c_new of the block
                 if (tid == 0) mbar_expect_tx(&abar[2], (uint32_t)(nvalid * Hd * 4));
                 __syncwarp();
                 if (lane * 8 + w < nvalid) {
@@ -406,13 +408,13 @@ __global__ void __launch_bounds__(NTH, 1) dec_fwd_persist_kernel(e2e_dec_persist
             // one bulk copy per enc row (dh floats), spread over the lanes of all warps
             // (a lane issues its copies serially, ~100 cycles each: slot = lane*8 + warp keeps that to a few per warp)
             for (int r = lane * 8 + w; r < c0; r += NTH) bulk_g2s(bufY + r * dh, encb + (size_t)r * D, (uint32_t)(dh * 4), &abar[1]);
-            if (t == 0) for (int a = tid; a < A; a += NTH) v_s[a] = p.attn_v[a];
-            if (p2p) tile_wait(pp.at(1, b / 16), (unsigned)((A / 8) * (t + 1)), p.err);        // y_t of the block
+            if (rnd == 0) for (int a = tid; a < A; a += NTH) v_s[a] = p.attn_v[a];
+            if (p2p) tile_wait(pp.at(1, b / 16), (unsigned)((A / 8) * (rnd + 1)), p.err);        // y_t of the block
             if (tid == 0) bulk_g2s(y_s, p.y + ((size_t)t * B + b) * A, (uint32_t)(A * 4), &abar[0]);
             DEC_STAMP(t, 8);
             mbar_wait_par(&abar[0], aph0);
             aph0 ^= 1u;
-            if (t == 0) __syncthreads();
+            if (rnd == 0) __syncthreads();
             DEC_STAMP(t, 9);
             // scores: 8 lanes per tau (4 taus per warp pass), lane covers float4 columns sub, sub+8, ...
             {
@@ -534,7 +536,7 @@ __global__ void __launch_bounds__(NTH, 1) dec_fwd_persist_kernel(e2e_dec_persist
                 const int b = item / 2, half = item % 2;
                 const int len = min(p.enc_len[b], Tn);
                 __syncthreads();
-                if (p2p) tile_wait(pp.at(1, b / 16), (unsigned)((A / 8) * (t + 1)), p.err);
+                if (p2p) tile_wait(pp.at(1, b / 16), (unsigned)((A / 8) * (rnd + 1)), p.err);
                 for (int a = tid; a < A; a += NTH) { y_s[a] = __ldcg(p.y + ((size_t)t * B + b) * A + a); v_s[a] = p.attn_v[a]; }
                 __syncthreads();
                 const float* HFb = p.HF + (size_t)b * Tp * A;

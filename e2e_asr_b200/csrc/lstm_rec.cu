@@ -366,7 +366,7 @@ int lstm_rec_cluster(cudaStream_t, bool, int, int, int, int, int, long long, lon
 int lstm_rec_mc(cudaStream_t, bool, int, int, int, int, int, long long, long long, float*, float*, float*,
                 const float*, const float*, const int*, void*, size_t);
 int lstm_rec_ws(cudaStream_t, bool, int, int, int, int, int, long long, long long, float*, float*, float*,
-                const float*, const float*, const int*, void*, size_t, int);
+                const float*, const float*, const int*, void*, size_t, int, int);
 extern int g_rec_mc_ns;
 // 0 = fastest eligible kernel (warp-specialised register-resident kernel for H in {128,256}, else the
 // cluster/DSMEM kernel, else the L2 kernel); 1 = always the L2 / global-barrier kernel; 2 = cluster/DSMEM or L2
@@ -376,6 +376,17 @@ extern int g_rec_mc_ns;
 // warp-specialised kernel with the fp16 split scheme in the backward pass too
 int g_rec_mode = 0;
 extern int g_rec_fwd_f16, g_rec_bwd_f16;
+
+// forward-only layer continuing a sequence (cell state carried in from Cst at time -1): the warp-specialised kernel only
+int lstm_rec_fwd_carry(cudaStream_t st, int B, int T, int Tp, int H, long long sb, long long stt, float* G, float* Hout,
+                       float* Cst, const float* Wh, const int* lens, void* ctr_ws, size_t ctr_ws_bytes) {
+    E2E_REQUIRE(H == 128 || H == 256, "lstm_rec_fwd_carry: hidden size %d (the carried-state entry serves 128 / 256)", H);
+    if (B <= 0 || T <= 0) return 0;
+    g_rec_fwd_f16 = 1;
+    int rc = lstm_rec_ws(st, false, B, T, Tp, H, 1, sb, stt, G, Hout, Cst, Wh, nullptr, lens, ctr_ws, ctr_ws_bytes, 0, 1);
+    E2E_REQUIRE(rc >= 0, "lstm_rec_fwd_carry: the cluster kernel is not available for these shapes");
+    return rc;
+}
 
 // workspace: ctr_ws must hold >= 4*ceil(B/4) unsigned + 1 int, zeroed by this function.
 int lstm_rec(cudaStream_t st, bool bwd, int B, int T, int Tp, int H, int ndir, long long sb, long long stt,
@@ -389,7 +400,7 @@ int lstm_rec(cudaStream_t st, bool bwd, int B, int T, int Tp, int H, int ndir, l
         g_rec_fwd_f16 = g_rec_mode != 7;
         g_rec_bwd_f16 = g_rec_mode == 8;
         int rc = lstm_rec_ws(st, bwd, B, T, Tp, H, ndir, sb, stt, G, Hout, Cst, Wh, dOut, lens, ctr_ws, ctr_ws_bytes,
-                             (g_rec_mode == 5 || g_rec_mode == 6) ? g_rec_mode - 4 : 0);
+                             (g_rec_mode == 5 || g_rec_mode == 6) ? g_rec_mode - 4 : 0, 0);
         if (rc >= 0) return rc;
     }
     if (g_rec_mode == 0 || g_rec_mode == 3 || g_rec_mode == 4) {

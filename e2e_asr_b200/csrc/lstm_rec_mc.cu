@@ -528,6 +528,7 @@ int lstm_rec_mc(cudaStream_t st, bool bwd, int B, int T, int Tp, int H, int ndir
     p.G = G; p.Hout = Hout; p.Cst = Cst; p.Wh = Wh; p.dOut = dOut; p.lens = lens; p.xg = nullptr;
     p.B = B; p.T = T; p.Tp = Tp; p.H = H; p.ndir = ndir; p.nslices = cdiv(B, R); p.sb = sb; p.st = stt;
     p.dbg = g_rec_dbg;
+    p.carry_c = 0;
     if (H == 128) return run_mc<8>(st, bwd, p, ws, ws_bytes, g_rec_mc_ns);
     return run_mc<16>(st, bwd, p, ws, ws_bytes, g_rec_mc_ns);
 }

@@ -205,6 +205,8 @@ __global__ void __launch_bounds__(256 + 32 * EW, 1) rec_fwd_ws_kernel(MParams p)
                 idx[sl][j] = (((long long)pb * p.sb + (long long)t0 * p.st) * ndir + dir) * H + unit;
                 gxn[sl][j] = make_float4(0.f, 0.f, 0.f, 0.f);
                 if (t0 < plen[sl][j]) gxn[sl][j] = reinterpret_cast<const float4*>(p.G)[idx[sl][j]];
+                // a continued sequence: c_{-1} from the row before the window (h_{-1} . Wh is already part of G_0)
+                if (p.carry_c && plen[sl][j] > 0) c_reg[sl][j] = p.Cst[idx[sl][j] - tstep];
             }
         uint32_t zph = 0;
         const bool rec = p.dbg != nullptr && blockIdx.x == 0 && e == 0;
@@ -705,10 +707,11 @@ extern long long* g_rec_dbg;
 // returns 0 = launched, -1 = not eligible (caller uses the other kernels), >0 = error
 int lstm_rec_ws(cudaStream_t st, bool bwd, int B, int T, int Tp, int H, int ndir, long long sb, long long stt,
                 float* G, float* Hout, float* Cst, const float* Wh, const float* dOut, const int* lens, void* ws,
-                size_t ws_bytes, int force_ns) {
+                size_t ws_bytes, int force_ns, int carry_c) {
     if (H != 128 && H != 256) return -1;
     if (B <= 0 || T <= 0) return 0;
     MParams p;
+    p.carry_c = (!bwd && ndir == 1) ? carry_c : 0;
     p.G = G; p.Hout = Hout; p.Cst = Cst; p.Wh = Wh; p.dOut = dOut; p.lens = lens; p.xg = nullptr;
     p.B = B; p.T = T; p.Tp = Tp; p.H = H; p.ndir = ndir; p.nslices = cdiv(B, R); p.sb = sb; p.st = stt;
     p.dbg = bwd ? nullptr : g_rec_dbg;

@@ -21,6 +21,7 @@ struct MParams {
     int nslices;          // 16-row batch slices per direction
     long long sb, st;
     long long* dbg;       // optional clock64 stamps of CTA 0 / thread 0: [step][slice][8]
+    int carry_c;          // forward, ndir = 1: the cell state entering step 0 is Cst at time -1 (a continued sequence)
 };
 
 constexpr int R = 16, UPC = 16, NTH = 256;

@@ -913,10 +913,11 @@ def _persist_fits(enc, dec_k, q_k, U):
     return bool(_lib.lib().e2e_decoder_persist_fits(ctypes.addressof(a)))
 
 
-def attn_decoder_apply(*args, lm_drop=None):
+def attn_decoder_apply(*args, lm_drop=None, samp=None):
     # args: enc, emb, attn_w, attn_v, lm_k, lm_b, dec_k, dec_b, q_k, ...
     if _DECODER_IMPL == "persist" and _persist_fits(args[0], args[6], args[8], args[21]):
-        return AttnDecoderFnV2.apply(*(args + (lm_drop,)))
+        return AttnDecoderFnV2.apply(*(args + (lm_drop, samp)))
+    assert samp is None, "in-pass scheduled sampling is served by the persistent decoder kernels"
     return AttnDecoderFn.apply(*(args + (lm_drop,)))
 
 
@@ -930,7 +931,7 @@ class AttnDecoderFnV2(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, enc, emb, attn_w, attn_v, lm_k, lm_b, dec_k, dec_b, q_k, q_b, ap_k, ap_b, out_k, out_b,
-                in_k, in_b, sp_k, sp_b, ids, lens_i32, enc_len_i32, U, stash, lm_drop=None):
+                in_k, in_b, sp_k, sp_b, ids, lens_i32, enc_len_i32, U, stash, lm_drop=None, samp=None):
         dev = enc.device
         st = _dev_state(dev)
         B, Tn, D = enc.shape
@@ -941,6 +942,10 @@ class AttnDecoderFnV2(torch.autograd.Function):
         assert r1 == 1, "encoder states must be batch-major"
         Tp = r0
         ids = ids[:U].contiguous()
+        if samp is not None:
+            return AttnDecoderFnV2._forward_sampled(ctx, enc, emb, attn_w, attn_v, lm_k, lm_b, dec_k, dec_b, q_k, q_b,
+                                                    ap_k, ap_b, out_k, out_b, in_k, in_b, sp_k, sp_b, ids, lens_i32,
+                                                    enc_len_i32, U, stash, lm_drop, samp)
         # The LM side of the decoder (embedding -> LM-LSTM -> InputProjection -> decoder-gate pre-activations) reads only
         # the teacher-forced ids and parameters: with the side streams on, it runs on the "dec" stream from the step's
         # start event, concurrently with the encoder, and the main stream joins it here.
@@ -995,19 +1000,110 @@ class AttnDecoderFnV2(torch.autograd.Function):
         proj = gemm(bufs["cat"], ap_k, bias=ap_b)
         logits = gemm(proj, out_k, bias=out_b)
         call("e2e_mask_rows", U, B, V, logits, lens_i32)
-        ctx.save_for_backward(enc, emb, attn_w, attn_v, lm_k, dec_k, q_k, q_b, ap_k, out_k, in_k, sp_k, ids,
-                              lens_i32, enc_len_i32, u, Wx_lm, Wh_lm, G_lm, hl, C_lm, m, pre, pre_g, W_ch, Wx_dec,
-                              HF, proj, bufs["cat"], bufs["hprev"], bufs["cprev"], bufs["acts"], bufs["y"],
-                              bufs["alpha"])
-        ctx.dims = (B, Tn, D, V, E, Hl, Hd, A, U, Tp)
+        AttnDecoderFnV2._save(ctx, (enc, emb, attn_w, attn_v, lm_k, dec_k, q_k, q_b, ap_k, out_k, in_k, sp_k, ids,
+                                    lens_i32, enc_len_i32, u, Wx_lm, Wh_lm, G_lm, hl, C_lm, m, pre, pre_g, W_ch, Wx_dec,
+                                    HF, proj, bufs["cat"], bufs["hprev"], bufs["cprev"], bufs["acts"], bufs["y"],
+                                    bufs["alpha"]),
+                              (B, Tn, D, V, E, Hl, Hd, A, U, Tp), stash,
+                              (emb, attn_w, attn_v, lm_k, lm_b, dec_k, dec_b, q_k, q_b, ap_k, ap_b, out_k, out_b,
+                               in_k, in_b, sp_k, sp_b), lm_drop, hl_out)
+        return logits
+
+    @staticmethod
+    def _save(ctx, tensors, dims, stash, params, lm_drop, hl_out):
+        ctx.save_for_backward(*tensors)
+        ctx.dims = dims
         ctx.stash = stash
         # flat-gradient-buffer views of the 17 parameters, in the order backward returns their gradients
-        ctx.grad_dst = tuple(None if t is None else getattr(t, "grad", None) for t in
-                             (emb, attn_w, attn_v, lm_k, lm_b, dec_k, dec_b, q_k, q_b, ap_k, ap_b, out_k, out_b,
-                              in_k, in_b, sp_k, sp_b))
-        ctx.has_sp = sp_k is not None
+        ctx.grad_dst = tuple(None if t is None else getattr(t, "grad", None) for t in params)
+        ctx.has_sp = params[15] is not None
         ctx.lm_drop = lm_drop
         ctx.hl_out = hl_out if lm_drop is not None else None
+
+    @staticmethod
+    def _forward_sampled(ctx, enc, emb, attn_w, attn_v, lm_k, lm_b, dec_k, dec_b, q_k, q_b, ap_k, ap_b, out_k, out_b,
+                         in_k, in_b, sp_k, sp_b, ids, lens_i32, enc_len_i32, U, stash, lm_drop, samp):
+        """Scheduled sampling (attn_decoder.py:130-139, decoder.py:155-180) INSIDE the training forward pass: the loop
+        is cut at the steps whose input is sampled.  Between two cuts the inputs are known, so the segment runs exactly
+        like the teacher-forced pass -- LM-LSTM over the segment (cell state carried in, h_{a-1} . Wh added to the first
+        pre-activations), the batched projections of its rows, the persistent decoder kernel over steps [a, b) -- and
+        at a cut the logits of step b-1 alone are formed and `e2e_sample_rows` draws ids[b] from them (the multinomial
+        over the unmasked previous logits).  Every buffer the backward pass reads is written once, by the segment that
+        owns the step: the backward pass is the ordinary one on the realised ids, and no second forward pass runs.
+        samp = (use_sample [U] bools, Philox key, stream offset)."""
+        dev = enc.device
+        st = _dev_state(dev)
+        B, Tn, D = enc.shape
+        V, E = emb.shape
+        Hl, Hd, A = lm_k.shape[1] // 4, dec_k.shape[1] // 4, q_k.shape[1]
+        f32 = dict(dtype=torch.float32, device=dev)
+        enc_flat, Tp, _ = flat_rows(enc)
+        use_sample, seed, offset = samp
+        ids = ids.clone()
+        u = torch.empty((U * B, E), **f32)
+        Wx_lm, Wh_lm, bp_lm = _pack_lstm([lm_k], [lm_b], E, Hl, dev)
+        G_lm = torch.empty((U * B, 4 * Hl), **f32)
+        hl = torch.zeros((U * B, Hl), **f32)
+        C_lm = torch.zeros((U * B, Hl), **f32)
+        hl_out = torch.empty_like(hl) if lm_drop is not None else hl
+        m = torch.empty((U * B, Hd), **f32) if sp_k is not None else hl_out
+        pre = torch.empty((U * B, E), **f32)
+        pre_g = torch.empty((U * B, 4 * Hd), **f32)
+        W_ch = torch.empty((D + Hd, 4 * Hd), **f32)
+        Wx_dec = torch.empty((E, 4 * Hd), **f32)
+        bp_dec = torch.empty((4 * Hd,), **f32)
+        call("e2e_lstm_pack_weights", E, Hd, dec_k, dec_b, Wx_dec, 4 * Hd, 0, W_ch[D:], bp_dec)
+        gemm(in_k[Hd:], Wx_dec, out=W_ch[:D])
+        HF = gemm(enc_flat, attn_w.view(D, A))
+        bufs = dict(cat=torch.empty((U * B, Hd + D), **f32), hprev=torch.zeros((U * B, Hd), **f32),
+                    cprev=torch.zeros((U * B, Hd), **f32), acts=torch.empty((U * B, 4 * Hd), **f32),
+                    y=torch.empty((U * B, A), **f32), alpha=torch.empty((U * B, Tn), **f32))
+        a_ = _lib.DecPersistArgs()
+        a_.B, a_.U, a_.Hd, a_.A, a_.D, a_.Tn, a_.Tp = B, U, Hd, A, D, Tn, Tp
+        for k, v in dict(W_ch=W_ch, pre_g=pre_g, q_k=q_k, q_b=q_b, attn_v=attn_v, HF=HF, enc=enc_flat,
+                         enc_len=enc_len_i32, lens=lens_i32, ctr=st["ctr"], err=st["err"], **bufs).items():
+            setattr(a_, k, v.data_ptr())
+        cuts = [t for t in range(1, U) if use_sample[t]] + [U]
+        a = 0
+        for b in cuts:
+            rows = slice(a * B, b * B)
+            call("e2e_embed_gather", (b - a) * B, E, emb, ids[a:b], u[rows])
+            gemm(u[rows], Wx_lm, bias=bp_lm, out=G_lm[rows])
+            lens_a = lens_i32
+            if a > 0:
+                gemm(hl[(a - 1) * B:a * B], Wh_lm[0], out=G_lm[a * B:(a + 1) * B], accumulate=True)
+                lens_a = (lens_i32 - a).clamp_(min=0)
+                call("e2e_lstm_rec_fwd_carry", B, b - a, b - a, Hl, 1, B, G_lm[rows], hl[rows], C_lm[rows], Wh_lm,
+                     lens_a, st["ctr"], st["ctr"].numel() * 4, st["err"], work=float(b - a), tag="lm_rec_fwd")
+            else:
+                call("e2e_lstm_rec_fwd", B, b, b, Hl, 1, 1, B, G_lm[rows], hl[rows], C_lm[rows], Wh_lm, lens_a,
+                     st["ctr"], st["ctr"].numel() * 4, st["err"], work=float(b), tag="lm_rec_fwd")
+            if lm_drop is not None:
+                call("e2e_dropout", (b - a) * B * Hl, hl[rows], hl_out[rows], float(lm_drop[0]), int(lm_drop[1]),
+                     int(lm_drop[2]), a * B * Hl, seed_dev(lm_drop[1]))
+            if sp_k is not None:
+                gemm(hl_out[rows], sp_k, bias=sp_b, out=m[rows])
+            gemm(m[rows], in_k[:Hd], bias=in_b, out=pre[rows])
+            gemm(pre[rows], Wx_dec, bias=bp_dec, out=pre_g[rows])
+            a_.t0, a_.t1 = a, b
+            call("e2e_decoder_persist_fwd", a_, work=float(b - a))
+            if b < U:           # ids[b] ~ multinomial(logits of step b-1), rows counted from b*B in the Philox stream
+                prj = gemm(bufs["cat"][(b - 1) * B:b * B], ap_k, bias=ap_b)
+                lg = gemm(prj, out_k, bias=out_b)
+                call("e2e_sample_rows", B, V, lg, V, int(seed), int(offset), b * B, ids[b])
+            a = b
+        proj = gemm(bufs["cat"], ap_k, bias=ap_b)
+        logits = gemm(proj, out_k, bias=out_b)
+        call("e2e_mask_rows", U, B, V, logits, lens_i32)
+        if stash is not None:
+            stash["realized_ids"] = ids
+        AttnDecoderFnV2._save(ctx, (enc, emb, attn_w, attn_v, lm_k, dec_k, q_k, q_b, ap_k, out_k, in_k, sp_k, ids,
+                                    lens_i32, enc_len_i32, u, Wx_lm, Wh_lm, G_lm, hl, C_lm, m, pre, pre_g, W_ch, Wx_dec,
+                                    HF, proj, bufs["cat"], bufs["hprev"], bufs["cprev"], bufs["acts"], bufs["y"],
+                                    bufs["alpha"]),
+                              (B, Tn, D, V, E, Hl, Hd, A, U, Tp), stash,
+                              (emb, attn_w, attn_v, lm_k, lm_b, dec_k, dec_b, q_k, q_b, ap_k, ap_b, out_k, out_b,
+                               in_k, in_b, sp_k, sp_b), lm_drop, hl_out)
         return logits
 
     @staticmethod
@@ -1113,9 +1209,9 @@ class AttnDecoderFnV2(torch.autograd.Function):
             for t_ in list(ctx.saved_tensors) + [dlogits, dproj, dz, dy, dv_part, dHF] + [g for g in grads if g is not None]:
                 if t_ is not None:
                     t_.record_stream(side)
-            return (denc_view,) + (None,) * 23
+            return (denc_view,) + (None,) * 24
         grads = param_grads(st["ctr"])
-        return (denc_view,) + tuple(grads) + (None, None, None, None, None, None)
+        return (denc_view,) + tuple(grads) + (None, None, None, None, None, None, None)
 
 
 # ---------------------------------------------------------------------------

@@ -118,6 +118,12 @@ int e2e_lstm_rec_fwd(void* stream, int B, int T, int Tp, int H, int ndir, long l
 int e2e_lstm_rec_bwd(void* stream, int B, int T, int Tp, int H, int ndir, long long sb, long long st,
                      float* G, const float* Cst, const float* Wh, const float* dOut, const int* lens,
                      void* ctr_ws, size_t ctr_ws_bytes, int* err_flag);
+/* e2e_lstm_rec_fwd for a forward-only layer (ndir = 1, H in {128, 256}) that CONTINUES a sequence: the cell state
+ * entering step 0 is Cst at time -1 (the row before the pointer passed in); the caller adds h_{-1} . Wh into the
+ * pre-activations G of step 0.  Lets the decoder's LM-LSTM run in segments (scheduled sampling). */
+int e2e_lstm_rec_fwd_carry(void* stream, int B, int T, int Tp, int H, long long sb, long long st,
+                           float* G, float* Hout, float* Cst, const float* Wh, const int* lens,
+                           void* ctr_ws, size_t ctr_ws_bytes, int* err_flag);
 
 /* Seq2SeqModel.get_batch frame stacking (seq2seq_model.py:164-183) + initial
  * striding (encoder.py:149-153) + zero padding to Tp rows per utterance. */
@@ -177,6 +183,8 @@ int e2e_decoder_loop_bwd(void* stream, const e2e_dec_loop_bwd_args* a);
  * Buffers marked (z) must be zero-initialised by the caller. */
 typedef struct {
     int B, U, Hd, A, D, Tn, Tp;
+    int t0, t1;            /* forward only: run steps [t0, t1) (t1 <= 0: all U); the state entering t0 is read from the
+                              step buffers (cat[t0-1], hprev[t0], cprev[t0]) a previous launch wrote */
     const float* W_ch;     /* [D+Hd, 4Hd] */
     const float* pre_g;    /* [U,B,4Hd] */
     const float* q_k;      /* [Hd, A] */
