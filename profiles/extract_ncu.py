@@ -41,8 +41,8 @@ def to_json(out_path, paths):
                      "msecond": 1e3, "ns": 1e-3, "nsecond": 1e-3, "s": 1e6, "second": 1e6}.get(u, 1.0)
             return v * scale
         for r in rows[2:]:
-            name = r[hdr.index("Kernel Name")].replace("(anonymous namespace)::", "").replace("<unnamed>::", "")
-            name = re.sub(r"<.*", "", re.sub(r"\(.*", "", name)).replace("e2e::", "").replace("void ", "").strip()
+            name = re.sub(r"\(.*", "", r[hdr.index("Kernel Name")]).replace("void ", "").strip()
+            name = re.sub(r"<[^<>]*>$", "", name).split("::")[-1]          # no template arguments, no namespaces
             if name in res:
                 continue
             rd, wr = val(r, "dram__bytes_read.sum"), val(r, "dram__bytes_write.sum")

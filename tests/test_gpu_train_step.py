@@ -193,14 +193,31 @@ def test_scheduled_sampling_matches_oracle(cname, keep):
     for step in range(3):
         model.run_step(batch)
         ops.check_device_errors("cuda:0")
-        ref = om.train_step(w, batch, num_layers={"char": cfg.L}, ctc_tasks=cfg.ctc, out_prob_dec=keep,
-                            dropout_seed=5 * 1000003 + step, samp_prob=0.5)
+        kw = dict(num_layers={"char": cfg.L}, ctc_tasks=cfg.ctc, out_prob_dec=keep, dropout_seed=5 * 1000003 + step)
+        ref = om.train_step(w, batch, samp_prob=0.5, **kw)
         ids = model.decoder["char"].stash["realized_ids"].cpu().numpy()
-        assert np.array_equal(ids, ref["realized_ids"]["char"])
+        ids_equal_up_to_bin_edges(ids, ref["realized_ids"]["char"])
         teacher = np.asarray(batch["char"]).T[:ids.shape[0]]
         sampled_any |= bool((ids != teacher).any())
+        if not np.array_equal(ids, ref["realized_ids"]["char"]):
+            ref = om.train_step(w, batch, forced_inputs={"char": ids}, **kw)      # the step on the ids realised here
         compare_step(model, ref, rtol=RTOL)
     assert sampled_any          # the rule really replaced ground-truth inputs
+
+
+def ids_equal_up_to_bin_edges(ids, ref_ids):
+    """The multinomial draw is an inverse-CDF lookup (first index whose cumulative mass exceeds u * total): logits that
+    differ in the 6th digit move a draw that falls within that distance of a bin edge to the ADJACENT id (with V = 1000
+    near-uniform classes about one draw in a hundred).  From there on that utterance is fed another embedding and its
+    later draws are no longer comparable.  So: per utterance the realised ids must be identical up to the first
+    difference, and that first difference must be an adjacent id.  (The step itself is then checked against the oracle
+    run on the ids realised here.)"""
+    assert ids.shape == ref_ids.shape
+    for b in range(ids.shape[1]):
+        d = np.flatnonzero(ids[:, b] != ref_ids[:, b])
+        if len(d):
+            t = int(d[0])
+            assert abs(int(ids[t, b]) - int(ref_ids[t, b])) == 1, (b, t, ids[t, b], ref_ids[t, b])
 
 
 def test_sample_rows_kernel_matches_oracle():
