@@ -338,6 +338,8 @@ def roofline_report(raw, cfg, peaks, K, ms_per_step, clocks, gemm_mode):
                 "frac": d["frac_of_tensor_peak"],
                 "traffic": (traffic.get(d["kernel"].split("<")[0]) or {}).get("dram_bytes_per_launch"),
                 "traffic_source": (traffic.get(d["kernel"].split("<")[0]) or {}).get("source"),
+                "traffic_note": "dram__bytes_read + dram__bytes_write of the FIRST launch ncu captured (one encoder layer: the "
+                                "launches of a step differ in T_l; profiles/r2_ncu_full_summary.txt), not of the average launch",
                 "peak_source": peaks["source"] + ", sustained bf16 (the kernel sits inside a long step)",
                 "algorithmic_gflop_per_launch": flop_per_step[name] * v["work"] / launches / 1e9,
                 "avg_launch_ms": v["ms"] / launches, "launches_per_step": launches / K,
@@ -531,7 +533,8 @@ def main():
         ms, host_busy_ms, n_tail, clocks, _ = timed_loop(gs.step, False)
         launches = n_tail + gs.launches_per_step * K         # kernels in the replayed graph + the eager tail
         step_host = lambda: gs.step(batch)
-        mode = "CUDA graph replay of fwd+bwd (%d kernels) + eager all-reduce/clip" % gs.launches_per_step
+        mode = ("CUDA graph replay of fwd+bwd%s (%d kernels) + eager clip"
+                % (" + gradient all-reduce spans" if world > 1 else "", gs.launches_per_step))
     loss_val = float(model.total_loss)
     total_frames = sum_over_ranks(frames)
     value = total_frames * K / (ms * 1e-3)
@@ -645,8 +648,8 @@ def beam_decode_rate(cfg_name, dev, n_utts=256, beam=10, cpu=True):
            "mean_output_len": float(np.mean([len(o) for o in out])), "ms_per_decoding_step": dt * 1e3 / steps,
            "fp64_gemm_tflops": flop_row * n_utts * beam * steps / dt / 1e12,
            "note": "random-init weights: hypotheses run to the 120-step limit (worst case); wall clock of decode_batch: "
-                   "float64 decoder step on all 2560 hypothesis slots + device-side k^2 candidate merge, one CUDA-graph "
-                   "replay per decoding step, sequences rebuilt from back-pointers on the host at the end"}
+                   "float64 decoder step on all 2560 hypothesis slots + device-side k^2 candidate merge (no host work "
+                   "per step but the launches), sequences rebuilt from back-pointers on the host at the end"}
     gold = os.path.join(ROOT, "tests", "golden", "fullsize_beam.npz")
     if os.path.exists(gold) and n_utts == 256 and beam == 10 and cfg_name == "cfg2":
         g = np.load(gold)

@@ -281,12 +281,18 @@ class Seq2SeqModel(BaseParams):
                         side.wait_stream(main)
                     with torch.cuda.stream(side):
                         d = params.num_layers[task]
-                        D = self.time_major_states[d].shape[2]
+                        # the encoder keeps the time-major view for tasks named "state" / "*_ctc" (encoder.py:143-144);
+                        # any other CTC task name finds its layer among the batch-major attention states (the head
+                        # takes either layout)
+                        states_d = self.time_major_states.get(d)
+                        if states_d is None:
+                            states_d = self.encoder_hidden_states[d]
+                        D = states_d.shape[2]
                         k = self.variables.get("model/ctc_%s/kernel" % task, (D, vocab + 1))
                         b = self.variables.get("model/ctc_%s/bias" % task, (vocab + 1,), ("zeros",))
                         self.ctc_stash[task] = {"consumer_stream": main}
                         self.losses[task] = LossUtils.ctc_head_loss(
-                            self.time_major_states[d], k, b, self.seq_len_encs[d], self.decoder_inputs[task],
+                            states_d, k, b, self.seq_len_encs[d], self.decoder_inputs[task],
                             self.seq_len_target[task], self.ctc_stash[task],
                             max_label_len=self.decoder_inputs[task].shape[1] if self.shape_bounds else None)
 

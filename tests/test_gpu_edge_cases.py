@@ -175,3 +175,16 @@ def test_one_captured_step_serves_a_length_bucket():
     too_long = crafted_batch(cfg, [38, 30, 21, 37, 12], [9, 4, 9, 2, 6], seed=4)
     with pytest.raises(ValueError, match="does not fit"):
         step(too_long)
+
+
+def test_ctc_head_with_a_task_name_the_encoder_does_not_keep_time_major():
+    """The reference's encoder keeps the time-major view only for tasks named "state" (encoder.py:143-144; here also
+    "*_ctc"); an auxiliary CTC head under any other task name reads its layer from the batch-major attention states."""
+    cfg = synth.get_config("tiny_b", ctc={"phone": (3, 6), "state": (2, 9)})
+    w = synth.make_weights(cfg, bias_noise=0.1)
+    batch = synth.make_batch(cfg)
+    ref = om.train_step(w, batch, num_layers={"char": cfg.L}, ctc_tasks=cfg.ctc)
+    model = build_model(cfg, w, device="cuda:0")
+    model.run_step(batch)
+    ops.check_device_errors("cuda:0")
+    compare_step(model, ref, rtol=1e-4)
