@@ -136,6 +136,8 @@ def lib():
         l.e2e_set_dec_sync.argtypes = [ctypes.c_int]
         l.e2e_ctc_workspace_floats.restype = ctypes.c_size_t
         l.e2e_ctc_workspace_floats.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_int]
+        l.e2e_lstm_rec_workspace_bytes.restype = ctypes.c_size_t
+        l.e2e_lstm_rec_workspace_bytes.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_int]
         l.e2e_set_tc_debug.restype = ctypes.c_int
         l.e2e_set_tc_debug.argtypes = [ctypes.c_void_p, ctypes.c_longlong]
         _lib = l
@@ -144,7 +146,7 @@ def lib():
 
 def exported_symbols():
     return sorted(list(_SIGS.keys()) + ["e2e_last_error", "e2e_version", "e2e_sm_count", "e2e_launch_count", "e2e_capture_status",
-                   "e2e_set_workspace", "e2e_set_dec_sync", "e2e_ctc_workspace_floats", "e2e_decoder_persist_fits", "e2e_set_tc_debug", "e2e_set_rec_mode", "e2e_set_rec_debug", "e2e_set_stream_workspace"])
+                   "e2e_set_workspace", "e2e_set_dec_sync", "e2e_ctc_workspace_floats", "e2e_lstm_rec_workspace_bytes", "e2e_decoder_persist_fits", "e2e_set_tc_debug", "e2e_set_rec_mode", "e2e_set_rec_debug", "e2e_set_stream_workspace"])
 
 
 def _ptr(x):

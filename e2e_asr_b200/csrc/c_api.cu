@@ -44,6 +44,7 @@ void set_tc_debug(float*, long long);
 int colsum(cudaStream_t, int, int, const float*, int, float*, int);
 int lstm_rec(cudaStream_t, bool, int, int, int, int, int, long long, long long, float*, float*, float*,
              const float*, const float*, const int*, void*, size_t, int*);
+size_t lstm_rec_h512_workspace(int B, int ndir, bool bwd);
 int lstm_rec_fwd_carry(cudaStream_t, int, int, int, int, long long, long long, float*, float*, float*, const float*,
                        const int*, void*, size_t);
 int lstm_pack_weights(cudaStream_t, int, int, const float*, const float*, float*, int, int, float*, float*);
@@ -237,6 +238,16 @@ int e2e_lstm_rec_fwd(void* stream, int B, int T, int Tp, int H, int ndir, long l
                      int* err_flag) {
     return lstm_rec(ST(stream), false, B, T, Tp, H, ndir, sb, st, G, Hout, Cst, Wh, nullptr, lens, ctr_ws,
                     ctr_ws_bytes, err_flag);
+}
+size_t e2e_lstm_rec_workspace_bytes(int B, int H, int ndir) {
+    size_t need = (size_t)4 * ndir * ((B + 3) / 4);
+    const size_t tiles = (size_t)4096 * ndir * 16 * ((B + 15) / 16);
+    if (tiles > need) need = tiles;
+    if (H == 512) {
+        const size_t wide = lstm_rec_h512_workspace(B, ndir, true);
+        if (wide > need) need = wide;
+    }
+    return need;
 }
 int e2e_lstm_rec_fwd_carry(void* stream, int B, int T, int Tp, int H, long long sb, long long st, float* G, float* Hout,
                            float* Cst, const float* Wh, const int* lens, void* ctr_ws, size_t ctr_ws_bytes,

@@ -367,9 +367,11 @@ int lstm_rec_mc(cudaStream_t, bool, int, int, int, int, int, long long, long lon
                 const float*, const float*, const int*, void*, size_t);
 int lstm_rec_ws(cudaStream_t, bool, int, int, int, int, int, long long, long long, float*, float*, float*,
                 const float*, const float*, const int*, void*, size_t, int, int);
+int lstm_rec_h512(cudaStream_t, bool, int, int, int, int, int, long long, long long, float*, float*, float*,
+                  const float*, const float*, const int*, void*, size_t);
 extern int g_rec_mc_ns;
-// 0 = fastest eligible kernel (warp-specialised register-resident kernel for H in {128,256}, else the
-// cluster/DSMEM kernel, else the L2 kernel); 1 = always the L2 / global-barrier kernel; 2 = cluster/DSMEM or L2
+// 0 = fastest eligible kernel (warp-specialised register-resident kernel for H in {128,256}, the H = 512 kernel of
+// lstm_rec_h512.cu when the workspace is large enough, else the cluster/DSMEM kernel, else the L2 kernel); 1 = always the L2 / global-barrier kernel; 2 = cluster/DSMEM or L2
 // kernel only; 3 / 4 = the non-specialised register-resident kernel (lstm_rec_mc.cu) with 1 / 2 interleaved
 // batch slices per cluster; 5 / 6 = the warp-specialised kernel with 1 / 2 slices forced (tests); 7 = the
 // warp-specialised kernel with the forward pass on the tf32 + bf16 scheme instead of the fp16 split scheme; 8 = the
@@ -401,6 +403,10 @@ int lstm_rec(cudaStream_t st, bool bwd, int B, int T, int Tp, int H, int ndir, l
         g_rec_bwd_f16 = g_rec_mode == 8;
         int rc = lstm_rec_ws(st, bwd, B, T, Tp, H, ndir, sb, stt, G, Hout, Cst, Wh, dOut, lens, ctr_ws, ctr_ws_bytes,
                              (g_rec_mode == 5 || g_rec_mode == 6) ? g_rec_mode - 4 : 0, 0);
+        if (rc >= 0) return rc;
+    }
+    if (g_rec_mode == 0) {
+        int rc = lstm_rec_h512(st, bwd, B, T, Tp, H, ndir, sb, stt, G, Hout, Cst, Wh, dOut, lens, ctr_ws, ctr_ws_bytes);
         if (rc >= 0) return rc;
     }
     if (g_rec_mode == 0 || g_rec_mode == 3 || g_rec_mode == 4) {

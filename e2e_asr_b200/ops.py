@@ -68,6 +68,19 @@ def _dev_state(device):
     return _state[key]
 
 
+def _rec_workspace(st, B, H, nd):
+    """Scratch of the recurrence kernels: the shared 4 MB buffer, or -- the H = 512 kernels reduce-scatter their partial
+    d h tiles through L2, 64 KB per CTA -- a dedicated buffer grown to e2e_lstm_rec_workspace_bytes."""
+    from ._lib import lib
+    need = int(lib().e2e_lstm_rec_workspace_bytes(B, H, nd))
+    if need <= st["ctr"].numel() * 4:
+        return st["ctr"]
+    big = st.get("ctr_wide")
+    if big is None or big.numel() * 4 < need:
+        big = st["ctr_wide"] = torch.zeros((need + 3) // 4, dtype=torch.int32, device=st["ctr"].device)
+    return big
+
+
 def check_device_errors(device):
     """Raises if a persistent-kernel step barrier ever timed out (host sync)."""
     st = _dev_state(device)
@@ -394,8 +407,9 @@ class BiLSTMLayerFn(torch.autograd.Function):
         G = gemm(x2, Wx, bias=bp, a_lo=x_lo, b_lo=Wx_lo)            # [B*Tp, nd*4H]
         out = torch.zeros((B, Tp, nd * H), dtype=torch.float32, device=dev)
         Cst = torch.empty((B, Tp, nd, H), dtype=torch.float32, device=dev)
-        call("e2e_lstm_rec_fwd", B, T, Tp, H, nd, Tp, 1, G, out, Cst, Wh, lens_i32, st["ctr"],
-             st["ctr"].numel() * 4, st["err"], work=float(T), tag="enc_rec_fwd")
+        ws = _rec_workspace(st, B, H, nd)
+        call("e2e_lstm_rec_fwd", B, T, Tp, H, nd, Tp, 1, G, out, Cst, Wh, lens_i32, ws,
+             ws.numel() * 4, st["err"], work=float(T), tag="enc_rec_fwd")
         ctx.save_for_backward(x, Wx, Wh, G, Cst, out, lens_i32)
         ctx.los = (x_lo, Wx_lo)
         ctx.dims = (B, Tp, I, H, T, nd)
@@ -410,8 +424,9 @@ class BiLSTMLayerFn(torch.autograd.Function):
         dev = x.device
         st = _dev_state(dev)
         dout = dout.contiguous()
-        call("e2e_lstm_rec_bwd", B, T, Tp, H, nd, Tp, 1, G, Cst, Wh, dout, lens_i32, st["ctr"],
-             st["ctr"].numel() * 4, st["err"], work=float(T), tag="enc_rec_bwd")   # G now holds d(pre-activations)
+        ws = _rec_workspace(st, B, H, nd)
+        call("e2e_lstm_rec_bwd", B, T, Tp, H, nd, Tp, 1, G, Cst, Wh, dout, lens_i32, ws,
+             ws.numel() * 4, st["err"], work=float(T), tag="enc_rec_bwd")   # G now holds d(pre-activations)
         N = B * Tp
         x2, o2 = x.view(N, I), out.view(N, nd * H)
         x_lo, Wx_lo = ctx.los

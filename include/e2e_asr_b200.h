@@ -98,10 +98,12 @@ int e2e_lstm_unpack_grads(void* stream, int I, int H, float* dkernel, float* dbi
  * Row (b,t) of every [.,.,x] buffer is b*sb + t*st.  G [rows][ndir][H][4]: in =
  * x-projection+bias, out = gate activations (fwd) / d pre-activations (bwd).
  * Hout [rows][ndir*H] must be zero-initialised (rows with t >= len stay 0).
- * ctr_ws: >= max(4*ndir*ceil(B/4), 4096*ndir*16*ceil(B/16)) bytes of scratch; err_flag: device int set to 1 if a
+ * ctr_ws: >= e2e_lstm_rec_workspace_bytes(B, H, ndir) bytes of scratch (exchange tiles of the cluster kernels; with
+ * less, a slower kernel that needs only 4*ndir*ceil(B/4) bytes serves the call); err_flag: device int set to 1 if a
  * step barrier ever times out. */
 /* 0 (default): fastest eligible kernel -- the warp-specialised register-resident multicast-cluster
- * recurrence for H in {128, 256} (needs ctr_ws >= 512 KB), else the cluster / DSMEM recurrence when H/16
+ * recurrence for H in {128, 256}, its H = 512 form (W_hh hi plane in registers, lo plane in shared memory; 64 KB of
+ * workspace per CTA for the backward reduce-scatter), else the cluster / DSMEM recurrence when H/16
  * is 1,2,4,8 or 16, else the L2-exchange kernel with per-group global counters;
  * 1: always the L2-exchange kernel; 2: cluster / DSMEM or L2 kernel only;
  * 3 / 4: non-specialised register-resident kernel with 1 / 2 interleaved batch slices per cluster;
@@ -112,6 +114,7 @@ int e2e_set_rec_debug(long long* dbg);
 /* test hook: 1 (default) = the persistent decoder kernels synchronise per 16-row block with point-to-point counters,
  * 0 = three grid-wide barriers per step */
 int e2e_set_dec_sync(int p2p);
+size_t e2e_lstm_rec_workspace_bytes(int B, int H, int ndir);
 int e2e_lstm_rec_fwd(void* stream, int B, int T, int Tp, int H, int ndir, long long sb, long long st,
                      float* G, float* Hout, float* Cst, const float* Wh, const int* lens,
                      void* ctr_ws, size_t ctr_ws_bytes, int* err_flag);
