@@ -492,12 +492,64 @@ split_rows_f16_reg_kernel(size_t rows, int cols, const float* __restrict__ x, in
         }
     }
 }
+// Wide rows (cols <= ITER * 2048): one CTA per row, 8 * ITER columns per thread in registers, amax through shared memory.
+template <int ITER>
+__global__ void __launch_bounds__(256)
+split_rows_f16_cta_kernel(size_t rows, int cols, const float* __restrict__ x, int ldx, __half* __restrict__ hi,
+                          __half* __restrict__ lo, int ldo, float* __restrict__ row_inv) {
+    __shared__ float wmax[8];
+    const size_t r = blockIdx.x;
+    const float* xr = x + r * ldx;
+    float v[ITER][8];
+    float amax = 0.f;
+#pragma unroll
+    for (int it = 0; it < ITER; ++it) {
+        const int c = (threadIdx.x + it * 256) * 8;
+        float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a;
+        if (c < cols) {
+            a = __ldg(reinterpret_cast<const float4*>(xr + c));
+            b = __ldg(reinterpret_cast<const float4*>(xr + c + 4));
+        }
+        v[it][0] = a.x; v[it][1] = a.y; v[it][2] = a.z; v[it][3] = a.w;
+        v[it][4] = b.x; v[it][5] = b.y; v[it][6] = b.z; v[it][7] = b.w;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) amax = fmaxf(amax, fabsf(v[it][j]));
+    }
+    amax = warp_max(amax);
+    if (threadIdx.x % 32 == 0) wmax[threadIdx.x / 32] = amax;
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < 8; ++i) amax = fmaxf(amax, wmax[i]);
+    float s = 1.0f;
+    if (amax >= 1.17549435e-38f && amax < 3.0e38f) {
+        const int e = (int)((__float_as_uint(amax) >> 23) & 0xFF) - 127;
+        const int se = min(max(13 - e, -126), 126);
+        s = __uint_as_float((uint32_t)(se + 127) << 23);
+    }
+    if (threadIdx.x == 0) row_inv[r] = 1.0f / s;
+#pragma unroll
+    for (int it = 0; it < ITER; ++it) {
+        const int c = (threadIdx.x + it * 256) * 8;
+        if (c < ldo) {
+            __align__(16) __half h[8], l[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) f16_parts(v[it][j] * s, h[j], l[j]);
+            *reinterpret_cast<uint4*>(hi + r * ldo + c) = *reinterpret_cast<const uint4*>(h);
+            *reinterpret_cast<uint4*>(lo + r * ldo + c) = *reinterpret_cast<const uint4*>(l);
+        }
+    }
+}
 // dispatch: register-resident rows when they fit, else the two-pass kernel
 static void launch_split_rows_f16(cudaStream_t st, size_t rows, int cols, const float* x, int ldx, __half* hi, __half* lo,
                                   int ldo, float* row_inv) {
-    const bool vec = cols % 8 == 0 && ldx % 4 == 0 && ((uintptr_t)x & 15) == 0 && ldo <= 2048;
+    const bool al = cols % 8 == 0 && ldx % 4 == 0 && ((uintptr_t)x & 15) == 0;
+    const bool vec = al && ldo <= 2048;
     const unsigned grid = (unsigned)cdiv(rows, 8);
-    if (vec && ldo <= 1024)
+    if (al && ldo > 2048 && ldo <= 4096)
+        split_rows_f16_cta_kernel<2><<<(unsigned)rows, 256, 0, st>>>(rows, cols, x, ldx, hi, lo, ldo, row_inv);
+    else if (al && ldo > 4096 && ldo <= 8192)
+        split_rows_f16_cta_kernel<4><<<(unsigned)rows, 256, 0, st>>>(rows, cols, x, ldx, hi, lo, ldo, row_inv);
+    else if (vec && ldo <= 1024)
         split_rows_f16_reg_kernel<4><<<grid, 256, 0, st>>>(rows, cols, x, ldx, hi, lo, ldo, row_inv);
     else if (vec)
         split_rows_f16_reg_kernel<8><<<grid, 256, 0, st>>>(rows, cols, x, ldx, hi, lo, ldo, row_inv);

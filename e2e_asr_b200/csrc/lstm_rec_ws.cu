@@ -327,6 +327,10 @@ __global__ void __launch_bounds__(256 + 32 * EW, 1) rec_bwd_ws_kernel(MParams p)
     float* dz_s = stage + NS * 2 * CS * TILE;                    // [NS][2][8 k-tiles][32 chunks][4] own dz, fragment order
     __shared__ __align__(8) uint64_t full[NS][2];                // the CS partial tiles of a step have arrived
     __shared__ __align__(8) uint64_t dzready[NS];                // the 4 epilogue warps have written dz_t
+    // the 8 MMA warps have seen dz_t: an epilogue warp signals dz_{t+1} only then.  Its step t+1 needs just ONE partial tile
+    // from every CTA (the warp that owns this CTA as a destination), so without this hand-shake dzready could complete two
+    // phases while a slow MMA warp (weight set-up at kernel start) has not yet tested the first -- parity aliasing
+    __shared__ __align__(8) uint64_t dzseen[NS];
     __shared__ float rinv_s[NS][2][R];                           // F16: 1 / (row scale) of the dz tile of (slice, buffer)
 
     const int ndir = p.ndir, T = p.T, Tp = p.Tp;
@@ -343,6 +347,7 @@ __global__ void __launch_bounds__(256 + 32 * EW, 1) rec_bwd_ws_kernel(MParams p)
             mbar_init(&full[sl][0], 1);
             mbar_init(&full[sl][1], 1);
             mbar_init(&dzready[sl], EW);
+            mbar_init(&dzseen[sl], 8);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 #pragma unroll
@@ -427,6 +432,7 @@ __global__ void __launch_bounds__(256 + 32 * EW, 1) rec_bwd_ws_kernel(MParams p)
                     for (int q = 0; q < 4; ++q) { acc[nt][q] = 0.f; accx[nt][q] = 0.f; }
                 mbar_wait(&dzready[sl], (dph >> sl) & 1u);
                 dph ^= 1u << sl;
+                if (lane == 0) mbar_arrive(&dzseen[sl]);
                 const float* dzs = dz_s + (size_t)(sl * 2 + buf) * 8 * 128;
                 if (F16) {
                     // [hi fragments of the 4 k16 pairs: 4 x 512 B | lo' fragments], already in register order
@@ -602,7 +608,10 @@ __global__ void __launch_bounds__(256 + 32 * EW, 1) rec_bwd_ws_kernel(MParams p)
                         }
                     }
                     __syncwarp();
-                    if (lane == 0) mbar_arrive(&dzready[sl]);
+                    if (lane == 0) {
+                        if (s > 0) mbar_wait(&dzseen[sl], (uint32_t)((s - 1) & 1));     // the MMA warps have taken dz_{s-1}
+                        mbar_arrive(&dzready[sl]);
+                    }
                 } else if (s + 1 < T) {
                     // own dz tile in fragment order [k-tile = ul/2][16-byte chunk (r0*4 + gate) ^ k-tile][2 (ul%2) + row/8]:
                     // the thread's two rows are the adjacent floats of one slot pair
@@ -620,7 +629,10 @@ __global__ void __launch_bounds__(256 + 32 * EW, 1) rec_bwd_ws_kernel(MParams p)
                         dq[((c0 + 3) ^ kx) * 4] = dz[0].w;
                     }
                     __syncwarp();
-                    if (lane == 0) mbar_arrive(&dzready[sl]);
+                    if (lane == 0) {
+                        if (s > 0) mbar_wait(&dzseen[sl], (uint32_t)((s - 1) & 1));     // the MMA warps have taken dz_{s-1}
+                        mbar_arrive(&dzready[sl]);
+                    }
                 }
 #pragma unroll
                 for (int j = 0; j < NR; ++j) {

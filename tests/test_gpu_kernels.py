@@ -237,13 +237,15 @@ def test_gemm_shared_operand_split(mode):
         ops.set_gemm_mode("fp32")
 
 
-def test_gemm_f16x2_rows_of_very_different_magnitude():
+@pytest.mark.parametrize("K", [1024, 4096, 5000])
+def test_gemm_f16x2_rows_of_very_different_magnitude(K):
     """Mode 4 scales every row of the A operand by its own power of two before the fp16 split (gradients of different
     utterances differ by many orders of magnitude) and scales the output row back: every ROW must be accurate
     relative to ITS OWN magnitude, for the GEMM's own pre-pass and for caller-held planes (e2e_split_rows_f16), and
-    the shared B planes of e2e_split_lo(4) must give the same result."""
+    the shared B planes of e2e_split_lo(4) must give the same result.  K = 1024: one warp per row with the row in
+    registers; 4096 / 5000: one CTA per row (the d z rows of the H = 512 encoder)."""
     rng = np.random.default_rng(11)
-    M, N, K = 700, 512, 1024
+    M, N = 700, 512
     scale = 10.0 ** rng.uniform(-12, 2, size=(M, 1))
     a = (rng.standard_normal((M, K)) * scale).astype(np.float32)
     a[5] = 0.0
@@ -259,7 +261,8 @@ def test_gemm_f16x2_rows_of_very_different_magnitude():
         err = np.abs(out.cpu().numpy().astype(np.float64) - ref) / row_mag
         assert err.max() < 2e-6, err.max()
         assert float(out[5].abs().max()) == 0.0
-    assert float((outs[0] - outs[1]).abs().max()) == 0.0                  # same planes, same arithmetic
+    if K == 1024:     # same planes, same arithmetic (larger K with this few tiles runs split-K: atomics reorder the sum)
+        assert float((outs[0] - outs[1]).abs().max()) == 0.0
 
 
 @pytest.mark.parametrize("mode,tol", [(1, 2e-5), (2, 2e-2), (3, 3e-5), (4, 5e-6)])
