@@ -636,20 +636,29 @@ def beam_decode_rate(cfg_name, dev, n_utts=256, beam=10, cpu=True):
     sp.beam_size = beam
     bs = BeamSearch(w, sp, device=dev)
     bs.decode_batch(encs[:8])
-    torch.cuda.synchronize()
-    t0 = time.perf_counter()
-    out = bs.decode_batch(encs)
-    torch.cuda.synchronize()
-    dt = time.perf_counter() - t0
+    # first call of this batch shape: launched kernel by kernel; second: captures the decoding step in a CUDA graph
+    # (decode_batch keeps the buffers and the graph of a batch signature); from the third on it replays -- the steady
+    # state of an evaluation loop over equally shaped batches, which is what `value` reports
+    times = []
+    for _ in range(4):
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        out = bs.decode_batch(encs)
+        torch.cuda.synchronize()
+        times.append(time.perf_counter() - t0)
+    dt = min(times[2:])
     steps = max(len(o) for o in out)
     Hd, Hl, D, E, A, V = cfg.Hd, cfg.Hl, 2 * cfg.H, cfg.E, cfg.A, cfg.V
     flop_row = 2.0 * ((E + Hl) * 4 * Hl + (Hd + D) * E + (E + Hd) * 4 * Hd + Hd * A + (Hd + D) * Hd + Hd * V)
     res = {"value": n_utts / dt, "unit": "utt/s", "beam_size": beam, "n_utts": n_utts,
            "mean_output_len": float(np.mean([len(o) for o in out])), "ms_per_decoding_step": dt * 1e3 / steps,
            "fp64_gemm_tflops": flop_row * n_utts * beam * steps / dt / 1e12,
+           "first_call_utt_s": n_utts / times[0], "capture_call_utt_s": n_utts / times[1],
            "note": "random-init weights: hypotheses run to the 120-step limit (worst case); wall clock of decode_batch: "
-                   "float64 decoder step on all 2560 hypothesis slots + device-side k^2 candidate merge (no host work "
-                   "per step but the launches), sequences rebuilt from back-pointers on the host at the end"}
+                   "float64 decoder step on all 2560 hypothesis slots + device-side k^2 candidate merge, one CUDA-graph replay "
+                   "per decoding step (value = steady state with the step graph cached; first_call_utt_s = kernel by "
+                   "kernel, capture_call_utt_s = the call that captures), the best sequence per utterance rebuilt from "
+                   "back-pointers on the host at the end"}
     gold = os.path.join(ROOT, "tests", "golden", "fullsize_beam.npz")
     if os.path.exists(gold) and n_utts == 256 and beam == 10 and cfg_name == "cfg2":
         g = np.load(gold)

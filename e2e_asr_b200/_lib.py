@@ -59,6 +59,7 @@ _SIGS = {
     "e2e_gemm_f64": "piiipipipip",
     "e2e_lstm_step_f64": "piippppi",
     "e2e_attn_beam_f64": "piiiipppppppi",
+    "e2e_attn_beam_group_f64": "piiiiipppppppi",
     "e2e_logsoftmax_topk_f64": "piippdpippp",
     "e2e_embed_gather_f64": "piipppi",
     "e2e_beam_merge": "pp",
@@ -77,7 +78,7 @@ class DecLoopFwdArgs(ctypes.Structure):
 
 class DecLoopBwdArgs(ctypes.Structure):
     _fields_ = [("f", DecLoopFwdArgs)] + [(n, ctypes.c_void_p) for n in (
-        "dcat", "dgates", "dxh", "dy", "dv_part", "dHF", "denc", "dc_carry")]
+        "dcat", "dgates", "dxh", "dy", "dv_part", "dHF", "denc", "dc_carry", "ds")]
 
 
 class DecPersistArgs(ctypes.Structure):

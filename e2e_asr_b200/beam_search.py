@@ -163,69 +163,53 @@ class BeamSearch(BaseParams):
         call("e2e_gemm_f64", a.shape[0], w.shape[1], a.shape[1], a, a.stride(0), w, w.stride(0), out, out.stride(0), b)
         return out
 
-    def decode_batch(self, enc_list, return_scores=False, use_graph=None):
-        """Decode a list of utterances ([T_i, D] arrays) together; returns a list of id arrays.
-
-        Every utterance owns `beam` fixed hypothesis slots (rows u*beam .. u*beam+beam-1 of every state matrix, live
-        ones first), so one decoding step is a fixed sequence of launches on fixed shapes -- the float64 decoder step
-        on all rows, the per-row top-k, the candidate merge per utterance (`e2e_beam_merge`: k*k candidates ->
-        np.argpartition's top-k set, EOS retirement, back-pointers) and the back-pointer gather of the states.  The
-        host only enqueues, polls the number of live hypotheses every few steps and rebuilds the token sequences from
-        the back-pointers at the end.  use_graph=True captures the step in a CUDA graph after step 0 and replays it
-        for steps 1..119; capturing costs ~70 ms per call, which a single 120-step decode does not win back
-        (measured, 256 utterances x beam 10: 282 ms with the graph, 215 ms launched kernel by kernel, 135 ms of which is
-        kernel time), so it is off unless asked for."""
-        import ctypes
+    def _plan(self, N, beam, rows_b, Tmax_b, D):
+        """Device buffers, the step function and (once captured) the CUDA graph of one decoding step for a batch
+        signature: N utterances x `beam` slots, encoder rows padded to rows_b, the longest utterance padded to Tmax_b.
+        Kept across decode_batch calls (the last few signatures): a serving loop replays the same graph."""
+        import types
         from ._lib import BeamGatherArgs, BeamMergeArgs
+        plans = self.__dict__.setdefault("_plans", {})
+        key = (N, beam, rows_b, Tmax_b, D, bool(self.use_lm))
+        if key in plans:
+            return plans[key]
         sp, p, lp, dev = self.search_params, self.dec_params, self.lm_params, self.device
-        beam = int(sp.beam_size)
         f64 = dict(dtype=torch.float64, device=dev)
         i32 = dict(dtype=torch.int32, device=dev)
-        encs = []
-        for e in enc_list:
-            e = e.detach().cpu().numpy() if isinstance(e, torch.Tensor) else np.asarray(e)
-            if e.ndim == 3:
-                e = np.squeeze(e, axis=0)
-            encs.append(np.ascontiguousarray(e, np.float32))
-        N = len(encs)
         R = N * beam
-        Ts = np.array([e.shape[0] for e in encs], np.int32)
-        offs = np.concatenate([[0], np.cumsum(Ts)[:-1]]).astype(np.int32)
-        enc_all = torch.from_numpy(np.concatenate(encs, axis=0)).to(dev)
-        D = enc_all.shape[1]
         A = p.attn_enc_w.shape[1]
         V, E = p.embedding.shape
         Hd, Hl = p.dec_lstm_w.shape[1] // 4, p.lm_lstm_w.shape[1] // 4
-        HF = ops.gemm(enc_all, p.attn_enc_w, mode=0)                      # float32 x float32 (beam_search.py:148)
-        Tmax = int(Ts.max())
         S = self.MAX_STEPS
-        row_off = torch.from_numpy(np.repeat(offs, beam)).to(dev)
-        row_T = torch.from_numpy(np.repeat(Ts, beam)).to(dev)
-
+        pl = types.SimpleNamespace(graph=None, calls=0, R=R, S=S)
+        pl.enc_all = torch.zeros((rows_b, D), dtype=torch.float32, device=dev)
+        pl.HF = torch.empty((rows_b, A), dtype=torch.float32, device=dev)
+        pl.row_off = torch.zeros((R,), **i32)
+        pl.row_T = torch.zeros((R,), **i32)
         # ---- slot state (device)
-        slot0 = (torch.arange(R, device=dev) % beam) == 0
-        tok = torch.full((R,), GO_ID, dtype=torch.int64, device=dev)
-        score = torch.zeros((R,), **f64)
-        alive = slot0.to(torch.int32)                                     # step 0: the GO row of every utterance
-        krow = alive * beam
-        k_u = torch.full((N,), beam, **i32)
+        pl.slot0 = ((torch.arange(R, device=dev) % beam) == 0).to(torch.int32)
+        tok = pl.tok = torch.empty((R,), dtype=torch.int64, device=dev)
+        score = pl.score = torch.empty((R,), **f64)
+        alive = pl.alive = torch.empty((R,), **i32)
+        krow = pl.krow = torch.empty((R,), **i32)
+        k_u = pl.k_u = torch.empty((N,), **i32)
         names = ["dc", "dh", "lc", "lh", "ctx"] + (["mc", "mh"] if self.use_lm else [])
         Hm = lp.lm_lstm_w.shape[1] // 4
         width = dict(dc=Hd, dh=Hd, lc=Hl, lh=Hl, ctx=D, mc=Hm, mh=Hm)
-        st = {n: torch.zeros((R, width[n]), **f64) for n in names}        # states entering the step
-        nx = {n: torch.empty((R, width[n]), **f64) for n in names}        # states leaving it (before the gather)
+        st = pl.st = {n: torch.empty((R, width[n]), **f64) for n in names}   # states entering the step
+        nx = {n: torch.empty((R, width[n]), **f64) for n in names}           # states leaving it (before the gather)
         new_tok = torch.empty((R,), dtype=torch.int64, device=dev)
         new_score = torch.empty((R,), **f64)
         new_alive = torch.empty((R,), **i32)
         parent = torch.empty((R,), **i32)
-        par_hist = torch.full((S, R), -1, **i32)
-        tok_hist = torch.full((S, R), -1, **i32)
-        fin_cnt = torch.zeros((N,), **i32)
-        fin_step = torch.zeros((R,), **i32)
-        fin_row = torch.zeros((R,), **i32)
-        fin_score = torch.zeros((R,), **f64)
-        step_dev = torch.zeros((1,), **i32)
-        n_live = torch.zeros((1,), **i32)
+        pl.par_hist = torch.empty((S, R), **i32)
+        pl.tok_hist = torch.empty((S, R), **i32)
+        pl.fin_cnt = torch.empty((N,), **i32)
+        pl.fin_step = torch.empty((R,), **i32)
+        pl.fin_row = torch.empty((R,), **i32)
+        pl.fin_score = torch.empty((R,), **f64)
+        step_dev = pl.step_dev = torch.empty((1,), **i32)
+        n_live = pl.n_live = torch.empty((1,), **i32)
         out_idx = torch.empty((R, beam), **i32)
         out_val = torch.empty((R, beam), **f64)
         scratch = torch.empty((R, V), **f64)
@@ -234,13 +218,15 @@ class BeamSearch(BaseParams):
         ma.N, ma.beam, ma.R, ma.eos_id, ma.word_ins_penalty = N, beam, R, EOS_ID, float(sp.word_ins_penalty)
         for k, t in dict(step=step_dev, out_idx=out_idx, out_val=out_val, score=score, alive=alive, k_u=k_u,
                          new_tok=new_tok, new_score=new_score, parent=parent, new_alive=new_alive, krow=krow,
-                         par_hist=par_hist, tok_hist=tok_hist, fin_cnt=fin_cnt, fin_step=fin_step, fin_row=fin_row,
-                         fin_score=fin_score, n_live=n_live).items():
+                         par_hist=pl.par_hist, tok_hist=pl.tok_hist, fin_cnt=pl.fin_cnt, fin_step=pl.fin_step,
+                         fin_row=pl.fin_row, fin_score=pl.fin_score, n_live=n_live).items():
             setattr(ma, k, t.data_ptr())
         ga = BeamGatherArgs()
         ga.nmat = len(names)
         for m, n in enumerate(names):
             ga.width[m], ga.src[m], ga.dst[m] = width[n], nx[n].data_ptr(), st[n].data_ptr()
+        pl.keep = (ma, ga, nx, new_tok, new_score, new_alive, parent, out_idx, out_val, scratch)
+        HF, enc_all, row_off, row_T = pl.HF, pl.enc_all, pl.row_off, pl.row_T
 
         def lstm(x, c, h, w, b, c_out, h_out):
             """BasicLSTM step on rows: [x, h] . w + b -> (new_c, new_h) written to c_out / h_out."""
@@ -257,7 +243,8 @@ class BeamSearch(BaseParams):
             lstm(x_dec, st["dc"], st["dh"], p.dec_lstm_w, p.dec_lstm_b, nx["dc"], nx["dh"])
             # attention with the CELL state as query (beam_search.py:193), AttnProjection, OutputProjection
             y = self._gemm64(nx["dc"], p.attn_dec_w, p.attn_dec_b)
-            call("e2e_attn_beam_f64", R, A, D, Tmax, HF, enc_all, row_off, row_T, y, p.attn_v, nx["ctx"], D)
+            call("e2e_attn_beam_group_f64", N, beam, A, D, Tmax_b, HF, enc_all, row_off, row_T, y, p.attn_v,
+                 nx["ctx"], D)
             proj = self._gemm64(torch.cat([nx["dc"], nx["ctx"]], dim=1), p.attn_proj_w, p.attn_proj_b)
             logits = self._gemm64(proj, p.out_w, p.out_b)
             lm_logits = None
@@ -277,21 +264,79 @@ class BeamSearch(BaseParams):
             alive.copy_(new_alive)
             step_dev.add_(1)
 
-        step_fn()                                                           # step 0, launched kernel by kernel
-        steps_done = 1
-        graph = None
+        pl.step_fn = step_fn
+        while len(plans) >= 4:                                              # a few signatures; the oldest goes first
+            plans.pop(next(iter(plans)))
+        plans[key] = pl
+        return pl
+
+    def decode_batch(self, enc_list, return_scores=False, use_graph=None):
+        """Decode a list of utterances ([T_i, D] arrays) together; returns a list of id arrays.
+
+        Every utterance owns `beam` fixed hypothesis slots (rows u*beam .. u*beam+beam-1 of every state matrix, live
+        ones first), so one decoding step is a fixed sequence of launches on fixed shapes -- the float64 decoder step
+        on all rows, the per-row top-k, the candidate merge per utterance (`e2e_beam_merge`: k*k candidates ->
+        np.argpartition's top-k set, EOS retirement, back-pointers) and the back-pointer gather of the states.  The
+        host only enqueues, polls the number of live hypotheses every few steps and rebuilds the token sequences from
+        the back-pointers at the end.
+
+        The buffers of a batch signature (utterance count, beam, padded row counts) are kept between calls, and so is
+        the CUDA graph of one step: capturing costs ~70 ms, which a single 120-step decode does not win back, so
+        use_graph=None captures the step the SECOND time a signature is seen and replays it from then on (a serving /
+        evaluation loop over equally shaped batches); True captures at once, False always launches kernel by kernel."""
+        sp, p, dev = self.search_params, self.dec_params, self.device
+        beam = int(sp.beam_size)
+        encs = []
+        for e in enc_list:
+            e = e.detach().cpu().numpy() if isinstance(e, torch.Tensor) else np.asarray(e)
+            if e.ndim == 3:
+                e = np.squeeze(e, axis=0)
+            encs.append(np.ascontiguousarray(e, np.float32))
+        N = len(encs)
+        R = N * beam
+        Ts = np.array([e.shape[0] for e in encs], np.int32)
+        offs = np.concatenate([[0], np.cumsum(Ts)[:-1]]).astype(np.int32)
+        rows = int(Ts.sum())
+        D = encs[0].shape[1]
+        pl = self._plan(N, beam, (rows + 255) // 256 * 256, (int(Ts.max()) + 7) // 8 * 8, D)
+        S = pl.S
+        pl.enc_all[:rows].copy_(torch.from_numpy(np.concatenate(encs, axis=0)))
+        ops.gemm(pl.enc_all, p.attn_enc_w, mode=0, out=pl.HF)             # float32 x float32 (beam_search.py:148)
+        pl.row_off.copy_(torch.from_numpy(np.repeat(offs, beam)))
+        pl.row_T.copy_(torch.from_numpy(np.repeat(Ts, beam)))
+        # ---- slot state: the GO row of every utterance is alive at step 0
+        pl.tok.fill_(GO_ID)
+        pl.score.zero_()
+        pl.alive.copy_(pl.slot0)
+        pl.krow.copy_(pl.slot0 * beam)
+        pl.k_u.fill_(beam)
+        for t in pl.st.values():
+            t.zero_()
+        pl.par_hist.fill_(-1)
+        pl.tok_hist.fill_(-1)
+        for t in (pl.fin_cnt, pl.fin_step, pl.fin_row, pl.fin_score, pl.step_dev, pl.n_live):
+            t.zero_()
+        alive, score, n_live = pl.alive, pl.score, pl.n_live
+        par_hist, tok_hist, fin_cnt, fin_step, fin_row, fin_score = (pl.par_hist, pl.tok_hist, pl.fin_cnt, pl.fin_step,
+                                                                     pl.fin_row, pl.fin_score)
+        step_fn = pl.step_fn
         if use_graph is None:
-            use_graph = False
-        if use_graph and S > 1:
+            use_graph = pl.graph is not None or pl.calls >= 1
+        pl.calls += 1
+        steps_done = 0
+        if use_graph and pl.graph is None and S > 1:
+            step_fn()                                                       # step 0 launched kernel by kernel: warm-up
+            steps_done = 1
             cur = torch.cuda.current_stream()
             cs = torch.cuda.Stream(device=dev)
             cs.wait_stream(cur)
-            graph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(graph, stream=cs):
+            pl.graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(pl.graph, stream=cs):
                 step_fn()
             cur.wait_stream(cs)
+        graph = pl.graph if use_graph else None
         while steps_done < S:
-            if steps_done % 4 == 0 and int(n_live.item()) == 0:             # every hypothesis has emitted EOS
+            if steps_done > 0 and steps_done % 4 == 0 and int(n_live.item()) == 0:   # every hypothesis has emitted EOS
                 break
             if graph is not None:
                 graph.replay()
@@ -314,17 +359,21 @@ class BeamSearch(BaseParams):
 
         outs, outs_sc = [], []
         for u in range(N):
-            final = []
-            for f in range(int(fc[u])):                                     # EOS-retired, in the order they finished
+            # candidates in the reference's order: EOS-retired hypotheses as they finished, then the leftovers
+            # (beam_search.py:332); the best is the FIRST maximum, no length normalisation (:336) -- only that one is
+            # traced back through the back-pointers
+            best, best_sc = None, None
+            for f in range(int(fc[u])):
                 i = u * beam + f
-                final.append((backtrack(int(fs[i]) - 1, int(fr[i])) + [EOS_ID], float(fsc[i])))
-            for slot in range(beam):                                        # leftovers (beam_search.py:332)
+                if best is None or fsc[i] > best_sc:
+                    best, best_sc = (int(fs[i]) - 1, int(fr[i]), True), float(fsc[i])
+            for slot in range(beam):
                 row = u * beam + slot
-                if alive_h[row]:
-                    final.append((backtrack(steps_done - 1, row), float(score_h[row])))
-            best = max(final, key=lambda e: e[1])                           # first maximum, no length norm (:336)
-            outs.append(np.asarray(best[0], np.int64))
-            outs_sc.append(best[1])
+                if alive_h[row] and (best is None or score_h[row] > best_sc):
+                    best, best_sc = (steps_done - 1, row, False), float(score_h[row])
+            seq = backtrack(best[0], best[1]) + ([EOS_ID] if best[2] else [])
+            outs.append(np.asarray(seq, np.int64))
+            outs_sc.append(best_sc)
         return (outs, outs_sc) if return_scores else outs
 
     @classmethod

@@ -247,6 +247,84 @@ int attn_beam_f64(cudaStream_t st, int n, int A, int D, int Tmax, const float* H
     return 0;
 }
 
+// The same read-out for hypotheses stored in groups: rows u*beam .. u*beam+beam-1 belong to utterance u and share its
+// encoder rows (row_off / Tlen of the group's first row).  One CTA per utterance: every HF / enc element is loaded ONCE
+// and used by all `beam` hypotheses (the per-row kernel re-reads the utterance's 100+ KB per hypothesis).  Every
+// hypothesis goes through exactly the arithmetic of attn_beam_f64_kernel -- same lane partition and shuffle trees of
+// the scores, same warp-chunked softmax sums, same sequential read-out -- so the results are bit-identical.
+constexpr int MAXB = 16;
+__global__ void __launch_bounds__(256)
+attn_beam_group_f64_kernel(int beam, int A, int D, int Tmax, const float* __restrict__ HF, const float* __restrict__ enc,
+                           const int* __restrict__ row_off, const int* __restrict__ Tlen, const double* __restrict__ y,
+                           const float* __restrict__ v, double* __restrict__ ctx, int ldctx) {
+    extern __shared__ double sm[];
+    double* y_s = sm;                       // [beam][A]
+    double* v_s = y_s + beam * A;           // [A]
+    double* s_s = v_s + A;                  // [beam][Tmax]  scores, then exp, then alpha
+    const int u = blockIdx.x, tid = threadIdx.x, lane = tid % 32, warp = tid / 32, nw = 8;
+    const int r0 = u * beam;
+    const int off = row_off[r0], T = Tlen[r0];
+    for (int i = tid; i < beam * A; i += 256) y_s[i] = y[(size_t)(r0 + i / A) * A + i % A];
+    for (int a = tid; a < A; a += 256) v_s[a] = (double)v[a];
+    __syncthreads();
+    // scores s[r][tau] = sum_a tanh(HF[tau][a] + y[r][a]) v[a]
+    for (int tau = warp; tau < T; tau += nw) {
+        const float* hrow = HF + (size_t)(off + tau) * A;
+        for (int r = 0; r < beam; ++r) {
+            double p = 0.0;
+            for (int a = lane; a < A; a += 32) p += tanh((double)__ldg(hrow + a) + y_s[r * A + a]) * v_s[a];
+            for (int o = 16; o > 0; o >>= 1) p += __shfl_xor_sync(0xffffffffu, p, o);
+            if (lane == 0) s_s[r * Tmax + tau] = p;
+        }
+    }
+    __syncthreads();
+    // softmax per hypothesis: one warp each; chunk c of 32 positions = warp c of the per-row kernel (T <= 256)
+    for (int r = warp; r < beam; r += nw) {
+        double* sr = s_s + r * Tmax;
+        double mx = -INFINITY;
+        for (int tau = lane; tau < T; tau += 32) mx = fmax(mx, sr[tau]);
+        for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+        double sum = 0.0;
+        for (int c = 0; c < nw; ++c) {
+            const int tau = 32 * c + lane;
+            double e = 0.0;
+            if (tau < T) { e = exp(sr[tau] - mx); sr[tau] = e; }
+            for (int o = 16; o > 0; o >>= 1) e += __shfl_xor_sync(0xffffffffu, e, o);
+            sum += e;
+        }
+        __syncwarp();
+        for (int tau = lane; tau < T; tau += 32) sr[tau] = sr[tau] / sum;
+    }
+    __syncthreads();
+    // read-out ctx[r][d] = sum_tau alpha[r][tau] enc[tau][d]
+    for (int d = tid; d < D; d += 256) {
+        double c[MAXB];
+#pragma unroll
+        for (int r = 0; r < MAXB; ++r) c[r] = 0.0;
+        for (int tau = 0; tau < T; ++tau) {
+            const double e = (double)__ldg(enc + (size_t)(off + tau) * D + d);
+#pragma unroll
+            for (int r = 0; r < MAXB; ++r)
+                if (r < beam) c[r] = fma(s_s[r * Tmax + tau], e, c[r]);
+        }
+#pragma unroll
+        for (int r = 0; r < MAXB; ++r)
+            if (r < beam) ctx[(size_t)(r0 + r) * ldctx + d] = c[r];
+    }
+}
+int attn_beam_group_f64(cudaStream_t st, int N, int beam, int A, int D, int Tmax, const float* HF, const float* enc,
+                        const int* row_off, const int* Tlen, const double* y, const float* v, double* ctx, int ldctx) {
+    if (N <= 0 || beam <= 0) return 0;
+    const size_t smem = sizeof(double) * ((size_t)beam * A + A + (size_t)beam * Tmax);
+    if (beam > MAXB || Tmax > 256 || smem > 200 * 1024)      // the per-row kernel serves any shape
+        return attn_beam_f64(st, N * beam, A, D, Tmax, HF, enc, row_off, Tlen, y, v, ctx, ldctx);
+    if (smem > 48 * 1024)
+        E2E_CHECK_CUDA(cudaFuncSetAttribute(attn_beam_group_f64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attn_beam_group_f64_kernel<<<N, 256, smem, st>>>(beam, A, D, Tmax, HF, enc, row_off, Tlen, y, v, ctx, ldctx);
+    E2E_LAUNCH_CHECK();
+    return 0;
+}
+
 // get_top_k tail (beam_search.py:196-214): combined = log(softmax(dec)) + lm_weight*log(softmax(lm));
 // the k largest entries per row (as a set, like np.argpartition), written in descending score order.
 __global__ void __launch_bounds__(256)

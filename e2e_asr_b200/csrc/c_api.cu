@@ -93,8 +93,13 @@ int attn_bwd(cudaStream_t, int, int, int, int, int, const float*, const float*, 
              const float*, const float*, int, float*, float*, float*, float*);
 int dec_persist(cudaStream_t, bool, const e2e_dec_persist_args*, float*, float*, float*);
 int dec_persist_fits(const e2e_dec_persist_args*);
+int dec_deferred_attn_grads(cudaStream_t, const e2e_dec_persist_args&, float*, float*, float*);
+int attn_bwd_step(cudaStream_t, int, int, int, int, int, const float*, const float*, const int*, const float*, const float*,
+                  const float*, const float*, int, float*, float*);
 int gemm_f64(cudaStream_t, int, int, int, const double*, int, const float*, int, double*, int, const float*);
 int lstm_step_f64(cudaStream_t, int, int, const double*, const double*, double*, double*, int);
+int attn_beam_group_f64(cudaStream_t, int, int, int, int, int, const float*, const float*, const int*, const int*,
+                        const double*, const float*, double*, int);
 int attn_beam_f64(cudaStream_t, int, int, int, int, const float*, const float*, const int*, const int*, const double*,
                   const float*, double*, int);
 int logsoftmax_topk_f64(cudaStream_t, int, int, const double*, const double*, double, const int*, int, int*, double*,
@@ -315,9 +320,9 @@ int e2e_decoder_loop_bwd(void* stream, const e2e_dec_loop_bwd_args* g) {
         float* dcat_t = g->dcat + (size_t)t * B * CAT;
         const float* cat_t = a->cat + (size_t)t * B * CAT;
         float* dy_t = g->dy + (size_t)t * B * A;
-        int rc = attn_bwd(st, B, a->Tn, a->Tp, A, D, a->HF, a->enc, a->enc_len, a->y + (size_t)t * B * A,
-                          a->attn_v, a->alpha + (size_t)t * B * a->Tn, dcat_t + Hd, CAT, g->dHF, g->denc, dy_t,
-                          g->dv_part);
+        int rc = attn_bwd_step(st, B, a->Tn, a->Tp, A, D, a->HF, a->enc, a->enc_len, a->y + (size_t)t * B * A,
+                               a->attn_v, a->alpha + (size_t)t * B * a->Tn, dcat_t + Hd, CAT,
+                               g->ds + (size_t)t * B * a->Tn, dy_t);
         if (rc) return rc;
         // d c_new += dy . q_k^T
         rc = gemm_any(st, mode, 0, 1, B, Hd, A, dy_t, A, a->q_k, A, dcat_t, CAT, nullptr, nullptr, 0, 1);
@@ -340,7 +345,12 @@ int e2e_decoder_loop_bwd(void* stream, const e2e_dec_loop_bwd_args* g) {
             if (rc) return rc;
         }
     }
-    return 0;
+    // sums over the steps: denc += sum_t alpha_t dctx_t (dcat now holds the total d ctx_t), dHF, dv_part
+    e2e_dec_persist_args p = {};
+    p.B = B; p.U = U; p.Hd = Hd; p.A = A; p.D = D; p.Tn = a->Tn; p.Tp = a->Tp;
+    p.attn_v = a->attn_v; p.HF = a->HF; p.enc = a->enc; p.enc_len = a->enc_len; p.lens = a->lens;
+    p.y = a->y; p.alpha = a->alpha; p.dcat = g->dcat; p.ds = g->ds;
+    return dec_deferred_attn_grads(st, p, g->denc, g->dHF, g->dv_part);
 }
 
 int e2e_decoder_persist_fits(const e2e_dec_persist_args* a) { return dec_persist_fits(a); }
@@ -421,6 +431,10 @@ int e2e_gemm_f64(void* stream, int M, int N, int K, const double* A, int lda, co
 int e2e_lstm_step_f64(void* stream, int n, int H, const double* z, const double* c_prev, double* c_out, double* h_out,
                       int ldh) {
     return lstm_step_f64(ST(stream), n, H, z, c_prev, c_out, h_out, ldh);
+}
+int e2e_attn_beam_group_f64(void* stream, int N, int beam, int A, int D, int Tmax, const float* HF, const float* enc,
+                            const int* row_off, const int* Tlen, const double* y, const float* v, double* ctx, int ldctx) {
+    return attn_beam_group_f64(ST(stream), N, beam, A, D, Tmax, HF, enc, row_off, Tlen, y, v, ctx, ldctx);
 }
 int e2e_attn_beam_f64(void* stream, int n, int A, int D, int Tmax, const float* HF, const float* enc,
                       const int* row_off, const int* Tlen, const double* y, const float* v, double* ctx, int ldctx) {

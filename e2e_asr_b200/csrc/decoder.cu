@@ -125,15 +125,23 @@ int dec_pointwise_bwd(cudaStream_t st, int B, int H, int t, const float* acts, c
 // HF/enc rows are (b*Tp + tau).  alpha is written for tau < Tn (zeros past len).
 constexpr int ATT_THREADS = 256;
 
+// ex2.approx + rcp.approx: absolute error ~2e-7, inside the 1e-4 parity budget (the persistent kernels use the same)
+__device__ __forceinline__ float att_tanh(float x) { return 2.0f * __fdividef(1.0f, 1.0f + __expf(-2.0f * x)) - 1.0f; }
+
+// VEC: A % 4 == 0, D % 4 == 0 and 16-byte aligned rows -- scores read HF with one float4 per lane, the read-out holds a
+// float4 of ctx per thread and splits the time axis over ATT_THREADS / (D / 4) thread groups (independent loads in flight
+// instead of one dependent chain per column).
+template <bool VEC>
 __global__ void __launch_bounds__(ATT_THREADS)
 attn_fwd_kernel(int Tn, int Tp, int A, int D, const float* __restrict__ HF, const float* __restrict__ enc,
                 const int* __restrict__ enc_len, const float* __restrict__ y, const float* __restrict__ v,
                 float* __restrict__ alpha, float* __restrict__ ctx, int ldctx) {
-    extern __shared__ float sm[];
+    extern __shared__ __align__(16) float sm[];
     float* y_s = sm;            // [A]
     float* v_s = sm + A;        // [A]
     float* s_s = sm + 2 * A;    // [Tn]
     __shared__ float red[32];
+    __shared__ __align__(16) float part_s[ATT_THREADS * 4];
     const int b = blockIdx.x, tid = threadIdx.x, lane = tid % 32, warp = tid / 32;
     const int nw = ATT_THREADS / 32;
     const int len = min(enc_len[b], Tn);
@@ -142,7 +150,15 @@ attn_fwd_kernel(int Tn, int Tp, int A, int D, const float* __restrict__ HF, cons
     const float* HFb = HF + (size_t)b * Tp * A;
     for (int tau = warp; tau < len; tau += nw) {
         float p = 0.f;
-        for (int a = lane; a < A; a += 32) p += v_s[a] * tanhf(HFb[(size_t)tau * A + a] + y_s[a]);
+        if (VEC) {
+            for (int a4 = lane; a4 < A / 4; a4 += 32) {
+                const float4 h = __ldg(reinterpret_cast<const float4*>(HFb + (size_t)tau * A) + a4);
+                const float4 yy = *reinterpret_cast<const float4*>(y_s + 4 * a4), vv = *reinterpret_cast<const float4*>(v_s + 4 * a4);
+                p += vv.x * att_tanh(h.x + yy.x) + vv.y * att_tanh(h.y + yy.y) + vv.z * att_tanh(h.z + yy.z) + vv.w * att_tanh(h.w + yy.w);
+            }
+        } else {
+            for (int a = lane; a < A; a += 32) p += v_s[a] * att_tanh(HFb[(size_t)tau * A + a] + y_s[a]);
+        }
         p = warp_sum(p);
         if (lane == 0) s_s[tau] = p;
     }
@@ -175,19 +191,51 @@ attn_fwd_kernel(int Tn, int Tp, int A, int D, const float* __restrict__ HF, cons
     }
     __syncthreads();
     const float* encb = enc + (size_t)b * Tp * D;
-    for (int d = tid; d < D; d += ATT_THREADS) {
-        float c = 0.f;
-        for (int tau = 0; tau < len; ++tau) c = fmaf(s_s[tau], encb[(size_t)tau * D + d], c);
-        ctx[(size_t)b * ldctx + d] = c;
+    if (VEC && D / 4 <= ATT_THREADS) {
+        const int d4n = D / 4, ng = ATT_THREADS / d4n;
+        const int d4 = tid % d4n, gi = tid / d4n;
+        float4 c = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (gi < ng) {
+#pragma unroll 4
+            for (int tau = gi; tau < len; tau += ng) {
+                const float4 e = __ldg(reinterpret_cast<const float4*>(encb + (size_t)tau * D) + d4);
+                const float al = s_s[tau];
+                c.x = fmaf(al, e.x, c.x); c.y = fmaf(al, e.y, c.y); c.z = fmaf(al, e.z, c.z); c.w = fmaf(al, e.w, c.w);
+            }
+        }
+        if (ng > 1) {
+            *reinterpret_cast<float4*>(part_s + 4 * tid) = c;
+            __syncthreads();
+            if (gi == 0) {
+                for (int g2 = 1; g2 < ng; ++g2) {
+                    const float4 o = *reinterpret_cast<const float4*>(part_s + 4 * (g2 * d4n + d4));
+                    c.x += o.x; c.y += o.y; c.z += o.z; c.w += o.w;
+                }
+            }
+        }
+        if (gi == 0) {
+            float* cr = ctx + (size_t)b * ldctx + 4 * d4;
+            cr[0] = c.x; cr[1] = c.y; cr[2] = c.z; cr[3] = c.w;
+        }
+    } else {
+        for (int d = tid; d < D; d += ATT_THREADS) {
+            float c = 0.f;
+            for (int tau = 0; tau < len; ++tau) c = fmaf(s_s[tau], encb[(size_t)tau * D + d], c);
+            ctx[(size_t)b * ldctx + d] = c;
+        }
     }
 }
 
 int attn_fwd(cudaStream_t st, int B, int Tn, int Tp, int A, int D, const float* HF, const float* enc,
              const int* enc_len, const float* y, const float* v, float* alpha, float* ctx, int ldctx) {
     size_t smem = sizeof(float) * (2 * A + Tn);
-    if (smem > 48 * 1024)
-        E2E_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attn_fwd_kernel<<<B, ATT_THREADS, smem, st>>>(Tn, Tp, A, D, HF, enc, enc_len, y, v, alpha, ctx, ldctx);
+    if (smem > 44 * 1024) {
+        E2E_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        E2E_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    }
+    const bool vec = A % 4 == 0 && D % 4 == 0 && (((uintptr_t)HF | (uintptr_t)enc) & 15) == 0;
+    if (vec) attn_fwd_kernel<true><<<B, ATT_THREADS, smem, st>>>(Tn, Tp, A, D, HF, enc, enc_len, y, v, alpha, ctx, ldctx);
+    else attn_fwd_kernel<false><<<B, ATT_THREADS, smem, st>>>(Tn, Tp, A, D, HF, enc, enc_len, y, v, alpha, ctx, ldctx);
     E2E_LAUNCH_CHECK();
     return 0;
 }
@@ -273,6 +321,96 @@ int attn_bwd(cudaStream_t st, int B, int Tn, int Tp, int A, int D, const float* 
         E2E_CHECK_CUDA(cudaFuncSetAttribute(attn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attn_bwd_kernel<<<B, ATT_THREADS, smem, st>>>(Tn, Tp, A, D, HF, enc, enc_len, y, v, alpha, dctx, lddctx, dHF,
                                                   denc, dy, dv_part);
+    E2E_LAUNCH_CHECK();
+    return 0;
+}
+
+// Per-step part of the attention backward for the step-by-step decoder loop: da, ds and dy only.  The sums over the
+// decoder steps (dHF, denc, dv) are formed AFTER the loop from the stored ds_t, alpha_t, y_t and dctx_t
+// (dec_deferred_attn_grads, decoder_persist.cu) instead of a read-modify-write of dHF[b] and denc[b] in every step.
+template <bool VEC>
+__global__ void __launch_bounds__(ATT_THREADS)
+attn_bwd_step_kernel(int Tn, int Tp, int A, int D, const float* __restrict__ HF, const float* __restrict__ enc,
+                     const int* __restrict__ enc_len, const float* __restrict__ y, const float* __restrict__ v,
+                     const float* __restrict__ alpha, const float* __restrict__ dctx, int lddctx,
+                     float* __restrict__ ds_out, float* __restrict__ dy) {
+    extern __shared__ __align__(16) float sm[];
+    float* y_s = sm;              // [A]
+    float* v_s = sm + A;          // [A]
+    float* dctx_s = sm + 2 * A;   // [D]
+    float* ds_s = dctx_s + D;     // [Tn]  (da, then ds)
+    float* acc_s = ds_s + Tn;     // [groups][A] partial dy
+    __shared__ float red[32];
+    const int b = blockIdx.x, tid = threadIdx.x, lane = tid % 32, warp = tid / 32;
+    const int nw = ATT_THREADS / 32;
+    const int len = min(enc_len[b], Tn);
+    for (int a = tid; a < A; a += ATT_THREADS) { y_s[a] = y[(size_t)b * A + a]; v_s[a] = v[a]; }
+    for (int d = tid; d < D; d += ATT_THREADS) dctx_s[d] = dctx[(size_t)b * lddctx + d];
+    __syncthreads();
+    const float* al = alpha + (size_t)b * Tn;
+    const float* encb = enc + (size_t)b * Tp * D;
+    // da_tau = dctx . enc_tau
+    float part = 0.f;
+    for (int tau = warp; tau < len; tau += nw) {
+        float p = 0.f;
+        if (VEC) {
+            const float4* er = reinterpret_cast<const float4*>(encb + (size_t)tau * D);
+#pragma unroll 4
+            for (int d4 = lane; d4 < D / 4; d4 += 32) {
+                const float4 e = __ldg(er + d4), c = *reinterpret_cast<const float4*>(dctx_s + 4 * d4);
+                p = fmaf(c.x, e.x, p); p = fmaf(c.y, e.y, p); p = fmaf(c.z, e.z, p); p = fmaf(c.w, e.w, p);
+            }
+        } else {
+            for (int d = lane; d < D; d += 32) p = fmaf(dctx_s[d], encb[(size_t)tau * D + d], p);
+        }
+        p = warp_sum(p);
+        if (lane == 0) { ds_s[tau] = p; part += al[tau] * p; }
+    }
+    if (lane == 0) red[warp] = part;
+    __syncthreads();
+    float dot = 0.f;
+    for (int w = 0; w < nw; ++w) dot += red[w];
+    // ds_tau = alpha_tau (da_tau - sum alpha da)
+    for (int tau = tid; tau < Tn; tau += ATT_THREADS) {
+        const float ds = tau < len ? al[tau] * (ds_s[tau] - dot) : 0.f;
+        if (tau < len) ds_s[tau] = ds;
+        ds_out[(size_t)b * Tn + tau] = ds;
+    }
+    __syncthreads();
+    // dy_a = sum_tau ds_tau v_a (1 - th^2): the time axis split over ATT_THREADS / A thread groups
+    const float* HFb = HF + (size_t)b * Tp * A;
+    const int groups = A <= ATT_THREADS ? ATT_THREADS / A : 1;
+    for (int idx = tid; idx < groups * A; idx += ATT_THREADS) {
+        const int a = idx % A, gi = idx / A;
+        const float ya = y_s[a];
+        float dya = 0.f;
+#pragma unroll 4
+        for (int tau = gi; tau < len; tau += groups) {
+            const float th = att_tanh(HFb[(size_t)tau * A + a] + ya);
+            dya = fmaf(ds_s[tau], 1.f - th * th, dya);
+        }
+        acc_s[idx] = dya * v_s[a];
+    }
+    __syncthreads();
+    for (int a = tid; a < A; a += ATT_THREADS) {
+        float dya = 0.f;
+        for (int gi = 0; gi < groups; ++gi) dya += acc_s[gi * A + a];
+        dy[(size_t)b * A + a] = dya;
+    }
+}
+
+int attn_bwd_step(cudaStream_t st, int B, int Tn, int Tp, int A, int D, const float* HF, const float* enc,
+                  const int* enc_len, const float* y, const float* v, const float* alpha, const float* dctx, int lddctx,
+                  float* ds_out, float* dy) {
+    const int groups = A <= ATT_THREADS ? ATT_THREADS / A : 1;
+    size_t smem = sizeof(float) * (2 * A + D + Tn + (size_t)groups * A);
+    const bool vec = D % 4 == 0 && ((uintptr_t)enc & 15) == 0 && A % 4 == 0;
+    if (smem > 44 * 1024) {
+        E2E_CHECK_CUDA(cudaFuncSetAttribute(attn_bwd_step_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        E2E_CHECK_CUDA(cudaFuncSetAttribute(attn_bwd_step_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    }
+    if (vec) attn_bwd_step_kernel<true><<<B, ATT_THREADS, smem, st>>>(Tn, Tp, A, D, HF, enc, enc_len, y, v, alpha, dctx, lddctx, ds_out, dy);
+    else attn_bwd_step_kernel<false><<<B, ATT_THREADS, smem, st>>>(Tn, Tp, A, D, HF, enc, enc_len, y, v, alpha, dctx, lddctx, ds_out, dy);
     E2E_LAUNCH_CHECK();
     return 0;
 }

@@ -1124,6 +1124,18 @@ int dec_persist_fits(const e2e_dec_persist_args* a) {
     return fwd_smem_bytes(p) <= 227 * 1024 && bwd_smem_bytes(p) <= 227 * 1024;
 }
 
+// The sums over the decoder steps of the attention backward -- denc += sum_t alpha_t dctx_t, dHF and dv_part [B*Tn, A]
+// -- from stored per-step tensors; also serves the step-by-step loop (e2e_decoder_loop_bwd).  Reads B, U, Hd, A, D, Tn,
+// Tp, enc_len, alpha, dcat, ds, y, HF, attn_v of `p`.
+int dec_deferred_attn_grads(cudaStream_t st, const e2e_dec_persist_args& p, float* denc, float* dHF, float* dv_part) {
+    if (p.B <= 0 || p.U <= 0 || p.Tn <= 0) return 0;
+    dec_denc_kernel<<<p.B * p.Tn, 256, sizeof(float) * p.U, st>>>(p, denc);
+    E2E_LAUNCH_CHECK();
+    dec_dhf_kernel<<<p.B * p.Tn, 128, sizeof(float) * p.U, st>>>(p, dHF, dv_part, 0);
+    E2E_LAUNCH_CHECK();
+    return 0;
+}
+
 int dec_persist(cudaStream_t st, bool bwd, const e2e_dec_persist_args* a, float* denc, float* dHF, float* dv_part) {
     e2e_dec_persist_args p = *a;
     E2E_REQUIRE(p.Hd % 8 == 0 && p.A % 8 == 0 && p.D % 8 == 0, "decoder_persist: Hd, A, D must be multiples of 8");

@@ -860,9 +860,9 @@ class AttnDecoderFn(torch.autograd.Function):
             setattr(a, k, v.data_ptr())
         nrows = enc_flat.shape[0]
         out = dict(dcat=dcat, dgates=torch.empty((U * B, 4 * Hd), **f32), dxh=torch.empty((U * B, E + Hd), **f32),
-                   dy=torch.empty((U * B, A), **f32), dv_part=torch.zeros((B, A), **f32),
+                   dy=torch.empty((U * B, A), **f32), dv_part=torch.empty((B * Tn, A), **f32),
                    dHF=torch.zeros((nrows, A), **f32), denc=torch.zeros((nrows, D), **f32),
-                   dc_carry=torch.zeros((B, Hd), **f32))
+                   dc_carry=torch.zeros((B, Hd), **f32), ds=torch.empty((U * B, Tn), **f32))
         for k, v in out.items():
             setattr(g, k, v.data_ptr())
         call("e2e_decoder_loop_bwd", g, work=float(U))

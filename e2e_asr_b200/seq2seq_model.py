@@ -288,6 +288,12 @@ class Seq2SeqModel(BaseParams):
                         if states_d is None:
                             states_d = self.encoder_hidden_states[d]
                         D = states_d.shape[2]
+                        if ops.get_gemm_mode() != 0:
+                            # operand pre-pass scratch of the head's largest product (d kernel = states^T . d logits:
+                            # two planes of both operands); grows only on the first, un-captured step
+                            rows = states_d.shape[0] * states_d.shape[1]
+                            need = 2 * 4 * rows * (D + vocab + 9) + (1 << 20)
+                            ops.ensure_workspace(self.device, nbytes=max(512 << 20, need), stream=side)
                         k = self.variables.get("model/ctc_%s/kernel" % task, (D, vocab + 1))
                         b = self.variables.get("model/ctc_%s/bias" % task, (vocab + 1,), ("zeros",))
                         self.ctc_stash[task] = {"consumer_stream": main}

@@ -172,10 +172,11 @@ typedef struct {
     float* dgates;         /* [U,B,4Hd] out */
     float* dxh;            /* [U,B,E+Hd] out: (dxin_t | dh_{t-1}) */
     float* dy;             /* [U,B,A] out */
-    float* dv_part;        /* [B,A]    zero-initialised, accumulated */
-    float* dHF;            /* [B,Tp,A] zero-initialised, accumulated */
-    float* denc;           /* [B,Tp,D] accumulated into */
+    float* dv_part;        /* [B*Tn,A] out: per (row, position) partial d attn_v (sum the rows) */
+    float* dHF;            /* [B,Tp,A] zero-initialised; rows of valid positions are written after the loop */
+    float* denc;           /* [B,Tp,D] accumulated into (after the loop: sum_t alpha_t dctx_t) */
     float* dc_carry;       /* [B,Hd]   zero-initialised scratch */
+    float* ds;             /* [U,B,Tn] out: d(pre-softmax scores) per step, kept for the sums over the steps */
 } e2e_dec_loop_bwd_args;
 int e2e_decoder_loop_bwd(void* stream, const e2e_dec_loop_bwd_args* a);
 
@@ -277,6 +278,11 @@ int e2e_gemm_f64(void* stream, int M, int N, int K, const double* A, int lda, co
                  double* C, int ldc, const float* bias);
 int e2e_lstm_step_f64(void* stream, int n, int H, const double* z, const double* c_prev, double* c_out,
                       double* h_out, int ldh);
+/* e2e_attn_beam_f64 for hypotheses stored in groups of `beam` rows per utterance (rows u*beam .. u*beam+beam-1 share
+ * row_off / Tlen of the group's first row): one CTA per utterance reads its encoder rows once for all hypotheses;
+ * bit-identical results (calc_attention, beam_search.py:150-159). */
+int e2e_attn_beam_group_f64(void* stream, int N, int beam, int A, int D, int Tmax, const float* HF, const float* enc,
+                            const int* row_off, const int* Tlen, const double* y, const float* v, double* ctx, int ldctx);
 int e2e_attn_beam_f64(void* stream, int n, int A, int D, int Tmax, const float* HF, const float* enc,
                       const int* row_off, const int* Tlen, const double* y, const float* v, double* ctx,
                       int ldctx);

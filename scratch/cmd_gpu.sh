@@ -1,3 +1,9 @@
-timeout 200 python -m pytest tests/test_gpu_kernels.py -q -k "rows_of_very" > gpurun_out/r2o_rows.log 2>&1; grep -v "^frame" gpurun_out/r2o_rows.log | grep -E "Error|assert|passed|failed" | head -20
-timeout 400 python -m pytest tests/test_gpu_kernels.py tests/test_gpu_fullsize.py -q -x -k "bilstm or fullsize_step" 2>&1 | tail -3
-for i in 1 2 3 4 5 6; do timeout 200 python -m pytest tests/test_gpu_fullsize.py -q -x -k "cfg5 and f16x2" > gpurun_out/r2o_t$i.log 2>&1; echo "run $i rc=$?"; done
+timeout 600 python -m pytest tests/test_gpu_beam.py tests/test_gpu_fullsize.py -q -x -k "beam" 2>&1 | tail -5
+PYTHONPATH=. timeout 300 python scratch/time_beam.py 2>&1 | tail -14
+timeout 300 python bench.py --steps 5 --warmup 3 --no-cpu-baseline > gpurun_out/r2r_bench.json 2> gpurun_out/r2r_bench.err
+python - <<P
+import json
+d=json.loads(open("gpurun_out/r2r_bench.json").read().strip().splitlines()[-1])
+print(d["ms_per_step"], d["value"], d["e2e"]["value"])
+print(json.dumps(d.get("beam_decode"))[:900])
+P

@@ -166,3 +166,75 @@ def test_gemm_f64_matches_numpy(M, N, K, lda_pad):
     call("e2e_gemm_f64", M, N, K, ad, ad.stride(0), bd, bd.stride(0), out, out.stride(0), biasd)
     ref = a[:, :K] @ b.astype(np.float64) + bias.astype(np.float64)
     assert np.abs(out.cpu().numpy() - ref).max() <= 1e-12 * max(1.0, np.abs(ref).max())
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("beam,A,D", [(10, 128, 512), (3, 40, 72), (16, 128, 1024), (17, 32, 64)])
+def test_grouped_beam_attention_is_bit_identical_to_the_per_row_kernel(beam, A, D):
+    """e2e_attn_beam_group_f64 (one CTA per utterance, encoder rows read once for all its hypotheses) against
+    e2e_attn_beam_f64 (one CTA per hypothesis): the same arithmetic in the same order, so exactly equal; both against
+    a NumPy float64 calc_attention (beam_search.py:150-159).  beam = 17 exceeds the grouped kernel's register tile and
+    must fall through to the per-row kernel."""
+    import torch
+    from e2e_asr_b200._lib import call
+    rng = np.random.default_rng(beam * 1000 + A + D)
+    Ts = np.array([44, 1, 87, 50, 9, 200, 33], np.int32)
+    N, Tmax = len(Ts), int(Ts.max())
+    offs = np.concatenate([[0], np.cumsum(Ts)[:-1]]).astype(np.int32)
+    rows = int(Ts.sum())
+    HF = rng.standard_normal((rows, A)).astype(np.float32)
+    enc = np.tanh(rng.standard_normal((rows, D))).astype(np.float32)
+    y = rng.standard_normal((N * beam, A))
+    v = rng.standard_normal(A).astype(np.float32)
+    dev = "cuda:0"
+    HFd, encd, yd, vd = (torch.from_numpy(x).to(dev) for x in (HF, enc, y, v))
+    ro = torch.from_numpy(np.repeat(offs, beam)).to(dev)
+    rt = torch.from_numpy(np.repeat(Ts, beam)).to(dev)
+    c_row = torch.full((N * beam, D), float("nan"), dtype=torch.float64, device=dev)
+    c_grp = torch.full((N * beam, D), float("nan"), dtype=torch.float64, device=dev)
+    call("e2e_attn_beam_f64", N * beam, A, D, Tmax, HFd, encd, ro, rt, yd, vd, c_row, D)
+    call("e2e_attn_beam_group_f64", N, beam, A, D, Tmax, HFd, encd, ro, rt, yd, vd, c_grp, D)
+    assert torch.equal(c_row, c_grp)
+    ref = np.empty((N * beam, D))
+    for r in range(N * beam):
+        u = r // beam
+        sl = slice(offs[u], offs[u] + Ts[u])
+        s = np.tanh(HF[sl].astype(np.float64) + y[r]) @ v.astype(np.float64)
+        e = np.exp(s - s.max())
+        ref[r] = (e / e.sum()) @ enc[sl].astype(np.float64)
+    assert np.abs(c_grp.cpu().numpy() - ref).max() <= 1e-12
+
+
+@pytest.mark.gpu
+def test_decode_batch_graph_capture_and_replay_repeat_the_eager_ids():
+    """decode_batch keeps the buffers and the step graph of a batch signature: call 1 launches kernel by kernel, call 2
+    captures the step, call 3 replays it -- the same ids and scores every time, also after a different batch of the same
+    signature went through the cached buffers in between."""
+    from e2e_asr_b200.beam_search import BeamSearch
+    cfg = synth.get_config("cfg1")
+    w = gg.dec_weights(cfg, 21, 2.5, 10.0)
+    rng = np.random.Generator(np.random.PCG64(5))
+    lens = [int(rng.integers(50, 89)) for _ in range(6)]
+    mk = lambda: [(np.tanh(rng.standard_normal((t, 2 * cfg.H))) * 0.8).astype(np.float32) for t in lens]
+    encs, other = mk(), mk()
+    sp = BeamSearch.class_params()
+    sp.beam_size = 5
+    bs = BeamSearch(w, sp, device="cuda:0")
+    first, sc1 = bs.decode_batch(encs, return_scores=True)
+    assert next(iter(bs._plans.values())).graph is None
+    second, sc2 = bs.decode_batch(encs, return_scores=True)
+    assert next(iter(bs._plans.values())).graph is not None and len(bs._plans) == 1
+    o3 = bs.decode_batch(other)
+    third, sc3 = bs.decode_batch(encs, return_scores=True)
+    for a, b, c in zip(first, second, third):
+        np.testing.assert_array_equal(a, b)
+        np.testing.assert_array_equal(a, c)
+    # enc . AttnW is a float32 product (beam_search.py:148) whose split-K partial sums land in arrival order: the scores
+    # repeat to float32 rounding of that product, the ids exactly
+    np.testing.assert_allclose(sc2, sc1, rtol=1e-6)
+    np.testing.assert_allclose(sc3, sc1, rtol=1e-6)
+    ref = BeamSearch(w, sp, device="cuda:0").decode_batch(other, use_graph=False)
+    for a, b in zip(o3, ref):
+        np.testing.assert_array_equal(a, b)
+    for u, enc in enumerate(encs):
+        np.testing.assert_array_equal(first[u], ob.beam_search(w, enc, beam_size=5))

@@ -31,7 +31,7 @@ def test_exports_every_declared_symbol(libpath):
 def test_struct_layout_matches_header():
     # 9 ints (padded to 40 bytes) + 18 pointers; bwd adds 8 pointers
     assert ctypes.sizeof(_lib.DecLoopFwdArgs) == 40 + 18 * 8
-    assert ctypes.sizeof(_lib.DecLoopBwdArgs) == 40 + 26 * 8
+    assert ctypes.sizeof(_lib.DecLoopBwdArgs) == 40 + 27 * 8
 
 
 @pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU behaviour")
