@@ -57,6 +57,7 @@ _SIGS = {
     "e2e_gru_rec_bwd": "piiiiippppppp",
     "e2e_sample_rows": "piipiQIIp",
     "e2e_gemm_f64": "piiipipipip",
+    "e2e_gemm_f64d": "piiipipipip",
     "e2e_lstm_step_f64": "piippppi",
     "e2e_attn_beam_f64": "piiiipppppppi",
     "e2e_attn_beam_group_f64": "piiiiipppppppi",
@@ -139,6 +140,8 @@ def lib():
         l.e2e_ctc_workspace_floats.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_int]
         l.e2e_lstm_rec_workspace_bytes.restype = ctypes.c_size_t
         l.e2e_lstm_rec_workspace_bytes.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_int]
+        l.e2e_set_f64_mma.restype = ctypes.c_int
+        l.e2e_set_f64_mma.argtypes = [ctypes.c_int]
         l.e2e_set_tc_debug.restype = ctypes.c_int
         l.e2e_set_tc_debug.argtypes = [ctypes.c_void_p, ctypes.c_longlong]
         _lib = l
@@ -147,7 +150,7 @@ def lib():
 
 def exported_symbols():
     return sorted(list(_SIGS.keys()) + ["e2e_last_error", "e2e_version", "e2e_sm_count", "e2e_launch_count", "e2e_capture_status",
-                   "e2e_set_workspace", "e2e_set_dec_sync", "e2e_ctc_workspace_floats", "e2e_lstm_rec_workspace_bytes", "e2e_decoder_persist_fits", "e2e_set_tc_debug", "e2e_set_rec_mode", "e2e_set_rec_debug", "e2e_set_stream_workspace"])
+                   "e2e_set_workspace", "e2e_set_dec_sync", "e2e_ctc_workspace_floats", "e2e_set_f64_mma", "e2e_lstm_rec_workspace_bytes", "e2e_decoder_persist_fits", "e2e_set_tc_debug", "e2e_set_rec_mode", "e2e_set_rec_debug", "e2e_set_stream_workspace"])
 
 
 def _ptr(x):

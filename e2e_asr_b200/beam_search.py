@@ -159,8 +159,19 @@ class BeamSearch(BaseParams):
         return self.decode_batch([encoder_hidden_states])[0]
 
     def _gemm64(self, a, w, b):
+        """a (float64 hypotheses) . w (float32 weights) + b in float64 (beam_search.py:182-199).  The weights are widened
+        to float64 once per matrix (exact), so the product kernel has no conversions in its inner loop."""
         out = torch.empty((a.shape[0], w.shape[1]), dtype=torch.float64, device=self.device)
-        call("e2e_gemm_f64", a.shape[0], w.shape[1], a.shape[1], a, a.stride(0), w, w.stride(0), out, out.stride(0), b)
+        K = a.shape[1]
+        if K % 16 == 0 and a.stride(0) % 2 == 0 and w.shape[1] % 2 == 0 and w.is_contiguous():
+            cache = self.__dict__.setdefault("_w64", {})
+            ent = cache.get(w.data_ptr())
+            if ent is None or ent[0] is not w:
+                ent = cache[w.data_ptr()] = (w, w.to(torch.float64))
+            w64 = ent[1]
+            call("e2e_gemm_f64d", a.shape[0], w.shape[1], K, a, a.stride(0), w64, w64.stride(0), out, out.stride(0), b)
+        else:
+            call("e2e_gemm_f64", a.shape[0], w.shape[1], K, a, a.stride(0), w, w.stride(0), out, out.stride(0), b)
         return out
 
     def _plan(self, N, beam, rows_b, Tmax_b, D):

@@ -80,11 +80,18 @@ __device__ __forceinline__ void cp_async16(void* dst, const void* src, int src_b
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"((uint32_t)__cvta_generic_to_shared(dst)),
                  "l"(src), "r"(src_bytes) : "memory");
 }
+template <typename T> struct Pair;
+template <> struct Pair<float> { typedef float2 type; };
+template <> struct Pair<double> { typedef double2 type; };
+// TB = double: the weights were widened once by the caller (e2e_gemm_f64d) -- no per-k conversions in the inner loop
+// (F2F shares the FP64 pipe with the FMAs); (double)float is exact, so the results are bit-identical.
+template <typename TB>
 __global__ void __launch_bounds__(128)
-gemm_f64_pipe_kernel(int M, int N, int K, const double* __restrict__ A, int lda, const float* __restrict__ B, int ldb,
+gemm_f64_pipe_kernel(int M, int N, int K, const double* __restrict__ A, int lda, const TB* __restrict__ B, int ldb,
                      double* __restrict__ C, int ldc, const float* __restrict__ bias) {
+    constexpr int BV = 16 / (int)sizeof(TB);                 // B elements per 16-byte chunk
     __shared__ __align__(16) double As[2][PT][PAS];
-    __shared__ __align__(16) float Bs[2][PK][PT];
+    __shared__ __align__(16) TB Bs[2][PK][PT];
     const int tid = threadIdx.x, tx = tid % 16, ty = tid / 16;
     const int m0 = blockIdx.y * PT, n0 = blockIdx.x * PT;
     auto issue = [&](int stage, int k0) {
@@ -96,10 +103,10 @@ gemm_f64_pipe_kernel(int M, int N, int K, const double* __restrict__ A, int lda,
             cp_async16(&As[stage][r][c], A + (size_t)(ok ? m0 + r : 0) * lda + k0 + c, ok ? 16 : 0);
         }
 #pragma unroll
-        for (int it = 0; it < 2; ++it) {
-            const int i = it * 128 + tid, k = i / 16, c = (i % 16) * 4;
+        for (int it = 0; it < PK * PT / BV / 128; ++it) {
+            const int i = it * 128 + tid, k = i / (PT / BV), c = (i % (PT / BV)) * BV;
             const int rem = N - (n0 + c);                       // columns left in this row of B
-            const int bytes = rem >= 4 ? 16 : (rem > 0 ? rem * 4 : 0);
+            const int bytes = rem >= BV ? 16 : (rem > 0 ? rem * (int)sizeof(TB) : 0);
             cp_async16(&Bs[stage][k][c], B + (size_t)(k0 + k) * ldb + (rem > 0 ? n0 + c : 0), bytes);
         }
         asm volatile("cp.async.commit_group;" ::: "memory");
@@ -130,7 +137,7 @@ gemm_f64_pipe_kernel(int M, int N, int K, const double* __restrict__ A, int lda,
             }
 #pragma unroll
             for (int j = 0; j < 2; ++j) {
-                const float2 bv = *reinterpret_cast<const float2*>(&Bs[s][k][32 * j + 2 * tx]);
+                const typename Pair<TB>::type bv = *reinterpret_cast<const typename Pair<TB>::type*>(&Bs[s][k][32 * j + 2 * tx]);
                 b[2 * j] = (double)bv.x;
                 b[2 * j + 1] = (double)bv.y;
             }
@@ -153,13 +160,107 @@ gemm_f64_pipe_kernel(int M, int N, int K, const double* __restrict__ A, int lda,
     }
 }
 
+int g_f64_mma = 1;      // e2e_gemm_f64d: 1 = FP64 tensor-core kernel, 0 = register-tiled DFMA kernel (e2e_set_f64_mma, tests)
+// FP64 tensor-core version (mma.sync m8n8k4 f64) of the aligned product with float64 weights: the register-tiled DFMA
+// kernels above spend three shared-memory wavefronts per four FMA issues (measured 15.6 TFLOP/s, the LSU as busy as the
+// FP64 pipe); a DMMA takes its 8x4 / 4x8 fragments with ONE 8-byte load per lane for 256 FMAs.  CTA = 64 x 64 tile,
+// 4 warps of 32 x 32 (4 x 4 m8n8 tiles, 32 accumulator doubles per lane), 2-stage cp.async pipeline over k-tiles of 16;
+// row strides 18 (A, [m][k]) and 68 (B, [k][n]) doubles spread the fragment loads evenly over the banks (two
+// wavefronts per 256-byte load, the minimum).  The four products of a k4 block are summed inside the tensor core, so
+// the result differs from the sequential-FMA kernels in the last bits (not in accuracy).
+constexpr int BS2 = PT + 4;
+__device__ __forceinline__ void dmma(double (&d)[2], double a, double b) {
+    asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(d[0]), "+d"(d[1]) : "d"(a), "d"(b));
+}
+__global__ void __launch_bounds__(128)
+gemm_f64_mma_kernel(int M, int N, int K, const double* __restrict__ A, int lda, const double* __restrict__ B, int ldb,
+                    double* __restrict__ C, int ldc, const float* __restrict__ bias) {
+    __shared__ __align__(16) double As[2][PT][PAS];
+    __shared__ __align__(16) double Bs[2][PK][BS2];
+    const int tid = threadIdx.x, lane = tid % 32, w = tid / 32, wm = w / 2, wn = w % 2;
+    const int lr = lane / 4, lc = lane % 4;
+    const int m0 = blockIdx.y * PT, n0 = blockIdx.x * PT;
+    auto issue = [&](int stage, int k0) {
+#pragma unroll
+        for (int it = 0; it < 4; ++it) {
+            const int i = it * 128 + tid, r = i / 8, c = (i % 8) * 2;
+            const bool ok = m0 + r < M;
+            cp_async16(&As[stage][r][c], A + (size_t)(ok ? m0 + r : 0) * lda + k0 + c, ok ? 16 : 0);
+        }
+#pragma unroll
+        for (int it = 0; it < 4; ++it) {
+            const int i = it * 128 + tid, k = i / 32, c = (i % 32) * 2;
+            const int rem = N - (n0 + c);
+            const int bytes = rem >= 2 ? 16 : (rem > 0 ? 8 : 0);
+            cp_async16(&Bs[stage][k][c], B + (size_t)(k0 + k) * ldb + (rem > 0 ? n0 + c : 0), bytes);
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    double acc[4][4][2];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { acc[i][j][0] = 0.0; acc[i][j][1] = 0.0; }
+    const int nk = K / PK;
+    issue(0, 0);
+    for (int t = 0; t < nk; ++t) {
+        if (t + 1 < nk) {
+            issue((t + 1) & 1, (t + 1) * PK);
+            asm volatile("cp.async.wait_group 1;" ::: "memory");
+        } else {
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
+        }
+        __syncthreads();
+        const int s = t & 1;
+#pragma unroll
+        for (int kk = 0; kk < PK / 4; ++kk) {
+            double a[4], b[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) a[i] = As[s][32 * wm + 8 * i + lr][4 * kk + lc];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) b[j] = Bs[s][4 * kk + lc][32 * wn + 8 * j + lr];
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) dmma(acc[i][j], a[i], b[j]);
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int m = m0 + 32 * wm + 8 * i + lr;
+        if (m >= M) continue;
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                const int n = n0 + 32 * wn + 8 * j + 2 * lc + e;
+                if (n < N) C[(size_t)m * ldc + n] = acc[i][j][e] + (bias ? (double)bias[n] : 0.0);
+            }
+    }
+}
+
+// the same product with the weights already widened to float64 (aligned operands only: K % 16 == 0, even lda / ldb)
+int gemm_f64d(cudaStream_t st, int M, int N, int K, const double* A, int lda, const double* B, int ldb, double* C,
+              int ldc, const float* bias) {
+    if (M <= 0 || N <= 0) return 0;
+    E2E_REQUIRE(K > 0 && K % PK == 0 && lda % 2 == 0 && ldb % 2 == 0 && ((uintptr_t)A & 15) == 0 && ((uintptr_t)B & 15) == 0,
+                "gemm_f64d: K %% 16 == 0 and 16-byte aligned rows required (K=%d lda=%d ldb=%d)", K, lda, ldb);
+    if (g_f64_mma)
+        gemm_f64_mma_kernel<<<dim3(cdiv(N, PT), cdiv(M, PT)), 128, 0, st>>>(M, N, K, A, lda, B, ldb, C, ldc, bias);
+    else
+        gemm_f64_pipe_kernel<double><<<dim3(cdiv(N, PT), cdiv(M, PT)), 128, 0, st>>>(M, N, K, A, lda, B, ldb, C, ldc, bias);
+    E2E_LAUNCH_CHECK();
+    return 0;
+}
+
 int gemm_f64(cudaStream_t st, int M, int N, int K, const double* A, int lda, const float* B, int ldb, double* C,
              int ldc, const float* bias) {
     if (M <= 0 || N <= 0) return 0;
     const bool aligned = K > 0 && K % PK == 0 && lda % 2 == 0 && ldb % 4 == 0 && ((uintptr_t)A & 15) == 0 &&
                          ((uintptr_t)B & 15) == 0;
     if (aligned)
-        gemm_f64_pipe_kernel<<<dim3(cdiv(N, PT), cdiv(M, PT)), 128, 0, st>>>(M, N, K, A, lda, B, ldb, C, ldc, bias);
+        gemm_f64_pipe_kernel<float><<<dim3(cdiv(N, PT), cdiv(M, PT)), 128, 0, st>>>(M, N, K, A, lda, B, ldb, C, ldc, bias);
     else
         gemm_f64_kernel<<<dim3(cdiv(N, GT), cdiv(M, GT)), 64, 0, st>>>(M, N, K, A, lda, B, ldb, C, ldc, bias);
     E2E_LAUNCH_CHECK();

@@ -97,6 +97,8 @@ int dec_deferred_attn_grads(cudaStream_t, const e2e_dec_persist_args&, float*, f
 int attn_bwd_step(cudaStream_t, int, int, int, int, int, const float*, const float*, const int*, const float*, const float*,
                   const float*, const float*, int, float*, float*);
 int gemm_f64(cudaStream_t, int, int, int, const double*, int, const float*, int, double*, int, const float*);
+int gemm_f64d(cudaStream_t, int, int, int, const double*, int, const double*, int, double*, int, const float*);
+extern int g_f64_mma;
 int lstm_step_f64(cudaStream_t, int, int, const double*, const double*, double*, double*, int);
 int attn_beam_group_f64(cudaStream_t, int, int, int, int, int, const float*, const float*, const int*, const int*,
                         const double*, const float*, double*, int);
@@ -424,6 +426,14 @@ int e2e_sample_rows(void* stream, int rows, int V, const float* logits, int ldl,
     return sample_rows(ST(stream), rows, V, logits, ldl, seed, offset, first_row, out);
 }
 
+int e2e_set_f64_mma(int on) {
+    g_f64_mma = on;
+    return 0;
+}
+int e2e_gemm_f64d(void* stream, int M, int N, int K, const double* A, int lda, const double* B, int ldb, double* C,
+                  int ldc, const float* bias) {
+    return gemm_f64d(ST(stream), M, N, K, A, lda, B, ldb, C, ldc, bias);
+}
 int e2e_gemm_f64(void* stream, int M, int N, int K, const double* A, int lda, const float* B, int ldb, double* C,
                  int ldc, const float* bias) {
     return gemm_f64(ST(stream), M, N, K, A, lda, B, ldb, C, ldc, bias);

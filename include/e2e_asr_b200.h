@@ -274,6 +274,13 @@ size_t e2e_ctc_workspace_floats(int T, int B, int max_label_len);
  * batched over every live hypothesis.  BasicLSTM.__call__ (basic_lstm.py:14-23),
  * calc_attention (beam_search.py:150-159, no length mask), get_top_k's
  * log-softmax + lm_weight term + top-k (beam_search.py:196-214). */
+/* e2e_gemm_f64 with the float32 weights widened to float64 once by the caller ((double)float is exact), on the FP64
+ * tensor cores (mma.sync m8n8k4 f64; the products of a k4 block are summed inside the tensor core, so the last bits
+ * differ from e2e_gemm_f64's sequential FMAs).  K % 16 == 0, even lda / ldb, 16-byte aligned A and B.
+ * e2e_set_f64_mma(0) selects the register-tiled DFMA kernel instead (bit-identical to e2e_gemm_f64; test hook). */
+int e2e_set_f64_mma(int on);
+int e2e_gemm_f64d(void* stream, int M, int N, int K, const double* A, int lda, const double* B, int ldb, double* C,
+                  int ldc, const float* bias);
 int e2e_gemm_f64(void* stream, int M, int N, int K, const double* A, int lda, const float* B, int ldb,
                  double* C, int ldc, const float* bias);
 int e2e_lstm_step_f64(void* stream, int n, int H, const double* z, const double* c_prev, double* c_out,

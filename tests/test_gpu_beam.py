@@ -166,6 +166,20 @@ def test_gemm_f64_matches_numpy(M, N, K, lda_pad):
     call("e2e_gemm_f64", M, N, K, ad, ad.stride(0), bd, bd.stride(0), out, out.stride(0), biasd)
     ref = a[:, :K] @ b.astype(np.float64) + bias.astype(np.float64)
     assert np.abs(out.cpu().numpy() - ref).max() <= 1e-12 * max(1.0, np.abs(ref).max())
+    if K % 16 == 0 and (K + lda_pad) % 2 == 0 and N % 2 == 0:
+        # the weights widened once by the caller
+        out_d = torch.full((M, N), float("nan"), dtype=torch.float64, device="cuda")
+        b64 = bd.to(torch.float64)
+        from e2e_asr_b200._lib import lib
+        lib().e2e_set_f64_mma(0)                 # register-tiled DFMA kernel: the same sums in the same order
+        try:
+            call("e2e_gemm_f64d", M, N, K, ad, ad.stride(0), b64, b64.stride(0), out_d, out_d.stride(0), biasd)
+        finally:
+            lib().e2e_set_f64_mma(1)
+        assert torch.equal(out, out_d)
+        out_t = torch.full((M, N), float("nan"), dtype=torch.float64, device="cuda")
+        call("e2e_gemm_f64d", M, N, K, ad, ad.stride(0), b64, b64.stride(0), out_t, out_t.stride(0), biasd)   # DMMA
+        assert np.abs(out_t.cpu().numpy() - ref).max() <= 1e-12 * max(1.0, np.abs(ref).max())
 
 
 @pytest.mark.gpu
