@@ -34,6 +34,8 @@
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
 
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace e2e {
@@ -621,6 +623,7 @@ bool set_stream_workspace(cudaStream_t st, void* ptr, size_t bytes) {
     g_stream_ws[g_n_stream_ws++] = StreamWs{st, ptr, bytes};
     return true;
 }
+int g_max_kblocks = 256;     // k-blocks (of 32 tf32 / 64 16-bit elements) per CTA before split-K kicks in; 0 = off
 void set_tc_debug(float* dbg, long long min_work) {
     g_dbg = dbg;
     g_min_work = min_work;
@@ -815,6 +818,18 @@ int gemm_tc(cudaStream_t st, int mode, int transA, int transB, int M, int N, int
     int splits = 1;
     const int nsm = sm_count();
     if (tiles * 2 <= nsm && kb_total >= 16) splits = min(nsm / tiles, kb_total / 8);
+    // very long K (the weight-gradient products: K = all frames of the batch): keep a CTA's life short.  These GEMMs run
+    // on side streams next to the cluster recurrences of the critical path, whose 16-CTA clusters need 16 EMPTY SMs of a
+    // GPC at once -- they wait for resident GEMM CTAs to retire, so a CTA that loops over all of K delays them by its
+    // whole run time.
+    {
+        static bool env_read = false;
+        if (!env_read) {
+            env_read = true;
+            if (const char* e = getenv("E2E_MAX_KBLOCKS")) g_max_kblocks = atoi(e);
+        }
+    }
+    if (g_max_kblocks > 0 && kb_total > 2 * g_max_kblocks) splits = max(splits, cdiv(kb_total, g_max_kblocks));
     if (splits < 1) splits = 1;
     p.kblocks_per_split = cdiv(kb_total, splits);
     splits = cdiv(kb_total, p.kblocks_per_split);

@@ -374,8 +374,8 @@ extern int g_rec_mc_ns;
 // lstm_rec_h512.cu when the workspace is large enough, else the cluster/DSMEM kernel, else the L2 kernel); 1 = always the L2 / global-barrier kernel; 2 = cluster/DSMEM or L2
 // kernel only; 3 / 4 = the non-specialised register-resident kernel (lstm_rec_mc.cu) with 1 / 2 interleaved
 // batch slices per cluster; 5 / 6 = the warp-specialised kernel with 1 / 2 slices forced (tests); 7 = the
-// warp-specialised kernel with the forward pass on the tf32 + bf16 scheme instead of the fp16 split scheme; 8 = the
-// warp-specialised kernel with the fp16 split scheme in the backward pass too
+// warp-specialised kernel with the forward pass on the tf32 + bf16 scheme instead of the fp16 split scheme; 8 = the same
+// for the backward pass (default: fp16 split scheme with per-row scaled dz tiles)
 int g_rec_mode = 0;
 extern int g_rec_fwd_f16, g_rec_bwd_f16;
 
@@ -400,7 +400,7 @@ int lstm_rec(cudaStream_t st, bool bwd, int B, int T, int Tp, int H, int ndir, l
     if (B <= 0 || T <= 0) return 0;
     if (g_rec_mode == 0 || (g_rec_mode >= 5 && g_rec_mode <= 8)) {
         g_rec_fwd_f16 = g_rec_mode != 7;
-        g_rec_bwd_f16 = g_rec_mode == 8;
+        g_rec_bwd_f16 = g_rec_mode != 8;
         int rc = lstm_rec_ws(st, bwd, B, T, Tp, H, ndir, sb, stt, G, Hout, Cst, Wh, dOut, lens, ctr_ws, ctr_ws_bytes,
                              (g_rec_mode == 5 || g_rec_mode == 6) ? g_rec_mode - 4 : 0, 0);
         if (rc >= 0) return rc;

@@ -254,11 +254,9 @@ __global__ void __launch_bounds__(NT5, 1) rec_bwd_h512_kernel(MParams p) {
     uint4* dz_s = reinterpret_cast<uint4*>(recv + 2 * CS5 * HT);         // [2][hi: 8 k16 x 32 lanes | lo': same] own dz fragments
     uint4* wl_s = dz_s + 2 * 512;                                        // [8 warps][8 k16][4 n-tile pairs][32 lanes]
     __shared__ __align__(8) uint64_t full[2];                            // the CS5 partial tiles of a step have arrived
-    __shared__ __align__(8) uint64_t dzready;                            // the epilogue warps have written dz_t
-    // the 8 MMA warps have seen dz_t: an epilogue warp may signal dz_{t+1} only then.  Its step t+1 needs just ONE partial
-    // tile from every CTA (the warp owning this CTA as a destination), so without this hand-shake dzready could complete
-    // two phases while a slow MMA warp (weight set-up at kernel start) has not yet tested the first -- parity aliasing
-    __shared__ __align__(8) uint64_t dzseen;
+    // the epilogue warps have written dz_t: two barriers alternating with the step, so that the barrier of step t cannot
+    // complete the phase of t+2 before every MMA warp has tested the phase of t (see lstm_rec_ws.cu)
+    __shared__ __align__(8) uint64_t dzready[2];
     __shared__ float rinv_s[2][R];                                       // 1 / (row scale) of the dz tile of a buffer
 
     const int ndir = p.ndir, T = p.T, Tp = p.Tp;
@@ -272,8 +270,8 @@ __global__ void __launch_bounds__(NT5, 1) rec_bwd_h512_kernel(MParams p) {
     if (tid == 0) {
         mbar_init(&full[0], 1);
         mbar_init(&full[1], 1);
-        mbar_init(&dzready, EW5);
-        mbar_init(&dzseen, 8);
+        mbar_init(&dzready[0], EW5);
+        mbar_init(&dzready[1], EW5);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         mbar_expect_tx(&full[0], CS5 * HT * 4);
         mbar_expect_tx(&full[1], CS5 * HT * 4);
@@ -317,12 +315,9 @@ __global__ void __launch_bounds__(NT5, 1) rec_bwd_h512_kernel(MParams p) {
             }
         }
         __syncwarp();
-        uint32_t dph = 0;
         for (int s = 0; s + 1 < T; ++s) {
             const int buf = s & 1;
-            mbar_wait(&dzready, dph);
-            dph ^= 1u;
-            if (lane == 0) mbar_arrive5(&dzseen);
+            mbar_wait(&dzready[buf], (uint32_t)((s >> 1) & 1));
             const uint4* dzb = dz_s + buf * 512 + lane;
             const float r0s = rinv_s[buf][g], r1s = rinv_s[buf][g + 8];
 #pragma unroll
@@ -481,10 +476,7 @@ __global__ void __launch_bounds__(NT5, 1) rec_bwd_h512_kernel(MParams p) {
                     }
                 }
                 __syncwarp();
-                if (lane == 0) {
-                    if (s > 0) mbar_wait(&dzseen, (uint32_t)((s - 1) & 1));     // the MMA warps have taken dz_{s-1}
-                    mbar_arrive5(&dzready);
-                }
+                if (lane == 0) mbar_arrive5(&dzready[buf]);
             }
 #pragma unroll
             for (int j = 0; j < 2; ++j) {

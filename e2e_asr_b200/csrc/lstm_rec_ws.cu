@@ -326,11 +326,12 @@ __global__ void __launch_bounds__(256 + 32 * EW, 1) rec_bwd_ws_kernel(MParams p)
     float* stage = recv + NS * 2 * CS * TILE;                    // [NS][2][CS][TILE] partial tiles to send
     float* dz_s = stage + NS * 2 * CS * TILE;                    // [NS][2][8 k-tiles][32 chunks][4] own dz, fragment order
     __shared__ __align__(8) uint64_t full[NS][2];                // the CS partial tiles of a step have arrived
-    __shared__ __align__(8) uint64_t dzready[NS];                // the 4 epilogue warps have written dz_t
-    // the 8 MMA warps have seen dz_t: an epilogue warp signals dz_{t+1} only then.  Its step t+1 needs just ONE partial tile
-    // from every CTA (the warp that owns this CTA as a destination), so without this hand-shake dzready could complete two
-    // phases while a slow MMA warp (weight set-up at kernel start) has not yet tested the first -- parity aliasing
-    __shared__ __align__(8) uint64_t dzseen[NS];
+    // the epilogue warps have written dz_t: TWO barriers per slice, alternating with the step.  An epilogue warp's step
+    // t+1 needs just ONE partial tile from every CTA (the MMA warp that owns this CTA as a destination), so with a single
+    // barrier it could complete the phase of t+1 while a slow MMA warp of its own CTA (weight set-up at kernel start) has
+    // not yet tested the phase of t -- the warp would then wait for a completion that depends on itself.  Step t+2 needs
+    // every warp's step-t tiles, so a barrier that is signalled only every other step can never run a phase ahead.
+    __shared__ __align__(8) uint64_t dzready[NS][2];
     __shared__ float rinv_s[NS][2][R];                           // F16: 1 / (row scale) of the dz tile of (slice, buffer)
 
     const int ndir = p.ndir, T = p.T, Tp = p.Tp;
@@ -346,8 +347,8 @@ __global__ void __launch_bounds__(256 + 32 * EW, 1) rec_bwd_ws_kernel(MParams p)
         for (int sl = 0; sl < NS; ++sl) {
             mbar_init(&full[sl][0], 1);
             mbar_init(&full[sl][1], 1);
-            mbar_init(&dzready[sl], EW);
-            mbar_init(&dzseen[sl], 8);
+            mbar_init(&dzready[sl][0], EW);
+            mbar_init(&dzready[sl][1], EW);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 #pragma unroll
@@ -419,7 +420,6 @@ __global__ void __launch_bounds__(256 + 32 * EW, 1) rec_bwd_ws_kernel(MParams p)
                     bl[2 * q + 1][nt][1] = pack_bf16(r[1][0], r[1][1]);
                 }
         }
-        uint32_t dph = 0;
         for (int s = 0; s + 1 < T; ++s) {
             const int buf = s & 1;
 #pragma unroll
@@ -430,9 +430,7 @@ __global__ void __launch_bounds__(256 + 32 * EW, 1) rec_bwd_ws_kernel(MParams p)
                 for (int nt = 0; nt < NTL; ++nt)
 #pragma unroll
                     for (int q = 0; q < 4; ++q) { acc[nt][q] = 0.f; accx[nt][q] = 0.f; }
-                mbar_wait(&dzready[sl], (dph >> sl) & 1u);
-                dph ^= 1u << sl;
-                if (lane == 0) mbar_arrive(&dzseen[sl]);
+                mbar_wait(&dzready[sl][buf], (uint32_t)((s >> 1) & 1));
                 const float* dzs = dz_s + (size_t)(sl * 2 + buf) * 8 * 128;
                 if (F16) {
                     // [hi fragments of the 4 k16 pairs: 4 x 512 B | lo' fragments], already in register order
@@ -608,10 +606,7 @@ __global__ void __launch_bounds__(256 + 32 * EW, 1) rec_bwd_ws_kernel(MParams p)
                         }
                     }
                     __syncwarp();
-                    if (lane == 0) {
-                        if (s > 0) mbar_wait(&dzseen[sl], (uint32_t)((s - 1) & 1));     // the MMA warps have taken dz_{s-1}
-                        mbar_arrive(&dzready[sl]);
-                    }
+                    if (lane == 0) mbar_arrive(&dzready[sl][buf]);
                 } else if (s + 1 < T) {
                     // own dz tile in fragment order [k-tile = ul/2][16-byte chunk (r0*4 + gate) ^ k-tile][2 (ul%2) + row/8]:
                     // the thread's two rows are the adjacent floats of one slot pair
@@ -629,10 +624,7 @@ __global__ void __launch_bounds__(256 + 32 * EW, 1) rec_bwd_ws_kernel(MParams p)
                         dq[((c0 + 3) ^ kx) * 4] = dz[0].w;
                     }
                     __syncwarp();
-                    if (lane == 0) {
-                        if (s > 0) mbar_wait(&dzseen[sl], (uint32_t)((s - 1) & 1));     // the MMA warps have taken dz_{s-1}
-                        mbar_arrive(&dzready[sl]);
-                    }
+                    if (lane == 0) mbar_arrive(&dzready[sl][buf]);
                 }
 #pragma unroll
                 for (int j = 0; j < NR; ++j) {
@@ -653,10 +645,9 @@ size_t bwd_ws_smem(int CS, int NS) { return sizeof(float) * ((size_t)NS * 4 * CS
 
 }  // namespace
 int g_rec_fwd_f16 = 1;      // forward recurrence: 1 = fp16 split scheme, 0 = tf32 + bf16 scheme (test mode 7)
-// backward recurrence: 0 = tf32 + bf16 scheme; 1 = fp16 split scheme with per-row scaled dz tiles (test mode 8).  Measured
-// at cfg-2: 2.197 vs 2.185 us per timestep -- the backward step is bound by the reduce-scatter of the partial d h tiles
-// and the epilogue, not by MMA issue, so the 25 % fewer MMAs buy nothing and the proven scheme stays the default.
-int g_rec_bwd_f16 = 0;
+// backward recurrence: 1 = fp16 split scheme with per-row scaled dz tiles, 0 = tf32 + bf16 scheme (test mode 8).  Measured
+// alone at cfg-2 (B = 64, T = 700): 1.95 vs 2.11 us per timestep.
+int g_rec_bwd_f16 = 1;
 
 namespace {
 

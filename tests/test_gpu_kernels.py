@@ -60,8 +60,8 @@ def test_gemm_strided_views():
 def test_bilstm_layer_fwd_bwd(B, T_, I, H, rec_mode):
     """rec_mode 0 = fastest eligible recurrence, 1 = L2-exchange kernel, 2 = cluster/DSMEM kernel,
     3 / 4 = register-resident multicast kernel with 1 / 2 interleaved batch slices per cluster,
-    5 / 6 = its warp-specialised version, 7 = with the forward pass on the tf32 + bf16 products instead of the fp16 split
-    scheme, 8 = with the fp16 split scheme (per-row scaled dz tiles) in the backward pass too.
+    5 / 6 = its warp-specialised version, 7 / 8 = with the forward / backward pass on the tf32 + bf16 products instead of
+    the fp16 split scheme (backward: per-row scaled dz tiles).
     H = 512 under mode 0 runs the kernels of lstm_rec_h512.cu (W_hh hi plane in registers, lo plane in shared memory;
     130 rows = 18 clusters of 16, more than are co-resident)."""
     if rec_mode >= 3 and H not in (128, 256):
