@@ -135,6 +135,20 @@ class Encoder(BaseParams):
         if self.isTraining is False:
             x = x.detach()
 
+        if params.use_lstm and x.is_cuda and max_depth > 1:
+            # the weights of the layers above the first are packed on a side stream while layer 1 runs
+            pre, in_size, r = [], x.shape[2], res
+            nd = 2 if params.bi_dir else 1
+            for i in range(max_depth):
+                if i > 0:
+                    kv = self._layer_vars(i + 1, in_size)
+                    pre.append(([kv[0], kv[2]][:nd], [kv[1], kv[3]][:nd], in_size, params.hidden_size))
+                in_size = nd * params.hidden_size
+                if params.skip_step > 1 and i != (max_depth - 1) and r < params.max_scaling_down:
+                    in_size *= 2
+                    r *= params.skip_step
+            ops.prepack_lstm(pre, dev)
+
         T_l = T
         for i in range(max_depth):
             layer_depth = i + 1
