@@ -698,7 +698,13 @@ int split_lo(cudaStream_t st, int mode, size_t n, const float* x, float* lo) {
         E2E_LAUNCH_CHECK();
         return 0;
     }
-    split_lo_kernel<<<(unsigned)min((size_t)148 * 8, (n / 4 + 255) / 256), 256, 0, st>>>(n / 4, (const float4*)x, (float4*)lo);
+    // short-lived CTAs (4 float4 per thread), not a resident grid-stride loop: these splits run on side streams, and a
+    // CTA that stays resident for the whole pass keeps its SM from the 16-CTA clusters of the recurrence on the
+    // critical path (they need EMPTY SMs) -- with many short CTAs the higher-priority clusters get in as SMs drain
+    static int g_split_grid_stride = -1;
+    if (g_split_grid_stride < 0) g_split_grid_stride = getenv("E2E_SPLIT_GRID_STRIDE") ? atoi(getenv("E2E_SPLIT_GRID_STRIDE")) : 0;
+    const size_t want = g_split_grid_stride ? (size_t)148 * 8 : (n / 4 + 1023) / 1024;
+    split_lo_kernel<<<(unsigned)min(want, (size_t)1 << 30), 256, 0, st>>>(n / 4, (const float4*)x, (float4*)lo);
     E2E_LAUNCH_CHECK();
     return 0;
 }
