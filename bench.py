@@ -198,7 +198,11 @@ def workload_config(name, n_gpus, note=None, batch_per_gpu=None, settings=None):
 #     other slice -> max(2048, 1416) = 2048
 #   recurrence, one slice per cluster (NS = 1, the LM-LSTM): k-loop 1024 + exchange 910 back to back = 1934
 #   decoder loop: three grid-wide barriers per step, 2600 cycles each (128 co-resident CTAs, one L2 atomic + poll)
-FLOOR_CYCLES = {"enc_rec_fwd": 2048, "enc_rec_bwd": 2048, "lm_rec_fwd": 1934, "lm_rec_bwd": 1934,
+# latency floors in cycles per timestep: fp16 split scheme = 768 cycles of MMA issue per slice-step
+# (3 x m16n8k16 per k16 and n-tile at one MMA per 2 cycles per SM); encoder layers interleave two slices per cluster
+# (2 x 768, the exchange hides behind the other slice), the LM-LSTM runs one slice per cluster (768 + the exchange:
+# 910-cycle multicast forward, 1416 cycles of bulk DSMEM copies backward)
+FLOOR_CYCLES = {"enc_rec_fwd": 1536, "enc_rec_bwd": 1536, "lm_rec_fwd": 1678, "lm_rec_bwd": 2184,
                 "e2e_decoder_persist_fwd": 7800, "e2e_decoder_persist_bwd": 7800}
 KERNEL_OF = {"enc_rec_fwd": "rec_fwd_ws_kernel<16,2,8>", "enc_rec_bwd": "rec_bwd_ws_kernel<16,2,8>",
              "lm_rec_fwd": "rec_fwd_ws_kernel<16,1,4>", "lm_rec_bwd": "rec_bwd_ws_kernel<16,1,4>",

@@ -1,8 +1,7 @@
-for rep in 1 2; do for gs in 0 1; do
-E2E_SPLIT_GRID_STRIDE=$gs timeout 300 python bench.py --steps 20 --warmup 5 --no-beam --no-cpu-baseline > gpurun_out/r3a_$gs.json 2> gpurun_out/r3a.err
-python - <<P
-import json
-d=json.loads(open("gpurun_out/r3a_$gs.json").read().strip().splitlines()[-1]); b=d["breakdown"]
-print("gridstride=$gs", round(d["ms_per_step"],3), round(d["e2e"]["value"]), {k:round(b[k]["main_stream_ms_per_step"],3) for k in ("enc_rec_bwd","enc_rec_fwd","e2e_gemm")}, round(b["e2e_split_lo"]["ms_per_step"],3))
-P
-done; done
+run() { name=$1; shift; timeout 400 python bench.py "$@" > gpurun_out/r3c_$name.json 2> gpurun_out/r3c_$name.err; echo "$name rc=$?"; tail -1 gpurun_out/r3c_$name.json | python -c "import sys,json; d=json.loads(sys.stdin.read()); print('  ', round(d['ms_per_step'],3), round(d['value']), round(d['e2e']['value']))"; }
+run default --steps 20 --warmup 5
+run tf32x3 --steps 10 --warmup 3 --gemm tf32x3 --no-beam --no-cpu-baseline
+run cfg4 --steps 10 --warmup 3 --config cfg4 --no-beam --no-cpu-baseline
+run cfg5 --steps 5 --warmup 3 --config cfg5 --no-beam --no-cpu-baseline
+run dropout --steps 10 --warmup 3 --dropout --no-beam --no-cpu-baseline
+run defaults --steps 10 --warmup 3 --defaults --no-beam --no-cpu-baseline
