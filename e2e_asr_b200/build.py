@@ -7,7 +7,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libe2e_asr_b200.so")
-SOURCES = ["c_api.cu", "gemm_simt.cu", "gemm_tc.cu", "lstm_rec.cu", "lstm_rec_cluster.cu", "lstm_rec_mc.cu", "lstm_rec_ws.cu", "lstm_rec_h512.cu", "gru_rec.cu", "cell_point.cu", "decoder.cu", "decoder_persist.cu", "beam.cu", "loss.cu", "misc.cu"]
+SOURCES = ["c_api.cu", "gemm_simt.cu", "gemm_tc.cu", "lstm_rec.cu", "lstm_rec_ws.cu", "lstm_rec_h512.cu", "gru_rec.cu", "cell_point.cu", "decoder.cu", "decoder_persist.cu", "beam.cu", "loss.cu", "misc.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr"]
 

@@ -361,22 +361,17 @@ static size_t rec_smem(bool bwd, int RT, int UPC, int H) {
     return sizeof(float) * ((size_t)(UPC + R) * (4 * H + 4));
 }
 
-int lstm_rec_cluster(cudaStream_t, bool, int, int, int, int, int, long long, long long, float*, float*, float*,
-                     const float*, const float*, const int*);
-int lstm_rec_mc(cudaStream_t, bool, int, int, int, int, int, long long, long long, float*, float*, float*,
-                const float*, const float*, const int*, void*, size_t);
 int lstm_rec_ws(cudaStream_t, bool, int, int, int, int, int, long long, long long, float*, float*, float*,
                 const float*, const float*, const int*, void*, size_t, int, int);
 int lstm_rec_h512(cudaStream_t, bool, int, int, int, int, int, long long, long long, float*, float*, float*,
                   const float*, const float*, const int*, void*, size_t);
-extern int g_rec_mc_ns;
-// 0 = fastest eligible kernel (warp-specialised register-resident kernel for H in {128,256}, the H = 512 kernel of
-// lstm_rec_h512.cu when the workspace is large enough, else the cluster/DSMEM kernel, else the L2 kernel); 1 = always the L2 / global-barrier kernel; 2 = cluster/DSMEM or L2
-// kernel only; 3 / 4 = the non-specialised register-resident kernel (lstm_rec_mc.cu) with 1 / 2 interleaved
-// batch slices per cluster; 5 / 6 = the warp-specialised kernel with 1 / 2 slices forced (tests); 7 = the
-// warp-specialised kernel with the forward pass on the tf32 + bf16 scheme instead of the fp16 split scheme; 8 = the same
-// for the backward pass (default: fp16 split scheme with per-row scaled dz tiles)
+// 0 = fastest eligible kernel (warp-specialised register-resident cluster kernel for H in {128, 256}, the H = 512
+// kernel of lstm_rec_h512.cu when the workspace is large enough, else the L2-exchange kernel below); 1 = always the L2
+// kernel; 5 / 6 = the warp-specialised kernel with 1 / 2 slices per cluster forced (tests); 7 / 8 = the warp-specialised
+// kernel with the forward / backward pass on the tf32 + bf16 scheme instead of the fp16 split scheme.  (2 - 4 selected
+// two earlier kernel generations, removed: they behave like 0.)
 int g_rec_mode = 0;
+long long* g_rec_dbg = nullptr;     // e2e_set_rec_debug: clock64 stamps of the forward cluster kernel / the decoder loop
 extern int g_rec_fwd_f16, g_rec_bwd_f16;
 
 // forward-only layer continuing a sequence (cell state carried in from Cst at time -1): the warp-specialised kernel only
@@ -398,25 +393,16 @@ int lstm_rec(cudaStream_t st, bool bwd, int B, int T, int Tp, int H, int ndir, l
     E2E_REQUIRE(ndir == 1 || ndir == 2, "lstm_rec: ndir must be 1 or 2");
     E2E_REQUIRE(Tp >= T, "lstm_rec: Tp (%d) must be >= T (%d)", Tp, T);
     if (B <= 0 || T <= 0) return 0;
-    if (g_rec_mode == 0 || (g_rec_mode >= 5 && g_rec_mode <= 8)) {
+    if (g_rec_mode != 1) {
         g_rec_fwd_f16 = g_rec_mode != 7;
         g_rec_bwd_f16 = g_rec_mode != 8;
         int rc = lstm_rec_ws(st, bwd, B, T, Tp, H, ndir, sb, stt, G, Hout, Cst, Wh, dOut, lens, ctr_ws, ctr_ws_bytes,
                              (g_rec_mode == 5 || g_rec_mode == 6) ? g_rec_mode - 4 : 0, 0);
         if (rc >= 0) return rc;
     }
-    if (g_rec_mode == 0) {
+    if (g_rec_mode != 1) {
         int rc = lstm_rec_h512(st, bwd, B, T, Tp, H, ndir, sb, stt, G, Hout, Cst, Wh, dOut, lens, ctr_ws, ctr_ws_bytes);
         if (rc >= 0) return rc;
-    }
-    if (g_rec_mode == 0 || g_rec_mode == 3 || g_rec_mode == 4) {
-        g_rec_mc_ns = g_rec_mode == 0 ? 0 : g_rec_mode - 2;
-        int rc = lstm_rec_mc(st, bwd, B, T, Tp, H, ndir, sb, stt, G, Hout, Cst, Wh, dOut, lens, ctr_ws, ctr_ws_bytes);
-        if (rc >= 0) return rc;
-    }
-    if (g_rec_mode != 1) {
-        int rc = lstm_rec_cluster(st, bwd, B, T, Tp, H, ndir, sb, stt, G, Hout, Cst, Wh, dOut, lens);
-        if (rc >= 0) return rc;     // launched (0) or failed (>0); -1 = not eligible -> fall through
     }
     const int UPC = (H % 16 == 0) ? 16 : 8;
     const int nslices = H / UPC;

@@ -1,9 +1,11 @@
-// Warp-specialised register-resident LSTM recurrence (H in {128, 256}): the same decomposition, fragment
-// layouts and exchanges as lstm_rec_mc.cu, but the k-loop and the pointwise/publish work of a step run on
+// Warp-specialised register-resident LSTM recurrence (H in {128, 256}).  One 16-row batch slice of one direction is
+// owned by a cluster of CS = H / 16 CTAs; CTA j owns hidden units [16 j, 16 j + 16) = 64 gate columns of W_hh, held as
+// MMA fragments in registers for the whole sequence; the h_t / d h tiles are exchanged in fragment order (multicast
+// bulk copy forward, bulk DSMEM reduce-scatter backward).  The k-loop and the pointwise / publish work of a step run on
 // DIFFERENT warps of the CTA, so they overlap instead of adding up.
 //
-// Measured on lstm_rec_mc.cu (cfg-2, two interleaved slices per cluster, cycles per slice-step): k-loop 1330,
-// everything else (k-half combine, gates, publish, global stores) 1070 -- executed back to back by the same
+// Measured on the non-specialised predecessor (cfg-2, two interleaved slices per cluster, cycles per slice-step):
+// k-loop 1330, everything else (k-half combine, gates, publish, global stores) 1070 -- executed back to back by the same
 // 8 warps, 4800 per step for the two slices, tensor pipe 42 % busy.  Here
 //   warps 0..7  (2 warpgroups, setmaxnreg 216) hold W_hh as fragments and only run k-loops: for every slice
 //               wait for h_{t-1} / dz_t, 64 MMAs per warp, hand the partial tile to the epilogue warps;

@@ -1,4 +1,4 @@
-// Shared device helpers of the register-resident LSTM recurrence kernels (lstm_rec_mc.cu, lstm_rec_ws.cu):
+// Shared device helpers of the register-resident LSTM recurrence kernels (lstm_rec_ws.cu, lstm_rec_h512.cu):
 // cluster / mbarrier / bulk-copy PTX wrappers, the 3xTF32 and mixed tf32+bf16 fragment products.
 #pragma once
 #include <cuda_bf16.h>

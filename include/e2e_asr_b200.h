@@ -103,11 +103,9 @@ int e2e_lstm_unpack_grads(void* stream, int I, int H, float* dkernel, float* dbi
  * step barrier ever times out. */
 /* 0 (default): fastest eligible kernel -- the warp-specialised register-resident multicast-cluster
  * recurrence for H in {128, 256}, its H = 512 form (W_hh hi plane in registers, lo plane in shared memory; 64 KB of
- * workspace per CTA for the backward reduce-scatter), else the cluster / DSMEM recurrence when H/16
- * is 1,2,4,8 or 16, else the L2-exchange kernel with per-group global counters;
- * 1: always the L2-exchange kernel; 2: cluster / DSMEM or L2 kernel only;
- * 3 / 4: non-specialised register-resident kernel with 1 / 2 interleaved batch slices per cluster;
- * 5 / 6: warp-specialised kernel with 1 / 2 slices (test hooks). */
+ * workspace per CTA for the backward reduce-scatter), else the L2-exchange kernel with per-group global counters;
+ * 1: always the L2-exchange kernel; 5 / 6: warp-specialised kernel with 1 / 2 slices per cluster; 7 / 8: its forward /
+ * backward pass on the tf32 + bf16 products instead of the fp16 split scheme (test hooks). */
 int e2e_set_rec_mode(int mode);
 /* test hook: device buffer (>= 5*T int64) receiving per-step clock64 stamps of the forward cluster kernel, or NULL */
 int e2e_set_rec_debug(long long* dbg);

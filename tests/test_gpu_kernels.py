@@ -53,19 +53,18 @@ def test_gemm_strided_views():
     assert relerr(cs, big[:, 8:24].cpu().numpy().sum(0)) < 2e-5
 
 
-@pytest.mark.parametrize("rec_mode", [0, 1, 2, 3, 4, 5, 6, 7, 8])
+@pytest.mark.parametrize("rec_mode", [0, 1, 5, 6, 7, 8])
 @pytest.mark.parametrize("B,T_,I,H", [(3, 11, 6, 8), (5, 20, 12, 16), (17, 9, 40, 24), (4, 30, 40, 256),
                                       (70, 6, 16, 32), (33, 25, 24, 128), (64, 40, 16, 256), (130, 7, 8, 256),
                                       (20, 9, 12, 512), (130, 5, 8, 512), (16, 33, 8, 512)])
 def test_bilstm_layer_fwd_bwd(B, T_, I, H, rec_mode):
-    """rec_mode 0 = fastest eligible recurrence, 1 = L2-exchange kernel, 2 = cluster/DSMEM kernel,
-    3 / 4 = register-resident multicast kernel with 1 / 2 interleaved batch slices per cluster,
-    5 / 6 = its warp-specialised version, 7 / 8 = with the forward / backward pass on the tf32 + bf16 products instead of
-    the fp16 split scheme (backward: per-row scaled dz tiles).
+    """rec_mode 0 = fastest eligible recurrence, 1 = L2-exchange kernel, 5 / 6 = the warp-specialised cluster kernel with
+    1 / 2 interleaved batch slices per cluster, 7 / 8 = with the forward / backward pass on the tf32 + bf16 products
+    instead of the fp16 split scheme (backward: per-row scaled dz tiles).
     H = 512 under mode 0 runs the kernels of lstm_rec_h512.cu (W_hh hi plane in registers, lo plane in shared memory;
     130 rows = 18 clusters of 16, more than are co-resident)."""
-    if rec_mode >= 3 and H not in (128, 256):
-        pytest.skip("multicast recurrence serves H in {128, 256}")
+    if rec_mode >= 5 and H not in (128, 256):
+        pytest.skip("the warp-specialised cluster recurrence serves H in {128, 256}")
     from e2e_asr_b200 import _lib
     _lib.lib().e2e_set_rec_mode(rec_mode)
     try:
