@@ -1,4 +1,4 @@
-timeout 1000 python -m pytest tests -m gpu -q > gpurun_out/r3e_full.log 2>&1; echo "suite rc=$?"; grep -v "^frame" gpurun_out/r3e_full.log | tail -2 | cut -c1-200
-timeout 400 python bench.py --steps 10 --warmup 3 --no-beam --no-cpu-baseline > gpurun_out/r3e_bench.json 2> gpurun_out/r3e_bench.err; echo "bench rc=$?"
-tail -1 gpurun_out/r3e_bench.json | python -c "import sys,json; d=json.loads(sys.stdin.read()); print(round(d['ms_per_step'],3), round(d['value']), round(d['e2e']['value']))"
-python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -1
+sed -i 's/for B in \[16, 32, 48, 56, 64, 112, 128, 256\]:/for B in [112]:/' scratch/time_rec512.py
+PYTHONPATH=. timeout 300 python scratch/time_rec512.py 2>&1 | tail -2
+PYTHONPATH=. timeout 400 ncu --set full --clock-control none --import-source on -k regex:rec_fwd_h512 -c 1 -f -o gpurun_out/prof_rec_fwd_h512_r2f python scratch/time_rec512.py > gpurun_out/ncu_h512f.log 2>&1; echo "rc=$?"
+PYTHONPATH=. timeout 400 ncu --set full --clock-control none --import-source on -k regex:rec_bwd_h512 -c 1 -f -o gpurun_out/prof_rec_bwd_h512_r2f python scratch/time_rec512.py > gpurun_out/ncu_h512b.log 2>&1; echo "rc=$?"
