@@ -1,4 +1,2 @@
-sed -i 's/for B in \[16, 32, 48, 56, 64, 112, 128, 256\]:/for B in [112]:/' scratch/time_rec512.py
-PYTHONPATH=. timeout 300 python scratch/time_rec512.py 2>&1 | tail -2
-PYTHONPATH=. timeout 400 ncu --set full --clock-control none --import-source on -k regex:rec_fwd_h512 -c 1 -f -o gpurun_out/prof_rec_fwd_h512_r2f python scratch/time_rec512.py > gpurun_out/ncu_h512f.log 2>&1; echo "rc=$?"
-PYTHONPATH=. timeout 400 ncu --set full --clock-control none --import-source on -k regex:rec_bwd_h512 -c 1 -f -o gpurun_out/prof_rec_bwd_h512_r2f python scratch/time_rec512.py > gpurun_out/ncu_h512b.log 2>&1; echo "rc=$?"
+timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node 4 --master-addr 127.0.0.1 --master-port 29514 bench.py --gpus 4 --steps 10 --warmup 3 > gpurun_out/r3f_n4.json 2> gpurun_out/r3f_n4.err; echo "rc=$?"
+tail -1 gpurun_out/r3f_n4.json | python -c "import sys,json; d=json.loads(sys.stdin.read()); print(d['n_gpus'], d['ms_per_step'], d['value'], d['e2e']['value'])"
