@@ -76,6 +76,49 @@ def merge_candidates(utt, scores, k_u, idx_h, val_h, step, word_ins_penalty):
     return dict(utt=u_all[keep], parent=par_all[keep], tok=tok_all[keep], score=sc_all[keep]), finished
 
 
+def best_sequences(par_hist, tok_hist, fin_cnt, fin_step, fin_row, fin_score, alive, score, beam):
+    """The decoded ids of every utterance from the device's history (host side, vectorised over utterances).
+
+    Candidates in the reference's order -- EOS-retired hypotheses as they finished, then the leftovers
+    (beam_search.py:332) -- the best is the FIRST maximum, no length normalisation (:336); only that one is traced
+    back through the back-pointers.  par_hist / tok_hist: [steps, R] parent row and token of every slot per step;
+    finished hypothesis f of utterance u sits at index u*beam + f of fin_step (the number of steps it took, EOS
+    excluded), fin_row (the row holding its last token at step fin_step - 1) and fin_score.
+    Returns (list of int64 id arrays incl. the trailing EOS of a finished hypothesis, list of scores)."""
+    steps, R = tok_hist.shape
+    N = R // beam
+    slot = np.arange(beam)
+    rows = np.arange(R).reshape(N, beam)
+    valid = np.concatenate([slot[None, :] < np.asarray(fin_cnt).reshape(N, 1),
+                            np.asarray(alive).reshape(N, beam) != 0], axis=1)
+    cand = np.concatenate([np.asarray(fin_score, np.float64).reshape(N, beam),
+                           np.asarray(score, np.float64).reshape(N, beam)], axis=1)
+    if not valid.any(axis=1).all():
+        raise RuntimeError("beam search: an utterance ended without any hypothesis")
+    # first maximum among the valid candidates (np.argmax returns the first; invalid entries can never win: a valid
+    # entry exists, and ties at -inf resolve to the first VALID one below)
+    masked = np.where(valid, cand, -np.inf)
+    best = np.argmax(masked, axis=1)
+    first_valid = np.argmax(valid, axis=1)
+    best = np.where(np.isneginf(masked[np.arange(N), best]), first_valid, best)
+    is_fin = best < beam
+    idx = rows[np.arange(N), np.where(is_fin, best, best - beam)]
+    t_start = np.where(is_fin, np.asarray(fin_step)[idx].astype(np.int64) - 1, steps - 1)
+    row = np.where(is_fin, np.asarray(fin_row)[idx], idx).astype(np.int64)
+    best_sc = masked[np.arange(N), best]
+    toks = np.full((N, max(steps, 1)), -1, np.int64)
+    for t in range(int(t_start.max()) if N else -1, -1, -1):
+        act = np.nonzero(t_start >= t)[0]
+        r = row[act]
+        toks[act, t] = tok_hist[t, r]
+        row[act] = par_hist[t, r]
+    outs = []
+    for u in range(N):
+        seq = toks[u, :t_start[u] + 1]
+        outs.append(np.concatenate([seq, [EOS_ID]]).astype(np.int64) if is_fin[u] else seq.copy())
+    return outs, [float(v) for v in best_sc]
+
+
 class BeamSearch(BaseParams):
     """Implementation of beam search for the attention decoder."""
 
@@ -355,36 +398,10 @@ class BeamSearch(BaseParams):
                 step_fn()
             steps_done += 1
 
-        # ---- host: rebuild the sequences from the back-pointers
+        # ---- host: rebuild the best sequence of every utterance from the back-pointers
         ph, th = par_hist[:steps_done].cpu().numpy(), tok_hist[:steps_done].cpu().numpy()
         fc, fs, fr, fsc = (t.cpu().numpy() for t in (fin_cnt, fin_step, fin_row, fin_score))
-        alive_h, score_h = alive.cpu().numpy(), score.cpu().numpy()
-
-        def backtrack(t, row):
-            seq = []
-            while t >= 0:
-                seq.append(int(th[t, row]))
-                row = int(ph[t, row])
-                t -= 1
-            return seq[::-1]
-
-        outs, outs_sc = [], []
-        for u in range(N):
-            # candidates in the reference's order: EOS-retired hypotheses as they finished, then the leftovers
-            # (beam_search.py:332); the best is the FIRST maximum, no length normalisation (:336) -- only that one is
-            # traced back through the back-pointers
-            best, best_sc = None, None
-            for f in range(int(fc[u])):
-                i = u * beam + f
-                if best is None or fsc[i] > best_sc:
-                    best, best_sc = (int(fs[i]) - 1, int(fr[i]), True), float(fsc[i])
-            for slot in range(beam):
-                row = u * beam + slot
-                if alive_h[row] and (best is None or score_h[row] > best_sc):
-                    best, best_sc = (steps_done - 1, row, False), float(score_h[row])
-            seq = backtrack(best[0], best[1]) + ([EOS_ID] if best[2] else [])
-            outs.append(np.asarray(seq, np.int64))
-            outs_sc.append(best_sc)
+        outs, outs_sc = best_sequences(ph, th, fc, fs, fr, fsc, alive.cpu().numpy(), score.cpu().numpy(), beam)
         return (outs, outs_sc) if return_scores else outs
 
     @classmethod

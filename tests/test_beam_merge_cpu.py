@@ -82,3 +82,59 @@ def test_vectorised_merge_equals_reference_loop(N, beam, V, seed, ties):
         utt_l, seqs_l, scores_l = nu, ns, nsc
         utt, scores = new["utt"], new["score"]
     assert any(len(f) for f in final)                    # EOS really retired some hypotheses
+
+
+def _loop_best_sequences(ph, th, fc, fs, fr, fsc, alive_h, score_h, beam):
+    """The per-utterance Python loop `best_sequences` replaced (first maximum over finals then leftovers, one
+    back-pointer walk per utterance)."""
+    steps_done, R = th.shape
+    N = R // beam
+
+    def backtrack(t, row):
+        seq = []
+        while t >= 0:
+            seq.append(int(th[t, row]))
+            row = int(ph[t, row])
+            t -= 1
+        return seq[::-1]
+
+    outs, scs = [], []
+    for u in range(N):
+        best, best_sc = None, None
+        for f in range(int(fc[u])):
+            i = u * beam + f
+            if best is None or fsc[i] > best_sc:
+                best, best_sc = (int(fs[i]) - 1, int(fr[i]), True), float(fsc[i])
+        for slot in range(beam):
+            row = u * beam + slot
+            if alive_h[row] and (best is None or score_h[row] > best_sc):
+                best, best_sc = (steps_done - 1, row, False), float(score_h[row])
+        outs.append(np.asarray(backtrack(best[0], best[1]) + ([EOS_ID] if best[2] else []), np.int64))
+        scs.append(best_sc)
+    return outs, scs
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_best_sequences_matches_per_utterance_loop(seed):
+    from e2e_asr_b200.beam_search import best_sequences
+    rng = np.random.default_rng(seed)
+    N, beam, S = 17, [1, 4, 10][seed % 3], [1, 9, 40][seed % 3]
+    R = N * beam
+    base = (np.arange(R) // beam * beam).astype(np.int32)
+    ph = (rng.integers(0, beam, (S, R)) + base[None, :]).astype(np.int32)
+    th = rng.integers(3, 50, (S, R)).astype(np.int32)
+    fc = rng.integers(0, beam + 1, N).astype(np.int32)
+    alive = rng.integers(0, 2, R).astype(np.int32)
+    for u in range(N):                          # every utterance keeps at least one candidate
+        if fc[u] == 0 and not alive[u * beam:(u + 1) * beam].any():
+            alive[u * beam] = 1
+    fs = rng.integers(0, S + 1, R).astype(np.int32)          # 0: EOS was the first token
+    fr = (rng.integers(0, beam, R) + base).astype(np.int32)
+    # coarse scores: ties between finals and leftovers must resolve to the FIRST maximum
+    fsc = rng.integers(-3, 3, R).astype(np.float64)
+    score = rng.integers(-3, 3, R).astype(np.float64)
+    got, got_sc = best_sequences(ph, th, fc, fs, fr, fsc, alive, score, beam)
+    want, want_sc = _loop_best_sequences(ph, th, fc, fs, fr, fsc, alive, score, beam)
+    assert got_sc == want_sc
+    for g, w in zip(got, want):
+        assert g.dtype == np.int64 and np.array_equal(g, w)
