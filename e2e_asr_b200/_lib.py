@@ -58,6 +58,10 @@ _SIGS = {
     "e2e_sample_rows": "piipiQIIp",
     "e2e_gemm_f64": "piiipipipip",
     "e2e_gemm_f64d": "piiipipipip",
+    "e2e_gemm_f64d_cat": "piiiipipipipippip",
+    "e2e_gemm_f64d_lstm": "piiiipipipippippppi",
+    "e2e_exp2x_f64": "pzpp",
+    "e2e_attn_beam_group_e_f64": "piiiiipppppppi",
     "e2e_lstm_step_f64": "piippppi",
     "e2e_attn_beam_f64": "piiiipppppppi",
     "e2e_attn_beam_group_f64": "piiiiipppppppi",

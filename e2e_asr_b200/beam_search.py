@@ -119,10 +119,27 @@ def best_sequences(par_hist, tok_hist, fin_cnt, fin_step, fin_row, fin_score, al
     return outs, [float(v) for v in best_sc]
 
 
+def lstm_gate_perm(H):
+    """Column order of the gate-interleaved LSTM layout of `e2e_gemm_f64d_lstm`: position 32 q + 8 g + i holds column
+    g * H + 8 q + i of the TF kernel (gate g of i | j | f | o, unit 8 q + i), so that one lane of the FP64 tensor-core
+    product owns the four gates of a unit."""
+    q, g, i = np.meshgrid(np.arange(H // 8), np.arange(4), np.arange(8), indexing="ij")
+    return (g * H + 8 * q + i).reshape(-1)
+
+
 class BeamSearch(BaseParams):
     """Implementation of beam search for the attention decoder."""
 
     MAX_STEPS = 120          # loop bound of beam_search.py:269
+    # The decoding step (all float64, same sums up to their order -- ids are checked bit-exact against the oracle on
+    # every golden): fast_step = products take their K-concatenated operands in place, merge output aliases the slot
+    # state; token_table = emb[tok] . Wx + b of the LM-LSTM from a per-model table; fused_lstm = BasicLSTM in the
+    # product's epilogue; exp_attention = tanh(h + y) from exp(2h) exp(2y).  False restores the earlier formulation
+    # (test / bisection hooks).
+    fast_step = True
+    token_table = True
+    fused_lstm = True
+    exp_attention = True
 
     @classmethod
     def class_params(cls):
@@ -207,7 +224,7 @@ class BeamSearch(BaseParams):
         out = torch.empty((a.shape[0], w.shape[1]), dtype=torch.float64, device=self.device)
         K = a.shape[1]
         if K % 16 == 0 and a.stride(0) % 2 == 0 and w.shape[1] % 2 == 0 and w.is_contiguous():
-            cache = self.__dict__.setdefault("_w64", {})
+            cache = self.__dict__.setdefault("_w64_cache", {})
             ent = cache.get(w.data_ptr())
             if ent is None or ent[0] is not w:
                 ent = cache[w.data_ptr()] = (w, w.to(torch.float64))
@@ -217,6 +234,39 @@ class BeamSearch(BaseParams):
             call("e2e_gemm_f64", a.shape[0], w.shape[1], K, a, a.stride(0), w, w.stride(0), out, out.stride(0), b)
         return out
 
+    def _w64(self, w):
+        """float32 weight matrix widened to float64 once ((double)float is exact)."""
+        cache = self.__dict__.setdefault("_w64_cache", {})
+        ent = cache.get(w.data_ptr())
+        if ent is None or ent[0] is not w:
+            ent = cache[w.data_ptr()] = (w, w.to(torch.float64).contiguous())
+        return ent[1]
+
+    def _lstm_pack(self, w, b, I, emb=None):
+        """Operands of one BasicLSTM for the step's product: kernel rows [0, I) take the input, rows [I, I+H) the
+        hidden state (basic_lstm.py:17).  `W` float64 (columns gate-interleaved when fused_lstm), `bias` float32 in
+        the same column order, and -- for a cell fed by the embedding -- `table` = emb . W[:I] + bias, float64 [V, 4H]."""
+        packs = self.__dict__.setdefault("_packs", {})
+        key = (w.data_ptr(), None if emb is None else emb.data_ptr(), bool(self.fused_lstm), bool(self.token_table))
+        if key in packs and packs[key].src is w:
+            return packs[key]
+        import types
+        H = w.shape[1] // 4
+        pk = types.SimpleNamespace(src=w, H=H, I=I)
+        W64, bias = w.to(torch.float64), b
+        if self.fused_lstm:
+            perm = torch.as_tensor(lstm_gate_perm(H), device=w.device)
+            W64, bias = W64[:, perm], b[perm]
+        pk.W, pk.bias = W64.contiguous(), bias.contiguous()
+        pk.table = None
+        if emb is not None and self.token_table:
+            e64 = emb.to(torch.float64).contiguous()
+            pk.table = torch.empty((emb.shape[0], 4 * H), dtype=torch.float64, device=w.device)
+            call("e2e_gemm_f64d", e64.shape[0], 4 * H, I, e64, e64.stride(0), pk.W, pk.W.stride(0), pk.table,
+                 pk.table.stride(0), pk.bias)
+        packs[key] = pk
+        return pk
+
     def _plan(self, N, beam, rows_b, Tmax_b, D):
         """Device buffers, the step function and (once captured) the CUDA graph of one decoding step for a batch
         signature: N utterances x `beam` slots, encoder rows padded to rows_b, the longest utterance padded to Tmax_b.
@@ -224,7 +274,8 @@ class BeamSearch(BaseParams):
         import types
         from ._lib import BeamGatherArgs, BeamMergeArgs
         plans = self.__dict__.setdefault("_plans", {})
-        key = (N, beam, rows_b, Tmax_b, D, bool(self.use_lm))
+        key = (N, beam, rows_b, Tmax_b, D, bool(self.use_lm), bool(self.fast_step), bool(self.token_table),
+               bool(self.fused_lstm), bool(self.exp_attention))
         if key in plans:
             return plans[key]
         sp, p, lp, dev = self.search_params, self.dec_params, self.lm_params, self.device
@@ -238,6 +289,8 @@ class BeamSearch(BaseParams):
         pl = types.SimpleNamespace(graph=None, calls=0, R=R, S=S)
         pl.enc_all = torch.zeros((rows_b, D), dtype=torch.float32, device=dev)
         pl.HF = torch.empty((rows_b, A), dtype=torch.float32, device=dev)
+        pl.EHF = None
+        pl.enc_pin = torch.empty((rows_b, D), dtype=torch.float32).pin_memory()
         pl.row_off = torch.zeros((R,), **i32)
         pl.row_T = torch.zeros((R,), **i32)
         # ---- slot state (device)
@@ -318,6 +371,90 @@ class BeamSearch(BaseParams):
             alive.copy_(new_alive)
             step_dev.add_(1)
 
+        def gemm_cat(a1, a2, w64, bias, out, z=None):
+            """out = [a1 | a2] . w64 + bias (+ z[tok]) without materialising the concatenation."""
+            call("e2e_gemm_f64d_cat", R, w64.shape[1], a1.shape[1], 0 if a2 is None else a2.shape[1], a1, a1.stride(0),
+                 a2, 0 if a2 is None else a2.stride(0), w64, w64.stride(0), out, out.stride(0), bias, z,
+                 0 if z is None else z.stride(0), None if z is None else tok)
+            return out
+
+        def make_lstm(w, b, I, emb, H):
+            """One BasicLSTM of the step: (x or None when the input is the token embedding, c, h) -> c_out, h_out."""
+            pk = self._lstm_pack(w, b, I, emb)
+            zbuf = None if self.fused_lstm else torch.empty((R, 4 * H), **f64)
+            xbuf = torch.empty((R, I), **f64) if (emb is not None and pk.table is None) else None
+
+            def run(x, c, h, c_out, h_out):
+                if emb is not None and pk.table is None:
+                    call("e2e_embed_gather_f64", R, I, emb, tok, xbuf, I)
+                    x = xbuf
+                if x is None:                                  # input half of the product from the token table
+                    a1, a2, W, bias, z = h, None, pk.W[I:], None, pk.table
+                else:
+                    a1, a2, W, bias, z = x, h, pk.W, pk.bias, None
+                if self.fused_lstm:
+                    call("e2e_gemm_f64d_lstm", R, H, a1.shape[1], 0 if a2 is None else a2.shape[1], a1, a1.stride(0),
+                         a2, 0 if a2 is None else a2.stride(0), W, W.stride(0), bias, z,
+                         0 if z is None else z.stride(0), None if z is None else tok, c, c_out, h_out, H)
+                else:
+                    gemm_cat(a1, a2, W, bias, zbuf, z)
+                    call("e2e_lstm_step_f64", R, H, zbuf, c, c_out, h_out, H)
+            return run
+
+        # the FP64 tensor-core products take k-tiles of 16 and (fused LSTM) 64-column tiles: other widths -- unit-test
+        # sizes -- run the earlier formulation (e2e_gemm_f64 serves any shape)
+        widths = [E, Hl, Hd, D, p.attn_proj_w.shape[1]] + ([p.simple_w.shape[1]] if p.simple_w is not None else [])
+        if self.use_lm:
+            widths += [lp.embedding.shape[1], Hm] + ([lp.simple_w.shape[1]] if lp.simple_w is not None else [])
+        pl.fast = bool(self.fast_step) and all(int(x) % 16 == 0 for x in widths)
+        if pl.fast:
+            lm_cell = make_lstm(p.lm_lstm_w, p.lm_lstm_b, E, p.embedding, Hl)
+            dec_cell = make_lstm(p.dec_lstm_w, p.dec_lstm_b, E, None, Hd)
+            lm2_cell = make_lstm(lp.lm_lstm_w, lp.lm_lstm_b, lp.embedding.shape[1], lp.embedding, Hm) if self.use_lm else None
+            Hs = p.simple_w.shape[1] if p.simple_w is not None else Hl
+            bufs = dict(m=torch.empty((R, Hs), **f64) if p.simple_w is not None else None,
+                        x_dec=torch.empty((R, E), **f64), y=torch.empty((R, A), **f64),
+                        proj=torch.empty((R, p.attn_proj_w.shape[1]), **f64), logits=torch.empty((R, V), **f64))
+            if self.use_lm:
+                bufs["lo"] = torch.empty((R, lp.simple_w.shape[1]), **f64) if lp.simple_w is not None else None
+                bufs["lm_logits"] = torch.empty((R, lp.out_w.shape[1]), **f64)
+            w64 = self._w64
+            if self.exp_attention and beam <= 16 and Tmax_b <= 256:
+                pl.EHF = torch.empty((rows_b, A), **f64)
+            # the merge writes the next step's token / score / liveness straight into the slot state: it reads them
+            # only while it collects the candidates of its own utterance, before the first write
+            ma.new_tok, ma.new_score, ma.new_alive = tok.data_ptr(), score.data_ptr(), alive.data_ptr()
+
+            def step_fn():                                                  # noqa: F811
+                # decoder's LM-LSTM, SimpleProjection, InputProjection, decoder LSTM (beam_search.py:182-191)
+                lm_cell(None, st["lc"], st["lh"], nx["lc"], nx["lh"])
+                m = nx["lh"] if p.simple_w is None else gemm_cat(nx["lh"], None, w64(p.simple_w), p.simple_b, bufs["m"])
+                gemm_cat(m, st["ctx"], w64(p.inp_w), p.inp_b, bufs["x_dec"])
+                dec_cell(bufs["x_dec"], st["dc"], st["dh"], nx["dc"], nx["dh"])
+                # attention with the CELL state as query (beam_search.py:193), AttnProjection, OutputProjection
+                gemm_cat(nx["dc"], None, w64(p.attn_dec_w), p.attn_dec_b, bufs["y"])
+                if pl.EHF is not None:
+                    call("e2e_attn_beam_group_e_f64", N, beam, A, D, Tmax_b, pl.EHF, enc_all, row_off, row_T, bufs["y"],
+                         p.attn_v, nx["ctx"], D)
+                else:
+                    call("e2e_attn_beam_group_f64", N, beam, A, D, Tmax_b, HF, enc_all, row_off, row_T, bufs["y"],
+                         p.attn_v, nx["ctx"], D)
+                gemm_cat(nx["dc"], nx["ctx"], w64(p.attn_proj_w), p.attn_proj_b, bufs["proj"])
+                gemm_cat(bufs["proj"], None, w64(p.out_w), p.out_b, bufs["logits"])
+                lm_logits = None
+                if self.use_lm:                                            # LM branch (beam_search.py:200-207)
+                    lm2_cell(None, st["mc"], st["mh"], nx["mc"], nx["mh"])
+                    lo = nx["mh"] if lp.simple_w is None else gemm_cat(nx["mh"], None, w64(lp.simple_w), lp.simple_b,
+                                                                      bufs["lo"])
+                    lm_logits = gemm_cat(lo, None, w64(lp.out_w), lp.out_b, bufs["lm_logits"])
+                call("e2e_logsoftmax_topk_f64", R, V, bufs["logits"], lm_logits, float(sp.lm_weight), krow, beam,
+                     out_idx, out_val, scratch)
+                n_live.zero_()
+                call("e2e_beam_merge", ma)                                  # -> new rows, back-pointers, finals
+                call("e2e_beam_gather", R, parent, ga)                      # states of the parent hypotheses
+                step_dev.add_(1)
+            pl.keep = pl.keep + (bufs, lm_cell, dec_cell, lm2_cell)
+
         pl.step_fn = step_fn
         while len(plans) >= 4:                                              # a few signatures; the oldest goes first
             plans.pop(next(iter(plans)))
@@ -354,8 +491,11 @@ class BeamSearch(BaseParams):
         D = encs[0].shape[1]
         pl = self._plan(N, beam, (rows + 255) // 256 * 256, (int(Ts.max()) + 7) // 8 * 8, D)
         S = pl.S
-        pl.enc_all[:rows].copy_(torch.from_numpy(np.concatenate(encs, axis=0)))
+        np.concatenate(encs, axis=0, out=pl.enc_pin.numpy()[:rows])       # pinned staging: one DMA, no pageable bounce
+        pl.enc_all[:rows].copy_(pl.enc_pin[:rows], non_blocking=True)
         ops.gemm(pl.enc_all, p.attn_enc_w, mode=0, out=pl.HF)             # float32 x float32 (beam_search.py:148)
+        if pl.EHF is not None:
+            call("e2e_exp2x_f64", pl.HF.numel(), pl.HF, pl.EHF)
         pl.row_off.copy_(torch.from_numpy(np.repeat(offs, beam)))
         pl.row_T.copy_(torch.from_numpy(np.repeat(Ts, beam)))
         # ---- slot state: the GO row of every utterance is alive at step 0

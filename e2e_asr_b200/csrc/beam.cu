@@ -172,20 +172,48 @@ constexpr int BS2 = PT + 4;
 __device__ __forceinline__ void dmma(double (&d)[2], double a, double b) {
     asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(d[0]), "+d"(d[1]) : "d"(a), "d"(b));
 }
+// Operands of the DMMA product beyond C = A.B + bias (all optional):
+//  * K-concatenated A: columns [0, K1) of the product's A come from A, columns [K1, K) from A2 (K1 % 16 == 0) -- the
+//    reference's np.concatenate([x, h]) . W (basic_lstm.py:17, beam_search.py:186,194) without materialising the
+//    concatenation;
+//  * a row addend Z[zrow[m], :] (float64): the part of a product that depends only on the row's TOKEN -- emb[tok] . Wx
+//    + b of the LM-LSTM -- is a table computed once per model, so the step's product keeps only K = H;
+//  * an LSTM epilogue (EPI = 1): with the 4H gate columns interleaved in blocks of 32 -- column 32 q + 8 g + i holds
+//    gate g (i, j, f, o) of unit 8 q + i -- the lane that owns rows {8 i + lr} and columns {8 j + 2 lc + e} of a warp
+//    tile holds all four gates of two units, so BasicLSTM.__call__ (basic_lstm.py:14-23) runs on the accumulators and
+//    the pre-activations never go to memory.  Same formulas as lstm_step_f64_kernel.
+struct GemmF64Ext {
+    const double* A2;
+    int lda2, K1;
+    const double* Z;
+    int ldz;
+    const long long* zrow;
+    const double* c_prev;      // EPI = 1: [M, H] in, c_out / h_out [M, H] resp. [M, ldh] out
+    double* c_out;
+    double* h_out;
+    int ldh, H;
+};
+// CTA = (2 WM) x 64 tile, 4 warps of WM x 32 (WM / 8 x 4 m8n8 tiles): WM = 32 for the large products, WM = 16 when
+// 64-row tiles would leave most SMs with one CTA or none (N <= 256 at 2560 rows: 160 CTAs on 148 SMs).
+template <int WM, int EPI>
 __global__ void __launch_bounds__(128)
 gemm_f64_mma_kernel(int M, int N, int K, const double* __restrict__ A, int lda, const double* __restrict__ B, int ldb,
-                    double* __restrict__ C, int ldc, const float* __restrict__ bias) {
-    __shared__ __align__(16) double As[2][PT][PAS];
+                    double* __restrict__ C, int ldc, const float* __restrict__ bias, GemmF64Ext x) {
+    constexpr int TM = 2 * WM, MI = WM / 8;
+    __shared__ __align__(16) double As[2][TM][PAS];
     __shared__ __align__(16) double Bs[2][PK][BS2];
     const int tid = threadIdx.x, lane = tid % 32, w = tid / 32, wm = w / 2, wn = w % 2;
     const int lr = lane / 4, lc = lane % 4;
-    const int m0 = blockIdx.y * PT, n0 = blockIdx.x * PT;
+    const int m0 = blockIdx.y * TM, n0 = blockIdx.x * PT;
     auto issue = [&](int stage, int k0) {
+        const bool second = k0 >= x.K1;
+        const double* Ab = second ? x.A2 : A;
+        const int ld = second ? x.lda2 : lda, kk0 = second ? k0 - x.K1 : k0;
 #pragma unroll
-        for (int it = 0; it < 4; ++it) {
+        for (int it = 0; it < TM / 16; ++it) {
             const int i = it * 128 + tid, r = i / 8, c = (i % 8) * 2;
             const bool ok = m0 + r < M;
-            cp_async16(&As[stage][r][c], A + (size_t)(ok ? m0 + r : 0) * lda + k0 + c, ok ? 16 : 0);
+            cp_async16(&As[stage][r][c], Ab + (size_t)(ok ? m0 + r : 0) * ld + kk0 + c, ok ? 16 : 0);
         }
 #pragma unroll
         for (int it = 0; it < 4; ++it) {
@@ -196,9 +224,9 @@ gemm_f64_mma_kernel(int M, int N, int K, const double* __restrict__ A, int lda, 
         }
         asm volatile("cp.async.commit_group;" ::: "memory");
     };
-    double acc[4][4][2];
+    double acc[MI][4][2];
 #pragma unroll
-    for (int i = 0; i < 4; ++i)
+    for (int i = 0; i < MI; ++i)
 #pragma unroll
         for (int j = 0; j < 4; ++j) { acc[i][j][0] = 0.0; acc[i][j][1] = 0.0; }
     const int nk = K / PK;
@@ -214,44 +242,110 @@ gemm_f64_mma_kernel(int M, int N, int K, const double* __restrict__ A, int lda, 
         const int s = t & 1;
 #pragma unroll
         for (int kk = 0; kk < PK / 4; ++kk) {
-            double a[4], b[4];
+            double a[MI], b[4];
 #pragma unroll
-            for (int i = 0; i < 4; ++i) a[i] = As[s][32 * wm + 8 * i + lr][4 * kk + lc];
+            for (int i = 0; i < MI; ++i) a[i] = As[s][WM * wm + 8 * i + lr][4 * kk + lc];
 #pragma unroll
             for (int j = 0; j < 4; ++j) b[j] = Bs[s][4 * kk + lc][32 * wn + 8 * j + lr];
 #pragma unroll
-            for (int i = 0; i < 4; ++i)
+            for (int i = 0; i < MI; ++i)
 #pragma unroll
                 for (int j = 0; j < 4; ++j) dmma(acc[i][j], a[i], b[j]);
         }
         __syncthreads();
     }
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        const int m = m0 + 32 * wm + 8 * i + lr;
+    for (int i = 0; i < MI; ++i) {
+        const int m = m0 + WM * wm + 8 * i + lr;
         if (m >= M) continue;
+        const double* zr = x.Z ? x.Z + (size_t)x.zrow[m] * x.ldz : nullptr;
+        if (EPI == 0) {
 #pragma unroll
-        for (int j = 0; j < 4; ++j)
+            for (int j = 0; j < 4; ++j)
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    const int n = n0 + 32 * wn + 8 * j + 2 * lc + e;
+                    if (n < N) {
+                        double v = acc[i][j][e] + (bias ? (double)bias[n] : 0.0);
+                        if (zr) v += zr[n];
+                        C[(size_t)m * ldc + n] = v;
+                    }
+                }
+        } else {
+            // N = 4H is a multiple of 64: no column bounds.  Column n0 + 32 wn + 8 g + (2 lc + e) = gate g of unit u
 #pragma unroll
             for (int e = 0; e < 2; ++e) {
-                const int n = n0 + 32 * wn + 8 * j + 2 * lc + e;
-                if (n < N) C[(size_t)m * ldc + n] = acc[i][j][e] + (bias ? (double)bias[n] : 0.0);
+                const int nb = n0 + 32 * wn + 2 * lc + e;
+                const int u = (nb / 32) * 8 + 2 * lc + e;
+                double g[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    g[j] = acc[i][j][e] + (bias ? (double)bias[nb + 8 * j] : 0.0);
+                    if (zr) g[j] += zr[nb + 8 * j];
+                }
+                const double si = 1.0 / (1.0 + exp(-g[0]));
+                const double tj = tanh(g[1]);
+                const double sf = 1.0 / (1.0 + exp(-(g[2] + 1.0)));
+                const double so = 1.0 / (1.0 + exp(-g[3]));
+                const double cn = x.c_prev[(size_t)m * x.H + u] * sf + si * tj;
+                x.c_out[(size_t)m * x.H + u] = cn;
+                x.h_out[(size_t)m * x.ldh + u] = so * tanh(cn);
             }
+        }
     }
 }
 
 // the same product with the weights already widened to float64 (aligned operands only: K % 16 == 0, even lda / ldb)
+static int launch_f64_mma(cudaStream_t st, int M, int N, int K, const double* A, int lda, const double* B, int ldb,
+                          double* C, int ldc, const float* bias, const GemmF64Ext& x, bool lstm) {
+    // 64-row tiles unless they leave fewer than two CTAs per SM
+    const bool small = (long long)cdiv(M, 64) * cdiv(N, PT) < 2 * 148;
+    const dim3 grid(cdiv(N, PT), cdiv(M, small ? 32 : 64));
+    if (lstm) {
+        if (small) gemm_f64_mma_kernel<16, 1><<<grid, 128, 0, st>>>(M, N, K, A, lda, B, ldb, C, ldc, bias, x);
+        else gemm_f64_mma_kernel<32, 1><<<grid, 128, 0, st>>>(M, N, K, A, lda, B, ldb, C, ldc, bias, x);
+    } else {
+        if (small) gemm_f64_mma_kernel<16, 0><<<grid, 128, 0, st>>>(M, N, K, A, lda, B, ldb, C, ldc, bias, x);
+        else gemm_f64_mma_kernel<32, 0><<<grid, 128, 0, st>>>(M, N, K, A, lda, B, ldb, C, ldc, bias, x);
+    }
+    E2E_LAUNCH_CHECK();
+    return 0;
+}
 int gemm_f64d(cudaStream_t st, int M, int N, int K, const double* A, int lda, const double* B, int ldb, double* C,
               int ldc, const float* bias) {
     if (M <= 0 || N <= 0) return 0;
     E2E_REQUIRE(K > 0 && K % PK == 0 && lda % 2 == 0 && ldb % 2 == 0 && ((uintptr_t)A & 15) == 0 && ((uintptr_t)B & 15) == 0,
                 "gemm_f64d: K %% 16 == 0 and 16-byte aligned rows required (K=%d lda=%d ldb=%d)", K, lda, ldb);
-    if (g_f64_mma)
-        gemm_f64_mma_kernel<<<dim3(cdiv(N, PT), cdiv(M, PT)), 128, 0, st>>>(M, N, K, A, lda, B, ldb, C, ldc, bias);
-    else
-        gemm_f64_pipe_kernel<double><<<dim3(cdiv(N, PT), cdiv(M, PT)), 128, 0, st>>>(M, N, K, A, lda, B, ldb, C, ldc, bias);
+    if (g_f64_mma) {
+        GemmF64Ext x = {};
+        x.K1 = K;
+        return launch_f64_mma(st, M, N, K, A, lda, B, ldb, C, ldc, bias, x, false);
+    }
+    gemm_f64_pipe_kernel<double><<<dim3(cdiv(N, PT), cdiv(M, PT)), 128, 0, st>>>(M, N, K, A, lda, B, ldb, C, ldc, bias);
     E2E_LAUNCH_CHECK();
     return 0;
+}
+// C = [A1 | A2] . B + bias + Z[zrow]  (A2 / Z optional), resp. the LSTM step on that product (c_out, h_out; no C)
+int gemm_f64d_cat(cudaStream_t st, int M, int N, int K1, int K2, const double* A1, int lda1, const double* A2, int lda2,
+                  const double* B, int ldb, double* C, int ldc, const float* bias, const double* Z, int ldz,
+                  const long long* zrow, const double* c_prev, double* c_out, double* h_out, int ldh) {
+    if (M <= 0 || N <= 0) return 0;
+    const bool lstm = c_out != nullptr;
+    E2E_REQUIRE(K1 > 0 && K1 % PK == 0 && K2 >= 0 && K2 % PK == 0 && lda1 % 2 == 0 && ldb % 2 == 0 &&
+                    ((uintptr_t)A1 & 15) == 0 && ((uintptr_t)B & 15) == 0,
+                "gemm_f64d_cat: K1, K2 %% 16 == 0 and 16-byte aligned rows required (K1=%d K2=%d lda1=%d ldb=%d)", K1, K2,
+                lda1, ldb);
+    E2E_REQUIRE(K2 == 0 || (A2 != nullptr && lda2 % 2 == 0 && ((uintptr_t)A2 & 15) == 0),
+                "gemm_f64d_cat: the second A operand must be 16-byte aligned with an even row stride (lda2=%d)", lda2);
+    E2E_REQUIRE(Z == nullptr || zrow != nullptr, "gemm_f64d_cat: a row addend needs its row indices");
+    E2E_REQUIRE(!lstm || (N % 64 == 0 && c_prev != nullptr && h_out != nullptr),
+                "gemm_f64d_cat: the LSTM epilogue needs N = 4H with H %% 16 == 0 (N=%d), c_prev and h_out", N);
+    E2E_REQUIRE(lstm || C != nullptr, "gemm_f64d_cat: no output");
+    GemmF64Ext x = {};
+    x.A2 = A2; x.lda2 = lda2; x.K1 = K1;
+    x.Z = Z; x.ldz = ldz; x.zrow = zrow;
+    x.c_prev = c_prev; x.c_out = c_out; x.h_out = h_out; x.ldh = ldh; x.H = N / 4;
+    return launch_f64_mma(st, M, N, K1 + K2, A1, lda1, B, ldb, C, ldc, bias, x, lstm);
 }
 
 int gemm_f64(cudaStream_t st, int M, int N, int K, const double* A, int lda, const float* B, int ldb, double* C,
@@ -448,6 +542,121 @@ int attn_beam_group_f64(cudaStream_t st, int N, int beam, int A, int D, int Tmax
     if (smem > 48 * 1024)
         E2E_CHECK_CUDA(cudaFuncSetAttribute(attn_beam_group_f64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attn_beam_group_f64_kernel<<<N, 256, smem, st>>>(beam, A, D, Tmax, HF, enc, row_off, Tlen, y, v, ctx, ldctx);
+    E2E_LAUNCH_CHECK();
+    return 0;
+}
+
+// ---- the same read-out from exponentials ----------------------------------------------------------------------------
+// tanh(h + y) = 1 - 2 / (exp(2h) exp(2y) + 1): exp(2 HF) depends only on the utterance (a table filled once per
+// decode, e2e_exp2x_f64) and exp(2 y) only on (hypothesis, a) -- `beam` x A values per step and utterance -- so the
+// T x beam x A inner loop of the scores is a multiplication, an addition and a division instead of an exp and a
+// division (the loop is bound by the FP64 pipe: ~3x fewer FP64 instructions).  Both exponents are clamped to
+// [-300, 300], so the product neither overflows to inf * 0 nor underflows to 0 * inf; inside the clamp the result
+// differs from tanh_exp(h + y) by the rounding of one product (absolute error < 3e-16 like tanh_exp itself), outside
+// it tanh is +-1 to machine precision unless the two arguments cancel to within a few units -- pre-activations of
+// magnitude 150, which a trained attention layer does not produce.
+constexpr double EXP2X_CLAMP = 300.0;
+__device__ __forceinline__ double exp2x(double x) { return exp(fmin(fmax(2.0 * x, -EXP2X_CLAMP), EXP2X_CLAMP)); }
+__global__ void exp2x_f64_kernel(size_t n, const float* __restrict__ x, double* __restrict__ out) {
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+        out[i] = exp2x((double)x[i]);
+}
+int exp2x_f64(cudaStream_t st, size_t n, const float* x, double* out) {
+    if (n == 0) return 0;
+    exp2x_f64_kernel<<<(unsigned)min((n + 255) / 256, (size_t)148 * 16), 256, 0, st>>>(n, x, out);
+    E2E_LAUNCH_CHECK();
+    return 0;
+}
+// attn_beam_group_f64_kernel with EHF = exp2x(HF) in place of HF; scores summed in the same order, softmax and
+// read-out identical.
+__global__ void __launch_bounds__(256)
+attn_beam_group_e_f64_kernel(int beam, int A, int D, int Tmax, const double* __restrict__ EHF,
+                             const float* __restrict__ enc, const int* __restrict__ row_off,
+                             const int* __restrict__ Tlen, const double* __restrict__ y, const float* __restrict__ v,
+                             double* __restrict__ ctx, int ldctx) {
+    extern __shared__ double sm[];
+    double* y_s = sm;                       // [beam][A]  exp(2 y)
+    double* v_s = y_s + beam * A;           // [A]
+    double* s_s = v_s + A;                  // [beam][Tmax]  scores, then exp, then alpha
+    const int u = blockIdx.x, tid = threadIdx.x, lane = tid % 32, warp = tid / 32, nw = 8;
+    const int r0 = u * beam;
+    const int off = row_off[r0], T = Tlen[r0];
+    for (int i = tid; i < beam * A; i += 256) y_s[i] = exp2x(y[(size_t)(r0 + i / A) * A + i % A]);
+    for (int a = tid; a < A; a += 256) v_s[a] = (double)v[a];
+    __syncthreads();
+    for (int tau = warp; tau < T; tau += nw) {
+        const double* hrow = EHF + (size_t)(off + tau) * A;
+        double eh[4];                        // this lane's columns of the row (A <= 128: loaded once for all hypotheses)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) eh[j] = lane + 32 * j < A ? __ldg(hrow + lane + 32 * j) : 0.0;
+        for (int r = 0; r < beam; ++r) {
+            double p = 0.0;
+            for (int a0 = lane; a0 < A; a0 += 128) {
+                double t[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int a = a0 + 32 * j;
+                    const double e = a0 == lane ? eh[j] : (a < A ? __ldg(hrow + a) : 0.0);
+                    t[j] = a < A ? 1.0 - 2.0 / (e * y_s[r * A + a] + 1.0) : 0.0;
+                }
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    if (a0 + 32 * j < A) p = fma(t[j], v_s[a0 + 32 * j], p);
+            }
+            for (int o = 16; o > 0; o >>= 1) p += __shfl_xor_sync(0xffffffffu, p, o);
+            if (lane == 0) s_s[r * Tmax + tau] = p;
+        }
+    }
+    __syncthreads();
+    for (int r = warp; r < beam; r += nw) {
+        double* sr = s_s + r * Tmax;
+        double mx = -INFINITY;
+        for (int tau = lane; tau < T; tau += 32) mx = fmax(mx, sr[tau]);
+        for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+        double sum = 0.0;
+        for (int c = 0; c < nw; ++c) {
+            const int tau = 32 * c + lane;
+            double e = 0.0;
+            if (tau < T) { e = exp(sr[tau] - mx); sr[tau] = e; }
+            for (int o = 16; o > 0; o >>= 1) e += __shfl_xor_sync(0xffffffffu, e, o);
+            sum += e;
+        }
+        __syncwarp();
+        for (int tau = lane; tau < T; tau += 32) sr[tau] = sr[tau] / sum;
+    }
+    __syncthreads();
+    for (int d = tid; d < D; d += 256) {
+        double c[MAXB];
+#pragma unroll
+        for (int r = 0; r < MAXB; ++r) c[r] = 0.0;
+        for (int tau0 = 0; tau0 < T; tau0 += 8) {
+            float ev[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) ev[i] = tau0 + i < T ? __ldg(enc + (size_t)(off + tau0 + i) * D + d) : 0.f;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                if (tau0 + i < T) {
+                    const double e = (double)ev[i];
+#pragma unroll
+                    for (int r = 0; r < MAXB; ++r)
+                        if (r < beam) c[r] = fma(s_s[r * Tmax + tau0 + i], e, c[r]);
+                }
+            }
+        }
+#pragma unroll
+        for (int r = 0; r < MAXB; ++r)
+            if (r < beam) ctx[(size_t)(r0 + r) * ldctx + d] = c[r];
+    }
+}
+int attn_beam_group_e_f64(cudaStream_t st, int N, int beam, int A, int D, int Tmax, const double* EHF, const float* enc,
+                          const int* row_off, const int* Tlen, const double* y, const float* v, double* ctx, int ldctx) {
+    if (N <= 0 || beam <= 0) return 0;
+    const size_t smem = sizeof(double) * ((size_t)beam * A + A + (size_t)beam * Tmax);
+    E2E_REQUIRE(beam <= MAXB && Tmax <= 256 && smem <= 200 * 1024,
+                "attn_beam_group_e_f64: beam <= %d, Tmax <= 256 required (beam=%d Tmax=%d)", MAXB, beam, Tmax);
+    if (smem > 48 * 1024)
+        E2E_CHECK_CUDA(cudaFuncSetAttribute(attn_beam_group_e_f64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attn_beam_group_e_f64_kernel<<<N, 256, smem, st>>>(beam, A, D, Tmax, EHF, enc, row_off, Tlen, y, v, ctx, ldctx);
     E2E_LAUNCH_CHECK();
     return 0;
 }

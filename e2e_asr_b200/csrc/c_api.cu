@@ -98,6 +98,11 @@ int attn_bwd_step(cudaStream_t, int, int, int, int, int, const float*, const flo
                   const float*, const float*, int, float*, float*);
 int gemm_f64(cudaStream_t, int, int, int, const double*, int, const float*, int, double*, int, const float*);
 int gemm_f64d(cudaStream_t, int, int, int, const double*, int, const double*, int, double*, int, const float*);
+int gemm_f64d_cat(cudaStream_t, int, int, int, int, const double*, int, const double*, int, const double*, int, double*,
+                  int, const float*, const double*, int, const long long*, const double*, double*, double*, int);
+int exp2x_f64(cudaStream_t, size_t, const float*, double*);
+int attn_beam_group_e_f64(cudaStream_t, int, int, int, int, int, const double*, const float*, const int*, const int*,
+                          const double*, const float*, double*, int);
 extern int g_f64_mma;
 int lstm_step_f64(cudaStream_t, int, int, const double*, const double*, double*, double*, int);
 int attn_beam_group_f64(cudaStream_t, int, int, int, int, int, const float*, const float*, const int*, const int*,
@@ -437,6 +442,28 @@ int e2e_gemm_f64d(void* stream, int M, int N, int K, const double* A, int lda, c
 int e2e_gemm_f64(void* stream, int M, int N, int K, const double* A, int lda, const float* B, int ldb, double* C,
                  int ldc, const float* bias) {
     return gemm_f64(ST(stream), M, N, K, A, lda, B, ldb, C, ldc, bias);
+}
+int e2e_gemm_f64d_cat(void* stream, int M, int N, int K1, int K2, const double* A1, int lda1, const double* A2,
+                      int lda2, const double* B, int ldb, double* C, int ldc, const float* bias, const double* Z,
+                      int ldz, const long long* zrow) {
+    return gemm_f64d_cat(ST(stream), M, N, K1, K2, A1, lda1, A2, lda2, B, ldb, C, ldc, bias, Z, ldz, zrow, nullptr,
+                         nullptr, nullptr, 0);
+}
+int e2e_gemm_f64d_lstm(void* stream, int M, int H, int K1, int K2, const double* A1, int lda1, const double* A2,
+                       int lda2, const double* B, int ldb, const float* bias, const double* Z, int ldz,
+                       const long long* zrow, const double* c_prev, double* c_out, double* h_out, int ldh) {
+    if (c_out == nullptr) {
+        set_error("e2e_gemm_f64d_lstm: c_out is NULL");
+        return 1;
+    }
+    return gemm_f64d_cat(ST(stream), M, 4 * H, K1, K2, A1, lda1, A2, lda2, B, ldb, nullptr, 0, bias, Z, ldz, zrow,
+                         c_prev, c_out, h_out, ldh);
+}
+int e2e_exp2x_f64(void* stream, size_t n, const float* x, double* out) { return exp2x_f64(ST(stream), n, x, out); }
+int e2e_attn_beam_group_e_f64(void* stream, int N, int beam, int A, int D, int Tmax, const double* EHF,
+                              const float* enc, const int* row_off, const int* Tlen, const double* y, const float* v,
+                              double* ctx, int ldctx) {
+    return attn_beam_group_e_f64(ST(stream), N, beam, A, D, Tmax, EHF, enc, row_off, Tlen, y, v, ctx, ldctx);
 }
 int e2e_lstm_step_f64(void* stream, int n, int H, const double* z, const double* c_prev, double* c_out, double* h_out,
                       int ldh) {

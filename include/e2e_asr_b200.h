@@ -281,6 +281,21 @@ int e2e_gemm_f64d(void* stream, int M, int N, int K, const double* A, int lda, c
                   int ldc, const float* bias);
 int e2e_gemm_f64(void* stream, int M, int N, int K, const double* A, int lda, const float* B, int ldb,
                  double* C, int ldc, const float* bias);
+/* C[M,N] = [A1 | A2] . B + bias + Z[zrow[m], :] on the FP64 tensor cores: A1 [M,K1] and A2 [M,K2] (optional, K2 = 0)
+ * are the two halves of the reference's np.concatenate([x, h]) (basic_lstm.py:17; beam_search.py:186,194), never
+ * materialised; Z (optional, float64 [*, ldz], row zrow[m] per output row) carries the part of a product that depends
+ * only on the row's token -- emb[tok] . Wx + b of the LM-LSTM, a table computed once per model.  B float64 [K1+K2, N];
+ * K1, K2 % 16 == 0, even row strides, 16-byte aligned operands. */
+int e2e_gemm_f64d_cat(void* stream, int M, int N, int K1, int K2, const double* A1, int lda1, const double* A2,
+                      int lda2, const double* B, int ldb, double* C, int ldc, const float* bias, const double* Z,
+                      int ldz, const long long* zrow);
+/* The same product followed by BasicLSTM.__call__ (basic_lstm.py:14-23) in the epilogue: (c_out, h_out) from c_prev and
+ * the pre-activations, which are never written.  B, bias and Z hold the 4H gate columns INTERLEAVED in blocks of 32:
+ * column 32 q + 8 g + i = gate g (i, j, f, o) of unit 8 q + i (e2e_asr_b200.beam_search.lstm_gate_perm).  H % 16 == 0.
+ * Same formulas as e2e_lstm_step_f64 on the same sums. */
+int e2e_gemm_f64d_lstm(void* stream, int M, int H, int K1, int K2, const double* A1, int lda1, const double* A2,
+                       int lda2, const double* B, int ldb, const float* bias, const double* Z, int ldz,
+                       const long long* zrow, const double* c_prev, double* c_out, double* h_out, int ldh);
 int e2e_lstm_step_f64(void* stream, int n, int H, const double* z, const double* c_prev, double* c_out,
                       double* h_out, int ldh);
 /* e2e_attn_beam_f64 for hypotheses stored in groups of `beam` rows per utterance (rows u*beam .. u*beam+beam-1 share
@@ -291,6 +306,15 @@ int e2e_attn_beam_group_f64(void* stream, int N, int beam, int A, int D, int Tma
 int e2e_attn_beam_f64(void* stream, int n, int A, int D, int Tmax, const float* HF, const float* enc,
                       const int* row_off, const int* Tlen, const double* y, const float* v, double* ctx,
                       int ldctx);
+/* calc_attention from exponentials: out[i] = exp(clamp(2 x[i], -300, 300)) in float64 (EHF = the table of
+ * enc . AttnW, filled once per decode), and e2e_attn_beam_group_f64 with tanh(h + y) evaluated as
+ * 1 - 2 / (EHF * exp(2 y) + 1) -- one multiplication and one division per (frame, hypothesis, a) instead of an exp and
+ * a division; same summation order; differs from the tanh form by the rounding of one product (< 3e-16 absolute).
+ * beam <= 16, Tmax <= 256. */
+int e2e_exp2x_f64(void* stream, size_t n, const float* x, double* out);
+int e2e_attn_beam_group_e_f64(void* stream, int N, int beam, int A, int D, int Tmax, const double* EHF,
+                              const float* enc, const int* row_off, const int* Tlen, const double* y, const float* v,
+                              double* ctx, int ldctx);
 int e2e_logsoftmax_topk_f64(void* stream, int n, int V, const double* logits, const double* lm_logits,
                             double lm_weight, const int* krow, int kmax, int* out_idx, double* out_val,
                             double* scratch);

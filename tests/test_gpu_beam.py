@@ -252,3 +252,147 @@ def test_decode_batch_graph_capture_and_replay_repeat_the_eager_ids():
         np.testing.assert_array_equal(a, b)
     for u, enc in enumerate(encs):
         np.testing.assert_array_equal(first[u], ob.beam_search(w, enc, beam_size=5))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("M,N,K1,K2,table", [(2560, 1024, 256, 0, True), (2560, 256, 256, 512, False),
+                                              (2560, 128, 256, 0, False), (77, 1000, 256, 0, False),
+                                              (2560, 1024, 256, 256, False), (33, 64, 16, 32, True)])
+def test_gemm_f64d_cat_matches_numpy(M, N, K1, K2, table):
+    """e2e_gemm_f64d_cat: [A1 | A2] . B + bias + Z[zrow] on the FP64 tensor cores (the reference's concatenated
+    operands, basic_lstm.py:17 / beam_search.py:186,194, taken in place; 64- and 32-row tiles) against NumPy float64."""
+    import torch
+    from e2e_asr_b200._lib import call
+    rng = np.random.default_rng(M + 3 * N + 5 * K1 + 7 * K2)
+    a1 = rng.standard_normal((M, K1 + 2))
+    a2 = rng.standard_normal((M, K2 + 4)) if K2 else None
+    b = rng.standard_normal((K1 + K2, N)).astype(np.float32).astype(np.float64)
+    bias = rng.standard_normal(N).astype(np.float32)
+    z = rng.standard_normal((50, N)) if table else None
+    rows = rng.integers(0, 50, M).astype(np.int64)
+    dev = "cuda:0"
+    a1d = torch.from_numpy(a1).to(dev)[:, :K1]
+    a2d = torch.from_numpy(a2).to(dev)[:, :K2] if K2 else None
+    bd, biasd = torch.from_numpy(b).to(dev), torch.from_numpy(bias).to(dev)
+    zd = torch.from_numpy(z).to(dev) if table else None
+    rd = torch.from_numpy(rows).to(dev)
+    out = torch.full((M, N), float("nan"), dtype=torch.float64, device=dev)
+    call("e2e_gemm_f64d_cat", M, N, K1, K2, a1d, a1d.stride(0), a2d, a2d.stride(0) if K2 else 0, bd, bd.stride(0), out,
+         out.stride(0), biasd, zd, N if table else 0, rd if table else None)
+    ref = a1[:, :K1] @ b[:K1] + bias.astype(np.float64)
+    if K2:
+        ref = ref + a2[:, :K2] @ b[K1:]
+    if table:
+        ref = ref + z[rows]
+    assert np.abs(out.cpu().numpy() - ref).max() <= 1e-12 * max(1.0, np.abs(ref).max())
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("M,H,K1,K2,table", [(2560, 256, 256, 0, True), (2560, 256, 256, 256, False),
+                                              (45, 16, 16, 16, False), (300, 64, 32, 0, True)])
+def test_gemm_f64d_lstm_matches_product_plus_lstm_step(M, H, K1, K2, table):
+    """e2e_gemm_f64d_lstm (BasicLSTM.__call__, basic_lstm.py:14-23, in the epilogue of the product over gate-interleaved
+    columns) against e2e_gemm_f64d_cat + e2e_lstm_step_f64 in the TF column order, and against NumPy."""
+    import torch
+    from e2e_asr_b200._lib import call
+    from e2e_asr_b200.beam_search import lstm_gate_perm
+    rng = np.random.default_rng(M + H + K1 + K2)
+    dev = "cuda:0"
+    a1 = rng.standard_normal((M, K1)) * 0.5
+    a2 = rng.standard_normal((M, K2)) * 0.5 if K2 else None
+    w = (rng.standard_normal((K1 + K2, 4 * H)) * 0.2).astype(np.float32).astype(np.float64)
+    bias = rng.standard_normal(4 * H).astype(np.float32)
+    z = rng.standard_normal((30, 4 * H)) if table else None
+    rows = rng.integers(0, 30, M).astype(np.int64)
+    c_prev = rng.standard_normal((M, H))
+    perm = lstm_gate_perm(H)
+    t = lambda x: None if x is None else torch.from_numpy(np.ascontiguousarray(x)).to(dev)
+    a1d, a2d, cd, rd = t(a1), t(a2), t(c_prev), t(rows)
+    # TF column order: product, then the step kernel
+    pre = torch.empty((M, 4 * H), dtype=torch.float64, device=dev)
+    wd, bd, zd = t(w), t(bias), t(z)
+    call("e2e_gemm_f64d_cat", M, 4 * H, K1, K2, a1d, K1, a2d, K2, wd, 4 * H, pre, 4 * H, bd, zd, 4 * H if table else 0,
+         rd if table else None)
+    c_ref = torch.empty((M, H), dtype=torch.float64, device=dev)
+    h_ref = torch.empty((M, H), dtype=torch.float64, device=dev)
+    call("e2e_lstm_step_f64", M, H, pre, cd, c_ref, h_ref, H)
+    # interleaved columns: one launch
+    wp, bp, zp = t(w[:, perm]), t(bias[perm]), t(None if z is None else z[:, perm])
+    c_out = torch.full((M, H), float("nan"), dtype=torch.float64, device=dev)
+    h_out = torch.full((M, H + 3), float("nan"), dtype=torch.float64, device=dev)
+    call("e2e_gemm_f64d_lstm", M, H, K1, K2, a1d, K1, a2d, K2, wp, 4 * H, bp, zp, 4 * H if table else 0,
+         rd if table else None, cd, c_out, h_out, H + 3)
+    # the same sums and formulas (compiled twice: allow the last bit)
+    assert (c_out - c_ref).abs().max().item() <= 1e-15 and (h_out[:, :H] - h_ref).abs().max().item() <= 1e-15
+    g = a1 @ w[:K1] + bias.astype(np.float64)
+    if K2:
+        g = g + a2 @ w[K1:]
+    if table:
+        g = g + z[rows]
+    sig = lambda x: 1.0 / (1.0 + np.exp(-x))
+    c_np = c_prev * sig(g[:, 2 * H:3 * H] + 1.0) + sig(g[:, :H]) * np.tanh(g[:, H:2 * H])
+    h_np = sig(g[:, 3 * H:]) * np.tanh(c_np)
+    assert np.abs(c_out.cpu().numpy() - c_np).max() <= 1e-12 and np.abs(h_out[:, :H].cpu().numpy() - h_np).max() <= 1e-12
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("beam,A,D,scale", [(10, 128, 512, 1.0), (3, 40, 72, 1.0), (16, 160, 1024, 1.0),
+                                             (4, 128, 64, 40.0)])
+def test_beam_attention_from_exponentials(beam, A, D, scale):
+    """e2e_exp2x_f64 + e2e_attn_beam_group_e_f64 (tanh(h + y) = 1 - 2 / (exp(2h) exp(2y) + 1)) against the tanh kernel
+    and NumPy's calc_attention (beam_search.py:150-159); scale = 40 saturates most tanh arguments."""
+    import torch
+    from e2e_asr_b200._lib import call
+    rng = np.random.default_rng(beam * 1000 + A + D)
+    Ts = np.array([44, 1, 87, 50, 9, 200, 33], np.int32)
+    N, Tmax = len(Ts), int(Ts.max())
+    offs = np.concatenate([[0], np.cumsum(Ts)[:-1]]).astype(np.int32)
+    rows = int(Ts.sum())
+    HF = (rng.standard_normal((rows, A)) * scale).astype(np.float32)
+    enc = np.tanh(rng.standard_normal((rows, D))).astype(np.float32)
+    y = rng.standard_normal((N * beam, A)) * scale
+    v = rng.standard_normal(A).astype(np.float32)
+    dev = "cuda:0"
+    HFd, encd, yd, vd = (torch.from_numpy(x).to(dev) for x in (HF, enc, y, v))
+    ro = torch.from_numpy(np.repeat(offs, beam)).to(dev)
+    rt = torch.from_numpy(np.repeat(Ts, beam)).to(dev)
+    EHF = torch.empty((rows, A), dtype=torch.float64, device=dev)
+    call("e2e_exp2x_f64", rows * A, HFd, EHF)
+    np.testing.assert_allclose(EHF.cpu().numpy(), np.exp(np.clip(2.0 * HF.astype(np.float64), -300.0, 300.0)), rtol=4e-16)
+    c_tanh = torch.full((N * beam, D), float("nan"), dtype=torch.float64, device=dev)
+    c_exp = torch.full((N * beam, D), float("nan"), dtype=torch.float64, device=dev)
+    call("e2e_attn_beam_group_f64", N, beam, A, D, Tmax, HFd, encd, ro, rt, yd, vd, c_tanh, D)
+    call("e2e_attn_beam_group_e_f64", N, beam, A, D, Tmax, EHF, encd, ro, rt, yd, vd, c_exp, D)
+    ref = np.empty((N * beam, D))
+    for r in range(N * beam):
+        u = r // beam
+        sl = slice(offs[u], offs[u] + Ts[u])
+        s = np.tanh(HF[sl].astype(np.float64) + y[r]) @ v.astype(np.float64)
+        e = np.exp(s - s.max())
+        ref[r] = (e / e.sum()) @ enc[sl].astype(np.float64)
+    tol = 1e-12 if scale == 1.0 else 1e-10       # saturated scores: the softmax amplifies 1e-16 of a score of ~100
+    assert np.abs(c_exp.cpu().numpy() - ref).max() <= tol
+    assert np.abs(c_exp.cpu().numpy() - c_tanh.cpu().numpy()).max() <= tol
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("flags", [dict(fast_step=False), dict(token_table=False, fused_lstm=False),
+                                   dict(exp_attention=False, fused_lstm=False), dict(token_table=False)])
+def test_beam_step_formulations_give_the_same_ids(flags):
+    """The decoding step in its earlier formulations (materialised concatenations, embedding product every step, LSTM
+    as its own kernel, tanh attention): the same ids as the oracle, with and without LM fusion."""
+    from e2e_asr_b200.beam_search import BeamSearch
+    cfg = synth.get_config("cfg1")
+    w = gg.dec_weights(cfg, 21, 2.5, 10.0)
+    rng = np.random.Generator(np.random.PCG64(23))
+    encs = [(np.tanh(rng.standard_normal((int(rng.integers(50, 89)), 2 * cfg.H))) * 0.8).astype(np.float32)
+            for _ in range(5)]
+    for k, lmw in ((6, 0.0), (3, 0.3)):
+        sp = BeamSearch.class_params()
+        sp.beam_size, sp.lm_weight, sp.lm_path = k, lmw, w
+        bs = BeamSearch(w, sp, device="cuda:0")
+        for name, val in flags.items():
+            setattr(bs, name, val)
+        out = bs.decode_batch(encs)
+        for u, enc in enumerate(encs):
+            np.testing.assert_array_equal(out[u], ob.beam_search(w, enc, beam_size=k, lm_weight=lmw))
