@@ -7,6 +7,7 @@
 // and are batched over every live hypothesis of every utterance.
 #include "../../include/e2e_asr_b200.h"
 #include "common.cuh"
+#include <cstdlib>
 
 namespace e2e {
 
@@ -193,15 +194,19 @@ struct GemmF64Ext {
     double* h_out;
     int ldh, H;
 };
-// CTA = (2 WM) x 64 tile, 4 warps of WM x 32 (WM / 8 x 4 m8n8 tiles): WM = 32 for the large products, WM = 16 when
-// 64-row tiles would leave most SMs with one CTA or none (N <= 256 at 2560 rows: 160 CTAs on 148 SMs).
-template <int WM, int EPI>
+// CTA = (2 WM) x 64 tile, 4 warps of WM x 32 (WM / 8 x 4 m8n8 tiles), k-tiles of TPK, 2-stage cp.async pipeline.
+// ncu (profiles/r4_ncu_beam_summary.txt): with 64-row tiles and k-tiles of 16 the DMMA pipe is ~77 % busy while an SM
+// has work, but only ~70 % of the SMs' time is covered -- 640 CTAs against 592 resident slots leave a tail on 48 SMs.
+// 32-row tiles halve the tail; k-tiles of 32 give them the 64 DMMAs per barrier pair of the 64-row tile.  Row strides
+// TPK + 4 (A, [m][k]) and 68 (B, [k][n]) doubles: both fragment loads are bank-conflict free.
+template <int WM, int TPK, int EPI>
 __global__ void __launch_bounds__(128)
 gemm_f64_mma_kernel(int M, int N, int K, const double* __restrict__ A, int lda, const double* __restrict__ B, int ldb,
                     double* __restrict__ C, int ldc, const float* __restrict__ bias, GemmF64Ext x) {
-    constexpr int TM = 2 * WM, MI = WM / 8;
-    __shared__ __align__(16) double As[2][TM][PAS];
-    __shared__ __align__(16) double Bs[2][PK][BS2];
+    constexpr int TM = 2 * WM, MI = WM / 8, AS = TPK + 4;
+    extern __shared__ __align__(16) double smem_d[];
+    double* As = smem_d;                                  // [2][TM][AS]
+    double* Bs = smem_d + 2 * TM * AS;                    // [2][TPK][BS2]
     const int tid = threadIdx.x, lane = tid % 32, w = tid / 32, wm = w / 2, wn = w % 2;
     const int lr = lane / 4, lc = lane % 4;
     const int m0 = blockIdx.y * TM, n0 = blockIdx.x * PT;
@@ -210,17 +215,17 @@ gemm_f64_mma_kernel(int M, int N, int K, const double* __restrict__ A, int lda, 
         const double* Ab = second ? x.A2 : A;
         const int ld = second ? x.lda2 : lda, kk0 = second ? k0 - x.K1 : k0;
 #pragma unroll
-        for (int it = 0; it < TM / 16; ++it) {
-            const int i = it * 128 + tid, r = i / 8, c = (i % 8) * 2;
+        for (int it = 0; it < TM * TPK / 256; ++it) {
+            const int i = it * 128 + tid, r = i / (TPK / 2), c = (i % (TPK / 2)) * 2;
             const bool ok = m0 + r < M;
-            cp_async16(&As[stage][r][c], Ab + (size_t)(ok ? m0 + r : 0) * ld + kk0 + c, ok ? 16 : 0);
+            cp_async16(&As[(stage * TM + r) * AS + c], Ab + (size_t)(ok ? m0 + r : 0) * ld + kk0 + c, ok ? 16 : 0);
         }
 #pragma unroll
-        for (int it = 0; it < 4; ++it) {
+        for (int it = 0; it < TPK / 4; ++it) {
             const int i = it * 128 + tid, k = i / 32, c = (i % 32) * 2;
             const int rem = N - (n0 + c);
             const int bytes = rem >= 2 ? 16 : (rem > 0 ? 8 : 0);
-            cp_async16(&Bs[stage][k][c], B + (size_t)(k0 + k) * ldb + (rem > 0 ? n0 + c : 0), bytes);
+            cp_async16(&Bs[(stage * TPK + k) * BS2 + c], B + (size_t)(k0 + k) * ldb + (rem > 0 ? n0 + c : 0), bytes);
         }
         asm volatile("cp.async.commit_group;" ::: "memory");
     };
@@ -229,24 +234,25 @@ gemm_f64_mma_kernel(int M, int N, int K, const double* __restrict__ A, int lda, 
     for (int i = 0; i < MI; ++i)
 #pragma unroll
         for (int j = 0; j < 4; ++j) { acc[i][j][0] = 0.0; acc[i][j][1] = 0.0; }
-    const int nk = K / PK;
+    const int nk = K / TPK;
     issue(0, 0);
     for (int t = 0; t < nk; ++t) {
         if (t + 1 < nk) {
-            issue((t + 1) & 1, (t + 1) * PK);
+            issue((t + 1) & 1, (t + 1) * TPK);
             asm volatile("cp.async.wait_group 1;" ::: "memory");
         } else {
             asm volatile("cp.async.wait_group 0;" ::: "memory");
         }
         __syncthreads();
-        const int s = t & 1;
+        const double* as = As + (t & 1) * TM * AS + (WM * wm + lr) * AS + lc;
+        const double* bs = Bs + (t & 1) * TPK * BS2 + lc * BS2 + 32 * wn + lr;
 #pragma unroll
-        for (int kk = 0; kk < PK / 4; ++kk) {
+        for (int kk = 0; kk < TPK / 4; ++kk) {
             double a[MI], b[4];
 #pragma unroll
-            for (int i = 0; i < MI; ++i) a[i] = As[s][WM * wm + 8 * i + lr][4 * kk + lc];
+            for (int i = 0; i < MI; ++i) a[i] = as[8 * i * AS + 4 * kk];
 #pragma unroll
-            for (int j = 0; j < 4; ++j) b[j] = Bs[s][4 * kk + lc][32 * wn + 8 * j + lr];
+            for (int j = 0; j < 4; ++j) b[j] = bs[4 * kk * BS2 + 8 * j];
 #pragma unroll
             for (int i = 0; i < MI; ++i)
 #pragma unroll
@@ -295,21 +301,37 @@ gemm_f64_mma_kernel(int M, int N, int K, const double* __restrict__ A, int lda, 
     }
 }
 
+int g_f64_tile = -1;     // E2E_F64_TILE: 0 = automatic (default), 1 = k-tiles of 16 only (64- / 32-row tiles by CTA count)
+template <int WM, int TPK, int EPI>
+static int launch_f64_mma_t(cudaStream_t st, int M, int N, int K, const double* A, int lda, const double* B, int ldb,
+                            double* C, int ldc, const float* bias, const GemmF64Ext& x) {
+    constexpr int SMEM = (2 * (2 * WM) * (TPK + 4) + 2 * TPK * BS2) * (int)sizeof(double);
+    static bool attr_set = false;
+    if (!attr_set && SMEM > 48 * 1024) {
+        E2E_CHECK_CUDA(cudaFuncSetAttribute(gemm_f64_mma_kernel<WM, TPK, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
+        attr_set = true;
+    }
+    gemm_f64_mma_kernel<WM, TPK, EPI><<<dim3(cdiv(N, PT), cdiv(M, 2 * WM)), 128, SMEM, st>>>(M, N, K, A, lda, B, ldb, C, ldc,
+                                                                                         bias, x);
+    E2E_LAUNCH_CHECK();
+    return 0;
+}
 // the same product with the weights already widened to float64 (aligned operands only: K % 16 == 0, even lda / ldb)
 static int launch_f64_mma(cudaStream_t st, int M, int N, int K, const double* A, int lda, const double* B, int ldb,
                           double* C, int ldc, const float* bias, const GemmF64Ext& x, bool lstm) {
+    if (g_f64_tile < 0) g_f64_tile = getenv("E2E_F64_TILE") ? atoi(getenv("E2E_F64_TILE")) : 0;
+    if (g_f64_tile == 0 && K % 32 == 0 && x.K1 % 32 == 0) {
+        if (lstm) return launch_f64_mma_t<16, 32, 1>(st, M, N, K, A, lda, B, ldb, C, ldc, bias, x);
+        return launch_f64_mma_t<16, 32, 0>(st, M, N, K, A, lda, B, ldb, C, ldc, bias, x);
+    }
     // 64-row tiles unless they leave fewer than two CTAs per SM
     const bool small = (long long)cdiv(M, 64) * cdiv(N, PT) < 2 * 148;
-    const dim3 grid(cdiv(N, PT), cdiv(M, small ? 32 : 64));
     if (lstm) {
-        if (small) gemm_f64_mma_kernel<16, 1><<<grid, 128, 0, st>>>(M, N, K, A, lda, B, ldb, C, ldc, bias, x);
-        else gemm_f64_mma_kernel<32, 1><<<grid, 128, 0, st>>>(M, N, K, A, lda, B, ldb, C, ldc, bias, x);
-    } else {
-        if (small) gemm_f64_mma_kernel<16, 0><<<grid, 128, 0, st>>>(M, N, K, A, lda, B, ldb, C, ldc, bias, x);
-        else gemm_f64_mma_kernel<32, 0><<<grid, 128, 0, st>>>(M, N, K, A, lda, B, ldb, C, ldc, bias, x);
+        if (small) return launch_f64_mma_t<16, 16, 1>(st, M, N, K, A, lda, B, ldb, C, ldc, bias, x);
+        return launch_f64_mma_t<32, 16, 1>(st, M, N, K, A, lda, B, ldb, C, ldc, bias, x);
     }
-    E2E_LAUNCH_CHECK();
-    return 0;
+    if (small) return launch_f64_mma_t<16, 16, 0>(st, M, N, K, A, lda, B, ldb, C, ldc, bias, x);
+    return launch_f64_mma_t<32, 16, 0>(st, M, N, K, A, lda, B, ldb, C, ldc, bias, x);
 }
 int gemm_f64d(cudaStream_t st, int M, int N, int K, const double* A, int lda, const double* B, int ldb, double* C,
               int ldc, const float* bias) {
@@ -567,9 +589,22 @@ int exp2x_f64(cudaStream_t st, size_t n, const float* x, double* out) {
     E2E_LAUNCH_CHECK();
     return 0;
 }
+// 1 / x for a normal positive x: MUFU.RCP64H seed (rcp.approx.ftz.f64, ~2^-20) + two Newton steps -- within an ulp of
+// the quotient, without the range checks and the slow-path branch of the generic division (x = exp(.) exp(.) + 1 lies
+// in [1, 1e261] here), so the chains of neighbouring elements interleave.
+__device__ __forceinline__ double rcp_pos(double x) {
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+    double e = fma(-x, r, 1.0);
+    r = fma(r, e, r);
+    e = fma(-x, r, 1.0);
+    return fma(r, e, r);
+}
 // attn_beam_group_f64_kernel with EHF = exp2x(HF) in place of HF; scores summed in the same order, softmax and
-// read-out identical.
-__global__ void __launch_bounds__(256)
+// read-out identical.  16 warps per utterance (the evaluation is latency bound: dependent FP64 chains), the scores of
+// all hypotheses of a frame kept in registers so that their shuffle reductions overlap.
+constexpr int ATT_E_THREADS = 512;
+__global__ void __launch_bounds__(ATT_E_THREADS, 2)
 attn_beam_group_e_f64_kernel(int beam, int A, int D, int Tmax, const double* __restrict__ EHF,
                              const float* __restrict__ enc, const int* __restrict__ row_off,
                              const int* __restrict__ Tlen, const double* __restrict__ y, const float* __restrict__ v,
@@ -578,43 +613,62 @@ attn_beam_group_e_f64_kernel(int beam, int A, int D, int Tmax, const double* __r
     double* y_s = sm;                       // [beam][A]  exp(2 y)
     double* v_s = y_s + beam * A;           // [A]
     double* s_s = v_s + A;                  // [beam][Tmax]  scores, then exp, then alpha
-    const int u = blockIdx.x, tid = threadIdx.x, lane = tid % 32, warp = tid / 32, nw = 8;
+    const int u = blockIdx.x, tid = threadIdx.x, lane = tid % 32, warp = tid / 32, nwarps = ATT_E_THREADS / 32;
     const int r0 = u * beam;
     const int off = row_off[r0], T = Tlen[r0];
-    for (int i = tid; i < beam * A; i += 256) y_s[i] = exp2x(y[(size_t)(r0 + i / A) * A + i % A]);
-    for (int a = tid; a < A; a += 256) v_s[a] = (double)v[a];
+    for (int i = tid; i < beam * A; i += ATT_E_THREADS) y_s[i] = exp2x(y[(size_t)(r0 + i / A) * A + i % A]);
+    for (int a = tid; a < A; a += ATT_E_THREADS) v_s[a] = (double)v[a];
     __syncthreads();
-    for (int tau = warp; tau < T; tau += nw) {
+    // scores s[r][tau] = sum_a (1 - 2 / (EHF[tau][a] exp(2 y[r][a]) + 1)) v[a], a = lane, lane + 32, ... in that order
+    for (int tau = warp; tau < T; tau += nwarps) {
         const double* hrow = EHF + (size_t)(off + tau) * A;
-        double eh[4];                        // this lane's columns of the row (A <= 128: loaded once for all hypotheses)
+        double p[MAXB];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) eh[j] = lane + 32 * j < A ? __ldg(hrow + lane + 32 * j) : 0.0;
-        for (int r = 0; r < beam; ++r) {
-            double p = 0.0;
-            for (int a0 = lane; a0 < A; a0 += 128) {
-                double t[4];
+        for (int r = 0; r < MAXB; ++r) p[r] = 0.0;
+        for (int a0 = lane; a0 < A; a0 += 128) {
+            double eh[4], vv[4];
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const int a = a0 + 32 * j;
-                    const double e = a0 == lane ? eh[j] : (a < A ? __ldg(hrow + a) : 0.0);
-                    t[j] = a < A ? 1.0 - 2.0 / (e * y_s[r * A + a] + 1.0) : 0.0;
-                }
-#pragma unroll
-                for (int j = 0; j < 4; ++j)
-                    if (a0 + 32 * j < A) p = fma(t[j], v_s[a0 + 32 * j], p);
+            for (int j = 0; j < 4; ++j) {
+                const int a = a0 + 32 * j;
+                eh[j] = a < A ? __ldg(hrow + a) : 0.0;
+                vv[j] = a < A ? v_s[a] : 0.0;
             }
-            for (int o = 16; o > 0; o >>= 1) p += __shfl_xor_sync(0xffffffffu, p, o);
-            if (lane == 0) s_s[r * Tmax + tau] = p;
+#pragma unroll
+            for (int r = 0; r < MAXB; ++r) {
+                if (r < beam) {
+                    double t[4];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const int a = a0 + 32 * j;
+                        t[j] = a < A ? fma(-2.0, rcp_pos(fma(eh[j], y_s[r * A + a], 1.0)), 1.0) : 0.0;
+                    }
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)
+                        if (a0 + 32 * j < A) p[r] = fma(t[j], vv[j], p[r]);
+                }
+            }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+            for (int r = 0; r < MAXB; ++r)
+                if (r < beam) p[r] += __shfl_xor_sync(0xffffffffu, p[r], o);
+        if (lane == 0) {
+#pragma unroll
+            for (int r = 0; r < MAXB; ++r)
+                if (r < beam) s_s[r * Tmax + tau] = p[r];
         }
     }
     __syncthreads();
-    for (int r = warp; r < beam; r += nw) {
+    // softmax per hypothesis: one warp each; eight chunks of 32 positions, summed chunk by chunk like the per-row
+    // kernel's eight warps (T <= 256)
+    for (int r = warp; r < beam; r += nwarps) {
         double* sr = s_s + r * Tmax;
         double mx = -INFINITY;
         for (int tau = lane; tau < T; tau += 32) mx = fmax(mx, sr[tau]);
         for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
         double sum = 0.0;
-        for (int c = 0; c < nw; ++c) {
+        for (int c = 0; c < 8; ++c) {
             const int tau = 32 * c + lane;
             double e = 0.0;
             if (tau < T) { e = exp(sr[tau] - mx); sr[tau] = e; }
@@ -625,7 +679,8 @@ attn_beam_group_e_f64_kernel(int beam, int A, int D, int Tmax, const double* __r
         for (int tau = lane; tau < T; tau += 32) sr[tau] = sr[tau] / sum;
     }
     __syncthreads();
-    for (int d = tid; d < D; d += 256) {
+    // read-out ctx[r][d] = sum_tau alpha[r][tau] enc[tau][d]
+    for (int d = tid; d < D; d += ATT_E_THREADS) {
         double c[MAXB];
 #pragma unroll
         for (int r = 0; r < MAXB; ++r) c[r] = 0.0;
@@ -656,7 +711,7 @@ int attn_beam_group_e_f64(cudaStream_t st, int N, int beam, int A, int D, int Tm
                 "attn_beam_group_e_f64: beam <= %d, Tmax <= 256 required (beam=%d Tmax=%d)", MAXB, beam, Tmax);
     if (smem > 48 * 1024)
         E2E_CHECK_CUDA(cudaFuncSetAttribute(attn_beam_group_e_f64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attn_beam_group_e_f64_kernel<<<N, 256, smem, st>>>(beam, A, D, Tmax, EHF, enc, row_off, Tlen, y, v, ctx, ldctx);
+    attn_beam_group_e_f64_kernel<<<N, ATT_E_THREADS, smem, st>>>(beam, A, D, Tmax, EHF, enc, row_off, Tlen, y, v, ctx, ldctx);
     E2E_LAUNCH_CHECK();
     return 0;
 }
