@@ -792,10 +792,106 @@ logsoftmax_topk_f64_kernel(int V, const double* __restrict__ logits, const doubl
         __syncthreads();
     }
 }
+// The same row with its entries in registers (V <= 256 PER): the k selection rounds of the kernel above re-read the
+// combined scores from global memory and take two CTA barriers and a one-thread scan each; here a round is a register
+// scan, a warp shuffle tree and ONE barrier (the warp results alternate between two shared buffers, and every thread
+// scans the eight of them itself).  Sums, maxima and tie rules are those of the kernel above, so the output is
+// bit-identical.
+template <int PER>
+__global__ void __launch_bounds__(256)
+logsoftmax_topk_reg_kernel(int V, const double* __restrict__ logits, const double* __restrict__ lm_logits,
+                           double lm_weight, const int* __restrict__ krow, int kmax, int* __restrict__ out_idx,
+                           double* __restrict__ out_val) {
+    __shared__ double red[2][8];
+    __shared__ int redi[2][8];
+    const int r = blockIdx.x, tid = threadIdx.x, lane = tid % 32, warp = tid / 32, nw = 8;
+    auto block_max = [&](double v) {
+        for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+        if (lane == 0) red[0][warp] = v;
+        __syncthreads();
+        double m = red[0][0];
+        for (int w = 1; w < nw; ++w) m = fmax(m, red[0][w]);
+        __syncthreads();
+        return m;
+    };
+    auto block_sum = [&](double v) {
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if (lane == 0) red[0][warp] = v;
+        __syncthreads();
+        double s = 0.0;
+        for (int w = 0; w < nw; ++w) s += red[0][w];
+        __syncthreads();
+        return s;
+    };
+    auto log_softmax = [&](const double* x, double (&out)[PER]) {
+        double mx = -INFINITY;
+#pragma unroll
+        for (int i = 0; i < PER; ++i) {
+            const int v = tid + 256 * i;
+            out[i] = v < V ? x[v] : -INFINITY;
+            mx = fmax(mx, out[i]);
+        }
+        mx = block_max(mx);
+        double s = 0.0;
+#pragma unroll
+        for (int i = 0; i < PER; ++i)
+            if (tid + 256 * i < V) { out[i] = exp(out[i] - mx); s += out[i]; }       // kept: not evaluated twice
+        s = block_sum(s);
+#pragma unroll
+        for (int i = 0; i < PER; ++i)
+            if (tid + 256 * i < V) out[i] = log(out[i] / s);
+    };
+    double comb[PER];
+    log_softmax(logits + (size_t)r * V, comb);
+    if (lm_logits != nullptr) {
+        double lm[PER];
+        log_softmax(lm_logits + (size_t)r * V, lm);
+#pragma unroll
+        for (int i = 0; i < PER; ++i)
+            if (tid + 256 * i < V) comb[i] += lm_weight * lm[i];
+    }
+    const int k = krow[r];
+    for (int j = 0; j < kmax; ++j) {
+        if (j >= k) {
+            if (tid == 0) { out_idx[(size_t)r * kmax + j] = -1; out_val[(size_t)r * kmax + j] = -INFINITY; }
+            continue;
+        }
+        double best = -INFINITY;
+        int bi = 0x7fffffff;
+#pragma unroll
+        for (int i = 0; i < PER; ++i) {
+            const int v = tid + 256 * i;
+            if (v < V && (comb[i] > best || (comb[i] == best && v < bi))) { best = comb[i]; bi = v; }
+        }
+        for (int o = 16; o > 0; o >>= 1) {
+            const double ob = __shfl_xor_sync(0xffffffffu, best, o);
+            const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+            if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; }
+        }
+        if (lane == 0) { red[j & 1][warp] = best; redi[j & 1][warp] = bi; }
+        __syncthreads();
+        best = red[j & 1][0];
+        bi = redi[j & 1][0];
+        for (int w = 1; w < nw; ++w) {
+            const double ob = red[j & 1][w];
+            const int oi = redi[j & 1][w];
+            if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; }
+        }
+        if (tid == 0) { out_idx[(size_t)r * kmax + j] = bi; out_val[(size_t)r * kmax + j] = best; }
+#pragma unroll
+        for (int i = 0; i < PER; ++i)
+            if (tid + 256 * i == bi) comb[i] = -INFINITY;            // taken
+    }
+}
 int logsoftmax_topk_f64(cudaStream_t st, int n, int V, const double* logits, const double* lm_logits,
                         double lm_weight, const int* krow, int kmax, int* out_idx, double* out_val, double* scratch) {
     if (n <= 0) return 0;
-    logsoftmax_topk_f64_kernel<<<n, 256, 0, st>>>(V, logits, lm_logits, lm_weight, krow, kmax, out_idx, out_val, scratch);
+    if (V <= 256 * 4)
+        logsoftmax_topk_reg_kernel<4><<<n, 256, 0, st>>>(V, logits, lm_logits, lm_weight, krow, kmax, out_idx, out_val);
+    else if (V <= 256 * 8)
+        logsoftmax_topk_reg_kernel<8><<<n, 256, 0, st>>>(V, logits, lm_logits, lm_weight, krow, kmax, out_idx, out_val);
+    else
+        logsoftmax_topk_f64_kernel<<<n, 256, 0, st>>>(V, logits, lm_logits, lm_weight, krow, kmax, out_idx, out_val, scratch);
     E2E_LAUNCH_CHECK();
     return 0;
 }

@@ -396,3 +396,44 @@ def test_beam_step_formulations_give_the_same_ids(flags):
         out = bs.decode_batch(encs)
         for u, enc in enumerate(encs):
             np.testing.assert_array_equal(out[u], ob.beam_search(w, enc, beam_size=k, lm_weight=lmw))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("V,kmax,lm", [(17, 4, False), (1000, 10, False), (1000, 10, True), (1500, 7, True),
+                                        (2500, 5, False)])
+def test_logsoftmax_topk_f64(V, kmax, lm):
+    """get_top_k's tail (beam_search.py:196-214): log(softmax) (+ lm_weight * log(softmax_LM)), the k best per row in
+    descending order, ties to the lower index, k per row from krow (0 = dead row); register-resident kernel for
+    V <= 2048, the global-memory one beyond -- against NumPy, with repeated logits to force ties."""
+    import torch
+    from e2e_asr_b200._lib import call
+    rng = np.random.default_rng(V + kmax)
+    n = 37
+    x = np.round(rng.standard_normal((n, V)) * 3.0, 1)            # one decimal: many exact ties
+    xl = np.round(rng.standard_normal((n, V)) * 2.0, 1)
+    krow = rng.integers(0, kmax + 1, n).astype(np.int32)
+    krow[0] = kmax
+    dev = "cuda:0"
+    xd, xld, kd = torch.from_numpy(x).to(dev), torch.from_numpy(xl).to(dev), torch.from_numpy(krow).to(dev)
+    oi = torch.full((n, kmax), -7, dtype=torch.int32, device=dev)
+    ov = torch.full((n, kmax), float("nan"), dtype=torch.float64, device=dev)
+    scratch = torch.empty((n, V), dtype=torch.float64, device=dev)
+    call("e2e_logsoftmax_topk_f64", n, V, xd, xld if lm else None, 0.3, kd, kmax, oi, ov, scratch)
+
+    def logsm(a):
+        e = np.exp(a - a.max(axis=1, keepdims=True))
+        return np.log(e / e.sum(axis=1, keepdims=True))
+    comb = logsm(x) + (0.3 * logsm(xl) if lm else 0.0)
+    oi, ov = oi.cpu().numpy(), ov.cpu().numpy()
+    for r in range(n):
+        k = int(krow[r])
+        assert (oi[r, k:] == -1).all() and np.isneginf(ov[r, k:]).all()
+        got = oi[r, :k]
+        assert len(set(got.tolist())) == k
+        np.testing.assert_allclose(ov[r, :k], comb[r, got], rtol=0, atol=1e-12)
+        # descending values; equal device values in ascending index order; nothing left out that beats the k-th
+        for a, b in zip(range(k - 1), range(1, k)):
+            assert ov[r, a] > ov[r, b] or (ov[r, a] == ov[r, b] and got[a] < got[b])
+        if 0 < k < V:
+            rest = np.delete(comb[r], got)
+            assert rest.max() <= ov[r, k - 1] + 1e-12
