@@ -624,6 +624,12 @@ def main():
         os._exit(0)
 
 
+# FP64 ceilings of a B200 of this pool, measured with scratch/ubench_f64.cu (profiles/r4_ubench_f64.txt): mma.sync
+# m8n8k4.f64 issues every 16.1 cycles per SM sub-partition = 37.0 TFLOP/s at 1.965 GHz; dependent-free DFMA 33.3 TFLOP/s
+FP64_DMMA_PEAK_TFLOPS = 37.0
+FP64_PEAK_SOURCE = "measured: scratch/ubench_f64.cu, profiles/r4_ubench_f64.txt (DMMA m8n8k4 37.0 TF/s, DFMA 33.3 TF/s)"
+
+
 def beam_decode_rate(cfg_name, dev, n_utts=256, beam=10, cpu=True):
     """Second half of BASELINE.json's metric: beam-search decoding (BASELINE configs[2]: beam width 10, a synthetic
     eval batch of 256 utterances with T_enc in [50, 88]) in utterances/s through BeamSearch.decode_batch, next to the
@@ -659,10 +665,44 @@ def beam_decode_rate(cfg_name, dev, n_utts=256, beam=10, cpu=True):
            "fp64_gemm_tflops": flop_row * n_utts * beam * steps / dt / 1e12,
            "first_call_utt_s": n_utts / times[0], "capture_call_utt_s": n_utts / times[1],
            "note": "random-init weights: hypotheses run to the 120-step limit (worst case); wall clock of decode_batch: "
-                   "float64 decoder step on all 2560 hypothesis slots + device-side k^2 candidate merge, one CUDA-graph replay "
+                   "float64 decoder step on all 2560 hypothesis slots (products on the FP64 tensor cores with the concatenated "
+                   "operands taken in place, LM-LSTM input half from a token table, BasicLSTM in the product epilogue, attention "
+                   "from tabulated exponentials) + device-side k^2 candidate merge, one CUDA-graph replay "
                    "per decoding step (value = steady state with the step graph cached; first_call_utt_s = kernel by "
                    "kernel, capture_call_utt_s = the call that captures), the best sequence per utterance rebuilt from "
                    "back-pointers on the host at the end"}
+    # where a decode goes, kernel by kernel (one more eager decode with an event pair around every C-ABI call), and the
+    # FP64 products against the measured FP64 tensor-core ceiling of this pool's B200s
+    try:
+        from e2e_asr_b200 import _lib
+        prof = _lib.Profiler()
+        _lib.PROFILER = prof
+        try:
+            bs.decode_batch(encs, use_graph=False)
+            torch.cuda.synchronize()
+        finally:
+            _lib.PROFILER = None
+        summ = prof.summary()
+        kern = {k: {"ms_per_decode": v["ms"], "calls": v["calls"], "us_per_call": 1e3 * v["ms"] / max(v["calls"], 1)}
+                for k, v in sorted(summ.items(), key=lambda kv: -kv[1]["ms"])}
+        gemm_ms = sum(v["ms"] for k, v in summ.items() if k.startswith("e2e_gemm_f64"))
+        # executed: the embedding half of the LM-LSTM product comes from the per-model token table
+        flop_exec = flop_row - 2.0 * E * 4 * Hl
+        R = n_utts * beam
+        res["roofline"] = {
+            "kernel": "gemm_f64_mma_kernel (e2e_gemm_f64d_cat + e2e_gemm_f64d_lstm: the six float64 products of a decoding "
+                      "step on all %d hypothesis rows, BasicLSTM in the epilogue)" % R,
+            "bound": "tensor (FP64)", "unit": "TFLOP/s",
+            "achieved": flop_exec * R * steps / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else None,
+            "peak": FP64_DMMA_PEAK_TFLOPS, "peak_source": FP64_PEAK_SOURCE,
+            "frac": (flop_exec * R * steps / (gemm_ms * 1e-3) / 1e12 / FP64_DMMA_PEAK_TFLOPS) if gemm_ms > 0 else None,
+            "executed_gflop_per_step": flop_exec * R / 1e9, "algorithmic_gflop_per_step": flop_row * R / 1e9,
+            "share_of_kernel_time": gemm_ms / max(sum(v["ms"] for v in summ.values()), 1e-9),
+            "note": "event time of an eager decode; the LSTM pointwise math (5 float64 exp / tanh per unit) runs in the same "
+                    "kernels' epilogues and is not counted as FLOPs"}
+        res["kernels"] = kern
+    except Exception as e:          # noqa: BLE001  (a side measurement must not take the bench line down)
+        res["roofline"] = {"error": repr(e)}
     gold = os.path.join(ROOT, "tests", "golden", "fullsize_beam.npz")
     if os.path.exists(gold) and n_utts == 256 and beam == 10 and cfg_name == "cfg2":
         g = np.load(gold)
