@@ -3,9 +3,9 @@
 Same surface as the reference `BeamSearch` (beam_search.py:15-350):
 `BeamSearch(ckpt_path, search_params)(encoder_hidden_states[T_enc, D]) -> ids`
 (1-D int array, trailing EOS included, beam_search.py:338), same `class_params`.
-`ckpt_path` may be a dict of weights keyed by the TF variable names of
-beam_search.py:56-98, or the path of an .npz holding them (TF checkpoint I/O is
-out of scope).
+`ckpt_path` (and `search_params.lm_path`) may be a dict of weights keyed by the TF
+variable names of beam_search.py:56-98, a TF V2 checkpoint prefix (read by
+tf_checkpoint.py, no TensorFlow needed) or the path of an .npz holding them.
 
 Where the reference loops utterance x step x hypothesis in NumPy, here every
 hypothesis slot of every utterance is one row of a float64 batch on the device
@@ -13,8 +13,18 @@ hypothesis slot of every utterance is one row of a float64 batch on the device
 O(k^2) candidate merge per utterance -- `np.argpartition` over k*k scores,
 back-pointers `idx // k`, EOS bookkeeping (beam_search.py:294-329) -- is a device
 kernel too (`e2e_beam_merge`), so a decoding step is one CUDA-graph replay.
-`merge_candidates` below is the host restatement of that merge (NumPy, vectorised
-over utterances) the device kernel is tested against.
+
+The step's float64 products run on the FP64 tensor cores with the reference's
+concatenated operands read in place (`e2e_gemm_f64d_cat`), the embedding half of
+the LM-LSTM product from a per-model token table, `BasicLSTM.__call__` in the
+product's epilogue (`e2e_gemm_f64d_lstm`) and `tanh` of the attention scores from
+tabulated exponentials (`e2e_attn_beam_group_e_f64`): the same sums up to their
+order; ids are checked bit-exact against the reference's own
+outputs (tests/golden/beam_*.npz) and the oracle.
+
+`merge_candidates` below is the host restatement of the merge (NumPy, vectorised
+over utterances) the device kernel is tested against; `best_sequences` rebuilds
+the decoded ids from the device's back-pointer history.
 """
 import numpy as np
 import torch

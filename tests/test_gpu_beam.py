@@ -1,4 +1,4 @@
-"""GPU beam search (float64 batched decoder step + host candidate merge) against the
+"""GPU beam search (float64 batched decoder step + device-side candidate merge) against the
 golden ids produced by the reference's own beam_search.py (tests/golden/gen_golden.py)
 and against the CPU oracle on a larger synthetic eval batch.  Token ids must be
 bit-exact (north-star)."""
