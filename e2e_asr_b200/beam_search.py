@@ -487,8 +487,17 @@ class BeamSearch(BaseParams):
         evaluation loop over equally shaped batches); True captures at once, False always launches kernel by kernel."""
         sp, p, dev = self.search_params, self.dec_params, self.device
         beam = int(sp.beam_size)
+        # encoder states that already live on this device (an evaluation loop feeding the encoder's output) are
+        # gathered there; host arrays go through one pinned staging buffer
+        on_dev = len(enc_list) > 0 and all(
+            isinstance(e, torch.Tensor) and e.device.type == dev.type and (dev.index is None or e.device.index == dev.index)
+            for e in enc_list)
         encs = []
         for e in enc_list:
+            if on_dev:
+                e = e.detach()
+                encs.append((e[0] if e.dim() == 3 else e).to(torch.float32))
+                continue
             e = e.detach().cpu().numpy() if isinstance(e, torch.Tensor) else np.asarray(e)
             if e.ndim == 3:
                 e = np.squeeze(e, axis=0)
@@ -501,8 +510,11 @@ class BeamSearch(BaseParams):
         D = encs[0].shape[1]
         pl = self._plan(N, beam, (rows + 255) // 256 * 256, (int(Ts.max()) + 7) // 8 * 8, D)
         S = pl.S
-        np.concatenate(encs, axis=0, out=pl.enc_pin.numpy()[:rows])       # pinned staging: one DMA, no pageable bounce
-        pl.enc_all[:rows].copy_(pl.enc_pin[:rows], non_blocking=True)
+        if on_dev:
+            torch.cat(encs, dim=0, out=pl.enc_all[:rows])
+        else:
+            np.concatenate(encs, axis=0, out=pl.enc_pin.numpy()[:rows])   # pinned staging: one DMA, no pageable bounce
+            pl.enc_all[:rows].copy_(pl.enc_pin[:rows], non_blocking=True)
         ops.gemm(pl.enc_all, p.attn_enc_w, mode=0, out=pl.HF)             # float32 x float32 (beam_search.py:148)
         if pl.EHF is not None:
             call("e2e_exp2x_f64", pl.HF.numel(), pl.HF, pl.EHF)

@@ -250,3 +250,20 @@ def test_widths_the_tensor_core_step_cannot_tile_fall_back(emulated):
     assert not next(iter(bs._plans.values())).fast and "e2e_gemm_f64d_cat" not in emulated.names
     for u, enc in enumerate(encs):
         np.testing.assert_array_equal(out[u], ob.beam_search(w, enc, beam_size=3))
+
+
+def test_device_resident_encoder_states_are_gathered_in_place(emulated):
+    """Tensors that already live on the search's device skip the host staging; [1, T, D] inputs are accepted."""
+    cfg = synth.get_config("tiny", H=8, E=16, A=16, Hd=16, Hl=16)
+    w = gg.dec_weights(cfg, 21, 2.5, 10.0)
+    rng = np.random.Generator(np.random.PCG64(9))
+    encs = [(np.tanh(rng.standard_normal((6 + 2 * u, 2 * cfg.H))) * 0.8).astype(np.float32) for u in range(3)]
+    sp = bsm.BeamSearch.class_params()
+    sp.beam_size = 3
+    bs = bsm.BeamSearch(w, sp, device="cpu")
+    as_t = [torch.from_numpy(encs[0]), torch.from_numpy(encs[1])[None], torch.from_numpy(encs[2]).double()]
+    out_t = bs.decode_batch(as_t, use_graph=False)
+    out_n = bs.decode_batch(encs, use_graph=False)
+    for a, b, enc in zip(out_t, out_n, encs):
+        np.testing.assert_array_equal(a, b)
+        np.testing.assert_array_equal(a, ob.beam_search(w, enc, beam_size=3))

@@ -437,3 +437,25 @@ def test_logsoftmax_topk_f64(V, kmax, lm):
         if 0 < k < V:
             rest = np.delete(comb[r], got)
             assert rest.max() <= ov[r, k - 1] + 1e-12
+
+
+@pytest.mark.gpu
+def test_device_resident_encoder_states_give_the_same_ids():
+    """Encoder states passed as CUDA tensors (an evaluation loop feeding the encoder's output) are gathered on the
+    device; [1, T, D] accepted; same ids as from host arrays."""
+    import torch
+    from e2e_asr_b200.beam_search import BeamSearch
+    cfg = synth.get_config("cfg1")
+    w = gg.dec_weights(cfg, 21, 2.5, 10.0)
+    rng = np.random.Generator(np.random.PCG64(31))
+    encs = [(np.tanh(rng.standard_normal((int(rng.integers(50, 89)), 2 * cfg.H))) * 0.8).astype(np.float32)
+            for _ in range(4)]
+    sp = BeamSearch.class_params()
+    sp.beam_size = 4
+    bs = BeamSearch(w, sp, device="cuda:0")
+    host = bs.decode_batch(encs)
+    devt = [torch.from_numpy(e).cuda() for e in encs]
+    devt[1] = devt[1][None]
+    on_dev = bs.decode_batch(devt)
+    for a, b in zip(host, on_dev):
+        np.testing.assert_array_equal(a, b)
