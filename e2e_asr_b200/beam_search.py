@@ -141,6 +141,7 @@ class BeamSearch(BaseParams):
     """Implementation of beam search for the attention decoder."""
 
     MAX_STEPS = 120          # loop bound of beam_search.py:269
+    MAX_PLANS = 12           # batch signatures whose device buffers and captured step are kept (see _plan)
     # The decoding step (all float64, same sums up to their order -- ids are checked bit-exact against the oracle on
     # every golden): fast_step = products take their K-concatenated operands in place, merge output aliases the slot
     # state; token_table = emb[tok] . Wx + b of the LM-LSTM from a per-model table; fused_lstm = BasicLSTM in the
@@ -466,7 +467,9 @@ class BeamSearch(BaseParams):
             pl.keep = pl.keep + (bufs, lm_cell, dec_cell, lm2_cell)
 
         pl.step_fn = step_fn
-        while len(plans) >= 4:                                              # a few signatures; the oldest goes first
+        # an evaluation loop over 256-utterance batches sees a handful of signatures (row counts padded to 256, the
+        # longest utterance to 8): keep their buffers and step graphs (~150 MB each at cfg-3 sizes); the oldest goes first
+        while len(plans) >= self.MAX_PLANS:
             plans.pop(next(iter(plans)))
         plans[key] = pl
         return pl
